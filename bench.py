@@ -1,0 +1,340 @@
+#!/usr/bin/env python
+"""bench.py -- samples/sec of the RecBox embedding + FM hot path on B200 (BASELINE.json metric).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--ids uniform|zipf]
+
+A "step" is one pass of the hot path over one Criteo-shaped synthetic batch (configs[1]: DeepFM,
+26 categorical + 13 numeric fields, 26 x 38 462 rows = 1 000 012-row fused table, D = 16,
+B = 65 536 per GPU):
+    forward  : fused multi-slot gather + numeric Linear(1,D) + FM product_sum + LR  -> E, S, fm, lr
+    backward : zero the dense grad tables, then scatter-add dE + d_fm*(S-e) (and d_lr) into them,
+               plus the numeric-slot / bias batch reductions
+The dense MLP tail (a true GEMM) is outside the path: its input gradient dE
+is a device-resident stand-in.  `value` times the step with inputs resident in HBM; `e2e` times
+the same step fed from a pinned HOST float64 batch matrix (what the reference's DataLoader hands
+to train_step) through H2D + rbx_split_batch_f64, with the logits read back to the host.
+`--impl reference` times the CPU restatement of the reference (oracle/, torch CPU ops on all host
+cores) on the same step.  Under torchrun each rank runs an independent replica of the path on its
+own batch shard (weak scaling, no data-path collective; DESIGN.md "Multi-GPU").
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+CFG = dict(B=65536, F=26, Fn=13, D=16, V=38462)
+# algorithmic bytes per sample, fp32 rows / int32 ids
+def bytes_fwd(F, Fn, D): return F * (4 + 4 * D) + (F + Fn) * 4 * D + 4 * F + 4 * Fn + 4
+def bytes_bwd(F, Fn, D): return 4 * F + (F + Fn) * 4 * D + F * 4 * D + F * 8 * D + 8 * F + 4
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def make_ids(B, F, V, kind, seed):
+    rng = np.random.default_rng(seed)
+    if kind == "zipf":
+        ids = np.minimum(rng.zipf(1.05, size=(B, F)), V - 1)
+    else:
+        ids = rng.integers(1, V, size=(B, F))          # pad row 0 never sampled (SURVEY 8d cfg 2)
+    return ids.astype(np.int64)
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.stop_flag = index, [], False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                parts = [x.strip() for x in out.strip().split(",")]
+                if len(parts) >= 6:
+                    self.samples.append(parts)
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        sm = sorted(float(s[0]) for s in self.samples)
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(s[2 + i].lower().startswith("active") for s in self.samples)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.samples[0][1]), "reasons": reasons,
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+# reference arm / cpu_baseline: the oracle's restatement of the same step, on the host cores
+# ------------------------------------------------------------------------------------------------
+def cpu_step_factory(B, ids_kind, seed):
+    from collections import OrderedDict
+    from oracle import recbox_oracle as oracle     # checker / baseline only (never the product path)
+    F, Fn, D, V = CFG["F"], CFG["Fn"], CFG["D"], CFG["V"]
+    g = torch.Generator().manual_seed(seed)
+    feats, W, W1, X = OrderedDict(), OrderedDict(), OrderedDict(), OrderedDict()
+    ids = make_ids(B, F, V, ids_kind, seed)
+    for n in range(Fn):
+        name = "I%d" % (n + 1)
+        feats[name] = {"type": "numeric", "source": ""}
+        W[name] = (torch.randn(D, 1, generator=g) * 0.1).requires_grad_(True)
+        W1[name] = (torch.randn(1, 1, generator=g) * 0.1).requires_grad_(True)
+        X[name] = torch.rand(B, generator=g, dtype=torch.float64)
+    for f in range(F):
+        name = "C%d" % (f + 1)
+        feats[name] = {"type": "categorical", "source": "", "vocab_size": V, "padding_idx": 0}
+        W[name] = (torch.randn(V, D, generator=g) * 0.01).requires_grad_(True)
+        W1[name] = (torch.randn(V, 1, generator=g) * 0.01).requires_grad_(True)
+        X[name] = torch.from_numpy(ids[:, f].astype(np.float64))
+    bias = torch.zeros(1, requires_grad=True)
+    dE = torch.randn(B, F + Fn, D, generator=g) * 1e-3
+    d_out = torch.randn(B, 1, generator=g) * 1e-3
+    params = list(W.values()) + list(W1.values()) + [bias]
+
+    def step():
+        for p in params:
+            p.grad = None                                          # optimizer.zero_grad()
+        E = oracle.dict2tensor(oracle.embed_dict(X, feats, W))     # FeatureEmbedding
+        y = oracle.factorization_machine(X, E, feats, W1, bias)    # FactorizationMachine
+        torch.autograd.backward([E, y], [dE, d_out])               # dense embedding grads
+        return y
+    return step
+
+
+def run_cpu(steps, warmup, B, ids_kind):
+    torch.set_num_threads(os.cpu_count() or 1)
+    step = cpu_step_factory(B, ids_kind, 20242)
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = (time.perf_counter() - t0) / max(steps, 1)
+    return B / dt, dt
+
+
+def main_reference(args, rank, world):
+    if rank != 0:
+        return
+    B = CFG["B"]
+    steps, warmup = max(1, min(args.steps, 20)), max(1, min(args.warmup, 3))
+    sps, dt = run_cpu(steps, warmup, B, args.ids)
+    cores = torch.get_num_threads()
+    line = {
+        "impl": "reference", "metric": "samples/sec on Criteo-shaped synthetic (embedding + FM hot path, fwd+bwd)",
+        "value": sps, "unit": "samples/s", "n_gpus": args.gpus, "steps": steps, "warmup": warmup,
+        "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic", "config": workload_config(args.ids, 1),
+        "cpu_baseline": {"value": sps, "unit": "samples/s", "cores": cores, "kind": "port",
+                         "sample": "%d step(s) of the full B=%d batch through oracle/recbox_oracle.py (torch %s CPU ops)" % (steps, B, torch.__version__)},
+        "e2e": {"value": sps, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def workload_config(ids_kind, world):
+    return {"workload": "BASELINE configs[1] DeepFM hot path: 26 cat + 13 dense, 26x38462 = 1000012-row fused table, "
+                        "D=16, B=65536 per GPU; fused gather+FM+LR fwd, dense-grad zero + scatter-add bwd; MLP tail outside the path",
+            "global_batch": CFG["B"] * world, "ids": ids_kind, "batches_rotated": 4,
+            "l2": "working set per step (E 163 MB + dE 163 MB + table/grad 136 MB) exceeds the 126 MB L2; 4 id batches rotate",
+            "parallelism": "dp%d replicas, no data-path collective" % world}
+
+
+# ------------------------------------------------------------------------------------------------
+# B200 arm
+# ------------------------------------------------------------------------------------------------
+def main_b200(args, rank, world, local_rank):
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the B200 arm has no CPU path; use --impl reference for the CPU baseline)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    from recbox_b200 import ops
+    import torch.distributed as dist
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    B, F, Fn, D, V = CFG["B"], CFG["F"], CFG["Fn"], CFG["D"], CFG["V"]
+    Ft, R = F + Fn, F * V
+    g = torch.Generator().manual_seed(20240 + 2 + rank)
+    table = (torch.randn(R, D, generator=g) * 0.01).to(dev)
+    table_lr = (torch.randn(R, generator=g) * 0.01).to(dev)
+    dense_w = (torch.randn(Fn, D, generator=g) * 0.1).to(dev)
+    dense_w_lr = (torch.randn(Fn, generator=g) * 0.1).to(dev)
+    bias = torch.zeros(1, device=dev)
+    field_off = [f * V for f in range(F)]
+    cat_pos = list(range(Fn, Ft))            # Criteo order: I1..I13 then C1..C26
+    num_pos = list(range(Fn))
+    pad_row = field_off                      # padding_idx = 0 of every table
+    NB = 4
+    host_batches, rows_l, dense_l = [], [], []
+    col_kind = [2] * Fn + [1] * F + [3]
+    col_slot = list(range(Fn)) + list(range(F)) + [0]
+    for i in range(NB):
+        ids = make_ids(B, F, V, args.ids, 1000 * rank + i)
+        dx = torch.rand(B, Fn, generator=g, dtype=torch.float64)
+        lab = (torch.rand(B, 1, generator=g) < 0.5).double()
+        M = torch.cat([dx, torch.from_numpy(ids).double(), lab], 1).contiguous().pin_memory()
+        host_batches.append(M)
+        r, d, _ = ops.split_batch(M.to(dev), col_kind, col_slot, field_off, F, Fn)
+        rows_l.append(r)
+        dense_l.append(d)
+    dE = (torch.randn(B, Ft, D, generator=g) * 1e-3).to(dev)
+    d_fm = (torch.randn(B, generator=g) * 1e-3).to(dev)
+    d_lr = d_fm.clone()
+    g_table = torch.empty_like(table)
+    g_table_lr = torch.empty_like(table_lr)
+    g_dense_w = torch.empty_like(dense_w)
+    g_dense_w_lr = torch.empty_like(dense_w_lr)
+    g_bias = torch.empty_like(bias)
+    E = torch.empty(B, Ft, D, device=dev)
+
+    def fwd(rows, dx):
+        return ops.embed_fm_fwd(table, table_lr, rows, cat_pos, dx, dense_w, dense_w_lr, num_pos, bias)
+
+    def zero():
+        g_table.zero_(); g_table_lr.zero_(); g_dense_w.zero_(); g_dense_w_lr.zero_(); g_bias.zero_()
+
+    def bwd(rows, dx, E, S):
+        ops.embed_fm_bwd(table, rows, cat_pos, pad_row, dx, dense_w, num_pos, E, S, dE, d_fm, d_lr,
+                         g_table, g_table_lr, g_dense_w, g_dense_w_lr, g_bias, D, R)
+
+    def step(i, evs=None):
+        rows, dx = rows_l[i % NB], dense_l[i % NB]
+        if evs: evs[0].record()
+        E, S, fm, lr = fwd(rows, dx)
+        if evs: evs[1].record()
+        zero()
+        if evs: evs[2].record()
+        bwd(rows, dx, E, S)
+        if evs: evs[3].record()
+        return fm, lr
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    K, W = args.steps, max(args.warmup, 3)
+    for i in range(W):
+        step(i)
+    # ---- value: device-resident, CUDA events, max over ranks ----
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(K)]
+    t_beg, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    t_beg.record()
+    for i in range(K):
+        step(i, evs[i])
+    t_end.record()
+    barrier()
+    ms_total = t_beg.elapsed_time(t_end)
+    t_f = sum(e[0].elapsed_time(e[1]) for e in evs) / K
+    t_z = sum(e[1].elapsed_time(e[2]) for e in evs) / K
+    t_b = sum(e[2].elapsed_time(e[3]) for e in evs) / K
+
+    # ---- e2e: pinned host float64 batch -> H2D -> split -> step -> logits back to host ----
+    dev_batch = [torch.empty_like(host_batches[0], device=dev) for _ in range(2)]
+    out_host = torch.empty(B, dtype=torch.float32).pin_memory()
+
+    def e2e_step(i):
+        M = dev_batch[i % 2]
+        M.copy_(host_batches[i % NB], non_blocking=True)
+        rows, dx, lab = ops.split_batch(M, col_kind, col_slot, field_off, F, Fn)
+        E, S, fm, lr = fwd(rows, dx)
+        logit = fm + lr
+        out_host.copy_(logit, non_blocking=True)
+        zero()
+        bwd(rows, dx, E, S)
+    for i in range(W):
+        e2e_step(i)
+    e_beg, e_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e_beg.record()
+    for i in range(K):
+        e2e_step(i)
+    e_end.record()
+    barrier()
+    ms_e2e = e_beg.elapsed_time(e_end)
+    sampler.stop_flag = True
+    sampler.join(timeout=2)
+
+    times = torch.tensor([ms_total, ms_e2e, t_f, t_z, t_b], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(times, op=dist.ReduceOp.MAX)
+    ms_total, ms_e2e, t_f, t_z, t_b = times.tolist()
+
+    if rank == 0:
+        peak, peak_src = peaks()
+        bf, bb = bytes_fwd(F, Fn, D) * B, bytes_bwd(F, Fn, D) * B
+        kern = {"embed_fm_fwd": {"ms": t_f, "alg_bytes": bf, "gbs": bf / t_f / 1e6},
+                "grad_zero_fill(memset)": {"ms": t_z, "alg_bytes": (R * D + R) * 4, "gbs": (R * D + R) * 4 / t_z / 1e6},
+                "embed_fm_bwd(+dense_w_bwd)": {"ms": t_b, "alg_bytes": bb, "gbs": bb / t_b / 1e6}}
+        dom = "embed_fm_bwd(+dense_w_bwd)" if t_b >= t_f else "embed_fm_fwd"
+        ach = kern[dom]["gbs"]
+        line = {
+            "metric": "samples/sec on Criteo-shaped synthetic (embedding + FM hot path, fwd+bwd)",
+            "value": B * world * K / (ms_total * 1e-3), "unit": "samples/s", "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": workload_config(args.ids, world),
+            "e2e": {"value": B * world * K / (ms_e2e * 1e-3), "unit": "samples/s",
+                    "h2d_bytes_per_step": host_batches[0].numel() * 8, "d2h_bytes_per_step": B * 4,
+                    "ms_per_step": ms_e2e / K},
+            "gpu_launches": 3 * K,
+            "roofline": {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                         "traffic": None, "peak_source": peak_src,
+                         "pair_achieved": (bf + bb) / (t_f + t_b) / 1e6, "pair_frac": (bf + bb) / (t_f + t_b) / 1e6 / peak},
+            "kernels": kern,
+            "clocks": sampler.summary(),
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            sps, dt = run_cpu(3, 1, B, args.ids)
+            line["cpu_baseline"] = {"value": sps, "unit": "samples/s", "cores": torch.get_num_threads(), "kind": "port",
+                                    "sample": "3 steps of the full B=%d batch through oracle/recbox_oracle.py (%.0f ms/step)" % (B, dt * 1e3)}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--ids", default="uniform", choices=["uniform", "zipf"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        main_reference(args, rank, world)
+    else:
+        main_b200(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

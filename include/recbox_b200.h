@@ -1,0 +1,241 @@
+/*
+ * recbox_b200.h -- C ABI of librecbox_b200.so: the sm_100a (B200) implementation of RecBox's
+ * embedding + feature-interaction hot path.
+ *
+ * The reference (reczoo/RecBox) is pure Python; it has no FFI of its own.  The boundary this
+ * library replaces is the arithmetic its nn.Module layers hand to PyTorch ATen.  Every entry
+ * point below names the reference code (file:line under /root/reference/recbox) whose work it
+ * performs; INTEGRATION.md shows the ctypes binding a RecBox maintainer adds on their side.
+ *
+ * Conventions (all entry points):
+ *   - plain pointers and sizes only; no torch types.  Pointers marked DEVICE are device memory
+ *     of the current CUDA device, pointers marked HOST are small host arrays read during the
+ *     call (they are copied into the kernel's parameter space; nothing is retained).
+ *   - all device work is enqueued on `stream` (a cudaStream_t passed as void*); nothing
+ *     synchronises, nothing allocates, no library-owned threads.
+ *   - return 0 on success, <0 on error (RBX_ERR_*); rbx_last_error() returns the message of the
+ *     calling thread's last failure.
+ *   - fp32 rows, int32 global row ids.  "Global row" = id + row offset of the slot's table inside
+ *     the fused table (all per-feature nn.Embedding weights live back to back in one [R, D]
+ *     allocation, see DESIGN.md "Data layout").
+ *   - gradient outputs ACCUMULATE (+=); the caller zero-fills (this is what lets autograd's
+ *     zero_grad(set_to_none=False) semantics and multi-call accumulation work unchanged).
+ */
+#ifndef RECBOX_B200_H
+#define RECBOX_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RBX_OK               0
+#define RBX_ERR_ARG         -1   /* bad argument (null pointer, unsupported size ...) */
+#define RBX_ERR_CUDA        -2   /* a CUDA runtime call or launch failed */
+#define RBX_ERR_UNSUPPORTED -3   /* shape outside what the kernels cover */
+
+#define RBX_MAX_SLOTS      256   /* max categorical (resp. numeric) slots per call */
+#define RBX_MAX_DIM        512   /* max embedding dim */
+
+typedef void* rbx_stream_t;      /* cudaStream_t */
+
+int         rbx_version(void);            /* 10000*major + 100*minor + patch */
+const char* rbx_last_error(void);         /* thread-local, never NULL */
+int         rbx_device_sm_count(void);    /* SM count of the current device (<0 on error) */
+
+/* ------------------------------------------------------------------------------------------
+ * a1  batch matrix -> slot blocks
+ * Replaces RankingModel.get_inputs / get_labels (ranking/pytorch/models/ranking_model.py:106-122:
+ * one column slice + .to(device) per feature) and the per-feature casts `.long()` / `.float()`
+ * of FeatureEmbeddingDict.forward (ranking/pytorch/layers/embeddings/feature_embedding.py:201,204).
+ * One pass over the [B, n_cols] float64 batch (h5_dataloader.py:46 builds it with np.hstack):
+ *   col_kind[c] = 0 ignore | 1 categorical | 2 numeric | 3 label ; col_slot[c] = slot index.
+ *   rows[b, s]   = (int32)trunc(batch[b,c]) + field_off[s]      (kind 1)
+ *   dense_x[b,s] = (float)batch[b,c]                            (kind 2)
+ *   label[b]     = (float)batch[b,c]                            (kind 3)
+ * ------------------------------------------------------------------------------------------ */
+int rbx_split_batch_f64(const double* batch /*DEVICE [B, ld]*/, int64_t B, int n_cols, int64_t ld,
+                        const int8_t* col_kind /*HOST [n_cols]*/,
+                        const int16_t* col_slot /*HOST [n_cols]*/,
+                        const int64_t* field_off /*HOST [F]*/, int F, int Fn,
+                        int32_t* rows /*DEVICE [B,F] | NULL*/,
+                        float* dense_x /*DEVICE [B,Fn] | NULL*/,
+                        float* label /*DEVICE [B] | NULL*/,
+                        rbx_stream_t stream);
+
+/* Same conversion for the dict-of-columns form of X (feature_embedding.py:188-214 receives
+ * {feature: Tensor[B]}): up to RBX_MAX_SLOTS separate column pointers with element strides.
+ * dtype codes: 0 = float64, 1 = float32, 2 = int64, 3 = int32.  Writes out[b, s] for every
+ * column s as int32 (+ add[s]) when as_rows != 0, else as float32. */
+int rbx_pack_columns(const void* const* cols /*HOST [n] of DEVICE ptrs*/,
+                     const int64_t* strides /*HOST [n], in elements*/,
+                     const int8_t* dtypes /*HOST [n]*/,
+                     const int64_t* add /*HOST [n] | NULL*/,
+                     int n, int64_t B, int as_rows,
+                     void* out /*DEVICE [B, n] int32 or float32*/,
+                     rbx_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * a2+a3+a6+a7+a8  fused multi-slot gather + FM + LR, forward      (kernel K1/K2)
+ * One launch does what the reference spreads over
+ *   FeatureEmbeddingDict.forward + dict2tensor   feature_embedding.py:169-214 (26 x aten::embedding,
+ *                                                13 x Linear(1,D), torch.stack)
+ *   LogisticRegression.forward                   blocks/logistic_regression.py:30-35 (2nd, D=1 lookup)
+ *   InnerProductInteraction("product_sum")       interactions/inner_product.py:40-48
+ *   FactorizationMachine.forward                 blocks/factorization_machine.py:30-34
+ * For sample b, slot f (categorical) e = table[rows[b,f], :]; slot n (numeric)
+ * e = dense_x[b,n] * dense_w[n, :].  Ft = F + Fn, slot output positions cat_pos / num_pos.
+ *   E[b, pos, :] = e                                       (nullable)
+ *   S[b, :]      = sum over slots of e                      (nullable; saved for backward)
+ *   fm_out[b]    = sum_d 0.5 * (S_d^2 - sum_slots e_d^2)    (nullable)
+ *   lr_out[b]    = sum_f table_lr[rows[b,f]] + sum_n dense_x[b,n]*dense_w_lr[n] + lr_bias[0]
+ *                                                           (nullable; needs table_lr)
+ * R = rows in the fused table.  A row id outside [0, R) reads as a zero row and receives no
+ * gradient (the reference raises IndexError on CPU / device-asserts on CUDA; a library must not
+ * fault the device).
+ * ------------------------------------------------------------------------------------------ */
+int rbx_embed_fm_fwd(const float* table /*DEVICE [R,D]*/,
+                     const float* table_lr /*DEVICE [R] | NULL*/,
+                     const int32_t* rows /*DEVICE [B,F]*/,
+                     const int32_t* cat_pos /*HOST [F]*/,
+                     const float* dense_x /*DEVICE [B,Fn] | NULL*/,
+                     const float* dense_w /*DEVICE [Fn,D] | NULL*/,
+                     const float* dense_w_lr /*DEVICE [Fn] | NULL*/,
+                     const int32_t* num_pos /*HOST [Fn]*/,
+                     const float* lr_bias /*DEVICE [1] | NULL*/,
+                     float* E /*DEVICE [B,Ft,D] | NULL*/,
+                     float* S /*DEVICE [B,D] | NULL*/,
+                     float* fm_out /*DEVICE [B] | NULL*/,
+                     float* lr_out /*DEVICE [B] | NULL*/,
+                     int64_t B, int64_t R, int F, int Fn, int D, rbx_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * a5+a6+a7 backward: grad scatter-add                                (kernel K3)
+ * Replaces aten::embedding_dense_backward x52 and the Pow/Sum backward chain autograd builds
+ * for inner_product.py:42-48 (loss.backward(), ranking_model.py:194).
+ *   g_e[b,slot,:] = dE[b,pos,:] + d_fm[b] * (S[b,:] - e[b,slot,:])
+ *   g_table[rows[b,f], :] += g_e        unless rows[b,f] == pad_row[f]   (padding_idx: zero grad)
+ *   g_table_lr[rows[b,f]] += d_lr[b]    unless padding row
+ *   g_dense_w[n,:]  += sum_b dense_x[b,n] * g_e[b,n,:] ;  g_dense_w_lr[n] += sum_b dense_x[b,n]*d_lr[b]
+ *   g_lr_bias[0]    += sum_b d_lr[b]
+ * e is re-read from E (streaming) when E != NULL, else re-gathered from `table`.
+ * dE, d_fm, d_lr are each nullable (treated as zero); S is required when d_fm != NULL.
+ * Atomic (red.global.add) accumulation: order is not deterministic; see rbx_scatter_add_sorted
+ * for the deterministic path.
+ * ------------------------------------------------------------------------------------------ */
+int rbx_embed_fm_bwd(const float* table /*DEVICE [R,D] | NULL if E given*/,
+                     const int32_t* rows /*DEVICE [B,F]*/,
+                     const int32_t* cat_pos /*HOST [F]*/,
+                     const int32_t* pad_row /*HOST [F], -1 = none*/,
+                     const float* dense_x /*DEVICE [B,Fn] | NULL*/,
+                     const float* dense_w /*DEVICE [Fn,D] | NULL*/,
+                     const int32_t* num_pos /*HOST [Fn]*/,
+                     const float* E /*DEVICE [B,Ft,D] | NULL*/,
+                     const float* S /*DEVICE [B,D] | NULL*/,
+                     const float* dE /*DEVICE [B,Ft,D] | NULL*/,
+                     const float* d_fm /*DEVICE [B] | NULL*/,
+                     const float* d_lr /*DEVICE [B] | NULL*/,
+                     float* g_table /*DEVICE [R,D] | NULL*/,
+                     float* g_table_lr /*DEVICE [R] | NULL*/,
+                     float* g_dense_w /*DEVICE [Fn,D] | NULL*/,
+                     float* g_dense_w_lr /*DEVICE [Fn] | NULL*/,
+                     float* g_lr_bias /*DEVICE [1] | NULL*/,
+                     int64_t B, int64_t R, int F, int Fn, int D, rbx_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * a5  plain row gather / scatter-add (un-pooled sequence features, SASRec's three shared-table
+ * lookups third_party/rechub/models/matching/sasrec.py:99-100; aten::embedding and
+ * aten::embedding_dense_backward).  out[i,:] = table[ids[i],:]; g_table[ids[i],:] += g[i,:]
+ * unless ids[i] == pad_row.
+ * ------------------------------------------------------------------------------------------ */
+int rbx_gather_rows(const float* table /*DEVICE [R,D]*/, const int32_t* ids /*DEVICE [N]*/,
+                    float* out /*DEVICE [N,D]*/, int64_t N, int D, rbx_stream_t stream);
+int rbx_scatter_add_rows(const float* g /*DEVICE [N,D]*/, const int32_t* ids /*DEVICE [N]*/,
+                         int32_t pad_row, float* g_table /*DEVICE [R,D]*/,
+                         int64_t N, int D, rbx_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * a9  pooled sequence gather  (nn.Embedding on [B,L] ids followed by MaskedSumPooling /
+ * MaskedAveragePooling: core/pytorch/layers/sequence.py:4-20, ranking/pytorch/layers/pooling.py:22-40)
+ * without materialising [B,L,D].  mode 0 = sum, 1 = masked average: divide by
+ * (#positions l whose gathered row sums to non-zero) + 1e-12, the reference's own mask rule.
+ * ids has row stride ids_ld (a sequence feature is L consecutive columns of the [B, n] int32 slot
+ * block rbx_split_batch_f64 writes); out has row stride out_ld floats (so it can be a slot of E).  cnt[b] (nullable) receives the
+ * divisor's count for backward.
+ * Backward: g_table[ids[b,l],:] += g[b,:] * (mode ? 1/(cnt[b]+1e-12) : 1), padding rows skipped.
+ * ------------------------------------------------------------------------------------------ */
+int rbx_pooled_gather_fwd(const float* table, const int32_t* ids /*DEVICE [B, ids_ld]*/, int64_t ids_ld,
+                          float* out /*DEVICE [B, out_ld]*/, int64_t out_ld,
+                          float* cnt /*DEVICE [B] | NULL*/,
+                          int64_t B, int L, int D, int mode, rbx_stream_t stream);
+int rbx_pooled_gather_bwd(const float* g /*DEVICE [B, g_ld]*/, int64_t g_ld,
+                          const int32_t* ids, int64_t ids_ld, const float* cnt /*DEVICE [B] | NULL (mode 0)*/,
+                          int32_t pad_row, float* g_table,
+                          int64_t B, int L, int D, int mode, rbx_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * a10  two-tower scores  y[b,k] = <u[b,:], v[b,k,:]>   (layout fixed by
+ * matching/pytorch/models/match_model.py:71-75; rechub dssm.py:48 is K = 1)
+ * Backward: du[b,:] = sum_k dy[b,k] v[b,k,:] ; dv[b,k,:] = dy[b,k] u[b,:]   (overwrite, not +=)
+ * ------------------------------------------------------------------------------------------ */
+int rbx_rowdot_fwd(const float* u /*DEVICE [B,D]*/, const float* v /*DEVICE [B,K,D]*/,
+                   float* y /*DEVICE [B,K]*/, int64_t B, int K, int D, rbx_stream_t stream);
+int rbx_rowdot_bwd(const float* u, const float* v, const float* dy,
+                   float* du /*DEVICE [B,D] | NULL*/, float* dv /*DEVICE [B,K,D] | NULL*/,
+                   int64_t B, int K, int D, rbx_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * a6  InnerProductInteraction on a materialised E [B,F,D]  (interactions/inner_product.py:40-56)
+ * mode 0 product_sum -> [B] ; 1 bi_interaction -> [B,D] ; 2 inner_product -> [B,F(F-1)/2]
+ * (row-major upper triangle, i<j) ; 3 elementwise_product -> [B,F(F-1)/2,D].
+ * Backward writes dE (overwrite).
+ * ------------------------------------------------------------------------------------------ */
+int rbx_interact_fwd(const float* E, float* out, int64_t B, int F, int D, int mode,
+                     rbx_stream_t stream);
+int rbx_interact_bwd(const float* E, const float* dout, float* dE, int64_t B, int F, int D,
+                     int mode, rbx_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * (e)  row-shard routing around the all-to-all (no reference counterpart --
+ * the reference has no sharded embedding).  owner(r) = r % world, local row = r / world.
+ * rbx_shard_route  : STABLE bucket by owner.  send[pos[i]] = rows[i] / world with pos[i] = start of
+ *                    owner's bucket + rank of i among the ids of that owner in input order;
+ *                    counts[w] = size of bucket w.  Deterministic; equals a stable argsort by owner.
+ *                    ws = rbx_shard_ws_bytes(N, world) bytes of scratch.
+ * rbx_shard_permute: out[pos[i],:] = in[i,:]     (payload into send order: grads going to owners)
+ * rbx_shard_unroute: out[i,:] = recv[pos[i],:]   (rows coming back in send order)
+ * ------------------------------------------------------------------------------------------ */
+size_t rbx_shard_ws_bytes(int64_t N, int world);
+int rbx_shard_route(const int32_t* rows /*DEVICE [N]*/, int64_t N, int world,
+                    void* ws /*DEVICE*/, size_t ws_bytes,
+                    int32_t* send /*DEVICE [N]*/, int32_t* pos /*DEVICE [N]*/,
+                    int32_t* counts /*DEVICE [world]*/, rbx_stream_t stream);
+int rbx_shard_permute(const float* in /*DEVICE [N,D]*/, const int32_t* pos /*DEVICE [N]*/,
+                      float* out /*DEVICE [N,D]*/, int64_t N, int D, rbx_stream_t stream);
+int rbx_shard_unroute(const float* recv /*DEVICE [N,D]*/, const int32_t* pos /*DEVICE [N]*/,
+                      float* out /*DEVICE [N,D]*/, int64_t N, int D, rbx_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * a12  clip + optimizer on the fused table  (RankingModel.train_step ranking_model.py:191-197:
+ * clip_grad_norm_(all params, max_norm) then torch.optim.Adam.step, dense over every row)
+ * rbx_sqnorm     : out[0] += sum g[i]^2    (float64 accumulator, the global-norm partial)
+ * rbx_clip_coef  : coef[0] = min(1, max_norm / (sqrt(sqnorm[0]) + 1e-6)); norm_out[0] = sqrt(sqnorm[0])
+ * rbx_adam_dense : torch.optim.Adam single-tensor update in its operation order, with the
+ *                  clip coefficient read from DEVICE memory (no host sync):
+ *                  g' = g * clip[0];  m = lerp(m, g', 1-b1);  v = b2 v + (1-b2) g'^2;
+ *                  w -= (lr/bc1) * m / (sqrt(v)/sqrt(bc2) + eps)
+ * ------------------------------------------------------------------------------------------ */
+int rbx_sqnorm(const float* g, int64_t n, double* out /*DEVICE [1]*/, rbx_stream_t stream);
+int rbx_clip_coef(const double* sqnorm /*DEVICE [1]*/, float max_norm, float* coef /*DEVICE [1]*/,
+                  float* norm_out /*DEVICE [1] | NULL*/, rbx_stream_t stream);
+int rbx_adam_dense(float* w, const float* g, float* m, float* v, int64_t n,
+                   const float* clip /*DEVICE [1] | NULL*/,
+                   float lr, float beta1, float beta2, float eps, int step,
+                   rbx_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RECBOX_B200_H */

@@ -1,0 +1,122 @@
+"""Loader (and in-tree builder) for librecbox_b200.so, the C-ABI CUDA library of include/recbox_b200.h.
+
+The product path has NO fallback: if the shared library is missing or a call fails, the caller gets
+an exception (`RbxError`).  Nothing here imports `oracle/`.
+"""
+import ctypes
+import glob
+import os
+import shutil
+import subprocess
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(_HERE, "csrc")
+LIB_PATH = os.path.join(_HERE, "librecbox_b200.so")
+HEADER = os.path.join(os.path.dirname(_HERE), "include", "recbox_b200.h")
+
+NVCC_FLAGS = [
+    "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
+    "-Xptxas=-v",
+    "-Xcompiler", "-fPIC", "-shared",
+]
+
+
+class RbxError(RuntimeError):
+    pass
+
+
+def _nvcc():
+    for cand in (os.environ.get("NVCC"), shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if cand and os.path.exists(cand):
+            return cand
+    raise RbxError("nvcc not found; cannot build librecbox_b200.so")
+
+
+def sources():
+    return sorted(glob.glob(os.path.join(CSRC, "*.cu")))
+
+
+def needs_build():
+    if not os.path.exists(LIB_PATH):
+        return True
+    t = os.path.getmtime(LIB_PATH)
+    deps = sources() + glob.glob(os.path.join(CSRC, "*.cuh")) + [HEADER]
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def build(force=False, verbose=False):
+    """Compile every csrc/*.cu for sm_100a into recbox_b200/librecbox_b200.so (in-tree, so the
+    built library travels with the repo snapshot).  nvcc cross-compiles without a GPU."""
+    if not force and not needs_build():
+        return LIB_PATH
+    tmp = LIB_PATH + ".tmp.%d" % os.getpid()
+    cmd = [_nvcc()] + [f for f in NVCC_FLAGS if f] + ["-o", tmp] + sources()
+    proc = subprocess.run(cmd, capture_output=True, text=True)
+    if proc.returncode != 0:
+        raise RbxError("nvcc failed:\n%s\n%s" % (" ".join(cmd), proc.stderr[-8000:]))
+    os.replace(tmp, LIB_PATH)
+    if verbose:
+        print(proc.stderr)
+    return LIB_PATH
+
+
+_lib = None
+
+_c = ctypes
+_P = _c.c_void_p
+_I64 = _c.c_int64
+_I = _c.c_int
+_F = _c.c_float
+
+# name -> argtypes, in the order of include/recbox_b200.h
+SIGNATURES = {
+    "rbx_version": [],
+    "rbx_last_error": [],
+    "rbx_device_sm_count": [],
+    "rbx_split_batch_f64": [_P, _I64, _I, _I64, _P, _P, _P, _I, _I, _P, _P, _P, _P],
+    "rbx_pack_columns": [_P, _P, _P, _P, _I, _I64, _I, _P, _P],
+    "rbx_embed_fm_fwd": [_P] * 13 + [_I64, _I64, _I, _I, _I, _P],
+    "rbx_embed_fm_bwd": [_P] * 17 + [_I64, _I64, _I, _I, _I, _P],
+    "rbx_gather_rows": [_P, _P, _P, _I64, _I, _P],
+    "rbx_scatter_add_rows": [_P, _P, _c.c_int32, _P, _I64, _I, _P],
+    "rbx_pooled_gather_fwd": [_P, _P, _I64, _P, _I64, _P, _I64, _I, _I, _I, _P],
+    "rbx_pooled_gather_bwd": [_P, _I64, _P, _I64, _P, _c.c_int32, _P, _I64, _I, _I, _I, _P],
+    "rbx_rowdot_fwd": [_P, _P, _P, _I64, _I, _I, _P],
+    "rbx_rowdot_bwd": [_P, _P, _P, _P, _P, _I64, _I, _I, _P],
+    "rbx_interact_fwd": [_P, _P, _I64, _I, _I, _I, _P],
+    "rbx_interact_bwd": [_P, _P, _P, _I64, _I, _I, _I, _P],
+    "rbx_shard_ws_bytes": [_I64, _I],
+    "rbx_shard_route": [_P, _I64, _I, _P, _c.c_size_t, _P, _P, _P, _P],
+    "rbx_shard_permute": [_P, _P, _P, _I64, _I, _P],
+    "rbx_shard_unroute": [_P, _P, _P, _I64, _I, _P],
+    "rbx_sqnorm": [_P, _I64, _P, _P],
+    "rbx_clip_coef": [_P, _F, _P, _P, _P],
+    "rbx_adam_dense": [_P, _P, _P, _P, _I64, _P, _F, _F, _F, _F, _I, _P],
+}
+
+
+def load():
+    """dlopen the library (building it first if sources are newer).  Raises RbxError if it cannot."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if needs_build():
+        build()
+    try:
+        lib = ctypes.CDLL(LIB_PATH)
+    except OSError as e:  # pragma: no cover
+        raise RbxError("cannot load %s: %s" % (LIB_PATH, e))
+    for name, argtypes in SIGNATURES.items():
+        fn = getattr(lib, name, None)
+        if fn is None:
+            raise RbxError("%s does not export %s (stale build?)" % (LIB_PATH, name))
+        fn.argtypes = argtypes
+        fn.restype = {"rbx_last_error": ctypes.c_char_p, "rbx_shard_ws_bytes": ctypes.c_size_t}.get(name, ctypes.c_int)
+    _lib = lib
+    return lib
+
+
+def check(rc, lib=None):
+    if rc != 0:
+        lib = lib or load()
+        raise RbxError("librecbox_b200 error %d: %s" % (rc, lib.rbx_last_error().decode()))

@@ -1,0 +1,323 @@
+// a5 / a9: plain row gather, scatter-add, and the pooled sequence gather (sum / masked average)
+// that never materialises [B, L, D].  Same lane mapping as embed_fm.cu: LPR = D/4 lanes per row
+// on the vector path; a generic lane-strided path covers every other D <= RBX_MAX_DIM.
+#include "rbx_common.cuh"
+
+namespace {
+
+constexpr int kThreads = 256;
+
+inline int capped_grid(int64_t warps_needed, int ctas_per_sm) {
+    int64_t ctas = (warps_needed + kThreads / 32 - 1) / (kThreads / 32);
+    const int64_t cap = (int64_t)rbx_sm_count() * ctas_per_sm;
+    if (ctas > cap) ctas = cap;
+    return ctas < 1 ? 1 : (int)ctas;
+}
+
+inline bool vec_ok(int D, const void* a, const void* b, const void* c) {
+    return D % 4 == 0 && D <= 128 && (D & (D - 1)) == 0 && (uintptr_t)a % 16 == 0 && (uintptr_t)b % 16 == 0 &&
+           (uintptr_t)c % 16 == 0;
+}
+
+// ----------------------------------------------------------------------------------------- gather
+template <int LPR, int U>
+__global__ void __launch_bounds__(kThreads) k_gather_vec(const float* __restrict__ table, const int32_t* __restrict__ ids,
+                                                        float* __restrict__ out, int64_t N) {
+    constexpr int D = 4 * LPR, RPW = 32 / LPR;
+    const int lane = threadIdx.x & 31, lig = lane & (LPR - 1), gi = lane / LPR;
+    const int64_t warp0 = (int64_t)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
+    const int64_t nwarps = (int64_t)gridDim.x * (kThreads / 32);
+    for (int64_t base = warp0 * (RPW * U); base < N; base += nwarps * (RPW * U)) {
+        int32_t r[U];
+        float4 v[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int64_t i = base + u * RPW + gi;
+            r[u] = i < N ? __ldg(ids + i) : -1;
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+            if (r[u] >= 0) v[u] = ld_row_f4(table + (size_t)r[u] * D + 4 * lig);
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int64_t i = base + u * RPW + gi;
+            if (r[u] >= 0) st_stream_f4(out + (size_t)i * D + 4 * lig, v[u]);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kThreads) k_gather_any(const float* __restrict__ table, const int32_t* __restrict__ ids,
+                                                        float* __restrict__ out, int64_t N, int D) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp0 = (int64_t)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
+    const int64_t nwarps = (int64_t)gridDim.x * (kThreads / 32);
+    for (int64_t i = warp0; i < N; i += nwarps) {
+        const int32_t r = __ldg(ids + i);
+        for (int d = lane; d < D; d += 32) out[(size_t)i * D + d] = r >= 0 ? __ldg(table + (size_t)r * D + d) : 0.f;
+    }
+}
+
+// ------------------------------------------------------------------------------------ scatter-add
+template <int LPR, int U>
+__global__ void __launch_bounds__(kThreads) k_scatter_vec(const float* __restrict__ g, const int32_t* __restrict__ ids,
+                                                         int32_t pad_row, float* __restrict__ gt, int64_t N) {
+    constexpr int D = 4 * LPR, RPW = 32 / LPR;
+    const int lane = threadIdx.x & 31, lig = lane & (LPR - 1), gi = lane / LPR;
+    const int64_t warp0 = (int64_t)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
+    const int64_t nwarps = (int64_t)gridDim.x * (kThreads / 32);
+    for (int64_t base = warp0 * (RPW * U); base < N; base += nwarps * (RPW * U)) {
+        int32_t r[U];
+        float4 v[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int64_t i = base + u * RPW + gi;
+            r[u] = i < N ? __ldg(ids + i) : -1;
+            if (r[u] == pad_row) r[u] = -1;
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int64_t i = base + u * RPW + gi;
+            if (r[u] >= 0) v[u] = ld_stream_f4(g + (size_t)i * D + 4 * lig);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+            if (r[u] >= 0) red_add_f4(gt + (size_t)r[u] * D + 4 * lig, v[u]);
+    }
+}
+
+__global__ void __launch_bounds__(kThreads) k_scatter_any(const float* __restrict__ g, const int32_t* __restrict__ ids,
+                                                         int32_t pad_row, float* __restrict__ gt, int64_t N, int D) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp0 = (int64_t)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
+    const int64_t nwarps = (int64_t)gridDim.x * (kThreads / 32);
+    for (int64_t i = warp0; i < N; i += nwarps) {
+        const int32_t r = __ldg(ids + i);
+        if (r < 0 || r == pad_row) continue;
+        for (int d = lane; d < D; d += 32) red_add_f1(gt + (size_t)r * D + d, g[(size_t)i * D + d]);
+    }
+}
+
+// ---------------------------------------------------------------------------------- pooled gather
+// group (LPR lanes) per sample; L ids walked U at a time.  mode 1 divides by the number of
+// positions whose gathered row has a non-zero element sum (sequence.py:10 / pooling.py:29).
+template <int LPR, int U>
+__global__ void __launch_bounds__(kThreads) k_pooled_fwd_vec(const float* __restrict__ table, const int32_t* __restrict__ ids,
+                                                            int64_t ids_ld, float* __restrict__ out, int64_t out_ld,
+                                                            float* __restrict__ cnt, int64_t B, int L, int mode) {
+    constexpr int D = 4 * LPR, SPW = 32 / LPR;
+    const int lane = threadIdx.x & 31, lig = lane & (LPR - 1), gi = lane / LPR;
+    const int64_t warp0 = (int64_t)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
+    const int64_t nwarps = (int64_t)gridDim.x * (kThreads / 32);
+    for (int64_t base = warp0 * SPW; base < B; base += nwarps * SPW) {
+        const int64_t b = base + gi;
+        const bool valid = b < B;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        float n_nonzero = 0.f;
+        for (int l0 = 0; l0 < L; l0 += U) {
+            int32_t r[U];
+            float4 v[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) r[u] = (valid && l0 + u < L) ? __ldg(ids + b * ids_ld + l0 + u) : -1;
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (r[u] >= 0) v[u] = ld_row_f4(table + (size_t)r[u] * D + 4 * lig);
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                acc = f4_add(acc, v[u]);
+                if (mode == 1) {
+                    const float rs = group_sum<LPR>((v[u].x + v[u].y) + (v[u].z + v[u].w));
+                    n_nonzero += (rs != 0.f) ? 1.f : 0.f;
+                }
+            }
+        }
+        if (valid) {
+            float4 o = acc;
+            if (mode == 1) {
+                const float den = n_nonzero + 1e-12f;
+                o = make_float4(acc.x / den, acc.y / den, acc.z / den, acc.w / den);
+            }
+            *reinterpret_cast<float4*>(out + (size_t)b * out_ld + 4 * lig) = o;
+            if (cnt && lig == 0) cnt[b] = n_nonzero;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kThreads) k_pooled_fwd_any(const float* __restrict__ table, const int32_t* __restrict__ ids,
+                                                            int64_t ids_ld, float* __restrict__ out, int64_t out_ld,
+                                                            float* __restrict__ cnt, int64_t B, int L, int D, int mode) {
+    constexpr int KD = RBX_MAX_DIM / 32;
+    const int lane = threadIdx.x & 31;
+    const int64_t warp0 = (int64_t)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
+    const int64_t nwarps = (int64_t)gridDim.x * (kThreads / 32);
+    for (int64_t b = warp0; b < B; b += nwarps) {
+        float acc[KD];
+#pragma unroll
+        for (int k = 0; k < KD; ++k) acc[k] = 0.f;
+        float n_nonzero = 0.f;
+        for (int l = 0; l < L; ++l) {
+            const int32_t r = __ldg(ids + b * ids_ld + l);
+            float rs = 0.f;
+#pragma unroll
+            for (int k = 0; k < KD; ++k) {
+                const int d = lane + 32 * k;
+                if (d < D && r >= 0) {
+                    const float e = __ldg(table + (size_t)r * D + d);
+                    acc[k] += e;
+                    rs += e;
+                }
+            }
+            if (mode == 1) {
+                rs = group_sum<32>(rs);
+                n_nonzero += (rs != 0.f) ? 1.f : 0.f;
+            }
+        }
+        const float den = n_nonzero + 1e-12f;
+#pragma unroll
+        for (int k = 0; k < KD; ++k) {
+            const int d = lane + 32 * k;
+            if (d < D) out[(size_t)b * out_ld + d] = mode == 1 ? acc[k] / den : acc[k];
+        }
+        if (cnt && lane == 0) cnt[b] = n_nonzero;
+    }
+}
+
+template <int LPR, int U>
+__global__ void __launch_bounds__(kThreads) k_pooled_bwd_vec(const float* __restrict__ g, int64_t g_ld,
+                                                            const int32_t* __restrict__ ids, int64_t ids_ld,
+                                                            const float* __restrict__ cnt, int32_t pad_row,
+                                                            float* __restrict__ gt, int64_t B, int L, int mode) {
+    constexpr int D = 4 * LPR, SPW = 32 / LPR;
+    const int lane = threadIdx.x & 31, lig = lane & (LPR - 1), gi = lane / LPR;
+    const int64_t warp0 = (int64_t)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
+    const int64_t nwarps = (int64_t)gridDim.x * (kThreads / 32);
+    for (int64_t base = warp0 * SPW; base < B; base += nwarps * SPW) {
+        const int64_t b = base + gi;
+        if (b >= B) continue;
+        float4 gv = ld_stream_f4(g + (size_t)b * g_ld + 4 * lig);
+        if (mode == 1) {
+            const float den = __ldg(cnt + b) + 1e-12f;
+            gv = make_float4(gv.x / den, gv.y / den, gv.z / den, gv.w / den);
+        }
+        for (int l0 = 0; l0 < L; l0 += U) {
+            int32_t r[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                r[u] = (l0 + u < L) ? __ldg(ids + b * ids_ld + l0 + u) : -1;
+                if (r[u] == pad_row) r[u] = -1;
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+                if (r[u] >= 0) red_add_f4(gt + (size_t)r[u] * D + 4 * lig, gv);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kThreads) k_pooled_bwd_any(const float* __restrict__ g, int64_t g_ld,
+                                                            const int32_t* __restrict__ ids, int64_t ids_ld,
+                                                            const float* __restrict__ cnt, int32_t pad_row,
+                                                            float* __restrict__ gt, int64_t B, int L, int D, int mode) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp0 = (int64_t)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
+    const int64_t nwarps = (int64_t)gridDim.x * (kThreads / 32);
+    for (int64_t b = warp0; b < B; b += nwarps) {
+        const float den = mode == 1 ? __ldg(cnt + b) + 1e-12f : 1.f;
+        for (int l = 0; l < L; ++l) {
+            const int32_t r = __ldg(ids + b * ids_ld + l);
+            if (r < 0 || r == pad_row) continue;
+            for (int d = lane; d < D; d += 32) {
+                const float x = g[(size_t)b * g_ld + d];
+                red_add_f1(gt + (size_t)r * D + d, mode == 1 ? x / den : x);
+            }
+        }
+    }
+}
+
+}  // namespace
+
+#define RBX_DISPATCH_LPR(D, CALL)                   \
+    switch ((D) / 4) {                              \
+        case 1: { constexpr int LPR = 1; CALL; } break;   \
+        case 2: { constexpr int LPR = 2; CALL; } break;   \
+        case 4: { constexpr int LPR = 4; CALL; } break;   \
+        case 8: { constexpr int LPR = 8; CALL; } break;   \
+        case 16: { constexpr int LPR = 16; CALL; } break; \
+        default: { constexpr int LPR = 32; CALL; } break; \
+    }
+
+extern "C" {
+
+int rbx_gather_rows(const float* table, const int32_t* ids, float* out, int64_t N, int D, rbx_stream_t stream) {
+    const char* who = "rbx_gather_rows";
+    RBX_REQUIRE(N >= 0 && D >= 1 && D <= RBX_MAX_DIM, "%s: bad size", who);
+    if (N == 0) return RBX_OK;
+    RBX_REQUIRE(table && ids && out, "%s: null pointer", who);
+    cudaStream_t st = rbx_cast_stream(stream);
+    if (vec_ok(D, table, out, nullptr)) {
+        RBX_DISPATCH_LPR(D, (k_gather_vec<LPR, 4><<<capped_grid((N + (32 / LPR) * 4 - 1) / ((32 / LPR) * 4), 8), kThreads, 0, st>>>(
+                                table, ids, out, N)));
+    } else {
+        k_gather_any<<<capped_grid(N, 8), kThreads, 0, st>>>(table, ids, out, N, D);
+    }
+    RBX_LAUNCH_CHECK(who);
+    return RBX_OK;
+}
+
+int rbx_scatter_add_rows(const float* g, const int32_t* ids, int32_t pad_row, float* g_table, int64_t N, int D,
+                         rbx_stream_t stream) {
+    const char* who = "rbx_scatter_add_rows";
+    RBX_REQUIRE(N >= 0 && D >= 1 && D <= RBX_MAX_DIM, "%s: bad size", who);
+    if (N == 0) return RBX_OK;
+    RBX_REQUIRE(g && ids && g_table, "%s: null pointer", who);
+    cudaStream_t st = rbx_cast_stream(stream);
+    if (vec_ok(D, g, g_table, nullptr)) {
+        RBX_DISPATCH_LPR(D, (k_scatter_vec<LPR, 4><<<capped_grid((N + (32 / LPR) * 4 - 1) / ((32 / LPR) * 4), 8), kThreads, 0, st>>>(
+                                g, ids, pad_row, g_table, N)));
+    } else {
+        k_scatter_any<<<capped_grid(N, 8), kThreads, 0, st>>>(g, ids, pad_row, g_table, N, D);
+    }
+    RBX_LAUNCH_CHECK(who);
+    return RBX_OK;
+}
+
+int rbx_pooled_gather_fwd(const float* table, const int32_t* ids, int64_t ids_ld, float* out, int64_t out_ld,
+                          float* cnt, int64_t B, int L, int D, int mode, rbx_stream_t stream) {
+    const char* who = "rbx_pooled_gather_fwd";
+    RBX_REQUIRE(B >= 0 && L >= 0 && D >= 1 && D <= RBX_MAX_DIM, "%s: bad size", who);
+    RBX_REQUIRE(mode == 0 || mode == 1, "%s: mode %d", who, mode);
+    RBX_REQUIRE(ids_ld >= L && out_ld >= D, "%s: leading dimension too small", who);
+    if (B == 0) return RBX_OK;
+    RBX_REQUIRE(table && ids && out, "%s: null pointer", who);
+    cudaStream_t st = rbx_cast_stream(stream);
+    if (vec_ok(D, table, out, nullptr) && out_ld % 4 == 0) {
+        RBX_DISPATCH_LPR(D, (k_pooled_fwd_vec<LPR, 8><<<capped_grid((B + 32 / LPR - 1) / (32 / LPR), 4), kThreads, 0, st>>>(
+                                table, ids, ids_ld, out, out_ld, cnt, B, L, mode)));
+    } else {
+        k_pooled_fwd_any<<<capped_grid(B, 4), kThreads, 0, st>>>(table, ids, ids_ld, out, out_ld, cnt, B, L, D, mode);
+    }
+    RBX_LAUNCH_CHECK(who);
+    return RBX_OK;
+}
+
+int rbx_pooled_gather_bwd(const float* g, int64_t g_ld, const int32_t* ids, int64_t ids_ld, const float* cnt,
+                          int32_t pad_row, float* g_table, int64_t B, int L, int D, int mode, rbx_stream_t stream) {
+    const char* who = "rbx_pooled_gather_bwd";
+    RBX_REQUIRE(B >= 0 && L >= 0 && D >= 1 && D <= RBX_MAX_DIM, "%s: bad size", who);
+    RBX_REQUIRE(mode == 0 || mode == 1, "%s: mode %d", who, mode);
+    RBX_REQUIRE(mode == 0 || cnt, "%s: cnt (saved by the forward) required for masked average", who);
+    RBX_REQUIRE(ids_ld >= L && g_ld >= D, "%s: leading dimension too small", who);
+    if (B == 0 || L == 0) return RBX_OK;
+    RBX_REQUIRE(g && ids && g_table, "%s: null pointer", who);
+    cudaStream_t st = rbx_cast_stream(stream);
+    if (vec_ok(D, g, g_table, nullptr) && g_ld % 4 == 0) {
+        RBX_DISPATCH_LPR(D, (k_pooled_bwd_vec<LPR, 8><<<capped_grid((B + 32 / LPR - 1) / (32 / LPR), 4), kThreads, 0, st>>>(
+                                g, g_ld, ids, ids_ld, cnt, pad_row, g_table, B, L, mode)));
+    } else {
+        k_pooled_bwd_any<<<capped_grid(B, 4), kThreads, 0, st>>>(g, g_ld, ids, ids_ld, cnt, pad_row, g_table, B, L, D, mode);
+    }
+    RBX_LAUNCH_CHECK(who);
+    return RBX_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,163 @@
+// a1: batch matrix / dict-of-columns -> dense slot blocks ([B,F] int32 global rows, [B,Fn] fp32,
+// [B] fp32 label).  One coalesced pass; replaces 39 column slices + 39 H2D copies + 26 .long()
+// casts per batch (ranking_model.py:106-122, feature_embedding.py:201,204).
+#include "rbx_common.cuh"
+
+namespace {
+
+constexpr int kMaxCols = 512;
+
+struct SplitParams {
+    const double* batch;
+    int32_t* rows;
+    float* dense_x;
+    float* label;
+    int64_t B, ld;
+    int n_cols, F, Fn;
+    int32_t col_add[kMaxCols];   // field offset of the column's slot (kind 1)
+    int16_t col_slot[kMaxCols];
+    int8_t col_kind[kMaxCols];
+};
+
+// thread <-> (b, c), c fastest: a warp reads 32 consecutive doubles of one row (256 B contiguous)
+__global__ void __launch_bounds__(256) k_split_batch(const __grid_constant__ SplitParams p) {
+    const int64_t total = p.B * p.n_cols;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t b = i / p.n_cols;
+        const int c = (int)(i - b * p.n_cols);
+        const int kind = p.col_kind[c];
+        if (kind == 0) continue;
+        const double v = __ldg(p.batch + b * p.ld + c);
+        const int s = p.col_slot[c];
+        if (kind == 1) {
+            p.rows[b * p.F + s] = (int32_t)(int64_t)v + p.col_add[c];   // .long(): truncation toward zero
+        } else if (kind == 2) {
+            p.dense_x[b * p.Fn + s] = (float)v;                         // .float(): round to nearest
+        } else {
+            p.label[b] = (float)v;
+        }
+    }
+}
+
+constexpr int kPackCols = 64;
+struct PackParams {
+    const void* col[kPackCols];
+    int64_t stride[kPackCols];
+    int64_t add[kPackCols];
+    int8_t dtype[kPackCols];
+    void* out;
+    int64_t B;
+    int n_total, c0, n_here, as_rows;
+};
+
+__device__ __forceinline__ double load_any(const void* p, int64_t i, int dtype) {
+    switch (dtype) {
+        case 0: return reinterpret_cast<const double*>(p)[i];
+        case 1: return (double)reinterpret_cast<const float*>(p)[i];
+        case 2: return (double)reinterpret_cast<const int64_t*>(p)[i];
+        default: return (double)reinterpret_cast<const int32_t*>(p)[i];
+    }
+}
+
+// 32 samples x n_here columns per CTA, transposed through shared memory so both the column reads
+// (along b) and the block writes (along the slot axis) are coalesced.
+__global__ void __launch_bounds__(256) k_pack_columns(const __grid_constant__ PackParams p) {
+    __shared__ int32_t tile[32][kPackCols + 1];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    for (int64_t b0 = (int64_t)blockIdx.x * 32; b0 < p.B; b0 += (int64_t)gridDim.x * 32) {
+        const int64_t b = b0 + tx;
+        for (int c = ty; c < p.n_here; c += 8) {
+            int32_t bits = 0;
+            if (b < p.B) {
+                const int dt = p.dtype[c];
+                if (p.as_rows) {
+                    int64_t id;
+                    if (dt == 2) id = reinterpret_cast<const int64_t*>(p.col[c])[b * p.stride[c]];
+                    else if (dt == 3) id = reinterpret_cast<const int32_t*>(p.col[c])[b * p.stride[c]];
+                    else id = (int64_t)load_any(p.col[c], b * p.stride[c], dt);
+                    bits = (int32_t)(id + p.add[c]);
+                } else {
+                    bits = __float_as_int((float)load_any(p.col[c], b * p.stride[c], dt));
+                }
+            }
+            tile[tx][c] = bits;
+        }
+        __syncthreads();
+        for (int r = ty; r < 32; r += 8) {
+            const int64_t bb = b0 + r;
+            if (bb < p.B)
+                for (int c = tx; c < p.n_here; c += 32)
+                    reinterpret_cast<int32_t*>(p.out)[bb * p.n_total + p.c0 + c] = tile[r][c];
+        }
+        __syncthreads();
+    }
+}
+
+}  // namespace
+
+extern "C" {
+
+int rbx_split_batch_f64(const double* batch, int64_t B, int n_cols, int64_t ld, const int8_t* col_kind,
+                        const int16_t* col_slot, const int64_t* field_off, int F, int Fn, int32_t* rows,
+                        float* dense_x, float* label, rbx_stream_t stream) {
+    const char* who = "rbx_split_batch_f64";
+    RBX_REQUIRE(B >= 0 && n_cols >= 0 && ld >= n_cols, "%s: bad shape", who);
+    RBX_REQUIRE(n_cols <= kMaxCols, "%s: n_cols=%d > %d", who, n_cols, kMaxCols);
+    if (B == 0 || n_cols == 0) return RBX_OK;
+    RBX_REQUIRE(batch && col_kind && col_slot, "%s: null pointer", who);
+    SplitParams p;
+    p.batch = batch; p.rows = rows; p.dense_x = dense_x; p.label = label; p.B = B; p.ld = ld;
+    p.n_cols = n_cols; p.F = F; p.Fn = Fn;
+    for (int c = 0; c < n_cols; ++c) {
+        const int k = col_kind[c], s = col_slot[c];
+        RBX_REQUIRE(k >= 0 && k <= 3, "%s: col_kind[%d]=%d", who, c, k);
+        if (k == 1) {
+            RBX_REQUIRE(rows && s >= 0 && s < F, "%s: column %d -> categorical slot %d of %d", who, c, s, F);
+            const int64_t off = field_off ? field_off[s] : 0;
+            RBX_REQUIRE(off >= 0 && off <= INT32_MAX, "%s: field_off[%d] outside int32", who, s);
+            p.col_add[c] = (int32_t)off;
+        } else {
+            p.col_add[c] = 0;
+        }
+        if (k == 2) RBX_REQUIRE(dense_x && s >= 0 && s < Fn, "%s: column %d -> numeric slot %d of %d", who, c, s, Fn);
+        if (k == 3) RBX_REQUIRE(label != nullptr, "%s: label column without label output", who);
+        p.col_kind[c] = (int8_t)k;
+        p.col_slot[c] = (int16_t)s;
+    }
+    const int64_t total = B * n_cols;
+    int64_t ctas = (total + 255) / 256;
+    const int64_t cap = (int64_t)rbx_sm_count() * 8;
+    if (ctas > cap) ctas = cap;
+    k_split_batch<<<(int)ctas, 256, 0, rbx_cast_stream(stream)>>>(p);
+    RBX_LAUNCH_CHECK(who);
+    return RBX_OK;
+}
+
+int rbx_pack_columns(const void* const* cols, const int64_t* strides, const int8_t* dtypes, const int64_t* add,
+                     int n, int64_t B, int as_rows, void* out, rbx_stream_t stream) {
+    const char* who = "rbx_pack_columns";
+    RBX_REQUIRE(n >= 0 && B >= 0, "%s: negative size", who);
+    if (n == 0 || B == 0) return RBX_OK;
+    RBX_REQUIRE(cols && strides && dtypes && out, "%s: null pointer", who);
+    for (int c0 = 0; c0 < n; c0 += kPackCols) {
+        PackParams p;
+        p.out = out; p.B = B; p.n_total = n; p.c0 = c0; p.as_rows = as_rows;
+        p.n_here = (n - c0 < kPackCols) ? n - c0 : kPackCols;
+        for (int c = 0; c < p.n_here; ++c) {
+            RBX_REQUIRE(cols[c0 + c] != nullptr, "%s: column %d is null", who, c0 + c);
+            RBX_REQUIRE(dtypes[c0 + c] >= 0 && dtypes[c0 + c] <= 3, "%s: dtype code %d", who, dtypes[c0 + c]);
+            p.col[c] = cols[c0 + c];
+            p.stride[c] = strides[c0 + c];
+            p.dtype[c] = dtypes[c0 + c];
+            p.add[c] = add ? add[c0 + c] : 0;
+        }
+        int64_t ctas = (B + 31) / 32;
+        const int64_t cap = (int64_t)rbx_sm_count() * 8;
+        if (ctas > cap) ctas = cap;
+        k_pack_columns<<<(int)ctas, 256, 0, rbx_cast_stream(stream)>>>(p);
+        RBX_LAUNCH_CHECK(who);
+    }
+    return RBX_OK;
+}
+
+}  // extern "C"

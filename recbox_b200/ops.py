@@ -1,0 +1,250 @@
+"""Thin tensor-level wrappers over the C ABI (include/recbox_b200.h).
+
+torch is plumbing here: it owns device memory and the current stream; every op below is ONE call
+into librecbox_b200.so with raw pointers.  There is no fallback of any kind: a non-CUDA tensor or a
+missing library raises.
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+from ._lib import RbxError
+
+MODES = {"product_sum": 0, "bi_interaction": 1, "inner_product": 2, "elementwise_product": 3}
+_DTYPE_CODE = {torch.float64: 0, torch.float32: 1, torch.int64: 2, torch.int32: 3}
+
+
+def _p(t, dtype=None, name="tensor"):
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise RbxError("%s must be a CUDA tensor (recbox_b200 has no CPU path)" % name)
+    if not t.is_contiguous():
+        raise RbxError("%s must be contiguous" % name)
+    if dtype is not None and t.dtype != dtype:
+        raise RbxError("%s must be %s, got %s" % (name, dtype, t.dtype))
+    return ctypes.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _i32(xs):
+    xs = list(xs)
+    return (ctypes.c_int32 * max(len(xs), 1))(*xs)
+
+
+def _call(name, *args):
+    lib = _lib.load()
+    rc = getattr(lib, name)(*args)
+    if rc != 0:
+        raise RbxError("%s failed (%d): %s" % (name, rc, lib.rbx_last_error().decode()))
+
+
+F32, I32 = torch.float32, torch.int32
+
+
+# ------------------------------------------------------------------------------------------- a1
+def split_batch(batch, col_kind, col_slot, field_off, F, Fn, want_label=True):
+    """[B, n_cols] float64 device matrix -> (rows int32 [B,F], dense_x fp32 [B,Fn], label fp32 [B])."""
+    if batch.dim() != 2 or batch.dtype != torch.float64 or not batch.is_cuda or batch.stride(1) != 1:
+        raise RbxError("split_batch: batch must be a CUDA float64 matrix with unit column stride")
+    B, n_cols = batch.shape
+    dev = batch.device
+    rows = torch.empty((B, F), dtype=I32, device=dev) if F else None
+    dense = torch.empty((B, Fn), dtype=F32, device=dev) if Fn else None
+    label = torch.empty((B,), dtype=F32, device=dev) if want_label and 3 in col_kind else None
+    kinds = (ctypes.c_int8 * max(n_cols, 1))(*col_kind)
+    slots = (ctypes.c_int16 * max(n_cols, 1))(*col_slot)
+    offs = (ctypes.c_int64 * max(F, 1))(*field_off)
+    _call("rbx_split_batch_f64", ctypes.c_void_p(batch.data_ptr()), B, n_cols, batch.stride(0), kinds, slots, offs,
+          F, Fn, _p(rows), _p(dense), _p(label), _stream())
+    return rows, dense, label
+
+
+def pack_columns(cols, add=None, as_rows=True):
+    """list of [B] device tensors (any of f64/f32/i64/i32, any stride) -> [B, n] int32 (+add) or fp32."""
+    n = len(cols)
+    B = cols[0].shape[0]
+    dev = cols[0].device
+    for c in cols:
+        if not c.is_cuda or c.dim() != 1 or c.shape[0] != B or c.dtype not in _DTYPE_CODE:
+            raise RbxError("pack_columns: every column must be a 1-D CUDA tensor of f64/f32/i64/i32 and equal length")
+    out = torch.empty((B, n), dtype=I32 if as_rows else F32, device=dev)
+    ptrs = (ctypes.c_void_p * n)(*[c.data_ptr() for c in cols])
+    strides = (ctypes.c_int64 * n)(*[c.stride(0) if B > 1 else 1 for c in cols])
+    dts = (ctypes.c_int8 * n)(*[_DTYPE_CODE[c.dtype] for c in cols])
+    adds = (ctypes.c_int64 * n)(*(add if add is not None else [0] * n))
+    _call("rbx_pack_columns", ptrs, strides, dts, adds, n, B, 1 if as_rows else 0, _p(out), _stream())
+    return out
+
+
+# ---------------------------------------------------------------------------------- K1 / K2 / K3
+def embed_fm_fwd(table, table_lr, rows, cat_pos, dense_x, dense_w, dense_w_lr, num_pos, lr_bias,
+                 want_E=True, want_S=True, want_fm=True, want_lr=True, B=None):
+    """Fused gather + FM + LR forward.  Returns (E, S, fm_out, lr_out); unrequested ones are None."""
+    F = len(cat_pos)
+    Fn = len(num_pos)
+    ref = table if table is not None else dense_w
+    D = ref.shape[-1]
+    dev = ref.device
+    if B is None:
+        B = rows.shape[0] if rows is not None else dense_x.shape[0]
+    R = table.shape[0] if table is not None else 0
+    Ft = F + Fn
+    E = torch.empty((B, Ft, D), dtype=F32, device=dev) if want_E else None
+    S = torch.empty((B, D), dtype=F32, device=dev) if want_S else None
+    fm = torch.empty((B,), dtype=F32, device=dev) if want_fm else None
+    lr = torch.empty((B,), dtype=F32, device=dev) if want_lr else None
+    _call("rbx_embed_fm_fwd", _p(table, F32, "table"), _p(table_lr, F32, "table_lr"), _p(rows, I32, "rows"),
+          _i32(cat_pos), _p(dense_x, F32, "dense_x"), _p(dense_w, F32, "dense_w"),
+          _p(dense_w_lr, F32, "dense_w_lr"), _i32(num_pos), _p(lr_bias, F32, "lr_bias"),
+          _p(E), _p(S), _p(fm), _p(lr), B, R, F, Fn, D, _stream())
+    return E, S, fm, lr
+
+
+def embed_fm_bwd(table, rows, cat_pos, pad_row, dense_x, dense_w, num_pos, E, S, dE, d_fm, d_lr,
+                 g_table, g_table_lr, g_dense_w, g_dense_w_lr, g_lr_bias, D, R, B=None):
+    """Gradient scatter-add (accumulates into the g_* tensors, which the caller zero-fills)."""
+    F = len(cat_pos)
+    Fn = len(num_pos)
+    if B is None:
+        B = rows.shape[0] if rows is not None else dense_x.shape[0]
+    _call("rbx_embed_fm_bwd", _p(table, F32, "table"), _p(rows, I32, "rows"), _i32(cat_pos),
+          _i32(pad_row if pad_row is not None else [-1] * F), _p(dense_x, F32, "dense_x"),
+          _p(dense_w, F32, "dense_w"), _i32(num_pos), _p(E, F32, "E"), _p(S, F32, "S"), _p(dE, F32, "dE"),
+          _p(d_fm, F32, "d_fm"), _p(d_lr, F32, "d_lr"), _p(g_table, F32, "g_table"),
+          _p(g_table_lr, F32, "g_table_lr"), _p(g_dense_w, F32, "g_dense_w"),
+          _p(g_dense_w_lr, F32, "g_dense_w_lr"), _p(g_lr_bias, F32, "g_lr_bias"), B, R, F, Fn, D, _stream())
+
+
+# ------------------------------------------------------------------------------------- a5 / a9
+def gather_rows(table, ids):
+    N = ids.numel()
+    D = table.shape[1]
+    out = torch.empty(tuple(ids.shape) + (D,), dtype=F32, device=table.device)
+    _call("rbx_gather_rows", _p(table, F32, "table"), _p(ids, I32, "ids"), _p(out), N, D, _stream())
+    return out
+
+
+def scatter_add_rows(g, ids, pad_row, g_table):
+    N = ids.numel()
+    D = g_table.shape[1]
+    _call("rbx_scatter_add_rows", _p(g, F32, "g"), _p(ids, I32, "ids"), -1 if pad_row is None else int(pad_row),
+          _p(g_table, F32, "g_table"), N, D, _stream())
+
+
+def pooled_gather_fwd(table, ids, mode, out=None, want_cnt=None):
+    """ids int32 [B, L] (row stride may exceed L) -> (out [B,D], cnt [B] | None)."""
+    if ids.dim() != 2 or ids.dtype != I32 or not ids.is_cuda or ids.stride(1) != 1:
+        raise RbxError("pooled_gather_fwd: ids must be a CUDA int32 matrix with unit column stride")
+    B, L = ids.shape
+    D = table.shape[1]
+    if out is None:
+        out = torch.empty((B, D), dtype=F32, device=table.device)
+    if out.stride(-1) != 1:
+        raise RbxError("pooled_gather_fwd: out must have unit inner stride")
+    want_cnt = (mode == 1) if want_cnt is None else want_cnt
+    cnt = torch.empty((B,), dtype=F32, device=table.device) if want_cnt else None
+    _call("rbx_pooled_gather_fwd", _p(table, F32, "table"), ctypes.c_void_p(ids.data_ptr()), ids.stride(0),
+          ctypes.c_void_p(out.data_ptr()), out.stride(0), _p(cnt), B, L, D, mode, _stream())
+    return out, cnt
+
+
+def pooled_gather_bwd(g, ids, cnt, pad_row, g_table, mode):
+    B, L = ids.shape
+    D = g_table.shape[1]
+    if g.stride(-1) != 1:
+        raise RbxError("pooled_gather_bwd: g must have unit inner stride")
+    _call("rbx_pooled_gather_bwd", ctypes.c_void_p(g.data_ptr()), g.stride(0), ctypes.c_void_p(ids.data_ptr()),
+          ids.stride(0), _p(cnt, F32, "cnt"), -1 if pad_row is None else int(pad_row), _p(g_table, F32, "g_table"),
+          B, L, D, mode, _stream())
+
+
+# ------------------------------------------------------------------------------------------ a10
+def rowdot_fwd(u, v):
+    B, D = u.shape
+    K = v.numel() // (B * D) if B * D else 0
+    y = torch.empty((B, K), dtype=F32, device=u.device)
+    _call("rbx_rowdot_fwd", _p(u, F32, "u"), _p(v, F32, "v"), _p(y), B, K, D, _stream())
+    return y
+
+
+def rowdot_bwd(u, v, dy, need_du=True, need_dv=True):
+    B, D = u.shape
+    K = dy.shape[1]
+    du = torch.empty_like(u) if need_du else None
+    dv = torch.empty_like(v) if need_dv else None
+    _call("rbx_rowdot_bwd", _p(u, F32, "u"), _p(v, F32, "v"), _p(dy, F32, "dy"), _p(du), _p(dv), B, K, D, _stream())
+    return du, dv
+
+
+# ------------------------------------------------------------------------------------------- a6
+def interact_out_shape(B, F, D, mode):
+    if mode not in (0, 1, 2, 3):
+        raise RbxError("InnerProductInteraction mode %r is not supported" % (mode,))
+    P = F * (F - 1) // 2
+    return {0: (B, 1), 1: (B, D), 2: (B, P), 3: (B, P, D)}[mode]
+
+
+def interact_fwd(E, mode):
+    B, F, D = E.shape
+    out = torch.empty(interact_out_shape(B, F, D, mode), dtype=F32, device=E.device)
+    _call("rbx_interact_fwd", _p(E, F32, "E"), _p(out), B, F, D, mode, _stream())
+    return out
+
+
+def interact_bwd(E, dout, mode):
+    B, F, D = E.shape
+    dE = torch.empty_like(E)
+    _call("rbx_interact_bwd", _p(E, F32, "E"), _p(dout, F32, "dout"), _p(dE), B, F, D, mode, _stream())
+    return dE
+
+
+# ------------------------------------------------------------------------------------------- (e)
+def shard_route(rows, world):
+    """flat int32 global rows -> (send local rows grouped by owner, pos, counts[world] int32 DEVICE)."""
+    flat = rows.reshape(-1)
+    N = flat.numel()
+    lib = _lib.load()
+    ws_bytes = lib.rbx_shard_ws_bytes(N, world)
+    dev = rows.device
+    ws = torch.empty((max(ws_bytes // 4, 1),), dtype=I32, device=dev)
+    send = torch.empty((N,), dtype=I32, device=dev)
+    pos = torch.empty((N,), dtype=I32, device=dev)
+    counts = torch.empty((world,), dtype=I32, device=dev)
+    _call("rbx_shard_route", _p(flat, I32, "rows"), N, world, _p(ws), ws_bytes, _p(send), _p(pos), _p(counts), _stream())
+    return send, pos, counts
+
+
+def shard_permute(x, pos):
+    N = pos.numel()
+    D = x.numel() // N if N else 1
+    out = torch.empty((N, D), dtype=F32, device=x.device)
+    _call("rbx_shard_permute", _p(x, F32, "x"), _p(pos, I32, "pos"), _p(out), N, D, _stream())
+    return out
+
+
+def shard_unroute(recv, pos):
+    N = pos.numel()
+    D = recv.numel() // N if N else 1
+    out = torch.empty((N, D), dtype=F32, device=recv.device)
+    _call("rbx_shard_unroute", _p(recv, F32, "recv"), _p(pos, I32, "pos"), _p(out), N, D, _stream())
+    return out
+
+
+# ------------------------------------------------------------------------------------------ a12
+def sqnorm_(g, acc):
+    """acc (float64 [1], device) += sum(g^2)."""
+    _call("rbx_sqnorm", _p(g, F32, "g"), g.numel(), _p(acc, torch.float64, "acc"), _stream())
+
+
+def clip_coef(acc, max_norm, coef, norm_out=None):
+    _call("rbx_clip_coef", _p(acc, torch.float64, "acc"), float(max_norm), _p(coef, F32, "coef"), _p(norm_out), _stream())
+
+
+def adam_dense_(w, g, m, v, step, lr=1e-3, beta1=0.9, beta2=0.999, eps=1e-8, clip=None):
+    _call("rbx_adam_dense", _p(w, F32, "w"), _p(g, F32, "g"), _p(m, F32, "m"), _p(v, F32, "v"), w.numel(),
+          _p(clip, F32, "clip"), float(lr), float(beta1), float(beta2), float(eps), int(step), _stream())

@@ -1,0 +1,129 @@
+"""Shared test scaffolding: a seeded synthetic multi-slot problem in BOTH layouts --
+the reference's (per-feature weights + {feature: column} dict, consumed by oracle/) and the
+product's (fused tables + [B,F] int32 global rows, consumed by the C ABI)."""
+import os
+import sys
+from collections import OrderedDict
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+from oracle import recbox_oracle as oracle  # noqa: E402  (tests are allowed to import the oracle)
+
+
+class Problem:
+    """kinds: string over {'c','n'} giving the feature order, e.g. 'nncccn'."""
+
+    def __init__(self, B, kinds, D, vocab=50, seed=0, pad=True, scale=0.5, zipf=None, pad_frac=0.1):
+        g = torch.Generator().manual_seed(seed)
+        rng = np.random.default_rng(seed)
+        self.B, self.D, self.kinds = B, D, kinds
+        self.features = OrderedDict()
+        self.W, self.W1 = OrderedDict(), OrderedDict()      # per-feature weights (reference layout)
+        self.X = OrderedDict()                              # {feature: float64 [B]} like get_inputs
+        self.cat_names, self.num_names, self.cat_pos, self.num_pos = [], [], [], []
+        self.field_off, self.pad_row = [], []
+        off = 0
+        for pos, k in enumerate(kinds):
+            name = "%s%d" % ("C" if k == "c" else "I", pos)
+            if k == "c":
+                V = int(vocab[len(self.cat_names)]) if not isinstance(vocab, int) else vocab
+                spec = {"type": "categorical", "source": "", "vocab_size": V}
+                if pad:
+                    spec["padding_idx"] = 0
+                w = torch.randn(V, D, generator=g) * scale
+                w1 = torch.randn(V, 1, generator=g) * scale
+                if pad:
+                    w[0] = 0
+                    w1[0] = 0
+                lo = 0 if pad else 0
+                if zipf:
+                    ids = np.minimum(rng.zipf(zipf, size=B), V - 1)
+                else:
+                    ids = rng.integers(lo, V, size=B)
+                if pad and pad_frac:
+                    ids[rng.random(B) < pad_frac] = 0
+                self.X[name] = torch.from_numpy(ids.astype(np.float64))
+                self.cat_names.append(name)
+                self.cat_pos.append(pos)
+                self.field_off.append(off)
+                self.pad_row.append(off if pad else -1)
+                off += V
+            else:
+                spec = {"type": "numeric", "source": ""}
+                w = torch.randn(D, 1, generator=g) * scale     # nn.Linear(1, D).weight
+                w1 = torch.randn(1, 1, generator=g) * scale
+                self.X[name] = torch.rand(B, generator=g, dtype=torch.float64)
+                self.num_names.append(name)
+                self.num_pos.append(pos)
+            self.features[name] = spec
+            self.W[name] = w
+            self.W1[name] = w1
+        self.R = off
+        self.bias = torch.randn(1, generator=g) * scale
+        self.F, self.Fn = len(self.cat_names), len(self.num_names)
+
+    # ---- product layout -------------------------------------------------------------------
+    def fused(self, device="cpu"):
+        D = self.D
+        table = torch.cat([self.W[n] for n in self.cat_names], 0) if self.F else torch.zeros(0, D)
+        table_lr = torch.cat([self.W1[n].reshape(-1) for n in self.cat_names], 0) if self.F else torch.zeros(0)
+        rows = (torch.stack([self.X[n].long() + o for n, o in zip(self.cat_names, self.field_off)], 1).int()
+                if self.F else None)
+        dense_x = torch.stack([self.X[n].float() for n in self.num_names], 1) if self.Fn else None
+        dense_w = torch.stack([self.W[n].reshape(-1) for n in self.num_names], 0) if self.Fn else None
+        dense_w_lr = torch.cat([self.W1[n].reshape(-1) for n in self.num_names], 0) if self.Fn else None
+        out = dict(table=table, table_lr=table_lr, rows=rows, dense_x=dense_x, dense_w=dense_w,
+                   dense_w_lr=dense_w_lr, bias=self.bias.clone())
+        return {k: (v.to(device).contiguous() if v is not None else None) for k, v in out.items()}
+
+    def batch_matrix(self, label=True):
+        cols = [self.X[n].reshape(-1, 1) for n in self.features]
+        if label:
+            g = torch.Generator().manual_seed(1234)
+            cols.append((torch.rand(self.B, 1, generator=g) < 0.5).double())
+        return torch.cat(cols, 1)
+
+    # ---- reference layout, through the oracle ---------------------------------------------
+    def oracle_forward(self, leaf=False):
+        W = OrderedDict((k, v.clone().requires_grad_(leaf)) for k, v in self.W.items())
+        W1 = OrderedDict((k, v.clone().requires_grad_(leaf)) for k, v in self.W1.items())
+        bias = self.bias.clone().requires_grad_(leaf)
+        E = oracle.dict2tensor(oracle.embed_dict(self.X, self.features, W))
+        fm = oracle.inner_product_interaction(E, "product_sum")
+        lr = oracle.logistic_regression(self.X, self.features, W1, bias)
+        return E, fm, lr, W, W1, bias
+
+    def oracle_grads(self, dE, d_fm, d_lr):
+        """dense per-feature grads of sum(E*dE) + sum(fm*d_fm) + sum(lr*d_lr), assembled into the
+        fused layout (padding rows are zero because nn.Embedding masks them)."""
+        E, fm, lr, W, W1, bias = self.oracle_forward(leaf=True)
+        loss = (E * dE).sum() + (fm.reshape(-1) * d_fm).sum() + (lr.reshape(-1) * d_lr).sum()
+        loss.backward()
+        D = self.D
+        z = lambda *s: torch.zeros(*s)
+        g_table = torch.cat([W[n].grad for n in self.cat_names], 0) if self.F else z(0, D)
+        g_table_lr = torch.cat([W1[n].grad.reshape(-1) for n in self.cat_names], 0) if self.F else z(0)
+        g_dense_w = torch.stack([W[n].grad.reshape(-1) for n in self.num_names], 0) if self.Fn else None
+        g_dense_w_lr = torch.cat([W1[n].grad.reshape(-1) for n in self.num_names], 0) if self.Fn else None
+        return g_table, g_table_lr, g_dense_w, g_dense_w_lr, bias.grad
+
+
+def assert_close(a, b, rtol=1e-5, atol_scale=1e-5, what=""):
+    """|a-b| <= rtol*|b| + atol_scale*max|b| : fp32 contract of BASELINE.json (1e-5 relative), with
+    the absolute floor tied to the tensor's own magnitude (sums of mixed-sign terms cancel)."""
+    a = a.detach().double().cpu()
+    b = b.detach().double().cpu()
+    assert a.shape == b.shape, "%s shape %s vs %s" % (what, tuple(a.shape), tuple(b.shape))
+    if b.numel() == 0:
+        return
+    atol = atol_scale * float(b.abs().max())
+    err = (a - b).abs()
+    tol = rtol * b.abs() + atol
+    bad = err > tol
+    assert not bool(bad.any()), "%s: %d / %d outside tolerance, max err %.3e (max |ref| %.3e)" % (
+        what, int(bad.sum()), b.numel(), float(err.max()), float(b.abs().max()))
