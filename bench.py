@@ -203,18 +203,23 @@ def main_b200(args, rank, world, local_rank):
     dE = (torch.randn(B, Ft, D, generator=g) * 1e-3).to(dev)
     d_fm = (torch.randn(B, generator=g) * 1e-3).to(dev)
     d_lr = d_fm.clone()
-    g_table = torch.empty_like(table)
-    g_table_lr = torch.empty_like(table_lr)
-    g_dense_w = torch.empty_like(dense_w)
-    g_dense_w_lr = torch.empty_like(dense_w_lr)
-    g_bias = torch.empty_like(bias)
-    E = torch.empty(B, Ft, D, device=dev)
+    # dense gradients of every fused parameter live in ONE allocation -> one zero-fill launch
+    sizes = [R * D, R, Fn * D, Fn, 1]
+    offs = [0]
+    for n in sizes:
+        offs.append((offs[-1] + n + 3) // 4 * 4)
+    gbuf = torch.empty(offs[-1], device=dev)
+    g_table = gbuf[offs[0]:offs[0] + R * D].view(R, D)
+    g_table_lr = gbuf[offs[1]:offs[1] + R]
+    g_dense_w = gbuf[offs[2]:offs[2] + Fn * D].view(Fn, D)
+    g_dense_w_lr = gbuf[offs[3]:offs[3] + Fn]
+    g_bias = gbuf[offs[4]:offs[4] + 1]
 
     def fwd(rows, dx):
         return ops.embed_fm_fwd(table, table_lr, rows, cat_pos, dx, dense_w, dense_w_lr, num_pos, bias)
 
     def zero():
-        g_table.zero_(); g_table_lr.zero_(); g_dense_w.zero_(); g_dense_w_lr.zero_(); g_bias.zero_()
+        gbuf.zero_()
 
     def bwd(rows, dx, E, S):
         ops.embed_fm_bwd(table, rows, cat_pos, pad_row, dx, dense_w, num_pos, E, S, dE, d_fm, d_lr,

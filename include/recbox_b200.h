@@ -36,7 +36,7 @@ extern "C" {
 #define RBX_ERR_CUDA        -2   /* a CUDA runtime call or launch failed */
 #define RBX_ERR_UNSUPPORTED -3   /* shape outside what the kernels cover */
 
-#define RBX_MAX_SLOTS      256   /* max categorical (resp. numeric) slots per call */
+#define RBX_MAX_SLOTS      192   /* max categorical (resp. numeric) slots per call */
 #define RBX_MAX_DIM        512   /* max embedding dim */
 
 typedef void* rbx_stream_t;      /* cudaStream_t */
@@ -92,6 +92,8 @@ int rbx_pack_columns(const void* const* cols /*HOST [n] of DEVICE ptrs*/,
  *   fm_out[b]    = sum_d 0.5 * (S_d^2 - sum_slots e_d^2)    (nullable)
  *   lr_out[b]    = sum_f table_lr[rows[b,f]] + sum_n dense_x[b,n]*dense_w_lr[n] + lr_bias[0]
  *                                                           (nullable; needs table_lr)
+ * With E, S and fm_out all NULL the call is the first-order term alone (LogisticRegression
+ * without a D-dim table): table / dense_w may be NULL and D is ignored.
  * R = rows in the fused table.  A row id outside [0, R) reads as a zero row and receives no
  * gradient (the reference raises IndexError on CPU / device-asserts on CUDA; a library must not
  * fault the device).
@@ -100,10 +102,12 @@ int rbx_embed_fm_fwd(const float* table /*DEVICE [R,D]*/,
                      const float* table_lr /*DEVICE [R] | NULL*/,
                      const int32_t* rows /*DEVICE [B,F]*/,
                      const int32_t* cat_pos /*HOST [F]*/,
+                     const int32_t* lr_delta /*HOST [F] | NULL: row in table_lr = rows[b,f] + lr_delta[f]*/,
                      const float* dense_x /*DEVICE [B,Fn] | NULL*/,
-                     const float* dense_w /*DEVICE [Fn,D] | NULL*/,
-                     const float* dense_w_lr /*DEVICE [Fn] | NULL*/,
+                     const float* dense_w /*DEVICE [*,D] | NULL*/,
+                     const float* dense_w_lr /*DEVICE [*] | NULL*/,
                      const int32_t* num_pos /*HOST [Fn]*/,
+                     const int32_t* num_widx /*HOST [Fn] | NULL: row of slot n in dense_w / dense_w_lr (identity)*/,
                      const float* lr_bias /*DEVICE [1] | NULL*/,
                      float* E /*DEVICE [B,Ft,D] | NULL*/,
                      float* S /*DEVICE [B,D] | NULL*/,
@@ -129,9 +133,11 @@ int rbx_embed_fm_bwd(const float* table /*DEVICE [R,D] | NULL if E given*/,
                      const int32_t* rows /*DEVICE [B,F]*/,
                      const int32_t* cat_pos /*HOST [F]*/,
                      const int32_t* pad_row /*HOST [F], -1 = none*/,
+                     const int32_t* lr_delta /*HOST [F] | NULL*/,
                      const float* dense_x /*DEVICE [B,Fn] | NULL*/,
-                     const float* dense_w /*DEVICE [Fn,D] | NULL*/,
+                     const float* dense_w /*DEVICE [*,D] | NULL*/,
                      const int32_t* num_pos /*HOST [Fn]*/,
+                     const int32_t* num_widx /*HOST [Fn] | NULL*/,
                      const float* E /*DEVICE [B,Ft,D] | NULL*/,
                      const float* S /*DEVICE [B,D] | NULL*/,
                      const float* dE /*DEVICE [B,Ft,D] | NULL*/,

@@ -1,0 +1,349 @@
+#!/usr/bin/env python
+"""Mint golden vectors from the UNMODIFIED reference (reczoo/RecBox at /root/reference), CPU, fp32.
+
+TEST INFRASTRUCTURE.  Run in the dev container only (the GPU box has no /root/reference):
+
+    python oracle/make_golden.py            # rewrites tests/golden/*.npz
+
+The reference ships no tests or fixtures ("parity unpinned" by the reference), so
+these files ARE the pin: every array below is produced by importing the reference's own modules
+through oracle/ref_shim.py and calling them on seeded inputs.  tests/test_oracle_golden.py holds
+the oracle (oracle/recbox_oracle.py) to them on CPU; tests/test_layers_gpu.py holds the CUDA
+product to them on the B200.
+"""
+import os
+import sys
+import tempfile
+from collections import OrderedDict
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from oracle import ref_shim  # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden")
+
+
+def npz(name, **arrays):
+    os.makedirs(OUT, exist_ok=True)
+    flat = {}
+    for k, v in arrays.items():
+        if isinstance(v, torch.Tensor):
+            v = v.detach().cpu().numpy()
+        flat[k] = np.asarray(v)
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **flat)
+    print("wrote %-28s %3d arrays, %7.1f KB" % (name + ".npz", len(flat), os.path.getsize(os.path.join(OUT, name + ".npz")) / 1024))
+
+
+def sd_arrays(module, prefix):
+    return {prefix + k: v for k, v in module.state_dict().items()}
+
+
+def grads_of(module, prefix):
+    return {prefix + k: (p.grad if p.grad is not None else torch.zeros_like(p)) for k, p in module.named_parameters()}
+
+
+# --------------------------------------------------------------------------------------------
+def ranking_feature_map(tmp, D, share=False, seq=False):
+    from recbox.ranking.features import FeatureMap
+    fm = FeatureMap("golden", tmp)
+    fm.features["I1"] = {"source": "", "type": "numeric"}
+    fm.features["C1"] = {"source": "", "type": "categorical", "vocab_size": 11, "padding_idx": 0}
+    fm.features["I2"] = {"source": "", "type": "numeric"}
+    fm.features["C2"] = {"source": "", "type": "categorical", "vocab_size": 7, "padding_idx": 0}
+    fm.features["C3"] = {"source": "", "type": "categorical", "vocab_size": 13, "padding_idx": 0}
+    c4 = {"source": "", "type": "categorical", "vocab_size": 11, "padding_idx": 0}
+    if share:
+        c4["share_embedding"] = "C1"
+    fm.features["C4"] = c4
+    if seq:
+        fm.features["S1"] = {"source": "", "type": "sequence", "vocab_size": 9, "padding_idx": 0, "max_len": 5,
+                             "feature_encoder": "layers.MaskedAveragePooling()"}
+    fm.labels = ["label"]
+    fm.num_fields = fm.get_num_fields()
+    fm.set_column_index()
+    fm.default_emb_dim = D
+    return fm
+
+
+def ranking_batch(fm, B, seed):
+    g = torch.Generator().manual_seed(seed)
+    cols = []
+    for name, spec in fm.features.items():
+        if spec["type"] == "numeric":
+            cols.append(torch.rand(B, 1, generator=g, dtype=torch.float64))
+        elif spec["type"] == "categorical":
+            cols.append(torch.randint(0, spec["vocab_size"], (B, 1), generator=g).double())
+        else:
+            L = spec["max_len"]
+            ids = torch.randint(1, spec["vocab_size"], (B, L), generator=g)
+            lens = torch.randint(0, L + 1, (B,), generator=g)
+            ids[torch.arange(L)[None, :] >= lens[:, None]] = 0
+            cols.append(ids.double())
+    cols.append((torch.rand(B, 1, generator=g) < 0.5).double())
+    return torch.cat(cols, 1)
+
+
+def inputs_of(fm, batch):
+    return {f: batch[:, fm.get_column_index(f)] for f, s in fm.features.items() if s["type"] != "meta"}
+
+
+def golden_interaction(L):
+    g = torch.Generator().manual_seed(11)
+    out = {}
+    for tag, E in (("kat", torch.arange(24, dtype=torch.float32).view(2, 3, 4)), ("rnd", torch.randn(5, 6, 8, generator=g))):
+        out[tag + ".E"] = E
+        for mode in ("product_sum", "bi_interaction", "inner_product", "elementwise_product"):
+            layer = L.InnerProductInteraction(E.shape[1], output=mode)
+            Ev = E.clone().requires_grad_(True)
+            y = layer(Ev)
+            w = torch.randn(y.shape, generator=g)
+            (y * w).sum().backward()
+            out["%s.%s.out" % (tag, mode)] = y
+            out["%s.%s.w" % (tag, mode)] = w
+            out["%s.%s.dE" % (tag, mode)] = Ev.grad
+    npz("interaction", **out)
+
+
+def golden_pooling(L):
+    import recbox.core.pytorch.layers as CL
+    g = torch.Generator().manual_seed(12)
+    emb = torch.randn(6, 7, 8, generator=g)
+    emb[0, 3:] = 0
+    emb[1] = 0
+    emb[2, 0] = 0
+    mask = torch.rand(6, 7, generator=g) < 0.6
+    npz("pooling", emb=emb, mask=mask,
+        ranking_avg=L.MaskedAveragePooling()(emb), ranking_avg_mask=L.MaskedAveragePooling()(emb, mask),
+        ranking_sum=L.MaskedSumPooling()(emb), core_avg=CL.MaskedAveragePooling()(emb), core_sum=CL.MaskedSumPooling()(emb))
+
+
+def golden_ranking_layers(L, tmp, tag, D, share=False, seq=False, B=37):
+    torch.manual_seed(100 + D)
+    fm = ranking_feature_map(tmp, D, share, seq)
+    emb = L.FeatureEmbedding(fm, D)
+    fml = L.FactorizationMachine(fm) if not seq else None
+    # the default init (std 1e-4) makes every output ~0; use O(0.3) weights so parity means something
+    g = torch.Generator().manual_seed(200 + D)
+    mods = [emb] + ([fml] if fml is not None else [])
+    with torch.no_grad():
+        for m in mods:
+            for p in m.parameters():
+                p.copy_(torch.randn(p.shape, generator=g) * 0.3)
+            for mod in m.modules():
+                if isinstance(mod, torch.nn.Embedding) and mod.padding_idx is not None:
+                    mod.weight[mod.padding_idx] = 0
+    batch = ranking_batch(fm, B, 300 + D)
+    X = inputs_of(fm, batch)
+    E = emb(X)
+    out = {"batch": batch, "E": E}
+    out.update(sd_arrays(emb, "emb."))
+    wE = torch.randn(E.shape, generator=g)
+    loss = (E * wE).sum()
+    out["wE"] = wE
+    if fml is not None:
+        lr_out = fml.lr_layer(X)
+        fm_out = fml.fm_layer(E)
+        y = fml(X, E)
+        wy = torch.randn(y.shape, generator=g)
+        loss = loss + (y * wy).sum()
+        out.update(lr_out=lr_out, fm_out=fm_out, y=y, wy=wy)
+        out.update(sd_arrays(fml, "fm."))
+    loss.backward()
+    out.update(grads_of(emb, "grad.emb."))
+    if fml is not None:
+        out.update(grads_of(fml, "grad.fm."))
+    npz(tag, **out)
+
+
+def golden_init(L, tmp):
+    """Same seed -> same initial weights is part of the drop-in contract."""
+    torch.manual_seed(2024)
+    fm = ranking_feature_map(tmp, 8, share=True)
+    emb = L.FeatureEmbedding(fm, 8)
+    fml = L.FactorizationMachine(fm)
+    out = sd_arrays(emb, "emb.")
+    out.update(sd_arrays(fml, "fm."))
+    npz("init_seed2024", **out)
+
+
+def golden_core_layers(tmp):
+    import recbox.core.pytorch.layers as CL
+
+    class FMap(object):
+        pass
+    fmap = FMap()
+    fmap.data_dir, fmap.dataset_id = tmp, "golden"
+    fmap.feature_specs = OrderedDict([
+        ("item_id", {"type": "categorical", "source": "item", "vocab_size": 23, "padding_idx": 22}),
+        ("item_cat", {"type": "categorical", "source": "item", "vocab_size": 6}),
+        ("user_id", {"type": "categorical", "source": "user", "vocab_size": 17}),
+        ("user_age", {"type": "numeric", "source": "user"}),
+        ("user_hist", {"type": "sequence", "source": "user", "vocab_size": 23, "padding_idx": 22,
+                       "share_embedding": "item_id", "embedding_callback": "layers.MaskedAveragePooling()"}),
+    ])
+    D, B, L = 8, 29, 6
+    torch.manual_seed(77)
+    layer = CL.EmbeddingLayer(fmap, D)
+    g = torch.Generator().manual_seed(78)
+    with torch.no_grad():
+        for p in layer.parameters():
+            p.copy_(torch.randn(p.shape, generator=g) * 0.3)
+        layer.embedding_layer.embedding_layers["item_id"].weight[22] = 0
+    hist = torch.randint(0, 22, (B, L), generator=g)
+    lens = torch.randint(0, L + 1, (B,), generator=g)
+    hist[torch.arange(L)[None, :] >= lens[:, None]] = 22
+    X = {"item_id": torch.randint(0, 23, (B,), generator=g), "item_cat": torch.randint(0, 6, (B,), generator=g),
+         "user_id": torch.randint(0, 17, (B,), generator=g), "user_age": torch.rand(B, generator=g, dtype=torch.float64),
+         "user_hist": hist}
+    U = layer(X, feature_source="user")
+    V = layer(X, feature_source="item")
+    wU, wV = torch.randn(U.shape, generator=g), torch.randn(V.shape, generator=g)
+    ((U * wU).sum() + (V * wV).sum()).backward()
+    out = {"X." + k: v for k, v in X.items()}
+    out.update(U=U, V=V, wU=wU, wV=wV)
+    out.update(sd_arrays(layer, "emb."))
+    out.update(grads_of(layer, "grad.emb."))
+    # single-feature selection returns the bare [B, D] tensor (embedding.py:110-111)
+    one = CL.EmbeddingLayer(fmap, D, required_feature_columns=["user_id"])
+    with torch.no_grad():
+        one.embedding_layer.embedding_layers["user_id"].weight.copy_(layer.embedding_layer.embedding_layers["user_id"].weight)
+    out["single"] = one(X)
+    npz("core_layers", **out)
+
+
+def golden_two_tower():
+    import recbox.core.pytorch.losses as losses
+    g = torch.Generator().manual_seed(31)
+    B, K, D = 19, 5, 16
+    u = torch.randn(B, D, generator=g, requires_grad=True)
+    v = torch.randn(B * K, D, generator=g, requires_grad=True)
+    y = torch.bmm(v.view(B, K, D), u.unsqueeze(-1)).squeeze(-1)       # convention of match_model.py:71-75
+    loss = losses.SoftmaxCrossEntropyLoss()(y, torch.zeros(B, K))
+    loss.backward()
+    # rechub DSSM: torch.mul(u, v).sum(dim=1) after F.normalize (dssm.py:48,57,65)
+    un = torch.nn.functional.normalize(u.detach(), p=2, dim=1)
+    vn = torch.nn.functional.normalize(v.detach()[:B], p=2, dim=1)
+    npz("two_tower", u=u, v=v, y=y, loss=loss, du=u.grad, dv=v.grad, dssm_u=un, dssm_v=vn, dssm_y=torch.mul(un, vn).sum(dim=1))
+
+
+def make_deepfm(L, fm, D, hidden, tmp, use_mlp=True):
+    from recbox.ranking.pytorch.models.ranking_model import RankingModel
+
+    class DeepFM(RankingModel):
+        def __init__(self, feature_map, **kw):
+            super(DeepFM, self).__init__(feature_map, **kw)
+            self.embedding_layer = L.FeatureEmbedding(feature_map, D)
+            self.fm_layer = L.FactorizationMachine(feature_map)
+            self.mlp = L.MLP_Block(input_dim=feature_map.sum_emb_out_dim(), output_dim=1, hidden_units=list(hidden)) if use_mlp else None
+            self.compile("adam", "binary_cross_entropy", 1e-3)
+            self.reset_parameters()
+            self.model_to_device()
+
+        def forward(self, inputs):
+            X = self.get_inputs(inputs)
+            E = self.embedding_layer(X)
+            y = self.fm_layer(X, E)
+            if self.mlp is not None:
+                y = y + self.mlp(E.flatten(start_dim=1))
+            return {"y_pred": self.output_activation(y)}
+    m = DeepFM(fm, model_id="DeepFM_golden", gpu=-1, verbose=0, model_root=tmp, metrics=["AUC"])
+    m._max_gradient_norm = 10.
+    return m
+
+
+def golden_deepfm_train(L, tmp):
+    torch.manual_seed(5)
+    D = 8
+    fm = ranking_feature_map(tmp, D)
+    model = make_deepfm(L, fm, D, (16, 8), tmp)
+    g = torch.Generator().manual_seed(6)
+    with torch.no_grad():          # O(0.1) embeddings so that gradients and Adam moments are not ~1e-8
+        for k, p in model.named_parameters():
+            if "embedding_layers" in k:
+                p.copy_(torch.randn(p.shape, generator=g) * 0.1)
+        for mod in model.modules():
+            if isinstance(mod, torch.nn.Embedding) and mod.padding_idx is not None:
+                mod.weight[mod.padding_idx] = 0
+    out = {"init." + k: v.clone() for k, v in model.state_dict().items()}
+    losses = []
+    for step in range(3):
+        batch = ranking_batch(fm, 64, 400 + step)
+        out["batch%d" % step] = batch
+        model.train()
+        losses.append(float(model.train_step(batch)))
+        if step == 0:
+            out.update({"grad0." + k: p.grad.clone() for k, p in model.named_parameters()})
+    out["losses"] = np.asarray(losses, dtype=np.float64)
+    out.update({"final." + k: v.clone() for k, v in model.state_dict().items()})
+    model.eval()
+    out["pred_final"] = model.forward(out["batch0"])["y_pred"]
+    npz("deepfm_train", **out)
+
+
+def golden_config1(L, tmp):
+    """BASELINE configs[0]: FM ranking on a 1k-row Criteo-shaped synthetic CSV through the
+    reference's own FeatureProcessor (SURVEY.md 8d cfg 1, Appendix A)."""
+    import pandas as pd
+    from recbox.ranking.preprocess.feature_processor import FeatureProcessor
+    rng = np.random.default_rng(2024)
+    N = 1000
+    data = {"label": (rng.random(N) < 0.5).astype(float)}
+    for i in range(1, 14):
+        data["I%d" % i] = np.round(rng.lognormal(0, 1, N), 4)
+    for i in range(1, 27):
+        data["C%d" % i] = ["%08x" % (int(z) % (50 * i)) for z in rng.zipf(1.2, N)]
+    csv = os.path.join(tmp, "criteo_1k.csv")
+    pd.DataFrame(data).to_csv(csv, index=False)
+    fp = FeatureProcessor(
+        feature_cols=[{"name": ["I%d" % i for i in range(1, 14)], "active": True, "dtype": "float", "type": "numeric"},
+                      {"name": ["C%d" % i for i in range(1, 27)], "active": True, "dtype": "str", "type": "categorical"}],
+        label_col={"name": "label", "dtype": "float"}, dataset_id="criteo_1k", data_root=tmp)
+    ddf = fp.read_csv(csv)
+    ddf = fp.preprocess(ddf)
+    fp.fit(ddf, min_categr_count=1)
+    arrays = fp.transform(ddf)
+    fm = fp.feature_map
+    fm.default_emb_dim = 10
+    cols = list(fm.features.keys()) + fm.labels
+    batch = torch.from_numpy(np.hstack([np.asarray(arrays[c]).reshape(N, -1) for c in cols]).astype(np.float64))
+    torch.manual_seed(9)
+    model = make_deepfm(L, fm, 10, (), tmp, use_mlp=False)       # FM = FeatureEmbedding + FactorizationMachine
+    out = {"batch": batch, "vocab_sizes": np.asarray([fm.features["C%d" % i]["vocab_size"] for i in range(1, 27)])}
+    out.update({"init." + k: v.clone() for k, v in model.state_dict().items()})
+    model.eval()
+    out["pred_init"] = model.forward(batch[:128])["y_pred"]
+    losses = []
+    model.train()
+    for step in range(4):
+        losses.append(float(model.train_step(batch[step * 128:(step + 1) * 128])))
+    out["losses"] = np.asarray(losses, dtype=np.float64)
+    model.eval()
+    out["pred_final"] = model.forward(batch[:128])["y_pred"]
+    out.update({"final." + k: v.clone() for k, v in model.state_dict().items()})
+    npz("config1_fm", **out)
+
+
+def main():
+    if not ref_shim.available():
+        raise SystemExit("reference tree not found at %s" % ref_shim.REFERENCE_ROOT)
+    L = ref_shim.install()
+    torch.set_num_threads(1)       # deterministic CPU reductions
+    with tempfile.TemporaryDirectory() as tmp:
+        golden_interaction(L)
+        golden_pooling(L)
+        golden_ranking_layers(L, tmp, "ranking_layers_d8", 8)
+        golden_ranking_layers(L, tmp, "ranking_layers_d10", 10)
+        golden_ranking_layers(L, tmp, "ranking_layers_share", 16, share=True)
+        golden_ranking_layers(L, tmp, "ranking_layers_seq", 8, seq=True)
+        golden_init(L, tmp)
+        golden_core_layers(tmp)
+        golden_two_tower()
+        golden_deepfm_train(L, tmp)
+        golden_config1(L, tmp)
+
+
+if __name__ == "__main__":
+    main()

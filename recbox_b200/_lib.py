@@ -11,7 +11,7 @@ import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
-LIB_PATH = os.path.join(_HERE, "librecbox_b200.so")
+LIB_PATH = os.environ.get("RBX_LIB_PATH") or os.path.join(_HERE, "librecbox_b200.so")   # override: tuning variants
 HEADER = os.path.join(os.path.dirname(_HERE), "include", "recbox_b200.h")
 
 NVCC_FLAGS = [
@@ -37,6 +37,8 @@ def sources():
 
 
 def needs_build():
+    if os.environ.get("RBX_LIB_PATH"):
+        return False
     if not os.path.exists(LIB_PATH):
         return True
     t = os.path.getmtime(LIB_PATH)
@@ -44,20 +46,21 @@ def needs_build():
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force=False, verbose=False):
+def build(force=False, verbose=False, defines=(), out=None):
     """Compile every csrc/*.cu for sm_100a into recbox_b200/librecbox_b200.so (in-tree, so the
     built library travels with the repo snapshot).  nvcc cross-compiles without a GPU."""
-    if not force and not needs_build():
+    out = out or LIB_PATH
+    if not force and out == LIB_PATH and not needs_build():
         return LIB_PATH
-    tmp = LIB_PATH + ".tmp.%d" % os.getpid()
-    cmd = [_nvcc()] + [f for f in NVCC_FLAGS if f] + ["-o", tmp] + sources()
+    tmp = out + ".tmp.%d" % os.getpid()
+    cmd = [_nvcc()] + [f for f in NVCC_FLAGS if f] + ["-D" + d for d in defines] + ["-o", tmp] + sources()
     proc = subprocess.run(cmd, capture_output=True, text=True)
     if proc.returncode != 0:
         raise RbxError("nvcc failed:\n%s\n%s" % (" ".join(cmd), proc.stderr[-8000:]))
-    os.replace(tmp, LIB_PATH)
+    os.replace(tmp, out)
     if verbose:
         print(proc.stderr)
-    return LIB_PATH
+    return out
 
 
 _lib = None
@@ -75,8 +78,8 @@ SIGNATURES = {
     "rbx_device_sm_count": [],
     "rbx_split_batch_f64": [_P, _I64, _I, _I64, _P, _P, _P, _I, _I, _P, _P, _P, _P],
     "rbx_pack_columns": [_P, _P, _P, _P, _I, _I64, _I, _P, _P],
-    "rbx_embed_fm_fwd": [_P] * 13 + [_I64, _I64, _I, _I, _I, _P],
-    "rbx_embed_fm_bwd": [_P] * 17 + [_I64, _I64, _I, _I, _I, _P],
+    "rbx_embed_fm_fwd": [_P] * 15 + [_I64, _I64, _I, _I, _I, _P],
+    "rbx_embed_fm_bwd": [_P] * 19 + [_I64, _I64, _I, _I, _I, _P],
     "rbx_gather_rows": [_P, _P, _P, _I64, _I, _P],
     "rbx_scatter_add_rows": [_P, _P, _c.c_int32, _P, _I64, _I, _P],
     "rbx_pooled_gather_fwd": [_P, _P, _I64, _P, _I64, _P, _I64, _I, _I, _I, _P],

@@ -3,19 +3,32 @@
 // each entry point replaces; DESIGN.md "Kernels" for the roofline of each.
 //
 // Thread mapping (vector path, D % 4 == 0, D <= 128): a row of D floats is D/4 float4; LPR = D/4
-// consecutive lanes own one SAMPLE and walk its slots, so a warp covers 32/LPR samples and one
-// warp-level LDG.128 fetches 32/LPR complete rows.  The FM sums S = sum_f e_f and Q = sum_f e_f^2
-// stay in registers; sum over d is a log2(LPR)-step shuffle.  Slots are processed U at a time with
-// all U row loads issued before the first use (memory-level parallelism: U x 16 B per lane in
-// flight; at 16 resident warps/SM that is 64 KB/SM outstanding, enough to cover HBM latency).
+// consecutive lanes own one SAMPLE and walk its slots, so a warp covers SPW = 32/LPR samples and
+// one warp-level LDG.128 fetches SPW complete rows.  The FM sums S = sum_f e_f, Q = sum_f e_f^2 stay
+// in registers; the sum over d is a log2(LPR)-step shuffle.
+//
+// Work distribution: persistent grid of (SMs x resident CTAs/SM) CTAs; warp w of the grid walks the
+// warp groups (SPW consecutive samples) w, w + #warps, ... -- no CTA-wide barrier anywhere.
+//
+// Index staging (kStaged): each warp owns a private, double-buffered slot of shared memory.  While
+// it works on group g, lane 0 has already launched ONE cp.async.bulk (TMA, SASS UBLKCP) for the id
+// span of group g + #warps (SPW*F*4 contiguous bytes of `rows`) and one for its dense_x span,
+// completing on the warp's own mbarrier.  Row addresses then come from shared memory (~30 cycles)
+// instead of a dependent global load (~1 us under load), so a warp's row gathers issue back to
+// back and the DRAM pipe stays full.  Spans that do not start on a 16-byte boundary are copied
+// from the boundary below (skew of <= 3 words).  The direct variant (ids read with LDG) remains for
+// unaligned base pointers.
+//
 // Scalar path (any D <= 512): one warp per sample, lane d owns columns d, d+32, ...
 #include "rbx_common.cuh"
 
 namespace {
 
 struct SlotMeta {
-    int16_t cat_pos[RBX_MAX_SLOTS];
-    int16_t num_pos[RBX_MAX_SLOTS];
+    int16_t cat_pos[RBX_MAX_SLOTS];    // output position of categorical slot f
+    int16_t num_pos[RBX_MAX_SLOTS];    // output position of numeric slot n
+    int16_t num_widx[RBX_MAX_SLOTS];   // row of numeric slot n in dense_w / dense_w_lr
+    int32_t lr_delta[RBX_MAX_SLOTS];   // row of slot f in table_lr = rows[b,f] + lr_delta[f]
 };
 
 struct FwdParams {
@@ -59,59 +72,181 @@ struct BwdParams {
 };
 
 constexpr int kThreads = 256;
+constexpr int kWarps = kThreads / 32;
+
+// tuning knobs (compile-time; profiles/ records the sweep that chose the defaults)
+#ifndef RBX_FWD_MINB
+#define RBX_FWD_MINB 3      // resident CTAs/SM the forward kernel is register-budgeted for
+#endif
+#ifndef RBX_BWD_MINB
+#define RBX_BWD_MINB 4
+#endif
+#ifndef RBX_FWD_U
+#define RBX_FWD_U 8         // row gathers in flight per lane, forward
+#endif
+#ifndef RBX_BWD_U
+#define RBX_BWD_U 4         // slots per chunk, backward (2 streaming loads + 1 red each)
+#endif
+#ifndef RBX_L2_HINTS
+#define RBX_L2_HINTS 0      // bit 0: table/grad rows evict_last; bit 1: E/dE streams evict_first
+#endif
+#if RBX_L2_HINTS & 1
+#define LD_ROW(p) ld_row_f4_hint(p, pol_keep)
+#define RED_ROW(p, v) red_add_f4_hint(p, v, pol_keep)
+#else
+#define LD_ROW(p) ld_row_f4(p)
+#define RED_ROW(p, v) red_add_f4(p, v)
+#endif
+#if RBX_L2_HINTS & 2
+#define LD_STREAM(p) ld_stream_f4_hint(p, pol_stream)
+#define ST_STREAM(p, v) st_stream_f4_hint(p, v, pol_stream)
+#else
+#define LD_STREAM(p) ld_stream_f4(p)
+#define ST_STREAM(p, v) st_stream_f4(p, v)
+#endif
+
+// ---------------------------------------------------------------------------------------------
+// TMA (1-D bulk copy) + mbarrier helpers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra DONE;\n"
+        "bra LAB_WAIT;\n"
+        "DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+
+// Stage the `n` 4-byte words starting at word offset `wo` of `base` (base 16-B aligned) into the
+// shared buffer `dst` (16-B aligned): the copy starts at the 16-B boundary below (skew = wo & 3
+// words, so word i lands at dst[skew + i]); the 16-B multiple goes through one TMA bulk copy that
+// completes on `bar`, the <= 3 trailing words through plain stores (so nothing past `wo + n` is
+// ever read).  Called by one lane, which arms `bar` with the returned transaction bytes first.
+__device__ __forceinline__ uint32_t stage_tx_bytes(int64_t wo, int64_t n) {
+    return (uint32_t)((((wo & 3) + n) * 4) & ~(int64_t)15);
+}
+__device__ __forceinline__ void stage_words(void* dst, const void* base, int64_t wo, int64_t n, uint64_t* bar) {
+    const int64_t skew = wo & 3;
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(base) + (wo - skew);
+    const uint32_t bulk = stage_tx_bytes(wo, n);
+    if (bulk) tma_load_1d(dst, src, bulk, bar);
+    for (int64_t w = bulk / 4; w < skew + n; ++w) reinterpret_cast<uint32_t*>(dst)[w] = __ldg(src + w);
+}
 
 // ---------------------------------------------------------------------------------------------
 // forward, vector path
 // ---------------------------------------------------------------------------------------------
-template <int LPR, int U>
-__global__ void __launch_bounds__(kThreads) k_embed_fm_fwd_vec(const __grid_constant__ FwdParams p) {
+template <int LPR, int U, bool kStaged>
+__global__ void __launch_bounds__(kThreads, RBX_FWD_MINB) k_embed_fm_fwd(const __grid_constant__ FwdParams p) {
     constexpr int D = 4 * LPR;
     constexpr int SPW = 32 / LPR;
-    const int lane = threadIdx.x & 31;
-    const int lig = lane & (LPR - 1);
-    const int gi = lane / LPR;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int lig = lane & (LPR - 1), gi = lane / LPR;
     const int F = p.F, Fn = p.Fn, Ft = p.F + p.Fn;
-    const int64_t warp0 = (int64_t)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
-    const int64_t nwarps = (int64_t)gridDim.x * (kThreads / 32);
     const float bias = p.lr_bias ? __ldg(p.lr_bias) : 0.f;
+    const uint64_t pol_keep = l2_policy_evict_last(), pol_stream = l2_policy_evict_first();
+    (void)pol_keep; (void)pol_stream;
 
-    for (int64_t base = warp0 * SPW; base < p.B; base += nwarps * SPW) {
-        const int64_t b = base + gi;
+    // per-warp staging slots: idx[2][wi] per warp | dx[2][wx] per warp | 2 mbarriers per warp
+    const int wi = (SPW * F + 6) & ~3, wx = Fn ? ((SPW * Fn + 6) & ~3) : 0;
+    int32_t* my_idx = reinterpret_cast<int32_t*>(smem_raw) + (size_t)warp * 2 * wi;
+    float* my_dx = reinterpret_cast<float*>(smem_raw) + (size_t)kWarps * 2 * wi + (size_t)warp * 2 * wx;
+    uint64_t* my_bar = reinterpret_cast<uint64_t*>(smem_raw + (size_t)kWarps * 2 * (wi + wx) * 4) + warp * 2;
+
+    const int64_t G = (p.B + SPW - 1) / SPW;
+    const int64_t gw = (int64_t)blockIdx.x * kWarps + warp, nw = (int64_t)gridDim.x * kWarps;
+    auto issue = [&](int64_t g, int buf) {   // lane 0: arm the barrier, launch the bulk copies of group g
+        const int64_t b0 = g * SPW;
+        const int64_t ns = (p.B - b0 < SPW) ? p.B - b0 : SPW;
+        mbar_expect_tx(&my_bar[buf], (F ? stage_tx_bytes(b0 * F, ns * F) : 0u) + (Fn ? stage_tx_bytes(b0 * Fn, ns * Fn) : 0u));
+        if (F) stage_words(my_idx + (size_t)buf * wi, p.rows, b0 * F, ns * F, &my_bar[buf]);
+        if (Fn) stage_words(my_dx + (size_t)buf * wx, p.dense_x, b0 * Fn, ns * Fn, &my_bar[buf]);
+    };
+    if (kStaged) {
+        if (lane == 0) {
+            mbar_init(&my_bar[0], 1);
+            mbar_init(&my_bar[1], 1);
+            fence_mbar_init();
+            if (gw < G) issue(gw, 0);
+        }
+        __syncwarp();
+    }
+
+    int it = 0;
+    for (int64_t g = gw; g < G; g += nw, ++it) {
+        const int buf = it & 1;
+        const int64_t b0 = g * SPW;
+        if (kStaged) {
+            if (lane == 0 && g + nw < G) issue(g + nw, buf ^ 1);   // slot buf^1 was released by the __syncwarp below
+            mbar_wait(&my_bar[buf], (it >> 1) & 1);
+            __syncwarp();                                           // trailing words written by lane 0
+        }
+        const int64_t b = b0 + gi;
         const bool valid = b < p.B;
-        const int32_t* rb = p.rows + b * F;
+        const int32_t* rb = kStaged ? my_idx + (size_t)buf * wi + ((b0 * F) & 3) + gi * F : p.rows + b * F;
+        const float* xb = kStaged ? my_dx + (size_t)buf * wx + ((b0 * Fn) & 3) + gi * Fn : p.dense_x + b * Fn;
         float* Eb = p.E ? p.E + (size_t)b * Ft * D + 4 * lig : nullptr;
         float4 S = make_float4(0.f, 0.f, 0.f, 0.f), Q = S;
 
-        for (int f0 = 0; f0 < F; f0 += U) {
+        // first-order gathers first: they are independent of everything below and overlap it
+        float lr = 0.f;
+        if (p.lr_out && valid) {
+#pragma unroll 4
+            for (int f = lig; f < F; f += LPR) {
+                const int32_t r = kStaged ? rb[f] : __ldg(rb + f);
+                if ((uint32_t)r < (uint64_t)p.R) lr += __ldg(p.table_lr + (r + p.meta.lr_delta[f]));
+            }
+        }
+        for (int f0 = 0; p.table && f0 < F; f0 += U) {
             int32_t r[U];
             float4 v[U];
 #pragma unroll
             for (int u = 0; u < U; ++u) {
                 r[u] = -1;
-                if (valid && f0 + u < F) r[u] = __ldg(rb + f0 + u);
+                if (valid && f0 + u < F) r[u] = kStaged ? rb[f0 + u] : __ldg(rb + f0 + u);
             }
 #pragma unroll
             for (int u = 0; u < U; ++u) {
                 v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if ((uint32_t)r[u] < (uint64_t)p.R) v[u] = ld_row_f4(p.table + (size_t)r[u] * D + 4 * lig);
+                if ((uint32_t)r[u] < (uint64_t)p.R) v[u] = LD_ROW(p.table + (size_t)r[u] * D + 4 * lig);
             }
 #pragma unroll
             for (int u = 0; u < U; ++u) {
                 if (valid && f0 + u < F) {
                     S = f4_add(S, v[u]);
                     Q = f4_sqacc(v[u], Q);
-                    if (Eb) st_stream_f4(Eb + (size_t)p.meta.cat_pos[f0 + u] * D, v[u]);
+                    if (Eb) ST_STREAM(Eb + (size_t)p.meta.cat_pos[f0 + u] * D, v[u]);
                 }
             }
         }
         // numeric slots: e = x * w  (nn.Linear(1, D, bias=False) on x.view(-1,1))
-        for (int n = 0; n < Fn; ++n) {
+        for (int n = 0; p.dense_w && n < Fn; ++n) {
             if (valid) {
-                const float x = __ldg(p.dense_x + b * Fn + n);
-                const float4 e = f4_scale(ld_row_f4(p.dense_w + (size_t)n * D + 4 * lig), x);
+                const float x = kStaged ? xb[n] : __ldg(xb + n);
+                const float4 e = f4_scale(ld_row_f4(p.dense_w + (size_t)p.meta.num_widx[n] * D + 4 * lig), x);
                 S = f4_add(S, e);
                 Q = f4_sqacc(e, Q);
-                if (Eb) st_stream_f4(Eb + (size_t)p.meta.num_pos[n] * D, e);
+                if (Eb) ST_STREAM(Eb + (size_t)p.meta.num_pos[n] * D, e);
             }
         }
         if (p.S && valid) *reinterpret_cast<float4*>(p.S + (size_t)b * D + 4 * lig) = S;
@@ -124,21 +259,16 @@ __global__ void __launch_bounds__(kThreads) k_embed_fm_fwd_vec(const __grid_cons
             if (valid && lig == 0) p.fm_out[b] = fm;
         }
         if (p.lr_out) {
-            // logistic_regression.py:30-35: D = 1 lookup of every slot, summed; lanes of the group
-            // stride over the slots so one warp instruction carries 32 useful 4-byte gathers
-            float lr = 0.f;
-            if (valid) {
-#pragma unroll 4
-                for (int f = lig; f < F; f += LPR) {
-                    const int32_t r = __ldg(rb + f);
-                    if ((uint32_t)r < (uint64_t)p.R) lr += __ldg(p.table_lr + r);
+            // logistic_regression.py:30-35: D = 1 lookup of every slot, summed, + bias
+            if (valid)
+                for (int n = lig; n < Fn; n += LPR) {
+                    const float x = kStaged ? xb[n] : __ldg(xb + n);
+                    lr = fmaf(x, __ldg(p.dense_w_lr + p.meta.num_widx[n]), lr);
                 }
-                for (int n = lig; n < Fn; n += LPR)
-                    lr = fmaf(__ldg(p.dense_x + b * Fn + n), __ldg(p.dense_w_lr + n), lr);
-            }
             lr = group_sum<LPR>(lr);
             if (valid && lig == 0) p.lr_out[b] = lr + bias;
         }
+        if (kStaged) __syncwarp();   // every lane is done with slot `buf` before it is refilled
     }
 }
 
@@ -149,8 +279,8 @@ template <int KD>
 __global__ void __launch_bounds__(kThreads) k_embed_fm_fwd_scalar(const __grid_constant__ FwdParams p) {
     const int lane = threadIdx.x & 31;
     const int F = p.F, Fn = p.Fn, Ft = p.F + p.Fn, D = p.D;
-    const int64_t warp0 = (int64_t)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
-    const int64_t nwarps = (int64_t)gridDim.x * (kThreads / 32);
+    const int64_t warp0 = (int64_t)blockIdx.x * kWarps + (threadIdx.x >> 5);
+    const int64_t nwarps = (int64_t)gridDim.x * kWarps;
     const float bias = p.lr_bias ? __ldg(p.lr_bias) : 0.f;
 
     for (int64_t b = warp0; b < p.B; b += nwarps) {
@@ -166,13 +296,13 @@ __global__ void __launch_bounds__(kThreads) k_embed_fm_fwd_scalar(const __grid_c
             for (int k = 0; k < KD; ++k) {
                 const int d = lane + 32 * k;
                 if (d < D) {
-                    const float e = ok ? __ldg(p.table + (size_t)r * D + d) : 0.f;
+                    const float e = (ok && p.table) ? __ldg(p.table + (size_t)r * D + d) : 0.f;
                     S[k] += e;
                     Q[k] = fmaf(e, e, Q[k]);
                     if (Eo) Eo[d] = e;
                 }
             }
-            if (p.lr_out && ok && lane == (f & 31)) lr += __ldg(p.table_lr + r);
+            if (p.lr_out && ok && lane == (f & 31)) lr += __ldg(p.table_lr + (r + p.meta.lr_delta[f]));
         }
         for (int n = 0; n < Fn; ++n) {
             const float x = __ldg(p.dense_x + b * Fn + n);
@@ -181,13 +311,13 @@ __global__ void __launch_bounds__(kThreads) k_embed_fm_fwd_scalar(const __grid_c
             for (int k = 0; k < KD; ++k) {
                 const int d = lane + 32 * k;
                 if (d < D) {
-                    const float e = x * __ldg(p.dense_w + (size_t)n * D + d);
+                    const float e = p.dense_w ? x * __ldg(p.dense_w + (size_t)p.meta.num_widx[n] * D + d) : 0.f;
                     S[k] += e;
                     Q[k] = fmaf(e, e, Q[k]);
                     if (Eo) Eo[d] = e;
                 }
             }
-            if (p.lr_out && lane == (n & 31)) lr = fmaf(x, __ldg(p.dense_w_lr + n), lr);
+            if (p.lr_out && lane == (n & 31)) lr = fmaf(x, __ldg(p.dense_w_lr + p.meta.num_widx[n]), lr);
         }
         float fm = 0.f;
 #pragma unroll
@@ -210,24 +340,55 @@ __global__ void __launch_bounds__(kThreads) k_embed_fm_fwd_scalar(const __grid_c
 }
 
 // ---------------------------------------------------------------------------------------------
-// backward, categorical slots: g_e = dE + d_fm * (S - e)  ->  red.global.add into the grad table
+// backward, categorical slots: g_e = dE + d_fm * (S - e)  ->  red.global.add.v4 into the grad table
+// The upstream-gradient and saved-activation loads do not depend on the ids (only the reduction
+// address does), so they are issued for the whole chunk before anything is consumed.
 // ---------------------------------------------------------------------------------------------
-template <int LPR, int U>
-__global__ void __launch_bounds__(kThreads) k_embed_fm_bwd_vec(const __grid_constant__ BwdParams p) {
+template <int LPR, int U, bool kStaged>
+__global__ void __launch_bounds__(kThreads, RBX_BWD_MINB) k_embed_fm_bwd(const __grid_constant__ BwdParams p) {
     constexpr int D = 4 * LPR;
     constexpr int SPW = 32 / LPR;
-    const int lane = threadIdx.x & 31;
-    const int lig = lane & (LPR - 1);
-    const int gi = lane / LPR;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int lig = lane & (LPR - 1), gi = lane / LPR;
     const int F = p.F, Ft = p.F + p.Fn;
-    const int64_t warp0 = (int64_t)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
-    const int64_t nwarps = (int64_t)gridDim.x * (kThreads / 32);
     const bool has_fm = p.d_fm != nullptr;
+    const uint64_t pol_keep = l2_policy_evict_last(), pol_stream = l2_policy_evict_first();
+    (void)pol_keep; (void)pol_stream;
 
-    for (int64_t base = warp0 * SPW; base < p.B; base += nwarps * SPW) {
-        const int64_t b = base + gi;
+    const int wi = (SPW * F + 6) & ~3;
+    int32_t* my_idx = reinterpret_cast<int32_t*>(smem_raw) + (size_t)warp * 2 * wi;
+    uint64_t* my_bar = reinterpret_cast<uint64_t*>(smem_raw + (size_t)kWarps * 2 * wi * 4) + warp * 2;
+    const int64_t G = (p.B + SPW - 1) / SPW;
+    const int64_t gw = (int64_t)blockIdx.x * kWarps + warp, nw = (int64_t)gridDim.x * kWarps;
+    auto issue = [&](int64_t g, int buf) {
+        const int64_t b0 = g * SPW;
+        const int64_t ns = (p.B - b0 < SPW) ? p.B - b0 : SPW;
+        mbar_expect_tx(&my_bar[buf], stage_tx_bytes(b0 * F, ns * F));
+        stage_words(my_idx + (size_t)buf * wi, p.rows, b0 * F, ns * F, &my_bar[buf]);
+    };
+    if (kStaged) {
+        if (lane == 0) {
+            mbar_init(&my_bar[0], 1);
+            mbar_init(&my_bar[1], 1);
+            fence_mbar_init();
+            if (gw < G) issue(gw, 0);
+        }
+        __syncwarp();
+    }
+
+    int it = 0;
+    for (int64_t g = gw; g < G; g += nw, ++it) {
+        const int buf = it & 1;
+        const int64_t b0 = g * SPW;
+        if (kStaged) {
+            if (lane == 0 && g + nw < G) issue(g + nw, buf ^ 1);
+            mbar_wait(&my_bar[buf], (it >> 1) & 1);
+            __syncwarp();
+        }
+        const int64_t b = b0 + gi;
         const bool valid = b < p.B;
-        const int32_t* rb = p.rows + b * F;
+        const int32_t* rb = kStaged ? my_idx + (size_t)buf * wi + ((b0 * F) & 3) + gi * F : p.rows + b * F;
         const size_t eoff = (size_t)b * Ft * D + 4 * lig;
         float4 S = make_float4(0.f, 0.f, 0.f, 0.f);
         float dfm = 0.f;
@@ -235,45 +396,46 @@ __global__ void __launch_bounds__(kThreads) k_embed_fm_bwd_vec(const __grid_cons
             S = ld_stream_f4(p.S + (size_t)b * D + 4 * lig);
             dfm = __ldg(p.d_fm + b);
         }
-        if (p.g_table) {
-            for (int f0 = 0; f0 < F; f0 += U) {
-                int32_t r[U];
-                float4 e[U], g[U];
-#pragma unroll
-                for (int u = 0; u < U; ++u) {
-                    r[u] = -1;
-                    if (valid && f0 + u < F) {
-                        const int32_t t = __ldg(rb + f0 + u);
-                        if (t != p.pad_row[f0 + u] && (uint32_t)t < (uint64_t)p.R) r[u] = t;
-                    }
-                }
-#pragma unroll
-                for (int u = 0; u < U; ++u) {
-                    e[u] = g[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (r[u] >= 0) {
-                        const size_t o = eoff + (size_t)p.meta.cat_pos[f0 + u] * D;
-                        if (p.dE) g[u] = ld_stream_f4(p.dE + o);
-                        if (has_fm)
-                            e[u] = p.E ? ld_stream_f4(p.E + o) : ld_row_f4(p.table + (size_t)r[u] * D + 4 * lig);
-                    }
-                }
-#pragma unroll
-                for (int u = 0; u < U; ++u) {
-                    if (r[u] >= 0) {
-                        if (has_fm) g[u] = f4_fma(f4_sub(S, e[u]), dfm, g[u]);
-                        red_add_f4(p.g_table + (size_t)r[u] * D + 4 * lig, g[u]);
-                    }
-                }
-            }
-        }
         if (p.g_table_lr && p.d_lr && valid) {
             const float dlr = __ldg(p.d_lr + b);
 #pragma unroll 4
             for (int f = lig; f < F; f += LPR) {
-                const int32_t t = __ldg(rb + f);
-                if (t != p.pad_row[f] && (uint32_t)t < (uint64_t)p.R) red_add_f1(p.g_table_lr + t, dlr);
+                const int32_t r = kStaged ? rb[f] : __ldg(rb + f);
+                if (r != p.pad_row[f] && (uint32_t)r < (uint64_t)p.R) red_add_f1(p.g_table_lr + (r + p.meta.lr_delta[f]), dlr);
             }
         }
+        if (p.g_table) {
+            const bool from_table = has_fm && !p.E;
+            for (int f0 = 0; f0 < F; f0 += U) {
+                int32_t r[U];
+                float4 e[U], gr[U];
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    r[u] = -1;
+                    e[u] = gr[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (valid && f0 + u < F) {
+                        const size_t o = eoff + (size_t)p.meta.cat_pos[f0 + u] * D;
+                        if (p.dE) gr[u] = LD_STREAM(p.dE + o);
+                        if (has_fm && p.E) e[u] = LD_STREAM(p.E + o);
+                        const int32_t tr = kStaged ? rb[f0 + u] : __ldg(rb + f0 + u);
+                        if (tr != p.pad_row[f0 + u] && (uint32_t)tr < (uint64_t)p.R) r[u] = tr;
+                    }
+                }
+                if (from_table) {
+#pragma unroll
+                    for (int u = 0; u < U; ++u)
+                        if (r[u] >= 0) e[u] = LD_ROW(p.table + (size_t)r[u] * D + 4 * lig);
+                }
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    if (r[u] >= 0) {
+                        if (has_fm) gr[u] = f4_fma(f4_sub(S, e[u]), dfm, gr[u]);
+                        RED_ROW(p.g_table + (size_t)r[u] * D + 4 * lig, gr[u]);
+                    }
+                }
+            }
+        }
+        if (kStaged) __syncwarp();
     }
 }
 
@@ -281,8 +443,8 @@ __global__ void __launch_bounds__(kThreads) k_embed_fm_bwd_vec(const __grid_cons
 __global__ void __launch_bounds__(kThreads) k_embed_fm_bwd_scalar(const __grid_constant__ BwdParams p) {
     const int lane = threadIdx.x & 31;
     const int F = p.F, Ft = p.F + p.Fn, D = p.D;
-    const int64_t warp0 = (int64_t)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
-    const int64_t nwarps = (int64_t)gridDim.x * (kThreads / 32);
+    const int64_t warp0 = (int64_t)blockIdx.x * kWarps + (threadIdx.x >> 5);
+    const int64_t nwarps = (int64_t)gridDim.x * kWarps;
     const bool has_fm = p.d_fm != nullptr;
     for (int64_t b = warp0; b < p.B; b += nwarps) {
         const float dfm = has_fm ? __ldg(p.d_fm + b) : 0.f;
@@ -301,28 +463,87 @@ __global__ void __launch_bounds__(kThreads) k_embed_fm_bwd_scalar(const __grid_c
                     red_add_f1(p.g_table + (size_t)r * D + d, g);
                 }
             }
-            if (p.g_table_lr && p.d_lr && lane == 0) red_add_f1(p.g_table_lr + r, dlr);
+            if (p.g_table_lr && p.d_lr && lane == 0) red_add_f1(p.g_table_lr + (r + p.meta.lr_delta[f]), dlr);
         }
     }
 }
 
 // ---------------------------------------------------------------------------------------------
-// backward, numeric slots + bias: batch reductions.  Role r of a CTA column:
-//   r <  Fn*D            : g_dense_w[n,d]   += sum_b x[b,n] * (dE[b,pos_n,d] + d_fm[b]*(S[b,d] - x[b,n] w[n,d]))
-//   r <  Fn*D + Fn       : g_dense_w_lr[n]  += sum_b x[b,n] * d_lr[b]
-//   r == Fn*D + Fn       : g_lr_bias        += sum_b d_lr[b]
-// Each thread keeps one fp32 partial over its CTA's samples, then one atomic per thread.
+// backward, numeric slots + bias: batch reductions (no gather, pure streaming)
+//   g_dense_w[n,:]  += sum_b x[b,n] * (dE[b,pos_n,:] + d_fm[b]*(S[b,:] - x[b,n] w[n,:]))
+//   g_dense_w_lr[n] += sum_b x[b,n] * d_lr[b] ;  g_lr_bias += sum_b d_lr[b]
+// Vector kernel (D % 4 == 0): thread <-> (sample lane `sub`, slot n, float4 column c); SUB sample
+// lanes per CTA run in parallel, partials meet in shared memory, one red per (n, c) per CTA.
+// The first-order roles follow in the same launch.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kThreads) k_dense_w_bwd(const __grid_constant__ BwdParams p) {
+__global__ void __launch_bounds__(kThreads) k_dense_w_bwd_vec(const __grid_constant__ BwdParams p) {
+    __shared__ float4 s_acc[kThreads];
+    __shared__ float s_lr[RBX_MAX_SLOTS + 1];
+    for (int i = threadIdx.x; i <= p.Fn; i += kThreads) s_lr[i] = 0.f;
+    const int Fn = p.Fn, D = p.D, Ft = p.F + p.Fn, V = D / 4;
+    const int R4 = Fn * V;                       // vector roles (<= kThreads, host-checked)
+    const int SUB = kThreads / R4;               // sample lanes
+    const int t = threadIdx.x;
+    const bool has_fm = p.d_fm != nullptr;
+    if (t < SUB * R4) {
+        const int sub = t / R4, role = t - sub * R4;
+        const int n = role / V, c = role - n * V;
+        const size_t wo = (size_t)p.meta.num_widx[n] * D + 4 * c;
+        const float4 w = p.dense_w ? ld_row_f4(p.dense_w + wo) : make_float4(0.f, 0.f, 0.f, 0.f);
+        const size_t po = (size_t)p.meta.num_pos[n] * D + 4 * c;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (p.g_dense_w) {
+#pragma unroll 4
+            for (int64_t b = (int64_t)blockIdx.x * SUB + sub; b < p.B; b += (int64_t)gridDim.x * SUB) {
+                const float x = __ldg(p.dense_x + b * Fn + n);
+                float4 g = p.dE ? ld_stream_f4(p.dE + (size_t)b * Ft * D + po) : make_float4(0.f, 0.f, 0.f, 0.f);
+                if (has_fm) {
+                    const float4 s4 = ld_row_f4(p.S + (size_t)b * D + 4 * c);
+                    g = f4_fma(f4_sub(s4, f4_scale(w, x)), __ldg(p.d_fm + b), g);
+                }
+                acc = f4_fma(g, x, acc);
+            }
+        }
+        s_acc[t] = acc;
+    }
+    __syncthreads();
+    if (t < R4 && p.g_dense_w) {
+        float4 a = s_acc[t];
+        for (int sub = 1; sub < SUB; ++sub) a = f4_add(a, s_acc[sub * R4 + t]);
+        const int n = t / V, c = t - n * V;
+        red_add_f4(p.g_dense_w + (size_t)p.meta.num_widx[n] * D + 4 * c, a);
+    }
+    // first-order roles, all threads: role j < Fn -> g_dense_w_lr[j]; j == Fn -> bias; `lanes` sample
+    // lanes per role meet in shared memory, one global atomic per role per CTA
+    if (p.d_lr && (p.g_dense_w_lr || p.g_lr_bias)) {
+        const int roles = Fn + 1, lanes = kThreads / roles;
+        if (t < lanes * roles) {
+            const int ln = t / roles, j = t - ln * roles;
+            float acc = 0.f;
+#pragma unroll 4
+            for (int64_t b = (int64_t)blockIdx.x * lanes + ln; b < p.B; b += (int64_t)gridDim.x * lanes)
+                acc = fmaf(j < Fn ? __ldg(p.dense_x + b * Fn + j) : 1.f, __ldg(p.d_lr + b), acc);
+            atomicAdd(&s_lr[j], acc);
+        }
+        __syncthreads();
+        if (t < Fn && p.g_dense_w_lr) atomicAdd(p.g_dense_w_lr + p.meta.num_widx[t], s_lr[t]);
+        if (t == Fn && p.g_lr_bias) atomicAdd(p.g_lr_bias, s_lr[t]);
+    }
+}
+
+// generic scalar kernel: role r of a CTA column (any D, any Fn); also covers the first-order roles
+// when the vector kernel has no spare threads (first_role selects where to start)
+__global__ void __launch_bounds__(kThreads) k_dense_w_bwd(const __grid_constant__ BwdParams p, int first_role) {
     const int Fn = p.Fn, D = p.D, Ft = p.F + p.Fn;
-    const int role = blockIdx.y * kThreads + threadIdx.x;
+    const int role = first_role + blockIdx.y * kThreads + threadIdx.x;
     const int n_w = Fn * D;
     if (role > n_w + Fn) return;
     float acc = 0.f;
     if (role < n_w) {
         if (!p.g_dense_w) return;
         const int n = role / D, d = role - n * D;
-        const float w = __ldg(p.dense_w + role);
+        const size_t wo = (size_t)p.meta.num_widx[n] * D + d;
+        const float w = p.dense_w ? __ldg(p.dense_w + wo) : 0.f;
         const size_t po = (size_t)p.meta.num_pos[n] * D + d;
         const bool has_fm = p.d_fm != nullptr;
 #pragma unroll 4
@@ -332,14 +553,14 @@ __global__ void __launch_bounds__(kThreads) k_dense_w_bwd(const __grid_constant_
             if (has_fm) g = fmaf(__ldg(p.S + (size_t)b * D + d) - x * w, __ldg(p.d_fm + b), g);
             acc = fmaf(x, g, acc);
         }
-        atomicAdd(p.g_dense_w + role, acc);
+        atomicAdd(p.g_dense_w + wo, acc);
     } else if (role < n_w + Fn) {
         if (!p.g_dense_w_lr || !p.d_lr) return;
         const int n = role - n_w;
 #pragma unroll 4
         for (int64_t b = blockIdx.x; b < p.B; b += gridDim.x)
             acc = fmaf(__ldg(p.dense_x + b * Fn + n), __ldg(p.d_lr + b), acc);
-        atomicAdd(p.g_dense_w_lr + n, acc);
+        atomicAdd(p.g_dense_w_lr + p.meta.num_widx[n], acc);
     } else {
         if (!p.g_lr_bias || !p.d_lr) return;
 #pragma unroll 4
@@ -351,27 +572,38 @@ __global__ void __launch_bounds__(kThreads) k_dense_w_bwd(const __grid_constant_
 // ---------------------------------------------------------------------------------------------
 // launch helpers
 // ---------------------------------------------------------------------------------------------
-// occupancy-capped persistent grid: min(CTAs needed, SMs x resident CTAs/SM), cached per kernel
-int grid_for(const void* kernel, int64_t warps_needed) {
-    struct Slot { const void* k; int occ; };
-    static thread_local Slot cache[32];
+// resident CTAs per SM for (kernel, dynamic smem), cached per (kernel, smem)
+int occupancy(const void* kernel, size_t smem) {
+    struct Slot { const void* k; size_t smem; int occ; };
+    static thread_local Slot cache[64];
     static thread_local int n_cache = 0;
-    int occ = 0;
     for (int i = 0; i < n_cache; ++i)
-        if (cache[i].k == kernel) occ = cache[i].occ;
-    if (occ == 0) {
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, kThreads, 0) != cudaSuccess || occ <= 0) occ = 4;
-        if (n_cache < 32) cache[n_cache++] = Slot{kernel, occ};
+        if (cache[i].k == kernel && cache[i].smem == smem) return cache[i].occ;
+    int occ = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, kThreads, smem) != cudaSuccess || occ <= 0) {
+        cudaGetLastError();
+        occ = 2;
     }
-    int64_t ctas = (warps_needed + kThreads / 32 - 1) / (kThreads / 32);
-    const int64_t cap = (int64_t)rbx_sm_count() * occ;
-    if (ctas > cap) ctas = cap;
-    if (ctas < 1) ctas = 1;
-    return (int)ctas;
+    if (n_cache < 64) cache[n_cache++] = Slot{kernel, smem, occ};
+    return occ;
 }
 
-int fill_meta(SlotMeta& m, const int32_t* cat_pos, int F, const int32_t* num_pos, int Fn, const char* who) {
+int grid_for(const void* kernel, size_t smem, int64_t warps_needed) {
+    int64_t ctas = (warps_needed + kWarps - 1) / kWarps;
+    const int64_t cap = (int64_t)rbx_sm_count() * occupancy(kernel, smem);
+    if (ctas > cap) ctas = cap;
+    return ctas < 1 ? 1 : (int)ctas;
+}
+
+int fill_meta(SlotMeta& m, const int32_t* cat_pos, int F, const int32_t* num_pos, int Fn, const int32_t* num_widx,
+              const int32_t* lr_delta, const char* who) {
     const int Ft = F + Fn;
+    for (int f = 0; f < F; ++f) m.lr_delta[f] = lr_delta ? lr_delta[f] : 0;
+    for (int n = 0; n < Fn; ++n) {
+        const int w = num_widx ? num_widx[n] : n;
+        if (w < 0 || w > INT16_MAX) return rbx_fail(RBX_ERR_ARG, "%s: num_widx[%d]=%d", who, n, w);
+        m.num_widx[n] = (int16_t)w;
+    }
     for (int f = 0; f < F; ++f) {
         if (cat_pos[f] < 0 || cat_pos[f] >= Ft) return rbx_fail(RBX_ERR_ARG, "%s: cat_pos[%d]=%d outside [0,%d)", who, f, cat_pos[f], Ft);
         m.cat_pos[f] = (int16_t)cat_pos[f];
@@ -383,57 +615,95 @@ int fill_meta(SlotMeta& m, const int32_t* cat_pos, int F, const int32_t* num_pos
     return RBX_OK;
 }
 
-template <int LPR, int U>
-void launch_fwd_vec(const FwdParams& p, cudaStream_t st) {
-    constexpr int SPW = 32 / LPR;
-    const int grid = grid_for((const void*)k_embed_fm_fwd_vec<LPR, U>, (p.B + SPW - 1) / SPW);
-    k_embed_fm_fwd_vec<LPR, U><<<grid, kThreads, 0, st>>>(p);
+// dynamic shared memory of the staged kernels: kWarps x 2 buffers of (SPW*words + skew slack) + barriers
+size_t staged_smem(int spw, int F, int Fn) {
+    const size_t wi = ((size_t)spw * F + 6) & ~(size_t)3, wx = Fn ? (((size_t)spw * Fn + 6) & ~(size_t)3) : 0;
+    return (size_t)kWarps * 2 * (wi + wx) * 4 + (size_t)kWarps * 2 * 8;
 }
+
+template <typename K>
+int set_smem_limit(K kernel, size_t smem) {
+    if (smem > 48 * 1024) {
+        if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
+    }
+    return 0;
+}
+
+template <int LPR, int U>
+void launch_fwd(FwdParams& p, bool staged, cudaStream_t st) {
+    constexpr int SPW = 32 / LPR;
+    const int64_t groups = (p.B + SPW - 1) / SPW;
+    if (staged) {
+        const size_t smem = staged_smem(SPW, p.F, p.Fn);
+        if (smem <= 200 * 1024 && set_smem_limit(k_embed_fm_fwd<LPR, U, true>, smem) == 0) {
+            const int grid = grid_for((const void*)k_embed_fm_fwd<LPR, U, true>, smem, groups);
+            k_embed_fm_fwd<LPR, U, true><<<grid, kThreads, smem, st>>>(p);
+            return;
+        }
+    }
+    const int grid = grid_for((const void*)k_embed_fm_fwd<LPR, U, false>, 0, groups);
+    k_embed_fm_fwd<LPR, U, false><<<grid, kThreads, 0, st>>>(p);
+}
+
 template <int KD>
 void launch_fwd_scalar(const FwdParams& p, cudaStream_t st) {
-    const int grid = grid_for((const void*)k_embed_fm_fwd_scalar<KD>, p.B);
+    const int grid = grid_for((const void*)k_embed_fm_fwd_scalar<KD>, 0, p.B);
     k_embed_fm_fwd_scalar<KD><<<grid, kThreads, 0, st>>>(p);
 }
+
 template <int LPR, int U>
-void launch_bwd_vec(const BwdParams& p, cudaStream_t st) {
+void launch_bwd(BwdParams& p, bool staged, cudaStream_t st) {
     constexpr int SPW = 32 / LPR;
-    const int grid = grid_for((const void*)k_embed_fm_bwd_vec<LPR, U>, (p.B + SPW - 1) / SPW);
-    k_embed_fm_bwd_vec<LPR, U><<<grid, kThreads, 0, st>>>(p);
+    const int64_t groups = (p.B + SPW - 1) / SPW;
+    if (staged) {
+        const size_t smem = staged_smem(SPW, p.F, 0);
+        if (smem <= 200 * 1024 && set_smem_limit(k_embed_fm_bwd<LPR, U, true>, smem) == 0) {
+            const int grid = grid_for((const void*)k_embed_fm_bwd<LPR, U, true>, smem, groups);
+            k_embed_fm_bwd<LPR, U, true><<<grid, kThreads, smem, st>>>(p);
+            return;
+        }
+    }
+    const int grid = grid_for((const void*)k_embed_fm_bwd<LPR, U, false>, 0, groups);
+    k_embed_fm_bwd<LPR, U, false><<<grid, kThreads, 0, st>>>(p);
 }
+
+inline bool al16(const void* p) { return (uintptr_t)p % 16 == 0; }
 
 }  // namespace
 
 extern "C" {
 
 int rbx_embed_fm_fwd(const float* table, const float* table_lr, const int32_t* rows, const int32_t* cat_pos,
-                     const float* dense_x, const float* dense_w, const float* dense_w_lr, const int32_t* num_pos,
-                     const float* lr_bias, float* E, float* S, float* fm_out, float* lr_out, int64_t B, int64_t R,
-                     int F, int Fn, int D, rbx_stream_t stream) {
+                     const int32_t* lr_delta, const float* dense_x, const float* dense_w, const float* dense_w_lr,
+                     const int32_t* num_pos, const int32_t* num_widx, const float* lr_bias, float* E, float* S,
+                     float* fm_out, float* lr_out, int64_t B, int64_t R, int F, int Fn, int D, rbx_stream_t stream) {
     const char* who = "rbx_embed_fm_fwd";
     RBX_REQUIRE(B >= 0 && F >= 0 && Fn >= 0 && D >= 1, "%s: negative size", who);
     RBX_REQUIRE(F <= RBX_MAX_SLOTS && Fn <= RBX_MAX_SLOTS, "%s: more than %d slots", who, RBX_MAX_SLOTS);
     RBX_REQUIRE(D <= RBX_MAX_DIM, "%s: D=%d > %d", who, D, RBX_MAX_DIM);
     RBX_REQUIRE(R >= 0 && R <= INT32_MAX, "%s: R=%lld outside int32 row ids", who, (long long)R);
     if (B == 0 || F + Fn == 0) return RBX_OK;
-    RBX_REQUIRE(F == 0 || (table && rows && cat_pos), "%s: table/rows/cat_pos required when F > 0", who);
-    RBX_REQUIRE(Fn == 0 || (dense_x && dense_w && num_pos), "%s: dense_x/dense_w/num_pos required when Fn > 0", who);
+    const bool lr_only = !E && !S && !fm_out;   // LogisticRegression alone: no D-dim tables needed
+    RBX_REQUIRE(F == 0 || (rows && cat_pos && (table || lr_only)), "%s: table/rows/cat_pos required when F > 0", who);
+    RBX_REQUIRE(Fn == 0 || (dense_x && num_pos && (dense_w || lr_only)), "%s: dense_x/dense_w/num_pos required when Fn > 0", who);
     RBX_REQUIRE(!lr_out || ((F == 0 || table_lr) && (Fn == 0 || dense_w_lr)), "%s: lr_out needs table_lr / dense_w_lr", who);
+    if (lr_only) { table = nullptr; dense_w = nullptr; D = 16; }
     FwdParams p;
     p.table = table; p.table_lr = table_lr; p.rows = rows; p.dense_x = dense_x; p.dense_w = dense_w;
     p.dense_w_lr = dense_w_lr; p.lr_bias = lr_bias; p.E = E; p.S = S; p.fm_out = fm_out; p.lr_out = lr_out;
     p.B = B; p.R = R; p.F = F; p.Fn = Fn; p.D = D;
-    if (int rc = fill_meta(p.meta, cat_pos, F, num_pos, Fn, who)) return rc;
+    if (int rc = fill_meta(p.meta, cat_pos, F, num_pos, Fn, num_widx, lr_delta, who)) return rc;
     cudaStream_t st = rbx_cast_stream(stream);
-    const bool aligned = ((uintptr_t)table % 16 == 0) && ((uintptr_t)dense_w % 16 == 0) && ((uintptr_t)E % 16 == 0) &&
-                         ((uintptr_t)S % 16 == 0);
+    const bool aligned = al16(table) && al16(dense_w) && al16(E) && al16(S);
     if (D % 4 == 0 && D <= 128 && (D & (D - 1)) == 0 && aligned) {
+        const bool staged = al16(rows) && al16(dense_x);
         switch (D / 4) {
-            case 1: launch_fwd_vec<1, 8>(p, st); break;
-            case 2: launch_fwd_vec<2, 8>(p, st); break;
-            case 4: launch_fwd_vec<4, 8>(p, st); break;
-            case 8: launch_fwd_vec<8, 8>(p, st); break;
-            case 16: launch_fwd_vec<16, 8>(p, st); break;
-            default: launch_fwd_vec<32, 8>(p, st); break;
+            case 1: launch_fwd<1, RBX_FWD_U>(p, staged, st); break;
+            case 2: launch_fwd<2, RBX_FWD_U>(p, staged, st); break;
+            case 4: launch_fwd<4, RBX_FWD_U>(p, staged, st); break;
+            case 8: launch_fwd<8, RBX_FWD_U>(p, staged, st); break;
+            case 16: launch_fwd<16, RBX_FWD_U>(p, staged, st); break;
+            default: launch_fwd<32, RBX_FWD_U>(p, staged, st); break;
         }
     } else {
         const int kd = (D + 31) / 32;
@@ -448,10 +718,10 @@ int rbx_embed_fm_fwd(const float* table, const float* table_lr, const int32_t* r
 }
 
 int rbx_embed_fm_bwd(const float* table, const int32_t* rows, const int32_t* cat_pos, const int32_t* pad_row,
-                     const float* dense_x, const float* dense_w, const int32_t* num_pos, const float* E,
-                     const float* S, const float* dE, const float* d_fm, const float* d_lr, float* g_table,
-                     float* g_table_lr, float* g_dense_w, float* g_dense_w_lr, float* g_lr_bias, int64_t B,
-                     int64_t R, int F, int Fn, int D, rbx_stream_t stream) {
+                     const int32_t* lr_delta, const float* dense_x, const float* dense_w, const int32_t* num_pos,
+                     const int32_t* num_widx, const float* E, const float* S, const float* dE, const float* d_fm,
+                     const float* d_lr, float* g_table, float* g_table_lr, float* g_dense_w, float* g_dense_w_lr,
+                     float* g_lr_bias, int64_t B, int64_t R, int F, int Fn, int D, rbx_stream_t stream) {
     const char* who = "rbx_embed_fm_bwd";
     RBX_REQUIRE(B >= 0 && F >= 0 && Fn >= 0 && D >= 1, "%s: negative size", who);
     RBX_REQUIRE(F <= RBX_MAX_SLOTS && Fn <= RBX_MAX_SLOTS, "%s: more than %d slots", who, RBX_MAX_SLOTS);
@@ -459,43 +729,63 @@ int rbx_embed_fm_bwd(const float* table, const int32_t* rows, const int32_t* cat
     RBX_REQUIRE(R >= 0 && R <= INT32_MAX, "%s: R=%lld outside int32 row ids", who, (long long)R);
     if (B == 0 || F + Fn == 0) return RBX_OK;
     RBX_REQUIRE(F == 0 || (rows && cat_pos), "%s: rows/cat_pos required when F > 0", who);
-    RBX_REQUIRE(Fn == 0 || (dense_x && dense_w && num_pos), "%s: dense_x/dense_w/num_pos required when Fn > 0", who);
+    const bool lr_only = !dE && !d_fm;
+    RBX_REQUIRE(Fn == 0 || (dense_x && num_pos && (dense_w || lr_only)), "%s: dense_x/dense_w/num_pos required when Fn > 0", who);
     RBX_REQUIRE(!d_fm || S, "%s: S (saved by the forward) required with d_fm", who);
+    if (lr_only) { g_table = nullptr; g_dense_w = nullptr; if (!table && !E) D = 16; }
     RBX_REQUIRE(!d_fm || E || table || F == 0, "%s: E or table required with d_fm", who);
     BwdParams p;
     p.table = table; p.rows = rows; p.dense_x = dense_x; p.dense_w = dense_w; p.E = E; p.S = S; p.dE = dE;
     p.d_fm = d_fm; p.d_lr = d_lr; p.g_table = g_table; p.g_table_lr = g_table_lr; p.g_dense_w = g_dense_w;
     p.g_dense_w_lr = g_dense_w_lr; p.g_lr_bias = g_lr_bias; p.B = B; p.R = R; p.F = F; p.Fn = Fn; p.D = D;
-    if (int rc = fill_meta(p.meta, cat_pos, F, num_pos, Fn, who)) return rc;
+    if (int rc = fill_meta(p.meta, cat_pos, F, num_pos, Fn, num_widx, lr_delta, who)) return rc;
     for (int f = 0; f < F; ++f) p.pad_row[f] = pad_row ? pad_row[f] : -1;
     cudaStream_t st = rbx_cast_stream(stream);
 
     if (F > 0 && (g_table || (g_table_lr && d_lr)) && (dE || d_fm || d_lr)) {
-        const bool aligned = ((uintptr_t)table % 16 == 0) && ((uintptr_t)E % 16 == 0) && ((uintptr_t)S % 16 == 0) &&
-                             ((uintptr_t)dE % 16 == 0) && ((uintptr_t)g_table % 16 == 0);
+        const bool aligned = al16(table) && al16(E) && al16(S) && al16(dE) && al16(g_table);
         if (D % 4 == 0 && D <= 128 && (D & (D - 1)) == 0 && aligned) {
+            const bool staged = al16(rows);
             switch (D / 4) {
-                case 1: launch_bwd_vec<1, 8>(p, st); break;
-                case 2: launch_bwd_vec<2, 8>(p, st); break;
-                case 4: launch_bwd_vec<4, 8>(p, st); break;
-                case 8: launch_bwd_vec<8, 8>(p, st); break;
-                case 16: launch_bwd_vec<16, 4>(p, st); break;
-                default: launch_bwd_vec<32, 4>(p, st); break;
+                case 1: launch_bwd<1, RBX_BWD_U>(p, staged, st); break;
+                case 2: launch_bwd<2, RBX_BWD_U>(p, staged, st); break;
+                case 4: launch_bwd<4, RBX_BWD_U>(p, staged, st); break;
+                case 8: launch_bwd<8, RBX_BWD_U>(p, staged, st); break;
+                case 16: launch_bwd<16, RBX_BWD_U>(p, staged, st); break;
+                default: launch_bwd<32, RBX_BWD_U>(p, staged, st); break;
             }
         } else {
-            const int grid = grid_for((const void*)k_embed_fm_bwd_scalar, B);
+            const int grid = grid_for((const void*)k_embed_fm_bwd_scalar, 0, B);
             k_embed_fm_bwd_scalar<<<grid, kThreads, 0, st>>>(p);
         }
         RBX_LAUNCH_CHECK(who);
     }
-    const bool want_dense = (Fn > 0 && ((g_dense_w && (dE || d_fm)) || (g_dense_w_lr && d_lr))) || (g_lr_bias && d_lr);
-    if (want_dense) {
-        const int roles = Fn * D + Fn + 1;
-        int gx = rbx_sm_count() * 4;
-        if (gx > B) gx = (int)B;
-        dim3 grid(gx, (roles + kThreads - 1) / kThreads);
-        k_dense_w_bwd<<<grid, kThreads, 0, st>>>(p);
-        RBX_LAUNCH_CHECK(who);
+    const bool want_w = Fn > 0 && g_dense_w && (dE || d_fm);
+    const bool want_lr = d_lr && ((Fn > 0 && g_dense_w_lr) || g_lr_bias);
+    if (want_w || want_lr) {
+        int first_scalar_role = 0;        // roles still to be covered by the scalar kernel
+        bool scalar_needed = true;
+        const int R4 = Fn * (D / 4);
+        const bool vec = want_w && D % 4 == 0 && R4 >= 1 && R4 <= kThreads && al16(dense_w) && al16(dE) && al16(S) && al16(g_dense_w);
+        if (vec) {
+            const int SUB = kThreads / R4;
+            int64_t gx = (B + SUB - 1) / SUB;
+            const int64_t cap = (int64_t)rbx_sm_count() * 8;
+            if (gx > cap) gx = cap;
+            k_dense_w_bwd_vec<<<(int)gx, kThreads, 0, st>>>(p);
+            RBX_LAUNCH_CHECK(who);
+            scalar_needed = false;                      // the vector kernel also covers the first-order roles
+        } else if (!want_w) {
+            first_scalar_role = Fn * D;
+        }
+        if (scalar_needed) {
+            const int roles = Fn * D + Fn + 1 - first_scalar_role;
+            int gx = rbx_sm_count() * 8;
+            if (gx > B) gx = (int)B;
+            dim3 grid(gx, (roles + kThreads - 1) / kThreads);
+            k_dense_w_bwd<<<grid, kThreads, 0, st>>>(p, first_scalar_role);
+            RBX_LAUNCH_CHECK(who);
+        }
     }
     return RBX_OK;
 }

@@ -1,0 +1,1033 @@
+"""The reference's layer / operator API on the fused B200 path.
+
+Same class names, constructor arguments, state_dict keys and output shapes as
+
+  recbox/ranking/pytorch/layers : FeatureEmbedding, FeatureEmbeddingDict        (embeddings/feature_embedding.py:28-214)
+                                  InnerProductInteraction                       (interactions/inner_product.py:22-56)
+                                  LogisticRegression, FactorizationMachine      (blocks/logistic_regression.py:23-35,
+                                                                                 blocks/factorization_machine.py:24-34)
+                                  MaskedAveragePooling, MaskedSumPooling        (pooling.py:22-40)
+  recbox/core/pytorch/layers    : EmbeddingLayer, EmbeddingDictLayer            (embedding.py:10-138)
+                                  MaskedAveragePooling, MaskedSumPooling        (sequence.py:4-20)   [Core* classes]
+
+so that existing model code and configs load unchanged (`recbox_b200.install()` rebinds the
+reference's symbols).  What differs is underneath:
+
+  * every per-feature nn.Embedding / nn.Linear(1, D) is still there under
+    `embedding_layers.<feature>` (same parameter names, same init order under a given seed, same
+    `type(v) == nn.Embedding` the reference's init / regulariser code scans for), but all of them
+    are VIEWS into one fused [sum V_f, D] table (+ one [Fn, D] block for the numeric slots);
+  * a forward is one launch of the fused gather (+ FM product_sum + LR) kernel writing [B, F, D]
+    in place -- no per-feature lookups, no torch.stack; the backward is one scatter-add launch
+    whose dense gradients are handed to autograd as views of one fused gradient buffer;
+  * FactorizationMachine / InnerProductInteraction("product_sum") / LogisticRegression called on
+    the tensors produced here return the values the same launch already computed.
+
+There is no CPU path: the modules raise if their parameters or inputs are not on a CUDA device.
+"""
+import weakref
+from collections import OrderedDict
+from functools import partial  # noqa: F401  (used by eval'd initializer strings, as in the reference)
+
+import numpy as np
+import torch
+from torch import nn
+
+from . import ops
+from ._lib import RbxError
+
+I32, F32 = torch.int32, torch.float32
+
+
+# =================================================================================================
+# pooling layers (feature_encoder / embedding_callback targets)
+# =================================================================================================
+class _PoolFn(torch.autograd.Function):
+    """[B,L,D] -> [B,D] pooling of an already materialised tensor, forward via torch reductions is
+    NOT used: this path is the plain-tensor entry (someone calls the pooling module directly on an
+    embedding tensor); the fused id -> pooled path lives in _PooledGatherFn."""
+
+    @staticmethod
+    def forward(ctx, emb, mask, average):
+        s = emb.sum(dim=1)
+        if not average:
+            ctx.save_for_backward()
+            ctx.meta = (emb.shape, None)
+            return s
+        if mask is None:
+            mask = emb.sum(dim=-1) != 0
+        den = mask.float().sum(-1, keepdim=True) + 1e-12
+        ctx.save_for_backward(den)
+        ctx.meta = (emb.shape, True)
+        return s / den
+
+    @staticmethod
+    def backward(ctx, g):
+        shape, avg = ctx.meta
+        if avg:
+            (den,) = ctx.saved_tensors
+            g = g / den
+        return g.unsqueeze(1).expand(shape), None, None
+
+
+class MaskedAveragePooling(nn.Module):
+    """ranking/pytorch/layers/pooling.py:22-31: sum over L / (#rows with non-zero element sum + 1e-12)."""
+
+    def __init__(self):
+        super(MaskedAveragePooling, self).__init__()
+
+    def forward(self, embedding_matrix, mask=None):
+        return _PoolFn.apply(embedding_matrix, mask, True)
+
+
+class MaskedSumPooling(nn.Module):
+    """ranking/pytorch/layers/pooling.py:34-40."""
+
+    def __init__(self):
+        super(MaskedSumPooling, self).__init__()
+
+    def forward(self, embedding_matrix):
+        return _PoolFn.apply(embedding_matrix, None, False)
+
+
+class CoreMaskedAveragePooling(MaskedAveragePooling):
+    """core/pytorch/layers/sequence.py:4-12 (no mask argument)."""
+
+    def forward(self, embedding_matrix):
+        return _PoolFn.apply(embedding_matrix, None, True)
+
+
+CoreMaskedSumPooling = MaskedSumPooling
+
+
+def _pool_mode(module):
+    """0 = sum, 1 = masked average, None = not one of ours (generic encoder)."""
+    if type(module) in (MaskedAveragePooling, CoreMaskedAveragePooling):
+        return 1
+    if type(module) is MaskedSumPooling:
+        return 0
+    return None
+
+
+# =================================================================================================
+# fused parameter storage
+# =================================================================================================
+class _Group(object):
+    """All unique embedding modules of one embedding dim, stored back to back."""
+
+    def __init__(self, D):
+        self.D = D
+        self.emb, self.emb_off, self.R = [], {}, 0        # nn.Embedding modules, id(module) -> row offset
+        self.lin, self.lin_idx = [], {}                   # nn.Linear(1, D) modules, id(module) -> row of dense_w
+        self.table = None                                  # [R, D]
+        self.dense_w = None                                # [Fn, D]
+        self.ptrs = None
+
+
+class _FusedStore(object):
+    """Keeps the Parameters of a ModuleDict of nn.Embedding / nn.Linear(1, D) pointing into one
+    allocation per embedding dim.  Parameter identity never changes (optimizers, state_dict,
+    named_parameters, DDP hooks all see the reference's per-feature parameters)."""
+
+    def __init__(self, modules):
+        self.groups = OrderedDict()
+        seen = set()
+        for m in modules:
+            if id(m) in seen:
+                continue
+            seen.add(id(m))
+            if isinstance(m, nn.Embedding):
+                g = self.groups.setdefault(m.embedding_dim, _Group(m.embedding_dim))
+                g.emb_off[id(m)] = g.R
+                g.emb.append(m)
+                g.R += m.num_embeddings
+            elif isinstance(m, nn.Linear):
+                g = self.groups.setdefault(m.out_features, _Group(m.out_features))
+                g.lin_idx[id(m)] = len(g.lin)
+                g.lin.append(m)
+        self.fuse()
+
+    def fuse(self):
+        for g in self.groups.values():
+            ref = (g.emb[0] if g.emb else g.lin[0]).weight
+            dev, dt = ref.device, ref.dtype
+            if g.R > 2 ** 31 - 1:
+                raise RbxError("fused table of %d rows exceeds int32 row ids" % g.R)
+            if g.emb:
+                table = torch.empty((g.R, g.D), dtype=dt, device=dev)
+                for m in g.emb:
+                    o = g.emb_off[id(m)]
+                    view = table[o:o + m.num_embeddings]
+                    view.copy_(m.weight.data)
+                    m.weight.data = view
+                g.table = table
+            if g.lin:
+                dw = torch.empty((len(g.lin), g.D), dtype=dt, device=dev)
+                for m in g.lin:
+                    i = g.lin_idx[id(m)]
+                    dw[i].copy_(m.weight.data.reshape(-1))
+                    m.weight.data = dw[i].view(g.D, 1)
+                g.dense_w = dw
+            g.ptrs = self._expected(g)
+
+    @staticmethod
+    def _expected(g):
+        out = []
+        if g.emb:
+            base, es = g.table.data_ptr(), g.table.element_size()
+            out += [base + g.emb_off[id(m)] * g.D * es for m in g.emb]
+        if g.lin:
+            base, es = g.dense_w.data_ptr(), g.dense_w.element_size()
+            out += [base + g.lin_idx[id(m)] * g.D * es for m in g.lin]
+        return out
+
+    def ensure(self):
+        """Re-fuse if someone re-pointed a parameter (module.to(), weight = Parameter(...), ...)."""
+        for g in self.groups.values():
+            if [m.weight.data_ptr() for m in g.emb] + [m.weight.data_ptr() for m in g.lin] != g.ptrs:
+                self.fuse()
+                return
+
+
+# =================================================================================================
+# the autograd node around the two fused kernels
+# =================================================================================================
+class _Call(object):
+    """Static description of one fused launch (built once per feature selection, cached)."""
+    __slots__ = ("D", "F", "Fn", "Ft", "cat_pos", "num_pos", "num_widx", "pad_row", "lr_delta", "group",
+                 "lr_group", "lr_bias", "params", "kinds", "emb_sizes", "lr_emb_sizes", "with_main", "with_lr")
+
+
+class _FusedEmbedFn(torch.autograd.Function):
+    """E, fm, lr = fused(rows, dense_x; per-feature parameters).  The parameters are passed so that
+    autograd tracks them; the kernels read the fused buffers they alias."""
+
+    @staticmethod
+    def forward(ctx, call, rows, dense_x, *params):
+        g, lg = call.group, call.lr_group
+        want_E = call.with_main
+        want_fm = call.with_main
+        want_lr = call.with_lr
+        E, S, fm, lr = ops.embed_fm_fwd(
+            g.table if (g is not None and call.F) else None,
+            lg.table.view(-1) if (lg is not None and call.F) else None,
+            rows, call.cat_pos, dense_x,
+            g.dense_w if (g is not None and call.Fn) else None,
+            lg.dense_w.view(-1) if (lg is not None and call.Fn) else None,
+            call.num_pos, call.lr_bias.data if call.lr_bias is not None else None,
+            want_E=want_E, want_S=want_fm, want_fm=want_fm, want_lr=want_lr,
+            B=(rows if rows is not None else dense_x).shape[0],
+            lr_delta=call.lr_delta, num_widx=call.num_widx, D=call.D)
+        ctx.call = call
+        ctx.save_for_backward(rows, dense_x, E, S)
+        outs = (E, fm.view(-1, 1) if fm is not None else None, lr.view(-1, 1) if lr is not None else None)
+        ctx.mark_non_differentiable(*[o for o in () if o is not None])
+        return outs
+
+    @staticmethod
+    def backward(ctx, dE, d_fm, d_lr):
+        call = ctx.call
+        rows, dense_x, E, S = ctx.saved_tensors
+        g, lg = call.group, call.lr_group
+        dev = (rows if rows is not None else dense_x).device
+        D = call.D
+        have_main = call.with_main and (dE is not None or d_fm is not None)
+        have_lr = call.with_lr and d_lr is not None
+        # one allocation, one zero-fill, for every dense gradient this launch produces
+        n_t = g.R * D if (have_main and g.emb) else 0
+        n_w = len(g.lin) * D if (have_main and g.lin) else 0
+        n_t1 = lg.R if (have_lr and lg.emb) else 0
+        n_w1 = len(lg.lin) if (have_lr and lg.lin) else 0
+        n_b = 1 if (have_lr and call.lr_bias is not None) else 0
+        offs, tot = [], 0
+        for n in (n_t, n_w, n_t1, n_w1, n_b):
+            offs.append(tot)
+            tot += (n + 3) // 4 * 4
+        buf = torch.zeros(max(tot, 1), dtype=F32, device=dev)
+        g_table = buf[offs[0]:offs[0] + n_t].view(-1, D) if n_t else None
+        g_dw = buf[offs[1]:offs[1] + n_w].view(-1, D) if n_w else None
+        g_t1 = buf[offs[2]:offs[2] + n_t1] if n_t1 else None
+        g_dw1 = buf[offs[3]:offs[3] + n_w1] if n_w1 else None
+        g_b = buf[offs[4]:offs[4] + 1] if n_b else None
+        if have_main or have_lr:
+            ops.embed_fm_bwd(
+                g.table if (g is not None and g.emb) else None, rows, call.cat_pos, call.pad_row, dense_x,
+                g.dense_w if (g is not None and g.lin) else None, call.num_pos,
+                E, S,
+                dE.contiguous() if (dE is not None and have_main) else None,
+                d_fm.contiguous().view(-1) if (d_fm is not None and have_main) else None,
+                d_lr.contiguous().view(-1) if have_lr else None,
+                g_table, g_t1, g_dw, g_dw1, g_b, D, g.R if (g is not None and g.emb) else (lg.R if lg is not None else 0),
+                B=(rows if rows is not None else dense_x).shape[0], lr_delta=call.lr_delta, num_widx=call.num_widx)
+        # hand the per-parameter views back to autograd (they alias `buf`; AccumulateGrad adopts them)
+        t_views = g_table.split(call.emb_sizes, 0) if g_table is not None else None
+        t1_views = g_t1.split(call.lr_emb_sizes, 0) if g_t1 is not None else None
+        grads = []
+        for kind, idx in call.kinds:
+            if kind == "emb":
+                grads.append(t_views[idx] if t_views is not None else None)
+            elif kind == "lin":
+                grads.append(g_dw[idx].view(D, 1) if g_dw is not None else None)
+            elif kind == "lr_emb":
+                grads.append(t1_views[idx].view(-1, 1) if t1_views is not None else None)
+            elif kind == "lr_lin":
+                grads.append(g_dw1[idx].view(1, 1) if g_dw1 is not None else None)
+            else:
+                grads.append(g_b if g_b is not None else None)
+        for i, p in enumerate(call.params):
+            if not ctx.needs_input_grad[3 + i]:
+                grads[i] = None
+        return (None, None, None) + tuple(grads)
+
+
+class _GatherFn(torch.autograd.Function):
+    """Plain lookup [.., ] ids -> [.., D] (un-pooled sequence features, generic encoders)."""
+
+    @staticmethod
+    def forward(ctx, weight, ids, pad):
+        ctx.save_for_backward(ids)
+        ctx.meta = (weight.shape, pad)
+        return ops.gather_rows(weight.data if isinstance(weight, nn.Parameter) else weight, ids)
+
+    @staticmethod
+    def backward(ctx, g):
+        (ids,) = ctx.saved_tensors
+        shape, pad = ctx.meta
+        gt = torch.zeros(shape, dtype=F32, device=g.device)
+        ops.scatter_add_rows(g.contiguous(), ids, pad, gt)
+        return gt, None, None
+
+
+class _PooledGatherFn(torch.autograd.Function):
+    """ids [B,L] -> pooled [B,D] without the [B,L,D] intermediate (a9)."""
+
+    @staticmethod
+    def forward(ctx, weight, ids, pad, mode):
+        out, cnt = ops.pooled_gather_fwd(weight, ids, mode)
+        ctx.save_for_backward(ids, cnt)
+        ctx.meta = (weight.shape, pad, mode)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        ids, cnt = ctx.saved_tensors
+        shape, pad, mode = ctx.meta
+        gt = torch.zeros(shape, dtype=F32, device=g.device)
+        ops.pooled_gather_bwd(g.contiguous(), ids, cnt, pad, gt, mode)
+        return gt, None, None, None
+
+
+class _InteractFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, E, mode):
+        E = E.contiguous()
+        ctx.save_for_backward(E)
+        ctx.mode = mode
+        return ops.interact_fwd(E, mode)
+
+    @staticmethod
+    def backward(ctx, g):
+        (E,) = ctx.saved_tensors
+        return ops.interact_bwd(E, g.contiguous(), ctx.mode), None
+
+
+class _RowDotFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, u, v):
+        u, v = u.contiguous(), v.contiguous()
+        ctx.save_for_backward(u, v)
+        return ops.rowdot_fwd(u, v)
+
+    @staticmethod
+    def backward(ctx, dy):
+        u, v = ctx.saved_tensors
+        du, dv = ops.rowdot_bwd(u, v, dy.contiguous(), ctx.needs_input_grad[0], ctx.needs_input_grad[1])
+        return du, (dv.view_as(v) if dv is not None else None)
+
+
+def two_tower_score(u, v):
+    """y[b,k] = <u[b], v[b,k]> for u [B,D], v [B*K, D] or [B,K,D]  (match_model.py:71-75 layout;
+    rechub dssm.py:48 is K = 1).  Differentiable; one kernel each way."""
+    return _RowDotFn.apply(u, v)
+
+
+# =================================================================================================
+# input packing (a1)
+# =================================================================================================
+class PackedInputs(dict):
+    """{feature: column} dict as RankingModel.get_inputs returns it, that also carries the device
+    batch matrix it was sliced from, so the embedding layer converts all slots in ONE launch
+    (rbx_split_batch_f64) instead of gathering 39 strided columns."""
+
+    def __init__(self, feature_map, batch):
+        super(PackedInputs, self).__init__()
+        self.batch = batch
+        self.feature_map = feature_map
+        for feature, spec in feature_map.features.items():
+            if spec["type"] == "meta":
+                continue
+            self[feature] = batch[:, feature_map.get_column_index(feature)]
+
+
+def get_inputs(model, inputs, feature_source=None):
+    """Drop-in for RankingModel.get_inputs (ranking_model.py:106-116): ONE host->device copy of the
+    batch matrix, then per-feature views of it."""
+    batch = inputs.to(model.device, non_blocking=True)
+    X = PackedInputs(model.feature_map, batch)
+    if feature_source:
+        if type(feature_source) == str:
+            feature_source = [feature_source]
+        for feature, spec in model.feature_map.features.items():
+            if spec["type"] != "meta" and spec["source"] not in feature_source:
+                X.pop(feature, None)
+    return X
+
+
+class _EmbDict(OrderedDict):
+    """OrderedDict of per-feature embeddings that remembers the stacked tensor they are views of."""
+    stacked = None
+    names = ()
+
+
+class _Stash(object):
+    __slots__ = ("X", "fm", "lr", "lr_owner", "producer", "full")
+
+
+# =================================================================================================
+# shared machinery of FeatureEmbeddingDict (ranking) and EmbeddingDictLayer (core / matching)
+# =================================================================================================
+class _FusedDictBase(nn.Module):
+    _specs_attr = "features"          # FeatureMap attribute holding the OrderedDict of feature specs
+
+    def _specs(self):
+        return getattr(self._feature_map, self._specs_attr)
+
+    def _encoders(self):
+        raise NotImplementedError
+
+    # -- storage ---------------------------------------------------------------------------------
+    def _build_store(self):
+        self._store = _FusedStore(list(self.embedding_layers.values()))
+        self._calls = {}
+        self._lr_partner = None
+
+    def _apply(self, fn, *args, **kwargs):
+        out = super(_FusedDictBase, self)._apply(fn, *args, **kwargs)
+        if getattr(self, "_store", None) is not None:
+            self._store.fuse()          # Module.to()/cuda()/float() re-pointed every parameter
+            self._calls = {}
+        return out
+
+    def __deepcopy__(self, memo):
+        import copy
+        cls = self.__class__
+        new = cls.__new__(cls)
+        memo[id(self)] = new
+        for k, v in self.__dict__.items():
+            if k in ("_store", "_calls", "_lr_partner"):
+                continue
+            setattr(new, k, copy.deepcopy(v, memo))
+        new._build_store()
+        return new
+
+    # -- call plans ------------------------------------------------------------------------------
+    def _select(self, feature_source, feature_type):
+        raise NotImplementedError
+
+    def _plan(self, key, names):
+        """Classify the selected features: which go through the fused launch, which need the
+        pooled / plain gather kernels.  Cached per selection."""
+        plan = self._calls.get(key)
+        if plan is not None:
+            return plan
+        specs, enc = self._specs(), self._encoders()
+        dims = set()
+        fused, seq_pool, generic = [], [], []
+        for name in names:
+            mod = self.embedding_layers[name]
+            spec = specs[name]
+            d = mod.embedding_dim if isinstance(mod, nn.Embedding) else mod.out_features
+            dims.add(d)
+            if spec["type"] in ("numeric", "categorical") and name not in enc:
+                fused.append(name)
+            elif spec["type"] == "sequence" and name in enc and _pool_mode(enc[name]) is not None:
+                seq_pool.append(name)
+            else:
+                generic.append(name)
+        plan = {"names": list(names), "fused": fused, "seq_pool": seq_pool, "generic": generic,
+                "uniform": len(dims) == 1 and not generic, "call": None}
+        if plan["uniform"] and (fused or seq_pool):
+            D = next(iter(dims))
+            plan["D"] = D
+            plan["call"] = self._make_call(names, fused, D, None)
+        self._calls[key] = plan
+        return plan
+
+    def _make_call(self, names, fused, D, lr_module):
+        """Static launch description for the `fused` features placed at their positions among
+        `names`; with lr_module (a LogisticRegression over the same features) the first-order term
+        is computed in the same launch."""
+        specs = self._specs()
+        g = self._store.groups[D]
+        c = _Call()
+        c.D, c.group = D, g
+        pos = {n: i for i, n in enumerate(names)}
+        cats = [n for n in fused if specs[n]["type"] == "categorical"]
+        nums = [n for n in fused if specs[n]["type"] == "numeric"]
+        c.F, c.Fn, c.Ft = len(cats), len(nums), len(names)
+        c.cat_pos = [pos[n] for n in cats]
+        c.num_pos = [pos[n] for n in nums]
+        c.num_widx = [g.lin_idx[id(self.embedding_layers[n])] for n in nums]
+        offs = [g.emb_off[id(self.embedding_layers[n])] for n in cats]
+        c.pad_row = []
+        for n, o in zip(cats, offs):
+            pi = self.embedding_layers[n].padding_idx
+            c.pad_row.append(-1 if pi is None else o + pi)
+        c.with_main, c.with_lr = True, False
+        c.lr_group, c.lr_bias, c.lr_delta = None, None, None
+        params, kinds = [], []
+        for i, m in enumerate(g.emb):
+            params.append(m.weight)
+            kinds.append(("emb", i))
+        for i, m in enumerate(g.lin):
+            params.append(m.weight)
+            kinds.append(("lin", i))
+        c.emb_sizes = [m.num_embeddings for m in g.emb]
+        c.lr_emb_sizes = []
+        if lr_module is not None:
+            ld = lr_module.embedding_layer.embedding_layer
+            lg = ld._store.groups[1]
+            c.lr_group, c.lr_bias, c.with_lr = lg, lr_module.bias, True
+            c.lr_delta = [lg.emb_off[id(ld.embedding_layers[n])] - o for n, o in zip(cats, offs)]
+            for i, m in enumerate(lg.emb):
+                params.append(m.weight)
+                kinds.append(("lr_emb", i))
+            for i, m in enumerate(lg.lin):
+                params.append(m.weight)
+                kinds.append(("lr_lin", i))
+            if lr_module.bias is not None:
+                params.append(lr_module.bias)
+                kinds.append(("bias", 0))
+            c.lr_emb_sizes = [m.num_embeddings for m in lg.emb]
+        c.params, c.kinds = params, kinds
+        c_names = {"cats": cats, "nums": nums, "offs": offs}
+        return c, c_names
+
+    # -- packing ---------------------------------------------------------------------------------
+    def _pack(self, inputs, cats, nums, offs):
+        fm = self._feature_map
+        if isinstance(inputs, PackedInputs) and inputs.feature_map is fm and inputs.batch.is_cuda \
+                and inputs.batch.dtype == torch.float64 and inputs.batch.stride(1) == 1:
+            n_cols = inputs.batch.shape[1]
+            kind, slot = [0] * n_cols, [0] * n_cols
+            for i, n in enumerate(cats):
+                ci = fm.get_column_index(n)
+                kind[ci], slot[ci] = 1, i
+            for i, n in enumerate(nums):
+                ci = fm.get_column_index(n)
+                kind[ci], slot[ci] = 2, i
+            rows, dense_x, _ = ops.split_batch(inputs.batch, kind, slot, offs, len(cats), len(nums), want_label=False)
+            return rows, dense_x
+        rows = dense_x = None
+        if cats:
+            rows = ops.pack_columns([self._col(inputs[n]) for n in cats], add=offs, as_rows=True)
+        if nums:
+            dense_x = ops.pack_columns([self._col(inputs[n]) for n in nums], as_rows=False)
+        return rows, dense_x
+
+    @staticmethod
+    def _col(t):
+        if not t.is_cuda:
+            raise RbxError("recbox_b200 layers need CUDA inputs (no CPU path); got a %s tensor" % t.device)
+        return t.reshape(-1) if t.dim() != 1 else t
+
+    # -- the forward all variants share ------------------------------------------------------------
+    def _embed(self, inputs, key, names):
+        """-> _EmbDict of per-feature embeddings for `names` (in order)."""
+        self._store.ensure()
+        for g in self._store.groups.values():
+            ref = g.table if g.table is not None else g.dense_w
+            if not ref.is_cuda:
+                raise RbxError("recbox_b200 layers have no CPU path: move the model to a CUDA device")
+        plan = self._plan(key, names)
+        specs, enc = self._specs(), self._encoders()
+        out = _EmbDict()
+        out.names = tuple(names)
+        if plan["call"] is not None:
+            call, cn = plan["call"]
+            partner = self._lr_partner() if self._lr_partner is not None else None
+            use_lr = None
+            if partner is not None and not plan["seq_pool"] and key == self._full_key():
+                pc = plan.get("lr_call")
+                if pc is None or pc[2] is not partner:
+                    pc = self._make_call(names, plan["fused"], plan["D"], partner) + (partner,)
+                    plan["lr_call"] = pc
+                call, cn, use_lr = pc[0], pc[1], partner
+            rows, dense_x = self._pack(inputs, cn["cats"], cn["nums"], cn["offs"])
+            E, fm, lr = _FusedEmbedFn.apply(call, rows, dense_x, *call.params)
+            for name in plan["seq_pool"]:          # pooled sequence slots: written by their own kernel
+                E = self._fill_seq_slot(E, inputs, name, names.index(name), enc[name])
+            if not plan["seq_pool"]:
+                st = _Stash()
+                st.X, st.fm, st.lr, st.lr_owner, st.producer = inputs, fm, lr, use_lr, weakref.ref(self)
+                st.full = key == self._full_key()
+                E._rbx_stash = st
+            out.stacked = E
+            for i, name in enumerate(names):
+                out[name] = E[:, i, :]
+            return out
+        # generic path: per-feature kernels, torch.stack later (mixed dims, custom encoders, ...)
+        for name in names:
+            mod, spec = self.embedding_layers[name], specs[name]
+            if spec["type"] == "numeric":
+                x = self._col(inputs[name]).float().view(-1, 1)
+                e = x * mod.weight.view(1, -1)
+            elif spec["type"] in ("categorical", "sequence"):
+                ids = inputs[name]
+                if not ids.is_cuda:
+                    raise RbxError("recbox_b200 layers need CUDA inputs (no CPU path)")
+                ids = ids.to(I32).contiguous()
+                pad = mod.padding_idx
+                mode = _pool_mode(enc[name]) if name in enc else None
+                if spec["type"] == "sequence" and mode is not None:
+                    e = _PooledGatherFn.apply(mod.weight, ids, pad, mode)
+                    out[name] = e
+                    continue
+                e = _GatherFn.apply(mod.weight, ids, pad)
+            else:
+                raise NotImplementedError
+            if name in enc:
+                e = enc[name](e)
+            out[name] = e
+        return out
+
+    def _fill_seq_slot(self, E, inputs, name, pos, encoder):
+        mod = self.embedding_layers[name]
+        ids = inputs[name]
+        if not ids.is_cuda:
+            raise RbxError("recbox_b200 layers need CUDA inputs (no CPU path)")
+        pooled = _PooledGatherFn.apply(mod.weight, ids.to(I32).contiguous(), mod.padding_idx, _pool_mode(encoder))
+        return _SetSlotFn.apply(E, pooled, pos)
+
+    def _full_key(self):
+        return ((), ())
+
+
+class _SetSlotFn(torch.autograd.Function):
+    """E[:, pos, :] = v, in place (E's slot `pos` was left unwritten by the fused launch)."""
+
+    @staticmethod
+    def forward(ctx, E, v, pos):
+        ctx.pos = pos
+        ctx.mark_dirty(E)
+        E[:, pos, :] = v
+        return E
+
+    @staticmethod
+    def backward(ctx, g):
+        gv = g[:, ctx.pos, :]
+        return g, gv, None
+
+
+# =================================================================================================
+# ranking side
+# =================================================================================================
+class FeatureEmbeddingDict(_FusedDictBase):
+    """ranking/pytorch/layers/embeddings/feature_embedding.py:52-214 (same ctor, attributes,
+    parameter names, init order)."""
+    _specs_attr = "features"
+
+    def __init__(self, feature_map, embedding_dim, embedding_initializer="partial(nn.init.normal_, std=1e-4)",
+                 required_feature_columns=None, not_required_feature_columns=None, use_pretrain=True,
+                 use_sharing=True):
+        super(FeatureEmbeddingDict, self).__init__()
+        self._feature_map = feature_map
+        self.required_feature_columns = required_feature_columns
+        self.not_required_feature_columns = not_required_feature_columns
+        self.use_pretrain = use_pretrain
+        self.embedding_initializer = embedding_initializer
+        self.embedding_layers = nn.ModuleDict()
+        self.feature_encoders = nn.ModuleDict()
+        for feature, feature_spec in self._feature_map.features.items():
+            if self.is_required(feature):
+                if not (use_pretrain and use_sharing) and embedding_dim == 1:
+                    feat_emb_dim = 1  # in case for LR
+                    if feature_spec["type"] == "sequence":
+                        self.feature_encoders[feature] = MaskedSumPooling()
+                else:
+                    feat_emb_dim = feature_spec.get("embedding_dim", embedding_dim)
+                    if feature_spec.get("feature_encoder", None):
+                        self.feature_encoders[feature] = self.get_feature_encoder(feature_spec["feature_encoder"])
+                if use_sharing and feature_spec.get("share_embedding") in self.embedding_layers:
+                    self.embedding_layers[feature] = self.embedding_layers[feature_spec["share_embedding"]]
+                    continue
+                if feature_spec["type"] == "numeric":
+                    self.embedding_layers[feature] = nn.Linear(1, feat_emb_dim, bias=False)
+                elif feature_spec["type"] in ("categorical", "sequence"):
+                    padding_idx = feature_spec.get("padding_idx", None)
+                    embedding_matrix = nn.Embedding(feature_spec["vocab_size"], feat_emb_dim, padding_idx=padding_idx)
+                    if use_pretrain and "pretrained_emb" in feature_spec:
+                        embedding_matrix = self.load_pretrained_embedding(
+                            embedding_matrix, feature_map, feature, freeze=feature_spec["freeze_emb"],
+                            padding_idx=padding_idx)
+                    self.embedding_layers[feature] = embedding_matrix
+        self.reset_parameters()
+        self._build_store()
+
+    def _encoders(self):
+        return self.feature_encoders
+
+    def get_feature_encoder(self, encoder):
+        import sys
+        layers = sys.modules[__name__]  # noqa: F841  ("layers.MaskedAveragePooling()" strings)
+        try:
+            if type(encoder) == list:
+                return nn.Sequential(*[eval(enc) for enc in encoder])
+            return eval(encoder)
+        except Exception:
+            raise ValueError("feature_encoder={} is not supported.".format(encoder))
+
+    def reset_parameters(self):
+        init = self.embedding_initializer
+        if isinstance(init, str):
+            try:
+                init = eval(init)
+            except Exception:
+                raise ValueError("initializer={} is not supported.".format(init))
+        self.embedding_initializer = init
+        for k, v in self.embedding_layers.items():
+            if self.use_pretrain and "pretrained_emb" in self._feature_map.features[k]:
+                continue
+            if "share_embedding" in self._feature_map.features[k] and v.weight.requires_grad == False:  # noqa: E712
+                continue
+            if type(v) == nn.Embedding:
+                if v.padding_idx is not None:  # using 0 index as padding_idx
+                    self.embedding_initializer(v.weight[1:, :])
+                else:
+                    self.embedding_initializer(v.weight)
+
+    def is_required(self, feature):
+        feature_spec = self._feature_map.features[feature]
+        if feature_spec["type"] == "meta":
+            return False
+        elif self.required_feature_columns and (feature not in self.required_feature_columns):
+            return False
+        elif self.not_required_feature_columns and (feature in self.not_required_feature_columns):
+            return False
+        return True
+
+    def get_pretrained_embedding(self, pretrained_path, feature_name):
+        import h5py
+        with h5py.File(pretrained_path, 'r') as hf:
+            embeddings = hf[feature_name][:]
+        return embeddings
+
+    def load_pretrained_embedding(self, embedding_matrix, feature_map, feature_name, freeze=False, padding_idx=None):
+        import os
+        pretrained_path = os.path.join(feature_map.data_dir, feature_map.features[feature_name]["pretrained_emb"])
+        embeddings = self.get_pretrained_embedding(pretrained_path, feature_name)
+        if padding_idx is not None:
+            embeddings[padding_idx] = np.zeros(embeddings.shape[-1])
+        assert embeddings.shape[-1] == embedding_matrix.embedding_dim, \
+            "{}\'s embedding_dim is not correctly set to match its pretrained_emb shape".format(feature_name)
+        embedding_matrix.weight = torch.nn.Parameter(torch.from_numpy(embeddings).float())
+        if freeze:
+            embedding_matrix.weight.requires_grad = False
+        return embedding_matrix
+
+    def _select(self, feature_source, feature_type):
+        if type(feature_source) != list:
+            feature_source = [feature_source]
+        if type(feature_type) != list:
+            feature_type = [feature_type]
+        key = (tuple(feature_source), tuple(feature_type))
+        names = []
+        for feature, spec in self._feature_map.features.items():
+            if feature_source and spec["source"] not in feature_source:
+                continue
+            if feature_type and spec["type"] not in feature_type:
+                continue
+            if feature in self.embedding_layers:
+                if spec["type"] not in ("numeric", "categorical", "sequence"):
+                    raise NotImplementedError
+                names.append(feature)
+        return key, names
+
+    def dict2tensor(self, embedding_dict, feature_source=[], feature_type=[], dynamic_emb_dim=False):
+        if type(feature_source) != list:
+            feature_source = [feature_source]
+        if type(feature_type) != list:
+            feature_type = [feature_type]
+        names = []
+        for feature, spec in self._feature_map.features.items():
+            if feature_source and spec["source"] not in feature_source:
+                continue
+            if feature_type and spec["type"] not in feature_type:
+                continue
+            if feature in embedding_dict:
+                names.append(feature)
+        if (not dynamic_emb_dim and isinstance(embedding_dict, _EmbDict) and embedding_dict.stacked is not None
+                and tuple(names) == embedding_dict.names):
+            return embedding_dict.stacked            # already [B, F, D] in place: no stack copy
+        vals = [embedding_dict[n] for n in names]
+        return torch.cat(vals, dim=-1) if dynamic_emb_dim else torch.stack(vals, dim=1)
+
+    def forward(self, inputs, feature_source=[], feature_type=[]):
+        key, names = self._select(feature_source, feature_type)
+        return self._embed(inputs, key, names)
+
+
+class FeatureEmbedding(nn.Module):
+    """ranking/pytorch/layers/embeddings/feature_embedding.py:28-49."""
+
+    def __init__(self, feature_map, embedding_dim, embedding_initializer="partial(nn.init.normal_, std=1e-4)",
+                 required_feature_columns=None, not_required_feature_columns=None, use_pretrain=True,
+                 use_sharing=True):
+        super(FeatureEmbedding, self).__init__()
+        self.embedding_layer = FeatureEmbeddingDict(feature_map, embedding_dim,
+                                                    embedding_initializer=embedding_initializer,
+                                                    required_feature_columns=required_feature_columns,
+                                                    not_required_feature_columns=not_required_feature_columns,
+                                                    use_pretrain=use_pretrain, use_sharing=use_sharing)
+
+    def forward(self, X, feature_source=[], feature_type=[], dynamic_emb_dim=False):
+        feature_emb_dict = self.embedding_layer(X, feature_source=feature_source, feature_type=feature_type)
+        return self.embedding_layer.dict2tensor(feature_emb_dict, dynamic_emb_dim=dynamic_emb_dim)
+
+
+class InnerProductInteraction(nn.Module):
+    """ranking/pytorch/layers/interactions/inner_product.py:22-56.
+    output: product_sum (bs x 1), bi_interaction (bs x dim), inner_product (bs x f(f-1)/2),
+            elementwise_product (bs x f(f-1)/2 x dim)"""
+
+    def __init__(self, num_fields, output="product_sum"):
+        super(InnerProductInteraction, self).__init__()
+        self._output_type = output
+        if output not in ["product_sum", "bi_interaction", "inner_product", "elementwise_product"]:
+            raise ValueError("InnerProductInteraction output={} is not supported.".format(output))
+        if output == "inner_product":       # kept so state_dict keys equal the reference's
+            self.interaction_units = int(num_fields * (num_fields - 1) / 2)
+            self.triu_mask = nn.Parameter(torch.triu(torch.ones(num_fields, num_fields), 1).bool(),
+                                          requires_grad=False)
+        elif output == "elementwise_product":
+            self.triu_index = nn.Parameter(torch.triu_indices(num_fields, num_fields, offset=1), requires_grad=False)
+
+    def forward(self, feature_emb):
+        if self._output_type == "product_sum":
+            st = getattr(feature_emb, "_rbx_stash", None)
+            if st is not None and st.fm is not None:
+                return st.fm                 # computed by the launch that produced feature_emb
+        if not feature_emb.is_cuda:
+            raise RbxError("recbox_b200 layers have no CPU path")
+        return _InteractFn.apply(feature_emb, ops.MODES[self._output_type])
+
+
+class LogisticRegression(nn.Module):
+    """ranking/pytorch/layers/blocks/logistic_regression.py:23-35."""
+
+    def __init__(self, feature_map, use_bias=True):
+        super(LogisticRegression, self).__init__()
+        self.bias = nn.Parameter(torch.zeros(1), requires_grad=True) if use_bias else None
+        # A trick for quick one-hot encoding in LR
+        self.embedding_layer = FeatureEmbedding(feature_map, 1, use_pretrain=False, use_sharing=False)
+
+    def forward(self, X):
+        d = self.embedding_layer.embedding_layer
+        key, names = d._select([], [])
+        plan = d._plan(key, names)
+        if plan["call"] is None or plan["seq_pool"]:
+            embed_weights = self.embedding_layer(X)        # generic route (sequence slots): sum over fields
+            output = embed_weights.sum(dim=1)
+            if self.bias is not None:
+                output = output + self.bias
+            return output
+        d._store.ensure()
+        c = plan.get("lr_only")
+        if c is None:
+            call, cn = plan["call"]
+            lo = _Call()
+            for k in _Call.__slots__:
+                if hasattr(call, k):
+                    setattr(lo, k, getattr(call, k))
+            g = d._store.groups[1]
+            lo.group, lo.lr_group, lo.with_main, lo.with_lr = None, g, False, True
+            lo.lr_bias, lo.lr_delta = self.bias, None
+            lo.params = [m.weight for m in g.emb] + [m.weight for m in g.lin] + ([self.bias] if self.bias is not None else [])
+            lo.kinds = [("lr_emb", i) for i in range(len(g.emb))] + [("lr_lin", i) for i in range(len(g.lin))] + \
+                       ([("bias", 0)] if self.bias is not None else [])
+            lo.lr_emb_sizes, lo.emb_sizes = [m.num_embeddings for m in g.emb], []
+            c = (lo, cn)
+            plan["lr_only"] = c
+        call, cn = c
+        rows, dense_x = d._pack(X, cn["cats"], cn["nums"], cn["offs"])
+        _, _, lr = _FusedEmbedFn.apply(call, rows, dense_x, *call.params)
+        return lr
+
+
+class FactorizationMachine(nn.Module):
+    """ranking/pytorch/layers/blocks/factorization_machine.py:24-34."""
+
+    def __init__(self, feature_map):
+        super(FactorizationMachine, self).__init__()
+        self.fm_layer = InnerProductInteraction(feature_map.num_fields, output="product_sum")
+        self.lr_layer = LogisticRegression(feature_map, use_bias=True)
+
+    def forward(self, X, feature_emb):
+        st = getattr(feature_emb, "_rbx_stash", None)
+        if st is not None and st.X is X and st.lr is not None and st.lr_owner is self.lr_layer:
+            return st.fm + st.lr             # both came out of the launch that produced feature_emb
+        lr_out = self.lr_layer(X)
+        fm_out = self.fm_layer(feature_emb)
+        if st is not None and st.X is X and st.full:
+            _try_pair(st.producer(), self.lr_layer)
+        return fm_out + lr_out
+
+
+def _try_pair(producer, lr_module):
+    """Let `producer` (the FeatureEmbeddingDict that made feature_emb) compute this FM block's
+    first-order term in its own launch from now on.  Only when both see the same features as
+    plain categorical / numeric slots."""
+    if producer is None or not FUSE_FM:
+        return
+    ld = lr_module.embedding_layer.embedding_layer
+    if ld._feature_map is not producer._feature_map:
+        return
+    kp, np_ = producer._select([], [])
+    kl, nl = ld._select([], [])
+    if np_ != nl:
+        return
+    pp, pl = producer._plan(kp, np_), ld._plan(kl, nl)
+    if pp["call"] is None or pl["call"] is None or pp["seq_pool"] or pl["seq_pool"]:
+        return
+    if pp["call"][0].num_widx != pl["call"][0].num_widx:
+        return
+    producer._lr_partner = weakref.ref(lr_module)
+
+
+FUSE_FM = True   # set False to keep FactorizationMachine's first-order term in its own launch
+
+
+# =================================================================================================
+# core / matching side
+# =================================================================================================
+class EmbeddingDictLayer(_FusedDictBase):
+    """core/pytorch/layers/embedding.py:30-138 (same ctor, attributes and parameter names)."""
+    _specs_attr = "feature_specs"
+
+    def __init__(self, feature_map, embedding_dim, disable_sharing_pretrain=False, required_feature_columns=None,
+                 not_required_feature_columns=None):
+        super(EmbeddingDictLayer, self).__init__()
+        import sys
+        layers = _CoreNamespace(sys.modules[__name__])  # noqa: F841  ("layers.MaskedAveragePooling()" strings)
+        self._feature_map = feature_map
+        self.required_feature_columns = required_feature_columns
+        self.not_required_feature_columns = not_required_feature_columns
+        self.embedding_layers = nn.ModuleDict()
+        self.embedding_callbacks = nn.ModuleDict()
+        for feature, feature_spec in self._feature_map.feature_specs.items():
+            if self.is_required(feature):
+                if disable_sharing_pretrain:  # in case for LR
+                    assert embedding_dim == 1
+                    feat_emb_dim = embedding_dim
+                else:
+                    feat_emb_dim = feature_spec.get("embedding_dim", embedding_dim)
+                if (not disable_sharing_pretrain) and "embedding_callback" in feature_spec:
+                    self.embedding_callbacks[feature] = eval(feature_spec["embedding_callback"])
+                if (not disable_sharing_pretrain) and "share_embedding" in feature_spec:
+                    self.embedding_layers[feature] = self.embedding_layers[feature_spec["share_embedding"]]
+                    continue
+                if feature_spec["type"] == "numeric":
+                    self.embedding_layers[feature] = nn.Linear(1, feat_emb_dim, bias=False)
+                elif feature_spec["type"] in ("categorical", "sequence"):
+                    padding_idx = feature_spec.get("padding_idx", None)
+                    embedding_matrix = nn.Embedding(feature_spec["vocab_size"], feat_emb_dim, padding_idx=padding_idx)
+                    if (not disable_sharing_pretrain) and "pretrained_emb" in feature_spec:
+                        embedding_matrix = self.load_pretrained_embedding(
+                            embedding_matrix, feature_map, feature, freeze=feature_spec["freeze_emb"],
+                            padding_idx=padding_idx)
+                    self.embedding_layers[feature] = embedding_matrix
+        self._build_store()
+
+    def _encoders(self):
+        return self.embedding_callbacks
+
+    def is_required(self, feature):
+        if self.required_feature_columns and (feature not in self.required_feature_columns):
+            return False
+        if self.not_required_feature_columns and (feature in self.not_required_feature_columns):
+            return False
+        return True
+
+    def get_pretrained_embedding(self, pretrained_path, feature_name):
+        import h5py
+        with h5py.File(pretrained_path, 'r') as hf:
+            embeddings = hf[feature_name][:]
+        return embeddings
+
+    def load_pretrained_embedding(self, embedding_matrix, feature_map, feature_name, freeze=False, padding_idx=None):
+        import os
+        pretrained_path = os.path.join(feature_map.data_dir, feature_map.feature_specs[feature_name]["pretrained_emb"])
+        embeddings = self.get_pretrained_embedding(pretrained_path, feature_name)
+        if padding_idx is not None:
+            embeddings[padding_idx] = np.zeros(embeddings.shape[-1])
+        embedding_matrix.weight = torch.nn.Parameter(torch.from_numpy(embeddings).float())
+        if freeze:
+            embedding_matrix.weight.requires_grad = False
+        return embedding_matrix
+
+    def dict2tensor(self, embedding_dict):
+        if len(embedding_dict) == 1:
+            return list(embedding_dict.values())[0]
+        if isinstance(embedding_dict, _EmbDict) and embedding_dict.stacked is not None \
+                and tuple(embedding_dict.keys()) == embedding_dict.names:
+            return embedding_dict.stacked
+        return torch.stack(list(embedding_dict.values()), dim=1)
+
+    def _select(self, feature_source, feature_type):
+        key = (feature_source, feature_type)
+        names = []
+        for feature, spec in self._feature_map.feature_specs.items():
+            if feature_source and spec["source"] != feature_source:
+                continue
+            if feature_type and spec["type"] != feature_type:
+                continue
+            if feature in self.embedding_layers:
+                if spec["type"] not in ("numeric", "categorical", "sequence"):
+                    raise NotImplementedError
+                names.append(feature)
+        return key, names
+
+    def _full_key(self):
+        return (None, None)
+
+    def forward(self, inputs, feature_source=None, feature_type=None):
+        key, names = self._select(feature_source, feature_type)
+        return self._embed(inputs, key, names)
+
+
+class _CoreNamespace(object):
+    """What `layers.X` resolves to inside core feature specs' embedding_callback strings."""
+
+    def __init__(self, mod):
+        self._mod = mod
+
+    def __getattr__(self, name):
+        if name == "MaskedAveragePooling":
+            return CoreMaskedAveragePooling
+        return getattr(self._mod, name)
+
+
+class EmbeddingLayer(nn.Module):
+    """core/pytorch/layers/embedding.py:10-27."""
+
+    def __init__(self, feature_map, embedding_dim, disable_sharing_pretrain=False, required_feature_columns=[],
+                 not_required_feature_columns=[]):
+        super(EmbeddingLayer, self).__init__()
+        self.embedding_layer = EmbeddingDictLayer(feature_map, embedding_dim,
+                                                  disable_sharing_pretrain=disable_sharing_pretrain,
+                                                  required_feature_columns=required_feature_columns,
+                                                  not_required_feature_columns=not_required_feature_columns)
+
+    def forward(self, X, feature_source=None):
+        feature_emb_dict = self.embedding_layer(X, feature_source=feature_source)
+        return self.embedding_layer.dict2tensor(feature_emb_dict)

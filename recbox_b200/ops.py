@@ -83,12 +83,13 @@ def pack_columns(cols, add=None, as_rows=True):
 
 # ---------------------------------------------------------------------------------- K1 / K2 / K3
 def embed_fm_fwd(table, table_lr, rows, cat_pos, dense_x, dense_w, dense_w_lr, num_pos, lr_bias,
-                 want_E=True, want_S=True, want_fm=True, want_lr=True, B=None):
+                 want_E=True, want_S=True, want_fm=True, want_lr=True, B=None, lr_delta=None, num_widx=None, D=None):
     """Fused gather + FM + LR forward.  Returns (E, S, fm_out, lr_out); unrequested ones are None."""
     F = len(cat_pos)
     Fn = len(num_pos)
-    ref = table if table is not None else dense_w
-    D = ref.shape[-1]
+    ref = table if table is not None else (dense_w if dense_w is not None else (rows if rows is not None else dense_x))
+    if D is None:
+        D = ref.shape[-1] if (table is not None or dense_w is not None) else 1
     dev = ref.device
     if B is None:
         B = rows.shape[0] if rows is not None else dense_x.shape[0]
@@ -99,22 +100,24 @@ def embed_fm_fwd(table, table_lr, rows, cat_pos, dense_x, dense_w, dense_w_lr, n
     fm = torch.empty((B,), dtype=F32, device=dev) if want_fm else None
     lr = torch.empty((B,), dtype=F32, device=dev) if want_lr else None
     _call("rbx_embed_fm_fwd", _p(table, F32, "table"), _p(table_lr, F32, "table_lr"), _p(rows, I32, "rows"),
-          _i32(cat_pos), _p(dense_x, F32, "dense_x"), _p(dense_w, F32, "dense_w"),
-          _p(dense_w_lr, F32, "dense_w_lr"), _i32(num_pos), _p(lr_bias, F32, "lr_bias"),
+          _i32(cat_pos), _i32(lr_delta) if lr_delta is not None else None, _p(dense_x, F32, "dense_x"),
+          _p(dense_w, F32, "dense_w"), _p(dense_w_lr, F32, "dense_w_lr"), _i32(num_pos),
+          _i32(num_widx) if num_widx is not None else None, _p(lr_bias, F32, "lr_bias"),
           _p(E), _p(S), _p(fm), _p(lr), B, R, F, Fn, D, _stream())
     return E, S, fm, lr
 
 
 def embed_fm_bwd(table, rows, cat_pos, pad_row, dense_x, dense_w, num_pos, E, S, dE, d_fm, d_lr,
-                 g_table, g_table_lr, g_dense_w, g_dense_w_lr, g_lr_bias, D, R, B=None):
+                 g_table, g_table_lr, g_dense_w, g_dense_w_lr, g_lr_bias, D, R, B=None, lr_delta=None, num_widx=None):
     """Gradient scatter-add (accumulates into the g_* tensors, which the caller zero-fills)."""
     F = len(cat_pos)
     Fn = len(num_pos)
     if B is None:
         B = rows.shape[0] if rows is not None else dense_x.shape[0]
     _call("rbx_embed_fm_bwd", _p(table, F32, "table"), _p(rows, I32, "rows"), _i32(cat_pos),
-          _i32(pad_row if pad_row is not None else [-1] * F), _p(dense_x, F32, "dense_x"),
-          _p(dense_w, F32, "dense_w"), _i32(num_pos), _p(E, F32, "E"), _p(S, F32, "S"), _p(dE, F32, "dE"),
+          _i32(pad_row if pad_row is not None else [-1] * F), _i32(lr_delta) if lr_delta is not None else None,
+          _p(dense_x, F32, "dense_x"), _p(dense_w, F32, "dense_w"), _i32(num_pos),
+          _i32(num_widx) if num_widx is not None else None, _p(E, F32, "E"), _p(S, F32, "S"), _p(dE, F32, "dE"),
           _p(d_fm, F32, "d_fm"), _p(d_lr, F32, "d_lr"), _p(g_table, F32, "g_table"),
           _p(g_table_lr, F32, "g_table_lr"), _p(g_dense_w, F32, "g_dense_w"),
           _p(g_dense_w_lr, F32, "g_dense_w_lr"), _p(g_lr_bias, F32, "g_lr_bias"), B, R, F, Fn, D, _stream())

@@ -1,0 +1,254 @@
+"""Pin the CPU oracle (oracle/recbox_oracle.py) against the golden vectors minted from the
+UNMODIFIED reference by oracle/make_golden.py (tests/golden/*.npz) and against the integer
+known-answer vectors of SURVEY.md section 4.  CPU only."""
+import os
+from collections import OrderedDict
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import assert_close, oracle
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def load(name):
+    z = np.load(os.path.join(GOLD, name + ".npz"))
+    return {k: torch.from_numpy(z[k]) if z[k].dtype != np.bool_ else torch.from_numpy(z[k]) for k in z.files}
+
+
+def ranking_features(tag):
+    seq = tag.endswith("seq")
+    share = tag.endswith("share")
+    f = OrderedDict()
+    f["I1"] = {"source": "", "type": "numeric"}
+    f["C1"] = {"source": "", "type": "categorical", "vocab_size": 11, "padding_idx": 0}
+    f["I2"] = {"source": "", "type": "numeric"}
+    f["C2"] = {"source": "", "type": "categorical", "vocab_size": 7, "padding_idx": 0}
+    f["C3"] = {"source": "", "type": "categorical", "vocab_size": 13, "padding_idx": 0}
+    f["C4"] = {"source": "", "type": "categorical", "vocab_size": 11, "padding_idx": 0}
+    if share:
+        f["C4"]["share_embedding"] = "C1"
+    if seq:
+        f["S1"] = {"source": "", "type": "sequence", "vocab_size": 9, "padding_idx": 0, "max_len": 5,
+                   "feature_encoder": "layers.MaskedAveragePooling()"}
+    return f
+
+
+EMB = "emb.embedding_layer.embedding_layers."
+LRP = "fm.lr_layer.embedding_layer.embedding_layer.embedding_layers."
+
+
+def weights_from(gold, prefix, features, share_ok=True):
+    W = OrderedDict()
+    for name, spec in features.items():
+        key = prefix + name + ".weight"
+        if share_ok and "share_embedding" in spec:      # one module registered under two names
+            W[name] = W[spec["share_embedding"]]
+        elif key in gold:
+            W[name] = gold[key].clone().requires_grad_(True)
+    return W
+
+
+# ------------------------------------------------------------------------------------------- KATs
+def test_known_answers_survey_section4():
+    E = torch.arange(24, dtype=torch.float32).view(2, 3, 4)
+    assert oracle.inner_product_interaction(E, "product_sum").reshape(-1).tolist() == [314, 3626]
+    assert oracle.inner_product_interaction(E, "bi_interaction").reshape(-1).tolist() == [32, 59, 92, 131, 752, 851, 956, 1067]
+    assert oracle.inner_product_interaction(E, "inner_product").reshape(-1).tolist() == [38, 62, 214, 950, 1166, 1510]
+    assert oracle.inner_product_interaction(E, "elementwise_product")[0].reshape(-1).tolist() == [0, 5, 12, 21, 0, 9, 20, 33, 32, 45, 60, 77]
+    Ev = E.clone().requires_grad_(True)
+    oracle.inner_product_interaction(Ev, "product_sum").sum().backward()
+    assert Ev.grad[0].tolist() == [[12, 14, 16, 18], [8, 10, 12, 14], [4, 6, 8, 10]]
+    with pytest.raises(ValueError):
+        oracle.inner_product_interaction(E, "nope")
+    W = np.arange(10, dtype=np.float32).reshape(5, 2)
+    idx = np.array([[1, 1, 0], [4, 0, 0]])
+    g = oracle.embedding_dense_backward_numpy(np.ones((2, 3, 2), np.float32), idx, 5, padding_idx=0)
+    assert g.tolist() == [[0, 0], [2, 2], [0, 0], [0, 0], [1, 1]]
+    emb = torch.from_numpy(oracle.gather_rows_numpy(W, idx))
+    assert_close(oracle.masked_average_pooling(emb), torch.tensor([[4 / 3, 7 / 3], [8 / 3, 11 / 3]]), what="masked avg")
+    # DSSM-style softmax loss at (near-)zero scores with 10 negatives = ln 11; SASRec BCE at init = 2 ln 2
+    assert abs(float(oracle.softmax_cross_entropy_loss(torch.zeros(4, 11))) - np.log(11)) < 1e-6
+
+
+# ---------------------------------------------------------------------------- golden: interaction
+@pytest.mark.parametrize("tag", ["kat", "rnd"])
+@pytest.mark.parametrize("mode", oracle.INTERACTION_MODES)
+def test_interaction_golden(tag, mode):
+    g = load("interaction")
+    E = g[tag + ".E"].clone().requires_grad_(True)
+    y = oracle.inner_product_interaction(E, mode)
+    assert torch.equal(y, g["%s.%s.out" % (tag, mode)])
+    (y * g["%s.%s.w" % (tag, mode)]).sum().backward()
+    assert torch.equal(E.grad, g["%s.%s.dE" % (tag, mode)])
+
+
+def test_pooling_golden():
+    g = load("pooling")
+    assert torch.equal(oracle.masked_average_pooling(g["emb"]), g["ranking_avg"])
+    assert torch.equal(oracle.masked_average_pooling(g["emb"]), g["core_avg"])
+    assert torch.equal(oracle.masked_average_pooling(g["emb"], g["mask"]), g["ranking_avg_mask"])
+    assert torch.equal(oracle.masked_sum_pooling(g["emb"]), g["ranking_sum"])
+    assert torch.equal(oracle.masked_sum_pooling(g["emb"]), g["core_sum"])
+
+
+# ------------------------------------------------------------------------- golden: ranking layers
+@pytest.mark.parametrize("tag", ["ranking_layers_d8", "ranking_layers_d10", "ranking_layers_share", "ranking_layers_seq"])
+def test_ranking_layers_golden(tag):
+    g = load(tag)
+    feats = ranking_features(tag)
+    W = weights_from(g, EMB, feats)
+    X = oracle.get_inputs(g["batch"], feats, ["label"])
+    enc = {"S1": oracle.masked_average_pooling} if "S1" in feats else None
+    E = oracle.dict2tensor(oracle.embed_dict(X, feats, W, enc))
+    assert torch.equal(E, g["E"])
+    loss = (E * g["wE"]).sum()
+    W1 = None
+    if "y" in g:
+        W1 = weights_from(g, LRP, feats, share_ok=False)
+        bias = g["fm.lr_layer.bias"].clone().requires_grad_(True)
+        lr = oracle.logistic_regression(X, feats, W1, bias)
+        fm = oracle.inner_product_interaction(E, "product_sum")
+        y = oracle.factorization_machine(X, E, feats, W1, bias)
+        assert torch.equal(lr, g["lr_out"]) and torch.equal(fm, g["fm_out"]) and torch.equal(y, g["y"])
+        loss = loss + (y * g["wy"]).sum()
+    loss.backward()
+    for name in feats:
+        k = "grad." + EMB + name + ".weight"
+        if k in g:
+            assert torch.equal(W[name].grad, g[k]), k
+        k1 = "grad." + LRP + name + ".weight"
+        if W1 is not None and k1 in g:
+            assert torch.equal(W1[name].grad, g[k1]), k1
+    if W1 is not None:
+        assert torch.equal(bias.grad, g["grad.fm.lr_layer.bias"])
+
+
+def test_core_layers_golden():
+    g = load("core_layers")
+    feats = OrderedDict([
+        ("item_id", {"type": "categorical", "source": "item", "vocab_size": 23, "padding_idx": 22}),
+        ("item_cat", {"type": "categorical", "source": "item", "vocab_size": 6}),
+        ("user_id", {"type": "categorical", "source": "user", "vocab_size": 17}),
+        ("user_age", {"type": "numeric", "source": "user"}),
+        ("user_hist", {"type": "sequence", "source": "user", "vocab_size": 23, "padding_idx": 22,
+                       "share_embedding": "item_id"}),
+    ])
+    W = weights_from(g, EMB, feats)
+    X = {k[2:]: v for k, v in g.items() if k.startswith("X.")}
+    enc = {"user_hist": oracle.masked_average_pooling}
+    U = oracle.dict2tensor(oracle.embed_dict(X, feats, W, enc, feature_source=("user",)), core_semantics=True)
+    V = oracle.dict2tensor(oracle.embed_dict(X, feats, W, enc, feature_source=("item",)), core_semantics=True)
+    assert torch.equal(U, g["U"]) and torch.equal(V, g["V"])
+    ((U * g["wU"]).sum() + (V * g["wV"]).sum()).backward()
+    for name in ("item_id", "item_cat", "user_id", "user_age"):
+        assert torch.equal(W[name].grad, g["grad." + EMB + name + ".weight"]), name
+    one = oracle.dict2tensor(oracle.embed_dict(X, OrderedDict(user_id=feats["user_id"]), W), core_semantics=True)
+    assert one.dim() == 2 and torch.equal(one, g["single"])
+
+
+def test_two_tower_golden():
+    g = load("two_tower")
+    u, v = g["u"].clone().requires_grad_(True), g["v"].clone().requires_grad_(True)
+    y = oracle.two_tower_score(u, v)
+    assert torch.equal(y, g["y"])
+    loss = oracle.softmax_cross_entropy_loss(y)
+    assert torch.equal(loss, g["loss"])
+    loss.backward()
+    assert torch.equal(u.grad, g["du"]) and torch.equal(v.grad, g["dv"])
+    assert torch.equal(oracle.dssm_score(g["dssm_u"], g["dssm_v"]), g["dssm_y"])
+
+
+# ------------------------------------------------------------------- golden: assembled train step
+def _deepfm_oracle(g, feats, D, hidden, use_mlp):
+    m = oracle.DeepFMOracle(feats, ["label"], D, hidden=hidden, use_mlp=use_mlp)
+    P = OrderedDict()
+    for k in m.params:
+        P[k] = g["init." + k].clone().requires_grad_(True)
+    m.params = P
+    m.m = OrderedDict((k, torch.zeros_like(v)) for k, v in P.items())
+    m.v = OrderedDict((k, torch.zeros_like(v)) for k, v in P.items())
+    return m
+
+
+def test_deepfm_train_golden():
+    g = load("deepfm_train")
+    feats = ranking_features("ranking_layers_d8")
+    m = _deepfm_oracle(g, feats, 8, (16, 8), True)
+    assert sorted(m.params) == sorted(k[5:] for k in g if k.startswith("init.")), "state_dict keys"
+    losses = []
+    for step in range(3):
+        losses.append(float(m.train_step(g["batch%d" % step])))
+        if step == 0:
+            pass
+    assert_close(torch.tensor(losses), g["losses"].float(), rtol=1e-6, atol_scale=0, what="losses")
+    for k, v in m.params.items():
+        assert_close(v, g["final." + k], rtol=1e-5, atol_scale=1e-6, what=k)
+    assert_close(m.forward(g["batch0"]), g["pred_final"], rtol=1e-5, what="pred")
+
+
+def test_config1_fm_golden():
+    """BASELINE configs[0]: FM on the 1k-row Criteo-shaped CSV the reference preprocessed."""
+    g = load("config1_fm")
+    feats = OrderedDict()
+    for i in range(1, 14):
+        feats["I%d" % i] = {"source": "", "type": "numeric"}
+    for i, V in enumerate(g["vocab_sizes"].tolist(), 1):
+        feats["C%d" % i] = {"source": "", "type": "categorical", "vocab_size": int(V), "padding_idx": 0}
+    m = _deepfm_oracle(g, feats, 10, (), False)
+    batch = g["batch"]
+    assert_close(m.forward(batch[:128]), g["pred_init"], rtol=1e-6, what="pred_init")
+    losses = [float(m.train_step(batch[s * 128:(s + 1) * 128])) for s in range(4)]
+    assert_close(torch.tensor(losses), g["losses"].float(), rtol=1e-6, atol_scale=0, what="losses")
+    assert_close(m.forward(batch[:128]), g["pred_final"], rtol=1e-5, what="pred_final")
+
+
+# ----------------------------------------------------------------------------- integer / index rows
+def test_split_batch_and_column_index():
+    feats = ranking_features("ranking_layers_seq")
+    cols = oracle.column_index(feats, ["label"])
+    assert cols["I1"] == 0 and cols["S1"] == [6, 7, 8, 9, 10] and cols["label"] == 11
+    batch = np.array([[0.25, 3.0, 0.5, 2.0, 12.0, 10.0, 1, 2, 0, 0, 0, 1.0]])
+    ids, dense, label = oracle.split_batch_numpy(batch, [1, 3, 4, 5], [0, 2], 11)
+    assert ids.tolist() == [[3, 2, 12, 10]] and dense.dtype == np.float32 and label.tolist() == [1.0]
+
+
+def test_unique_items_first_occurrence():
+    uniq, first, inv = oracle.unique_items(np.array([[5, 3, 5], [9, 3, 1]]))
+    assert uniq.tolist() == [1, 3, 5, 9] and first.tolist() == [5, 1, 0, 3] and inv.tolist() == [2, 1, 2, 3, 1, 0]
+
+
+@pytest.mark.parametrize("world", [1, 2, 8])
+def test_shard_route_roundtrip(world):
+    rng = np.random.default_rng(world)
+    rows = rng.integers(0, 10_000, size=1000)
+    send, counts, pos = oracle.shard_route(rows, world)
+    assert counts.sum() == 1000 and np.array_equal(np.sort(pos), np.arange(1000))
+    starts = np.concatenate([[0], np.cumsum(counts)])
+    for w in range(world):
+        seg = slice(starts[w], starts[w + 1])
+        orig = rows[rows % world == w]
+        assert np.array_equal(send[seg] * world + w, orig), "bucket keeps first-come order"
+    payload = rng.standard_normal((1000, 4))
+    sent = np.empty_like(payload)
+    sent[pos] = payload
+    assert np.array_equal(oracle.shard_unroute(sent, pos), payload)
+
+
+def test_clip_and_adam_match_torch():
+    g = torch.Generator().manual_seed(0)
+    p = torch.randn(50, generator=g, requires_grad=True)
+    q = p.detach().clone()
+    opt = torch.optim.Adam([p], lr=1e-3)
+    m, v = torch.zeros(50), torch.zeros(50)
+    for step in range(1, 4):
+        grad = torch.randn(50, generator=g) * 5
+        p.grad = grad.clone()
+        total = torch.nn.utils.clip_grad_norm_([p], 10.0)
+        norm, coef = oracle.clip_grad_norm([grad], 10.0)
+        assert torch.equal(norm, total)
+        opt.step()
+        oracle.adam_step(q, grad * coef, m, v, step)
+        assert_close(q, p, rtol=1e-6, atol_scale=1e-7, what="adam")

@@ -1,0 +1,26 @@
+#!/usr/bin/env python
+"""Build tuning variants of librecbox_b200.so (compile-time knobs of csrc/embed_fm.cu) into
+build/variants/; bench.py picks one with RBX_LIB_PATH=...  Used for the sweeps under profiles/."""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from recbox_b200 import _lib  # noqa: E402
+
+VARIANTS = {
+    "base": [],
+    "fwd_minb4": ["RBX_FWD_MINB=4"],
+    "l2_keep": ["RBX_L2_HINTS=1"],
+    "l2_stream": ["RBX_L2_HINTS=2"],
+    "l2_both": ["RBX_L2_HINTS=3"],
+    "l2_both_minb4": ["RBX_L2_HINTS=3", "RBX_FWD_MINB=4"],
+}
+
+if __name__ == "__main__":
+    out_dir = os.path.join(ROOT, "build", "variants")
+    os.makedirs(out_dir, exist_ok=True)
+    names = sys.argv[1:] or list(VARIANTS)
+    for name in names:
+        path = _lib.build(force=True, defines=VARIANTS[name], out=os.path.join(out_dir, name + ".so"))
+        print(name, "->", path)
