@@ -113,7 +113,10 @@ int rbx_embed_fm_fwd(const float* table /*DEVICE [R,D]*/,
                      float* S /*DEVICE [B,D] | NULL*/,
                      float* fm_out /*DEVICE [B] | NULL*/,
                      float* lr_out /*DEVICE [B] | NULL*/,
-                     int64_t B, int64_t R, int F, int Fn, int D, rbx_stream_t stream);
+                     int64_t B, int64_t R, int F, int Fn, int D,
+                     int n_slots /* slots of E (row stride n_slots*D); 0 = F + Fn.  Slots not named by
+                                    cat_pos / num_pos are left untouched (pooled sequence slots) */,
+                     rbx_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * a5+a6+a7 backward: grad scatter-add                                (kernel K3)
@@ -148,7 +151,8 @@ int rbx_embed_fm_bwd(const float* table /*DEVICE [R,D] | NULL if E given*/,
                      float* g_dense_w /*DEVICE [Fn,D] | NULL*/,
                      float* g_dense_w_lr /*DEVICE [Fn] | NULL*/,
                      float* g_lr_bias /*DEVICE [1] | NULL*/,
-                     int64_t B, int64_t R, int F, int Fn, int D, rbx_stream_t stream);
+                     int64_t B, int64_t R, int F, int Fn, int D, int n_slots /* of E and dE; 0 = F + Fn */,
+                     rbx_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * a5  plain row gather / scatter-add (un-pooled sequence features, SASRec's three shared-table
@@ -180,6 +184,17 @@ int rbx_pooled_gather_bwd(const float* g /*DEVICE [B, g_ld]*/, int64_t g_ld,
                           const int32_t* ids, int64_t ids_ld, const float* cnt /*DEVICE [B] | NULL (mode 0)*/,
                           int32_t pad_row, float* g_table,
                           int64_t B, int L, int D, int mode, rbx_stream_t stream);
+
+/* The same two pooling layers applied to an already materialised emb [B,L,D] (the modules called
+ * directly: core/pytorch/layers/sequence.py:4-20, ranking/pytorch/layers/pooling.py:22-40).
+ * mask (uint8 [B,L], nullable) replaces the row-sum != 0 rule (pooling.py:27-29).  cnt[b] receives
+ * the mask count (mode 1).  Backward: d_emb[b,l,:] = g[b,:] / (cnt[b] + 1e-12) (mode 1) or g[b,:]
+ * (mode 0) for EVERY l -- the sum's gradient reaches masked positions too, as in autograd. */
+int rbx_pool_fwd(const float* emb /*DEVICE [B,L,D]*/, const uint8_t* mask /*DEVICE [B,L] | NULL*/,
+                 float* out /*DEVICE [B,D]*/, float* cnt /*DEVICE [B] | NULL*/,
+                 int64_t B, int L, int D, int mode, rbx_stream_t stream);
+int rbx_pool_bwd(const float* g /*DEVICE [B,D]*/, const float* cnt /*DEVICE [B] | NULL (mode 0)*/,
+                 float* d_emb /*DEVICE [B,L,D]*/, int64_t B, int L, int D, int mode, rbx_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * a10  two-tower scores  y[b,k] = <u[b,:], v[b,k,:]>   (layout fixed by

@@ -78,12 +78,14 @@ SIGNATURES = {
     "rbx_device_sm_count": [],
     "rbx_split_batch_f64": [_P, _I64, _I, _I64, _P, _P, _P, _I, _I, _P, _P, _P, _P],
     "rbx_pack_columns": [_P, _P, _P, _P, _I, _I64, _I, _P, _P],
-    "rbx_embed_fm_fwd": [_P] * 15 + [_I64, _I64, _I, _I, _I, _P],
-    "rbx_embed_fm_bwd": [_P] * 19 + [_I64, _I64, _I, _I, _I, _P],
+    "rbx_embed_fm_fwd": [_P] * 15 + [_I64, _I64, _I, _I, _I, _I, _P],
+    "rbx_embed_fm_bwd": [_P] * 19 + [_I64, _I64, _I, _I, _I, _I, _P],
     "rbx_gather_rows": [_P, _P, _P, _I64, _I, _P],
     "rbx_scatter_add_rows": [_P, _P, _c.c_int32, _P, _I64, _I, _P],
     "rbx_pooled_gather_fwd": [_P, _P, _I64, _P, _I64, _P, _I64, _I, _I, _I, _P],
     "rbx_pooled_gather_bwd": [_P, _I64, _P, _I64, _P, _c.c_int32, _P, _I64, _I, _I, _I, _P],
+    "rbx_pool_fwd": [_P, _P, _P, _P, _I64, _I, _I, _I, _P],
+    "rbx_pool_bwd": [_P, _P, _P, _I64, _I, _I, _I, _P],
     "rbx_rowdot_fwd": [_P, _P, _P, _I64, _I, _I, _P],
     "rbx_rowdot_bwd": [_P, _P, _P, _P, _P, _I64, _I, _I, _P],
     "rbx_interact_fwd": [_P, _P, _I64, _I, _I, _I, _P],

@@ -45,7 +45,7 @@ struct FwdParams {
     float* lr_out;
     int64_t B;
     int64_t R;
-    int F, Fn, D;
+    int F, Fn, D, Ft;
     SlotMeta meta;
 };
 
@@ -66,7 +66,7 @@ struct BwdParams {
     float* g_lr_bias;
     int64_t B;
     int64_t R;
-    int F, Fn, D;
+    int F, Fn, D, Ft;
     SlotMeta meta;
     int32_t pad_row[RBX_MAX_SLOTS];
 };
@@ -162,7 +162,7 @@ __global__ void __launch_bounds__(kThreads, RBX_FWD_MINB) k_embed_fm_fwd(const _
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int lig = lane & (LPR - 1), gi = lane / LPR;
-    const int F = p.F, Fn = p.Fn, Ft = p.F + p.Fn;
+    const int F = p.F, Fn = p.Fn, Ft = p.Ft;
     const float bias = p.lr_bias ? __ldg(p.lr_bias) : 0.f;
     const uint64_t pol_keep = l2_policy_evict_last(), pol_stream = l2_policy_evict_first();
     (void)pol_keep; (void)pol_stream;
@@ -278,7 +278,7 @@ __global__ void __launch_bounds__(kThreads, RBX_FWD_MINB) k_embed_fm_fwd(const _
 template <int KD>
 __global__ void __launch_bounds__(kThreads) k_embed_fm_fwd_scalar(const __grid_constant__ FwdParams p) {
     const int lane = threadIdx.x & 31;
-    const int F = p.F, Fn = p.Fn, Ft = p.F + p.Fn, D = p.D;
+    const int F = p.F, Fn = p.Fn, Ft = p.Ft, D = p.D;
     const int64_t warp0 = (int64_t)blockIdx.x * kWarps + (threadIdx.x >> 5);
     const int64_t nwarps = (int64_t)gridDim.x * kWarps;
     const float bias = p.lr_bias ? __ldg(p.lr_bias) : 0.f;
@@ -351,7 +351,7 @@ __global__ void __launch_bounds__(kThreads, RBX_BWD_MINB) k_embed_fm_bwd(const _
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int lig = lane & (LPR - 1), gi = lane / LPR;
-    const int F = p.F, Ft = p.F + p.Fn;
+    const int F = p.F, Ft = p.Ft;
     const bool has_fm = p.d_fm != nullptr;
     const uint64_t pol_keep = l2_policy_evict_last(), pol_stream = l2_policy_evict_first();
     (void)pol_keep; (void)pol_stream;
@@ -442,7 +442,7 @@ __global__ void __launch_bounds__(kThreads, RBX_BWD_MINB) k_embed_fm_bwd(const _
 // backward, scalar path (any D): warp per sample
 __global__ void __launch_bounds__(kThreads) k_embed_fm_bwd_scalar(const __grid_constant__ BwdParams p) {
     const int lane = threadIdx.x & 31;
-    const int F = p.F, Ft = p.F + p.Fn, D = p.D;
+    const int F = p.F, Ft = p.Ft, D = p.D;
     const int64_t warp0 = (int64_t)blockIdx.x * kWarps + (threadIdx.x >> 5);
     const int64_t nwarps = (int64_t)gridDim.x * kWarps;
     const bool has_fm = p.d_fm != nullptr;
@@ -480,7 +480,7 @@ __global__ void __launch_bounds__(kThreads) k_dense_w_bwd_vec(const __grid_const
     __shared__ float4 s_acc[kThreads];
     __shared__ float s_lr[RBX_MAX_SLOTS + 1];
     for (int i = threadIdx.x; i <= p.Fn; i += kThreads) s_lr[i] = 0.f;
-    const int Fn = p.Fn, D = p.D, Ft = p.F + p.Fn, V = D / 4;
+    const int Fn = p.Fn, D = p.D, Ft = p.Ft, V = D / 4;
     const int R4 = Fn * V;                       // vector roles (<= kThreads, host-checked)
     const int SUB = kThreads / R4;               // sample lanes
     const int t = threadIdx.x;
@@ -534,7 +534,7 @@ __global__ void __launch_bounds__(kThreads) k_dense_w_bwd_vec(const __grid_const
 // generic scalar kernel: role r of a CTA column (any D, any Fn); also covers the first-order roles
 // when the vector kernel has no spare threads (first_role selects where to start)
 __global__ void __launch_bounds__(kThreads) k_dense_w_bwd(const __grid_constant__ BwdParams p, int first_role) {
-    const int Fn = p.Fn, D = p.D, Ft = p.F + p.Fn;
+    const int Fn = p.Fn, D = p.D, Ft = p.Ft;
     const int role = first_role + blockIdx.y * kThreads + threadIdx.x;
     const int n_w = Fn * D;
     if (role > n_w + Fn) return;
@@ -595,9 +595,8 @@ int grid_for(const void* kernel, size_t smem, int64_t warps_needed) {
     return ctas < 1 ? 1 : (int)ctas;
 }
 
-int fill_meta(SlotMeta& m, const int32_t* cat_pos, int F, const int32_t* num_pos, int Fn, const int32_t* num_widx,
+int fill_meta(SlotMeta& m, const int32_t* cat_pos, int F, const int32_t* num_pos, int Fn, int Ft, const int32_t* num_widx,
               const int32_t* lr_delta, const char* who) {
-    const int Ft = F + Fn;
     for (int f = 0; f < F; ++f) m.lr_delta[f] = lr_delta ? lr_delta[f] : 0;
     for (int n = 0; n < Fn; ++n) {
         const int w = num_widx ? num_widx[n] : n;
@@ -676,13 +675,15 @@ extern "C" {
 int rbx_embed_fm_fwd(const float* table, const float* table_lr, const int32_t* rows, const int32_t* cat_pos,
                      const int32_t* lr_delta, const float* dense_x, const float* dense_w, const float* dense_w_lr,
                      const int32_t* num_pos, const int32_t* num_widx, const float* lr_bias, float* E, float* S,
-                     float* fm_out, float* lr_out, int64_t B, int64_t R, int F, int Fn, int D, rbx_stream_t stream) {
+                     float* fm_out, float* lr_out, int64_t B, int64_t R, int F, int Fn, int D, int n_slots, rbx_stream_t stream) {
     const char* who = "rbx_embed_fm_fwd";
     RBX_REQUIRE(B >= 0 && F >= 0 && Fn >= 0 && D >= 1, "%s: negative size", who);
     RBX_REQUIRE(F <= RBX_MAX_SLOTS && Fn <= RBX_MAX_SLOTS, "%s: more than %d slots", who, RBX_MAX_SLOTS);
     RBX_REQUIRE(D <= RBX_MAX_DIM, "%s: D=%d > %d", who, D, RBX_MAX_DIM);
     RBX_REQUIRE(R >= 0 && R <= INT32_MAX, "%s: R=%lld outside int32 row ids", who, (long long)R);
     if (B == 0 || F + Fn == 0) return RBX_OK;
+    if (n_slots <= 0) n_slots = F + Fn;
+    RBX_REQUIRE(n_slots >= F + Fn, "%s: n_slots=%d < F + Fn", who, n_slots);
     const bool lr_only = !E && !S && !fm_out;   // LogisticRegression alone: no D-dim tables needed
     RBX_REQUIRE(F == 0 || (rows && cat_pos && (table || lr_only)), "%s: table/rows/cat_pos required when F > 0", who);
     RBX_REQUIRE(Fn == 0 || (dense_x && num_pos && (dense_w || lr_only)), "%s: dense_x/dense_w/num_pos required when Fn > 0", who);
@@ -691,8 +692,8 @@ int rbx_embed_fm_fwd(const float* table, const float* table_lr, const int32_t* r
     FwdParams p;
     p.table = table; p.table_lr = table_lr; p.rows = rows; p.dense_x = dense_x; p.dense_w = dense_w;
     p.dense_w_lr = dense_w_lr; p.lr_bias = lr_bias; p.E = E; p.S = S; p.fm_out = fm_out; p.lr_out = lr_out;
-    p.B = B; p.R = R; p.F = F; p.Fn = Fn; p.D = D;
-    if (int rc = fill_meta(p.meta, cat_pos, F, num_pos, Fn, num_widx, lr_delta, who)) return rc;
+    p.B = B; p.R = R; p.F = F; p.Fn = Fn; p.D = D; p.Ft = n_slots;
+    if (int rc = fill_meta(p.meta, cat_pos, F, num_pos, Fn, n_slots, num_widx, lr_delta, who)) return rc;
     cudaStream_t st = rbx_cast_stream(stream);
     const bool aligned = al16(table) && al16(dense_w) && al16(E) && al16(S);
     if (D % 4 == 0 && D <= 128 && (D & (D - 1)) == 0 && aligned) {
@@ -721,13 +722,15 @@ int rbx_embed_fm_bwd(const float* table, const int32_t* rows, const int32_t* cat
                      const int32_t* lr_delta, const float* dense_x, const float* dense_w, const int32_t* num_pos,
                      const int32_t* num_widx, const float* E, const float* S, const float* dE, const float* d_fm,
                      const float* d_lr, float* g_table, float* g_table_lr, float* g_dense_w, float* g_dense_w_lr,
-                     float* g_lr_bias, int64_t B, int64_t R, int F, int Fn, int D, rbx_stream_t stream) {
+                     float* g_lr_bias, int64_t B, int64_t R, int F, int Fn, int D, int n_slots, rbx_stream_t stream) {
     const char* who = "rbx_embed_fm_bwd";
     RBX_REQUIRE(B >= 0 && F >= 0 && Fn >= 0 && D >= 1, "%s: negative size", who);
     RBX_REQUIRE(F <= RBX_MAX_SLOTS && Fn <= RBX_MAX_SLOTS, "%s: more than %d slots", who, RBX_MAX_SLOTS);
     RBX_REQUIRE(D <= RBX_MAX_DIM, "%s: D=%d > %d", who, D, RBX_MAX_DIM);
     RBX_REQUIRE(R >= 0 && R <= INT32_MAX, "%s: R=%lld outside int32 row ids", who, (long long)R);
     if (B == 0 || F + Fn == 0) return RBX_OK;
+    if (n_slots <= 0) n_slots = F + Fn;
+    RBX_REQUIRE(n_slots >= F + Fn, "%s: n_slots=%d < F + Fn", who, n_slots);
     RBX_REQUIRE(F == 0 || (rows && cat_pos), "%s: rows/cat_pos required when F > 0", who);
     const bool lr_only = !dE && !d_fm;
     RBX_REQUIRE(Fn == 0 || (dense_x && num_pos && (dense_w || lr_only)), "%s: dense_x/dense_w/num_pos required when Fn > 0", who);
@@ -737,8 +740,8 @@ int rbx_embed_fm_bwd(const float* table, const int32_t* rows, const int32_t* cat
     BwdParams p;
     p.table = table; p.rows = rows; p.dense_x = dense_x; p.dense_w = dense_w; p.E = E; p.S = S; p.dE = dE;
     p.d_fm = d_fm; p.d_lr = d_lr; p.g_table = g_table; p.g_table_lr = g_table_lr; p.g_dense_w = g_dense_w;
-    p.g_dense_w_lr = g_dense_w_lr; p.g_lr_bias = g_lr_bias; p.B = B; p.R = R; p.F = F; p.Fn = Fn; p.D = D;
-    if (int rc = fill_meta(p.meta, cat_pos, F, num_pos, Fn, num_widx, lr_delta, who)) return rc;
+    p.g_dense_w_lr = g_dense_w_lr; p.g_lr_bias = g_lr_bias; p.B = B; p.R = R; p.F = F; p.Fn = Fn; p.D = D; p.Ft = n_slots;
+    if (int rc = fill_meta(p.meta, cat_pos, F, num_pos, Fn, n_slots, num_widx, lr_delta, who)) return rc;
     for (int f = 0; f < F; ++f) p.pad_row[f] = pad_row ? pad_row[f] : -1;
     cudaStream_t st = rbx_cast_stream(stream);
 

@@ -234,6 +234,62 @@ __global__ void __launch_bounds__(kThreads) k_pooled_bwd_any(const float* __rest
     }
 }
 
+// ------------------------------------------------------------------ pooling of a materialised [B,L,D]
+// (MaskedSumPooling / MaskedAveragePooling called directly on an embedding tensor: sequence.py:4-20,
+// pooling.py:22-40).  One warp per sample, lane d owns columns d, d+32, ...; mask (uint8 [B,L]) is
+// optional -- without it the reference's rule applies (row element-sum != 0).
+__global__ void __launch_bounds__(kThreads) k_pool_fwd(const float* __restrict__ emb, const uint8_t* __restrict__ mask,
+                                                      float* __restrict__ out, float* __restrict__ cnt, int64_t B, int L,
+                                                      int D, int mode) {
+    constexpr int KD = RBX_MAX_DIM / 32;
+    const int lane = threadIdx.x & 31;
+    const int64_t warp0 = (int64_t)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
+    const int64_t nwarps = (int64_t)gridDim.x * (kThreads / 32);
+    for (int64_t b = warp0; b < B; b += nwarps) {
+        float acc[KD];
+#pragma unroll
+        for (int k = 0; k < KD; ++k) acc[k] = 0.f;
+        float n = 0.f;
+        for (int l = 0; l < L; ++l) {
+            const float* row = emb + ((size_t)b * L + l) * D;
+            float rs = 0.f;
+#pragma unroll
+            for (int k = 0; k < KD; ++k) {
+                const int d = lane + 32 * k;
+                if (d < D) {
+                    const float e = ld_stream_f1(row + d);
+                    acc[k] += e;
+                    rs += e;
+                }
+            }
+            if (mode == 1) {
+                if (mask) n += mask[b * L + l] ? 1.f : 0.f;
+                else n += (group_sum<32>(rs) != 0.f) ? 1.f : 0.f;
+            }
+        }
+        const float den = n + 1e-12f;
+#pragma unroll
+        for (int k = 0; k < KD; ++k) {
+            const int d = lane + 32 * k;
+            if (d < D) out[(size_t)b * D + d] = mode == 1 ? acc[k] / den : acc[k];
+        }
+        if (cnt && lane == 0) cnt[b] = n;
+    }
+}
+
+// d_emb[b,l,:] = g[b,:] / (cnt[b] + 1e-12)  (mode 1)  |  g[b,:]  (mode 0): the sum's gradient reaches
+// every position, masked or not, exactly as autograd does for sequence.py:8-12
+__global__ void __launch_bounds__(kThreads) k_pool_bwd(const float* __restrict__ g, const float* __restrict__ cnt,
+                                                      float* __restrict__ d_emb, int64_t B, int L, int D, int mode) {
+    const int64_t n = B * (int64_t)L * D;
+    for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < n; i += (int64_t)gridDim.x * kThreads) {
+        const int64_t b = i / ((int64_t)L * D);
+        const int d = (int)(i % D);
+        const float x = __ldg(g + b * D + d);
+        d_emb[i] = mode == 1 ? x / (__ldg(cnt + b) + 1e-12f) : x;
+    }
+}
+
 }  // namespace
 
 #define RBX_DISPATCH_LPR(D, CALL)                   \
@@ -316,6 +372,33 @@ int rbx_pooled_gather_bwd(const float* g, int64_t g_ld, const int32_t* ids, int6
     } else {
         k_pooled_bwd_any<<<capped_grid(B, 4), kThreads, 0, st>>>(g, g_ld, ids, ids_ld, cnt, pad_row, g_table, B, L, D, mode);
     }
+    RBX_LAUNCH_CHECK(who);
+    return RBX_OK;
+}
+
+int rbx_pool_fwd(const float* emb, const uint8_t* mask, float* out, float* cnt, int64_t B, int L, int D, int mode,
+                 rbx_stream_t stream) {
+    const char* who = "rbx_pool_fwd";
+    RBX_REQUIRE(B >= 0 && L >= 0 && D >= 1 && D <= RBX_MAX_DIM, "%s: bad size", who);
+    RBX_REQUIRE(mode == 0 || mode == 1, "%s: mode %d", who, mode);
+    if (B == 0) return RBX_OK;
+    RBX_REQUIRE((emb || L == 0) && out, "%s: null pointer", who);
+    k_pool_fwd<<<capped_grid(B, 8), kThreads, 0, rbx_cast_stream(stream)>>>(emb, mask, out, cnt, B, L, D, mode);
+    RBX_LAUNCH_CHECK(who);
+    return RBX_OK;
+}
+
+int rbx_pool_bwd(const float* g, const float* cnt, float* d_emb, int64_t B, int L, int D, int mode, rbx_stream_t stream) {
+    const char* who = "rbx_pool_bwd";
+    RBX_REQUIRE(B >= 0 && L >= 0 && D >= 1 && D <= RBX_MAX_DIM, "%s: bad size", who);
+    RBX_REQUIRE(mode == 0 || (mode == 1 && cnt), "%s: mode %d / cnt", who, mode);
+    if (B == 0 || L == 0) return RBX_OK;
+    RBX_REQUIRE(g && d_emb, "%s: null pointer", who);
+    const int64_t n = B * (int64_t)L * D;
+    int64_t grid = (n + kThreads - 1) / kThreads;
+    const int64_t cap = (int64_t)rbx_sm_count() * 16;
+    if (grid > cap) grid = cap;
+    k_pool_bwd<<<(int)grid, kThreads, 0, rbx_cast_stream(stream)>>>(g, cnt, d_emb, B, L, D, mode);
     RBX_LAUNCH_CHECK(who);
     return RBX_OK;
 }

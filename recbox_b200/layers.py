@@ -43,31 +43,24 @@ I32, F32 = torch.int32, torch.float32
 # pooling layers (feature_encoder / embedding_callback targets)
 # =================================================================================================
 class _PoolFn(torch.autograd.Function):
-    """[B,L,D] -> [B,D] pooling of an already materialised tensor, forward via torch reductions is
-    NOT used: this path is the plain-tensor entry (someone calls the pooling module directly on an
-    embedding tensor); the fused id -> pooled path lives in _PooledGatherFn."""
+    """[B,L,D] -> [B,D] pooling of an already materialised tensor (someone calls the pooling module
+    directly on an embedding tensor); the fused id -> pooled path lives in _PooledGatherFn."""
 
     @staticmethod
     def forward(ctx, emb, mask, average):
-        s = emb.sum(dim=1)
-        if not average:
-            ctx.save_for_backward()
-            ctx.meta = (emb.shape, None)
-            return s
-        if mask is None:
-            mask = emb.sum(dim=-1) != 0
-        den = mask.float().sum(-1, keepdim=True) + 1e-12
-        ctx.save_for_backward(den)
-        ctx.meta = (emb.shape, True)
-        return s / den
+        if not emb.is_cuda:
+            raise RbxError("recbox_b200 layers have no CPU path")
+        mode = 1 if average else 0
+        out, cnt = ops.pool_fwd(emb.contiguous(), mask, mode)
+        ctx.save_for_backward(cnt)
+        ctx.meta = (tuple(emb.shape), mode)
+        return out
 
     @staticmethod
     def backward(ctx, g):
-        shape, avg = ctx.meta
-        if avg:
-            (den,) = ctx.saved_tensors
-            g = g / den
-        return g.unsqueeze(1).expand(shape), None, None
+        (cnt,) = ctx.saved_tensors
+        shape, mode = ctx.meta
+        return ops.pool_bwd(g.contiguous(), cnt, shape, mode), None, None
 
 
 class MaskedAveragePooling(nn.Module):
@@ -195,7 +188,7 @@ class _FusedStore(object):
 class _Call(object):
     """Static description of one fused launch (built once per feature selection, cached)."""
     __slots__ = ("D", "F", "Fn", "Ft", "cat_pos", "num_pos", "num_widx", "pad_row", "lr_delta", "group",
-                 "lr_group", "lr_bias", "params", "kinds", "emb_sizes", "lr_emb_sizes", "with_main", "with_lr")
+                 "lr_group", "lr_bias", "params", "kinds", "emb_sizes", "lr_emb_sizes", "with_main", "with_lr", "seq")
 
 
 class _FusedEmbedFn(torch.autograd.Function):
@@ -203,11 +196,13 @@ class _FusedEmbedFn(torch.autograd.Function):
     autograd tracks them; the kernels read the fused buffers they alias."""
 
     @staticmethod
-    def forward(ctx, call, rows, dense_x, *params):
+    def forward(ctx, call, rows, dense_x, seq_ids, *params):
         g, lg = call.group, call.lr_group
+        seq = call.seq or ()
         want_E = call.with_main
-        want_fm = call.with_main
+        want_fm = call.with_main and not seq          # pooled sequence slots are not in the kernel's FM sums
         want_lr = call.with_lr
+        B = (rows if rows is not None else (dense_x if dense_x is not None else seq_ids[0])).shape[0]
         E, S, fm, lr = ops.embed_fm_fwd(
             g.table if (g is not None and call.F) else None,
             lg.table.view(-1) if (lg is not None and call.F) else None,
@@ -215,21 +210,30 @@ class _FusedEmbedFn(torch.autograd.Function):
             g.dense_w if (g is not None and call.Fn) else None,
             lg.dense_w.view(-1) if (lg is not None and call.Fn) else None,
             call.num_pos, call.lr_bias.data if call.lr_bias is not None else None,
-            want_E=want_E, want_S=want_fm, want_fm=want_fm, want_lr=want_lr,
-            B=(rows if rows is not None else dense_x).shape[0],
-            lr_delta=call.lr_delta, num_widx=call.num_widx, D=call.D)
+            want_E=want_E, want_S=want_fm, want_fm=want_fm, want_lr=want_lr, B=B,
+            lr_delta=call.lr_delta, num_widx=call.num_widx, D=call.D, n_slots=call.Ft,
+            device=(g.table if g.table is not None else g.dense_w).device if g is not None else None)
+        cnts = []
+        for sq, ids in zip(seq, seq_ids):              # a9: pooled sequence slots, straight into their slot of E
+            _, cnt = ops.pooled_gather_fwd(g.table, ids, sq["mode"], out=E[:, sq["pos"], :])
+            cnts.append(cnt)
         ctx.call = call
-        ctx.save_for_backward(rows, dense_x, E, S)
-        outs = (E, fm.view(-1, 1) if fm is not None else None, lr.view(-1, 1) if lr is not None else None)
-        ctx.mark_non_differentiable(*[o for o in () if o is not None])
-        return outs
+        ctx.n_seq = len(seq)
+        ctx.has_cnt = [c is not None for c in cnts]
+        ctx.save_for_backward(rows, dense_x, E if want_fm else None, S, *seq_ids, *[c for c in cnts if c is not None])
+        return (E, fm.view(-1, 1) if fm is not None else None, lr.view(-1, 1) if lr is not None else None)
 
     @staticmethod
     def backward(ctx, dE, d_fm, d_lr):
         call = ctx.call
-        rows, dense_x, E, S = ctx.saved_tensors
+        saved = ctx.saved_tensors
+        rows, dense_x, E, S = saved[:4]
+        seq_ids = saved[4:4 + ctx.n_seq]
+        cnt_it = iter(saved[4 + ctx.n_seq:])
+        cnts = [next(cnt_it) if h else None for h in ctx.has_cnt]
         g, lg = call.group, call.lr_group
-        dev = (rows if rows is not None else dense_x).device
+        dev = (rows if rows is not None else (dense_x if dense_x is not None else seq_ids[0])).device
+        B = (rows if rows is not None else (dense_x if dense_x is not None else seq_ids[0])).shape[0]
         D = call.D
         have_main = call.with_main and (dE is not None or d_fm is not None)
         have_lr = call.with_lr and d_lr is not None
@@ -249,16 +253,19 @@ class _FusedEmbedFn(torch.autograd.Function):
         g_t1 = buf[offs[2]:offs[2] + n_t1] if n_t1 else None
         g_dw1 = buf[offs[3]:offs[3] + n_w1] if n_w1 else None
         g_b = buf[offs[4]:offs[4] + 1] if n_b else None
-        if have_main or have_lr:
+        dE = dE.contiguous() if (dE is not None and have_main) else None
+        if (have_main or have_lr) and (call.F or call.Fn):
             ops.embed_fm_bwd(
                 g.table if (g is not None and g.emb) else None, rows, call.cat_pos, call.pad_row, dense_x,
                 g.dense_w if (g is not None and g.lin) else None, call.num_pos,
-                E, S,
-                dE.contiguous() if (dE is not None and have_main) else None,
-                d_fm.contiguous().view(-1) if (d_fm is not None and have_main) else None,
+                E, S, dE,
+                d_fm.contiguous().view(-1) if (d_fm is not None and have_main and S is not None) else None,
                 d_lr.contiguous().view(-1) if have_lr else None,
                 g_table, g_t1, g_dw, g_dw1, g_b, D, g.R if (g is not None and g.emb) else (lg.R if lg is not None else 0),
-                B=(rows if rows is not None else dense_x).shape[0], lr_delta=call.lr_delta, num_widx=call.num_widx)
+                B=B, lr_delta=call.lr_delta, num_widx=call.num_widx, n_slots=call.Ft)
+        if dE is not None and g_table is not None:
+            for sq, ids, cnt in zip(call.seq or (), seq_ids, cnts):
+                ops.pooled_gather_bwd(dE[:, sq["pos"], :], ids, cnt, sq["pad_row"], g_table, sq["mode"])
         # hand the per-parameter views back to autograd (they alias `buf`; AccumulateGrad adopts them)
         t_views = g_table.split(call.emb_sizes, 0) if g_table is not None else None
         t1_views = g_t1.split(call.lr_emb_sizes, 0) if g_t1 is not None else None
@@ -275,9 +282,9 @@ class _FusedEmbedFn(torch.autograd.Function):
             else:
                 grads.append(g_b if g_b is not None else None)
         for i, p in enumerate(call.params):
-            if not ctx.needs_input_grad[3 + i]:
+            if not ctx.needs_input_grad[4 + i]:
                 grads[i] = None
-        return (None, None, None) + tuple(grads)
+        return (None, None, None, None) + tuple(grads)
 
 
 class _GatherFn(torch.autograd.Function):
@@ -459,11 +466,11 @@ class _FusedDictBase(nn.Module):
         if plan["uniform"] and (fused or seq_pool):
             D = next(iter(dims))
             plan["D"] = D
-            plan["call"] = self._make_call(names, fused, D, None)
+            plan["call"] = self._make_call(names, fused, D, None, seq_pool)
         self._calls[key] = plan
         return plan
 
-    def _make_call(self, names, fused, D, lr_module):
+    def _make_call(self, names, fused, D, lr_module, seq_pool=()):
         """Static launch description for the `fused` features placed at their positions among
         `names`; with lr_module (a LogisticRegression over the same features) the first-order term
         is computed in the same launch."""
@@ -485,6 +492,13 @@ class _FusedDictBase(nn.Module):
             c.pad_row.append(-1 if pi is None else o + pi)
         c.with_main, c.with_lr = True, False
         c.lr_group, c.lr_bias, c.lr_delta = None, None, None
+        enc = self._encoders()
+        c.seq = []
+        for n in seq_pool:
+            m = self.embedding_layers[n]
+            o = g.emb_off[id(m)]
+            c.seq.append({"name": n, "pos": pos[n], "off": o, "mode": _pool_mode(enc[n]),
+                          "pad_row": -1 if m.padding_idx is None else o + m.padding_idx})
         params, kinds = [], []
         for i, m in enumerate(g.emb):
             params.append(m.weight)
@@ -564,9 +578,8 @@ class _FusedDictBase(nn.Module):
                     plan["lr_call"] = pc
                 call, cn, use_lr = pc[0], pc[1], partner
             rows, dense_x = self._pack(inputs, cn["cats"], cn["nums"], cn["offs"])
-            E, fm, lr = _FusedEmbedFn.apply(call, rows, dense_x, *call.params)
-            for name in plan["seq_pool"]:          # pooled sequence slots: written by their own kernel
-                E = self._fill_seq_slot(E, inputs, name, names.index(name), enc[name])
+            seq_ids = tuple(self._seq_rows(inputs[sq["name"]], sq["off"]) for sq in call.seq)
+            E, fm, lr = _FusedEmbedFn.apply(call, rows, dense_x, seq_ids, *call.params)
             if not plan["seq_pool"]:
                 st = _Stash()
                 st.X, st.fm, st.lr, st.lr_owner, st.producer = inputs, fm, lr, use_lr, weakref.ref(self)
@@ -601,32 +614,21 @@ class _FusedDictBase(nn.Module):
             out[name] = e
         return out
 
-    def _fill_seq_slot(self, E, inputs, name, pos, encoder):
-        mod = self.embedding_layers[name]
-        ids = inputs[name]
+    @staticmethod
+    def _seq_rows(ids, off):
+        """[B, L] ids (float64 / int64 / int32 as the loader delivers them) -> int32 global rows."""
         if not ids.is_cuda:
             raise RbxError("recbox_b200 layers need CUDA inputs (no CPU path)")
-        pooled = _PooledGatherFn.apply(mod.weight, ids.to(I32).contiguous(), mod.padding_idx, _pool_mode(encoder))
-        return _SetSlotFn.apply(E, pooled, pos)
+        if ids.dim() != 2:
+            ids = ids.reshape(ids.shape[0], -1)
+        L = ids.shape[1]
+        if L == 0 or L > 192:
+            out = ids.to(I32)
+            return (out + off if off else out).contiguous()
+        return ops.pack_columns([ids[:, l] for l in range(L)], add=[off] * L, as_rows=True)
 
     def _full_key(self):
         return ((), ())
-
-
-class _SetSlotFn(torch.autograd.Function):
-    """E[:, pos, :] = v, in place (E's slot `pos` was left unwritten by the fused launch)."""
-
-    @staticmethod
-    def forward(ctx, E, v, pos):
-        ctx.pos = pos
-        ctx.mark_dirty(E)
-        E[:, pos, :] = v
-        return E
-
-    @staticmethod
-    def backward(ctx, g):
-        gv = g[:, ctx.pos, :]
-        return g, gv, None
 
 
 # =================================================================================================
@@ -855,12 +857,12 @@ class LogisticRegression(nn.Module):
             lo.params = [m.weight for m in g.emb] + [m.weight for m in g.lin] + ([self.bias] if self.bias is not None else [])
             lo.kinds = [("lr_emb", i) for i in range(len(g.emb))] + [("lr_lin", i) for i in range(len(g.lin))] + \
                        ([("bias", 0)] if self.bias is not None else [])
-            lo.lr_emb_sizes, lo.emb_sizes = [m.num_embeddings for m in g.emb], []
+            lo.lr_emb_sizes, lo.emb_sizes, lo.seq = [m.num_embeddings for m in g.emb], [], []
             c = (lo, cn)
             plan["lr_only"] = c
         call, cn = c
         rows, dense_x = d._pack(X, cn["cats"], cn["nums"], cn["offs"])
-        _, _, lr = _FusedEmbedFn.apply(call, rows, dense_x, *call.params)
+        _, _, lr = _FusedEmbedFn.apply(call, rows, dense_x, (), *call.params)
         return lr
 
 

@@ -83,18 +83,19 @@ def pack_columns(cols, add=None, as_rows=True):
 
 # ---------------------------------------------------------------------------------- K1 / K2 / K3
 def embed_fm_fwd(table, table_lr, rows, cat_pos, dense_x, dense_w, dense_w_lr, num_pos, lr_bias,
-                 want_E=True, want_S=True, want_fm=True, want_lr=True, B=None, lr_delta=None, num_widx=None, D=None):
+                 want_E=True, want_S=True, want_fm=True, want_lr=True, B=None, lr_delta=None, num_widx=None, D=None,
+                 n_slots=None, device=None):
     """Fused gather + FM + LR forward.  Returns (E, S, fm_out, lr_out); unrequested ones are None."""
     F = len(cat_pos)
     Fn = len(num_pos)
     ref = table if table is not None else (dense_w if dense_w is not None else (rows if rows is not None else dense_x))
     if D is None:
         D = ref.shape[-1] if (table is not None or dense_w is not None) else 1
-    dev = ref.device
+    dev = device if device is not None else ref.device
     if B is None:
         B = rows.shape[0] if rows is not None else dense_x.shape[0]
-    R = table.shape[0] if table is not None else 0
-    Ft = F + Fn
+    R = table.shape[0] if table is not None else (table_lr.numel() if table_lr is not None else 0)
+    Ft = n_slots or (F + Fn)
     E = torch.empty((B, Ft, D), dtype=F32, device=dev) if want_E else None
     S = torch.empty((B, D), dtype=F32, device=dev) if want_S else None
     fm = torch.empty((B,), dtype=F32, device=dev) if want_fm else None
@@ -103,12 +104,13 @@ def embed_fm_fwd(table, table_lr, rows, cat_pos, dense_x, dense_w, dense_w_lr, n
           _i32(cat_pos), _i32(lr_delta) if lr_delta is not None else None, _p(dense_x, F32, "dense_x"),
           _p(dense_w, F32, "dense_w"), _p(dense_w_lr, F32, "dense_w_lr"), _i32(num_pos),
           _i32(num_widx) if num_widx is not None else None, _p(lr_bias, F32, "lr_bias"),
-          _p(E), _p(S), _p(fm), _p(lr), B, R, F, Fn, D, _stream())
+          _p(E), _p(S), _p(fm), _p(lr), B, R, F, Fn, D, Ft, _stream())
     return E, S, fm, lr
 
 
 def embed_fm_bwd(table, rows, cat_pos, pad_row, dense_x, dense_w, num_pos, E, S, dE, d_fm, d_lr,
-                 g_table, g_table_lr, g_dense_w, g_dense_w_lr, g_lr_bias, D, R, B=None, lr_delta=None, num_widx=None):
+                 g_table, g_table_lr, g_dense_w, g_dense_w_lr, g_lr_bias, D, R, B=None, lr_delta=None, num_widx=None,
+                 n_slots=None):
     """Gradient scatter-add (accumulates into the g_* tensors, which the caller zero-fills)."""
     F = len(cat_pos)
     Fn = len(num_pos)
@@ -120,7 +122,8 @@ def embed_fm_bwd(table, rows, cat_pos, pad_row, dense_x, dense_w, num_pos, E, S,
           _i32(num_widx) if num_widx is not None else None, _p(E, F32, "E"), _p(S, F32, "S"), _p(dE, F32, "dE"),
           _p(d_fm, F32, "d_fm"), _p(d_lr, F32, "d_lr"), _p(g_table, F32, "g_table"),
           _p(g_table_lr, F32, "g_table_lr"), _p(g_dense_w, F32, "g_dense_w"),
-          _p(g_dense_w_lr, F32, "g_dense_w_lr"), _p(g_lr_bias, F32, "g_lr_bias"), B, R, F, Fn, D, _stream())
+          _p(g_dense_w_lr, F32, "g_dense_w_lr"), _p(g_lr_bias, F32, "g_lr_bias"), B, R, F, Fn, D, n_slots or (F + Fn),
+          _stream())
 
 
 # ------------------------------------------------------------------------------------- a5 / a9
@@ -164,6 +167,26 @@ def pooled_gather_bwd(g, ids, cnt, pad_row, g_table, mode):
     _call("rbx_pooled_gather_bwd", ctypes.c_void_p(g.data_ptr()), g.stride(0), ctypes.c_void_p(ids.data_ptr()),
           ids.stride(0), _p(cnt, F32, "cnt"), -1 if pad_row is None else int(pad_row), _p(g_table, F32, "g_table"),
           B, L, D, mode, _stream())
+
+
+def pool_fwd(emb, mask, mode):
+    """materialised emb [B,L,D] (+ optional bool/uint8 mask [B,L]) -> (out [B,D], cnt [B] | None)."""
+    B, L, D = emb.shape
+    out = torch.empty((B, D), dtype=F32, device=emb.device)
+    cnt = torch.empty((B,), dtype=F32, device=emb.device) if mode == 1 else None
+    if mask is not None:
+        mask = mask.to(torch.uint8).contiguous()
+        if tuple(mask.shape) != (B, L):
+            raise RbxError("pool_fwd: mask must be [B, L]")
+    _call("rbx_pool_fwd", _p(emb, F32, "emb"), _p(mask, torch.uint8, "mask"), _p(out), _p(cnt), B, L, D, mode, _stream())
+    return out, cnt
+
+
+def pool_bwd(g, cnt, shape, mode):
+    B, L, D = shape
+    d_emb = torch.empty(shape, dtype=F32, device=g.device)
+    _call("rbx_pool_bwd", _p(g, F32, "g"), _p(cnt, F32, "cnt"), _p(d_emb), B, L, D, mode, _stream())
+    return d_emb
 
 
 # ------------------------------------------------------------------------------------------ a10

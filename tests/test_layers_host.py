@@ -1,0 +1,167 @@
+"""Host-side logic of the layer API (no GPU): construction, parameter naming, seeded init,
+fused-storage aliasing, install() rebinding, and the "no CPU path" contract."""
+from collections import OrderedDict
+
+import numpy as np
+import pytest
+import torch
+from torch import nn
+
+from test_oracle_golden import load, ranking_features
+
+from recbox_b200 import RbxError, layers
+from recbox_b200.features import FeatureMap, MatchingFeatureMap
+
+
+def feature_map(tag, D):
+    fm = FeatureMap("golden", ".")
+    for k, v in ranking_features(tag).items():
+        fm.features[k] = dict(v)
+    fm.finalize(["label"])
+    fm.default_emb_dim = D
+    return fm
+
+
+def test_state_dict_keys_and_seeded_init_match_reference():
+    """Same seed -> same initial weights, same parameter names (golden minted from the reference:
+    oracle/make_golden.py golden_init)."""
+    g = load("init_seed2024")
+    torch.manual_seed(2024)
+    fm = feature_map("ranking_layers_share", 8)
+    emb = layers.FeatureEmbedding(fm, 8)
+    fml = layers.FactorizationMachine(fm)
+    got = OrderedDict(("emb." + k, v) for k, v in emb.state_dict().items())
+    got.update(("fm." + k, v) for k, v in fml.state_dict().items())
+    assert sorted(got) == sorted(g)
+    for k, v in got.items():
+        assert torch.equal(v, g[k]), k
+
+
+def test_per_feature_parameters_alias_one_fused_table():
+    fm = feature_map("ranking_layers_d8", 8)
+    emb = layers.FeatureEmbedding(fm, 8)
+    d = emb.embedding_layer
+    grp = d._store.groups[8]
+    assert grp.R == 11 + 7 + 13 + 11 and grp.table.shape == (grp.R, 8) and grp.dense_w.shape == (2, 8)
+    for name in ("C1", "C2", "C3", "C4"):
+        m = d.embedding_layers[name]
+        assert type(m) == nn.Embedding                       # match_model.py:92-103 scans for exactly this
+        off = grp.emb_off[id(m)]
+        assert m.weight.data_ptr() == grp.table[off].data_ptr()
+        assert float(m.weight[0].abs().sum()) == 0.0          # padding row stays zero
+    # writes through the per-feature parameter land in the fused table (checkpoint load path)
+    with torch.no_grad():
+        d.embedding_layers["C2"].weight.fill_(3.0)
+    o = grp.emb_off[id(d.embedding_layers["C2"])]
+    assert float(grp.table[o:o + 7].min()) == 3.0
+    # load_state_dict keeps the aliasing
+    sd = {k: torch.full_like(v, 2.0) for k, v in emb.state_dict().items()}
+    emb.load_state_dict(sd)
+    d._store.ensure()
+    assert float(d._store.groups[8].table.min()) == 2.0 and float(d._store.groups[8].dense_w.max()) == 2.0
+
+
+def test_shared_embedding_registers_one_module_under_two_names():
+    fm = feature_map("ranking_layers_share", 16)
+    d = layers.FeatureEmbedding(fm, 16).embedding_layer
+    assert d.embedding_layers["C4"] is d.embedding_layers["C1"]
+    assert d._store.groups[16].R == 11 + 7 + 13                 # shared table stored once
+
+
+def test_lr_layer_uses_dim_one_and_sum_pooling_for_sequences():
+    fm = feature_map("ranking_layers_seq", 8)
+    lr = layers.LogisticRegression(fm)
+    d = lr.embedding_layer.embedding_layer
+    assert d.embedding_layers["C1"].embedding_dim == 1 and d.embedding_layers["I1"].out_features == 1
+    assert type(d.feature_encoders["S1"]) is layers.MaskedSumPooling      # feature_embedding.py:66-68
+    emb = layers.FeatureEmbedding(fm, 8).embedding_layer
+    assert type(emb.feature_encoders["S1"]) is layers.MaskedAveragePooling  # from the "layers.X()" spec string
+
+
+def test_unknown_modes_raise_like_the_reference():
+    with pytest.raises(ValueError):
+        layers.InnerProductInteraction(5, output="nope")
+    fm = feature_map("ranking_layers_d8", 8)
+    fm.features["C1"]["feature_encoder"] = "layers.DoesNotExist()"
+    with pytest.raises(ValueError):
+        layers.FeatureEmbedding(fm, 8)
+
+
+def test_no_cpu_path():
+    fm = feature_map("ranking_layers_d8", 8)
+    emb = layers.FeatureEmbedding(fm, 8)
+    X = {k: torch.zeros(4, dtype=torch.float64) for k in fm.features}
+    with pytest.raises(RbxError):
+        emb(X)
+    with pytest.raises(RbxError):
+        layers.InnerProductInteraction(3, "bi_interaction")(torch.zeros(2, 3, 4))
+    with pytest.raises(RbxError):
+        layers.two_tower_score(torch.zeros(2, 4), torch.zeros(2, 3, 4))
+    with pytest.raises(RbxError):
+        layers.MaskedAveragePooling()(torch.zeros(2, 3, 4))
+
+
+def test_core_layer_construction():
+    fmap = MatchingFeatureMap(feature_specs=OrderedDict([
+        ("item_id", {"type": "categorical", "source": "item", "vocab_size": 23, "padding_idx": 22}),
+        ("user_id", {"type": "categorical", "source": "user", "vocab_size": 17}),
+        ("user_age", {"type": "numeric", "source": "user"}),
+        ("user_hist", {"type": "sequence", "source": "user", "vocab_size": 23, "padding_idx": 22,
+                       "share_embedding": "item_id", "embedding_callback": "layers.MaskedAveragePooling()"}),
+    ]))
+    layer = layers.EmbeddingLayer(fmap, 8)
+    d = layer.embedding_layer
+    assert d.embedding_layers["user_hist"] is d.embedding_layers["item_id"]
+    assert type(d.embedding_callbacks["user_hist"]) is layers.CoreMaskedAveragePooling
+    assert sorted(layer.state_dict()) == sorted("embedding_layer.embedding_layers.%s.weight" % n
+                                                for n in ("item_id", "user_id", "user_age", "user_hist"))
+
+
+@pytest.mark.reference
+def test_install_rebinds_reference_symbols():
+    """Unmodified reference model code picks the fused modules up after recbox_b200.install()."""
+    import tempfile
+
+    import recbox_b200
+    from oracle import ref_shim
+    L = ref_shim.install()
+    ref_cls = L.FeatureEmbedding
+    try:
+        done = recbox_b200.install()
+        assert ("recbox.ranking.pytorch.layers", "FeatureEmbedding") in done
+        assert L.FeatureEmbedding is layers.FeatureEmbedding and L.FactorizationMachine is layers.FactorizationMachine
+        import fuxictr.pytorch.layers as FL
+        assert FL.LogisticRegression is layers.LogisticRegression
+        import recbox.core.pytorch.layers as CL
+        assert CL.EmbeddingLayer is layers.EmbeddingLayer
+        from recbox.ranking.features import FeatureMap as RefFeatureMap
+        from recbox.ranking.pytorch.models.ranking_model import RankingModel
+        tmp = tempfile.mkdtemp()
+        fm = RefFeatureMap("golden", tmp)
+        for k, v in ranking_features("ranking_layers_d8").items():
+            fm.features[k] = dict(v)
+        fm.labels = ["label"]
+        fm.num_fields = fm.get_num_fields()
+        fm.set_column_index()
+        fm.default_emb_dim = 8
+
+        class DeepFM(RankingModel):           # FuxiCTR-style model body, verbatim against the reference API
+            def __init__(self, feature_map, **kw):
+                super(DeepFM, self).__init__(feature_map, **kw)
+                self.embedding_layer = L.FeatureEmbedding(feature_map, 8)
+                self.fm_layer = L.FactorizationMachine(feature_map)
+                self.mlp = L.MLP_Block(input_dim=feature_map.sum_emb_out_dim(), output_dim=1, hidden_units=[16, 8])
+                self.compile("adam", "binary_cross_entropy", 1e-3)
+                self.reset_parameters()
+                self.model_to_device()
+        torch.manual_seed(5)
+        m = DeepFM(fm, model_id="m", gpu=-1, verbose=0, model_root=tmp, metrics=["AUC"])
+        assert type(m.embedding_layer) is layers.FeatureEmbedding
+        g = load("deepfm_train")
+        init = {k[5:]: v for k, v in g.items() if k.startswith("init.")}
+        assert sorted(m.state_dict()) == sorted(init)
+        # reference's reset_parameters (xavier on the Linear(1,D), ranking_model.py:93-104) ran through our modules
+        assert all(m.state_dict()[k].shape == v.shape for k, v in init.items())
+    finally:
+        recbox_b200.uninstall()
+    assert L.FeatureEmbedding is ref_cls
