@@ -38,6 +38,8 @@ extern "C" {
 
 #define RBX_MAX_SLOTS      192   /* max categorical (resp. numeric) slots per call */
 #define RBX_MAX_DIM        512   /* max embedding dim */
+#define RBX_MAX_WORLD        8   /* GPUs of one NVSwitch box a table can be sharded over */
+#define RBX_PEER_HANDLE_BYTES 64 /* sizeof(cudaIpcMemHandle_t) */
 
 typedef void* rbx_stream_t;      /* cudaStream_t */
 
@@ -237,6 +239,52 @@ int rbx_shard_permute(const float* in /*DEVICE [N,D]*/, const int32_t* pos /*DEV
                       float* out /*DEVICE [N,D]*/, int64_t N, int D, rbx_stream_t stream);
 int rbx_shard_unroute(const float* recv /*DEVICE [N,D]*/, const int32_t* pos /*DEVICE [N]*/,
                       float* out /*DEVICE [N,D]*/, int64_t N, int D, rbx_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * (e)  row-sharded table over NVLink peer memory: the fused kernels with the exchange inside.
+ * No reference counterpart (the reference has no sharded embedding).
+ * Global row r lives on shard r % world (world a power of two <= RBX_MAX_WORLD) at local row
+ * r / world.  shard_tables[w] is a pointer valid on the CALLING device: this rank's own
+ * allocation for w == rank, a peer's allocation mapped with rbx_peer_open otherwise.  The forward
+ * reads remote rows with plain loads over NVLink/NVSwitch; the backward issues its reductions
+ * (red.global.add) straight into the owner's gradient table.  Everything else is
+ * rbx_embed_fm_fwd / rbx_embed_fm_bwd (rows are GLOBAL row ids; pad_row too; the first-order
+ * table shares the row numbering).  The caller separates steps with a cross-rank barrier: remote
+ * reductions of step t must land before the owner's optimizer reads its gradient shard.
+ * Covers D in {4,8,16,32,64,128} with 16-byte aligned buffers; RBX_ERR_UNSUPPORTED otherwise.
+ * ------------------------------------------------------------------------------------------ */
+int rbx_embed_fm_fwd_sharded(const float* const* shard_tables /*HOST [world] of DEVICE [R_w, D]*/,
+                             const float* const* shard_tables_lr /*HOST [world] of DEVICE [R_w] | NULL*/,
+                             int world,
+                             const int32_t* rows /*DEVICE [B,F] global rows*/, const int32_t* cat_pos,
+                             const float* dense_x, const float* dense_w, const float* dense_w_lr,
+                             const int32_t* num_pos, const int32_t* num_widx, const float* lr_bias,
+                             float* E, float* S, float* fm_out, float* lr_out,
+                             int64_t B, int64_t R /*global rows*/, int F, int Fn, int D, int n_slots,
+                             rbx_stream_t stream);
+int rbx_embed_fm_bwd_sharded(const float* const* shard_tables /*HOST [world] | NULL when E is given*/,
+                             float* const* shard_g_tables /*HOST [world] of DEVICE [R_w, D] | NULL*/,
+                             float* const* shard_g_tables_lr /*HOST [world] of DEVICE [R_w] | NULL*/,
+                             int world,
+                             const int32_t* rows, const int32_t* cat_pos, const int32_t* pad_row,
+                             const float* dense_x, const float* dense_w, const int32_t* num_pos,
+                             const int32_t* num_widx, const float* E, const float* S, const float* dE,
+                             const float* d_fm, const float* d_lr,
+                             float* g_dense_w, float* g_dense_w_lr, float* g_lr_bias,
+                             int64_t B, int64_t R, int F, int Fn, int D, int n_slots, rbx_stream_t stream);
+
+/* Peer-visible device memory (CUDA IPC; one process per GPU, all on one box).
+ * rbx_peer_alloc  : cudaMalloc'd block (IPC-exportable, unlike a caching-allocator sub-block)
+ * rbx_peer_export : 64-byte handle the owner sends to its peers (any byte transport)
+ * rbx_peer_open   : map a peer's block into this process / device; enables peer access lazily
+ * rbx_peer_close / rbx_peer_free : unmap / release
+ * rbx_peer_can_access : 1 if `device` can address `peer_device` memory directly (NVLink / PCIe P2P) */
+int rbx_peer_alloc(size_t bytes, void** ptr /*HOST out*/);
+int rbx_peer_free(void* ptr);
+int rbx_peer_export(const void* ptr, unsigned char handle[RBX_PEER_HANDLE_BYTES] /*HOST out*/);
+int rbx_peer_open(const unsigned char handle[RBX_PEER_HANDLE_BYTES], void** ptr /*HOST out*/);
+int rbx_peer_close(void* ptr);
+int rbx_peer_can_access(int device, int peer_device);
 
 /* ------------------------------------------------------------------------------------------
  * a12  clip + optimizer on the fused table  (RankingModel.train_step ranking_model.py:191-197:

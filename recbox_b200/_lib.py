@@ -94,6 +94,14 @@ SIGNATURES = {
     "rbx_shard_route": [_P, _I64, _I, _P, _c.c_size_t, _P, _P, _P, _P],
     "rbx_shard_permute": [_P, _P, _P, _I64, _I, _P],
     "rbx_shard_unroute": [_P, _P, _P, _I64, _I, _P],
+    "rbx_embed_fm_fwd_sharded": [_P, _P, _I] + [_P] * 12 + [_I64, _I64, _I, _I, _I, _I, _P],
+    "rbx_embed_fm_bwd_sharded": [_P, _P, _P, _I] + [_P] * 15 + [_I64, _I64, _I, _I, _I, _I, _P],
+    "rbx_peer_alloc": [_c.c_size_t, _P],
+    "rbx_peer_free": [_P],
+    "rbx_peer_export": [_P, _P],
+    "rbx_peer_open": [_P, _P],
+    "rbx_peer_close": [_P],
+    "rbx_peer_can_access": [_I, _I],
     "rbx_sqnorm": [_P, _I64, _P, _P],
     "rbx_clip_coef": [_P, _F, _P, _P, _P],
     "rbx_adam_dense": [_P, _P, _P, _P, _I64, _P, _F, _F, _F, _F, _I, _P],

@@ -46,6 +46,12 @@ struct FwdParams {
     int64_t B;
     int64_t R;
     int F, Fn, D, Ft;
+    // row-sharded table over NVLink peer memory (rbx_embed_fm_fwd_sharded): global row r lives on
+    // shard r & (2^wlog2 - 1) at local row r >> wlog2; shard[w] / shard_lr[w] are device pointers
+    // valid on THIS device (the local allocation, or a peer's mapped through CUDA IPC)
+    int wlog2;
+    const float* shard[RBX_MAX_WORLD];
+    const float* shard_lr[RBX_MAX_WORLD];
     SlotMeta meta;
 };
 
@@ -67,6 +73,10 @@ struct BwdParams {
     int64_t B;
     int64_t R;
     int F, Fn, D, Ft;
+    int wlog2;
+    const float* shard[RBX_MAX_WORLD];       // tables (re-gather of e when E is not given)
+    float* g_shard[RBX_MAX_WORLD];           // gradient tables of every shard (local + peer-mapped)
+    float* g_shard_lr[RBX_MAX_WORLD];
     SlotMeta meta;
     int32_t pad_row[RBX_MAX_SLOTS];
 };
@@ -97,6 +107,15 @@ constexpr int kWarps = kThreads / 32;
 #define LD_ROW(p) ld_row_f4(p)
 #define RED_ROW(p, v) red_add_f4(p, v)
 #endif
+// reductions into a peer's gradient table travel over NVLink: vector (v4) or four scalar reds
+#ifndef RBX_PEER_RED_V4
+#define RBX_PEER_RED_V4 1
+#endif
+#define RED_GRAD(p, v)                                                   \
+    do {                                                                 \
+        if (!kSharded || RBX_PEER_RED_V4) { RED_ROW(p, v); }             \
+        else { red_add_f1((p), (v).x); red_add_f1((p) + 1, (v).y); red_add_f1((p) + 2, (v).z); red_add_f1((p) + 3, (v).w); } \
+    } while (0)
 #if RBX_L2_HINTS & 2
 #define LD_STREAM(p) ld_stream_f4_hint(p, pol_stream)
 #define ST_STREAM(p, v) st_stream_f4_hint(p, v, pol_stream)
@@ -153,9 +172,33 @@ __device__ __forceinline__ void stage_words(void* dst, const void* base, int64_t
 }
 
 // ---------------------------------------------------------------------------------------------
+// row addressing: one local fused table, or 2^wlog2 shards reached through NVLink peer mappings
+// ---------------------------------------------------------------------------------------------
+template <bool kSharded, int D, typename P>
+__device__ __forceinline__ const float* row_src(const P& p, int32_t r) {
+    if constexpr (!kSharded) return p.table + (size_t)r * D;
+    else return p.shard[r & ((1 << p.wlog2) - 1)] + (size_t)(r >> p.wlog2) * D;
+}
+template <bool kSharded>
+__device__ __forceinline__ const float* lr_src(const FwdParams& p, int32_t r, int f) {
+    if constexpr (!kSharded) return p.table_lr + (r + p.meta.lr_delta[f]);
+    else return p.shard_lr[r & ((1 << p.wlog2) - 1)] + (r >> p.wlog2);
+}
+template <bool kSharded, int D>
+__device__ __forceinline__ float* grad_dst(const BwdParams& p, int32_t r) {
+    if constexpr (!kSharded) return p.g_table + (size_t)r * D;
+    else return p.g_shard[r & ((1 << p.wlog2) - 1)] + (size_t)(r >> p.wlog2) * D;
+}
+template <bool kSharded>
+__device__ __forceinline__ float* grad_lr_dst(const BwdParams& p, int32_t r, int f) {
+    if constexpr (!kSharded) return p.g_table_lr + (r + p.meta.lr_delta[f]);
+    else return p.g_shard_lr[r & ((1 << p.wlog2) - 1)] + (r >> p.wlog2);
+}
+
+// ---------------------------------------------------------------------------------------------
 // forward, vector path
 // ---------------------------------------------------------------------------------------------
-template <int LPR, int U, bool kStaged>
+template <int LPR, int U, bool kStaged, bool kSharded>
 __global__ void __launch_bounds__(kThreads, RBX_FWD_MINB) k_embed_fm_fwd(const __grid_constant__ FwdParams p) {
     constexpr int D = 4 * LPR;
     constexpr int SPW = 32 / LPR;
@@ -214,10 +257,10 @@ __global__ void __launch_bounds__(kThreads, RBX_FWD_MINB) k_embed_fm_fwd(const _
 #pragma unroll 4
             for (int f = lig; f < F; f += LPR) {
                 const int32_t r = kStaged ? rb[f] : __ldg(rb + f);
-                if ((uint32_t)r < (uint64_t)p.R) lr += __ldg(p.table_lr + (r + p.meta.lr_delta[f]));
+                if ((uint32_t)r < (uint64_t)p.R) lr += __ldg(lr_src<kSharded>(p, r, f));
             }
         }
-        for (int f0 = 0; p.table && f0 < F; f0 += U) {
+        for (int f0 = 0; (kSharded || p.table) && f0 < F; f0 += U) {
             int32_t r[U];
             float4 v[U];
 #pragma unroll
@@ -228,7 +271,7 @@ __global__ void __launch_bounds__(kThreads, RBX_FWD_MINB) k_embed_fm_fwd(const _
 #pragma unroll
             for (int u = 0; u < U; ++u) {
                 v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if ((uint32_t)r[u] < (uint64_t)p.R) v[u] = LD_ROW(p.table + (size_t)r[u] * D + 4 * lig);
+                if ((uint32_t)r[u] < (uint64_t)p.R) v[u] = LD_ROW((row_src<kSharded, D>(p, r[u]) + 4 * lig));
             }
 #pragma unroll
             for (int u = 0; u < U; ++u) {
@@ -344,7 +387,7 @@ __global__ void __launch_bounds__(kThreads) k_embed_fm_fwd_scalar(const __grid_c
 // The upstream-gradient and saved-activation loads do not depend on the ids (only the reduction
 // address does), so they are issued for the whole chunk before anything is consumed.
 // ---------------------------------------------------------------------------------------------
-template <int LPR, int U, bool kStaged>
+template <int LPR, int U, bool kStaged, bool kSharded>
 __global__ void __launch_bounds__(kThreads, RBX_BWD_MINB) k_embed_fm_bwd(const __grid_constant__ BwdParams p) {
     constexpr int D = 4 * LPR;
     constexpr int SPW = 32 / LPR;
@@ -396,15 +439,15 @@ __global__ void __launch_bounds__(kThreads, RBX_BWD_MINB) k_embed_fm_bwd(const _
             S = ld_stream_f4(p.S + (size_t)b * D + 4 * lig);
             dfm = __ldg(p.d_fm + b);
         }
-        if (p.g_table_lr && p.d_lr && valid) {
+        if ((kSharded ? p.g_shard_lr[0] != nullptr : p.g_table_lr != nullptr) && p.d_lr && valid) {
             const float dlr = __ldg(p.d_lr + b);
 #pragma unroll 4
             for (int f = lig; f < F; f += LPR) {
                 const int32_t r = kStaged ? rb[f] : __ldg(rb + f);
-                if (r != p.pad_row[f] && (uint32_t)r < (uint64_t)p.R) red_add_f1(p.g_table_lr + (r + p.meta.lr_delta[f]), dlr);
+                if (r != p.pad_row[f] && (uint32_t)r < (uint64_t)p.R) red_add_f1(grad_lr_dst<kSharded>(p, r, f), dlr);
             }
         }
-        if (p.g_table) {
+        if (kSharded ? p.g_shard[0] != nullptr : p.g_table != nullptr) {
             const bool from_table = has_fm && !p.E;
             for (int f0 = 0; f0 < F; f0 += U) {
                 int32_t r[U];
@@ -424,13 +467,13 @@ __global__ void __launch_bounds__(kThreads, RBX_BWD_MINB) k_embed_fm_bwd(const _
                 if (from_table) {
 #pragma unroll
                     for (int u = 0; u < U; ++u)
-                        if (r[u] >= 0) e[u] = LD_ROW(p.table + (size_t)r[u] * D + 4 * lig);
+                        if (r[u] >= 0) e[u] = LD_ROW((row_src<kSharded, D>(p, r[u]) + 4 * lig));
                 }
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
                     if (r[u] >= 0) {
                         if (has_fm) gr[u] = f4_fma(f4_sub(S, e[u]), dfm, gr[u]);
-                        RED_ROW(p.g_table + (size_t)r[u] * D + 4 * lig, gr[u]);
+                        RED_GRAD((grad_dst<kSharded, D>(p, r[u]) + 4 * lig), gr[u]);
                     }
                 }
             }
@@ -629,19 +672,26 @@ int set_smem_limit(K kernel, size_t smem) {
 }
 
 template <int LPR, int U>
-void launch_fwd(FwdParams& p, bool staged, cudaStream_t st) {
+int launch_fwd(FwdParams& p, bool staged, bool sharded, cudaStream_t st) {
     constexpr int SPW = 32 / LPR;
     const int64_t groups = (p.B + SPW - 1) / SPW;
+    const size_t smem = staged_smem(SPW, p.F, p.Fn);
+    if (sharded) {   // the peer-memory variant exists in its staged form only
+        if (!staged || smem > 200 * 1024 || set_smem_limit(k_embed_fm_fwd<LPR, U, true, true>, smem) != 0) return -1;
+        const int grid = grid_for((const void*)k_embed_fm_fwd<LPR, U, true, true>, smem, groups);
+        k_embed_fm_fwd<LPR, U, true, true><<<grid, kThreads, smem, st>>>(p);
+        return 0;
+    }
     if (staged) {
-        const size_t smem = staged_smem(SPW, p.F, p.Fn);
-        if (smem <= 200 * 1024 && set_smem_limit(k_embed_fm_fwd<LPR, U, true>, smem) == 0) {
-            const int grid = grid_for((const void*)k_embed_fm_fwd<LPR, U, true>, smem, groups);
-            k_embed_fm_fwd<LPR, U, true><<<grid, kThreads, smem, st>>>(p);
-            return;
+        if (smem <= 200 * 1024 && set_smem_limit(k_embed_fm_fwd<LPR, U, true, false>, smem) == 0) {
+            const int grid = grid_for((const void*)k_embed_fm_fwd<LPR, U, true, false>, smem, groups);
+            k_embed_fm_fwd<LPR, U, true, false><<<grid, kThreads, smem, st>>>(p);
+            return 0;
         }
     }
-    const int grid = grid_for((const void*)k_embed_fm_fwd<LPR, U, false>, 0, groups);
-    k_embed_fm_fwd<LPR, U, false><<<grid, kThreads, 0, st>>>(p);
+    const int grid = grid_for((const void*)k_embed_fm_fwd<LPR, U, false, false>, 0, groups);
+    k_embed_fm_fwd<LPR, U, false, false><<<grid, kThreads, 0, st>>>(p);
+    return 0;
 }
 
 template <int KD>
@@ -651,32 +701,55 @@ void launch_fwd_scalar(const FwdParams& p, cudaStream_t st) {
 }
 
 template <int LPR, int U>
-void launch_bwd(BwdParams& p, bool staged, cudaStream_t st) {
+int launch_bwd(BwdParams& p, bool staged, bool sharded, cudaStream_t st) {
     constexpr int SPW = 32 / LPR;
     const int64_t groups = (p.B + SPW - 1) / SPW;
+    const size_t smem = staged_smem(SPW, p.F, 0);
+    if (sharded) {
+        if (!staged || smem > 200 * 1024 || set_smem_limit(k_embed_fm_bwd<LPR, U, true, true>, smem) != 0) return -1;
+        const int grid = grid_for((const void*)k_embed_fm_bwd<LPR, U, true, true>, smem, groups);
+        k_embed_fm_bwd<LPR, U, true, true><<<grid, kThreads, smem, st>>>(p);
+        return 0;
+    }
     if (staged) {
-        const size_t smem = staged_smem(SPW, p.F, 0);
-        if (smem <= 200 * 1024 && set_smem_limit(k_embed_fm_bwd<LPR, U, true>, smem) == 0) {
-            const int grid = grid_for((const void*)k_embed_fm_bwd<LPR, U, true>, smem, groups);
-            k_embed_fm_bwd<LPR, U, true><<<grid, kThreads, smem, st>>>(p);
-            return;
+        if (smem <= 200 * 1024 && set_smem_limit(k_embed_fm_bwd<LPR, U, true, false>, smem) == 0) {
+            const int grid = grid_for((const void*)k_embed_fm_bwd<LPR, U, true, false>, smem, groups);
+            k_embed_fm_bwd<LPR, U, true, false><<<grid, kThreads, smem, st>>>(p);
+            return 0;
         }
     }
-    const int grid = grid_for((const void*)k_embed_fm_bwd<LPR, U, false>, 0, groups);
-    k_embed_fm_bwd<LPR, U, false><<<grid, kThreads, 0, st>>>(p);
+    const int grid = grid_for((const void*)k_embed_fm_bwd<LPR, U, false, false>, 0, groups);
+    k_embed_fm_bwd<LPR, U, false, false><<<grid, kThreads, 0, st>>>(p);
+    return 0;
 }
 
 inline bool al16(const void* p) { return (uintptr_t)p % 16 == 0; }
 
-}  // namespace
+// ---------------------------------------------------------------------------------------------
+// shared bodies of the plain and the sharded entry points
+// ---------------------------------------------------------------------------------------------
+struct ShardArgs {                    // world == 0: single local table
+    int world = 0;
+    const float* const* tables = nullptr;
+    const float* const* tables_lr = nullptr;
+    float* const* g_tables = nullptr;
+    float* const* g_tables_lr = nullptr;
+};
 
-extern "C" {
+int shard_log2(int world, const char* who) {
+    int l = 0;
+    while ((1 << l) < world) ++l;
+    if (world < 1 || world > RBX_MAX_WORLD || (1 << l) != world)
+        return rbx_fail(RBX_ERR_UNSUPPORTED, "%s: world=%d must be a power of two <= %d", who, world, RBX_MAX_WORLD);
+    return l;
+}
 
-int rbx_embed_fm_fwd(const float* table, const float* table_lr, const int32_t* rows, const int32_t* cat_pos,
-                     const int32_t* lr_delta, const float* dense_x, const float* dense_w, const float* dense_w_lr,
-                     const int32_t* num_pos, const int32_t* num_widx, const float* lr_bias, float* E, float* S,
-                     float* fm_out, float* lr_out, int64_t B, int64_t R, int F, int Fn, int D, int n_slots, rbx_stream_t stream) {
-    const char* who = "rbx_embed_fm_fwd";
+int embed_fm_fwd_impl(const char* who, const float* table, const float* table_lr, const ShardArgs& sh, const int32_t* rows,
+                      const int32_t* cat_pos, const int32_t* lr_delta, const float* dense_x, const float* dense_w,
+                      const float* dense_w_lr, const int32_t* num_pos, const int32_t* num_widx, const float* lr_bias,
+                      float* E, float* S, float* fm_out, float* lr_out, int64_t B, int64_t R, int F, int Fn, int D,
+                      int n_slots, rbx_stream_t stream) {
+    const bool sharded = sh.world > 0;
     RBX_REQUIRE(B >= 0 && F >= 0 && Fn >= 0 && D >= 1, "%s: negative size", who);
     RBX_REQUIRE(F <= RBX_MAX_SLOTS && Fn <= RBX_MAX_SLOTS, "%s: more than %d slots", who, RBX_MAX_SLOTS);
     RBX_REQUIRE(D <= RBX_MAX_DIM, "%s: D=%d > %d", who, D, RBX_MAX_DIM);
@@ -685,28 +758,47 @@ int rbx_embed_fm_fwd(const float* table, const float* table_lr, const int32_t* r
     if (n_slots <= 0) n_slots = F + Fn;
     RBX_REQUIRE(n_slots >= F + Fn, "%s: n_slots=%d < F + Fn", who, n_slots);
     const bool lr_only = !E && !S && !fm_out;   // LogisticRegression alone: no D-dim tables needed
-    RBX_REQUIRE(F == 0 || (rows && cat_pos && (table || lr_only)), "%s: table/rows/cat_pos required when F > 0", who);
+    RBX_REQUIRE(F == 0 || (rows && cat_pos && (table || sharded || lr_only)), "%s: table/rows/cat_pos required when F > 0", who);
     RBX_REQUIRE(Fn == 0 || (dense_x && num_pos && (dense_w || lr_only)), "%s: dense_x/dense_w/num_pos required when Fn > 0", who);
-    RBX_REQUIRE(!lr_out || ((F == 0 || table_lr) && (Fn == 0 || dense_w_lr)), "%s: lr_out needs table_lr / dense_w_lr", who);
-    if (lr_only) { table = nullptr; dense_w = nullptr; D = 16; }
+    RBX_REQUIRE(!lr_out || ((F == 0 || table_lr || (sharded && sh.tables_lr)) && (Fn == 0 || dense_w_lr)),
+                "%s: lr_out needs table_lr / dense_w_lr", who);
+    if (lr_only && !sharded) { table = nullptr; dense_w = nullptr; D = 16; }
     FwdParams p;
     p.table = table; p.table_lr = table_lr; p.rows = rows; p.dense_x = dense_x; p.dense_w = dense_w;
     p.dense_w_lr = dense_w_lr; p.lr_bias = lr_bias; p.E = E; p.S = S; p.fm_out = fm_out; p.lr_out = lr_out;
-    p.B = B; p.R = R; p.F = F; p.Fn = Fn; p.D = D; p.Ft = n_slots;
+    p.B = B; p.R = R; p.F = F; p.Fn = Fn; p.D = D; p.Ft = n_slots; p.wlog2 = 0;
+    bool shard_aligned = true;
+    if (sharded) {
+        const int l = shard_log2(sh.world, who);
+        if (l < 0) return l;
+        p.wlog2 = l;
+        for (int w = 0; w < sh.world; ++w) {
+            RBX_REQUIRE(sh.tables && sh.tables[w], "%s: shard table %d is null", who, w);
+            p.shard[w] = sh.tables[w];
+            p.shard_lr[w] = sh.tables_lr ? sh.tables_lr[w] : nullptr;
+            RBX_REQUIRE(!lr_out || F == 0 || p.shard_lr[w], "%s: shard lr table %d is null", who, w);
+            shard_aligned = shard_aligned && (uintptr_t)p.shard[w] % 16 == 0;
+        }
+        RBX_REQUIRE(!lr_delta, "%s: sharded tables share one row numbering (lr_delta must be NULL)", who);
+    }
     if (int rc = fill_meta(p.meta, cat_pos, F, num_pos, Fn, n_slots, num_widx, lr_delta, who)) return rc;
     cudaStream_t st = rbx_cast_stream(stream);
-    const bool aligned = al16(table) && al16(dense_w) && al16(E) && al16(S);
+    const bool aligned = al16(table) && al16(dense_w) && al16(E) && al16(S) && shard_aligned;
     if (D % 4 == 0 && D <= 128 && (D & (D - 1)) == 0 && aligned) {
         const bool staged = al16(rows) && al16(dense_x);
+        int rc = 0;
         switch (D / 4) {
-            case 1: launch_fwd<1, RBX_FWD_U>(p, staged, st); break;
-            case 2: launch_fwd<2, RBX_FWD_U>(p, staged, st); break;
-            case 4: launch_fwd<4, RBX_FWD_U>(p, staged, st); break;
-            case 8: launch_fwd<8, RBX_FWD_U>(p, staged, st); break;
-            case 16: launch_fwd<16, RBX_FWD_U>(p, staged, st); break;
-            default: launch_fwd<32, RBX_FWD_U>(p, staged, st); break;
+            case 1: rc = launch_fwd<1, RBX_FWD_U>(p, staged, sharded, st); break;
+            case 2: rc = launch_fwd<2, RBX_FWD_U>(p, staged, sharded, st); break;
+            case 4: rc = launch_fwd<4, RBX_FWD_U>(p, staged, sharded, st); break;
+            case 8: rc = launch_fwd<8, RBX_FWD_U>(p, staged, sharded, st); break;
+            case 16: rc = launch_fwd<16, RBX_FWD_U>(p, staged, sharded, st); break;
+            default: rc = launch_fwd<32, RBX_FWD_U>(p, staged, sharded, st); break;
         }
+        if (rc) return rbx_fail(RBX_ERR_UNSUPPORTED, "%s: sharded path needs 16-byte aligned rows / dense_x", who);
     } else {
+        if (sharded)
+            return rbx_fail(RBX_ERR_UNSUPPORTED, "%s: sharded path covers D in {4,8,16,32,64,128} with 16-byte aligned buffers (D=%d)", who, D);
         const int kd = (D + 31) / 32;
         if (kd <= 1) launch_fwd_scalar<1>(p, st);
         else if (kd <= 2) launch_fwd_scalar<2>(p, st);
@@ -718,12 +810,13 @@ int rbx_embed_fm_fwd(const float* table, const float* table_lr, const int32_t* r
     return RBX_OK;
 }
 
-int rbx_embed_fm_bwd(const float* table, const int32_t* rows, const int32_t* cat_pos, const int32_t* pad_row,
-                     const int32_t* lr_delta, const float* dense_x, const float* dense_w, const int32_t* num_pos,
-                     const int32_t* num_widx, const float* E, const float* S, const float* dE, const float* d_fm,
-                     const float* d_lr, float* g_table, float* g_table_lr, float* g_dense_w, float* g_dense_w_lr,
-                     float* g_lr_bias, int64_t B, int64_t R, int F, int Fn, int D, int n_slots, rbx_stream_t stream) {
-    const char* who = "rbx_embed_fm_bwd";
+int embed_fm_bwd_impl(const char* who, const float* table, const ShardArgs& sh, const int32_t* rows, const int32_t* cat_pos,
+                      const int32_t* pad_row, const int32_t* lr_delta, const float* dense_x, const float* dense_w,
+                      const int32_t* num_pos, const int32_t* num_widx, const float* E, const float* S, const float* dE,
+                      const float* d_fm, const float* d_lr, float* g_table, float* g_table_lr, float* g_dense_w,
+                      float* g_dense_w_lr, float* g_lr_bias, int64_t B, int64_t R, int F, int Fn, int D, int n_slots,
+                      rbx_stream_t stream) {
+    const bool sharded = sh.world > 0;
     RBX_REQUIRE(B >= 0 && F >= 0 && Fn >= 0 && D >= 1, "%s: negative size", who);
     RBX_REQUIRE(F <= RBX_MAX_SLOTS && Fn <= RBX_MAX_SLOTS, "%s: more than %d slots", who, RBX_MAX_SLOTS);
     RBX_REQUIRE(D <= RBX_MAX_DIM, "%s: D=%d > %d", who, D, RBX_MAX_DIM);
@@ -735,29 +828,52 @@ int rbx_embed_fm_bwd(const float* table, const int32_t* rows, const int32_t* cat
     const bool lr_only = !dE && !d_fm;
     RBX_REQUIRE(Fn == 0 || (dense_x && num_pos && (dense_w || lr_only)), "%s: dense_x/dense_w/num_pos required when Fn > 0", who);
     RBX_REQUIRE(!d_fm || S, "%s: S (saved by the forward) required with d_fm", who);
-    if (lr_only) { g_table = nullptr; g_dense_w = nullptr; if (!table && !E) D = 16; }
-    RBX_REQUIRE(!d_fm || E || table || F == 0, "%s: E or table required with d_fm", who);
+    if (lr_only && !sharded) { g_table = nullptr; g_dense_w = nullptr; if (!table && !E) D = 16; }
+    RBX_REQUIRE(!d_fm || E || table || sharded || F == 0, "%s: E or table required with d_fm", who);
     BwdParams p;
     p.table = table; p.rows = rows; p.dense_x = dense_x; p.dense_w = dense_w; p.E = E; p.S = S; p.dE = dE;
     p.d_fm = d_fm; p.d_lr = d_lr; p.g_table = g_table; p.g_table_lr = g_table_lr; p.g_dense_w = g_dense_w;
     p.g_dense_w_lr = g_dense_w_lr; p.g_lr_bias = g_lr_bias; p.B = B; p.R = R; p.F = F; p.Fn = Fn; p.D = D; p.Ft = n_slots;
+    p.wlog2 = 0;
+    bool shard_aligned = true, any_g = g_table != nullptr, any_g_lr = g_table_lr != nullptr;
+    if (sharded) {
+        const int l = shard_log2(sh.world, who);
+        if (l < 0) return l;
+        p.wlog2 = l;
+        any_g = sh.g_tables && sh.g_tables[0] && !lr_only;
+        any_g_lr = sh.g_tables_lr && sh.g_tables_lr[0];
+        for (int w = 0; w < sh.world; ++w) {
+            p.shard[w] = sh.tables ? sh.tables[w] : nullptr;
+            p.g_shard[w] = any_g ? sh.g_tables[w] : nullptr;
+            p.g_shard_lr[w] = any_g_lr ? sh.g_tables_lr[w] : nullptr;
+            RBX_REQUIRE(!any_g || p.g_shard[w], "%s: shard grad table %d is null", who, w);
+            RBX_REQUIRE(!any_g_lr || p.g_shard_lr[w], "%s: shard lr grad table %d is null", who, w);
+            RBX_REQUIRE(!(d_fm && !E) || p.shard[w], "%s: shard table %d needed to re-gather e", who, w);
+            shard_aligned = shard_aligned && (uintptr_t)p.shard[w] % 16 == 0 && (uintptr_t)p.g_shard[w] % 16 == 0;
+        }
+        RBX_REQUIRE(!lr_delta, "%s: sharded tables share one row numbering (lr_delta must be NULL)", who);
+    }
     if (int rc = fill_meta(p.meta, cat_pos, F, num_pos, Fn, n_slots, num_widx, lr_delta, who)) return rc;
     for (int f = 0; f < F; ++f) p.pad_row[f] = pad_row ? pad_row[f] : -1;
     cudaStream_t st = rbx_cast_stream(stream);
 
-    if (F > 0 && (g_table || (g_table_lr && d_lr)) && (dE || d_fm || d_lr)) {
-        const bool aligned = al16(table) && al16(E) && al16(S) && al16(dE) && al16(g_table);
+    if (F > 0 && (any_g || (any_g_lr && d_lr)) && (dE || d_fm || d_lr)) {
+        const bool aligned = al16(table) && al16(E) && al16(S) && al16(dE) && al16(g_table) && shard_aligned;
         if (D % 4 == 0 && D <= 128 && (D & (D - 1)) == 0 && aligned) {
             const bool staged = al16(rows);
+            int rc = 0;
             switch (D / 4) {
-                case 1: launch_bwd<1, RBX_BWD_U>(p, staged, st); break;
-                case 2: launch_bwd<2, RBX_BWD_U>(p, staged, st); break;
-                case 4: launch_bwd<4, RBX_BWD_U>(p, staged, st); break;
-                case 8: launch_bwd<8, RBX_BWD_U>(p, staged, st); break;
-                case 16: launch_bwd<16, RBX_BWD_U>(p, staged, st); break;
-                default: launch_bwd<32, RBX_BWD_U>(p, staged, st); break;
+                case 1: rc = launch_bwd<1, RBX_BWD_U>(p, staged, sharded, st); break;
+                case 2: rc = launch_bwd<2, RBX_BWD_U>(p, staged, sharded, st); break;
+                case 4: rc = launch_bwd<4, RBX_BWD_U>(p, staged, sharded, st); break;
+                case 8: rc = launch_bwd<8, RBX_BWD_U>(p, staged, sharded, st); break;
+                case 16: rc = launch_bwd<16, RBX_BWD_U>(p, staged, sharded, st); break;
+                default: rc = launch_bwd<32, RBX_BWD_U>(p, staged, sharded, st); break;
             }
+            if (rc) return rbx_fail(RBX_ERR_UNSUPPORTED, "%s: sharded path needs 16-byte aligned rows", who);
         } else {
+            if (sharded)
+                return rbx_fail(RBX_ERR_UNSUPPORTED, "%s: sharded path covers D in {4,8,16,32,64,128} with 16-byte aligned buffers (D=%d)", who, D);
             const int grid = grid_for((const void*)k_embed_fm_bwd_scalar, 0, B);
             k_embed_fm_bwd_scalar<<<grid, kThreads, 0, st>>>(p);
         }
@@ -791,6 +907,57 @@ int rbx_embed_fm_bwd(const float* table, const int32_t* rows, const int32_t* cat
         }
     }
     return RBX_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int rbx_embed_fm_fwd(const float* table, const float* table_lr, const int32_t* rows, const int32_t* cat_pos,
+                     const int32_t* lr_delta, const float* dense_x, const float* dense_w, const float* dense_w_lr,
+                     const int32_t* num_pos, const int32_t* num_widx, const float* lr_bias, float* E, float* S,
+                     float* fm_out, float* lr_out, int64_t B, int64_t R, int F, int Fn, int D, int n_slots,
+                     rbx_stream_t stream) {
+    return embed_fm_fwd_impl("rbx_embed_fm_fwd", table, table_lr, ShardArgs(), rows, cat_pos, lr_delta, dense_x, dense_w,
+                             dense_w_lr, num_pos, num_widx, lr_bias, E, S, fm_out, lr_out, B, R, F, Fn, D, n_slots, stream);
+}
+
+int rbx_embed_fm_bwd(const float* table, const int32_t* rows, const int32_t* cat_pos, const int32_t* pad_row,
+                     const int32_t* lr_delta, const float* dense_x, const float* dense_w, const int32_t* num_pos,
+                     const int32_t* num_widx, const float* E, const float* S, const float* dE, const float* d_fm,
+                     const float* d_lr, float* g_table, float* g_table_lr, float* g_dense_w, float* g_dense_w_lr,
+                     float* g_lr_bias, int64_t B, int64_t R, int F, int Fn, int D, int n_slots, rbx_stream_t stream) {
+    return embed_fm_bwd_impl("rbx_embed_fm_bwd", table, ShardArgs(), rows, cat_pos, pad_row, lr_delta, dense_x, dense_w,
+                             num_pos, num_widx, E, S, dE, d_fm, d_lr, g_table, g_table_lr, g_dense_w, g_dense_w_lr,
+                             g_lr_bias, B, R, F, Fn, D, n_slots, stream);
+}
+
+int rbx_embed_fm_fwd_sharded(const float* const* shard_tables, const float* const* shard_tables_lr, int world,
+                             const int32_t* rows, const int32_t* cat_pos, const float* dense_x, const float* dense_w,
+                             const float* dense_w_lr, const int32_t* num_pos, const int32_t* num_widx,
+                             const float* lr_bias, float* E, float* S, float* fm_out, float* lr_out, int64_t B, int64_t R,
+                             int F, int Fn, int D, int n_slots, rbx_stream_t stream) {
+    const char* who = "rbx_embed_fm_fwd_sharded";
+    RBX_REQUIRE(world >= 1 && shard_tables, "%s: shard tables required", who);
+    ShardArgs sh;
+    sh.world = world; sh.tables = shard_tables; sh.tables_lr = shard_tables_lr;
+    return embed_fm_fwd_impl(who, nullptr, nullptr, sh, rows, cat_pos, nullptr, dense_x, dense_w, dense_w_lr, num_pos,
+                             num_widx, lr_bias, E, S, fm_out, lr_out, B, R, F, Fn, D, n_slots, stream);
+}
+
+int rbx_embed_fm_bwd_sharded(const float* const* shard_tables, float* const* shard_g_tables,
+                             float* const* shard_g_tables_lr, int world, const int32_t* rows, const int32_t* cat_pos,
+                             const int32_t* pad_row, const float* dense_x, const float* dense_w, const int32_t* num_pos,
+                             const int32_t* num_widx, const float* E, const float* S, const float* dE, const float* d_fm,
+                             const float* d_lr, float* g_dense_w, float* g_dense_w_lr, float* g_lr_bias, int64_t B,
+                             int64_t R, int F, int Fn, int D, int n_slots, rbx_stream_t stream) {
+    const char* who = "rbx_embed_fm_bwd_sharded";
+    RBX_REQUIRE(world >= 1, "%s: world", who);
+    ShardArgs sh;
+    sh.world = world; sh.tables = shard_tables; sh.g_tables = shard_g_tables; sh.g_tables_lr = shard_g_tables_lr;
+    return embed_fm_bwd_impl(who, nullptr, sh, rows, cat_pos, pad_row, nullptr, dense_x, dense_w, num_pos, num_widx, E, S,
+                             dE, d_fm, d_lr, nullptr, nullptr, g_dense_w, g_dense_w_lr, g_lr_bias, B, R, F, Fn, D, n_slots,
+                             stream);
 }
 
 }  // extern "C"

@@ -1,0 +1,307 @@
+"""Row-sharded embedding table across the GPUs of one box (BASELINE configs[3]).
+
+The reference has no sharded embedding (its only multi-device modes are nn.DataParallel / DDP
+replicas), so this module has no reference counterpart; its contract is: the sharded forward /
+backward produce exactly what the single-table fused kernels (ops.embed_fm_fwd / embed_fm_bwd, the
+reference-parity path) produce on the concatenated table.
+
+Partition: global row r (= id + field offset in the fused table) lives on rank r % world at local
+row r // world.  One process per GPU, torch.distributed for the plumbing.  Two data paths:
+
+  mode="peer"  (product path)  every rank maps every other rank's table / gradient shard through
+               CUDA IPC (rbx_peer_*), and ONE fused kernel per direction does compute + exchange:
+               the forward gathers remote rows with plain loads over NVLink / NVSwitch, the backward
+               reduces (red.global.add) straight into the owner's gradient shard.  No routing, no
+               staging buffers, no collective on the data path; a barrier separates steps.
+  mode="a2a"   (the NCCL baseline the north star names) bucket ids by owner (rbx_shard_route),
+               all_to_all_single ids -> owners gather (rbx_gather_rows) -> all_to_all_single rows
+               back; the un-permute is folded into the fused FM kernel by handing it the received
+               buffer as its "table" and the send positions as its "rows".  Backward mirrors it.
+
+`kern` is the kernel provider (recbox_b200.ops by default).  Host-side orchestration (split sizes,
+buffer bookkeeping, pad rows) is independent of it, which is what the world_size-2 gloo tests on
+CPU exercise with a stand-in provider.
+"""
+import ctypes
+
+import torch
+import torch.distributed as dist
+
+from . import _lib
+from ._lib import RbxError
+
+F32, I32 = torch.float32, torch.int32
+
+
+# -------------------------------------------------------------------------------------------------
+# peer-visible device memory
+# -------------------------------------------------------------------------------------------------
+class _RawCuda(object):
+    """Minimal __cuda_array_interface__ carrier so torch can view memory this library allocated."""
+
+    def __init__(self, ptr, numel, owner):
+        self.owner = owner
+        self.__cuda_array_interface__ = {"shape": (numel,), "typestr": "<f4", "data": (ptr, False), "version": 3,
+                                         "strides": None}
+
+
+class PeerBlock(object):
+    """One cudaMalloc'd fp32 block (IPC-exportable), viewed as a torch tensor."""
+
+    def __init__(self, numel, device):
+        self.lib = _lib.load()
+        self.device = torch.device(device)
+        self.numel = int(numel)
+        out = ctypes.c_void_p()
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.rbx_peer_alloc(ctypes.c_size_t(max(self.numel, 4) * 4), ctypes.byref(out)), self.lib)
+        self.ptr = out.value
+        self.tensor = torch.as_tensor(_RawCuda(self.ptr, max(self.numel, 4), self), device=self.device)[:self.numel]
+        self.tensor.zero_()
+
+    def handle(self):
+        buf = (ctypes.c_ubyte * 64)()
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.rbx_peer_export(ctypes.c_void_p(self.ptr), buf), self.lib)
+        return bytes(buf)
+
+    def free(self):
+        if self.ptr:
+            self.tensor = None
+            with torch.cuda.device(self.device):
+                self.lib.rbx_peer_free(ctypes.c_void_p(self.ptr))
+            self.ptr = None
+
+
+def open_peer(handle, device):
+    lib = _lib.load()
+    out = ctypes.c_void_p()
+    buf = (ctypes.c_ubyte * 64)(*handle)
+    with torch.cuda.device(device):
+        _lib.check(lib.rbx_peer_open(buf, ctypes.byref(out)), lib)
+    return out.value
+
+
+def close_peer(ptr, device):
+    lib = _lib.load()
+    with torch.cuda.device(device):
+        lib.rbx_peer_close(ctypes.c_void_p(ptr))
+
+
+# -------------------------------------------------------------------------------------------------
+# host-side bookkeeping shared by both modes (pure Python / integer arithmetic)
+# -------------------------------------------------------------------------------------------------
+def local_rows(R, world, rank):
+    """Number of global rows r in [0, R) with r % world == rank."""
+    return (R - rank + world - 1) // world if R > rank else 0
+
+
+def shard_capacity(R, world):
+    return (R + world - 1) // world
+
+
+def owned_pad_rows(pad_rows, world, rank):
+    """Local row numbers of the padding rows this rank owns (their gradient is defined as zero)."""
+    return [p // world for p in pad_rows if p is not None and p >= 0 and p % world == rank]
+
+
+class ShardedEmbeddingFM(object):
+    """Fused multi-slot gather + FM + LR over a row-sharded table.
+
+    R: rows of the global fused table, D: embedding dim.  `table`, `table_lr`, `g_table`,
+    `g_table_lr` are this rank's shards ([cap, D] / [cap], cap = ceil(R / world))."""
+
+    def __init__(self, R, D, mode="peer", group=None, device=None, with_lr=True, kern=None):
+        if mode not in ("peer", "a2a"):
+            raise RbxError("ShardedEmbeddingFM: mode must be 'peer' or 'a2a'")
+        self.R, self.D, self.mode, self.group, self.with_lr = int(R), int(D), mode, group, with_lr
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        if kern is None:
+            from . import ops as kern
+        self.kern = kern
+        self.cap = shard_capacity(self.R, self.world)
+        self.n_local = local_rows(self.R, self.world, self.rank)
+        self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+        n_t, n_l = self.cap * self.D, self.cap
+        n_l4 = (n_l + 3) // 4 * 4
+        self._block = None
+        self._peers = []
+        if mode == "peer":
+            if self.world & (self.world - 1) or self.world > 8:
+                raise RbxError("peer mode needs a power-of-two world <= 8 (got %d)" % self.world)
+            # one block: table | table_lr | g_table | g_table_lr   (offsets in floats, 16-byte aligned)
+            self._offs = (0, n_t, n_t + n_l4, 2 * n_t + n_l4)
+            self._block = PeerBlock(2 * n_t + 2 * n_l4, self.device)
+            flat = self._block.tensor
+        else:
+            self._offs = (0, n_t, n_t + n_l4, 2 * n_t + n_l4)
+            flat = torch.zeros(2 * n_t + 2 * n_l4, dtype=F32, device=self.device)
+        o = self._offs
+        self.table = flat[o[0]:o[0] + n_t].view(self.cap, self.D)
+        self.table_lr = flat[o[1]:o[1] + n_l]
+        self.g_table = flat[o[2]:o[2] + n_t].view(self.cap, self.D)
+        self.g_table_lr = flat[o[3]:o[3] + n_l]
+        self._gflat = flat[o[2]:o[3] + n_l]
+        self._flat = flat
+        self._ptr_arrays = None
+        if mode == "peer":
+            self._map_peers()
+        self._saved = None
+
+    # -- peer mapping ------------------------------------------------------------------------------
+    def _map_peers(self):
+        base = [None] * self.world
+        base[self.rank] = self._block.ptr
+        if self.world > 1:
+            handles = [None] * self.world
+            dist.all_gather_object(handles, self._block.handle(), group=self.group)
+            for w, h in enumerate(handles):
+                if w != self.rank:
+                    base[w] = open_peer(h, self.device)
+                    self._peers.append(base[w])
+        o = self._offs
+        mk = lambda off: (ctypes.c_void_p * self.world)(*[b + off * 4 for b in base])
+        self._ptr_arrays = {"table": mk(o[0]), "table_lr": mk(o[1]), "g_table": mk(o[2]), "g_table_lr": mk(o[3])}
+
+    def close(self):
+        for p in self._peers:
+            close_peer(p, self.device)
+        self._peers = []
+        if self._block is not None:
+            self.barrier()
+            self.table = self.table_lr = self.g_table = self.g_table_lr = self._gflat = self._flat = None
+            self._block.free()
+            self._block = None
+
+    # -- parameter plumbing -------------------------------------------------------------------------
+    def load_global(self, table, table_lr=None):
+        """Fill this rank's shard from a full [R, D] (and [R]) table (tests / checkpoints)."""
+        mine = table[self.rank::self.world].to(self.device, F32)
+        self.table[:mine.shape[0]].copy_(mine)
+        if table_lr is not None:
+            m1 = table_lr.reshape(-1)[self.rank::self.world].to(self.device, F32)
+            self.table_lr[:m1.shape[0]].copy_(m1)
+        self.barrier()
+
+    def gather_global(self, which="g_table"):
+        """All ranks' shards of `which` re-interleaved to the global row order (tests / checkpoints)."""
+        local = getattr(self, which)
+        parts = [torch.empty_like(local) for _ in range(self.world)]
+        if self.world > 1:
+            dist.all_gather(parts, local.contiguous(), group=self.group)
+        else:
+            parts = [local]
+        out = torch.empty((self.cap * self.world,) + tuple(local.shape[1:]), dtype=F32, device=local.device)
+        for w, p in enumerate(parts):
+            out[w::self.world] = p
+        return out[:self.R]
+
+    def zero_grad(self):
+        self._gflat.zero_()
+
+    def barrier(self):
+        if self.world > 1:
+            if self._flat is not None and self._flat.is_cuda:
+                torch.cuda.current_stream(self.device).synchronize()
+            dist.barrier(group=self.group)
+
+    # -- forward / backward ---------------------------------------------------------------------------
+    def forward(self, rows, cat_pos, dense_x=None, dense_w=None, dense_w_lr=None, num_pos=(), lr_bias=None,
+                want_E=True, n_slots=None):
+        """rows: int32 [B, F] GLOBAL row ids of this rank's batch shard.  Returns (E, S, fm, lr)."""
+        if self.mode == "peer":
+            out = self._fwd_peer(rows, cat_pos, dense_x, dense_w, dense_w_lr, list(num_pos), lr_bias, want_E, n_slots)
+        else:
+            out = self._fwd_a2a(rows, cat_pos, dense_x, dense_w, dense_w_lr, list(num_pos), lr_bias, want_E, n_slots)
+        return out
+
+    def backward(self, rows, cat_pos, pad_rows, dense_x, dense_w, num_pos, E, S, dE, d_fm, d_lr,
+                 g_dense_w=None, g_dense_w_lr=None, g_lr_bias=None, n_slots=None):
+        """Accumulates into this rank's AND (peer mode) the owners' gradient shards; the dense
+        (replicated) gradients g_dense_* are local partial sums the caller all-reduces."""
+        if self.mode == "peer":
+            self._bwd_peer(rows, cat_pos, pad_rows, dense_x, dense_w, list(num_pos), E, S, dE, d_fm, d_lr,
+                           g_dense_w, g_dense_w_lr, g_lr_bias, n_slots)
+        else:
+            self._bwd_a2a(rows, cat_pos, pad_rows, dense_x, dense_w, list(num_pos), E, S, dE, d_fm, d_lr,
+                          g_dense_w, g_dense_w_lr, g_lr_bias, n_slots)
+
+    # ---- peer mode: one fused kernel per direction, exchange inside ----------------------------------
+    def _fwd_peer(self, rows, cat_pos, dense_x, dense_w, dense_w_lr, num_pos, lr_bias, want_E, n_slots):
+        return self.kern.embed_fm_fwd_sharded(self._ptr_arrays["table"], self._ptr_arrays["table_lr"] if self.with_lr else None,
+                                              self.world, rows, cat_pos, dense_x, dense_w, dense_w_lr, num_pos, lr_bias,
+                                              self.R, self.D, want_E=want_E, want_lr=self.with_lr, n_slots=n_slots)
+
+    def _bwd_peer(self, rows, cat_pos, pad_rows, dense_x, dense_w, num_pos, E, S, dE, d_fm, d_lr,
+                  g_dense_w, g_dense_w_lr, g_lr_bias, n_slots):
+        self.kern.embed_fm_bwd_sharded(self._ptr_arrays["table"], self._ptr_arrays["g_table"],
+                                       self._ptr_arrays["g_table_lr"] if self.with_lr else None, self.world, rows,
+                                       cat_pos, pad_rows, dense_x, dense_w, num_pos, E, S, dE, d_fm,
+                                       d_lr if self.with_lr else None, g_dense_w, g_dense_w_lr, g_lr_bias,
+                                       self.R, self.D, n_slots=n_slots)
+
+    # ---- a2a mode: route -> all_to_all ids -> gather -> all_to_all rows -> fused FM on the received buffer --
+    def _exchange_counts(self, counts):
+        """counts[w] = ids this rank sends to w  ->  (send_sizes, recv_sizes) as Python lists."""
+        recv = torch.empty_like(counts)
+        if self.world > 1:
+            dist.all_to_all_single(recv, counts, group=self.group)
+        else:
+            recv.copy_(counts)
+        both = torch.stack([counts, recv]).cpu().tolist()         # the one host sync of the step
+        return [int(x) for x in both[0]], [int(x) for x in both[1]]
+
+    def _a2a(self, out, inp, out_sizes, in_sizes):
+        if self.world > 1:
+            dist.all_to_all_single(out, inp, out_sizes, in_sizes, group=self.group)
+        else:
+            out.copy_(inp)
+        return out
+
+    def _fwd_a2a(self, rows, cat_pos, dense_x, dense_w, dense_w_lr, num_pos, lr_bias, want_E, n_slots):
+        k, D = self.kern, self.D
+        B, F = rows.shape
+        N = B * F
+        send, pos, counts = k.shard_route(rows.reshape(-1), self.world)
+        send_sizes, recv_sizes = self._exchange_counts(counts)
+        Nr = sum(recv_sizes)
+        ids_recv = self._a2a(torch.empty(Nr, dtype=I32, device=rows.device), send, recv_sizes, send_sizes)
+        rows_out = k.gather_rows(self.table, ids_recv)                                   # [Nr, D]
+        got = self._a2a(torch.empty((N, D), dtype=F32, device=rows.device), rows_out, send_sizes, recv_sizes)
+        got_lr = None
+        if self.with_lr:
+            lr_out = k.gather_rows(self.table_lr.view(-1, 1), ids_recv).view(-1)        # [Nr]
+            got_lr = self._a2a(torch.empty(N, dtype=F32, device=rows.device), lr_out, send_sizes, recv_sizes)
+        # un-permute folded into the fused kernel: its "table" is the received buffer, its "rows" the send positions
+        E, S, fm, lr = k.embed_fm_fwd(got, got_lr, pos.view(B, F), cat_pos, dense_x, dense_w, dense_w_lr, num_pos, lr_bias,
+                                      want_E=want_E, want_lr=self.with_lr, n_slots=n_slots)
+        self._saved = (pos, ids_recv, send_sizes, recv_sizes, got)
+        return E, S, fm, lr
+
+    def _bwd_a2a(self, rows, cat_pos, pad_rows, dense_x, dense_w, num_pos, E, S, dE, d_fm, d_lr,
+                 g_dense_w, g_dense_w_lr, g_lr_bias, n_slots):
+        if self._saved is None:
+            raise RbxError("ShardedEmbeddingFM.backward (a2a) needs the forward of the same batch first")
+        k, D = self.kern, self.D
+        pos, ids_recv, send_sizes, recv_sizes, got = self._saved
+        B, F = rows.shape
+        N, Nr = B * F, ids_recv.numel()
+        dev = rows.device
+        # gradients computed straight into send order (each position is written by exactly one (b, f))
+        gsend = torch.zeros((N, D), dtype=F32, device=dev)
+        gsend_lr = torch.zeros(N, dtype=F32, device=dev) if (self.with_lr and d_lr is not None) else None
+        k.embed_fm_bwd(got, pos.view(B, F), cat_pos, None, dense_x, dense_w, num_pos, E, S, dE, d_fm,
+                       d_lr if self.with_lr else None, gsend, gsend_lr, g_dense_w, g_dense_w_lr, g_lr_bias, D, N,
+                       n_slots=n_slots)
+        grecv = self._a2a(torch.empty((Nr, D), dtype=F32, device=dev), gsend, recv_sizes, send_sizes)
+        k.scatter_add_rows(grecv, ids_recv, None, self.g_table)
+        if gsend_lr is not None:
+            grecv_lr = self._a2a(torch.empty(Nr, dtype=F32, device=dev), gsend_lr, recv_sizes, send_sizes)
+            k.scatter_add_rows(grecv_lr.view(-1, 1), ids_recv, None, self.g_table_lr.view(-1, 1))
+        # padding rows: nn.Embedding(padding_idx) defines their gradient as zero; the owner clears them
+        mine = owned_pad_rows(pad_rows or [], self.world, self.rank)
+        if mine:
+            idx = torch.tensor(mine, dtype=torch.long, device=dev)
+            self.g_table.index_fill_(0, idx, 0.0)
+            self.g_table_lr.index_fill_(0, idx, 0.0)

@@ -127,3 +127,65 @@ def assert_close(a, b, rtol=1e-5, atol_scale=1e-5, what=""):
     bad = err > tol
     assert not bool(bad.any()), "%s: %d / %d outside tolerance, max err %.3e (max |ref| %.3e)" % (
         what, int(bad.sum()), b.numel(), float(err.max()), float(b.abs().max()))
+
+
+class CpuKern:
+    """Stand-in kernel provider for host-logic tests of recbox_b200.sharded on CPU (gloo): the same
+    call surface as recbox_b200.ops, implemented with the oracle / torch CPU ops.  TEST ONLY."""
+
+    @staticmethod
+    def shard_route(rows, world):
+        send, counts, pos = oracle.shard_route(rows.numpy(), world)
+        return (torch.from_numpy(send.astype(np.int32)), torch.from_numpy(pos.astype(np.int32)),
+                torch.from_numpy(counts.astype(np.int32)))
+
+    @staticmethod
+    def gather_rows(table, ids):
+        return torch.from_numpy(oracle.gather_rows_numpy(table.numpy(), ids.numpy()))
+
+    @staticmethod
+    def scatter_add_rows(g, ids, pad_row, g_table):
+        keep = torch.ones_like(ids, dtype=torch.bool) if pad_row is None else ids != pad_row
+        g_table.index_add_(0, ids[keep].long(), g[keep])
+
+    @staticmethod
+    def embed_fm_fwd(table, table_lr, rows, cat_pos, dense_x, dense_w, dense_w_lr, num_pos, lr_bias,
+                     want_E=True, want_lr=True, n_slots=None, **_):
+        B, F = rows.shape
+        Fn = len(num_pos)
+        D = table.shape[1]
+        E = torch.zeros(B, n_slots or (F + Fn), D)
+        E[:, list(cat_pos)] = table[rows.long()]
+        if Fn:
+            E[:, list(num_pos)] = dense_x[:, :, None] * dense_w[None]
+        S = E.sum(1)
+        fm = oracle.inner_product_interaction(E, "product_sum").reshape(-1)
+        lr = None
+        if want_lr:
+            lr = table_lr[rows.long()].sum(1)
+            if Fn:
+                lr = lr + (dense_x * dense_w_lr[None]).sum(1)
+            if lr_bias is not None:
+                lr = lr + lr_bias
+        return (E if want_E else None), S, fm, lr
+
+    @staticmethod
+    def embed_fm_bwd(table, rows, cat_pos, pad_row, dense_x, dense_w, num_pos, E, S, dE, d_fm, d_lr,
+                     g_table, g_table_lr, g_dense_w, g_dense_w_lr, g_lr_bias, D, R, n_slots=None, **_):
+        B, F = rows.shape
+        e_cat = table[rows.long()]                                          # [B,F,D]
+        g_e = dE[:, list(cat_pos)] + d_fm.view(-1, 1, 1) * (S[:, None, :] - e_cat)
+        keep = torch.ones(B, F, dtype=torch.bool)
+        if pad_row is not None:
+            keep = rows != torch.tensor(pad_row, dtype=rows.dtype)[None]
+        g_table.index_add_(0, rows[keep].long(), g_e[keep])
+        if g_table_lr is not None and d_lr is not None:
+            g_table_lr.index_add_(0, rows[keep].long(), d_lr.view(-1, 1).expand(B, F)[keep])
+        if len(num_pos) and g_dense_w is not None:
+            e_num = dense_x[:, :, None] * dense_w[None]
+            g_n = dE[:, list(num_pos)] + d_fm.view(-1, 1, 1) * (S[:, None, :] - e_num)
+            g_dense_w += (dense_x[:, :, None] * g_n).sum(0)
+            if g_dense_w_lr is not None and d_lr is not None:
+                g_dense_w_lr += (dense_x * d_lr.view(-1, 1)).sum(0)
+        if g_lr_bias is not None and d_lr is not None:
+            g_lr_bias += d_lr.sum()

@@ -1,0 +1,79 @@
+"""Host-side logic of the row-sharded path (recbox_b200.sharded, mode="a2a") with world_size 2 over
+gloo on CPU: split sizes, buffer bookkeeping, owner-side scatter and pad rows -- with the oracle
+standing in for the CUDA kernels (tests/helpers.CpuKern).  The sharded result must equal the
+single-table oracle result on the concatenated batch."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from helpers import CpuKern, Problem, assert_close
+
+from recbox_b200 import sharded
+
+
+def test_row_ownership_arithmetic():
+    for R in (0, 1, 7, 8, 9, 1000003):
+        for world in (1, 2, 3, 8):
+            ns = [sharded.local_rows(R, world, r) for r in range(world)]
+            assert sum(ns) == R and max(ns) <= sharded.shard_capacity(R, world)
+            assert ns == [len(range(r, R, world)) for r in range(world)]
+    assert sharded.owned_pad_rows([0, 11, 18, 31, -1], 2, 0) == [0, 9]
+    assert sharded.owned_pad_rows([0, 11, 18, 31, -1], 2, 1) == [5, 15]
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        B, D = 48, 8
+        pb = Problem(B * world, "nccncc", D, vocab=[11, 7, 13, 5], seed=3)
+        f = pb.fused("cpu")
+        g = torch.Generator().manual_seed(4)
+        dE = torch.randn(B * world, 6, D, generator=g)
+        d_fm = torch.randn(B * world, generator=g)
+        d_lr = torch.randn(B * world, generator=g)
+        sl = slice(rank * B, (rank + 1) * B)
+        sh = sharded.ShardedEmbeddingFM(pb.R, D, mode="a2a", device="cpu", kern=CpuKern)
+        assert sh.world == world and sh.rank == rank
+        sh.load_global(f["table"], f["table_lr"])
+        E, S, fm, lr = sh.forward(f["rows"][sl], pb.cat_pos, f["dense_x"][sl], f["dense_w"], f["dense_w_lr"], pb.num_pos,
+                                  f["bias"])
+        gw, gw1, gb = torch.zeros_like(f["dense_w"]), torch.zeros_like(f["dense_w_lr"]), torch.zeros(1)
+        sh.zero_grad()
+        sh.backward(f["rows"][sl], pb.cat_pos, pb.pad_row, f["dense_x"][sl], f["dense_w"], pb.num_pos, E, S, dE[sl],
+                    d_fm[sl], d_lr[sl], gw, gw1, gb)
+        for t in (gw, gw1, gb):
+            dist.all_reduce(t)
+        gt = sh.gather_global("g_table")
+        gt1 = sh.gather_global("g_table_lr")
+        # reference: the oracle on the whole batch / whole table
+        Er, fmr, lrr, *_ = pb.oracle_forward()
+        assert torch.equal(E, Er[sl])
+        assert_close(fm, fmr.reshape(-1)[sl], atol_scale=1e-4, what="fm")
+        assert_close(lr, lrr.reshape(-1)[sl], what="lr")
+        want = pb.oracle_grads(dE, d_fm, d_lr)
+        for got, ref, name in zip((gt, gt1, gw, gw1, gb), want, ("g_table", "g_table_lr", "g_dense_w", "g_dense_w_lr", "g_bias")):
+            assert_close(got, ref, atol_scale=2e-5, what=name)
+        open(os.path.join(out_dir, "ok%d" % rank), "w").write("ok")
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2])
+def test_a2a_orchestration_world2_gloo(world, tmp_path):
+    port = _free_port()
+    mp.spawn(_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    assert all(os.path.exists(os.path.join(str(tmp_path), "ok%d" % r)) for r in range(world))

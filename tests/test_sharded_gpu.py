@@ -1,0 +1,93 @@
+"""Row-sharded table on real GPUs (one process per GPU, NCCL): both data paths -- the NVLink
+peer-memory fused kernels ("peer") and the NCCL all-to-all baseline ("a2a") -- must reproduce the
+single-table fused path (which tests/test_kernels_gpu.py pins to the oracle) on the same inputs:
+E bit-exact, sums / gradients within 1e-5.  World = min(#GPUs, 8) rounded down to a power of two
+(1 on a single-GPU box: the sharded kernels still run, with one shard)."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from helpers import Problem, assert_close
+
+pytestmark = pytest.mark.gpu
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, mode, D, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    try:
+        from recbox_b200 import ops, sharded
+        B = 1000
+        pb = Problem(B * world, "nn" + "c" * 9 + "n", D, vocab=[101, 7, 13, 1000, 3, 50, 77, 256, 19], seed=11 + D, zipf=1.3)
+        f = pb.fused(dev)
+        g = torch.Generator().manual_seed(5)
+        Ft = pb.F + pb.Fn
+        dE = torch.randn(B * world, Ft, D, generator=g).to(dev)
+        d_fm = torch.randn(B * world, generator=g).to(dev)
+        d_lr = torch.randn(B * world, generator=g).to(dev)
+        sl = slice(rank * B, (rank + 1) * B)
+        rows, dx = f["rows"][sl].contiguous(), f["dense_x"][sl].contiguous()
+
+        sh = sharded.ShardedEmbeddingFM(pb.R, D, mode=mode, device=dev)
+        sh.load_global(f["table"], f["table_lr"])
+        E, S, fm, lr = sh.forward(rows, pb.cat_pos, dx, f["dense_w"], f["dense_w_lr"], pb.num_pos, f["bias"])
+        gw, gw1, gb = torch.zeros_like(f["dense_w"]), torch.zeros_like(f["dense_w_lr"]), torch.zeros(1, device=dev)
+        sh.zero_grad()
+        sh.barrier()
+        for use_E in (True, False):
+            sh.backward(rows, pb.cat_pos, pb.pad_row, dx, f["dense_w"], pb.num_pos, E if use_E else None, S,
+                        dE[sl].contiguous(), d_fm[sl].contiguous(), d_lr[sl].contiguous(), gw, gw1, gb)
+        sh.barrier()
+        for t in (gw, gw1, gb):
+            dist.all_reduce(t)
+        gt, gt1 = sh.gather_global("g_table"), sh.gather_global("g_table_lr")
+
+        # single-table fused path on the whole batch (every rank computes it locally)
+        Er, Sr, fmr, lrr = ops.embed_fm_fwd(f["table"], f["table_lr"], f["rows"], pb.cat_pos, f["dense_x"], f["dense_w"],
+                                            f["dense_w_lr"], pb.num_pos, f["bias"])
+        assert torch.equal(E, Er[sl]), "gathered rows must be bit-exact"
+        assert torch.equal(S, Sr[sl]) and torch.equal(fm, fmr[sl]) and torch.equal(lr, lrr[sl]), "same kernel, same order"
+        rt, rt1 = torch.zeros_like(f["table"]), torch.zeros_like(f["table_lr"])
+        rw, rw1, rb = torch.zeros_like(gw), torch.zeros_like(gw1), torch.zeros_like(gb)
+        for use_E in (True, False):
+            ops.embed_fm_bwd(f["table"], f["rows"], pb.cat_pos, pb.pad_row, f["dense_x"], f["dense_w"], pb.num_pos,
+                             Er if use_E else None, Sr, dE, d_fm, d_lr, rt, rt1, rw, rw1, rb, D, pb.R)
+        for got, ref, name in zip((gt, gt1, gw, gw1, gb), (rt, rt1, rw, rw1, rb),
+                                  ("g_table", "g_table_lr", "g_dense_w", "g_dense_w_lr", "g_bias")):
+            assert_close(got, ref, atol_scale=2e-5, what="%s[%s]" % (name, mode))
+        for p in pb.pad_row:
+            assert float(gt[p].abs().sum()) == 0.0 and float(gt1[p]) == 0.0, "padding rows keep a zero gradient"
+        sh.close()
+        open(os.path.join(out_dir, "ok%d" % rank), "w").write("ok")
+    finally:
+        dist.destroy_process_group()
+
+
+def _world():
+    n = torch.cuda.device_count()
+    w = 1
+    while w * 2 <= min(n, 8):
+        w *= 2
+    return w
+
+
+@pytest.mark.parametrize("D", [16, 64])
+@pytest.mark.parametrize("mode", ["peer", "a2a"])
+def test_sharded_matches_single_table(mode, D, tmp_path):
+    world = _world()
+    mp.spawn(_worker, args=(world, _free_port(), mode, D, str(tmp_path)), nprocs=world, join=True)
+    assert all(os.path.exists(os.path.join(str(tmp_path), "ok%d" % r)) for r in range(world))
