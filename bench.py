@@ -323,6 +323,117 @@ def main_b200(args, rank, world, local_rank):
         dist.destroy_process_group()
 
 
+# ------------------------------------------------------------------------------------------------
+# B200 arm, BASELINE configs[3]: 100M-row table row-sharded over the ranks (weak scaling: B per GPU fixed)
+# ------------------------------------------------------------------------------------------------
+def main_sharded(args, rank, world, local_rank):
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    import torch.distributed as dist
+    from recbox_b200 import ops, sharded
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    B, F, Fn, D, V = CFG["B"], CFG["F"], CFG["Fn"], args.dim, args.rows_per_field
+    Ft, R = F + Fn, F * V
+    sh = sharded.ShardedEmbeddingFM(R, D, mode=args.shard_mode, device=dev, max_ids=B * F, alloc=args.peer_alloc, with_lr=not args.no_lr)
+    gen = torch.Generator(device=dev).manual_seed(20240 + 4 + rank)
+    sh.table.normal_(0, 0.01, generator=gen)
+    sh.table_lr.normal_(0, 0.01, generator=gen)
+    g = torch.Generator().manual_seed(20240 + 4)
+    dense_w = (torch.randn(Fn, D, generator=g) * 0.1).to(dev)
+    dense_w_lr = (torch.randn(Fn, generator=g) * 0.1).to(dev)
+    bias = torch.zeros(1, device=dev)
+    field_off = [f * V for f in range(F)]
+    cat_pos, num_pos, pad_row = list(range(Fn, Ft)), list(range(Fn)), field_off
+    NB = 4
+    rows_l, dense_l = [], []
+    for i in range(NB):
+        ids = torch.from_numpy(make_ids(B, F, V, args.ids, 1000 * rank + i))
+        rows_l.append((ids + torch.tensor(field_off)[None]).to(torch.int32).to(dev))
+        dense_l.append(torch.rand(B, Fn, generator=g).to(dev))
+    dE = (torch.randn(B, Ft, D, generator=g) * 1e-3).to(dev)
+    d_fm = (torch.randn(B, generator=g) * 1e-3).to(dev)
+    d_lr = d_fm.clone()
+    gw, gw1, gb = torch.zeros(Fn, D, device=dev), torch.zeros(Fn, device=dev), torch.zeros(1, device=dev)
+    sh.barrier()
+
+    def step(i, evs=None):
+        rows, dx = rows_l[i % NB], dense_l[i % NB]
+        if evs: evs[0].record()
+        E, S, fm, lr = sh.forward(rows, cat_pos, dx, dense_w, dense_w_lr, num_pos, bias)
+        if evs: evs[1].record()
+        sh.backward(rows, cat_pos, pad_row, dx, dense_w, num_pos, E, S, dE, d_fm, d_lr, gw, gw1, gb)
+        if evs: evs[2].record()
+        sh.device_barrier()            # remote reductions of this step have landed in every owner's shard
+        if evs: evs[3].record()
+        return fm
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    K, W = args.steps, max(args.warmup, 3)
+    for i in range(W):
+        step(i)
+    sh.check_overflow()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(K)]
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    t0.record()
+    for i in range(K):
+        step(i, evs[i])
+    t1.record()
+    barrier()
+    sampler.stop_flag = True
+    sampler.join(timeout=2)
+    ms_total = t0.elapsed_time(t1)
+    t_f = sum(e[0].elapsed_time(e[1]) for e in evs) / K
+    t_b = sum(e[1].elapsed_time(e[2]) for e in evs) / K
+    t_s = sum(e[2].elapsed_time(e[3]) for e in evs) / K
+    times = torch.tensor([ms_total, t_f, t_b, t_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(times, op=dist.ReduceOp.MAX)
+    ms_total, t_f, t_b, t_s = times.tolist()
+    if rank == 0:
+        peak, peak_src = peaks()
+        bf, bb = bytes_fwd(F, Fn, D) * B, bytes_bwd(F, Fn, D) * B
+        remote = (world - 1) / world
+        nv_f = remote * B * F * (4 * D + 4)               # row + lr value read from peers
+        nv_b = remote * B * F * (4 * D + 4)               # row grad + lr grad reduced into peers
+        line = {
+            "metric": "samples/sec on Criteo-shaped synthetic (embedding + FM hot path, fwd+bwd)",
+            "value": B * world * K / (ms_total * 1e-3), "unit": "samples/s", "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "BASELINE configs[3]: DeepFM hot path, %d-row fused table (26 x %d) row-sharded over %d GPU(s), "
+                                   "D=%d, B=65536 per GPU; mode=%s" % (R, V, world, D, args.shard_mode),
+                       "global_batch": B * world, "ids": args.ids, "batches_rotated": NB,
+                       "l2": "table shard (%.1f GB) and E/dE streams exceed the 126 MB L2" % (sh.cap * D * 4 / 1e9),
+                       "parallelism": "dp%d batch shards + row-sharded table (r %% %d), exchange inside the fused kernels over NVLink" % (world, world)
+                       if args.shard_mode == "peer" else "dp%d + row-sharded table, NCCL all_to_all" % world},
+            "gpu_launches": (3 if args.shard_mode == "peer" else 12) * K,
+            "roofline": {"bound": "hbm" if world == 1 else "nvlink", "kernel": "embed_fm_bwd_sharded" if t_b >= t_f else "embed_fm_fwd_sharded",
+                         "achieved": max(bf / t_f, bb / t_b) / 1e6 if world == 1 else (nv_b / t_b if t_b >= t_f else nv_f / t_f) / 1e6,
+                         "peak": peak if world == 1 else 770.0, "unit": "GB/s",
+                         "frac": (max(bf / t_f, bb / t_b) / 1e6 / peak) if world == 1 else ((nv_b / t_b if t_b >= t_f else nv_f / t_f) / 1e6 / 770.0),
+                         "traffic": None,
+                         "peak_source": peak_src if world == 1 else "B200_PROFILING.md measured peer copy 770 GB/s per direction"},
+            "kernels": {"fwd": {"ms": t_f, "hbm_alg_gbs": bf / t_f / 1e6, "nvlink_gbs": nv_f / t_f / 1e6},
+                        "bwd": {"ms": t_b, "hbm_alg_gbs": bb / t_b / 1e6, "nvlink_gbs": nv_b / t_b / 1e6},
+                        "step_barrier": {"ms": t_s}},
+            "clocks": sampler.summary(),
+        }
+        print(json.dumps(line))
+    sh.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -331,12 +442,22 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--ids", default="uniform", choices=["uniform", "zipf"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="cfg2", choices=["cfg2", "sharded"],
+                    help="cfg2: BASELINE configs[1], replicated 1M-row table (default, the metric's config); "
+                         "sharded: configs[3], 100M-row table row-sharded over the ranks")
+    ap.add_argument("--shard-mode", default="push", choices=["push", "peer", "a2a"])
+    ap.add_argument("--peer-alloc", default="ipc", choices=["ipc", "symm"])
+    ap.add_argument("--no-lr", action="store_true", help="sharded workload without the first-order (LR) table")
+    ap.add_argument("--dim", type=int, default=16)
+    ap.add_argument("--rows-per-field", type=int, default=3846154)
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
         main_reference(args, rank, world)
+    elif args.workload == "sharded":
+        main_sharded(args, rank, world, local_rank)
     else:
         main_b200(args, rank, world, local_rank)
 

@@ -273,6 +273,36 @@ int rbx_embed_fm_bwd_sharded(const float* const* shard_tables /*HOST [world] | N
                              float* g_dense_w, float* g_dense_w_lr, float* g_lr_bias,
                              int64_t B, int64_t R, int F, int Fn, int D, int n_slots, rbx_stream_t stream);
 
+/* Push-based exchange (the path used for tables too large for remote gathers, see
+ * csrc/shard_push.cu): only dense, contiguous buffers cross NVLink; every random access is local
+ * to the row's owner.  All `*const*` arguments are HOST arrays of `world` DEVICE pointers valid on
+ * the calling device (own allocation or rbx_peer_open mapping); `cap` = slot capacity in ids per
+ * (owner, requester) pair; inbox_meta is int32 [world][4] = {count, offset, overflow flag, 0}.
+ *   rbx_shard_push_ids   requester: inbox_ids[w][rank*cap + j] = send[start_w + j] for every owner w
+ *                        (send / counts from rbx_shard_route), plus (count, start_w) into w's meta
+ *   rbx_shard_serve_rows owner: out_rows[q][(off_q + j)*D ..] = table[inbox_ids[q*cap + j]] (and the
+ *                        first-order value into out_lr[q]) -- rows land in q's buffer in q's send order
+ *   rbx_shard_push_grads requester: ginbox[w][(rank*cap + j)*D ..] = gsend[(start_w + j)*D ..]
+ *   rbx_shard_apply_grads owner: g_table[inbox_ids[q*cap + j]] += ginbox[q*cap + j]; then clears the
+ *                        owned padding rows (pad_local: DEVICE int32 [n_pad] local row numbers)
+ * The caller separates the phases with cross-rank barriers. */
+int rbx_shard_push_ids(const int32_t* send /*DEVICE [N]*/, const int32_t* counts /*DEVICE [world]*/,
+                       int32_t* const* inbox_ids, int32_t* const* inbox_meta,
+                       int rank, int world, int64_t cap, int64_t N, rbx_stream_t stream);
+int rbx_shard_serve_rows(const float* table /*DEVICE [R_w,D]*/, const float* table_lr /*DEVICE [R_w] | NULL*/, int D,
+                         const int32_t* inbox_ids /*DEVICE [world,cap]*/, const int32_t* inbox_meta /*DEVICE [world,4]*/,
+                         float* const* out_rows, float* const* out_lr /*| NULL*/,
+                         int world, int64_t cap, rbx_stream_t stream);
+int rbx_shard_push_grads(const float* gsend /*DEVICE [N,D]*/, const float* gsend_lr /*DEVICE [N] | NULL*/,
+                         const int32_t* counts /*DEVICE [world]*/,
+                         float* const* ginbox, float* const* ginbox_lr /*| NULL*/,
+                         int rank, int world, int64_t cap, int D, int64_t N, rbx_stream_t stream);
+int rbx_shard_apply_grads(const float* ginbox /*DEVICE [world,cap,D]*/, const float* ginbox_lr /*DEVICE [world,cap] | NULL*/,
+                          const int32_t* inbox_ids, const int32_t* inbox_meta,
+                          float* g_table, float* g_table_lr /*| NULL*/,
+                          int world, int64_t cap, int D,
+                          const int32_t* pad_local /*DEVICE [n_pad] | NULL*/, int n_pad, rbx_stream_t stream);
+
 /* Peer-visible device memory (CUDA IPC; one process per GPU, all on one box).
  * rbx_peer_alloc  : cudaMalloc'd block (IPC-exportable, unlike a caching-allocator sub-block)
  * rbx_peer_export : 64-byte handle the owner sends to its peers (any byte transport)

@@ -96,6 +96,10 @@ SIGNATURES = {
     "rbx_shard_unroute": [_P, _P, _P, _I64, _I, _P],
     "rbx_embed_fm_fwd_sharded": [_P, _P, _I] + [_P] * 12 + [_I64, _I64, _I, _I, _I, _I, _P],
     "rbx_embed_fm_bwd_sharded": [_P, _P, _P, _I] + [_P] * 15 + [_I64, _I64, _I, _I, _I, _I, _P],
+    "rbx_shard_push_ids": [_P, _P, _P, _P, _I, _I, _I64, _I64, _P],
+    "rbx_shard_serve_rows": [_P, _P, _I, _P, _P, _P, _P, _I, _I64, _P],
+    "rbx_shard_push_grads": [_P, _P, _P, _P, _P, _I, _I, _I64, _I, _I64, _P],
+    "rbx_shard_apply_grads": [_P, _P, _P, _P, _P, _P, _I, _I64, _I, _P, _I, _P],
     "rbx_peer_alloc": [_c.c_size_t, _P],
     "rbx_peer_free": [_P],
     "rbx_peer_export": [_P, _P],

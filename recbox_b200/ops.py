@@ -293,6 +293,30 @@ def shard_unroute(recv, pos):
     return out
 
 
+def shard_push_ids(send, counts, inbox_ids_ptrs, inbox_meta_ptrs, rank, world, cap):
+    _call("rbx_shard_push_ids", _p(send, I32, "send"), _p(counts, I32, "counts"), inbox_ids_ptrs, inbox_meta_ptrs,
+          rank, world, cap, send.numel(), _stream())
+
+
+def shard_serve_rows(table, table_lr, inbox_ids, inbox_meta, out_rows_ptrs, out_lr_ptrs, world, cap):
+    _call("rbx_shard_serve_rows", _p(table, F32, "table"), _p(table_lr, F32, "table_lr"), table.shape[1],
+          _p(inbox_ids, I32, "inbox_ids"), _p(inbox_meta, I32, "inbox_meta"), out_rows_ptrs, out_lr_ptrs, world, cap,
+          _stream())
+
+
+def shard_push_grads(gsend, gsend_lr, counts, ginbox_ptrs, ginbox_lr_ptrs, rank, world, cap):
+    N, D = gsend.shape
+    _call("rbx_shard_push_grads", _p(gsend, F32, "gsend"), _p(gsend_lr, F32, "gsend_lr"), _p(counts, I32, "counts"),
+          ginbox_ptrs, ginbox_lr_ptrs, rank, world, cap, D, N, _stream())
+
+
+def shard_apply_grads(ginbox, ginbox_lr, inbox_ids, inbox_meta, g_table, g_table_lr, world, cap, pad_local=None):
+    D = g_table.shape[1]
+    _call("rbx_shard_apply_grads", _p(ginbox, F32, "ginbox"), _p(ginbox_lr, F32, "ginbox_lr"), _p(inbox_ids, I32, "inbox_ids"),
+          _p(inbox_meta, I32, "inbox_meta"), _p(g_table, F32, "g_table"), _p(g_table_lr, F32, "g_table_lr"), world, cap, D,
+          _p(pad_local, I32, "pad_local"), 0 if pad_local is None else pad_local.numel(), _stream())
+
+
 # ------------------------------------------------------------------------------------------ a12
 def sqnorm_(g, acc):
     """acc (float64 [1], device) += sum(g^2)."""

@@ -13,6 +13,11 @@ row r // world.  One process per GPU, torch.distributed for the plumbing.  Two d
                the forward gathers remote rows with plain loads over NVLink / NVSwitch, the backward
                reduces (red.global.add) straight into the owner's gradient shard.  No routing, no
                staging buffers, no collective on the data path; a barrier separates steps.
+  mode="push"  (product path for tables too large for remote gathers -- random 64-byte reads into a
+               multi-GB peer mapping collapse to ~10 GB/s on NVSwitch, measured) the same exchange as
+               "a2a" but done by the kernels themselves: ids, rows and row gradients are streamed
+               into the peers' inboxes with plain stores over NVLink (csrc/shard_push.cu); no NCCL on
+               the data path, no host-side split sizes, no host synchronisation.
   mode="a2a"   (the NCCL baseline the north star names) bucket ids by owner (rbx_shard_route),
                all_to_all_single ids -> owners gather (rbx_gather_rows) -> all_to_all_single rows
                back; the un-permute is folded into the fused FM kernel by handing it the received
@@ -73,6 +78,26 @@ class PeerBlock(object):
             self.ptr = None
 
 
+class SymmBlock(object):
+    """The same block allocated through torch's symmetric memory (CUDA VMM: cuMemCreate / cuMemMap,
+    2 MB pages on the importing side too) instead of legacy CUDA IPC.  Collective over `group`."""
+
+    def __init__(self, numel, device, group=None):
+        import torch.distributed._symmetric_memory as symm_mem
+        self.device = torch.device(device)
+        self.numel = int(numel)
+        self.tensor = symm_mem.empty(max(self.numel, 4), dtype=F32, device=self.device)
+        self.tensor.zero_()
+        self.hdl = symm_mem.rendezvous(self.tensor, group if group is not None else dist.group.WORLD)
+        self.ptrs = [int(p) for p in self.hdl.buffer_ptrs]
+        self.ptr = self.tensor.data_ptr()
+        self.tensor = self.tensor[:self.numel]
+
+    def free(self):
+        self.tensor = None
+        self.hdl = None
+
+
 def open_peer(handle, device):
     lib = _lib.load()
     out = ctypes.c_void_p()
@@ -111,15 +136,17 @@ class ShardedEmbeddingFM(object):
     R: rows of the global fused table, D: embedding dim.  `table`, `table_lr`, `g_table`,
     `g_table_lr` are this rank's shards ([cap, D] / [cap], cap = ceil(R / world))."""
 
-    def __init__(self, R, D, mode="peer", group=None, device=None, with_lr=True, kern=None):
-        if mode not in ("peer", "a2a"):
-            raise RbxError("ShardedEmbeddingFM: mode must be 'peer' or 'a2a'")
+    def __init__(self, R, D, mode="peer", group=None, device=None, with_lr=True, kern=None, max_ids=None, slack=1.5,
+                 alloc="ipc"):
+        if mode not in ("peer", "push", "a2a"):
+            raise RbxError("ShardedEmbeddingFM: mode must be 'peer', 'push' or 'a2a'")
         self.R, self.D, self.mode, self.group, self.with_lr = int(R), int(D), mode, group, with_lr
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         if kern is None:
             from . import ops as kern
         self.kern = kern
+        self.alloc = alloc if (dist.is_initialized() and dist.get_world_size(group) > 1) else "ipc"
         self.cap = shard_capacity(self.R, self.world)
         self.n_local = local_rows(self.R, self.world, self.rank)
         self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
@@ -132,7 +159,7 @@ class ShardedEmbeddingFM(object):
                 raise RbxError("peer mode needs a power-of-two world <= 8 (got %d)" % self.world)
             # one block: table | table_lr | g_table | g_table_lr   (offsets in floats, 16-byte aligned)
             self._offs = (0, n_t, n_t + n_l4, 2 * n_t + n_l4)
-            self._block = PeerBlock(2 * n_t + 2 * n_l4, self.device)
+            self._block = self._shared_block(2 * n_t + 2 * n_l4)
             flat = self._block.tensor
         else:
             self._offs = (0, n_t, n_t + n_l4, 2 * n_t + n_l4)
@@ -148,18 +175,70 @@ class ShardedEmbeddingFM(object):
         if mode == "peer":
             self._map_peers()
         self._saved = None
+        self._ws = None
+        if mode == "push":
+            if max_ids is None:
+                raise RbxError("push mode needs max_ids (= max batch * categorical slots per rank)")
+            self._init_push(int(max_ids), float(slack))
+
+    # -- push-mode workspace: inboxes every peer can write ---------------------------------------------
+    def _init_push(self, max_ids, slack):
+        W, D = self.world, self.D
+        if W > 8:
+            raise RbxError("push mode covers up to 8 ranks (got %d)" % W)
+        self.max_ids = max_ids
+        self.slot_cap = min(max_ids, int(max_ids / W * slack) + 1024) if W > 1 else max_ids
+        al = lambda n: (n + 3) // 4 * 4
+        sizes = [("inbox_ids", al(W * self.slot_cap)), ("inbox_meta", al(W * 4)), ("rowbuf", al(max_ids * D)),
+                 ("rowbuf_lr", al(max_ids)), ("ginbox", al(W * self.slot_cap * D)), ("ginbox_lr", al(W * self.slot_cap))]
+        offs, tot = {}, 0
+        for name, n in sizes:
+            offs[name] = (tot, n)
+            tot += n
+        self._ws = self._shared_block(tot)
+        flat = self._ws.tensor
+        v = {name: flat[o:o + n] for name, (o, n) in offs.items()}
+        self.inbox_ids = v["inbox_ids"].view(I32)[:W * self.slot_cap]
+        self.inbox_meta = v["inbox_meta"].view(I32)[:W * 4]
+        self.rowbuf = v["rowbuf"][:max_ids * D].view(max_ids, D)
+        self.rowbuf_lr = v["rowbuf_lr"][:max_ids]
+        self.ginbox = v["ginbox"][:W * self.slot_cap * D]
+        self.ginbox_lr = v["ginbox_lr"][:W * self.slot_cap]
+        self.gsend = torch.zeros((max_ids, D), dtype=F32, device=self.device)
+        self.gsend_lr = torch.zeros(max_ids, dtype=F32, device=self.device)
+        base = self._peer_bases(self._ws)
+        self._ptr_arrays = {name: (ctypes.c_void_p * W)(*[b + o * 4 for b in base]) for name, (o, n) in offs.items()}
+        self._pad_cache = {}
+        self.barrier()
+
+    def check_overflow(self):
+        """Host check (synchronises): did any (owner, requester) bucket exceed its slot capacity?"""
+        if self.mode == "push" and int(self.inbox_meta.view(self.world, 4)[:, 2].max()) != 0:
+            raise RbxError("sharded push: an id bucket exceeded the slot capacity %d; raise `slack`" % self.slot_cap)
 
     # -- peer mapping ------------------------------------------------------------------------------
-    def _map_peers(self):
+    def _shared_block(self, numel):
+        if self.alloc == "symm":
+            return SymmBlock(numel, self.device, self.group)
+        return PeerBlock(numel, self.device)
+
+    def _peer_bases(self, block):
+        """Device pointers (valid on this device) of every rank's copy of `block`."""
+        if isinstance(block, SymmBlock):
+            return list(block.ptrs)
         base = [None] * self.world
-        base[self.rank] = self._block.ptr
+        base[self.rank] = block.ptr
         if self.world > 1:
             handles = [None] * self.world
-            dist.all_gather_object(handles, self._block.handle(), group=self.group)
+            dist.all_gather_object(handles, block.handle(), group=self.group)
             for w, h in enumerate(handles):
                 if w != self.rank:
                     base[w] = open_peer(h, self.device)
                     self._peers.append(base[w])
+        return base
+
+    def _map_peers(self):
+        base = self._peer_bases(self._block)
         o = self._offs
         mk = lambda off: (ctypes.c_void_p * self.world)(*[b + off * 4 for b in base])
         self._ptr_arrays = {"table": mk(o[0]), "table_lr": mk(o[1]), "g_table": mk(o[2]), "g_table_lr": mk(o[3])}
@@ -168,6 +247,11 @@ class ShardedEmbeddingFM(object):
         for p in self._peers:
             close_peer(p, self.device)
         self._peers = []
+        if self._ws is not None:
+            self.barrier()
+            self.inbox_ids = self.inbox_meta = self.rowbuf = self.rowbuf_lr = self.ginbox = self.ginbox_lr = None
+            self._ws.free()
+            self._ws = None
         if self._block is not None:
             self.barrier()
             self.table = self.table_lr = self.g_table = self.g_table_lr = self._gflat = self._flat = None
@@ -200,6 +284,15 @@ class ShardedEmbeddingFM(object):
     def zero_grad(self):
         self._gflat.zero_()
 
+    def device_barrier(self):
+        """Stream-ordered cross-rank barrier (a 1-element all-reduce on the current stream): every
+        rank's earlier kernels -- including their reductions into this rank's gradient shard -- have
+        completed before anything enqueued after it starts.  No host synchronisation."""
+        if self.world > 1:
+            if getattr(self, "_tok", None) is None:
+                self._tok = torch.zeros(1, dtype=F32, device=self.device)
+            dist.all_reduce(self._tok, group=self.group)
+
     def barrier(self):
         if self.world > 1:
             if self._flat is not None and self._flat.is_cuda:
@@ -212,6 +305,8 @@ class ShardedEmbeddingFM(object):
         """rows: int32 [B, F] GLOBAL row ids of this rank's batch shard.  Returns (E, S, fm, lr)."""
         if self.mode == "peer":
             out = self._fwd_peer(rows, cat_pos, dense_x, dense_w, dense_w_lr, list(num_pos), lr_bias, want_E, n_slots)
+        elif self.mode == "push":
+            out = self._fwd_push(rows, cat_pos, dense_x, dense_w, dense_w_lr, list(num_pos), lr_bias, want_E, n_slots)
         else:
             out = self._fwd_a2a(rows, cat_pos, dense_x, dense_w, dense_w_lr, list(num_pos), lr_bias, want_E, n_slots)
         return out
@@ -222,6 +317,9 @@ class ShardedEmbeddingFM(object):
         (replicated) gradients g_dense_* are local partial sums the caller all-reduces."""
         if self.mode == "peer":
             self._bwd_peer(rows, cat_pos, pad_rows, dense_x, dense_w, list(num_pos), E, S, dE, d_fm, d_lr,
+                           g_dense_w, g_dense_w_lr, g_lr_bias, n_slots)
+        elif self.mode == "push":
+            self._bwd_push(rows, cat_pos, pad_rows, dense_x, dense_w, list(num_pos), E, S, dE, d_fm, d_lr,
                            g_dense_w, g_dense_w_lr, g_lr_bias, n_slots)
         else:
             self._bwd_a2a(rows, cat_pos, pad_rows, dense_x, dense_w, list(num_pos), E, S, dE, d_fm, d_lr,
@@ -240,6 +338,51 @@ class ShardedEmbeddingFM(object):
                                        cat_pos, pad_rows, dense_x, dense_w, num_pos, E, S, dE, d_fm,
                                        d_lr if self.with_lr else None, g_dense_w, g_dense_w_lr, g_lr_bias,
                                        self.R, self.D, n_slots=n_slots)
+
+    # ---- push mode: the exchange done by the kernels, stores over NVLink into the peers' inboxes ---------
+    def _fwd_push(self, rows, cat_pos, dense_x, dense_w, dense_w_lr, num_pos, lr_bias, want_E, n_slots):
+        k, pa = self.kern, self._ptr_arrays
+        B, F = rows.shape
+        N = B * F
+        if N > self.max_ids:
+            raise RbxError("sharded push: %d ids exceed max_ids=%d" % (N, self.max_ids))
+        send, pos, counts = k.shard_route(rows.reshape(-1), self.world)
+        k.shard_push_ids(send, counts, pa["inbox_ids"], pa["inbox_meta"], self.rank, self.world, self.slot_cap)
+        self.device_barrier()                      # every requester's ids are in my inbox
+        k.shard_serve_rows(self.table, self.table_lr if self.with_lr else None, self.inbox_ids, self.inbox_meta,
+                           pa["rowbuf"], pa["rowbuf_lr"] if self.with_lr else None, self.world, self.slot_cap)
+        self.device_barrier()                      # every owner's rows are in my row buffer
+        E, S, fm, lr = k.embed_fm_fwd(self.rowbuf[:N], self.rowbuf_lr[:N] if self.with_lr else None, pos.view(B, F), cat_pos,
+                                      dense_x, dense_w, dense_w_lr, num_pos, lr_bias, want_E=want_E, want_lr=self.with_lr,
+                                      n_slots=n_slots)
+        self._saved = (pos, counts)
+        return E, S, fm, lr
+
+    def _bwd_push(self, rows, cat_pos, pad_rows, dense_x, dense_w, num_pos, E, S, dE, d_fm, d_lr,
+                  g_dense_w, g_dense_w_lr, g_lr_bias, n_slots):
+        if self._saved is None:
+            raise RbxError("ShardedEmbeddingFM.backward (push) needs the forward of the same batch first")
+        k, pa, D = self.kern, self._ptr_arrays, self.D
+        pos, counts = self._saved
+        B, F = rows.shape
+        N = B * F
+        use_lr = self.with_lr and d_lr is not None
+        gsend, gsend_lr = self.gsend[:N], (self.gsend_lr[:N] if use_lr else None)
+        gsend.zero_()
+        if use_lr:
+            gsend_lr.zero_()
+        k.embed_fm_bwd(self.rowbuf[:N], pos.view(B, F), cat_pos, None, dense_x, dense_w, num_pos, E, S, dE, d_fm,
+                       d_lr if use_lr else None, gsend, gsend_lr, g_dense_w, g_dense_w_lr, g_lr_bias, D, N, n_slots=n_slots)
+        k.shard_push_grads(gsend, gsend_lr, counts, pa["ginbox"], pa["ginbox_lr"] if use_lr else None, self.rank,
+                           self.world, self.slot_cap)
+        self.device_barrier()                      # every requester's gradients are in my inbox
+        key = tuple(pad_rows or ())
+        if key not in self._pad_cache:
+            mine = owned_pad_rows(pad_rows or [], self.world, self.rank)
+            self._pad_cache[key] = torch.tensor(mine, dtype=I32, device=self.device) if mine else None
+        k.shard_apply_grads(self.ginbox, self.ginbox_lr if use_lr else None, self.inbox_ids, self.inbox_meta, self.g_table,
+                            self.g_table_lr if use_lr else None, self.world, self.slot_cap, self._pad_cache[key])
+        self.device_barrier()                      # inboxes are free for the next step
 
     # ---- a2a mode: route -> all_to_all ids -> gather -> all_to_all rows -> fused FM on the received buffer --
     def _exchange_counts(self, counts):

@@ -42,7 +42,7 @@ def _worker(rank, world, port, mode, D, out_dir):
         sl = slice(rank * B, (rank + 1) * B)
         rows, dx = f["rows"][sl].contiguous(), f["dense_x"][sl].contiguous()
 
-        sh = sharded.ShardedEmbeddingFM(pb.R, D, mode=mode, device=dev)
+        sh = sharded.ShardedEmbeddingFM(pb.R, D, mode=mode, device=dev, max_ids=B * pb.F, slack=3.0)
         sh.load_global(f["table"], f["table_lr"])
         E, S, fm, lr = sh.forward(rows, pb.cat_pos, dx, f["dense_w"], f["dense_w_lr"], pb.num_pos, f["bias"])
         gw, gw1, gb = torch.zeros_like(f["dense_w"]), torch.zeros_like(f["dense_w_lr"]), torch.zeros(1, device=dev)
@@ -52,6 +52,7 @@ def _worker(rank, world, port, mode, D, out_dir):
             sh.backward(rows, pb.cat_pos, pb.pad_row, dx, f["dense_w"], pb.num_pos, E if use_E else None, S,
                         dE[sl].contiguous(), d_fm[sl].contiguous(), d_lr[sl].contiguous(), gw, gw1, gb)
         sh.barrier()
+        sh.check_overflow()
         for t in (gw, gw1, gb):
             dist.all_reduce(t)
         gt, gt1 = sh.gather_global("g_table"), sh.gather_global("g_table_lr")
@@ -61,6 +62,13 @@ def _worker(rank, world, port, mode, D, out_dir):
                                             f["dense_w_lr"], pb.num_pos, f["bias"])
         assert torch.equal(E, Er[sl]), "gathered rows must be bit-exact"
         assert torch.equal(S, Sr[sl]) and torch.equal(fm, fmr[sl]) and torch.equal(lr, lrr[sl]), "same kernel, same order"
+        if mode == "push":      # a bucket larger than its slot is flagged, not silently dropped
+            tiny = sharded.ShardedEmbeddingFM(pb.R, D, mode="push", device=dev, max_ids=B * pb.F, slack=0.0)
+            tiny.slot_cap = 8
+            tiny.forward(rows, pb.cat_pos, dx, f["dense_w"], f["dense_w_lr"], pb.num_pos, f["bias"])
+            with pytest.raises(sharded.RbxError):
+                tiny.check_overflow()
+            tiny.close()
         rt, rt1 = torch.zeros_like(f["table"]), torch.zeros_like(f["table_lr"])
         rw, rw1, rb = torch.zeros_like(gw), torch.zeros_like(gw1), torch.zeros_like(gb)
         for use_E in (True, False):
@@ -86,7 +94,7 @@ def _world():
 
 
 @pytest.mark.parametrize("D", [16, 64])
-@pytest.mark.parametrize("mode", ["peer", "a2a"])
+@pytest.mark.parametrize("mode", ["peer", "push", "a2a"])
 def test_sharded_matches_single_table(mode, D, tmp_path):
     world = _world()
     mp.spawn(_worker, args=(world, _free_port(), mode, D, str(tmp_path)), nprocs=world, join=True)
