@@ -45,6 +45,21 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def ncu_traffic(kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel`, from the committed ncu
+    capture of this workload (profiles/r*_traffic.json, newest round); None if not captured."""
+    import glob
+    for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_traffic.json")), reverse=True):
+        try:
+            with open(path) as f:
+                d = json.load(f)
+            if kernel in d:
+                return d[kernel]["dram_bytes_read"] + d[kernel]["dram_bytes_write"]
+        except Exception:
+            pass
+    return None
+
+
 def make_ids(B, F, V, kind, seed):
     rng = np.random.default_rng(seed)
     if kind == "zipf":
@@ -175,6 +190,7 @@ def main_b200(args, rank, world, local_rank):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
+    l2_persist = ops.l2_set_persisting_bytes(int(os.environ.get("RBX_L2_PERSIST_MB", "0")) << 20)
     B, F, Fn, D, V = CFG["B"], CFG["F"], CFG["Fn"], CFG["D"], CFG["V"]
     Ft, R = F + Fn, F * V
     g = torch.Generator().manual_seed(20240 + 2 + rank)
@@ -261,25 +277,58 @@ def main_b200(args, rank, world, local_rank):
     t_b = sum(e[2].elapsed_time(e[3]) for e in evs) / K
 
     # ---- e2e: pinned host float64 batch -> H2D -> split -> step -> logits back to host ----
+    # Every step's input crosses PCIe inside the timed region.  The loader-side prefetch is the usual
+    # one: batch i+1 is copied on a copy stream while batch i computes (two device buffers, events
+    # both ways); the logits go back on a third stream.
     dev_batch = [torch.empty_like(host_batches[0], device=dev) for _ in range(2)]
-    out_host = torch.empty(B, dtype=torch.float32).pin_memory()
+    out_host = [torch.empty(B, dtype=torch.float32).pin_memory() for _ in range(2)]
+    logit_dev = [torch.empty(B, dtype=torch.float32, device=dev) for _ in range(2)]
+    main = torch.cuda.current_stream()
+    h2d, d2h = torch.cuda.Stream(), torch.cuda.Stream()
+    ev_in = [torch.cuda.Event() for _ in range(2)]      # batch landed in dev_batch[j]
+    ev_free = [torch.cuda.Event() for _ in range(2)]    # dev_batch[j] consumed (split done)
+    ev_out = [torch.cuda.Event() for _ in range(2)]     # logits of slot j computed
+    ev_read = [torch.cuda.Event() for _ in range(2)]    # logits of slot j copied to the host
 
-    def e2e_step(i):
-        M = dev_batch[i % 2]
-        M.copy_(host_batches[i % NB], non_blocking=True)
-        rows, dx, lab = ops.split_batch(M, col_kind, col_slot, field_off, F, Fn)
+    def e2e_copy(i):
+        j = i % 2
+        with torch.cuda.stream(h2d):
+            h2d.wait_event(ev_free[j])
+            dev_batch[j].copy_(host_batches[i % NB], non_blocking=True)
+            ev_in[j].record(h2d)
+
+    def e2e_compute(i):
+        j = i % 2
+        main.wait_event(ev_in[j])
+        rows, dx, lab = ops.split_batch(dev_batch[j], col_kind, col_slot, field_off, F, Fn)
+        ev_free[j].record(main)
         E, S, fm, lr = fwd(rows, dx)
-        logit = fm + lr
-        out_host.copy_(logit, non_blocking=True)
+        main.wait_event(ev_read[j])                      # the previous logits of this slot left the device
+        torch.add(fm, lr, out=logit_dev[j])
+        ev_out[j].record(main)
+        with torch.cuda.stream(d2h):
+            d2h.wait_event(ev_out[j])
+            out_host[j].copy_(logit_dev[j], non_blocking=True)
+            ev_read[j].record(d2h)
         zero()
         bwd(rows, dx, E, S)
-    for i in range(W):
-        e2e_step(i)
+
+    def e2e_run(n):
+        e2e_copy(0)
+        for i in range(n):
+            if i + 1 < n:
+                e2e_copy(i + 1)
+            e2e_compute(i)
+        main.wait_stream(d2h)
+    for e in ev_free + ev_read:
+        e.record(main)
     e_beg, e_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    if not args.no_e2e:
+        e2e_run(W)
     barrier()
     e_beg.record()
-    for i in range(K):
-        e2e_step(i)
+    if not args.no_e2e:
+        e2e_run(K)
     e_end.record()
     barrier()
     ms_e2e = e_beg.elapsed_time(e_end)
@@ -304,14 +353,14 @@ def main_b200(args, rank, world, local_rank):
             "value": B * world * K / (ms_total * 1e-3), "unit": "samples/s", "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic", "config": workload_config(args.ids, world),
-            "e2e": {"value": B * world * K / (ms_e2e * 1e-3), "unit": "samples/s",
+            "e2e": None if args.no_e2e else {"value": B * world * K / (ms_e2e * 1e-3), "unit": "samples/s",
                     "h2d_bytes_per_step": host_batches[0].numel() * 8, "d2h_bytes_per_step": B * 4,
                     "ms_per_step": ms_e2e / K},
             "gpu_launches": 3 * K,
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                         "traffic": None, "peak_source": peak_src,
+                         "traffic": ncu_traffic(dom) if args.ids == "uniform" else None, "peak_source": peak_src,
                          "pair_achieved": (bf + bb) / (t_f + t_b) / 1e6, "pair_frac": (bf + bb) / (t_f + t_b) / 1e6 / peak},
-            "kernels": kern,
+            "kernels": kern, "l2_persisting_bytes": l2_persist,
             "clocks": sampler.summary(),
         }
         if world == 1 and not args.no_cpu_baseline:
@@ -442,11 +491,12 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--ids", default="uniform", choices=["uniform", "zipf"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end leg (profiling runs under ncu)")
     ap.add_argument("--workload", default="cfg2", choices=["cfg2", "sharded"],
                     help="cfg2: BASELINE configs[1], replicated 1M-row table (default, the metric's config); "
                          "sharded: configs[3], 100M-row table row-sharded over the ranks")
-    ap.add_argument("--shard-mode", default="push", choices=["push", "peer", "a2a"])
-    ap.add_argument("--peer-alloc", default="ipc", choices=["ipc", "symm"])
+    ap.add_argument("--shard-mode", default="peer", choices=["push", "peer", "a2a"])
+    ap.add_argument("--peer-alloc", default="symm", choices=["ipc", "symm"])
     ap.add_argument("--no-lr", action="store_true", help="sharded workload without the first-order (LR) table")
     ap.add_argument("--dim", type=int, default=16)
     ap.add_argument("--rows-per-field", type=int, default=3846154)

@@ -46,6 +46,10 @@ typedef void* rbx_stream_t;      /* cudaStream_t */
 int         rbx_version(void);            /* 10000*major + 100*minor + patch */
 const char* rbx_last_error(void);         /* thread-local, never NULL */
 int         rbx_device_sm_count(void);    /* SM count of the current device (<0 on error) */
+/* Reserve `bytes` of the current device's L2 for persisting (evict_last) lines -- what the fused
+ * kernels' table / gradient-table hints live in.  Clamped to the device maximum; returns the size
+ * in effect, <0 on error.  Process-wide device setting: the host decides, the kernels only hint. */
+long long   rbx_l2_set_persisting_bytes(long long bytes);
 
 /* ------------------------------------------------------------------------------------------
  * a1  batch matrix -> slot blocks

@@ -76,6 +76,7 @@ SIGNATURES = {
     "rbx_version": [],
     "rbx_last_error": [],
     "rbx_device_sm_count": [],
+    "rbx_l2_set_persisting_bytes": [_c.c_longlong],
     "rbx_split_batch_f64": [_P, _I64, _I, _I64, _P, _P, _P, _I, _I, _P, _P, _P, _P],
     "rbx_pack_columns": [_P, _P, _P, _P, _I, _I64, _I, _P, _P],
     "rbx_embed_fm_fwd": [_P] * 15 + [_I64, _I64, _I, _I, _I, _I, _P],
@@ -128,7 +129,8 @@ def load():
         if fn is None:
             raise RbxError("%s does not export %s (stale build?)" % (LIB_PATH, name))
         fn.argtypes = argtypes
-        fn.restype = {"rbx_last_error": ctypes.c_char_p, "rbx_shard_ws_bytes": ctypes.c_size_t}.get(name, ctypes.c_int)
+        fn.restype = {"rbx_last_error": ctypes.c_char_p, "rbx_shard_ws_bytes": ctypes.c_size_t,
+                      "rbx_l2_set_persisting_bytes": ctypes.c_longlong}.get(name, ctypes.c_int)
     _lib = lib
     return lib
 

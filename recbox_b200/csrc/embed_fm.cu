@@ -97,14 +97,23 @@ constexpr int kWarps = kThreads / 32;
 #ifndef RBX_BWD_U
 #define RBX_BWD_U 4         // slots per chunk, backward (2 streaming loads + 1 red each)
 #endif
+#ifndef RBX_BWD_WARP_AGG
+#define RBX_BWD_WARP_AGG 1  // aggregate same-row reductions across the samples of a warp before the atomic
+#endif
+#ifndef RBX_BWD_REVERSE
+#define RBX_BWD_REVERSE 0   // 1: the backward walks the batch back to front (L2 reuse of the forward's tail)
+#endif
 #ifndef RBX_L2_HINTS
-#define RBX_L2_HINTS 0      // bit 0: table/grad rows evict_last; bit 1: E/dE streams evict_first
+#define RBX_L2_HINTS 3      // (sweeps: profiles/r1_variant_sweeps.md) bit 0: table row loads evict_last; bit 1: E/dE streams evict_first; bit 2: grad reds evict_last
 #endif
 #if RBX_L2_HINTS & 1
 #define LD_ROW(p) ld_row_f4_hint(p, pol_keep)
-#define RED_ROW(p, v) red_add_f4_hint(p, v, pol_keep)
 #else
 #define LD_ROW(p) ld_row_f4(p)
+#endif
+#if RBX_L2_HINTS & 4
+#define RED_ROW(p, v) red_add_f4_hint(p, v, pol_keep)
+#else
 #define RED_ROW(p, v) red_add_f4(p, v)
 #endif
 // reductions into a peer's gradient table travel over NVLink: vector (v4) or four scalar reds
@@ -396,6 +405,9 @@ __global__ void __launch_bounds__(kThreads, RBX_BWD_MINB) k_embed_fm_bwd(const _
     const int lig = lane & (LPR - 1), gi = lane / LPR;
     const int F = p.F, Ft = p.Ft;
     const bool has_fm = p.d_fm != nullptr;
+    constexpr bool kAgg = RBX_BWD_WARP_AGG && SPW > 1;
+    constexpr unsigned kGroupMask = LPR >= 32 ? 0xffffffffu : ((1u << LPR) - 1u);
+    (void)kGroupMask;
     const uint64_t pol_keep = l2_policy_evict_last(), pol_stream = l2_policy_evict_first();
     (void)pol_keep; (void)pol_stream;
 
@@ -410,22 +422,26 @@ __global__ void __launch_bounds__(kThreads, RBX_BWD_MINB) k_embed_fm_bwd(const _
         mbar_expect_tx(&my_bar[buf], stage_tx_bytes(b0 * F, ns * F));
         stage_words(my_idx + (size_t)buf * wi, p.rows, b0 * F, ns * F, &my_bar[buf]);
     };
+    // RBX_BWD_REVERSE: walk the batch from its END.  The forward wrote E front to back, so the tail of
+    // E (and of the ids) is what is still resident in L2 when the backward starts.
+    auto group_of = [&](int64_t t) { return RBX_BWD_REVERSE ? G - 1 - t : t; };
     if (kStaged) {
         if (lane == 0) {
             mbar_init(&my_bar[0], 1);
             mbar_init(&my_bar[1], 1);
             fence_mbar_init();
-            if (gw < G) issue(gw, 0);
+            if (gw < G) issue(group_of(gw), 0);
         }
         __syncwarp();
     }
 
     int it = 0;
-    for (int64_t g = gw; g < G; g += nw, ++it) {
+    for (int64_t t = gw; t < G; t += nw, ++it) {
+        const int64_t g = group_of(t);
         const int buf = it & 1;
         const int64_t b0 = g * SPW;
         if (kStaged) {
-            if (lane == 0 && g + nw < G) issue(g + nw, buf ^ 1);
+            if (lane == 0 && t + nw < G) issue(group_of(t + nw), buf ^ 1);
             mbar_wait(&my_bar[buf], (it >> 1) & 1);
             __syncwarp();
         }
@@ -439,12 +455,36 @@ __global__ void __launch_bounds__(kThreads, RBX_BWD_MINB) k_embed_fm_bwd(const _
             S = ld_stream_f4(p.S + (size_t)b * D + 4 * lig);
             dfm = __ldg(p.d_fm + b);
         }
-        if ((kSharded ? p.g_shard_lr[0] != nullptr : p.g_table_lr != nullptr) && p.d_lr && valid) {
-            const float dlr = __ldg(p.d_lr + b);
-#pragma unroll 4
-            for (int f = lig; f < F; f += LPR) {
-                const int32_t r = kStaged ? rb[f] : __ldg(rb + f);
-                if (r != p.pad_row[f] && (uint32_t)r < (uint64_t)p.R) red_add_f1(grad_lr_dst<kSharded>(p, r, f), dlr);
+        if ((kSharded ? p.g_shard_lr[0] != nullptr : p.g_table_lr != nullptr) && p.d_lr) {
+            const float dlr = valid ? __ldg(p.d_lr + b) : 0.f;
+#pragma unroll 2
+            for (int f0 = 0; f0 < F; f0 += LPR) {            // uniform trip count: the warp votes inside
+                const int f = f0 + lig;
+                int32_t r = -1, key = -1;
+                if (valid && f < F) {
+                    const int32_t tr = kStaged ? rb[f] : __ldg(rb + f);
+                    if (tr != p.pad_row[f] && (uint32_t)tr < (uint64_t)p.R) {
+                        r = tr;
+                        key = kSharded ? tr : tr + p.meta.lr_delta[f];
+                    }
+                }
+                float v = dlr;
+                bool leader = true;
+                if (kAgg) {
+                    // warp-aggregated atomics: lanes (= samples) hitting the same first-order row send ONE red
+                    const unsigned peers = __match_any_sync(0xffffffffu, key);
+                    if (__any_sync(0xffffffffu, key >= 0 && peers != (1u << lane))) {
+                        float acc = 0.f;
+#pragma unroll
+                        for (int sg = 0; sg < SPW; ++sg) {
+                            const float d = __shfl_sync(0xffffffffu, dlr, sg * LPR);
+                            acc = fmaf(d, (float)__popc(peers & (kGroupMask << (sg * LPR))), acc);
+                        }
+                        v = acc;
+                        leader = (__ffs(peers) - 1) == lane;
+                    }
+                }
+                if (r >= 0 && leader) red_add_f1(grad_lr_dst<kSharded>(p, r, f), v);
             }
         }
         if (kSharded ? p.g_shard[0] != nullptr : p.g_table != nullptr) {
@@ -471,10 +511,28 @@ __global__ void __launch_bounds__(kThreads, RBX_BWD_MINB) k_embed_fm_bwd(const _
                 }
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
-                    if (r[u] >= 0) {
-                        if (has_fm) gr[u] = f4_fma(f4_sub(S, e[u]), dfm, gr[u]);
-                        RED_GRAD((grad_dst<kSharded, D>(p, r[u]) + 4 * lig), gr[u]);
+                    if (r[u] >= 0 && has_fm) gr[u] = f4_fma(f4_sub(S, e[u]), dfm, gr[u]);
+                    bool leader = true;
+                    if (kAgg) {
+                        // warp-aggregated atomics: the SPW samples of this warp that hit the same row in this slot
+                        // (hot ids under Zipf) are summed with shuffles and reduced into memory once
+                        const unsigned peers = __match_any_sync(0xffffffffu, r[u]);
+                        if (__any_sync(0xffffffffu, r[u] >= 0 && peers != (kGroupMask << (gi * LPR)))) {
+                            float4 acc = gr[u];
+#pragma unroll
+                            for (int sg = 0; sg < SPW; ++sg) {
+                                float4 v;
+                                v.x = __shfl_sync(0xffffffffu, gr[u].x, sg * LPR + lig);
+                                v.y = __shfl_sync(0xffffffffu, gr[u].y, sg * LPR + lig);
+                                v.z = __shfl_sync(0xffffffffu, gr[u].z, sg * LPR + lig);
+                                v.w = __shfl_sync(0xffffffffu, gr[u].w, sg * LPR + lig);
+                                if (sg != gi && ((peers >> (sg * LPR)) & 1u)) acc = f4_add(acc, v);
+                            }
+                            gr[u] = acc;
+                            leader = (__ffs(peers) - 1) / LPR == gi;
+                        }
                     }
+                    if (r[u] >= 0 && leader) RED_GRAD((grad_dst<kSharded, D>(p, r[u]) + 4 * lig), gr[u]);
                 }
             }
         }

@@ -39,4 +39,18 @@ int rbx_device_sm_count(void) {
     return n;
 }
 
+// L2 set-aside for persisting (evict_last) lines: without it the evict_last hints of the fused kernels
+// have nothing to live in.  bytes is clamped to the device maximum; returns the size in effect (<0 = error).
+long long rbx_l2_set_persisting_bytes(long long bytes) {
+    int dev = 0, max_bytes = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e == cudaSuccess) e = cudaDeviceGetAttribute(&max_bytes, cudaDevAttrMaxPersistingL2CacheSize, dev);
+    if (e != cudaSuccess) return rbx_fail(RBX_ERR_CUDA, "rbx_l2_set_persisting_bytes: %s", cudaGetErrorString(e));
+    if (bytes < 0) bytes = 0;
+    if (bytes > max_bytes) bytes = max_bytes;
+    e = cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)bytes);
+    if (e != cudaSuccess) return rbx_fail(RBX_ERR_CUDA, "rbx_l2_set_persisting_bytes: %s", cudaGetErrorString(e));
+    return bytes;
+}
+
 }  // extern "C"

@@ -46,6 +46,14 @@ def _call(name, *args):
 F32, I32 = torch.float32, torch.int32
 
 
+def l2_set_persisting_bytes(nbytes):
+    """Reserve part of the current device's L2 for the kernels' evict_last lines; returns the size in effect."""
+    got = _lib.load().rbx_l2_set_persisting_bytes(int(nbytes))
+    if got < 0:
+        raise RbxError("rbx_l2_set_persisting_bytes failed: %s" % _lib.load().rbx_last_error().decode())
+    return int(got)
+
+
 # ------------------------------------------------------------------------------------------- a1
 def split_batch(batch, col_kind, col_slot, field_off, F, Fn, want_label=True):
     """[B, n_cols] float64 device matrix -> (rows int32 [B,F], dense_x fp32 [B,Fn], label fp32 [B])."""

@@ -134,10 +134,13 @@ class ShardedEmbeddingFM(object):
     """Fused multi-slot gather + FM + LR over a row-sharded table.
 
     R: rows of the global fused table, D: embedding dim.  `table`, `table_lr`, `g_table`,
-    `g_table_lr` are this rank's shards ([cap, D] / [cap], cap = ceil(R / world))."""
+    `g_table_lr` are this rank's shards ([cap, D] / [cap], cap = ceil(R / world)).
+    alloc: how peer-visible memory is obtained -- "symm" (CUDA VMM via torch symmetric memory; peers map
+    it with 2 MB pages) or "ipc" (legacy cudaIpc*; measured to collapse to ~10 GB/s for random access
+    into multi-GB tables, kept for small tables / debugging)."""
 
     def __init__(self, R, D, mode="peer", group=None, device=None, with_lr=True, kern=None, max_ids=None, slack=1.5,
-                 alloc="ipc"):
+                 alloc="symm"):
         if mode not in ("peer", "push", "a2a"):
             raise RbxError("ShardedEmbeddingFM: mode must be 'peer', 'push' or 'a2a'")
         self.R, self.D, self.mode, self.group, self.with_lr = int(R), int(D), mode, group, with_lr

@@ -1,0 +1,107 @@
+"""Parity at BASELINE.json's full size (configs[1]: B = 65 536, 26 cat + 13 dense, 26 x 38 462 rows,
+D = 16) through size-independent properties -- the oracle finishes only small cases in seconds:
+
+  * gather exactness : E[b, pos_f, :] is bit-identical to table[rows[b, f], :] (index_select)
+  * FM identity      : fm = 1/2 (|S|^2 - sum_f |e_f|^2), S = sum_f e_f  (inner_product.py:42-48), in float64
+  * checksum         : sum of all gradient rows = sum_b sum_f (dE + d_fm (S - e)) over non-pad slots
+  * linearity        : bwd(a dE1 + dE2, ...) = a bwd(dE1) + bwd(dE2)
+  * padding          : rows equal to the slot's pad row receive exactly zero gradient
+  * idempotence      : two forwards of the same batch are bit-identical
+"""
+import numpy as np
+import pytest
+import torch
+
+from helpers import assert_close
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+B, F, Fn, D, V = 65536, 26, 13, 16, 38462
+
+
+@pytest.fixture(scope="module")
+def setup():
+    from recbox_b200 import ops
+    g = torch.Generator().manual_seed(7)
+    R = F * V
+    table = (torch.randn(R, D, generator=g) * 0.05).to(DEV)
+    table_lr = (torch.randn(R, generator=g) * 0.05).to(DEV)
+    dense_w = (torch.randn(Fn, D, generator=g) * 0.1).to(DEV)
+    dense_w_lr = (torch.randn(Fn, generator=g) * 0.1).to(DEV)
+    bias = torch.full((1,), 0.25, device=DEV)
+    rng = np.random.default_rng(7)
+    ids = rng.integers(0, V, size=(B, F))
+    ids[rng.random((B, F)) < 0.05] = 0                      # 5 % padding ids
+    off = np.arange(F) * V
+    rows = torch.from_numpy((ids + off).astype(np.int32)).to(DEV)
+    dx = torch.rand(B, Fn, generator=g).to(DEV)
+    cat_pos, num_pos = list(range(Fn, Fn + F)), list(range(Fn))
+    pad_row = [int(o) for o in off]
+    for p in pad_row:
+        table[p] = 0
+        table_lr[p] = 0
+    return dict(ops=ops, table=table, table_lr=table_lr, dense_w=dense_w, dense_w_lr=dense_w_lr, bias=bias, rows=rows,
+                dx=dx, cat_pos=cat_pos, num_pos=num_pos, pad_row=pad_row, R=R, g=g)
+
+
+def _fwd(s):
+    return s["ops"].embed_fm_fwd(s["table"], s["table_lr"], s["rows"], s["cat_pos"], s["dx"], s["dense_w"], s["dense_w_lr"],
+                                 s["num_pos"], s["bias"])
+
+
+def _bwd(s, E, S, dE, d_fm, d_lr):
+    gt = torch.zeros_like(s["table"])
+    gt1 = torch.zeros_like(s["table_lr"])
+    gw, gw1, gb = torch.zeros_like(s["dense_w"]), torch.zeros_like(s["dense_w_lr"]), torch.zeros(1, device=DEV)
+    s["ops"].embed_fm_bwd(s["table"], s["rows"], s["cat_pos"], s["pad_row"], s["dx"], s["dense_w"], s["num_pos"], E, S, dE,
+                          d_fm, d_lr, gt, gt1, gw, gw1, gb, D, s["R"])
+    return gt, gt1, gw, gw1, gb
+
+
+def test_full_size_forward_properties(setup):
+    s = setup
+    E, S, fm, lr = _fwd(s)
+    assert torch.equal(E[:, Fn:, :], s["table"][s["rows"].long()]), "gather must be bit-exact at full size"
+    assert torch.equal(E[:, :Fn, :], s["dx"][:, :, None] * s["dense_w"][None]), "numeric slots: x * w"
+    E64 = E.double()
+    S64 = E64.sum(1)
+    assert_close(S, S64, what="S")
+    fm64 = 0.5 * (S64.pow(2).sum(-1) - E64.pow(2).sum((1, 2)))
+    assert_close(fm, fm64, atol_scale=2e-5, what="fm identity")
+    lr64 = s["table_lr"].double()[s["rows"].long()].sum(1) + (s["dx"].double() * s["dense_w_lr"].double()[None]).sum(1) + 0.25
+    assert_close(lr, lr64, what="lr")
+    E2, S2, fm2, lr2 = _fwd(s)
+    assert torch.equal(E, E2) and torch.equal(S, S2) and torch.equal(fm, fm2) and torch.equal(lr, lr2), "idempotent"
+
+
+def test_full_size_backward_properties(setup):
+    s = setup
+    g = s["g"]
+    E, S, fm, lr = _fwd(s)
+    dE1 = torch.randn(B, F + Fn, D, generator=g).to(DEV)
+    dE2 = torch.randn(B, F + Fn, D, generator=g).to(DEV)
+    d1 = torch.randn(B, generator=g).to(DEV)
+    d2 = torch.randn(B, generator=g).to(DEV)
+    a = 0.5
+    g1 = _bwd(s, E, S, dE1, d1, d1)
+    g2 = _bwd(s, E, S, dE2, d2, d2)
+    g12 = _bwd(s, E, S, a * dE1 + dE2, a * d1 + d2, a * d1 + d2)
+    for x1, x2, x12, name in zip(g1, g2, g12, ("g_table", "g_table_lr", "g_dense_w", "g_dense_w_lr", "g_bias")):
+        assert_close(x12, a * x1.double() + x2.double(), atol_scale=3e-5, what="linearity " + name)
+    gt, gt1, gw, gw1, gb = g1
+    # padding rows: exactly zero
+    pads = torch.tensor(s["pad_row"], device=DEV)
+    assert float(gt[pads].abs().sum()) == 0.0 and float(gt1[pads].abs().sum()) == 0.0
+    # checksum of checksums: column sums of the whole gradient table vs the per-sample formula in float64
+    keep = (s["rows"] != pads[None].int()).double()                          # [B,F]
+    ge = dE1[:, Fn:, :].double() + d1.double()[:, None, None] * (S.double()[:, None, :] - E[:, Fn:, :].double())
+    want = (ge * keep[:, :, None]).sum((0, 1))
+    assert_close(gt.double().sum(0), want, atol_scale=1e-5, rtol=1e-5, what="grad table column sums")
+    assert_close(gt1.double().sum(), (keep * d1.double()[:, None]).sum(), what="lr grad checksum")
+    assert_close(gb, d1.double().sum().reshape(1), atol_scale=1e-5, what="bias grad")
+    gn = dE1[:, :Fn, :].double() + d1.double()[:, None, None] * (S.double()[:, None, :] - E[:, :Fn, :].double())
+    assert_close(gw, (s["dx"].double()[:, :, None] * gn).sum(0), atol_scale=2e-5, what="dense_w grad")
+    # the scatter really is index_add: compare against torch's index_add on the same per-slot gradients
+    ref = torch.zeros(s["R"], D, dtype=torch.float64, device=DEV)
+    ref.index_add_(0, s["rows"].long().reshape(-1), (ge * keep[:, :, None]).reshape(-1, D))
+    assert_close(gt, ref, atol_scale=2e-5, what="scatter-add vs index_add_")

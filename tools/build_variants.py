@@ -15,6 +15,15 @@ VARIANTS = {
     "l2_stream": ["RBX_L2_HINTS=2"],
     "l2_both": ["RBX_L2_HINTS=3"],
     "l2_both_minb4": ["RBX_L2_HINTS=3", "RBX_FWD_MINB=4"],
+    "h3": ["RBX_L2_HINTS=3"], "h6": ["RBX_L2_HINTS=6"], "h7": ["RBX_L2_HINTS=7"], "h2": ["RBX_L2_HINTS=2"],
+    "noagg": ["RBX_BWD_WARP_AGG=0"],
+    "rev": ["RBX_BWD_REVERSE=1"],
+    "rev_l2both": ["RBX_BWD_REVERSE=1", "RBX_L2_HINTS=3"],
+    "fwd_u13_b2": ["RBX_FWD_U=13", "RBX_FWD_MINB=2"],
+    "fwd_u6_b4": ["RBX_FWD_U=6", "RBX_FWD_MINB=4"],
+    "fwd_u4_b5": ["RBX_FWD_U=4", "RBX_FWD_MINB=5"],
+    "bwd_u8_b3": ["RBX_BWD_U=8", "RBX_BWD_MINB=3"],
+    "bwd_u2_b6": ["RBX_BWD_U=2", "RBX_BWD_MINB=6"],
 }
 
 if __name__ == "__main__":

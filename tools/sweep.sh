@@ -3,11 +3,13 @@
 tag=$1; shift
 mkdir -p gpurun_out
 : > gpurun_out/${tag}_sweep.jsonl
-for v in "$@"; do
-  RBX_LIB_PATH=$PWD/build/variants/$v.so python bench.py --steps 30 --warmup 5 --no-cpu-baseline 2>>gpurun_out/${tag}_sweep.err | python -c "
+for spec in "$@"; do
+  v=${spec%%:*}; mb=0; [ "$spec" != "$v" ] && mb=${spec##*:}
+  export RBX_L2_PERSIST_MB=$mb
+  RBX_LIB_PATH=$PWD/build/variants/$v.so python bench.py --steps 30 --warmup 5 --no-cpu-baseline $BENCH_ARGS 2>>gpurun_out/${tag}_sweep.err | python -c "
 import sys, json
 for l in sys.stdin:
-    d = json.loads(l); d['variant'] = '$v'; print(json.dumps(d))" >> gpurun_out/${tag}_sweep.jsonl
+    d = json.loads(l); d['variant'] = '$spec'; print(json.dumps(d))" >> gpurun_out/${tag}_sweep.jsonl
 done
 python - <<PY
 import json
