@@ -338,6 +338,48 @@ int rbx_adam_dense(float* w, const float* g, float* m, float* v, int64_t n,
                    float lr, float beta1, float beta2, float eps, int step,
                    rbx_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------
+ * f1  touched-rows clip + optimizer (same reference lines as a12).
+ * `rows` = sorted-unique table rows the batch touched (rbx_unique_ids_i32 over its global row ids),
+ * n_rows_dev = its length in DEVICE memory (NULL: use max_rows), max_rows bounds the launch.
+ * rbx_sqnorm_rows : out[0] += sum over touched rows |g[row,:]|^2  (equals the dense sum)
+ * rbx_optim_rows  : kind 0 SGD (exact), 1 Adagrad (exact; v = state sum), 2 Adam -- the dense formula
+ *                   of rbx_adam_dense on touched rows only ("lazy": untouched rows keep their moments,
+ *                   which is NOT the reference's dense Adam), 3 torch.optim.SparseAdam's formula.
+ *                   g' = g * clip[0].  zero_grad != 0 clears the consumed gradient rows, so the dense
+ *                   gradient table stays all-zero between steps with no O(table) memset.
+ * ------------------------------------------------------------------------------------------ */
+int rbx_sqnorm_rows(const float* g /*DEVICE [R,D]*/, const int32_t* rows /*DEVICE [max_rows]*/,
+                    const int64_t* n_rows_dev /*DEVICE [1] | NULL*/, int64_t max_rows, int D,
+                    double* out /*DEVICE [1]*/, rbx_stream_t stream);
+int rbx_optim_rows(float* w, float* g, float* m /*| NULL*/, float* v /*| NULL*/,
+                   const int32_t* rows, const int64_t* n_rows_dev, int64_t max_rows, int D,
+                   const float* clip /*DEVICE [1] | NULL*/, int kind,
+                   float lr, float beta1, float beta2, float eps, int step, int zero_grad,
+                   rbx_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * a14  sorted unique + inverse + first occurrence of a bag of ids bounded by a vocabulary
+ * (collate_fn_unique, recbox/matching/pytorch/dataloaders/h5_generator.py:45-53:
+ *  torch.unique(item_indexes.flatten(), return_inverse=True, sorted=True) + the flip/scatter_
+ *  "return_index").  No sort: a vocab-bit bitmap + popcount prefix (csrc/dedup.cu).
+ *   uniq[0..U)   ascending distinct ids            (capacity min(n, vocab))
+ *   first[u]     smallest flat position i with ids[i] == uniq[u]   (int64; NULL to skip)
+ *   inverse[i]   u with uniq[u] == ids[i]; -1 for an id outside [0, vocab)   (NULL to skip)
+ *   n_out[0] = U, n_out[1] = number of out-of-range ids          (DEVICE int64[2])
+ * ws = rbx_unique_ws_bytes(vocab) bytes of 8-byte aligned DEVICE scratch.  Also used to list the
+ * table rows a batch touched (vocab = R) for the f1 optimizer.
+ * ------------------------------------------------------------------------------------------ */
+size_t rbx_unique_ws_bytes(int64_t vocab);
+int rbx_unique_ids_i64(const int64_t* ids /*DEVICE [n]*/, int64_t n, int64_t vocab,
+                       void* ws /*DEVICE*/, size_t ws_bytes,
+                       int64_t* uniq, int64_t* first, int64_t* inverse, int64_t* n_out,
+                       rbx_stream_t stream);
+int rbx_unique_ids_i32(const int32_t* ids /*DEVICE [n]*/, int64_t n, int64_t vocab,
+                       void* ws /*DEVICE*/, size_t ws_bytes,
+                       int32_t* uniq, int64_t* first, int32_t* inverse, int64_t* n_out,
+                       rbx_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -326,11 +326,42 @@ def golden_config1(L, tmp):
     npz("config1_fm", **out)
 
 
-def main():
+def golden_collate_unique():
+    """a14: the reference's collate_fn_unique (matching/pytorch/dataloaders/h5_generator.py:45-58) called as its
+    DataLoader would call it -- a list of per-sample (user_dict, item_dict, label, item_indexes) tuples."""
+    from recbox.matching.pytorch.dataloaders.h5_generator import collate_fn_unique
+    rng = np.random.default_rng(77)
+    out, cases = {}, [(8, 3, 12), (64, 10, 500), (256, 4, 40), (33, 0, 1000)]
+    for k, (B, negs, vocab) in enumerate(cases):
+        item = np.minimum(rng.zipf(1.3, size=(B, 1 + negs)), vocab - 1).astype(np.int64)
+        batch = []
+        for b in range(B):
+            item_dict = {"item_id": torch.from_numpy(item[b].copy()), "cate": torch.from_numpy(item[b] % 7)}
+            batch.append(({"user_id": torch.tensor(b)}, item_dict, torch.tensor(1.0), torch.from_numpy(item[b].copy())))
+        user_dict, item_dict, labels, inverse = collate_fn_unique(batch)
+        uniq = item_dict["item_id"]
+        flat = torch.from_numpy(item).flatten()
+        # unique_indexes is local to the reference function; recover it from what it returns: the row it kept for
+        # each distinct item is flat[unique_indexes] == unique, and "cate" was gathered with the same indexes
+        first = np.array([int(np.nonzero(flat.numpy() == u)[0][0]) for u in uniq.numpy()], dtype=np.int64)
+        assert torch.equal(flat[first], uniq) and torch.equal((flat % 7)[first], item_dict["cate"])
+        out["item_indexes_%d" % k] = item
+        out["vocab_%d" % k] = np.int64(vocab)
+        out["unique_%d" % k] = uniq.numpy()
+        out["unique_indexes_%d" % k] = first
+        out["inverse_indexes_%d" % k] = inverse.numpy()
+        out["labels_%d" % k] = labels.numpy()
+    out["n_cases"] = np.int64(len(cases))
+    npz("collate_unique", **out)
+
+
+def main(only=None):
     if not ref_shim.available():
         raise SystemExit("reference tree not found at %s" % ref_shim.REFERENCE_ROOT)
     L = ref_shim.install()
     torch.set_num_threads(1)       # deterministic CPU reductions
+    if only == "collate_unique":    # added after the other fixtures were minted; regenerate it alone
+        return golden_collate_unique()
     with tempfile.TemporaryDirectory() as tmp:
         golden_interaction(L)
         golden_pooling(L)
@@ -343,7 +374,8 @@ def main():
         golden_two_tower()
         golden_deepfm_train(L, tmp)
         golden_config1(L, tmp)
+    golden_collate_unique()
 
 
 if __name__ == "__main__":
-    main()
+    main(sys.argv[1] if len(sys.argv) > 1 else None)

@@ -281,6 +281,60 @@ def unique_items(item_indexes):
     return uniq, first, inverse.reshape(-1)
 
 
+def collate_unique_reference(item_indexes):
+    """collate_fn_unique's item-id arithmetic, line for line in its own torch calls
+    (recbox/matching/pytorch/dataloaders/h5_generator.py:49-52,58): returns (unique, unique_indexes,
+    inverse_indexes) exactly as the reference does -- including that the returned inverse is the flipped one."""
+    item_indexes = torch.as_tensor(item_indexes)
+    unique, inverse_indexes = torch.unique(item_indexes.flatten(), return_inverse=True, sorted=True)
+    perm = torch.arange(inverse_indexes.size(0), dtype=inverse_indexes.dtype)
+    inverse_indexes, perm = inverse_indexes.flip([0]), perm.flip([0])
+    unique_indexes = inverse_indexes.new_empty(unique.size(0)).scatter_(0, inverse_indexes, perm)
+    return unique, unique_indexes, inverse_indexes
+
+
+# --------------------------------------------------------------------------------------------
+# (f1)  touched-rows optimizers: the published torch.optim algorithms run on CPU tensors
+# --------------------------------------------------------------------------------------------
+def touched_rows_step(kind, w, g, state, step, lr=1e-3, beta1=0.9, beta2=0.999, eps=1e-8, clip=1.0):
+    """One update of table w [R, D] with dense gradient g restricted to its non-zero ("touched") rows.
+    kind: "sgd" / "adagrad" (torch.optim.SGD / Adagrad: exact on a dense gradient, untouched rows do not move),
+    "adam_rows" (adam_step of this file on the touched rows only), "sparse_adam" (torch.optim.SparseAdam).
+    state: dict with "m", "v" tensors (updated in place).  Returns the new w."""
+    w = w.clone()
+    g = g * clip
+    rows = torch.nonzero(g.reshape(g.shape[0], -1).abs().sum(1) > 0).reshape(-1)
+    if kind == "sgd":
+        w[rows] = w[rows] - lr * g[rows]
+    elif kind == "adagrad":
+        p = torch.nn.Parameter(w.clone())
+        opt = torch.optim.Adagrad([p], lr=lr, eps=eps)
+        opt.state[p]["sum"] = state["v"].clone()
+        opt.state[p]["step"] = torch.tensor(float(step - 1))
+        p.grad = g.clone()
+        opt.step()
+        state["v"].copy_(opt.state[p]["sum"])
+        w = p.detach().clone()
+    elif kind == "adam_rows":
+        wr, mr, vr = w[rows].clone(), state["m"][rows].clone(), state["v"][rows].clone()
+        adam_step(wr, g[rows].clone(), mr, vr, step, lr, beta1, beta2, eps)
+        w[rows], state["m"][rows], state["v"][rows] = wr, mr, vr
+    elif kind == "sparse_adam":
+        p = torch.nn.Parameter(w.clone())
+        opt = torch.optim.SparseAdam([p], lr=lr, betas=(beta1, beta2), eps=eps)
+        opt.state[p]["step"] = step - 1
+        opt.state[p]["exp_avg"] = state["m"].clone()
+        opt.state[p]["exp_avg_sq"] = state["v"].clone()
+        p.grad = torch.sparse_coo_tensor(rows.unsqueeze(0), g[rows], size=g.shape).coalesce()
+        opt.step()
+        state["m"].copy_(opt.state[p]["exp_avg"])
+        state["v"].copy_(opt.state[p]["exp_avg_sq"])
+        w = p.detach().clone()
+    else:
+        raise ValueError(kind)
+    return w
+
+
 # --------------------------------------------------------------------------------------------
 # (e)  row-shard routing around the all-to-all  (new; defined in SURVEY.md section 8e)
 # --------------------------------------------------------------------------------------------

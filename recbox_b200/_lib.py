@@ -110,6 +110,11 @@ SIGNATURES = {
     "rbx_sqnorm": [_P, _I64, _P, _P],
     "rbx_clip_coef": [_P, _F, _P, _P, _P],
     "rbx_adam_dense": [_P, _P, _P, _P, _I64, _P, _F, _F, _F, _F, _I, _P],
+    "rbx_sqnorm_rows": [_P, _P, _P, _I64, _I, _P, _P],
+    "rbx_optim_rows": [_P, _P, _P, _P, _P, _P, _I64, _I, _P, _I, _F, _F, _F, _F, _I, _I, _P],
+    "rbx_unique_ws_bytes": [_I64],
+    "rbx_unique_ids_i64": [_P, _I64, _I64, _P, _c.c_size_t, _P, _P, _P, _P, _P],
+    "rbx_unique_ids_i32": [_P, _I64, _I64, _P, _c.c_size_t, _P, _P, _P, _P, _P],
 }
 
 
@@ -129,7 +134,7 @@ def load():
         if fn is None:
             raise RbxError("%s does not export %s (stale build?)" % (LIB_PATH, name))
         fn.argtypes = argtypes
-        fn.restype = {"rbx_last_error": ctypes.c_char_p, "rbx_shard_ws_bytes": ctypes.c_size_t,
+        fn.restype = {"rbx_last_error": ctypes.c_char_p, "rbx_shard_ws_bytes": ctypes.c_size_t, "rbx_unique_ws_bytes": ctypes.c_size_t,
                       "rbx_l2_set_persisting_bytes": ctypes.c_longlong}.get(name, ctypes.c_int)
     _lib = lib
     return lib

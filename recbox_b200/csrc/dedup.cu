@@ -1,0 +1,198 @@
+// a14: sorted unique + inverse + first occurrence of a bag of item ids, for ids bounded by a
+// known vocabulary (every id the reference's loaders produce is < vocab_size of its feature).
+//
+// Replaces torch.unique(item_indexes.flatten(), return_inverse=True, sorted=True) and the
+// flip/scatter_ "return_index" trick of collate_fn_unique
+// (recbox/matching/pytorch/dataloaders/h5_generator.py:45-53), which sorts on the CPU inside the
+// DataLoader worker.  No sort here: because ids live in [0, vocab) the sorted-unique set is a
+// BITMAP of vocab bits (1.25 MB for 10 M items -- it lives in L2), the rank of an id is a
+// popcount prefix over that bitmap, and the whole job is five streaming passes:
+//   1 clear bitmap            2 mark: atomicOr(bitmap[id>>5], 1 << (id&31))
+//   3 per-CTA popcount sums   4 scan of the CTA sums (one CTA) + word prefixes, emit sorted uniques
+//   5 inverse[i] = prefix[id>>5] + popc(bitmap[id>>5] & lower bits); first[rank] = min(i)
+// Integer work: results are bit-identical to numpy/torch unique (tests compare with the oracle).
+#include "rbx_common.cuh"
+
+namespace {
+
+constexpr int kT = 256;             // threads per CTA
+constexpr int kWPT = 8;             // bitmap words per thread in the count / emit passes
+constexpr int kChunk = kT * kWPT;   // words per CTA (= 65 536 ids of vocabulary)
+
+struct UniqueWs {
+    uint32_t* bitmap;    // [W]
+    uint32_t* wprefix;   // [W]   exclusive popcount prefix of every word
+    uint32_t* blocksum;  // [NB]  popcount of every chunk, then its exclusive prefix
+    int64_t* counters;   // [2]   n_unique, n_out_of_range (mirrors of n_out, for the kernels)
+};
+
+__host__ __device__ inline int64_t words_of(int64_t vocab) { return (vocab + 31) / 32; }
+
+size_t ws_bytes(int64_t vocab) {
+    const int64_t W = words_of(vocab), NB = (W + kChunk - 1) / kChunk;
+    return (size_t)(2 * W + NB) * 4 + 64;
+}
+
+UniqueWs carve(void* ws, int64_t vocab) {
+    const int64_t W = words_of(vocab), NB = (W + kChunk - 1) / kChunk;
+    UniqueWs u;
+    u.counters = reinterpret_cast<int64_t*>(ws);                              // 64 bytes reserved
+    u.bitmap = reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(ws) + 64);
+    u.wprefix = u.bitmap + W;
+    u.blocksum = u.wprefix + W;
+    (void)NB;
+    return u;
+}
+
+template <typename IdT>
+__global__ void __launch_bounds__(kT) k_mark(const IdT* __restrict__ ids, int64_t n, int64_t vocab, uint32_t* bitmap,
+                                             int64_t* n_out) {
+    int64_t bad = 0;
+    for (int64_t i = (int64_t)blockIdx.x * kT + threadIdx.x; i < n; i += (int64_t)gridDim.x * kT) {
+        const int64_t id = (int64_t)ids[i];
+        if (id < 0 || id >= vocab) { ++bad; continue; }
+        const uint32_t bit = 1u << (id & 31);
+        // most ids of a batch are distinct: test first so repeated (hot) ids do not serialise on the atomic
+        if (!(__ldcg(bitmap + (id >> 5)) & bit)) atomicOr(bitmap + (id >> 5), bit);
+    }
+    if (bad) atomicAdd(reinterpret_cast<unsigned long long*>(n_out + 1), (unsigned long long)bad);
+}
+
+__device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t* total) {
+    __shared__ uint32_t s_warp[kT / 32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+    }
+    if (lane == 31) s_warp[warp] = inc;
+    __syncthreads();
+    uint32_t base = 0, tot = 0;
+#pragma unroll
+    for (int w = 0; w < kT / 32; ++w) {
+        const uint32_t s = s_warp[w];
+        if (w < warp) base += s;
+        tot += s;
+    }
+    __syncthreads();
+    *total = tot;
+    return base + inc - v;
+}
+
+__global__ void __launch_bounds__(kT) k_count(const uint32_t* __restrict__ bitmap, int64_t W, uint32_t* blocksum) {
+    const int64_t w0 = (int64_t)blockIdx.x * kChunk + (int64_t)threadIdx.x * kWPT;
+    uint32_t c = 0;
+#pragma unroll
+    for (int k = 0; k < kWPT; ++k)
+        if (w0 + k < W) c += __popc(bitmap[w0 + k]);
+    uint32_t total;
+    (void)block_exclusive_scan(c, &total);
+    if (threadIdx.x == 0) blocksum[blockIdx.x] = total;
+}
+
+// one CTA: exclusive scan of the chunk sums in place, total -> n_out[0]
+__global__ void __launch_bounds__(kT) k_scan_chunks(uint32_t* blocksum, int64_t NB, int64_t* n_out) {
+    uint32_t carry = 0;
+    for (int64_t base = 0; base < NB; base += kT) {
+        const int64_t i = base + threadIdx.x;
+        const uint32_t v = i < NB ? blocksum[i] : 0u;
+        uint32_t total;
+        const uint32_t ex = block_exclusive_scan(v, &total);
+        if (i < NB) blocksum[i] = carry + ex;
+        carry += total;
+    }
+    if (threadIdx.x == 0) n_out[0] = (int64_t)carry;
+}
+
+template <typename IdT>
+__global__ void __launch_bounds__(kT) k_emit(const uint32_t* __restrict__ bitmap, int64_t W, const uint32_t* __restrict__ blocksum,
+                                             uint32_t* wprefix, IdT* uniq, int64_t* first, int64_t n) {
+    const int64_t w0 = (int64_t)blockIdx.x * kChunk + (int64_t)threadIdx.x * kWPT;
+    uint32_t words[kWPT], c = 0;
+#pragma unroll
+    for (int k = 0; k < kWPT; ++k) {
+        words[k] = (w0 + k < W) ? bitmap[w0 + k] : 0u;
+        c += __popc(words[k]);
+    }
+    uint32_t total;
+    uint32_t rank = blocksum[blockIdx.x] + block_exclusive_scan(c, &total);
+#pragma unroll
+    for (int k = 0; k < kWPT; ++k) {
+        if (w0 + k < W) wprefix[w0 + k] = rank;
+        uint32_t m = words[k];
+        while (m) {
+            const int b = __ffs(m) - 1;
+            m &= m - 1;
+            if (uniq) uniq[rank] = (IdT)((w0 + k) * 32 + b);
+            if (first) first[rank] = n;           // sentinel; k_inverse takes the minimum position
+            ++rank;
+        }
+    }
+}
+
+template <typename IdT>
+__global__ void __launch_bounds__(kT) k_inverse(const IdT* __restrict__ ids, int64_t n, int64_t vocab,
+                                                const uint32_t* __restrict__ bitmap, const uint32_t* __restrict__ wprefix,
+                                                IdT* inverse, int64_t* first) {
+    for (int64_t i = (int64_t)blockIdx.x * kT + threadIdx.x; i < n; i += (int64_t)gridDim.x * kT) {
+        const int64_t id = (int64_t)ids[i];
+        if (id < 0 || id >= vocab) {
+            if (inverse) inverse[i] = (IdT)-1;
+            continue;
+        }
+        const uint32_t word = __ldg(bitmap + (id >> 5));
+        const uint32_t rank = __ldg(wprefix + (id >> 5)) + __popc(word & ((1u << (id & 31)) - 1u));
+        if (inverse) inverse[i] = (IdT)rank;
+        if (first) atomicMin(reinterpret_cast<unsigned long long*>(first + rank), (unsigned long long)i);
+    }
+}
+
+template <typename IdT>
+int unique_impl(const char* who, const IdT* ids, int64_t n, int64_t vocab, void* ws, size_t ws_have, IdT* uniq, int64_t* first,
+                IdT* inverse, int64_t* n_out, rbx_stream_t stream) {
+    RBX_REQUIRE(n >= 0 && vocab >= 1, "%s: n=%lld vocab=%lld", who, (long long)n, (long long)vocab);
+    RBX_REQUIRE(vocab <= (int64_t)INT32_MAX * 32, "%s: vocab=%lld too large for the bitmap", who, (long long)vocab);
+    RBX_REQUIRE(sizeof(IdT) == 8 || vocab <= (int64_t)INT32_MAX, "%s: int32 ids need vocab < 2^31", who);
+    RBX_REQUIRE(n == 0 || ids, "%s: ids is null", who);
+    RBX_REQUIRE(n_out, "%s: n_out (device int64[2]) is required", who);
+    RBX_REQUIRE(ws && ws_have >= ws_bytes(vocab), "%s: workspace of %zu bytes needed (rbx_unique_ws_bytes), got %zu", who,
+                ws_bytes(vocab), ws_have);
+    RBX_REQUIRE((uintptr_t)ws % 8 == 0, "%s: workspace must be 8-byte aligned", who);
+    cudaStream_t st = rbx_cast_stream(stream);
+    const int64_t W = words_of(vocab), NB = (W + kChunk - 1) / kChunk;
+    const UniqueWs u = carve(ws, vocab);
+    cudaError_t e = cudaMemsetAsync(ws, 0, 64 + (size_t)W * 4, st);           // counters + bitmap
+    if (e == cudaSuccess) e = cudaMemsetAsync(n_out, 0, 16, st);
+    if (e != cudaSuccess) return rbx_fail(RBX_ERR_CUDA, "%s: memset: %s", who, cudaGetErrorString(e));
+    const int64_t cap = (int64_t)rbx_sm_count() * 8;
+    int64_t g = (n + kT - 1) / kT;
+    if (g > cap) g = cap;
+    if (g < 1) g = 1;
+    if (n > 0) k_mark<IdT><<<(int)g, kT, 0, st>>>(ids, n, vocab, u.bitmap, n_out);
+    k_count<<<(int)NB, kT, 0, st>>>(u.bitmap, W, u.blocksum);
+    k_scan_chunks<<<1, kT, 0, st>>>(u.blocksum, NB, n_out);
+    k_emit<IdT><<<(int)NB, kT, 0, st>>>(u.bitmap, W, u.blocksum, u.wprefix, uniq, first, n);
+    if (n > 0 && (inverse || first)) k_inverse<IdT><<<(int)g, kT, 0, st>>>(ids, n, vocab, u.bitmap, u.wprefix, inverse, first);
+    RBX_LAUNCH_CHECK(who);
+    return RBX_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+size_t rbx_unique_ws_bytes(int64_t vocab) { return vocab < 1 ? 0 : ws_bytes(vocab); }
+
+int rbx_unique_ids_i64(const int64_t* ids, int64_t n, int64_t vocab, void* ws, size_t ws_bytes_have, int64_t* uniq,
+                       int64_t* first, int64_t* inverse, int64_t* n_out, rbx_stream_t stream) {
+    return unique_impl<int64_t>("rbx_unique_ids_i64", ids, n, vocab, ws, ws_bytes_have, uniq, first, inverse, n_out, stream);
+}
+
+int rbx_unique_ids_i32(const int32_t* ids, int64_t n, int64_t vocab, void* ws, size_t ws_bytes_have, int32_t* uniq,
+                       int64_t* first, int32_t* inverse, int64_t* n_out, rbx_stream_t stream) {
+    return unique_impl<int32_t>("rbx_unique_ids_i32", ids, n, vocab, ws, ws_bytes_have, uniq, first, inverse, n_out, stream);
+}
+
+}  // extern "C"

@@ -79,6 +79,10 @@ struct BwdParams {
     float* g_shard_lr[RBX_MAX_WORLD];
     SlotMeta meta;
     int32_t pad_row[RBX_MAX_SLOTS];
+    // numeric-slot / bias batch reductions folded into the vector kernel: the CTA accumulates
+    // g_dense_w [Fn,D] | g_dense_w_lr [Fn] | g_lr_bias [1] in the first num_smem bytes of its dynamic
+    // shared memory and flushes them with one red per element at the end (0 = separate kernels)
+    int num_smem;
 };
 
 constexpr int kThreads = 256;
@@ -99,6 +103,9 @@ constexpr int kWarps = kThreads / 32;
 #endif
 #ifndef RBX_BWD_WARP_AGG
 #define RBX_BWD_WARP_AGG 1  // aggregate same-row reductions across the samples of a warp before the atomic
+#endif
+#ifndef RBX_BWD_FUSE_NUM
+#define RBX_BWD_FUSE_NUM 1  // numeric-slot / bias batch reductions inside the vector backward kernel (0: k_dense_w_bwd*)
 #endif
 #ifndef RBX_BWD_REVERSE
 #define RBX_BWD_REVERSE 0   // 1: the backward walks the batch back to front (L2 reuse of the forward's tail)
@@ -412,8 +419,15 @@ __global__ void __launch_bounds__(kThreads, RBX_BWD_MINB) k_embed_fm_bwd(const _
     (void)pol_keep; (void)pol_stream;
 
     const int wi = (SPW * F + 6) & ~3;
-    int32_t* my_idx = reinterpret_cast<int32_t*>(smem_raw) + (size_t)warp * 2 * wi;
-    uint64_t* my_bar = reinterpret_cast<uint64_t*>(smem_raw + (size_t)kWarps * 2 * wi * 4) + warp * 2;
+    float* s_gw = reinterpret_cast<float*>(smem_raw);                       // [Fn*D] | [Fn] | [1], see BwdParams::num_smem
+    unsigned char* stage_raw = smem_raw + p.num_smem;
+    int32_t* my_idx = reinterpret_cast<int32_t*>(stage_raw) + (size_t)warp * 2 * wi;
+    uint64_t* my_bar = reinterpret_cast<uint64_t*>(stage_raw + (size_t)kWarps * 2 * wi * 4) + warp * 2;
+    const bool fuse_num = p.num_smem > 0;
+    if (fuse_num) {
+        for (int i = threadIdx.x; i < p.Fn * D + p.Fn + 1; i += kThreads) s_gw[i] = 0.f;
+        __syncthreads();
+    }
     const int64_t G = (p.B + SPW - 1) / SPW;
     const int64_t gw = (int64_t)blockIdx.x * kWarps + warp, nw = (int64_t)gridDim.x * kWarps;
     auto issue = [&](int64_t g, int buf) {
@@ -536,7 +550,79 @@ __global__ void __launch_bounds__(kThreads, RBX_BWD_MINB) k_embed_fm_bwd(const _
                 }
             }
         }
+        if (fuse_num) {
+            // numeric slots (nn.Linear(1, D) on x.view(-1,1)) and the first-order / bias terms are batch
+            // reductions: sum over the warp's samples with shuffles, then one shared-memory add per element
+            const int Fn = p.Fn;
+            const float* xb = p.dense_x + b * Fn;
+            if (p.g_dense_w && (p.dE || has_fm)) {
+                for (int n0 = 0; n0 < Fn; n0 += U) {
+                    float x[U];
+                    float4 g[U];
+#pragma unroll
+                    for (int u = 0; u < U; ++u) {
+                        x[u] = 0.f;
+                        g[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (valid && n0 + u < Fn) {
+                            x[u] = __ldg(xb + n0 + u);
+                            if (p.dE) g[u] = LD_STREAM(p.dE + eoff + (size_t)p.meta.num_pos[n0 + u] * D);
+                        }
+                    }
+#pragma unroll
+                    for (int u = 0; u < U; ++u) {
+                        if (n0 + u < Fn) {
+                            const int n = n0 + u;
+                            if (has_fm) {
+                                const float4 w = ld_row_f4(p.dense_w + (size_t)p.meta.num_widx[n] * D + 4 * lig);
+                                g[u] = f4_fma(f4_sub(S, f4_scale(w, x[u])), dfm, g[u]);
+                            }
+                            float4 c = f4_scale(g[u], x[u]);
+#pragma unroll
+                            for (int o = LPR; o < 32; o <<= 1) {
+                                c.x += __shfl_xor_sync(0xffffffffu, c.x, o);
+                                c.y += __shfl_xor_sync(0xffffffffu, c.y, o);
+                                c.z += __shfl_xor_sync(0xffffffffu, c.z, o);
+                                c.w += __shfl_xor_sync(0xffffffffu, c.w, o);
+                            }
+                            if (gi == 0) {
+                                float* a = s_gw + n * D + 4 * lig;
+                                atomicAdd(a, c.x);
+                                atomicAdd(a + 1, c.y);
+                                atomicAdd(a + 2, c.z);
+                                atomicAdd(a + 3, c.w);
+                            }
+                        }
+                    }
+                }
+            }
+            if (p.d_lr && (p.g_dense_w_lr || p.g_lr_bias)) {
+                const float dlr = valid ? __ldg(p.d_lr + b) : 0.f;
+                for (int n0 = 0; n0 <= Fn; n0 += LPR) {          // role n < Fn: g_dense_w_lr[n]; n == Fn: bias
+                    const int n = n0 + lig;
+                    float v = 0.f;
+                    if (valid && n < Fn) v = __ldg(xb + n) * dlr;
+                    else if (n == Fn) v = dlr;
+#pragma unroll
+                    for (int o = LPR; o < 32; o <<= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+                    if (gi == 0 && n <= Fn) atomicAdd(s_gw + Fn * D + n, v);
+                }
+            }
+        }
         if (kStaged) __syncwarp();
+    }
+    if (fuse_num) {
+        __syncthreads();
+        const int Fn = p.Fn;
+        if (p.g_dense_w)
+            for (int i = threadIdx.x; i < Fn * LPR; i += kThreads) {
+                const int n = i / LPR, c = i - n * LPR;
+                red_add_f4(p.g_dense_w + (size_t)p.meta.num_widx[n] * D + 4 * c, *reinterpret_cast<const float4*>(s_gw + n * D + 4 * c));
+            }
+        if (p.d_lr)
+            for (int i = threadIdx.x; i <= Fn; i += kThreads) {
+                if (i < Fn && p.g_dense_w_lr) red_add_f1(p.g_dense_w_lr + p.meta.num_widx[i], s_gw[Fn * D + i]);
+                if (i == Fn && p.g_lr_bias) red_add_f1(p.g_lr_bias, s_gw[Fn * D + i]);
+            }
     }
 }
 
@@ -762,7 +848,7 @@ template <int LPR, int U>
 int launch_bwd(BwdParams& p, bool staged, bool sharded, cudaStream_t st) {
     constexpr int SPW = 32 / LPR;
     const int64_t groups = (p.B + SPW - 1) / SPW;
-    const size_t smem = staged_smem(SPW, p.F, 0);
+    const size_t smem = staged_smem(SPW, p.F, 0) + p.num_smem;
     if (sharded) {
         if (!staged || smem > 200 * 1024 || set_smem_limit(k_embed_fm_bwd<LPR, U, true, true>, smem) != 0) return -1;
         const int grid = grid_for((const void*)k_embed_fm_bwd<LPR, U, true, true>, smem, groups);
@@ -776,8 +862,8 @@ int launch_bwd(BwdParams& p, bool staged, bool sharded, cudaStream_t st) {
             return 0;
         }
     }
-    const int grid = grid_for((const void*)k_embed_fm_bwd<LPR, U, false, false>, 0, groups);
-    k_embed_fm_bwd<LPR, U, false, false><<<grid, kThreads, 0, st>>>(p);
+    const int grid = grid_for((const void*)k_embed_fm_bwd<LPR, U, false, false>, p.num_smem, groups);
+    k_embed_fm_bwd<LPR, U, false, false><<<grid, kThreads, p.num_smem, st>>>(p);
     return 0;
 }
 
@@ -915,10 +1001,20 @@ int embed_fm_bwd_impl(const char* who, const float* table, const ShardArgs& sh, 
     for (int f = 0; f < F; ++f) p.pad_row[f] = pad_row ? pad_row[f] : -1;
     cudaStream_t st = rbx_cast_stream(stream);
 
+    const bool want_w = Fn > 0 && g_dense_w && (dE || d_fm);
+    const bool want_lr = d_lr && ((Fn > 0 && g_dense_w_lr) || g_lr_bias);
+    bool num_fused = false;
+    p.num_smem = 0;
     if (F > 0 && (any_g || (any_g_lr && d_lr)) && (dE || d_fm || d_lr)) {
         const bool aligned = al16(table) && al16(E) && al16(S) && al16(dE) && al16(g_table) && shard_aligned;
         if (D % 4 == 0 && D <= 128 && (D & (D - 1)) == 0 && aligned) {
             const bool staged = al16(rows);
+            // fold the numeric-slot / bias reductions into this launch (dE is then read exactly once)
+            if (RBX_BWD_FUSE_NUM && (want_w || want_lr) && (Fn == 0 || dense_x) && Fn * D <= 4096 && al16(dense_w) &&
+                al16(g_dense_w)) {
+                p.num_smem = (int)((((size_t)Fn * D + Fn + 1) * 4 + 15) & ~(size_t)15);
+                num_fused = true;
+            }
             int rc = 0;
             switch (D / 4) {
                 case 1: rc = launch_bwd<1, RBX_BWD_U>(p, staged, sharded, st); break;
@@ -937,9 +1033,7 @@ int embed_fm_bwd_impl(const char* who, const float* table, const ShardArgs& sh, 
         }
         RBX_LAUNCH_CHECK(who);
     }
-    const bool want_w = Fn > 0 && g_dense_w && (dE || d_fm);
-    const bool want_lr = d_lr && ((Fn > 0 && g_dense_w_lr) || g_lr_bias);
-    if (want_w || want_lr) {
+    if ((want_w || want_lr) && !num_fused) {
         int first_scalar_role = 0;        // roles still to be covered by the scalar kernel
         bool scalar_needed = true;
         const int R4 = Fn * (D / 4);

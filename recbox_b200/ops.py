@@ -338,3 +338,61 @@ def clip_coef(acc, max_norm, coef, norm_out=None):
 def adam_dense_(w, g, m, v, step, lr=1e-3, beta1=0.9, beta2=0.999, eps=1e-8, clip=None):
     _call("rbx_adam_dense", _p(w, F32, "w"), _p(g, F32, "g"), _p(m, F32, "m"), _p(v, F32, "v"), w.numel(),
           _p(clip, F32, "clip"), float(lr), float(beta1), float(beta2), float(eps), int(step), _stream())
+
+
+# ------------------------------------------------------------------------------------------- f1
+OPTIM_KINDS = {"sgd": 0, "adagrad": 1, "adam_rows": 2, "sparse_adam": 3}
+
+
+def sqnorm_rows_(g, rows, n_rows, acc):
+    """acc (float64 [1]) += sum over the touched `rows` (int32, first n_rows[0] valid) of |g[row,:]|^2."""
+    D = 1 if g.dim() == 1 else g.shape[1]
+    _call("rbx_sqnorm_rows", _p(g, F32, "g"), _p(rows, I32, "rows"), _p(n_rows, torch.int64, "n_rows"), rows.numel(), D,
+          _p(acc, torch.float64, "acc"), _stream())
+
+
+def optim_rows_(w, g, m, v, rows, n_rows, step, kind="adam_rows", lr=1e-3, beta1=0.9, beta2=0.999, eps=1e-8, clip=None,
+                zero_grad=True):
+    """Touched-rows optimizer update of table w [R,D] (or [R]) in place; see rbx_optim_rows for `kind`."""
+    if kind not in OPTIM_KINDS:
+        raise RbxError("optim_rows_: kind must be one of %s" % sorted(OPTIM_KINDS))
+    D = 1 if w.dim() == 1 else w.shape[1]
+    _call("rbx_optim_rows", _p(w, F32, "w"), _p(g, F32, "g"), _p(m, F32, "m"), _p(v, F32, "v"), _p(rows, I32, "rows"),
+          _p(n_rows, torch.int64, "n_rows"), rows.numel(), D, _p(clip, F32, "clip"), OPTIM_KINDS[kind], float(lr),
+          float(beta1), float(beta2), float(eps), int(step), int(bool(zero_grad)), _stream())
+
+
+# ------------------------------------------------------------------------------------------ a14
+_unique_ws = {}
+
+
+def unique_ids(ids, vocab, want_first=True, want_inverse=True, sync=True):
+    """Sorted unique ids, first flat position of each, inverse map -- ids int64 or int32 CUDA tensor of
+    any shape, every id in [0, vocab).  sync=True trims the outputs to the U uniques found (one 16-byte
+    D2H read, as torch.unique does); sync=False returns full-capacity buffers plus the device counter
+    n_out (int64 [2]: U, #out-of-range) for consumers that read the count on the device."""
+    if not ids.is_cuda:
+        raise RbxError("ids must be a CUDA tensor (recbox_b200 has no CPU path)")
+    if ids.dtype not in (torch.int64, torch.int32):
+        raise RbxError("ids must be int64 or int32, got %s" % ids.dtype)
+    flat = ids.contiguous().view(-1)
+    n, vocab = flat.numel(), int(vocab)
+    lib = _lib.load()
+    need = int(lib.rbx_unique_ws_bytes(vocab))
+    key = (flat.device, vocab)
+    ws = _unique_ws.get(key)
+    if ws is None or ws.numel() * 8 < need:
+        ws = _unique_ws[key] = torch.empty((need + 7) // 8, dtype=torch.int64, device=flat.device)
+    cap = max(min(n, vocab), 1)
+    uniq = torch.empty(cap, dtype=flat.dtype, device=flat.device)
+    first = torch.empty(cap, dtype=torch.int64, device=flat.device) if want_first else None
+    inverse = torch.empty(max(n, 1), dtype=flat.dtype, device=flat.device)[:n] if want_inverse else None
+    n_out = torch.empty(2, dtype=torch.int64, device=flat.device)
+    name = "rbx_unique_ids_i64" if flat.dtype == torch.int64 else "rbx_unique_ids_i32"
+    _call(name, _p(flat), n, vocab, _p(ws), ws.numel() * 8, _p(uniq), _p(first), _p(inverse), _p(n_out), _stream())
+    if not sync:
+        return uniq, first, inverse, n_out
+    U, bad = (int(x) for x in n_out.tolist())
+    if bad:
+        raise RbxError("unique_ids: %d id(s) outside [0, %d)" % (bad, vocab))
+    return uniq[:U], (first[:U] if want_first else None), inverse

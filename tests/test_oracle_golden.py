@@ -252,3 +252,47 @@ def test_clip_and_adam_match_torch():
         opt.step()
         oracle.adam_step(q, grad * coef, m, v, step)
         assert_close(q, p, rtol=1e-6, atol_scale=1e-7, what="adam")
+
+
+def test_collate_unique_matches_reference_golden():
+    """a14: collate_unique.npz holds what the reference's own collate_fn_unique returned
+    (oracle/make_golden.py::golden_collate_unique)."""
+    z = np.load(os.path.join(GOLD, "collate_unique.npz"))
+    for k in range(int(z["n_cases"])):
+        item = z["item_indexes_%d" % k]
+        uniq, uidx, inv = oracle.collate_unique_reference(item)
+        assert np.array_equal(uniq.numpy(), z["unique_%d" % k])
+        assert np.array_equal(uidx.numpy(), z["unique_indexes_%d" % k])
+        assert np.array_equal(inv.numpy(), z["inverse_indexes_%d" % k])
+        u2, f2, i2 = oracle.unique_items(item)            # the numpy form the GPU tests compare with
+        assert np.array_equal(u2, z["unique_%d" % k]) and np.array_equal(f2, z["unique_indexes_%d" % k])
+        assert np.array_equal(i2[::-1], z["inverse_indexes_%d" % k]), "the reference returns the flipped inverse"
+
+
+@pytest.mark.parametrize("kind", ["sgd", "adagrad"])
+def test_touched_rows_exact_kinds_equal_dense_torch_optimizers(kind):
+    """f1: for SGD / Adagrad a touched-rows update IS the dense torch optimizer step (zero-gradient rows do not move)."""
+    g = torch.Generator().manual_seed(1)
+    w = torch.randn(30, 4, generator=g)
+    grad = torch.zeros(30, 4)
+    grad[[2, 9, 17]] = torch.randn(3, 4, generator=g)
+    p = torch.nn.Parameter(w.clone())
+    opt = (torch.optim.SGD if kind == "sgd" else torch.optim.Adagrad)([p], lr=0.05)
+    state = {"m": torch.zeros(30, 4), "v": torch.zeros(30, 4)}
+    q = w
+    for step in range(1, 4):
+        p.grad = grad.clone() * step
+        opt.step()
+        q = oracle.touched_rows_step(kind, q, grad * step, state, step, lr=0.05, eps=1e-10)
+        assert_close(q, p.detach(), rtol=1e-6, atol_scale=1e-7, what=kind)
+
+
+def test_touched_rows_adam_is_lazy_not_dense():
+    """f1: "adam_rows" leaves untouched rows alone -- documented difference from the reference's dense Adam."""
+    w = torch.ones(6, 2)
+    grad = torch.zeros(6, 2)
+    grad[1] = 0.5
+    state = {"m": torch.full((6, 2), 0.1), "v": torch.full((6, 2), 0.01)}
+    q = oracle.touched_rows_step("adam_rows", w, grad, state, 2)
+    assert torch.equal(q[0], w[0]) and not torch.equal(q[1], w[1])
+    assert float(state["m"][0, 0]) == pytest.approx(0.1)     # dense Adam would have decayed it to 0.09

@@ -17,6 +17,8 @@ VARIANTS = {
     "l2_both_minb4": ["RBX_L2_HINTS=3", "RBX_FWD_MINB=4"],
     "h3": ["RBX_L2_HINTS=3"], "h6": ["RBX_L2_HINTS=6"], "h7": ["RBX_L2_HINTS=7"], "h2": ["RBX_L2_HINTS=2"],
     "noagg": ["RBX_BWD_WARP_AGG=0"],
+    "nofuse": ["RBX_BWD_FUSE_NUM=0"],
+    "fuse_noagg": ["RBX_BWD_WARP_AGG=0"],
     "rev": ["RBX_BWD_REVERSE=1"],
     "rev_l2both": ["RBX_BWD_REVERSE=1", "RBX_L2_HINTS=3"],
     "fwd_u13_b2": ["RBX_FWD_U=13", "RBX_FWD_MINB=2"],
