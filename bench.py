@@ -386,7 +386,8 @@ def main_sharded(args, rank, world, local_rank):
         dist.init_process_group("nccl", device_id=dev)
     B, F, Fn, D, V = CFG["B"], CFG["F"], CFG["Fn"], args.dim, args.rows_per_field
     Ft, R = F + Fn, F * V
-    sh = sharded.ShardedEmbeddingFM(R, D, mode=args.shard_mode, device=dev, max_ids=B * F, alloc=args.peer_alloc, with_lr=not args.no_lr)
+    sh = sharded.ShardedEmbeddingFM(R, D, mode=args.shard_mode, device=dev, max_ids=B * F, alloc=args.peer_alloc, with_lr=not args.no_lr,
+                                    layout=args.shard_layout)
     gen = torch.Generator(device=dev).manual_seed(20240 + 4 + rank)
     sh.table.normal_(0, 0.01, generator=gen)
     sh.table_lr.normal_(0, 0.01, generator=gen)
@@ -460,7 +461,8 @@ def main_sharded(args, rank, world, local_rank):
             "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": "BASELINE configs[3]: DeepFM hot path, %d-row fused table (26 x %d) row-sharded over %d GPU(s), "
-                                   "D=%d, B=65536 per GPU; mode=%s" % (R, V, world, D, args.shard_mode),
+                                   "D=%d, B=65536 per GPU; mode=%s%s" % (R, V, world, D, args.shard_mode,
+                                                                            ", layout=rowlr" if args.shard_layout == "rowlr" else ""),
                        "global_batch": B * world, "ids": args.ids, "batches_rotated": NB,
                        "l2": "table shard (%.1f GB) and E/dE streams exceed the 126 MB L2" % (sh.cap * D * 4 / 1e9),
                        "parallelism": "dp%d batch shards + row-sharded table (r %% %d), exchange inside the fused kernels over NVLink" % (world, world)
@@ -497,6 +499,8 @@ def main():
                          "sharded: configs[3], 100M-row table row-sharded over the ranks")
     ap.add_argument("--shard-mode", default="peer", choices=["push", "peer", "a2a"])
     ap.add_argument("--peer-alloc", default="symm", choices=["ipc", "symm"])
+    ap.add_argument("--shard-layout", default="split", choices=["split", "rowlr"],
+                    help="rowlr: embedding row + first-order weight in one physical row (one NVLink request per slot)")
     ap.add_argument("--no-lr", action="store_true", help="sharded workload without the first-order (LR) table")
     ap.add_argument("--dim", type=int, default=16)
     ap.add_argument("--rows-per-field", type=int, default=3846154)

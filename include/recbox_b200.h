@@ -277,6 +277,25 @@ int rbx_embed_fm_bwd_sharded(const float* const* shard_tables /*HOST [world] | N
                              float* g_dense_w, float* g_dense_w_lr, float* g_lr_bias,
                              int64_t B, int64_t R, int F, int Fn, int D, int n_slots, rbx_stream_t stream);
 
+/* ROW+LR shard layout: every shard is [cap, 2 D] floats, physical row = [e_0 .. e_{D-1} | w_lr | 0 ...], and the
+ * gradient shards mirror it, so an embedding row and its first-order weight (resp. their gradients) cross NVLink
+ * in ONE request instead of two -- remote traffic of 64-byte rows is bound by request count.
+ * D in {4, 8, 16}.  Same outputs as rbx_embed_fm_fwd/bwd_sharded. */
+int rbx_embed_fm_fwd_sharded_rowlr(const float* const* shard_tables /*HOST [world] of DEVICE [cap,2D]*/, int world,
+                                   const int32_t* rows, const int32_t* cat_pos /*HOST*/,
+                                   const float* dense_x, const float* dense_w, const float* dense_w_lr,
+                                   const int32_t* num_pos /*HOST*/, const int32_t* num_widx /*HOST | NULL*/,
+                                   const float* lr_bias, float* E, float* S, float* fm_out, float* lr_out,
+                                   int64_t B, int64_t R, int F, int Fn, int D, int n_slots, rbx_stream_t stream);
+int rbx_embed_fm_bwd_sharded_rowlr(const float* const* shard_tables /*| NULL when E is given*/,
+                                   float* const* shard_g_tables /*HOST [world] of DEVICE [cap,2D]*/, int world,
+                                   const int32_t* rows, const int32_t* cat_pos, const int32_t* pad_row,
+                                   const float* dense_x, const float* dense_w, const int32_t* num_pos,
+                                   const int32_t* num_widx, const float* E, const float* S, const float* dE,
+                                   const float* d_fm, const float* d_lr,
+                                   float* g_dense_w, float* g_dense_w_lr, float* g_lr_bias,
+                                   int64_t B, int64_t R, int F, int Fn, int D, int n_slots, rbx_stream_t stream);
+
 /* Push-based exchange (the path used for tables too large for remote gathers, see
  * csrc/shard_push.cu): only dense, contiguous buffers cross NVLink; every random access is local
  * to the row's owner.  All `*const*` arguments are HOST arrays of `world` DEVICE pointers valid on

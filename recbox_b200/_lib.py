@@ -97,6 +97,8 @@ SIGNATURES = {
     "rbx_shard_unroute": [_P, _P, _P, _I64, _I, _P],
     "rbx_embed_fm_fwd_sharded": [_P, _P, _I] + [_P] * 12 + [_I64, _I64, _I, _I, _I, _I, _P],
     "rbx_embed_fm_bwd_sharded": [_P, _P, _P, _I] + [_P] * 15 + [_I64, _I64, _I, _I, _I, _I, _P],
+    "rbx_embed_fm_fwd_sharded_rowlr": [_P, _I] + [_P] * 12 + [_I64, _I64, _I, _I, _I, _I, _P],
+    "rbx_embed_fm_bwd_sharded_rowlr": [_P, _P, _I] + [_P] * 15 + [_I64, _I64, _I, _I, _I, _I, _P],
     "rbx_shard_push_ids": [_P, _P, _P, _P, _I, _I, _I64, _I64, _P],
     "rbx_shard_serve_rows": [_P, _P, _I, _P, _P, _P, _P, _I, _I64, _P],
     "rbx_shard_push_grads": [_P, _P, _P, _P, _P, _I, _I, _I64, _I, _I64, _P],

@@ -190,37 +190,45 @@ __device__ __forceinline__ void stage_words(void* dst, const void* base, int64_t
 // ---------------------------------------------------------------------------------------------
 // row addressing: one local fused table, or 2^wlog2 shards reached through NVLink peer mappings
 // ---------------------------------------------------------------------------------------------
-template <bool kSharded, int D, typename P>
+// kSharded: 0 = one local table; 1 = row shards, first-order weights in their own shard vectors;
+// 2 = row shards in the ROW+LR layout: a physical row is RS = 2 D floats, [e_0 .. e_{D-1} | w_lr | 0 ...],
+// so the embedding row and its first-order weight travel in ONE NVLink request (remote
+// traffic of 64-byte rows is bound by request count, not bytes)
+template <int kSharded, int RS, typename P>
 __device__ __forceinline__ const float* row_src(const P& p, int32_t r) {
-    if constexpr (!kSharded) return p.table + (size_t)r * D;
-    else return p.shard[r & ((1 << p.wlog2) - 1)] + (size_t)(r >> p.wlog2) * D;
+    if constexpr (kSharded == 0) return p.table + (size_t)r * RS;
+    else return p.shard[r & ((1 << p.wlog2) - 1)] + (size_t)(r >> p.wlog2) * RS;
 }
-template <bool kSharded>
+template <int kSharded>
 __device__ __forceinline__ const float* lr_src(const FwdParams& p, int32_t r, int f) {
-    if constexpr (!kSharded) return p.table_lr + (r + p.meta.lr_delta[f]);
+    if constexpr (kSharded == 0) return p.table_lr + (r + p.meta.lr_delta[f]);
     else return p.shard_lr[r & ((1 << p.wlog2) - 1)] + (r >> p.wlog2);
 }
-template <bool kSharded, int D>
+template <int kSharded, int RS>
 __device__ __forceinline__ float* grad_dst(const BwdParams& p, int32_t r) {
-    if constexpr (!kSharded) return p.g_table + (size_t)r * D;
-    else return p.g_shard[r & ((1 << p.wlog2) - 1)] + (size_t)(r >> p.wlog2) * D;
+    if constexpr (kSharded == 0) return p.g_table + (size_t)r * RS;
+    else return p.g_shard[r & ((1 << p.wlog2) - 1)] + (size_t)(r >> p.wlog2) * RS;
 }
-template <bool kSharded>
+template <int kSharded>
 __device__ __forceinline__ float* grad_lr_dst(const BwdParams& p, int32_t r, int f) {
-    if constexpr (!kSharded) return p.g_table_lr + (r + p.meta.lr_delta[f]);
+    if constexpr (kSharded == 0) return p.g_table_lr + (r + p.meta.lr_delta[f]);
     else return p.g_shard_lr[r & ((1 << p.wlog2) - 1)] + (r >> p.wlog2);
 }
 
 // ---------------------------------------------------------------------------------------------
 // forward, vector path
 // ---------------------------------------------------------------------------------------------
-template <int LPR, int U, bool kStaged, bool kSharded>
+template <int LPR, int U, bool kStaged, int kSharded>
 __global__ void __launch_bounds__(kThreads, RBX_FWD_MINB) k_embed_fm_fwd(const __grid_constant__ FwdParams p) {
-    constexpr int D = 4 * LPR;
+    constexpr bool kRowLr = kSharded == 2;        // LPR lanes span a physical row of RS floats; the first LPE carry e
+    constexpr int RS = 4 * LPR;
+    constexpr int D = kRowLr ? RS / 2 : RS;
+    constexpr int LPE = D / 4;
     constexpr int SPW = 32 / LPR;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int lig = lane & (LPR - 1), gi = lane / LPR;
+    const bool elane = !kRowLr || lig < LPE;       // this lane owns 4 embedding columns
     const int F = p.F, Fn = p.Fn, Ft = p.Ft;
     const float bias = p.lr_bias ? __ldg(p.lr_bias) : 0.f;
     const uint64_t pol_keep = l2_policy_evict_last(), pol_stream = l2_policy_evict_first();
@@ -264,12 +272,12 @@ __global__ void __launch_bounds__(kThreads, RBX_FWD_MINB) k_embed_fm_fwd(const _
         const bool valid = b < p.B;
         const int32_t* rb = kStaged ? my_idx + (size_t)buf * wi + ((b0 * F) & 3) + gi * F : p.rows + b * F;
         const float* xb = kStaged ? my_dx + (size_t)buf * wx + ((b0 * Fn) & 3) + gi * Fn : p.dense_x + b * Fn;
-        float* Eb = p.E ? p.E + (size_t)b * Ft * D + 4 * lig : nullptr;
+        float* Eb = (p.E && elane) ? p.E + (size_t)b * Ft * D + 4 * lig : nullptr;
         float4 S = make_float4(0.f, 0.f, 0.f, 0.f), Q = S;
 
         // first-order gathers first: they are independent of everything below and overlap it
         float lr = 0.f;
-        if (p.lr_out && valid) {
+        if (!kRowLr && p.lr_out && valid) {
 #pragma unroll 4
             for (int f = lig; f < F; f += LPR) {
                 const int32_t r = kStaged ? rb[f] : __ldg(rb + f);
@@ -287,20 +295,25 @@ __global__ void __launch_bounds__(kThreads, RBX_FWD_MINB) k_embed_fm_fwd(const _
 #pragma unroll
             for (int u = 0; u < U; ++u) {
                 v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if ((uint32_t)r[u] < (uint64_t)p.R) v[u] = LD_ROW((row_src<kSharded, D>(p, r[u]) + 4 * lig));
+                if ((uint32_t)r[u] < (uint64_t)p.R && (!kRowLr || lig <= LPE))
+                    v[u] = LD_ROW((row_src<kSharded, RS>(p, r[u]) + 4 * lig));
             }
 #pragma unroll
             for (int u = 0; u < U; ++u) {
                 if (valid && f0 + u < F) {
-                    S = f4_add(S, v[u]);
-                    Q = f4_sqacc(v[u], Q);
-                    if (Eb) ST_STREAM(Eb + (size_t)p.meta.cat_pos[f0 + u] * D, v[u]);
+                    if (elane) {
+                        S = f4_add(S, v[u]);
+                        Q = f4_sqacc(v[u], Q);
+                        if (Eb) ST_STREAM(Eb + (size_t)p.meta.cat_pos[f0 + u] * D, v[u]);
+                    } else if (lig == LPE) {
+                        lr += v[u].x;             // the first-order weight rode along in column D of the row
+                    }
                 }
             }
         }
         // numeric slots: e = x * w  (nn.Linear(1, D, bias=False) on x.view(-1,1))
         for (int n = 0; p.dense_w && n < Fn; ++n) {
-            if (valid) {
+            if (valid && elane) {
                 const float x = kStaged ? xb[n] : __ldg(xb + n);
                 const float4 e = f4_scale(ld_row_f4(p.dense_w + (size_t)p.meta.num_widx[n] * D + 4 * lig), x);
                 S = f4_add(S, e);
@@ -308,7 +321,7 @@ __global__ void __launch_bounds__(kThreads, RBX_FWD_MINB) k_embed_fm_fwd(const _
                 if (Eb) ST_STREAM(Eb + (size_t)p.meta.num_pos[n] * D, e);
             }
         }
-        if (p.S && valid) *reinterpret_cast<float4*>(p.S + (size_t)b * D + 4 * lig) = S;
+        if (p.S && valid && elane) *reinterpret_cast<float4*>(p.S + (size_t)b * D + 4 * lig) = S;
 
         if (p.fm_out) {
             // inner_product.py:42-48: (sum^2 - sum of squares) * 0.5 per d, then sum over d
@@ -403,13 +416,17 @@ __global__ void __launch_bounds__(kThreads) k_embed_fm_fwd_scalar(const __grid_c
 // The upstream-gradient and saved-activation loads do not depend on the ids (only the reduction
 // address does), so they are issued for the whole chunk before anything is consumed.
 // ---------------------------------------------------------------------------------------------
-template <int LPR, int U, bool kStaged, bool kSharded>
+template <int LPR, int U, bool kStaged, int kSharded>
 __global__ void __launch_bounds__(kThreads, RBX_BWD_MINB) k_embed_fm_bwd(const __grid_constant__ BwdParams p) {
-    constexpr int D = 4 * LPR;
+    constexpr bool kRowLr = kSharded == 2;
+    constexpr int RS = 4 * LPR;
+    constexpr int D = kRowLr ? RS / 2 : RS;
+    constexpr int LPE = D / 4;
     constexpr int SPW = 32 / LPR;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int lig = lane & (LPR - 1), gi = lane / LPR;
+    const bool elane = !kRowLr || lig < LPE;
     const int F = p.F, Ft = p.Ft;
     const bool has_fm = p.d_fm != nullptr;
     constexpr bool kAgg = RBX_BWD_WARP_AGG && SPW > 1;
@@ -465,11 +482,13 @@ __global__ void __launch_bounds__(kThreads, RBX_BWD_MINB) k_embed_fm_bwd(const _
         const size_t eoff = (size_t)b * Ft * D + 4 * lig;
         float4 S = make_float4(0.f, 0.f, 0.f, 0.f);
         float dfm = 0.f;
-        if (valid && has_fm) {
+        if (valid && has_fm && elane) {
             S = ld_stream_f4(p.S + (size_t)b * D + 4 * lig);
             dfm = __ldg(p.d_fm + b);
         }
-        if ((kSharded ? p.g_shard_lr[0] != nullptr : p.g_table_lr != nullptr) && p.d_lr) {
+        float dlr_row = 0.f;                          // ROW+LR layout: the first-order gradient rides in column D
+        if (kRowLr && p.d_lr && valid && lig == LPE) dlr_row = __ldg(p.d_lr + b);
+        if (!kRowLr && (kSharded ? p.g_shard_lr[0] != nullptr : p.g_table_lr != nullptr) && p.d_lr) {
             const float dlr = valid ? __ldg(p.d_lr + b) : 0.f;
 #pragma unroll 2
             for (int f0 = 0; f0 < F; f0 += LPR) {            // uniform trip count: the warp votes inside
@@ -512,8 +531,9 @@ __global__ void __launch_bounds__(kThreads, RBX_BWD_MINB) k_embed_fm_bwd(const _
                     e[u] = gr[u] = make_float4(0.f, 0.f, 0.f, 0.f);
                     if (valid && f0 + u < F) {
                         const size_t o = eoff + (size_t)p.meta.cat_pos[f0 + u] * D;
-                        if (p.dE) gr[u] = LD_STREAM(p.dE + o);
-                        if (has_fm && p.E) e[u] = LD_STREAM(p.E + o);
+                        if (p.dE && elane) gr[u] = LD_STREAM(p.dE + o);
+                        if (has_fm && p.E && elane) e[u] = LD_STREAM(p.E + o);
+                        if (kRowLr && lig == LPE) gr[u].x = dlr_row;
                         const int32_t tr = kStaged ? rb[f0 + u] : __ldg(rb + f0 + u);
                         if (tr != p.pad_row[f0 + u] && (uint32_t)tr < (uint64_t)p.R) r[u] = tr;
                     }
@@ -521,11 +541,11 @@ __global__ void __launch_bounds__(kThreads, RBX_BWD_MINB) k_embed_fm_bwd(const _
                 if (from_table) {
 #pragma unroll
                     for (int u = 0; u < U; ++u)
-                        if (r[u] >= 0) e[u] = LD_ROW((row_src<kSharded, D>(p, r[u]) + 4 * lig));
+                        if (r[u] >= 0 && elane) e[u] = LD_ROW((row_src<kSharded, RS>(p, r[u]) + 4 * lig));
                 }
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
-                    if (r[u] >= 0 && has_fm) gr[u] = f4_fma(f4_sub(S, e[u]), dfm, gr[u]);
+                    if (r[u] >= 0 && has_fm && elane) gr[u] = f4_fma(f4_sub(S, e[u]), dfm, gr[u]);
                     bool leader = true;
                     if (kAgg) {
                         // warp-aggregated atomics: the SPW samples of this warp that hit the same row in this slot
@@ -546,7 +566,7 @@ __global__ void __launch_bounds__(kThreads, RBX_BWD_MINB) k_embed_fm_bwd(const _
                             leader = (__ffs(peers) - 1) / LPR == gi;
                         }
                     }
-                    if (r[u] >= 0 && leader) RED_GRAD((grad_dst<kSharded, D>(p, r[u]) + 4 * lig), gr[u]);
+                    if (r[u] >= 0 && leader && (!kRowLr || lig <= LPE)) RED_GRAD((grad_dst<kSharded, RS>(p, r[u]) + 4 * lig), gr[u]);
                 }
             }
         }
@@ -563,7 +583,7 @@ __global__ void __launch_bounds__(kThreads, RBX_BWD_MINB) k_embed_fm_bwd(const _
                     for (int u = 0; u < U; ++u) {
                         x[u] = 0.f;
                         g[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (valid && n0 + u < Fn) {
+                        if (valid && elane && n0 + u < Fn) {
                             x[u] = __ldg(xb + n0 + u);
                             if (p.dE) g[u] = LD_STREAM(p.dE + eoff + (size_t)p.meta.num_pos[n0 + u] * D);
                         }
@@ -572,7 +592,7 @@ __global__ void __launch_bounds__(kThreads, RBX_BWD_MINB) k_embed_fm_bwd(const _
                     for (int u = 0; u < U; ++u) {
                         if (n0 + u < Fn) {
                             const int n = n0 + u;
-                            if (has_fm) {
+                            if (has_fm && elane) {
                                 const float4 w = ld_row_f4(p.dense_w + (size_t)p.meta.num_widx[n] * D + 4 * lig);
                                 g[u] = f4_fma(f4_sub(S, f4_scale(w, x[u])), dfm, g[u]);
                             }
@@ -584,7 +604,7 @@ __global__ void __launch_bounds__(kThreads, RBX_BWD_MINB) k_embed_fm_bwd(const _
                                 c.z += __shfl_xor_sync(0xffffffffu, c.z, o);
                                 c.w += __shfl_xor_sync(0xffffffffu, c.w, o);
                             }
-                            if (gi == 0) {
+                            if (gi == 0 && elane) {
                                 float* a = s_gw + n * D + 4 * lig;
                                 atomicAdd(a, c.x);
                                 atomicAdd(a + 1, c.y);
@@ -614,8 +634,8 @@ __global__ void __launch_bounds__(kThreads, RBX_BWD_MINB) k_embed_fm_bwd(const _
         __syncthreads();
         const int Fn = p.Fn;
         if (p.g_dense_w)
-            for (int i = threadIdx.x; i < Fn * LPR; i += kThreads) {
-                const int n = i / LPR, c = i - n * LPR;
+            for (int i = threadIdx.x; i < Fn * LPE; i += kThreads) {
+                const int n = i / LPE, c = i - n * LPE;
                 red_add_f4(p.g_dense_w + (size_t)p.meta.num_widx[n] * D + 4 * c, *reinterpret_cast<const float4*>(s_gw + n * D + 4 * c));
             }
         if (p.d_lr)
@@ -815,26 +835,37 @@ int set_smem_limit(K kernel, size_t smem) {
     return 0;
 }
 
+// sharded: 0 local table, 1 row shards, 2 row shards in the ROW+LR layout (LPR lanes span the 2 D-float physical row)
 template <int LPR, int U>
-int launch_fwd(FwdParams& p, bool staged, bool sharded, cudaStream_t st) {
+int launch_fwd(FwdParams& p, bool staged, int sharded, cudaStream_t st) {
     constexpr int SPW = 32 / LPR;
     const int64_t groups = (p.B + SPW - 1) / SPW;
     const size_t smem = staged_smem(SPW, p.F, p.Fn);
+    if (sharded == 2) {
+        if constexpr (LPR >= 2 && LPR <= 8) {
+            if (!staged || smem > 200 * 1024 || set_smem_limit(k_embed_fm_fwd<LPR, U, true, 2>, smem) != 0) return -1;
+            const int grid = grid_for((const void*)k_embed_fm_fwd<LPR, U, true, 2>, smem, groups);
+            k_embed_fm_fwd<LPR, U, true, 2><<<grid, kThreads, smem, st>>>(p);
+            return 0;
+        } else {
+            return -1;
+        }
+    }
     if (sharded) {   // the peer-memory variant exists in its staged form only
-        if (!staged || smem > 200 * 1024 || set_smem_limit(k_embed_fm_fwd<LPR, U, true, true>, smem) != 0) return -1;
-        const int grid = grid_for((const void*)k_embed_fm_fwd<LPR, U, true, true>, smem, groups);
-        k_embed_fm_fwd<LPR, U, true, true><<<grid, kThreads, smem, st>>>(p);
+        if (!staged || smem > 200 * 1024 || set_smem_limit(k_embed_fm_fwd<LPR, U, true, 1>, smem) != 0) return -1;
+        const int grid = grid_for((const void*)k_embed_fm_fwd<LPR, U, true, 1>, smem, groups);
+        k_embed_fm_fwd<LPR, U, true, 1><<<grid, kThreads, smem, st>>>(p);
         return 0;
     }
     if (staged) {
-        if (smem <= 200 * 1024 && set_smem_limit(k_embed_fm_fwd<LPR, U, true, false>, smem) == 0) {
-            const int grid = grid_for((const void*)k_embed_fm_fwd<LPR, U, true, false>, smem, groups);
-            k_embed_fm_fwd<LPR, U, true, false><<<grid, kThreads, smem, st>>>(p);
+        if (smem <= 200 * 1024 && set_smem_limit(k_embed_fm_fwd<LPR, U, true, 0>, smem) == 0) {
+            const int grid = grid_for((const void*)k_embed_fm_fwd<LPR, U, true, 0>, smem, groups);
+            k_embed_fm_fwd<LPR, U, true, 0><<<grid, kThreads, smem, st>>>(p);
             return 0;
         }
     }
-    const int grid = grid_for((const void*)k_embed_fm_fwd<LPR, U, false, false>, 0, groups);
-    k_embed_fm_fwd<LPR, U, false, false><<<grid, kThreads, 0, st>>>(p);
+    const int grid = grid_for((const void*)k_embed_fm_fwd<LPR, U, false, 0>, 0, groups);
+    k_embed_fm_fwd<LPR, U, false, 0><<<grid, kThreads, 0, st>>>(p);
     return 0;
 }
 
@@ -845,25 +876,35 @@ void launch_fwd_scalar(const FwdParams& p, cudaStream_t st) {
 }
 
 template <int LPR, int U>
-int launch_bwd(BwdParams& p, bool staged, bool sharded, cudaStream_t st) {
+int launch_bwd(BwdParams& p, bool staged, int sharded, cudaStream_t st) {
     constexpr int SPW = 32 / LPR;
     const int64_t groups = (p.B + SPW - 1) / SPW;
     const size_t smem = staged_smem(SPW, p.F, 0) + p.num_smem;
+    if (sharded == 2) {
+        if constexpr (LPR >= 2 && LPR <= 8) {
+            if (!staged || smem > 200 * 1024 || set_smem_limit(k_embed_fm_bwd<LPR, U, true, 2>, smem) != 0) return -1;
+            const int grid = grid_for((const void*)k_embed_fm_bwd<LPR, U, true, 2>, smem, groups);
+            k_embed_fm_bwd<LPR, U, true, 2><<<grid, kThreads, smem, st>>>(p);
+            return 0;
+        } else {
+            return -1;
+        }
+    }
     if (sharded) {
-        if (!staged || smem > 200 * 1024 || set_smem_limit(k_embed_fm_bwd<LPR, U, true, true>, smem) != 0) return -1;
-        const int grid = grid_for((const void*)k_embed_fm_bwd<LPR, U, true, true>, smem, groups);
-        k_embed_fm_bwd<LPR, U, true, true><<<grid, kThreads, smem, st>>>(p);
+        if (!staged || smem > 200 * 1024 || set_smem_limit(k_embed_fm_bwd<LPR, U, true, 1>, smem) != 0) return -1;
+        const int grid = grid_for((const void*)k_embed_fm_bwd<LPR, U, true, 1>, smem, groups);
+        k_embed_fm_bwd<LPR, U, true, 1><<<grid, kThreads, smem, st>>>(p);
         return 0;
     }
     if (staged) {
-        if (smem <= 200 * 1024 && set_smem_limit(k_embed_fm_bwd<LPR, U, true, false>, smem) == 0) {
-            const int grid = grid_for((const void*)k_embed_fm_bwd<LPR, U, true, false>, smem, groups);
-            k_embed_fm_bwd<LPR, U, true, false><<<grid, kThreads, smem, st>>>(p);
+        if (smem <= 200 * 1024 && set_smem_limit(k_embed_fm_bwd<LPR, U, true, 0>, smem) == 0) {
+            const int grid = grid_for((const void*)k_embed_fm_bwd<LPR, U, true, 0>, smem, groups);
+            k_embed_fm_bwd<LPR, U, true, 0><<<grid, kThreads, smem, st>>>(p);
             return 0;
         }
     }
-    const int grid = grid_for((const void*)k_embed_fm_bwd<LPR, U, false, false>, p.num_smem, groups);
-    k_embed_fm_bwd<LPR, U, false, false><<<grid, kThreads, p.num_smem, st>>>(p);
+    const int grid = grid_for((const void*)k_embed_fm_bwd<LPR, U, false, 0>, p.num_smem, groups);
+    k_embed_fm_bwd<LPR, U, false, 0><<<grid, kThreads, p.num_smem, st>>>(p);
     return 0;
 }
 
@@ -878,6 +919,7 @@ struct ShardArgs {                    // world == 0: single local table
     const float* const* tables_lr = nullptr;
     float* const* g_tables = nullptr;
     float* const* g_tables_lr = nullptr;
+    bool row_lr = false;              // ROW+LR layout: shard rows are 2 D floats, first-order weight at column D
 };
 
 int shard_log2(int world, const char* who) {
@@ -904,8 +946,9 @@ int embed_fm_fwd_impl(const char* who, const float* table, const float* table_lr
     const bool lr_only = !E && !S && !fm_out;   // LogisticRegression alone: no D-dim tables needed
     RBX_REQUIRE(F == 0 || (rows && cat_pos && (table || sharded || lr_only)), "%s: table/rows/cat_pos required when F > 0", who);
     RBX_REQUIRE(Fn == 0 || (dense_x && num_pos && (dense_w || lr_only)), "%s: dense_x/dense_w/num_pos required when Fn > 0", who);
-    RBX_REQUIRE(!lr_out || ((F == 0 || table_lr || (sharded && sh.tables_lr)) && (Fn == 0 || dense_w_lr)),
+    RBX_REQUIRE(!lr_out || ((F == 0 || table_lr || (sharded && (sh.tables_lr || sh.row_lr))) && (Fn == 0 || dense_w_lr)),
                 "%s: lr_out needs table_lr / dense_w_lr", who);
+    RBX_REQUIRE(!sh.row_lr || D == 4 || D == 8 || D == 16, "%s: the ROW+LR layout covers D in {4, 8, 16} (D=%d)", who, D);
     if (lr_only && !sharded) { table = nullptr; dense_w = nullptr; D = 16; }
     FwdParams p;
     p.table = table; p.table_lr = table_lr; p.rows = rows; p.dense_x = dense_x; p.dense_w = dense_w;
@@ -920,7 +963,7 @@ int embed_fm_fwd_impl(const char* who, const float* table, const float* table_lr
             RBX_REQUIRE(sh.tables && sh.tables[w], "%s: shard table %d is null", who, w);
             p.shard[w] = sh.tables[w];
             p.shard_lr[w] = sh.tables_lr ? sh.tables_lr[w] : nullptr;
-            RBX_REQUIRE(!lr_out || F == 0 || p.shard_lr[w], "%s: shard lr table %d is null", who, w);
+            RBX_REQUIRE(!lr_out || F == 0 || sh.row_lr || p.shard_lr[w], "%s: shard lr table %d is null", who, w);
             shard_aligned = shard_aligned && (uintptr_t)p.shard[w] % 16 == 0;
         }
         RBX_REQUIRE(!lr_delta, "%s: sharded tables share one row numbering (lr_delta must be NULL)", who);
@@ -930,14 +973,15 @@ int embed_fm_fwd_impl(const char* who, const float* table, const float* table_lr
     const bool aligned = al16(table) && al16(dense_w) && al16(E) && al16(S) && shard_aligned;
     if (D % 4 == 0 && D <= 128 && (D & (D - 1)) == 0 && aligned) {
         const bool staged = al16(rows) && al16(dense_x);
+        const int smode = sh.row_lr ? 2 : (sharded ? 1 : 0);
         int rc = 0;
-        switch (D / 4) {
-            case 1: rc = launch_fwd<1, RBX_FWD_U>(p, staged, sharded, st); break;
-            case 2: rc = launch_fwd<2, RBX_FWD_U>(p, staged, sharded, st); break;
-            case 4: rc = launch_fwd<4, RBX_FWD_U>(p, staged, sharded, st); break;
-            case 8: rc = launch_fwd<8, RBX_FWD_U>(p, staged, sharded, st); break;
-            case 16: rc = launch_fwd<16, RBX_FWD_U>(p, staged, sharded, st); break;
-            default: rc = launch_fwd<32, RBX_FWD_U>(p, staged, sharded, st); break;
+        switch (sh.row_lr ? D / 2 : D / 4) {      // lanes per physical row
+            case 1: rc = launch_fwd<1, RBX_FWD_U>(p, staged, smode, st); break;
+            case 2: rc = launch_fwd<2, RBX_FWD_U>(p, staged, smode, st); break;
+            case 4: rc = launch_fwd<4, RBX_FWD_U>(p, staged, smode, st); break;
+            case 8: rc = launch_fwd<8, RBX_FWD_U>(p, staged, smode, st); break;
+            case 16: rc = launch_fwd<16, RBX_FWD_U>(p, staged, smode, st); break;
+            default: rc = launch_fwd<32, RBX_FWD_U>(p, staged, smode, st); break;
         }
         if (rc) return rbx_fail(RBX_ERR_UNSUPPORTED, "%s: sharded path needs 16-byte aligned rows / dense_x", who);
     } else {
@@ -984,8 +1028,9 @@ int embed_fm_bwd_impl(const char* who, const float* table, const ShardArgs& sh, 
         const int l = shard_log2(sh.world, who);
         if (l < 0) return l;
         p.wlog2 = l;
-        any_g = sh.g_tables && sh.g_tables[0] && !lr_only;
+        any_g = sh.g_tables && sh.g_tables[0] && (!lr_only || sh.row_lr);
         any_g_lr = sh.g_tables_lr && sh.g_tables_lr[0];
+        RBX_REQUIRE(!sh.row_lr || D == 4 || D == 8 || D == 16, "%s: the ROW+LR layout covers D in {4, 8, 16} (D=%d)", who, D);
         for (int w = 0; w < sh.world; ++w) {
             p.shard[w] = sh.tables ? sh.tables[w] : nullptr;
             p.g_shard[w] = any_g ? sh.g_tables[w] : nullptr;
@@ -1009,6 +1054,7 @@ int embed_fm_bwd_impl(const char* who, const float* table, const ShardArgs& sh, 
         const bool aligned = al16(table) && al16(E) && al16(S) && al16(dE) && al16(g_table) && shard_aligned;
         if (D % 4 == 0 && D <= 128 && (D & (D - 1)) == 0 && aligned) {
             const bool staged = al16(rows);
+            const int smode = sh.row_lr ? 2 : (sharded ? 1 : 0);
             // fold the numeric-slot / bias reductions into this launch (dE is then read exactly once)
             if (RBX_BWD_FUSE_NUM && (want_w || want_lr) && (Fn == 0 || dense_x) && Fn * D <= 4096 && al16(dense_w) &&
                 al16(g_dense_w)) {
@@ -1016,13 +1062,13 @@ int embed_fm_bwd_impl(const char* who, const float* table, const ShardArgs& sh, 
                 num_fused = true;
             }
             int rc = 0;
-            switch (D / 4) {
-                case 1: rc = launch_bwd<1, RBX_BWD_U>(p, staged, sharded, st); break;
-                case 2: rc = launch_bwd<2, RBX_BWD_U>(p, staged, sharded, st); break;
-                case 4: rc = launch_bwd<4, RBX_BWD_U>(p, staged, sharded, st); break;
-                case 8: rc = launch_bwd<8, RBX_BWD_U>(p, staged, sharded, st); break;
-                case 16: rc = launch_bwd<16, RBX_BWD_U>(p, staged, sharded, st); break;
-                default: rc = launch_bwd<32, RBX_BWD_U>(p, staged, sharded, st); break;
+            switch (sh.row_lr ? D / 2 : D / 4) {
+                case 1: rc = launch_bwd<1, RBX_BWD_U>(p, staged, smode, st); break;
+                case 2: rc = launch_bwd<2, RBX_BWD_U>(p, staged, smode, st); break;
+                case 4: rc = launch_bwd<4, RBX_BWD_U>(p, staged, smode, st); break;
+                case 8: rc = launch_bwd<8, RBX_BWD_U>(p, staged, smode, st); break;
+                case 16: rc = launch_bwd<16, RBX_BWD_U>(p, staged, smode, st); break;
+                default: rc = launch_bwd<32, RBX_BWD_U>(p, staged, smode, st); break;
             }
             if (rc) return rbx_fail(RBX_ERR_UNSUPPORTED, "%s: sharded path needs 16-byte aligned rows", who);
         } else {
@@ -1107,6 +1153,38 @@ int rbx_embed_fm_bwd_sharded(const float* const* shard_tables, float* const* sha
     RBX_REQUIRE(world >= 1, "%s: world", who);
     ShardArgs sh;
     sh.world = world; sh.tables = shard_tables; sh.g_tables = shard_g_tables; sh.g_tables_lr = shard_g_tables_lr;
+    return embed_fm_bwd_impl(who, nullptr, sh, rows, cat_pos, pad_row, nullptr, dense_x, dense_w, num_pos, num_widx, E, S,
+                             dE, d_fm, d_lr, nullptr, nullptr, g_dense_w, g_dense_w_lr, g_lr_bias, B, R, F, Fn, D, n_slots,
+                             stream);
+}
+
+
+// ROW+LR layout: every shard is [cap, 2 D] floats, row = [e_0 .. e_{D-1} | w_lr | 0 ...]; the
+// gradient shards mirror it.  One request per slot over NVLink instead of two.
+int rbx_embed_fm_fwd_sharded_rowlr(const float* const* shard_tables, int world, const int32_t* rows, const int32_t* cat_pos,
+                                   const float* dense_x, const float* dense_w, const float* dense_w_lr,
+                                   const int32_t* num_pos, const int32_t* num_widx, const float* lr_bias, float* E,
+                                   float* S, float* fm_out, float* lr_out, int64_t B, int64_t R, int F, int Fn, int D,
+                                   int n_slots, rbx_stream_t stream) {
+    const char* who = "rbx_embed_fm_fwd_sharded_rowlr";
+    RBX_REQUIRE(world >= 1 && shard_tables, "%s: shard tables required", who);
+    ShardArgs sh;
+    sh.world = world; sh.tables = shard_tables; sh.row_lr = true;
+    return embed_fm_fwd_impl(who, nullptr, nullptr, sh, rows, cat_pos, nullptr, dense_x, dense_w, dense_w_lr, num_pos,
+                             num_widx, lr_bias, E, S, fm_out, lr_out, B, R, F, Fn, D, n_slots, stream);
+}
+
+int rbx_embed_fm_bwd_sharded_rowlr(const float* const* shard_tables, float* const* shard_g_tables, int world,
+                                   const int32_t* rows, const int32_t* cat_pos, const int32_t* pad_row,
+                                   const float* dense_x, const float* dense_w, const int32_t* num_pos,
+                                   const int32_t* num_widx, const float* E, const float* S, const float* dE,
+                                   const float* d_fm, const float* d_lr, float* g_dense_w, float* g_dense_w_lr,
+                                   float* g_lr_bias, int64_t B, int64_t R, int F, int Fn, int D, int n_slots,
+                                   rbx_stream_t stream) {
+    const char* who = "rbx_embed_fm_bwd_sharded_rowlr";
+    RBX_REQUIRE(world >= 1 && shard_g_tables, "%s: gradient shards required", who);
+    ShardArgs sh;
+    sh.world = world; sh.tables = shard_tables; sh.g_tables = shard_g_tables; sh.row_lr = true;
     return embed_fm_bwd_impl(who, nullptr, sh, rows, cat_pos, pad_row, nullptr, dense_x, dense_w, num_pos, num_widx, E, S,
                              dE, d_fm, d_lr, nullptr, nullptr, g_dense_w, g_dense_w_lr, g_lr_bias, B, R, F, Fn, D, n_slots,
                              stream);

@@ -166,6 +166,36 @@ def embed_fm_bwd_sharded(shard_tables, shard_g_tables, shard_g_tables_lr, world,
           B, R, F, Fn, D, n_slots or (F + Fn), _stream())
 
 
+def embed_fm_fwd_sharded_rowlr(shard_tables, world, rows, cat_pos, dense_x, dense_w, dense_w_lr, num_pos, lr_bias, R, D,
+                               want_E=True, want_S=True, want_fm=True, want_lr=True, num_widx=None, n_slots=None):
+    """As embed_fm_fwd_sharded, for shards in the ROW+LR layout ([cap, 2 D] floats, first-order weight at column D)."""
+    F, Fn = len(cat_pos), len(num_pos)
+    B = rows.shape[0] if rows is not None else dense_x.shape[0]
+    dev = (rows if rows is not None else dense_x).device
+    Ft = n_slots or (F + Fn)
+    E = torch.empty((B, Ft, D), dtype=F32, device=dev) if want_E else None
+    S = torch.empty((B, D), dtype=F32, device=dev) if want_S else None
+    fm = torch.empty((B,), dtype=F32, device=dev) if want_fm else None
+    lr = torch.empty((B,), dtype=F32, device=dev) if want_lr else None
+    _call("rbx_embed_fm_fwd_sharded_rowlr", shard_tables, world, _p(rows, I32, "rows"), _i32(cat_pos),
+          _p(dense_x, F32, "dense_x"), _p(dense_w, F32, "dense_w"), _p(dense_w_lr, F32, "dense_w_lr"), _i32(num_pos),
+          _i32(num_widx) if num_widx is not None else None, _p(lr_bias, F32, "lr_bias"), _p(E), _p(S), _p(fm), _p(lr),
+          B, R, F, Fn, D, Ft, _stream())
+    return E, S, fm, lr
+
+
+def embed_fm_bwd_sharded_rowlr(shard_tables, shard_g_tables, world, rows, cat_pos, pad_row, dense_x, dense_w, num_pos,
+                               E, S, dE, d_fm, d_lr, g_dense_w, g_dense_w_lr, g_lr_bias, R, D, num_widx=None, n_slots=None):
+    F, Fn = len(cat_pos), len(num_pos)
+    B = rows.shape[0] if rows is not None else dense_x.shape[0]
+    _call("rbx_embed_fm_bwd_sharded_rowlr", shard_tables, shard_g_tables, world, _p(rows, I32, "rows"),
+          _i32(cat_pos), _i32(pad_row if pad_row is not None else [-1] * F), _p(dense_x, F32, "dense_x"),
+          _p(dense_w, F32, "dense_w"), _i32(num_pos), _i32(num_widx) if num_widx is not None else None,
+          _p(E, F32, "E"), _p(S, F32, "S"), _p(dE, F32, "dE"), _p(d_fm, F32, "d_fm"), _p(d_lr, F32, "d_lr"),
+          _p(g_dense_w, F32, "g_dense_w"), _p(g_dense_w_lr, F32, "g_dense_w_lr"), _p(g_lr_bias, F32, "g_lr_bias"),
+          B, R, F, Fn, D, n_slots or (F + Fn), _stream())
+
+
 # ------------------------------------------------------------------------------------- a5 / a9
 def gather_rows(table, ids):
     N = ids.numel()

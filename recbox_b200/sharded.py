@@ -140,9 +140,15 @@ class ShardedEmbeddingFM(object):
     into multi-GB tables, kept for small tables / debugging)."""
 
     def __init__(self, R, D, mode="peer", group=None, device=None, with_lr=True, kern=None, max_ids=None, slack=1.5,
-                 alloc="symm"):
+                 alloc="symm", layout="split"):
         if mode not in ("peer", "push", "a2a"):
             raise RbxError("ShardedEmbeddingFM: mode must be 'peer', 'push' or 'a2a'")
+        if layout not in ("split", "rowlr"):
+            raise RbxError("ShardedEmbeddingFM: layout must be 'split' or 'rowlr'")
+        if layout == "rowlr" and (mode != "peer" or not with_lr or D not in (4, 8, 16)):
+            raise RbxError("layout='rowlr' (row + first-order weight in one 2D-float physical row) needs mode='peer', "
+                           "with_lr=True and D in {4, 8, 16}")
+        self.layout = layout
         self.R, self.D, self.mode, self.group, self.with_lr = int(R), int(D), mode, group, with_lr
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
@@ -157,6 +163,23 @@ class ShardedEmbeddingFM(object):
         n_l4 = (n_l + 3) // 4 * 4
         self._block = None
         self._peers = []
+        if mode == "peer" and layout == "rowlr":
+            if self.world & (self.world - 1) or self.world > 8:
+                raise RbxError("peer mode needs a power-of-two world <= 8 (got %d)" % self.world)
+            # one block: table_phys [cap, 2D] | g_phys [cap, 2D]; physical row = [e (D) | w_lr | zeros]
+            RS = 2 * self.D
+            self._offs = (0, self.cap * RS)
+            self._block = self._shared_block(2 * self.cap * RS)
+            flat = self._block.tensor
+            tp = flat[:self.cap * RS].view(self.cap, RS)
+            gp = flat[self.cap * RS:].view(self.cap, RS)
+            self.table, self.table_lr = tp[:, :self.D], tp[:, self.D]
+            self.g_table, self.g_table_lr = gp[:, :self.D], gp[:, self.D]
+            self._gflat = flat[self.cap * RS:]
+            self._flat = flat
+            self._map_peers()
+            self._saved = self._ws = None
+            return
         if mode == "peer":
             if self.world & (self.world - 1) or self.world > 8:
                 raise RbxError("peer mode needs a power-of-two world <= 8 (got %d)" % self.world)
@@ -244,6 +267,9 @@ class ShardedEmbeddingFM(object):
         base = self._peer_bases(self._block)
         o = self._offs
         mk = lambda off: (ctypes.c_void_p * self.world)(*[b + off * 4 for b in base])
+        if self.layout == "rowlr":
+            self._ptr_arrays = {"table": mk(o[0]), "g_table": mk(o[1])}
+            return
         self._ptr_arrays = {"table": mk(o[0]), "table_lr": mk(o[1]), "g_table": mk(o[2]), "g_table_lr": mk(o[3])}
 
     def close(self):
@@ -265,7 +291,7 @@ class ShardedEmbeddingFM(object):
     def load_global(self, table, table_lr=None):
         """Fill this rank's shard from a full [R, D] (and [R]) table (tests / checkpoints)."""
         mine = table[self.rank::self.world].to(self.device, F32)
-        self.table[:mine.shape[0]].copy_(mine)
+        self.table[:mine.shape[0]].copy_(mine)                    # (strided views in the rowlr layout)
         if table_lr is not None:
             m1 = table_lr.reshape(-1)[self.rank::self.world].to(self.device, F32)
             self.table_lr[:m1.shape[0]].copy_(m1)
@@ -273,10 +299,10 @@ class ShardedEmbeddingFM(object):
 
     def gather_global(self, which="g_table"):
         """All ranks' shards of `which` re-interleaved to the global row order (tests / checkpoints)."""
-        local = getattr(self, which)
+        local = getattr(self, which).contiguous()                 # (the rowlr layout hands out strided views)
         parts = [torch.empty_like(local) for _ in range(self.world)]
         if self.world > 1:
-            dist.all_gather(parts, local.contiguous(), group=self.group)
+            dist.all_gather(parts, local, group=self.group)
         else:
             parts = [local]
         out = torch.empty((self.cap * self.world,) + tuple(local.shape[1:]), dtype=F32, device=local.device)
@@ -330,12 +356,21 @@ class ShardedEmbeddingFM(object):
 
     # ---- peer mode: one fused kernel per direction, exchange inside ----------------------------------
     def _fwd_peer(self, rows, cat_pos, dense_x, dense_w, dense_w_lr, num_pos, lr_bias, want_E, n_slots):
+        if self.layout == "rowlr":
+            return self.kern.embed_fm_fwd_sharded_rowlr(self._ptr_arrays["table"], self.world, rows, cat_pos, dense_x,
+                                                        dense_w, dense_w_lr, num_pos, lr_bias, self.R, self.D,
+                                                        want_E=want_E, n_slots=n_slots)
         return self.kern.embed_fm_fwd_sharded(self._ptr_arrays["table"], self._ptr_arrays["table_lr"] if self.with_lr else None,
                                               self.world, rows, cat_pos, dense_x, dense_w, dense_w_lr, num_pos, lr_bias,
                                               self.R, self.D, want_E=want_E, want_lr=self.with_lr, n_slots=n_slots)
 
     def _bwd_peer(self, rows, cat_pos, pad_rows, dense_x, dense_w, num_pos, E, S, dE, d_fm, d_lr,
                   g_dense_w, g_dense_w_lr, g_lr_bias, n_slots):
+        if self.layout == "rowlr":
+            self.kern.embed_fm_bwd_sharded_rowlr(self._ptr_arrays["table"], self._ptr_arrays["g_table"], self.world, rows,
+                                                 cat_pos, pad_rows, dense_x, dense_w, num_pos, E, S, dE, d_fm, d_lr,
+                                                 g_dense_w, g_dense_w_lr, g_lr_bias, self.R, self.D, n_slots=n_slots)
+            return
         self.kern.embed_fm_bwd_sharded(self._ptr_arrays["table"], self._ptr_arrays["g_table"],
                                        self._ptr_arrays["g_table_lr"] if self.with_lr else None, self.world, rows,
                                        cat_pos, pad_rows, dense_x, dense_w, num_pos, E, S, dE, d_fm,

@@ -42,7 +42,9 @@ def _worker(rank, world, port, mode, D, out_dir):
         sl = slice(rank * B, (rank + 1) * B)
         rows, dx = f["rows"][sl].contiguous(), f["dense_x"][sl].contiguous()
 
-        sh = sharded.ShardedEmbeddingFM(pb.R, D, mode=mode, device=dev, max_ids=B * pb.F, slack=3.0)
+        layout = "rowlr" if mode == "peer_rowlr" else "split"
+        mode = "peer" if mode == "peer_rowlr" else mode
+        sh = sharded.ShardedEmbeddingFM(pb.R, D, mode=mode, device=dev, max_ids=B * pb.F, slack=3.0, layout=layout)
         sh.load_global(f["table"], f["table_lr"])
         E, S, fm, lr = sh.forward(rows, pb.cat_pos, dx, f["dense_w"], f["dense_w_lr"], pb.num_pos, f["bias"])
         gw, gw1, gb = torch.zeros_like(f["dense_w"]), torch.zeros_like(f["dense_w_lr"]), torch.zeros(1, device=dev)
@@ -61,7 +63,11 @@ def _worker(rank, world, port, mode, D, out_dir):
         Er, Sr, fmr, lrr = ops.embed_fm_fwd(f["table"], f["table_lr"], f["rows"], pb.cat_pos, f["dense_x"], f["dense_w"],
                                             f["dense_w_lr"], pb.num_pos, f["bias"])
         assert torch.equal(E, Er[sl]), "gathered rows must be bit-exact"
-        assert torch.equal(S, Sr[sl]) and torch.equal(fm, fmr[sl]) and torch.equal(lr, lrr[sl]), "same kernel, same order"
+        assert torch.equal(S, Sr[sl]) and torch.equal(fm, fmr[sl]), "same kernel, same order"
+        if layout == "rowlr":   # the first-order weights ride in the row: one lane sums them, in slot order
+            assert_close(lr, lrr[sl], what="lr[rowlr]")
+        else:
+            assert torch.equal(lr, lrr[sl]), "same kernel, same order"
         if mode == "push":      # a bucket larger than its slot is flagged, not silently dropped
             tiny = sharded.ShardedEmbeddingFM(pb.R, D, mode="push", device=dev, max_ids=B * pb.F, slack=0.0)
             tiny.slot_cap = 8
@@ -97,5 +103,13 @@ def _world():
 @pytest.mark.parametrize("mode", ["peer", "push", "a2a"])
 def test_sharded_matches_single_table(mode, D, tmp_path):
     world = _world()
+    mp.spawn(_worker, args=(world, _free_port(), mode, D, str(tmp_path)), nprocs=world, join=True)
+    assert all(os.path.exists(os.path.join(str(tmp_path), "ok%d" % r)) for r in range(world))
+
+
+@pytest.mark.parametrize("D", [16, 8, 4])
+def test_sharded_rowlr_layout_matches_single_table(D, tmp_path):
+    """ROW+LR shard layout (row and first-order weight in one physical row / one NVLink request)."""
+    world, mode = _world(), "peer_rowlr"
     mp.spawn(_worker, args=(world, _free_port(), mode, D, str(tmp_path)), nprocs=world, join=True)
     assert all(os.path.exists(os.path.join(str(tmp_path), "ok%d" % r)) for r in range(world))
