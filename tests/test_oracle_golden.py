@@ -10,6 +10,15 @@ import torch
 
 from helpers import assert_close, oracle
 
+def same_sum(a, b, what=""):
+    """Floating-point SUMS (reductions over the batch / fields): bit-exact when the host runs ATen with the
+    reduction split the goldens were minted with, else within 1e-6 (ATen's mm / sum partial order
+    depends on the host's thread count).  Gathers stay torch.equal."""
+    if not torch.equal(a, b):
+        assert_close(a, b, rtol=1e-6, atol_scale=1e-6, what=what)
+    return True
+
+
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 
@@ -80,18 +89,18 @@ def test_interaction_golden(tag, mode):
     g = load("interaction")
     E = g[tag + ".E"].clone().requires_grad_(True)
     y = oracle.inner_product_interaction(E, mode)
-    assert torch.equal(y, g["%s.%s.out" % (tag, mode)])
+    assert same_sum(y, g["%s.%s.out" % (tag, mode)])
     (y * g["%s.%s.w" % (tag, mode)]).sum().backward()
-    assert torch.equal(E.grad, g["%s.%s.dE" % (tag, mode)])
+    assert same_sum(E.grad, g["%s.%s.dE" % (tag, mode)])
 
 
 def test_pooling_golden():
     g = load("pooling")
-    assert torch.equal(oracle.masked_average_pooling(g["emb"]), g["ranking_avg"])
-    assert torch.equal(oracle.masked_average_pooling(g["emb"]), g["core_avg"])
-    assert torch.equal(oracle.masked_average_pooling(g["emb"], g["mask"]), g["ranking_avg_mask"])
-    assert torch.equal(oracle.masked_sum_pooling(g["emb"]), g["ranking_sum"])
-    assert torch.equal(oracle.masked_sum_pooling(g["emb"]), g["core_sum"])
+    assert same_sum(oracle.masked_average_pooling(g["emb"]), g["ranking_avg"])
+    assert same_sum(oracle.masked_average_pooling(g["emb"]), g["core_avg"])
+    assert same_sum(oracle.masked_average_pooling(g["emb"], g["mask"]), g["ranking_avg_mask"])
+    assert same_sum(oracle.masked_sum_pooling(g["emb"]), g["ranking_sum"])
+    assert same_sum(oracle.masked_sum_pooling(g["emb"]), g["core_sum"])
 
 
 # ------------------------------------------------------------------------- golden: ranking layers
@@ -112,18 +121,18 @@ def test_ranking_layers_golden(tag):
         lr = oracle.logistic_regression(X, feats, W1, bias)
         fm = oracle.inner_product_interaction(E, "product_sum")
         y = oracle.factorization_machine(X, E, feats, W1, bias)
-        assert torch.equal(lr, g["lr_out"]) and torch.equal(fm, g["fm_out"]) and torch.equal(y, g["y"])
+        assert same_sum(lr, g["lr_out"]) and same_sum(fm, g["fm_out"]) and same_sum(y, g["y"])
         loss = loss + (y * g["wy"]).sum()
     loss.backward()
     for name in feats:
         k = "grad." + EMB + name + ".weight"
         if k in g:
-            assert torch.equal(W[name].grad, g[k]), k
+            assert same_sum(W[name].grad, g[k]), k
         k1 = "grad." + LRP + name + ".weight"
         if W1 is not None and k1 in g:
-            assert torch.equal(W1[name].grad, g[k1]), k1
+            assert same_sum(W1[name].grad, g[k1]), k1
     if W1 is not None:
-        assert torch.equal(bias.grad, g["grad.fm.lr_layer.bias"])
+        assert same_sum(bias.grad, g["grad.fm.lr_layer.bias"])
 
 
 def test_core_layers_golden():
@@ -141,10 +150,10 @@ def test_core_layers_golden():
     enc = {"user_hist": oracle.masked_average_pooling}
     U = oracle.dict2tensor(oracle.embed_dict(X, feats, W, enc, feature_source=("user",)), core_semantics=True)
     V = oracle.dict2tensor(oracle.embed_dict(X, feats, W, enc, feature_source=("item",)), core_semantics=True)
-    assert torch.equal(U, g["U"]) and torch.equal(V, g["V"])
+    assert same_sum(U, g["U"]) and same_sum(V, g["V"])
     ((U * g["wU"]).sum() + (V * g["wV"]).sum()).backward()
     for name in ("item_id", "item_cat", "user_id", "user_age"):
-        assert torch.equal(W[name].grad, g["grad." + EMB + name + ".weight"]), name
+        assert same_sum(W[name].grad, g["grad." + EMB + name + ".weight"]), name
     one = oracle.dict2tensor(oracle.embed_dict(X, OrderedDict(user_id=feats["user_id"]), W), core_semantics=True)
     assert one.dim() == 2 and torch.equal(one, g["single"])
 
@@ -153,12 +162,12 @@ def test_two_tower_golden():
     g = load("two_tower")
     u, v = g["u"].clone().requires_grad_(True), g["v"].clone().requires_grad_(True)
     y = oracle.two_tower_score(u, v)
-    assert torch.equal(y, g["y"])
+    assert same_sum(y, g["y"])
     loss = oracle.softmax_cross_entropy_loss(y)
-    assert torch.equal(loss, g["loss"])
+    assert same_sum(loss, g["loss"])
     loss.backward()
-    assert torch.equal(u.grad, g["du"]) and torch.equal(v.grad, g["dv"])
-    assert torch.equal(oracle.dssm_score(g["dssm_u"], g["dssm_v"]), g["dssm_y"])
+    assert same_sum(u.grad, g["du"]) and same_sum(v.grad, g["dv"])
+    assert same_sum(oracle.dssm_score(g["dssm_u"], g["dssm_v"]), g["dssm_y"])
 
 
 # ------------------------------------------------------------------- golden: assembled train step
