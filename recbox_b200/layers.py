@@ -35,6 +35,7 @@ from torch import nn
 
 from . import ops
 from ._lib import RbxError
+from .loader import PackedBatch, PackedColumns
 
 I32, F32 = torch.int32, torch.float32
 
@@ -379,6 +380,16 @@ class PackedInputs(dict):
 def get_inputs(model, inputs, feature_source=None):
     """Drop-in for RankingModel.get_inputs (ranking_model.py:106-116): ONE host->device copy of the
     batch matrix, then per-feature views of it."""
+    if isinstance(inputs, PackedBatch):          # loader.PackedDataLoader: 160 B / Criteo sample, no casts
+        pb = inputs if inputs.ids is None or inputs.ids.is_cuda else inputs.to(model.device, non_blocking=True)
+        X = PackedColumns(pb)
+        if feature_source:
+            if type(feature_source) == str:
+                feature_source = [feature_source]
+            for feature, spec in model.feature_map.features.items():
+                if spec["type"] != "meta" and spec["source"] not in feature_source:
+                    X.pop(feature, None)
+        return X
     batch = inputs.to(model.device, non_blocking=True)
     X = PackedInputs(model.feature_map, batch)
     if feature_source:
@@ -388,6 +399,15 @@ def get_inputs(model, inputs, feature_source=None):
             if spec["type"] != "meta" and spec["source"] not in feature_source:
                 X.pop(feature, None)
     return X
+
+
+def get_labels(model, inputs):
+    """Drop-in for RankingModel.get_labels (ranking_model.py:118-122): [B,1] float labels on the device."""
+    if isinstance(inputs, PackedBatch):
+        return inputs.labels.to(model.device, non_blocking=True).float().view(-1, 1)
+    labels = model.feature_map.labels
+    assert len(labels) == 1, "Please override get_labels(), add_loss(), evaluate() when using multiple labels!"
+    return inputs[:, model.feature_map.get_column_index(labels[0])].to(model.device).float().view(-1, 1)
 
 
 class _EmbDict(OrderedDict):
@@ -436,6 +456,20 @@ class _FusedDictBase(nn.Module):
             setattr(new, k, copy.deepcopy(v, memo))
         new._build_store()
         return new
+
+    def row_offsets(self, cat_names):
+        """First fused-table row of each named categorical feature (loader.PackedDataLoader.bind)."""
+        self._store.ensure()
+        offs, dims = [], set()
+        for n in cat_names:
+            m = self.embedding_layers[n]
+            if not isinstance(m, nn.Embedding):
+                raise RbxError("feature %r has no embedding table" % n)
+            dims.add(m.embedding_dim)
+            offs.append(self._store.groups[m.embedding_dim].emb_off[id(m)])
+        if len(dims) > 1:
+            raise RbxError("row_offsets: features of different embedding dims live in different fused tables")
+        return offs
 
     # -- call plans ------------------------------------------------------------------------------
     def _select(self, feature_source, feature_type):
@@ -543,9 +577,19 @@ class _FusedDictBase(nn.Module):
             rows, dense_x, _ = ops.split_batch(inputs.batch, kind, slot, offs, len(cats), len(nums), want_label=False)
             return rows, dense_x
         rows = dense_x = None
-        if cats:
+        if isinstance(inputs, PackedColumns):
+            pb = inputs.packed
+            if pb.offsets is not None:                  # the loader pre-added ITS layer's row offsets
+                pre = dict(zip(pb.cat_names, pb.offsets))
+                offs = [o - pre.get(n, 0) for n, o in zip(cats, offs)]
+            if cats and pb.ids is not None and pb.ids.is_cuda and list(cats) == list(pb.cat_names) \
+                    and pb.offsets is not None and not any(offs):
+                rows = pb.ids                           # the block IS the kernels' `rows` argument
+            if nums and pb.dense is not None and pb.dense.is_cuda and list(nums) == list(pb.num_names):
+                dense_x = pb.dense
+        if cats and rows is None:
             rows = ops.pack_columns([self._col(inputs[n]) for n in cats], add=offs, as_rows=True)
-        if nums:
+        if nums and dense_x is None:
             dense_x = ops.pack_columns([self._col(inputs[n]) for n in nums], as_rows=False)
         return rows, dense_x
 
