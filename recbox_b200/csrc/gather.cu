@@ -290,6 +290,81 @@ __global__ void __launch_bounds__(kThreads) k_pool_bwd(const float* __restrict__
     }
 }
 
+// Vector forms of the two materialised pooling kernels (D = 4*LPR a power of two <= 128, 16-byte aligned).  The scalar
+// kernels above walk the L rows one at a time with one 4-byte load per lane and a full-warp shuffle reduction per row
+// (0.24 of the HBM roofline on [8192,200,64], profiles/r1u_kernel_rooflines.md).  Here LPR lanes own a row, a warp step
+// covers 32/LPR rows and kU steps are in flight; the row-sum test of sequence.py:10 is a log2(LPR)-step shuffle.
+template <int LPR>
+__global__ void __launch_bounds__(kThreads) k_pool_fwd_vec(const float* __restrict__ emb, const uint8_t* __restrict__ mask,
+                                                          float* __restrict__ out, float* __restrict__ cnt, int64_t B, int L,
+                                                          int mode) {
+    constexpr int D = 4 * LPR, RPW = 32 / LPR, kU = 4;
+    const int lane = threadIdx.x & 31, lig = lane & (LPR - 1), ri = lane / LPR;
+    const int64_t warp0 = (int64_t)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
+    const int64_t nwarps = (int64_t)gridDim.x * (kThreads / 32);
+    for (int64_t b = warp0; b < B; b += nwarps) {
+        const float* eb = emb + (size_t)b * L * D + 4 * lig;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        float n = 0.f;
+        for (int l0 = 0; l0 < L; l0 += kU * RPW) {
+            float4 v[kU];
+#pragma unroll
+            for (int u = 0; u < kU; ++u) {
+                const int l = l0 + u * RPW + ri;
+                v[u] = l < L ? ld_stream_f4(eb + (size_t)l * D) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int u = 0; u < kU; ++u) {
+                const int l = l0 + u * RPW + ri;
+                acc = f4_add(acc, v[u]);
+                if (mode == 1) {
+                    if (mask) {
+                        if (l < L && lig == 0 && mask[b * L + l]) n += 1.f;
+                    } else {
+                        const float rs = group_sum<LPR>((v[u].x + v[u].y) + (v[u].z + v[u].w));
+                        if (l < L && lig == 0 && rs != 0.f) n += 1.f;
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int o = LPR; o < 32; o <<= 1) {
+            acc.x += __shfl_xor_sync(0xffffffffu, acc.x, o);
+            acc.y += __shfl_xor_sync(0xffffffffu, acc.y, o);
+            acc.z += __shfl_xor_sync(0xffffffffu, acc.z, o);
+            acc.w += __shfl_xor_sync(0xffffffffu, acc.w, o);
+        }
+        n = group_sum<32>(n);
+        if (ri == 0) {
+            const float den = n + 1e-12f;                 // sequence.py:11 divides (no reciprocal-multiply)
+            float4 r = acc;
+            if (mode == 1) r = make_float4(acc.x / den, acc.y / den, acc.z / den, acc.w / den);
+            *reinterpret_cast<float4*>(out + (size_t)b * D + 4 * lig) = r;
+        }
+        if (cnt && lane == 0) cnt[b] = n;
+    }
+}
+
+template <int LPR>
+__global__ void __launch_bounds__(kThreads) k_pool_bwd_vec(const float* __restrict__ g, const float* __restrict__ cnt,
+                                                          float* __restrict__ d_emb, int64_t B, int L, int mode) {
+    constexpr int D = 4 * LPR;
+    const int lane = threadIdx.x & 31, lig = lane & (LPR - 1);
+    const int64_t warp0 = (int64_t)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
+    const int64_t nwarps = (int64_t)gridDim.x * (kThreads / 32);
+    const int n4 = L * LPR;                       // float4 per sample; lane t, t+32, ... all hit column chunk `lig`
+    for (int64_t b = warp0; b < B; b += nwarps) {
+        float4 x = ld_row_f4(g + (size_t)b * D + 4 * lig);
+        if (mode == 1) {
+            const float den = __ldg(cnt + b) + 1e-12f;
+            x = make_float4(x.x / den, x.y / den, x.z / den, x.w / den);
+        }
+        float* db = d_emb + (size_t)b * L * D;
+#pragma unroll 4
+        for (int t = lane; t < n4; t += 32) st_stream_f4(db + 4 * (size_t)t, x);
+    }
+}
+
 }  // namespace
 
 #define RBX_DISPATCH_LPR(D, CALL)                   \
@@ -383,7 +458,11 @@ int rbx_pool_fwd(const float* emb, const uint8_t* mask, float* out, float* cnt, 
     RBX_REQUIRE(mode == 0 || mode == 1, "%s: mode %d", who, mode);
     if (B == 0) return RBX_OK;
     RBX_REQUIRE((emb || L == 0) && out, "%s: null pointer", who);
-    k_pool_fwd<<<capped_grid(B, 8), kThreads, 0, rbx_cast_stream(stream)>>>(emb, mask, out, cnt, B, L, D, mode);
+    if (L > 0 && vec_ok(D, emb, out, nullptr)) {
+        RBX_DISPATCH_LPR(D, (k_pool_fwd_vec<LPR><<<capped_grid(B, 8), kThreads, 0, rbx_cast_stream(stream)>>>(emb, mask, out, cnt, B, L, mode)));
+    } else {
+        k_pool_fwd<<<capped_grid(B, 8), kThreads, 0, rbx_cast_stream(stream)>>>(emb, mask, out, cnt, B, L, D, mode);
+    }
     RBX_LAUNCH_CHECK(who);
     return RBX_OK;
 }
@@ -394,6 +473,11 @@ int rbx_pool_bwd(const float* g, const float* cnt, float* d_emb, int64_t B, int 
     RBX_REQUIRE(mode == 0 || (mode == 1 && cnt), "%s: mode %d / cnt", who, mode);
     if (B == 0 || L == 0) return RBX_OK;
     RBX_REQUIRE(g && d_emb, "%s: null pointer", who);
+    if (vec_ok(D, g, d_emb, nullptr)) {
+        RBX_DISPATCH_LPR(D, (k_pool_bwd_vec<LPR><<<capped_grid(B, 8), kThreads, 0, rbx_cast_stream(stream)>>>(g, cnt, d_emb, B, L, mode)));
+        RBX_LAUNCH_CHECK(who);
+        return RBX_OK;
+    }
     const int64_t n = B * (int64_t)L * D;
     int64_t grid = (n + kThreads - 1) / kThreads;
     const int64_t cap = (int64_t)rbx_sm_count() * 16;

@@ -183,6 +183,265 @@ __global__ void __launch_bounds__(kThreads) k_pairs_bwd(const float* __restrict_
     }
 }
 
+// ------------------------------------------------------------------ modes 2/3, vector path: WARP per sample
+// (D = 4*LPR a power of two <= 128).  The CTA-per-sample kernels below synchronise the whole CTA twice per sample,
+// divide by D per element and re-derive pair indices in the inner loop; they ran at 0.04-0.3 of the HBM roofline
+// (profiles/r1u_kernel_rooflines.md).  Here every warp owns a sample: E[b] is staged in the warp's private slice of
+// shared memory with coalesced 16-byte loads, and the pair work is register-tiled so shared-memory bandwidth stays
+// below the HBM time.  No CTA-wide barrier after the setup.
+//
+// Slice layout: row r of the sample at float offset r*D + 4*(r>>2) -- the extra 16 B per 4-row block spreads the
+// blocks over the eight 16-byte bank groups, so an LDS.128 of column chunk c of rows {4t+k : t = lane's block} is
+// conflict-free.  Rows F .. 4*ceil(F/4)-1 are zero padding (tiles read them, results are not written).
+__device__ __forceinline__ int row_off(int r, int D) { return r * D + ((r >> 2) << 2); }
+__host__ __device__ inline int slice_floats(int F, int D) { const int FB = (F + 3) >> 2; return 4 * FB * D + 4 * FB; }
+
+__device__ __forceinline__ float dot4(float4 a, float4 b, float acc) {
+    acc = fmaf(a.x, b.x, acc); acc = fmaf(a.y, b.y, acc); acc = fmaf(a.z, b.z, acc); return fmaf(a.w, b.w, acc);
+}
+__device__ __forceinline__ float4 f4_mul(float4 a, float4 b) { return make_float4(a.x * b.x, a.y * b.y, a.z * b.z, a.w * b.w); }
+__device__ __forceinline__ float4 f4_fma4(float4 a, float4 b, float4 c) {
+    return make_float4(fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y), fmaf(a.z, b.z, c.z), fmaf(a.w, b.w, c.w));
+}
+
+template <int LPR>
+__device__ __forceinline__ void stage_sample(float* sE, const float* __restrict__ Eb, int F, int lane) {
+    constexpr int D = 4 * LPR;
+    for (int t = lane; t < F * LPR; t += 32) {
+        const int r = t / LPR, c = t & (LPR - 1);
+        *reinterpret_cast<float4*>(sE + row_off(r, D) + 4 * c) = ld_stream_f4(Eb + 4 * (size_t)t);
+    }
+}
+
+template <int LPR>
+__device__ __forceinline__ void zero_pad_rows(float* sE, int F, int lane) {
+    constexpr int D = 4 * LPR;
+    const int FB = (F + 3) >> 2;
+    for (int t = F * LPR + lane; t < 4 * FB * LPR; t += 32)
+        *reinterpret_cast<float4*>(sE + row_off(t / LPR, D) + 4 * (t & (LPR - 1))) = make_float4(0.f, 0.f, 0.f, 0.f);
+}
+
+// mode 2 forward: out[b, p(i,j)] = <e_i, e_j>.  A lane owns a 4x4 tile of the upper triangle (tile table shared by the
+// CTA): 8 LDS.128 per 64 FMA.
+template <int LPR>
+__global__ void __launch_bounds__(kThreads) k_ip_fwd_warp(const float* __restrict__ E, float* __restrict__ out, int64_t B, int F) {
+    constexpr int D = 4 * LPR;
+    extern __shared__ __align__(16) float smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpc = blockDim.x >> 5;
+    const int FB = (F + 3) >> 2, NT = FB * (FB + 1) / 2, P = F * (F - 1) / 2;
+    int* sTile = reinterpret_cast<int*>(smem);                       // [NT] (ti << 8) | tj, ti <= tj
+    float* sE = smem + ((NT + 3) & ~3) + (size_t)warp * slice_floats(F, D);
+    for (int ti = threadIdx.x; ti < FB; ti += blockDim.x)
+        for (int tj = ti; tj < FB; ++tj) sTile[ti * FB - ti * (ti - 1) / 2 + (tj - ti)] = (ti << 8) | tj;
+    zero_pad_rows<LPR>(sE, F, lane);
+    __syncthreads();
+    const int64_t gw = (int64_t)blockIdx.x * wpc + warp, nw = (int64_t)gridDim.x * wpc;
+    for (int64_t b = gw; b < B; b += nw) {
+        __syncwarp();
+        stage_sample<LPR>(sE, E + (size_t)b * F * D, F, lane);
+        __syncwarp();
+        float* ob = out + (size_t)b * P;
+        for (int t = lane; t < NT; t += 32) {
+            const int ti = sTile[t] >> 8, tj = sTile[t] & 0xff;
+            float acc[4][4];
+#pragma unroll
+            for (int x = 0; x < 4; ++x)
+#pragma unroll
+                for (int y = 0; y < 4; ++y) acc[x][y] = 0.f;
+            const float* pa = sE + row_off(4 * ti, D);
+            const float* pb = sE + row_off(4 * tj, D);
+#pragma unroll 4
+            for (int c = 0; c < LPR; ++c) {
+                float4 a[4], bb[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    a[k] = *reinterpret_cast<const float4*>(pa + k * D + 4 * c);
+                    bb[k] = *reinterpret_cast<const float4*>(pb + k * D + 4 * c);
+                }
+#pragma unroll
+                for (int x = 0; x < 4; ++x)
+#pragma unroll
+                    for (int y = 0; y < 4; ++y) acc[x][y] = dot4(a[x], bb[y], acc[x][y]);
+            }
+#pragma unroll
+            for (int x = 0; x < 4; ++x) {
+                const int i = 4 * ti + x;
+                if (i >= F - 1) continue;
+                const int base = i * (2 * F - i - 1) / 2 - i - 1;          // pair_index(i, j) = base + j
+#pragma unroll
+                for (int y = 0; y < 4; ++y) {
+                    const int j = 4 * tj + y;
+                    if (j > i && j < F) ob[base + j] = acc[x][y];
+                }
+            }
+        }
+    }
+}
+
+// mode 2 backward: dE[b,i,:] = sum_j G[i,j] e_j with G the symmetric, zero-diagonal matrix of dout[b, p(i,j)].
+// G is scattered into the warp's slice as sG[j][i] (row stride GS), a lane owns (4 rows i) x (one 16-byte column chunk).
+template <int LPR>
+__global__ void __launch_bounds__(kThreads) k_ip_bwd_warp(const float* __restrict__ E, const float* __restrict__ dout,
+                                                         float* __restrict__ dE, int64_t B, int F) {
+    constexpr int D = 4 * LPR;
+    extern __shared__ __align__(16) float smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpc = blockDim.x >> 5;
+    const int FB = (F + 3) >> 2, P = F * (F - 1) / 2, GS = 4 * FB + 4;
+    int* sPair = reinterpret_cast<int*>(smem);                        // [P] (i << 16) | j
+    const int per_warp = slice_floats(F, D) + F * GS;
+    float* sE = smem + ((P + 3) & ~3) + (size_t)warp * per_warp;
+    float* sG = sE + slice_floats(F, D);
+    for (int i = threadIdx.x; i < F; i += blockDim.x)
+        for (int j = i + 1; j < F; ++j) sPair[pair_index(i, j, F)] = (i << 16) | j;
+    zero_pad_rows<LPR>(sE, F, lane);
+    for (int t = lane; t < F * GS; t += 32) sG[t] = 0.f;               // diagonal and padding stay zero
+    __syncthreads();
+    const int64_t gw = (int64_t)blockIdx.x * wpc + warp, nw = (int64_t)gridDim.x * wpc;
+    const int NTask = FB * LPR;
+    for (int64_t b = gw; b < B; b += nw) {
+        __syncwarp();
+        stage_sample<LPR>(sE, E + (size_t)b * F * D, F, lane);
+        for (int p = lane; p < P; p += 32) {
+            const int ij = sPair[p], i = ij >> 16, j = ij & 0xffff;
+            const float w = ld_stream_f1(dout + (size_t)b * P + p);
+            sG[j * GS + i] = w;
+            sG[i * GS + j] = w;
+        }
+        __syncwarp();
+        float* db = dE + (size_t)b * F * D;
+        for (int t = lane; t < NTask; t += 32) {
+            const int ib = t / LPR, c = t & (LPR - 1);
+            float4 acc[4];
+#pragma unroll
+            for (int x = 0; x < 4; ++x) acc[x] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
+            for (int j = 0; j < F; ++j) {
+                const float4 g = *reinterpret_cast<const float4*>(sG + j * GS + 4 * ib);
+                const float4 e = *reinterpret_cast<const float4*>(sE + row_off(j, D) + 4 * c);
+                acc[0] = f4_fma(e, g.x, acc[0]);
+                acc[1] = f4_fma(e, g.y, acc[1]);
+                acc[2] = f4_fma(e, g.z, acc[2]);
+                acc[3] = f4_fma(e, g.w, acc[3]);
+            }
+#pragma unroll
+            for (int x = 0; x < 4; ++x)
+                if (4 * ib + x < F) st_stream_f4(db + (size_t)(4 * ib + x) * D + 4 * c, acc[x]);
+        }
+    }
+}
+
+// mode 3 forward: out[b, p, :] = e_i * e_j.  LPR lanes per pair, 32/LPR pairs per step, 512-byte coalesced stores.
+template <int LPR>
+__global__ void __launch_bounds__(kThreads) k_ew_fwd_warp(const float* __restrict__ E, float* __restrict__ out, int64_t B, int F) {
+    constexpr int D = 4 * LPR, PPW = 32 / LPR;
+    extern __shared__ __align__(16) float smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpc = blockDim.x >> 5;
+    const int P = F * (F - 1) / 2;
+    int* sPair = reinterpret_cast<int*>(smem);
+    float* sE = smem + ((P + 3) & ~3) + (size_t)warp * slice_floats(F, D);
+    for (int i = threadIdx.x; i < F; i += blockDim.x)
+        for (int j = i + 1; j < F; ++j) sPair[pair_index(i, j, F)] = (i << 16) | j;
+    __syncthreads();
+    const int ps = lane / LPR, c = lane & (LPR - 1);
+    const int64_t gw = (int64_t)blockIdx.x * wpc + warp, nw = (int64_t)gridDim.x * wpc;
+    for (int64_t b = gw; b < B; b += nw) {
+        __syncwarp();
+        stage_sample<LPR>(sE, E + (size_t)b * F * D, F, lane);
+        __syncwarp();
+        float* ob = out + (size_t)b * P * D + 4 * c;
+#pragma unroll 4
+        for (int p = ps; p < P; p += PPW) {
+            const int ij = sPair[p];
+            const float4 a = *reinterpret_cast<const float4*>(sE + row_off(ij >> 16, D) + 4 * c);
+            const float4 bb = *reinterpret_cast<const float4*>(sE + row_off(ij & 0xffff, D) + 4 * c);
+            st_stream_f4(ob + (size_t)p * D, f4_mul(a, bb));
+        }
+    }
+}
+
+// mode 3 backward: dE[b,i,:] = sum_{j != i} dout[b, p(i,j), :] * e_j.  dout is streamed once in pair order; a step is
+// (row i, 32/LPR consecutive j): the lane of (j, chunk c) adds w*e_j into its register accumulator of row i and w*e_i
+// into the shared accumulator of row j (one owner per (j, c) within a row i; __syncwarp between rows).
+template <int LPR>
+__global__ void __launch_bounds__(kThreads) k_ew_bwd_warp(const float* __restrict__ E, const float* __restrict__ dout,
+                                                         float* __restrict__ dE, int64_t B, int F) {
+    constexpr int D = 4 * LPR, PPW = 32 / LPR;
+    extern __shared__ __align__(16) float smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpc = blockDim.x >> 5;
+    const int P = F * (F - 1) / 2;
+    const int per_warp = 2 * slice_floats(F, D);
+    float* sE = smem + (size_t)warp * per_warp;
+    float* sD = sE + slice_floats(F, D);
+    const int ps = lane / LPR, c = lane & (LPR - 1);
+    const int64_t gw = (int64_t)blockIdx.x * wpc + warp, nw = (int64_t)gridDim.x * wpc;
+    const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int64_t b = gw; b < B; b += nw) {
+        __syncwarp();
+        stage_sample<LPR>(sE, E + (size_t)b * F * D, F, lane);
+        for (int t = lane; t < F * LPR; t += 32) *reinterpret_cast<float4*>(sD + row_off(t / LPR, D) + 4 * (t & (LPR - 1))) = zero;
+        __syncwarp();
+        const float* gb = dout + (size_t)b * P * D + 4 * c;
+        int pbase = 0;                                   // pair_index(i, i+1)
+        for (int i = 0; i + 1 < F; ++i) {
+            const float4 ei = *reinterpret_cast<const float4*>(sE + row_off(i, D) + 4 * c);
+            float4 acc = zero;
+            const int nj = F - 1 - i;
+            // loads of the whole row first (they do not depend on shared memory), then the accumulation
+            for (int q0 = 0; q0 < nj; q0 += 4 * PPW) {
+                float4 w[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int q = q0 + u * PPW + ps;
+                    w[u] = q < nj ? ld_stream_f4(gb + (size_t)(pbase + q) * D) : zero;
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int q = q0 + u * PPW + ps;
+                    if (q < nj) {
+                        const int j = i + 1 + q;
+                        float4* dj = reinterpret_cast<float4*>(sD + row_off(j, D) + 4 * c);
+                        acc = f4_fma4(w[u], *reinterpret_cast<const float4*>(sE + row_off(j, D) + 4 * c), acc);
+                        *dj = f4_fma4(w[u], ei, *dj);
+                    }
+                }
+            }
+#pragma unroll
+            for (int o = LPR; o < 32; o <<= 1) {
+                acc.x += __shfl_xor_sync(0xffffffffu, acc.x, o);
+                acc.y += __shfl_xor_sync(0xffffffffu, acc.y, o);
+                acc.z += __shfl_xor_sync(0xffffffffu, acc.z, o);
+                acc.w += __shfl_xor_sync(0xffffffffu, acc.w, o);
+            }
+            if (ps == 0) {
+                float4* di = reinterpret_cast<float4*>(sD + row_off(i, D) + 4 * c);
+                *di = f4_add(*di, acc);
+            }
+            pbase += nj;
+            __syncwarp();
+        }
+        float* db = dE + (size_t)b * F * D;
+        for (int t = lane; t < F * LPR; t += 32)
+            st_stream_f4(db + 4 * (size_t)t, *reinterpret_cast<const float4*>(sD + row_off(t / LPR, D) + 4 * (t & (LPR - 1))));
+    }
+}
+
+// warps per CTA so that `fixed + wpc * per_warp` floats fit the shared-memory budget; 0 = does not fit at all
+inline int warps_for(size_t fixed_floats, size_t per_warp_floats, size_t* smem_bytes) {
+    const size_t budget = 200 * 1024;
+    int wpc = kThreads / 32;
+    while (wpc > 0 && (fixed_floats + wpc * per_warp_floats) * 4 > budget) --wpc;
+    *smem_bytes = (fixed_floats + (size_t)wpc * per_warp_floats) * 4;
+    return wpc;
+}
+
+template <typename K>
+inline int warp_grid(K kernel, int wpc, size_t smem, int64_t B) {
+    if (smem > 48 * 1024) cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    int per_sm = 1;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, wpc * 32, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
+    return capped_grid((B + wpc - 1) / wpc, per_sm);
+}
+
 inline bool vec_ok(int D, const void* a, const void* b, const void* c) {
     return D % 4 == 0 && D <= 128 && (D & (D - 1)) == 0 && (uintptr_t)a % 16 == 0 && (uintptr_t)b % 16 == 0 &&
            (uintptr_t)c % 16 == 0;
@@ -219,6 +478,21 @@ int rbx_interact_fwd(const float* E, float* out, int64_t B, int F, int D, int mo
         if (F < 2) return RBX_OK;
         RBX_REQUIRE(F < 32768, "%s: F too large", who);
         const size_t P = (size_t)F * (F - 1) / 2;
+        if (vec_ok(D, E, mode == 3 ? out : nullptr, nullptr) && F <= 255) {
+            const int FB = (F + 3) / 4;
+            size_t wsmem = 0;
+            const size_t fixed = mode == 2 ? (size_t)((FB * (FB + 1) / 2 + 3) & ~3) : ((P + 3) & ~(size_t)3);
+            const int wpc = warps_for(fixed, slice_floats(F, D), &wsmem);
+            if (wpc > 0) {
+                if (mode == 2) {
+                    RBX_DISPATCH_LPR(D, (k_ip_fwd_warp<LPR><<<warp_grid(k_ip_fwd_warp<LPR>, wpc, wsmem, B), wpc * 32, wsmem, st>>>(E, out, B, F)));
+                } else {
+                    RBX_DISPATCH_LPR(D, (k_ew_fwd_warp<LPR><<<warp_grid(k_ew_fwd_warp<LPR>, wpc, wsmem, B), wpc * 32, wsmem, st>>>(E, out, B, F)));
+                }
+                RBX_LAUNCH_CHECK(who);
+                return RBX_OK;
+            }
+        }
         const size_t smem = ((size_t)F * (D + 1) + P) * 4;
         RBX_REQUIRE(smem <= 200 * 1024, "%s: F=%d D=%d needs %zu B shared memory", who, F, D, smem);
         if (smem > 48 * 1024) cudaFuncSetAttribute(k_pairs_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -248,6 +522,22 @@ int rbx_interact_bwd(const float* E, const float* dout, float* dE, int64_t B, in
             return RBX_OK;
         }
         const size_t P = (size_t)F * (F - 1) / 2;
+        if (vec_ok(D, E, dE, mode == 3 ? dout : nullptr) && F <= 255) {
+            const int FB = (F + 3) / 4;
+            size_t wsmem = 0;
+            const size_t fixed = mode == 2 ? ((P + 3) & ~(size_t)3) : 0;
+            const size_t per_warp = mode == 2 ? (size_t)slice_floats(F, D) + (size_t)F * (4 * FB + 4) : 2 * (size_t)slice_floats(F, D);
+            const int wpc = warps_for(fixed, per_warp, &wsmem);
+            if (wpc > 0) {
+                if (mode == 2) {
+                    RBX_DISPATCH_LPR(D, (k_ip_bwd_warp<LPR><<<warp_grid(k_ip_bwd_warp<LPR>, wpc, wsmem, B), wpc * 32, wsmem, st>>>(E, dout, dE, B, F)));
+                } else {
+                    RBX_DISPATCH_LPR(D, (k_ew_bwd_warp<LPR><<<warp_grid(k_ew_bwd_warp<LPR>, wpc, wsmem, B), wpc * 32, wsmem, st>>>(E, dout, dE, B, F)));
+                }
+                RBX_LAUNCH_CHECK(who);
+                return RBX_OK;
+            }
+        }
         const size_t smem = ((size_t)F * (D + 1) + (mode == 2 ? P : 0)) * 4;
         RBX_REQUIRE(smem <= 200 * 1024, "%s: F=%d D=%d needs %zu B shared memory", who, F, D, smem);
         if (smem > 48 * 1024) cudaFuncSetAttribute(k_pairs_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -151,6 +151,35 @@ def test_pooled_gather(D, mode, L):
     assert_close(gt, tl.grad, atol_scale=2e-5, what="pooled bwd")
 
 
+@pytest.mark.parametrize("mode", [0, 1])
+@pytest.mark.parametrize("D,L", [(4, 1), (8, 7), (64, 200), (128, 33), (16, 20), (10, 5), (1, 9)])
+def test_pool_materialised(D, L, mode):
+    """rbx_pool_fwd/bwd (Masked{Average,Sum}Pooling called on a [B,L,D] tensor, sequence.py:4-20 / pooling.py:22-40):
+    zero rows do not count, an explicit mask overrides the row-sum test, the gradient reaches every position."""
+    ops = _ops()
+    g = torch.Generator().manual_seed(D * 100 + L + mode)
+    B = 301
+    emb = torch.randn(B, L, D, generator=g)
+    emb[torch.rand(B, L, generator=g) < 0.3] = 0.0           # padded positions
+    emb[5] = 0.0                                             # a sample with no valid position at all
+    ref = oracle.masked_average_pooling(emb) if mode else oracle.masked_sum_pooling(emb)
+    out, cnt = ops.pool_fwd(emb.to(DEV), None, mode)
+    assert_close(out, ref, what="pool fwd")
+    if mode == 1:
+        assert torch.equal(cnt.cpu(), (emb.sum(-1) != 0).float().sum(-1))
+        mask = torch.rand(B, L, generator=g) < 0.5
+        out_m, cnt_m = ops.pool_fwd(emb.to(DEV), mask.to(DEV), 1)
+        assert_close(out_m, oracle.masked_average_pooling(emb, mask), what="pool fwd mask")
+        assert torch.equal(cnt_m.cpu(), mask.float().sum(-1))
+    go = torch.randn(B, D, generator=g)
+    e2 = emb.clone().requires_grad_(True)
+    ((oracle.masked_average_pooling(e2) if mode else oracle.masked_sum_pooling(e2)) * go).sum().backward()
+    d_emb = ops.pool_bwd(go.to(DEV), cnt, (B, L, D), mode)
+    keep = torch.ones(B, dtype=torch.bool)
+    keep[5] = False                       # 0/1e-12: the reference's own gradient there is g*1e12, compare the rest
+    assert_close(d_emb.cpu()[keep], e2.grad[keep], what="pool bwd")
+
+
 def test_pooled_known_answer():
     """MaskedAveragePooling on W=arange(10).view(5,2) (row 0 zeroed as the
     reference relies on), idx=[[1,1,0],[4,0,0]] -> [[2,3],[8,9]] (two, resp. one, non-pad rows)."""
@@ -210,7 +239,7 @@ def test_interact_elementwise_known_answer():
 
 
 @pytest.mark.parametrize("mode", [0, 1, 2, 3])
-@pytest.mark.parametrize("F,D", [(39, 16), (5, 10), (2, 64), (13, 128), (7, 1)])
+@pytest.mark.parametrize("F,D", [(39, 16), (5, 10), (2, 64), (13, 128), (7, 1), (8, 4), (40, 8), (33, 32), (4, 16)])
 def test_interact_random(mode, F, D):
     ops = _ops()
     name = [k for k, v in ops.MODES.items() if v == mode][0]
@@ -221,6 +250,23 @@ def test_interact_random(mode, F, D):
     out = ops.interact_fwd(E.detach().to(DEV), mode)
     scale = float((E.detach().sum(1) ** 2).sum(-1).max()) if mode <= 1 else 1.0
     assert_close(out.reshape(ref.shape), ref, atol_scale=1e-5 * max(1.0, scale / float(ref.abs().max())), what=name)
+    dout = torch.randn(ref.shape, generator=g)
+    (ref * dout).sum().backward()
+    dE = ops.interact_bwd(E.detach().to(DEV), dout.to(DEV).contiguous(), mode)
+    assert_close(dE, E.grad, atol_scale=2e-5, what=name + " bwd")
+
+
+@pytest.mark.parametrize("mode", [2, 3])
+def test_interact_pairs_many_samples_per_warp(mode):
+    """B far above the resident warp count: every warp of the warp-per-sample kernels reuses its shared-memory slice."""
+    ops = _ops()
+    name = [k for k, v in ops.MODES.items() if v == mode][0]
+    g = torch.Generator().manual_seed(mode)
+    B, F, D = 50021, 6, 8
+    E = torch.randn(B, F, D, generator=g, requires_grad=True)
+    ref = oracle.inner_product_interaction(E, name)
+    out = ops.interact_fwd(E.detach().to(DEV), mode)
+    assert_close(out.reshape(ref.shape), ref, what=name)
     dout = torch.randn(ref.shape, generator=g)
     (ref * dout).sum().backward()
     dE = ops.interact_bwd(E.detach().to(DEV), dout.to(DEV).contiguous(), mode)
