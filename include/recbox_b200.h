@@ -399,6 +399,56 @@ int rbx_unique_ids_i32(const int32_t* ids /*DEVICE [n]*/, int64_t n, int64_t voc
                        int32_t* uniq, int64_t* first, int32_t* inverse, int64_t* n_out,
                        rbx_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------
+ * f2  per-epoch negative sampling (csrc/sample.cu)
+ * Replaces sampling_block + the hstack of TrainGenerator.negative_sampling
+ * (recbox/matching/pytorch/dataloaders/h5_generator.py:72-95, 144-181): uniform draws with
+ * replacement over [0, num_items); with pos_ptr/pos_items (CSR of each user's interacted items,
+ * sorted ascending per user) draws that hit one of the query user's items are redrawn
+ * (= ignore_pos_items=True: probabilities of those items zeroed and renormalised).
+ *   out [n_queries, (pos ? 1 : 0) + num_negs] int64: pos[q] first when given, then the negatives
+ *   user_of_query [n_queries] | NULL (= identity): row of the CSR for query q
+ *   gave_up DEVICE int32[1]: += number of elements still colliding after 4096 redraws
+ * Counter-based RNG keyed by (seed, element index): reproducible, geometry-independent; not numpy's
+ * MT19937 stream (parity is distributional).
+ * ------------------------------------------------------------------------------------------ */
+int rbx_sample_negatives(int64_t n_queries, int num_negs, int64_t num_items, uint64_t seed,
+                         const int64_t* pos /*DEVICE [n_queries] | NULL*/,
+                         const int64_t* user_of_query /*DEVICE | NULL*/,
+                         const int64_t* pos_ptr /*DEVICE [n_users+1] | NULL*/,
+                         const int64_t* pos_items /*DEVICE | NULL*/,
+                         int64_t* out /*DEVICE*/, int* gave_up /*DEVICE [1] | NULL*/,
+                         rbx_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * f3  retrieval evaluation (csrc/topk.cu)
+ * rbx_topk_ip replaces FaissIndex.search = faiss.IndexFlatIP(dim).search(query, topk)
+ * (recbox/utils/ann/faiss.py:3-14; called from evaluate_block, recbox/core/metrics.py:52-54):
+ * exact inner-product top-k of every query row against the whole corpus, descending, ties to the
+ * smaller index; rows of a corpus smaller than k are padded with (-inf, -1).  fp32 FMA arithmetic
+ * (no tf32).  D a multiple of 4 in [4,128]; k <= 1024; q, items 16-byte aligned.
+ *   chunk = items per pass (rounded up to 128); ws = rbx_topk_ws_bytes(U, k, chunk) bytes of
+ *   256-byte aligned DEVICE scratch (U * chunk * 8 B candidate queue + the running lists).
+ * rbx_rank_metrics replaces the rest of evaluate_block (core/metrics.py:55-68) and the metric
+ * classes (core/metrics.py:71-200): candidates the user clicked in train sink behind all others
+ * (scores += -1e9 * mask; argsort), the first kmax are `ranked`, hit[u,r] = ranked[u,r] is a valid
+ * item of u, and out[u,m] = metric kinds[m] at cut-off ks[m]:
+ *   0 Recall 1 nRecall 2 Precision 3 F1 4 DCG 5 NDCG 6 MRR 7 HitRate 8 MAP   (float64, as Python)
+ * train_* / valid_*: CSR over the U query rows, items sorted ascending per row (duplicates kept:
+ * len(true_items) counts them, core/metrics.py:78).
+ * ------------------------------------------------------------------------------------------ */
+size_t rbx_topk_ws_bytes(int64_t U, int k, int64_t chunk);
+int rbx_topk_ip(const float* q /*DEVICE [U,D]*/, const float* items /*DEVICE [N,D]*/,
+                int64_t U, int64_t N, int D, int k, int64_t chunk,
+                float* out_scores /*DEVICE [U,k] | NULL*/, int64_t* out_idx /*DEVICE [U,k] | NULL*/,
+                void* ws /*DEVICE*/, size_t ws_bytes, rbx_stream_t stream);
+int rbx_rank_metrics(const int64_t* cand /*DEVICE [U,T] top-T item ids, descending*/, int T, int64_t U,
+                     const int64_t* train_ptr /*DEVICE [U+1] | NULL*/, const int64_t* train_items /*DEVICE | NULL*/,
+                     const int64_t* valid_ptr /*DEVICE [U+1]*/, const int64_t* valid_items /*DEVICE*/,
+                     int kmax, const int* kinds /*DEVICE [M]*/, const int* ks /*DEVICE [M]*/, int M,
+                     int64_t* ranked /*DEVICE [U,kmax]*/, uint8_t* hit /*DEVICE [U,kmax]*/,
+                     double* out /*DEVICE [U,M] | NULL when M == 0*/, rbx_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

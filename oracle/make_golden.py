@@ -355,6 +355,70 @@ def golden_collate_unique():
     npz("collate_unique", **out)
 
 
+class _NumpyFlatIP(object):
+    """Stand-in for faiss.IndexFlatIP (faiss is absent from this image): exact float32 inner products, descending,
+    (-3.4028235e38, -1) padding -- enough for the reference's FaissIndex / evaluate_block to run unmodified."""
+
+    def __init__(self, dim):
+        self.dim, self.vecs, self.ntotal = dim, np.zeros((0, dim), np.float32), 0
+
+    def add(self, x):
+        self.vecs = np.concatenate([self.vecs, np.asarray(x, np.float32)], 0)
+        self.ntotal = len(self.vecs)
+
+    def search(self, q, topk):
+        s = np.asarray(q, np.float32) @ self.vecs.T
+        k = min(topk, self.ntotal)
+        order = np.lexsort((np.broadcast_to(np.arange(self.ntotal), s.shape), -s), axis=1)[:, :k]
+        top = np.take_along_axis(s, order, 1)
+        if k < topk:
+            top = np.concatenate([top, np.full((len(s), topk - k), -3.4028235e38, np.float32)], 1)
+            order = np.concatenate([order, np.full((len(s), topk - k), -1)], 1)
+        return top, order.astype(np.int64)
+
+
+def golden_retrieval():
+    """f3: the reference's evaluate_metrics / evaluate_block / metric classes (core/metrics.py) run unmodified on a
+    synthetic two-tower output; only faiss.IndexFlatIP is a numpy stand-in (exact search, so results are the ones real
+    faiss returns up to float32 summation order)."""
+    import faiss
+    faiss.IndexFlatIP = _NumpyFlatIP
+    import recbox.core.metrics as M
+    rng = np.random.default_rng(91)
+    U, N, D = 61, 900, 16
+    user = rng.standard_normal((U, D)).astype(np.float32)
+    item = rng.standard_normal((N, D)).astype(np.float32)
+    query = [int(x) for x in rng.permutation(200)[:U]]
+    train, valid = {}, {}
+    for i, q in enumerate(query):
+        s = user[i] @ item.T
+        top = np.argsort(-s)
+        n_tr = int(rng.integers(0, 40)) if i % 7 else 480                     # some users clicked most of their top-500
+        tr = list(rng.choice(top[:520], size=n_tr, replace=False)) + list(rng.integers(0, N, size=3))
+        train[q] = [int(x) for x in tr]
+        nv = int(rng.integers(1, 12))
+        va = list(rng.choice(top[:60], size=nv, replace=False)) + list(rng.integers(0, N, size=2))
+        if i % 7 == 0:
+            # fewer than max_topk candidates survive the mask for this user, so masked items reach the metric window;
+            # their float32 scores all collapse to -1e9 and numpy's (unstable) argsort orders them arbitrarily --
+            # keep them out of the valid set, as a train/valid split does, so the golden does not pin that accident
+            va = [x for x in va if x not in set(train[q])] or [int(top[521])]
+        if i % 5 == 0:
+            va.append(va[0])                                                  # duplicate: len(true_items) counts it
+        valid[q] = [int(x) for x in va]
+    metrics = ["%s(k=%d)" % (n, k) for n in ("Recall", "nRecall", "Precision", "F1", "DCG", "NDCG", "MRR", "HitRate", "MAP")
+               for k in (1, 5, 20, 50)]
+    avg = M.evaluate_metrics(user.astype(np.float64), item.astype(np.float64), train, valid, query, metrics)
+    funcs = [eval(m, vars(M)) for m in metrics]
+    index = M.FaissIndex(item.astype(np.float64), dim=D)
+    per_user = M.evaluate_block(user.astype(np.float64), index, query, train, valid, funcs, 50)
+    tp = np.cumsum([0] + [len(train[q]) for q in query])
+    vp = np.cumsum([0] + [len(valid[q]) for q in query])
+    npz("retrieval", user=user, item=item, query=np.array(query), train_ptr=tp, train_items=np.concatenate([train[q] for q in query]),
+        valid_ptr=vp, valid_items=np.concatenate([valid[q] for q in query]), metrics=np.array(metrics),
+        average=np.array([avg[m] for m in metrics]), per_user=np.array(per_user, dtype=np.float64))
+
+
 def main(only=None):
     if not ref_shim.available():
         raise SystemExit("reference tree not found at %s" % ref_shim.REFERENCE_ROOT)
@@ -362,6 +426,8 @@ def main(only=None):
     torch.set_num_threads(1)       # deterministic CPU reductions
     if only == "collate_unique":    # added after the other fixtures were minted; regenerate it alone
         return golden_collate_unique()
+    if only == "retrieval":
+        return golden_retrieval()
     with tempfile.TemporaryDirectory() as tmp:
         golden_interaction(L)
         golden_pooling(L)
@@ -375,6 +441,7 @@ def main(only=None):
         golden_deepfm_train(L, tmp)
         golden_config1(L, tmp)
     golden_collate_unique()
+    golden_retrieval()
 
 
 if __name__ == "__main__":

@@ -294,6 +294,142 @@ def collate_unique_reference(item_indexes):
 
 
 # --------------------------------------------------------------------------------------------
+# (f2)  negative sampling
+# --------------------------------------------------------------------------------------------
+def sampling_block(num_items, block_query_indexes, num_negs, user2items_dict, ignore_pos_items=False, seed=None):
+    """recbox/matching/pytorch/dataloaders/h5_generator.py:72-95 (sampling_block, uniform sampling_probs): uniform
+    draws with replacement; with ignore_pos_items the query user's items get probability 0 and the rest is
+    renormalised.  numpy's global MT19937 stream, as in the reference."""
+    if seed is not None:
+        np.random.seed(seed)
+    if ignore_pos_items:
+        rows = []
+        for q in block_query_indexes:
+            probs = np.ones(num_items) / num_items
+            probs[user2items_dict[q]] = 0
+            probs = probs / np.sum(probs)
+            rows.append(np.random.choice(num_items, size=num_negs, replace=True, p=probs))
+        return np.array(rows)
+    return np.random.choice(num_items, size=(len(block_query_indexes), num_negs), replace=True)
+
+
+# --------------------------------------------------------------------------------------------
+# (f3)  retrieval evaluation
+# --------------------------------------------------------------------------------------------
+def flat_ip_search(query_vecs, corpus_vecs, topk):
+    """faiss.IndexFlatIP(dim).search (recbox/utils/ann/faiss.py:8-14; faiss is a third-party dependency, un-pinned in
+    setup.py / requirements.txt and absent from this image): exact inner products in float32, the topk largest per
+    query in descending order; ties resolved to the smaller index here; (-inf, -1) padding when the corpus is smaller
+    than topk."""
+    q = np.asarray(query_vecs, dtype=np.float32)
+    c = np.asarray(corpus_vecs, dtype=np.float32)
+    scores = q @ c.T
+    U, N = scores.shape
+    k = min(topk, N)
+    order = np.lexsort((np.broadcast_to(np.arange(N), scores.shape), -scores), axis=1)[:, :k]
+    top_s = np.take_along_axis(scores, order, axis=1)
+    if k < topk:
+        top_s = np.concatenate([top_s, np.full((U, topk - k), -np.inf, np.float32)], 1)
+        order = np.concatenate([order, np.full((U, topk - k), -1, order.dtype)], 1)
+    return top_s, order.astype(np.int64)
+
+
+class _Metric(object):
+    def __init__(self, k=1):
+        self.topk = k
+
+
+class Recall(_Metric):
+    def __call__(self, topk_items, true_items):          # core/metrics.py:71-80
+        return len(set(true_items) & set(topk_items[:self.topk])) / (len(true_items) + 1e-12)
+
+
+class nRecall(_Metric):
+    def __call__(self, topk_items, true_items):          # core/metrics.py:83-92
+        return len(set(true_items) & set(topk_items[:self.topk])) / min(self.topk, len(true_items) + 1e-12)
+
+
+class Precision(_Metric):
+    def __call__(self, topk_items, true_items):          # core/metrics.py:95-104
+        return len(set(true_items) & set(topk_items[:self.topk])) / (self.topk + 1e-12)
+
+
+class F1(_Metric):
+    def __call__(self, topk_items, true_items):          # core/metrics.py:107-116
+        p, r = Precision(self.topk)(topk_items, true_items), Recall(self.topk)(topk_items, true_items)
+        return 2 * p * r / (p + r + 1e-12)
+
+
+class DCG(_Metric):
+    def __call__(self, topk_items, true_items):          # core/metrics.py:119-132
+        true_items = set(true_items)
+        return sum(1 / np.log(2 + i) for i, item in enumerate(topk_items[:self.topk]) if item in true_items)
+
+
+class NDCG(_Metric):
+    def __call__(self, topk_items, true_items):          # core/metrics.py:135-145
+        dcg_fn = DCG(k=self.topk)
+        return dcg_fn(topk_items[:self.topk], true_items) / (dcg_fn(true_items[:self.topk], true_items) + 1e-12)
+
+
+class MRR(_Metric):
+    def __call__(self, topk_items, true_items):          # core/metrics.py:148-160
+        true_items = set(true_items)
+        return sum(1 / (i + 1.0) for i, item in enumerate(topk_items[:self.topk]) if item in true_items)
+
+
+class HitRate(_Metric):
+    def __call__(self, topk_items, true_items):          # core/metrics.py:163-171
+        return 1 if len(set(true_items) & set(topk_items[:self.topk])) > 0 else 0
+
+
+class MAP(_Metric):
+    def __call__(self, topk_items, true_items):          # core/metrics.py:174-190
+        true_items = set(true_items)
+        pos, precision = 0, 0
+        for i, item in enumerate(topk_items[:self.topk]):
+            if item in true_items:
+                pos += 1
+                precision += pos / (i + 1.0)
+        return precision / (pos + 1e-12)
+
+
+def evaluate_block(user_embs, corpus_vecs, query_indices, train_user2items, valid_user2items, metric_funcs, max_topk,
+                   search_topk=500):
+    """core/metrics.py:52-68: top-500 search, train items pushed down by -1e9, argsort, first max_topk, metrics."""
+    scores, indices = flat_ip_search(user_embs, corpus_vecs, search_topk)
+    ok = indices >= 0
+    mask = np.zeros((len(user_embs), len(corpus_vecs)))
+    for i, q in enumerate(query_indices):
+        mask[i, train_user2items[q]] = 1
+    mask = np.where(ok, np.take_along_axis(mask, np.maximum(indices, 0), axis=1), 0)
+    scores = scores + (-1e9 * mask).astype(np.float32)
+    sorted_idxs = np.argsort(-scores, axis=1, kind="stable")
+    topk_items = np.take_along_axis(indices, sorted_idxs, axis=1)[:, 0:max_topk]
+    true_items = [valid_user2items[q] for q in query_indices]
+    return topk_items, [[f(preds, labels) for f in metric_funcs] for preds, labels in zip(topk_items, true_items)]
+
+
+def evaluate_metrics(user_embs, item_embs, train_user2items, valid_user2items, query_indices, metrics, search_topk=500):
+    """core/metrics.py:11-50 (single worker): {metric string: mean over users}."""
+    ns = {"Recall": Recall, "nRecall": nRecall, "Precision": Precision, "F1": F1, "DCG": DCG, "NDCG": NDCG, "MRR": MRR,
+          "HitRate": HitRate, "MAP": MAP}
+    funcs, max_topk = [], 0
+    for m in metrics:
+        try:
+            funcs.append(eval(m, {}, ns))
+            max_topk = max(max_topk, int(m.split("k=")[-1].strip(")")))
+        except Exception:
+            raise NotImplementedError("metrics={} not implemented.".format(m))
+    results = []
+    for idx in range(0, len(user_embs), 1000):
+        _, r = evaluate_block(user_embs[idx:idx + 1000], item_embs, query_indices[idx:idx + 1000], train_user2items,
+                              valid_user2items, funcs, max_topk, search_topk)
+        results += r
+    return dict(zip(metrics, np.average(np.array(results), axis=0).tolist()))
+
+
+# --------------------------------------------------------------------------------------------
 # (f1)  touched-rows optimizers: the published torch.optim algorithms run on CPU tensors
 # --------------------------------------------------------------------------------------------
 def touched_rows_step(kind, w, g, state, step, lr=1e-3, beta1=0.9, beta2=0.999, eps=1e-8, clip=1.0):

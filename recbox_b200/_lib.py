@@ -117,6 +117,10 @@ SIGNATURES = {
     "rbx_unique_ws_bytes": [_I64],
     "rbx_unique_ids_i64": [_P, _I64, _I64, _P, _c.c_size_t, _P, _P, _P, _P, _P],
     "rbx_unique_ids_i32": [_P, _I64, _I64, _P, _c.c_size_t, _P, _P, _P, _P, _P],
+    "rbx_sample_negatives": [_I64, _I, _I64, _c.c_uint64, _P, _P, _P, _P, _P, _P, _P],
+    "rbx_topk_ws_bytes": [_I64, _I, _I64],
+    "rbx_topk_ip": [_P, _P, _I64, _I64, _I, _I, _I64, _P, _P, _P, _c.c_size_t, _P],
+    "rbx_rank_metrics": [_P, _I, _I64, _P, _P, _P, _P, _I, _P, _P, _I, _P, _P, _P, _P],
 }
 
 
@@ -136,7 +140,7 @@ def load():
         if fn is None:
             raise RbxError("%s does not export %s (stale build?)" % (LIB_PATH, name))
         fn.argtypes = argtypes
-        fn.restype = {"rbx_last_error": ctypes.c_char_p, "rbx_shard_ws_bytes": ctypes.c_size_t, "rbx_unique_ws_bytes": ctypes.c_size_t,
+        fn.restype = {"rbx_last_error": ctypes.c_char_p, "rbx_shard_ws_bytes": ctypes.c_size_t, "rbx_unique_ws_bytes": ctypes.c_size_t, "rbx_topk_ws_bytes": ctypes.c_size_t,
                       "rbx_l2_set_persisting_bytes": ctypes.c_longlong}.get(name, ctypes.c_int)
     _lib = lib
     return lib

@@ -426,3 +426,72 @@ def unique_ids(ids, vocab, want_first=True, want_inverse=True, sync=True):
     if bad:
         raise RbxError("unique_ids: %d id(s) outside [0, %d)" % (bad, vocab))
     return uniq[:U], (first[:U] if want_first else None), inverse
+
+
+# ------------------------------------------------------------------------------------------- f2
+def sample_negatives(n_queries, num_negs, num_items, seed, pos=None, user_of_query=None, pos_ptr=None, pos_items=None,
+                     device=None):
+    """[n_queries, (pos is not None) + num_negs] int64: the positive column (when given) then uniform negatives; with
+    the CSR (pos_ptr, pos_items: each user's interacted items, sorted) draws hitting the query user's items are redrawn
+    (h5_generator.py:72-95 ignore_pos_items).  Returns (out, gave_up int32[1] | None)."""
+    I64 = torch.int64
+    dev = device if device is not None else (pos.device if pos is not None else pos_ptr.device)
+    lead = 0 if pos is None else 1
+    out = torch.empty((n_queries, lead + num_negs), dtype=I64, device=dev)
+    if not out.is_cuda:
+        raise RbxError("sample_negatives needs a CUDA device (recbox_b200 has no CPU path)")
+    gave_up = torch.zeros(1, dtype=I32, device=dev) if pos_ptr is not None else None
+    _call("rbx_sample_negatives", int(n_queries), int(num_negs), int(num_items), ctypes.c_uint64(int(seed) & (2 ** 64 - 1)),
+          _p(pos, I64, "pos"), _p(user_of_query, I64, "user_of_query"), _p(pos_ptr, I64, "pos_ptr"),
+          _p(pos_items, I64, "pos_items"), _p(out), _p(gave_up), _stream())
+    return out, gave_up
+
+
+# ------------------------------------------------------------------------------------------- f3
+_topk_ws = {}
+
+
+def topk_ip(q, items, k, chunk=None, want_scores=True):
+    """Exact inner-product top-k of q [U,D] against items [N,D] (faiss.IndexFlatIP.search): (scores [U,k] desc | None,
+    idx [U,k] int64)."""
+    if q.dim() != 2 or items.dim() != 2 or q.shape[1] != items.shape[1]:
+        raise RbxError("topk_ip: q [U,D] and items [N,D] must share D")
+    U, D = q.shape
+    N = items.shape[0]
+    lib = _lib.load()
+    if chunk is None:
+        chunk = max(4096, min(131072, (1 << 27) // max(U, 1) // 128 * 128))      # <= 1 GiB of candidate queue
+    need = int(lib.rbx_topk_ws_bytes(U, int(k), int(chunk))) if U else 0
+    if U and need == 0:
+        raise RbxError("topk_ip: k=%d outside [1, 1024]" % k)
+    ws = _topk_ws.get(q.device)
+    if ws is None or ws.numel() < need:
+        _topk_ws[q.device] = None
+        ws = _topk_ws[q.device] = torch.empty(max(need, 256), dtype=torch.uint8, device=q.device)
+    scores = torch.empty((U, k), dtype=F32, device=q.device) if want_scores else None
+    idx = torch.empty((U, k), dtype=torch.int64, device=q.device)
+    _call("rbx_topk_ip", _p(q, F32, "q"), _p(items, F32, "items"), U, N, D, int(k), int(chunk), _p(scores), _p(idx), _p(ws),
+          ws.numel(), _stream())
+    return scores, idx
+
+
+METRIC_KINDS = {"Recall": 0, "nRecall": 1, "Precision": 2, "F1": 3, "DCG": 4, "NDCG": 5, "MRR": 6, "HitRate": 7, "MAP": 8}
+
+
+def rank_metrics(cand, train_ptr, train_items, valid_ptr, valid_items, kinds, ks, kmax=None):
+    """cand [U,T] int64 top-T ids (descending) -> (ranked [U,kmax], hit [U,kmax] uint8, per-user metrics [U,M] float64)
+    after pushing the user's train items behind the others (core/metrics.py:52-68) -- see rbx_rank_metrics."""
+    I64 = torch.int64
+    U, T = cand.shape
+    M = len(kinds)
+    kmax = int(kmax or (max(ks) if M else T))
+    dev = cand.device
+    ranked = torch.empty((U, kmax), dtype=I64, device=dev)
+    hit = torch.empty((U, kmax), dtype=torch.uint8, device=dev)
+    out = torch.empty((U, M), dtype=torch.float64, device=dev) if M else None
+    kd = torch.tensor(list(kinds), dtype=I32, device=dev) if M else None
+    kk = torch.tensor(list(ks), dtype=I32, device=dev) if M else None
+    _call("rbx_rank_metrics", _p(cand, I64, "cand"), T, U, _p(train_ptr, I64, "train_ptr"), _p(train_items, I64, "train_items"),
+          _p(valid_ptr, I64, "valid_ptr"), _p(valid_items, I64, "valid_items"), kmax, _p(kd), _p(kk), M, _p(ranked), _p(hit),
+          _p(out), _stream())
+    return ranked, hit, out

@@ -147,12 +147,24 @@ del emb
 ids = torch.from_numpy(rng.integers(0, N_items - 1, size=(8192, 11)).astype(np.int64)).to(dev)
 case("a14", "rbx_unique_ids_i64", "n=8192x11 ids, vocab 10M (collate_fn_unique)", ids.numel() * 16 + 2 * (N_items // 8),
      lambda: ops.unique_ids(ids, N_items, sync=False))
-if hasattr(ops, "topk_ip"):
-    # f3: brute-force inner-product retrieval, 10M items, top-100 per user
-    for U_ in (1024,):
-        q = torch.randn(U_, D, generator=g).to(dev)
-        case("f3", "rbx_topk_ip", "U=%d users x 10M items D=64 k=100" % U_, N_items * D * 4 + U_ * D * 4,
-             lambda: ops.topk_ip(q, items, 100))
+# f3: brute-force inner-product retrieval, 10M items (bound: fp32 FMA pipe, 2*U*N*D flop; nominal peak
+# 148 SMs x 128 lanes x 2 x 1.965 GHz = 74.4 TFLOP/s -- computed, not measured)
+FP32_PEAK = 148 * 128 * 2 * 1.965e9
+for U_, k_ in ((1024, 100), (1024, 500), (128, 100)):
+    q = torch.randn(U_, D, generator=g).to(dev)
+    try:
+        us = timeit(lambda: ops.topk_ip(q, items, k_), reps=3)
+        fl = 2.0 * U_ * N_items * D
+        results.append({"row": "f3", "kernel": "rbx_topk_ip", "shape": "U=%d x 10M items D=64 k=%d" % (U_, k_), "flop": fl,
+                        "us": us, "tflops": fl / us / 1e6, "frac_fp32_peak": fl / (us * 1e-6) / FP32_PEAK,
+                        "corpus_gbs": N_items * D * 4 / us / 1e3})
+        print("| f3 | `rbx_topk_ip` | U=%d x 10M items D=64 k=%d | %.2f TFLOP | %.0f | %.1f TFLOP/s fp32 | %.2f of 74.4 (FMA pipe) |" % (
+            U_, k_, fl / 1e12, us, fl / us / 1e6, fl / (us * 1e-6) / FP32_PEAK))
+    except Exception as e:
+        print("rbx_topk_ip FAILED:", e)
+pos = torch.randint(0, N_items, (1_000_000,), device=dev)
+case("f2", "rbx_sample_negatives", "1M queries x 10 negs over 10M items", 1_000_000 * 11 * 8 + 1_000_000 * 8,
+     lambda: ops.sample_negatives(1_000_000, 10, N_items, 1, pos=pos))
 del items, g_items
 
 # ---- a11: configs[4] SASRec, 1M items, L=200, D=64, B=1024: three shared-table lookups -------
