@@ -279,25 +279,30 @@ __global__ void __launch_bounds__(kThreads) k_ip_fwd_warp(const float* __restric
 }
 
 // mode 2 backward: dE[b,i,:] = sum_j G[i,j] e_j with G the symmetric, zero-diagonal matrix of dout[b, p(i,j)].
-// G is scattered into the warp's slice as sG[j][i] (row stride GS), a lane owns (4 rows i) x (one 16-byte column chunk).
-template <int LPR>
+// G is scattered into the warp's slice as sG[j][i] (row stride GS).  A lane owns RPT consecutive rows i x one 16-byte
+// column chunk, RPT = ceil(F / (32/LPR)) so that ONE round covers the sample with all 32 lanes busy (F = 39, D = 16:
+// 8 row blocks of 5 x 4 chunks); per j it reads RPT scalars of G (lanes of a row block share the address) and one
+// 16-byte chunk of e_j for 4*RPT FMAs.  (The first version used 4-row tasks: 40 tasks = two rounds, the second with
+// 8 lanes, and two LDS.128 per 16 FMAs -- 0.28 of the HBM roofline.)
+template <int LPR, int RPT>
 __global__ void __launch_bounds__(kThreads) k_ip_bwd_warp(const float* __restrict__ E, const float* __restrict__ dout,
                                                          float* __restrict__ dE, int64_t B, int F) {
     constexpr int D = 4 * LPR;
     extern __shared__ __align__(16) float smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpc = blockDim.x >> 5;
-    const int FB = (F + 3) >> 2, P = F * (F - 1) / 2, GS = 4 * FB + 4;
+    const int P = F * (F - 1) / 2;
+    const int NB = (F + RPT - 1) / RPT;               // row blocks
+    const int GS = NB * RPT + 1;                      // odd-ish stride: the transposed scatter below spreads over banks
     int* sPair = reinterpret_cast<int*>(smem);                        // [P] (i << 16) | j
-    const int per_warp = slice_floats(F, D) + F * GS;
+    const int per_warp = slice_floats(F, D) + ((F * GS + 3) & ~3);
     float* sE = smem + ((P + 3) & ~3) + (size_t)warp * per_warp;
     float* sG = sE + slice_floats(F, D);
     for (int i = threadIdx.x; i < F; i += blockDim.x)
         for (int j = i + 1; j < F; ++j) sPair[pair_index(i, j, F)] = (i << 16) | j;
-    zero_pad_rows<LPR>(sE, F, lane);
     for (int t = lane; t < F * GS; t += 32) sG[t] = 0.f;               // diagonal and padding stay zero
     __syncthreads();
     const int64_t gw = (int64_t)blockIdx.x * wpc + warp, nw = (int64_t)gridDim.x * wpc;
-    const int NTask = FB * LPR;
+    const int NTask = NB * LPR;
     for (int64_t b = gw; b < B; b += nw) {
         __syncwarp();
         stage_sample<LPR>(sE, E + (size_t)b * F * D, F, lane);
@@ -311,21 +316,20 @@ __global__ void __launch_bounds__(kThreads) k_ip_bwd_warp(const float* __restric
         float* db = dE + (size_t)b * F * D;
         for (int t = lane; t < NTask; t += 32) {
             const int ib = t / LPR, c = t & (LPR - 1);
-            float4 acc[4];
+            float4 acc[RPT];
 #pragma unroll
-            for (int x = 0; x < 4; ++x) acc[x] = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll 4
+            for (int x = 0; x < RPT; ++x) acc[x] = make_float4(0.f, 0.f, 0.f, 0.f);
+            const float* gcol = sG + ib * RPT;
+            const float* ecol = sE + 4 * c;
+#pragma unroll 2
             for (int j = 0; j < F; ++j) {
-                const float4 g = *reinterpret_cast<const float4*>(sG + j * GS + 4 * ib);
-                const float4 e = *reinterpret_cast<const float4*>(sE + row_off(j, D) + 4 * c);
-                acc[0] = f4_fma(e, g.x, acc[0]);
-                acc[1] = f4_fma(e, g.y, acc[1]);
-                acc[2] = f4_fma(e, g.z, acc[2]);
-                acc[3] = f4_fma(e, g.w, acc[3]);
+                const float4 e = *reinterpret_cast<const float4*>(ecol + row_off(j, D));
+#pragma unroll
+                for (int x = 0; x < RPT; ++x) acc[x] = f4_fma(e, gcol[j * GS + x], acc[x]);
             }
 #pragma unroll
-            for (int x = 0; x < 4; ++x)
-                if (4 * ib + x < F) st_stream_f4(db + (size_t)(4 * ib + x) * D + 4 * c, acc[x]);
+            for (int x = 0; x < RPT; ++x)
+                if (ib * RPT + x < F) st_stream_f4(db + (size_t)(ib * RPT + x) * D + 4 * c, acc[x]);
         }
     }
 }
@@ -525,12 +529,28 @@ int rbx_interact_bwd(const float* E, const float* dout, float* dE, int64_t B, in
         if (vec_ok(D, E, dE, mode == 3 ? dout : nullptr) && F <= 255) {
             const int FB = (F + 3) / 4;
             size_t wsmem = 0;
+            (void)FB;
+            // mode 2: rows per lane so that one round of 32 lanes covers the sample (capped at 8: more rounds beyond)
+            int rpt = (F + (32 / (D / 4)) - 1) / (32 / (D / 4));
+            rpt = rpt < 1 ? 1 : (rpt > 8 ? 8 : rpt);
+            const int NBk = (F + rpt - 1) / rpt, GS = NBk * rpt + 1;
             const size_t fixed = mode == 2 ? ((P + 3) & ~(size_t)3) : 0;
-            const size_t per_warp = mode == 2 ? (size_t)slice_floats(F, D) + (size_t)F * (4 * FB + 4) : 2 * (size_t)slice_floats(F, D);
+            const size_t per_warp = mode == 2 ? (size_t)slice_floats(F, D) + (((size_t)F * GS + 3) & ~(size_t)3) : 2 * (size_t)slice_floats(F, D);
             const int wpc = warps_for(fixed, per_warp, &wsmem);
             if (wpc > 0) {
                 if (mode == 2) {
-                    RBX_DISPATCH_LPR(D, (k_ip_bwd_warp<LPR><<<warp_grid(k_ip_bwd_warp<LPR>, wpc, wsmem, B), wpc * 32, wsmem, st>>>(E, dout, dE, B, F)));
+#define RBX_IPB(R) RBX_DISPATCH_LPR(D, (k_ip_bwd_warp<LPR, R><<<warp_grid(k_ip_bwd_warp<LPR, R>, wpc, wsmem, B), wpc * 32, wsmem, st>>>(E, dout, dE, B, F)))
+                    switch (rpt) {
+                        case 1: RBX_IPB(1); break;
+                        case 2: RBX_IPB(2); break;
+                        case 3: RBX_IPB(3); break;
+                        case 4: RBX_IPB(4); break;
+                        case 5: RBX_IPB(5); break;
+                        case 6: RBX_IPB(6); break;
+                        case 7: RBX_IPB(7); break;
+                        default: RBX_IPB(8); break;
+                    }
+#undef RBX_IPB
                 } else {
                     RBX_DISPATCH_LPR(D, (k_ew_bwd_warp<LPR><<<warp_grid(k_ew_bwd_warp<LPR>, wpc, wsmem, B), wpc * 32, wsmem, st>>>(E, dout, dE, B, F)));
                 }

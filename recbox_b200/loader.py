@@ -233,3 +233,46 @@ class PackedDataLoader(object):
             if t is not None:
                 t.record_stream(main)
         return pb
+
+
+# =================================================================================================
+# matching side: per-epoch negative sampling (h5_generator.py:72-95, 144-181)
+# =================================================================================================
+class EpochNegativeSampler(object):
+    """TrainGenerator.negative_sampling on the GPU: `all_item_indexes = hstack([pos_item_indexes, negatives])` rebuilt
+    every epoch in ONE launch instead of np.random.choice per query row (+ a multiprocessing pool and pickle round trips).
+
+    query_indexes [N] and pos_item_indexes [N] are the columns TrainGenerator keeps (h5_generator.py:131,20);
+    user2items_dict is `get_user2items_dict` (h5_generator.py:37-42) and is only needed with ignore_pos_items=True."""
+
+    def __init__(self, num_items, query_indexes, pos_item_indexes, num_negs, user2items_dict=None, ignore_pos_items=False,
+                 seed=0, device="cuda"):
+        from . import ops
+        self._ops = ops
+        self.num_items, self.num_negs, self.seed, self.epoch = int(num_items), int(num_negs), int(seed), 0
+        dev = torch.device(device)
+        q = np.asarray(query_indexes).reshape(-1)
+        self.n = len(q)
+        self.pos = torch.as_tensor(np.asarray(pos_item_indexes).reshape(-1), dtype=torch.int64).to(dev)
+        self.user_of_query = self.pos_ptr = self.pos_items = None
+        if ignore_pos_items:
+            if user2items_dict is None:
+                raise RbxError("ignore_pos_items needs user2items_dict")
+            users, inv = np.unique(q, return_inverse=True)
+            lens = np.fromiter((len(user2items_dict[u]) for u in users), dtype=np.int64, count=len(users))
+            ptr = np.zeros(len(users) + 1, dtype=np.int64)
+            np.cumsum(lens, out=ptr[1:])
+            items = np.empty(int(ptr[-1]), dtype=np.int64)
+            for i, u in enumerate(users):
+                items[ptr[i]:ptr[i + 1]] = np.sort(np.asarray(user2items_dict[u], dtype=np.int64))
+            self.user_of_query = torch.from_numpy(inv.astype(np.int64)).to(dev)
+            self.pos_ptr, self.pos_items = torch.from_numpy(ptr).to(dev), torch.from_numpy(items).to(dev)
+
+    def sample(self):
+        """-> all_item_indexes int64 [N, 1 + num_negs] on the device (column 0 = the positive); a new stream per epoch."""
+        out, gave_up = self._ops.sample_negatives(self.n, self.num_negs, self.num_items, self.seed * 1000003 + self.epoch,
+                                                  pos=self.pos, user_of_query=self.user_of_query, pos_ptr=self.pos_ptr,
+                                                  pos_items=self.pos_items)
+        self.epoch += 1
+        self.gave_up = gave_up
+        return out

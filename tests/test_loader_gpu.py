@@ -56,7 +56,8 @@ def test_packed_batch_equals_float64_batch(tag, D, bind):
     X = layers.get_inputs(model, pb)
     got = _run(emb, fml, X, wE, wy)
     assert torch.equal(got[0], ref[0]), "E"
-    assert torch.equal(got[1], ref[1]), "y"
+    # the second call computes the first-order term inside the embedding launch (other summation order)
+    assert_close(got[1], ref[1], rtol=1e-6, atol_scale=1e-6, what="y")
     for k in ref[2]:
         assert_close(got[2][k], ref[2][k], rtol=1e-6, atol_scale=1e-6, what=k)     # atomics reorder sums
     assert torch.equal(layers.get_labels(model, pb).cpu(), g["batch"][:, -1].float().view(-1, 1))

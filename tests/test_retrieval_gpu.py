@@ -150,3 +150,24 @@ def test_sample_negatives_contract():
     out, gave_up = ops.sample_negatives(8, 4, 16, seed=1, pos_ptr=full_ptr, pos_items=full_items,
                                         user_of_query=torch.zeros(8, dtype=torch.int64, device=DEV))
     assert int(gave_up) == 32
+
+
+def test_epoch_negative_sampler_mirrors_train_generator():
+    from recbox_b200.loader import EpochNegativeSampler
+    rng = np.random.default_rng(2)
+    n_items, N = 500, 3000
+    query = rng.integers(0, 40, N)
+    pos = rng.integers(0, n_items, N)
+    u2i = {}
+    for qi, it in zip(query, pos):
+        u2i.setdefault(int(qi), []).append(int(it))            # get_user2items_dict, h5_generator.py:37-42
+    smp = EpochNegativeSampler(n_items, query, pos, 6, user2items_dict=u2i, ignore_pos_items=True, seed=5)
+    a = smp.sample()
+    b = smp.sample()
+    assert a.shape == (N, 7) and torch.equal(a[:, 0].cpu(), torch.from_numpy(pos)) and not torch.equal(a, b)
+    an = a.cpu().numpy()
+    for r in range(0, N, 11):
+        assert not set(an[r, 1:].tolist()) & set(u2i[int(query[r])])
+    assert int(smp.gave_up) == 0
+    plain = EpochNegativeSampler(n_items, query, pos, 6, seed=5).sample()
+    assert plain.shape == (N, 7) and int(plain[:, 1:].max()) < n_items
