@@ -8,6 +8,8 @@ Layout:
   features.py  FeatureMap schema objects (same surface / feature_map.json as the reference's)
   sharded.py   row-sharded table across the GPUs of one box (NCCL all-to-all or NVLink peer access)
   optim.py     exact-dense clip + Adam on the fused tables, and the touched-rows variant
+  loader.py    packed input pipeline (ids / dense converted once to pinned int32 / fp32 blocks), epoch negative sampler
+  retrieval.py FaissIndex / evaluate_metrics drop-ins on the fused top-k and ranking-metric kernels
 
 `install()` rebinds the reference's own symbols (recbox.ranking.pytorch.layers.*, recbox.core.pytorch.layers.*,
 recbox.matching.pytorch.layers.*, and the fuxictr.* aliases RecBox's ranking package still imports) to the

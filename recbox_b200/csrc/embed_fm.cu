@@ -123,6 +123,10 @@ constexpr int kWarps = kThreads / 32;
 #else
 #define RED_ROW(p, v) red_add_f4(p, v)
 #endif
+#ifndef RBX_BWD_BULK
+#define RBX_BWD_BULK 0      // 1: gradient rows leave through ONE TMA bulk reduction per row (cp.reduce.async.bulk ... add.f32 from a
+                            // per-warp shared-memory staging slot) instead of D/4 red.global.add.v4.f32 -- one packet per row
+#endif
 // reductions into a peer's gradient table travel over NVLink: vector (v4) or four scalar reds
 #ifndef RBX_PEER_RED_V4
 #define RBX_PEER_RED_V4 1
@@ -170,6 +174,19 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         "r"(parity)
         : "memory");
 }
+
+// TMA bulk reduction shared -> global (element-wise fp32 add of `bytes` contiguous bytes, multiple of 16, both 16-B aligned)
+__device__ __forceinline__ void bulk_red_add_f32(float* gdst, const void* ssrc, uint32_t bytes) {
+    asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(ssrc)),
+                 "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait() { asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // Stage the `n` 4-byte words starting at word offset `wo` of `base` (base 16-B aligned) into the
 // shared buffer `dst` (16-B aligned): the copy starts at the 16-B boundary below (skew = wo & 3
@@ -445,6 +462,17 @@ __global__ void __launch_bounds__(kThreads, RBX_BWD_MINB) k_embed_fm_bwd(const _
         for (int i = threadIdx.x; i < p.Fn * D + p.Fn + 1; i += kThreads) s_gw[i] = 0.f;
         __syncthreads();
     }
+#if RBX_BWD_BULK
+    // per warp: 2 x (U*SPW rows of RS floats) staging + 2 x (U*SPW) destination pointers, behind the id staging area
+    constexpr int kBulkRows = U * SPW;
+    constexpr bool kBulk = kStaged && kBulkRows <= 32;
+    unsigned char* bulk_raw = stage_raw + (size_t)kWarps * 2 * wi * 4 + (size_t)kWarps * 2 * 8;
+    float* my_gstage = reinterpret_cast<float*>(bulk_raw) + (size_t)warp * 2 * kBulkRows * RS;
+    unsigned long long* my_gdst = reinterpret_cast<unsigned long long*>(bulk_raw + (size_t)kWarps * 2 * kBulkRows * RS * 4) + warp * 2 * kBulkRows;
+    int chunk_no = 0;
+#else
+    constexpr bool kBulk = false;
+#endif
     const int64_t G = (p.B + SPW - 1) / SPW;
     const int64_t gw = (int64_t)blockIdx.x * kWarps + warp, nw = (int64_t)gridDim.x * kWarps;
     auto issue = [&](int64_t g, int buf) {
@@ -525,6 +553,14 @@ __global__ void __launch_bounds__(kThreads, RBX_BWD_MINB) k_embed_fm_bwd(const _
             for (int f0 = 0; f0 < F; f0 += U) {
                 int32_t r[U];
                 float4 e[U], gr[U];
+#if RBX_BWD_BULK
+                const int sb = chunk_no & 1;
+                if (kBulk) {
+                    ++chunk_no;
+                    bulk_wait_read<1>();          // this lane's bulk ops of two chunks ago have read their staging rows
+                    __syncwarp();
+                }
+#endif
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
                     r[u] = -1;
@@ -566,8 +602,29 @@ __global__ void __launch_bounds__(kThreads, RBX_BWD_MINB) k_embed_fm_bwd(const _
                             leader = (__ffs(peers) - 1) / LPR == gi;
                         }
                     }
+#if RBX_BWD_BULK
+                    if (kBulk) {
+                        const int slot = sb * kBulkRows + u * SPW + gi;
+                        if (!kRowLr || lig <= LPE) *reinterpret_cast<float4*>(my_gstage + (size_t)slot * RS + 4 * lig) = gr[u];
+                        if (lig == 0)
+                            my_gdst[slot] = (r[u] >= 0 && leader) ? (unsigned long long)(uintptr_t)grad_dst<kSharded, RS>(p, r[u]) : 0ull;
+                        continue;
+                    }
+#endif
                     if (r[u] >= 0 && leader && (!kRowLr || lig <= LPE)) RED_GRAD((grad_dst<kSharded, RS>(p, r[u]) + 4 * lig), gr[u]);
                 }
+#if RBX_BWD_BULK
+                if (kBulk) {
+                    fence_proxy_async_smem();     // staging rows written through the generic proxy -> visible to the TMA engine
+                    __syncwarp();
+                    if (lane < kBulkRows) {
+                        const unsigned long long d = my_gdst[sb * kBulkRows + lane];
+                        if (d) bulk_red_add_f32(reinterpret_cast<float*>((uintptr_t)d), my_gstage + (size_t)(sb * kBulkRows + lane) * RS,
+                                                kRowLr ? (D + 4) * 4 : D * 4);
+                    }
+                    bulk_commit();
+                }
+#endif
             }
         }
         if (fuse_num) {
@@ -630,6 +687,9 @@ __global__ void __launch_bounds__(kThreads, RBX_BWD_MINB) k_embed_fm_bwd(const _
         }
         if (kStaged) __syncwarp();
     }
+#if RBX_BWD_BULK
+    if (kBulk) bulk_wait<0>();
+#endif
     if (fuse_num) {
         __syncthreads();
         const int Fn = p.Fn;
@@ -879,7 +939,10 @@ template <int LPR, int U>
 int launch_bwd(BwdParams& p, bool staged, int sharded, cudaStream_t st) {
     constexpr int SPW = 32 / LPR;
     const int64_t groups = (p.B + SPW - 1) / SPW;
-    const size_t smem = staged_smem(SPW, p.F, 0) + p.num_smem;
+    size_t smem = staged_smem(SPW, p.F, 0) + p.num_smem;
+#if RBX_BWD_BULK
+    if (staged && U * SPW <= 32) smem += (size_t)kWarps * 2 * (U * SPW) * (4 * LPR * 4 + 8);   // gradient-row staging + destinations
+#endif
     if (sharded == 2) {
         if constexpr (LPR >= 2 && LPR <= 8) {
             if (!staged || smem > 200 * 1024 || set_smem_limit(k_embed_fm_bwd<LPR, U, true, 2>, smem) != 0) return -1;
