@@ -257,6 +257,11 @@ int rbx_shard_unroute(const float* recv /*DEVICE [N,D]*/, const int32_t* pos /*D
  * reductions of step t must land before the owner's optimizer reads its gradient shard.
  * Covers D in {4,8,16,32,64,128} with 16-byte aligned buffers; RBX_ERR_UNSUPPORTED otherwise.
  * ------------------------------------------------------------------------------------------ */
+/* Tell the library which shard this process owns (one process per GPU; -1 = unknown, the default).  Only a hint: the
+ * sharded backward may route rows it owns and rows a peer owns differently (RBX_BWD_BULK=2 build: TMA bulk
+ * reductions for peer rows).  Results do not depend on it. */
+int rbx_shard_set_rank(int rank);
+
 int rbx_embed_fm_fwd_sharded(const float* const* shard_tables /*HOST [world] of DEVICE [R_w, D]*/,
                              const float* const* shard_tables_lr /*HOST [world] of DEVICE [R_w] | NULL*/,
                              int world,
@@ -425,8 +430,9 @@ int rbx_sample_negatives(int64_t n_queries, int num_negs, int64_t num_items, uin
  * rbx_topk_ip replaces FaissIndex.search = faiss.IndexFlatIP(dim).search(query, topk)
  * (recbox/utils/ann/faiss.py:3-14; called from evaluate_block, recbox/core/metrics.py:52-54):
  * exact inner-product top-k of every query row against the whole corpus, descending, ties to the
- * smaller index; rows of a corpus smaller than k are padded with (-inf, -1).  fp32 FMA arithmetic
- * (no tf32).  D a multiple of 4 in [4,128]; k <= 1024; q, items 16-byte aligned.
+ * smaller index; rows of a corpus smaller than k are padded with (-inf, -1).  fp32-level accuracy
+ * (3xTF32 split products on the tensor cores, fp32 accumulation; RBX_TOPK_MMA=0 builds plain fp32
+ * FMA chains).  D a multiple of 4 in [4,128]; k <= 1024; q, items 16-byte aligned.
  *   chunk = items per pass (rounded up to 128); ws = rbx_topk_ws_bytes(U, k, chunk) bytes of
  *   256-byte aligned DEVICE scratch (U * chunk * 8 B candidate queue + the running lists).
  * rbx_rank_metrics replaces the rest of evaluate_block (core/metrics.py:55-68) and the metric

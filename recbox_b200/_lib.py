@@ -95,6 +95,7 @@ SIGNATURES = {
     "rbx_shard_route": [_P, _I64, _I, _P, _c.c_size_t, _P, _P, _P, _P],
     "rbx_shard_permute": [_P, _P, _P, _I64, _I, _P],
     "rbx_shard_unroute": [_P, _P, _P, _I64, _I, _P],
+    "rbx_shard_set_rank": [_I],
     "rbx_embed_fm_fwd_sharded": [_P, _P, _I] + [_P] * 12 + [_I64, _I64, _I, _I, _I, _I, _P],
     "rbx_embed_fm_bwd_sharded": [_P, _P, _P, _I] + [_P] * 15 + [_I64, _I64, _I, _I, _I, _I, _P],
     "rbx_embed_fm_fwd_sharded_rowlr": [_P, _I] + [_P] * 12 + [_I64, _I64, _I, _I, _I, _I, _P],

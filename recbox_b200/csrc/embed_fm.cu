@@ -74,6 +74,7 @@ struct BwdParams {
     int64_t R;
     int F, Fn, D, Ft;
     int wlog2;
+    int self_shard;                          // shard owned by this process (rbx_shard_set_rank), -1 = unknown
     const float* shard[RBX_MAX_WORLD];       // tables (re-gather of e when E is not given)
     float* g_shard[RBX_MAX_WORLD];           // gradient tables of every shard (local + peer-mapped)
     float* g_shard_lr[RBX_MAX_WORLD];
@@ -124,8 +125,10 @@ constexpr int kWarps = kThreads / 32;
 #define RED_ROW(p, v) red_add_f4(p, v)
 #endif
 #ifndef RBX_BWD_BULK
-#define RBX_BWD_BULK 0      // 1: gradient rows leave through ONE TMA bulk reduction per row (cp.reduce.async.bulk ... add.f32 from a
-                            // per-warp shared-memory staging slot) instead of D/4 red.global.add.v4.f32 -- one packet per row
+#define RBX_BWD_BULK 0      // gradient rows leave through ONE TMA bulk reduction per row (cp.reduce.async.bulk ... add.f32 from a
+                            // per-warp shared-memory staging slot) instead of D/4 red.global.add.v4.f32 -- one NVLink packet per
+                            // row.  1: every row of every staged kernel; 2: only rows owned by a PEER in the sharded kernels
+                            // (rbx_shard_set_rank tells the library which shard is local); 0: never
 #endif
 // reductions into a peer's gradient table travel over NVLink: vector (v4) or four scalar reds
 #ifndef RBX_PEER_RED_V4
@@ -465,7 +468,7 @@ __global__ void __launch_bounds__(kThreads, RBX_BWD_MINB) k_embed_fm_bwd(const _
 #if RBX_BWD_BULK
     // per warp: 2 x (U*SPW rows of RS floats) staging + 2 x (U*SPW) destination pointers, behind the id staging area
     constexpr int kBulkRows = U * SPW;
-    constexpr bool kBulk = kStaged && kBulkRows <= 32;
+    constexpr bool kBulk = kStaged && kBulkRows <= 32 && (RBX_BWD_BULK == 1 || kSharded != 0);
     unsigned char* bulk_raw = stage_raw + (size_t)kWarps * 2 * wi * 4 + (size_t)kWarps * 2 * 8;
     float* my_gstage = reinterpret_cast<float*>(bulk_raw) + (size_t)warp * 2 * kBulkRows * RS;
     unsigned long long* my_gdst = reinterpret_cast<unsigned long long*>(bulk_raw + (size_t)kWarps * 2 * kBulkRows * RS * 4) + warp * 2 * kBulkRows;
@@ -605,9 +608,15 @@ __global__ void __launch_bounds__(kThreads, RBX_BWD_MINB) k_embed_fm_bwd(const _
 #if RBX_BWD_BULK
                     if (kBulk) {
                         const int slot = sb * kBulkRows + u * SPW + gi;
-                        if (!kRowLr || lig <= LPE) *reinterpret_cast<float4*>(my_gstage + (size_t)slot * RS + 4 * lig) = gr[u];
+                        // mode 2: rows this rank owns go the direct way (into local HBM red.v4 is faster, profiles/r1_variant_sweeps.md)
+                        const bool remote = RBX_BWD_BULK == 1 || !kSharded || (r[u] & ((1 << p.wlog2) - 1)) != p.self_shard;
+                        if (remote) {
+                            if (!kRowLr || lig <= LPE) *reinterpret_cast<float4*>(my_gstage + (size_t)slot * RS + 4 * lig) = gr[u];
+                        } else if (r[u] >= 0 && leader && (!kRowLr || lig <= LPE)) {
+                            RED_GRAD((grad_dst<kSharded, RS>(p, r[u]) + 4 * lig), gr[u]);
+                        }
                         if (lig == 0)
-                            my_gdst[slot] = (r[u] >= 0 && leader) ? (unsigned long long)(uintptr_t)grad_dst<kSharded, RS>(p, r[u]) : 0ull;
+                            my_gdst[slot] = (remote && r[u] >= 0 && leader) ? (unsigned long long)(uintptr_t)grad_dst<kSharded, RS>(p, r[u]) : 0ull;
                         continue;
                     }
 #endif
@@ -941,7 +950,8 @@ int launch_bwd(BwdParams& p, bool staged, int sharded, cudaStream_t st) {
     const int64_t groups = (p.B + SPW - 1) / SPW;
     size_t smem = staged_smem(SPW, p.F, 0) + p.num_smem;
 #if RBX_BWD_BULK
-    if (staged && U * SPW <= 32) smem += (size_t)kWarps * 2 * (U * SPW) * (4 * LPR * 4 + 8);   // gradient-row staging + destinations
+    if (staged && U * SPW <= 32 && (RBX_BWD_BULK == 1 || sharded != 0))
+        smem += (size_t)kWarps * 2 * (U * SPW) * (4 * LPR * 4 + 8);   // gradient-row staging + destinations
 #endif
     if (sharded == 2) {
         if constexpr (LPR >= 2 && LPR <= 8) {
@@ -972,6 +982,9 @@ int launch_bwd(BwdParams& p, bool staged, int sharded, cudaStream_t st) {
 }
 
 inline bool al16(const void* p) { return (uintptr_t)p % 16 == 0; }
+
+// which shard of a row-sharded table this process owns (one process per GPU); -1 = not told
+int g_shard_rank = -1;
 
 // ---------------------------------------------------------------------------------------------
 // shared bodies of the plain and the sharded entry points
@@ -1086,6 +1099,7 @@ int embed_fm_bwd_impl(const char* who, const float* table, const ShardArgs& sh, 
     p.d_fm = d_fm; p.d_lr = d_lr; p.g_table = g_table; p.g_table_lr = g_table_lr; p.g_dense_w = g_dense_w;
     p.g_dense_w_lr = g_dense_w_lr; p.g_lr_bias = g_lr_bias; p.B = B; p.R = R; p.F = F; p.Fn = Fn; p.D = D; p.Ft = n_slots;
     p.wlog2 = 0;
+    p.self_shard = g_shard_rank;
     bool shard_aligned = true, any_g = g_table != nullptr, any_g_lr = g_table_lr != nullptr;
     if (sharded) {
         const int l = shard_log2(sh.world, who);
@@ -1173,6 +1187,12 @@ int embed_fm_bwd_impl(const char* who, const float* table, const ShardArgs& sh, 
 }  // namespace
 
 extern "C" {
+
+int rbx_shard_set_rank(int rank) {
+    if (rank < -1 || rank >= RBX_MAX_WORLD) return rbx_fail(RBX_ERR_ARG, "rbx_shard_set_rank: rank %d outside [-1, %d)", rank, RBX_MAX_WORLD);
+    g_shard_rank = rank;
+    return RBX_OK;
+}
 
 int rbx_embed_fm_fwd(const float* table, const float* table_lr, const int32_t* rows, const int32_t* cat_pos,
                      const int32_t* lr_delta, const float* dense_x, const float* dense_w, const float* dense_w_lr,

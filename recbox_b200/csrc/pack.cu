@@ -19,12 +19,13 @@ struct SplitParams {
     int8_t col_kind[kMaxCols];
 };
 
-// warp <-> sample row, lane <-> column (c = lane, lane + 32, ...): a warp reads 32 consecutive doubles of one row
-// (256 B contiguous) and writes consecutive slots.  kRows rows are in flight per warp (loads of all of them are issued
-// before the first store).  The per-column metadata is staged in shared memory once per CTA: indexing the
-// __grid_constant__ arrays with a lane-dependent column serialises on the constant cache (the first version of this
-// kernel did that, plus a 64-bit division per element, and ran at 0.08 of the HBM roofline).
-constexpr int kSplitRows = 4;
+// A CTA takes blocks of kSplitRows consecutive rows and walks their elements in memory order (thread <-> element, so
+// every lane of every load is busy and a warp reads 256 contiguous bytes); row / column of an element come from one
+// 32-bit division.  The per-column metadata is staged in shared memory once per CTA: indexing the __grid_constant__
+// arrays with a lane-dependent column serialises on the constant cache (the first version of this kernel did that, plus
+// a 64-bit division per element, and ran at 0.08 of the HBM roofline; a warp-per-row version idled 24 of 32 lanes on the
+// second pass over a 40-column row: 0.19).
+constexpr int kSplitRows = 32;
 __global__ void __launch_bounds__(256) k_split_batch(const __grid_constant__ SplitParams p) {
     __shared__ int32_t s_add[kMaxCols];
     __shared__ int16_t s_slot[kMaxCols];
@@ -35,31 +36,24 @@ __global__ void __launch_bounds__(256) k_split_batch(const __grid_constant__ Spl
         s_kind[c] = p.col_kind[c];
     }
     __syncthreads();
-    const int lane = threadIdx.x & 31;
-    const int64_t gw = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    const int64_t nw = (int64_t)gridDim.x * (blockDim.x >> 5);
-    for (int64_t b0 = gw; b0 < p.B; b0 += nw * kSplitRows) {
-        for (int c = lane; c < p.n_cols; c += 32) {
+    const uint32_t n_cols = (uint32_t)p.n_cols;
+    for (int64_t b0 = (int64_t)blockIdx.x * kSplitRows; b0 < p.B; b0 += (int64_t)gridDim.x * kSplitRows) {
+        const uint32_t rows_here = (uint32_t)(p.B - b0 < kSplitRows ? p.B - b0 : kSplitRows);
+        const uint32_t n = rows_here * n_cols;
+#pragma unroll 4
+        for (uint32_t e = threadIdx.x; e < n; e += 256) {
+            const uint32_t r = e / n_cols, c = e - r * n_cols;
             const int kind = s_kind[c];
             if (kind == 0) continue;
-            const int s = s_slot[c], add = s_add[c];
-            double v[kSplitRows];
-#pragma unroll
-            for (int r = 0; r < kSplitRows; ++r) {
-                const int64_t b = b0 + r * nw;
-                v[r] = (b < p.B) ? __ldcs(p.batch + b * p.ld + c) : 0.0;
-            }
-#pragma unroll
-            for (int r = 0; r < kSplitRows; ++r) {
-                const int64_t b = b0 + r * nw;
-                if (b >= p.B) continue;
-                if (kind == 1) {
-                    p.rows[b * p.F + s] = (int32_t)(int64_t)v[r] + add;   // .long(): truncation toward zero
-                } else if (kind == 2) {
-                    p.dense_x[b * p.Fn + s] = (float)v[r];                // .float(): round to nearest
-                } else {
-                    p.label[b] = (float)v[r];
-                }
+            const int64_t b = b0 + r;
+            const double v = __ldcs(p.batch + b * p.ld + c);
+            const int s = s_slot[c];
+            if (kind == 1) {
+                p.rows[b * p.F + s] = (int32_t)(int64_t)v + s_add[c];   // .long(): truncation toward zero
+            } else if (kind == 2) {
+                p.dense_x[b * p.Fn + s] = (float)v;                     // .float(): round to nearest
+            } else {
+                p.label[b] = (float)v;
             }
         }
     }
@@ -150,7 +144,7 @@ int rbx_split_batch_f64(const double* batch, int64_t B, int n_cols, int64_t ld, 
         p.col_kind[c] = (int8_t)k;
         p.col_slot[c] = (int16_t)s;
     }
-    int64_t ctas = (B + 8 * kSplitRows - 1) / (8 * kSplitRows);   // 8 warps per CTA, kSplitRows rows per warp pass
+    int64_t ctas = (B + kSplitRows - 1) / kSplitRows;
     const int64_t cap = (int64_t)rbx_sm_count() * 8;
     if (ctas > cap) ctas = cap;
     k_split_batch<<<(int)ctas, 256, 0, rbx_cast_stream(stream)>>>(p);

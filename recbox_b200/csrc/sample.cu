@@ -43,8 +43,9 @@ __global__ void __launch_bounds__(256) k_sample_negs(int64_t n_queries, int num_
                                                      int64_t* __restrict__ out, int lead, int* __restrict__ gave_up) {
     const int64_t total = n_queries * num_negs;
     const int ld = lead + num_negs;
+    const bool small = total < (1ll << 31);                    // 32-bit division: the 64-bit one costs more than the draw
     for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t qi = e / num_negs;
+        const int64_t qi = small ? (int64_t)((uint32_t)e / (uint32_t)num_negs) : e / num_negs;
         const int j = (int)(e - qi * num_negs);
         int64_t id = draw(seed, (uint64_t)e, 0, num_items);
         if (pos_ptr) {

@@ -16,7 +16,8 @@
 //                         bitonic sort (2048 keys per round) and publishes the new tau.
 // Item chunks grow geometrically (4096, 8192, ... up to `chunk`) so that the number of survivors per pass stays ~k even
 // while tau is still loose.  Everything is stream-ordered; the host never reads a count.
-// Exactness: scores are plain fp32 FMA chains over d = 0..D-1 (no tf32 / bf16), ties go to the smaller item index.
+// Accuracy: fp32 level -- the default pass A forms every product as a 3xTF32 split on the tensor cores with fp32 accumulators
+// (k_ip_filter_mma); RBX_TOPK_MMA=0 builds the plain fp32 FMA-chain kernel.  Ties go to the smaller item index.
 #include "rbx_common.cuh"
 
 namespace {
@@ -137,6 +138,124 @@ __global__ void __launch_bounds__(kT, 2) k_ip_filter(const __grid_constant__ IpP
     }
     cp_async_wait<0>();
 }
+
+// ---------------------------------------------------------------------------------------------
+// Tensor-core form of pass A (default, RBX_TOPK_MMA=1): the same 128 x 128 tile, cp.async pipeline and filter epilogue,
+// with the products on the tensor cores in "3xTF32": x = hi + lo with hi = tf32(x), lo = tf32(x - hi), and
+//   <a, b> ~= sum a_lo*b_hi + a_hi*b_lo + a_hi*b_hi      (fp32 accumulators; the dropped a_lo*b_lo term is ~2^-22 relative)
+// which keeps fp32-level accuracy (the score matrix is a true GEMM: [U,D] x [D,N]).  mma.sync.m16n8k8 tf32 fragments:
+//   A (16x8, row): a0 (g, t) a1 (g+8, t) a2 (g, t+4) a3 (g+8, t+4);  B (8x8, col): b0 (k=t, n=g) b1 (k=t+4, n=g);
+//   C (16x8): c0 (g, 2t) c1 (g, 2t+1) c2 (g+8, 2t) c3 (g+8, 2t+1)          with g = lane >> 2, t = lane & 3.
+// Both operand tiles are row-major [row][k] in shared memory with a row stride of D + 4 floats, so a fragment load is a
+// conflict-free LDS.32 (bank = 4 g + t when (D + 4) mod 32 is an odd multiple of 4).  8 warps = 2 (users) x 4 (items),
+// a warp owns 64 x 32 = 4 x 4 mma tiles.  The kernel is written against the legacy warp-level mma; a tcgen05 / TMEM
+// version is the next step.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t to_tf32(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
+    hi = to_tf32(x);
+    lo = to_tf32(x - __uint_as_float(hi));
+}
+__device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+
+__global__ void __launch_bounds__(kT, 2) k_ip_filter_mma(const __grid_constant__ IpParams p) {
+    extern __shared__ __align__(16) float smem[];
+    const int D = p.D, LD = D + 4, KE = (D + 7) & ~7;
+    float* sA = smem;
+    float* sTau = sA + 3 * TM * LD;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int wm = warp >> 2, wn = warp & 3, g = lane >> 2, t = lane & 3;
+    const int64_t m_base = (int64_t)blockIdx.y * TM;
+    const int64_t n_tiles = (p.n1 - p.n0 + TN - 1) / TN;
+
+    // the 4 padding columns of every tile row are read when D % 8 == 4: keep them zero (cp.async never writes them)
+    for (int r = tid; r < 3 * TM; r += kT) *reinterpret_cast<float4*>(sA + r * LD + D) = make_float4(0.f, 0.f, 0.f, 0.f);
+    load_tile(sA, p.q, m_base, p.U, D, LD);
+    if (tid < TM) sTau[tid] = (m_base + tid < p.U) ? __ldcg(p.tau + m_base + tid) : __int_as_float(0x7f800000);
+    int64_t tile = blockIdx.x;
+    if (tile < n_tiles) load_tile(sA + TM * LD, p.items, p.n0 + tile * TN, p.n1, D, LD);
+    cp_async_commit();
+
+    int buf = 0;
+    for (; tile < n_tiles; tile += gridDim.x, buf ^= 1) {
+        const int64_t tn = tile + gridDim.x;
+        if (tn < n_tiles) load_tile(sA + (2 - buf) * TM * LD, p.items, p.n0 + tn * TN, p.n1, D, LD);
+        cp_async_commit();
+        cp_async_wait<1>();
+        __syncthreads();
+
+        float acc[4][4][4];
+#pragma unroll
+        for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+            for (int ni = 0; ni < 4; ++ni)
+#pragma unroll
+                for (int x = 0; x < 4; ++x) acc[mi][ni][x] = 0.f;
+        const float* pa = sA + (wm * 64 + g) * LD + t;
+        const float* pb = sA + (1 + buf) * TM * LD + (wn * 32 + g) * LD + t;
+        for (int k0 = 0; k0 < KE; k0 += 8) {
+            uint32_t ah[4][4], al[4][4];
+#pragma unroll
+            for (int mi = 0; mi < 4; ++mi) {
+                const float* r0 = pa + mi * 16 * LD + k0;
+                split_tf32(r0[0], ah[mi][0], al[mi][0]);
+                split_tf32(r0[8 * LD], ah[mi][1], al[mi][1]);
+                split_tf32(r0[4], ah[mi][2], al[mi][2]);
+                split_tf32(r0[8 * LD + 4], ah[mi][3], al[mi][3]);
+            }
+#pragma unroll
+            for (int ni = 0; ni < 4; ++ni) {
+                const float* c0 = pb + ni * 8 * LD + k0;
+                uint32_t bh[2], bl[2];
+                split_tf32(c0[0], bh[0], bl[0]);
+                split_tf32(c0[4], bh[1], bl[1]);
+#pragma unroll
+                for (int mi = 0; mi < 4; ++mi) {
+                    mma_tf32(acc[mi][ni], al[mi], bh);          // small terms first
+                    mma_tf32(acc[mi][ni], ah[mi], bl);
+                    mma_tf32(acc[mi][ni], ah[mi], bh);
+                }
+            }
+        }
+        // epilogue: keep what beats the user's current k-th best
+        const int64_t n_base = p.n0 + tile * TN;
+#pragma unroll
+        for (int mi = 0; mi < 4; ++mi) {
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int m = wm * 64 + mi * 16 + g + 8 * h;
+                const float tau = sTau[m];
+                const int64_t u = m_base + m;
+#pragma unroll
+                for (int ni = 0; ni < 4; ++ni) {
+#pragma unroll
+                    for (int x = 0; x < 2; ++x) {
+                        const float sc = acc[mi][ni][2 * h + x];
+                        const int64_t n = n_base + wn * 32 + ni * 8 + 2 * t + x;
+                        if (sc > tau && n < p.n1) {
+                            const int pos = atomicAdd(p.count + u, 1);
+                            if (pos < p.qcap) p.queue[(size_t)u * p.qcap + pos] = make_key(sc, (uint32_t)n);
+                        }
+                    }
+                }
+            }
+        }
+        __syncthreads();
+    }
+    cp_async_wait<0>();
+}
+
+#ifndef RBX_TOPK_MMA
+#define RBX_TOPK_MMA 1      // 1: k_ip_filter_mma (3xTF32 on the tensor cores); 0: k_ip_filter (plain fp32 FMA chains)
+#endif
 
 // descending bitonic sort of n (power of two) keys in shared memory, whole CTA
 __device__ void bitonic_desc(unsigned long long* s, int n) {
@@ -336,7 +455,14 @@ int rbx_topk_ip(const float* q, const float* items, int64_t U, int64_t N, int D,
     RBX_LAUNCH_CHECK(who);
 
     const size_t smem = ((size_t)3 * TM * (D + 4) + TM) * 4;
-    cudaError_t e = cudaFuncSetAttribute(k_ip_filter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+#if RBX_TOPK_MMA
+    const auto kernel_a = k_ip_filter_mma;
+    (void)&k_ip_filter;
+#else
+    const auto kernel_a = k_ip_filter;
+    (void)&k_ip_filter_mma;
+#endif
+    cudaError_t e = cudaFuncSetAttribute(kernel_a, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return rbx_fail(RBX_ERR_CUDA, "%s: %s", who, cudaGetErrorString(e));
     const int64_t UT = (U + TM - 1) / TM;
     RBX_REQUIRE(UT <= 65535, "%s: U too large for one call", who);
@@ -351,7 +477,7 @@ int rbx_topk_ip(const float* q, const float* items, int64_t U, int64_t N, int D,
         int64_t gx = resident / UT;
         if (gx < 1) gx = 1;
         if (gx > tiles) gx = tiles;
-        k_ip_filter<<<dim3((unsigned)gx, (unsigned)UT), kT, smem, st>>>(p);
+        kernel_a<<<dim3((unsigned)gx, (unsigned)UT), kT, smem, st>>>(p);
         RBX_LAUNCH_CHECK(who);
         k_select<<<(unsigned)U, kT, 0, st>>>(t.R, t.queue, t.count, t.tau, chunk, Kp, k);
         RBX_LAUNCH_CHECK(who);

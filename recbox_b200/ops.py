@@ -300,6 +300,11 @@ def interact_bwd(E, dout, mode):
 
 
 # ------------------------------------------------------------------------------------------- (e)
+def shard_set_rank(rank):
+    """Tell the library which shard this process owns (hint only; see rbx_shard_set_rank)."""
+    _call("rbx_shard_set_rank", int(rank))
+
+
 def shard_route(rows, world):
     """flat int32 global rows -> (send local rows grouped by owner, pos, counts[world] int32 DEVICE)."""
     flat = rows.reshape(-1)

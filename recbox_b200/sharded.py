@@ -155,6 +155,8 @@ class ShardedEmbeddingFM(object):
         if kern is None:
             from . import ops as kern
         self.kern = kern
+        if mode == "peer" and hasattr(kern, "shard_set_rank"):
+            kern.shard_set_rank(self.rank)          # hint: which shard's rows are local (see rbx_shard_set_rank)
         self.alloc = alloc if (dist.is_initialized() and dist.get_world_size(group) > 1) else "ipc"
         self.cap = shard_capacity(self.R, self.world)
         self.n_local = local_rows(self.R, self.world, self.rank)

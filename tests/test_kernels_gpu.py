@@ -324,6 +324,21 @@ def test_split_batch_and_pack_columns():
     assert torch.equal(ops.pack_columns(dcols, as_rows=False), dense)
 
 
+@pytest.mark.parametrize("B", [1, 31, 33, 70001])
+def test_split_batch_ragged_and_strided(B):
+    """Row counts around the 32-row block size, an ignored column, and a batch that is a column-slice view (ld > n_cols)."""
+    ops = _ops()
+    rng = np.random.default_rng(B)
+    wide = np.concatenate([rng.integers(0, 50, (B, 3)).astype(np.float64), rng.standard_normal((B, 2)),
+                           rng.integers(0, 2, (B, 1)).astype(np.float64), rng.standard_normal((B, 4))], 1)
+    Md = torch.from_numpy(wide).to(DEV)[:, :7]                      # stride(0) = 10, 7 visible columns
+    kinds, slots = [1, 1, 0, 2, 2, 3, 0], [1, 0, 0, 0, 1, 0, 0]
+    rows, dense, label = ops.split_batch(Md, kinds, slots, [100, 200], 2, 2)
+    assert np.array_equal(rows.cpu().numpy(), np.stack([wide[:, 1] + 100, wide[:, 0] + 200], 1).astype(np.int32))
+    assert np.array_equal(dense.cpu().numpy(), wide[:, 3:5].astype(np.float32))
+    assert np.array_equal(label.cpu().numpy(), wide[:, 5].astype(np.float32))
+
+
 # --------------------------------------------------------------------------------------- a12
 def test_clip_and_adam():
     ops = _ops()

@@ -27,6 +27,7 @@ VARIANTS = {
     "bwd_u8_b3": ["RBX_BWD_U=8", "RBX_BWD_MINB=3"],
     "bwd_u2_b6": ["RBX_BWD_U=2", "RBX_BWD_MINB=6"],
     "bulk": ["RBX_BWD_BULK=1"],
+    "bulk_remote": ["RBX_BWD_BULK=2"],
     "bulk_b3": ["RBX_BWD_BULK=1", "RBX_BWD_MINB=3"],
     "bulk_u2": ["RBX_BWD_BULK=1", "RBX_BWD_U=2", "RBX_BWD_MINB=5"],
 }
