@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Every kernel of the C ABI against the HBM roofline on one B200, at the sizes of BASELINE.json's configs
-(SURVEY.md section 8d): achieved = ALGORITHMIC bytes / CUDA-event time (median of 15 reps, a 256 MB memset
-flushes the 126 MB L2 between reps), peak = MEASURED_PEAKS.json hbm_gbs.
+(SURVEY.md section 8d): achieved = ALGORITHMIC bytes / CUDA-event time (median of 15 reps, a 256 MB read flushes the
+126 MB L2 between reps), peak = MEASURED_PEAKS.json hbm_gbs.
 
   python tools/kernel_rooflines.py [tag]      -> gpurun_out/<tag>_kernels.json + a markdown table on stdout
 
@@ -27,14 +27,17 @@ try:
     peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
 except Exception:
     pass
-flush = torch.empty(64 * 1024 * 1024, device=dev)
+flush = torch.zeros(64 * 1024 * 1024, device=dev)
 results = []
 
 
 def timeit(fn, reps=15):
+    """L2 flush = READING 256 MB (torch.sum): it evicts the previous rep's lines and leaves the L2 full of CLEAN lines.
+    (Flushing with a memset leaves ~126 MB of dirty lines whose write-back is then billed to the kernel under test:
+    that cost small kernels 10-20 us in the r1u / r1v tables.)"""
     ts = []
     for _ in range(reps + 3):
-        flush.zero_()
+        flush.sum()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
         fn()
@@ -180,5 +183,5 @@ case("a11", "rbx_scatter_add_rows", "3 x [1024,200] ids, 1M-row table D=64", n *
 
 os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
 with open(os.path.join(ROOT, "gpurun_out", tag + "_kernels.json"), "w") as f:
-    json.dump({"peak_gbs": peak, "timing": "CUDA events, median of 15, L2 flushed by a 256 MB memset between reps",
+    json.dump({"peak_gbs": peak, "timing": "CUDA events, median of 15, L2 flushed by a 256 MB read (torch.sum) between reps",
                "kernels": results}, f, indent=1)
