@@ -405,6 +405,18 @@ int rbx_unique_ids_i32(const int32_t* ids /*DEVICE [n]*/, int64_t n, int64_t voc
                        rbx_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
+ * f4  power sums over the fields: P[b,k-1,:] = sum_f E[b,f,:]^k, k = 1..order (order <= 5)
+ * The single pass over [B,F,D] behind InteractionMachine.forward
+ * (ranking/pytorch/layers/interactions/interaction_machine.py:44-70: p_k = (Q *= X).sum(dim=1), `order` passes
+ * and `order` temporaries in the reference); the polynomial combinations of p_1..p_order (:29-42) act on [B,D].
+ * Backward: dE[b,f,:] = sum_k k * E[b,f,:]^(k-1) * dP[b,k-1,:].
+ * ------------------------------------------------------------------------------------------ */
+int rbx_power_sums_fwd(const float* E /*DEVICE [B,F,D]*/, float* P /*DEVICE [B,order,D]*/,
+                       int64_t B, int F, int D, int order, rbx_stream_t stream);
+int rbx_power_sums_bwd(const float* E, const float* dP /*DEVICE [B,order,D]*/, float* dE /*DEVICE [B,F,D]*/,
+                       int64_t B, int F, int D, int order, rbx_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
  * f2  per-epoch negative sampling (csrc/sample.cu)
  * Replaces sampling_block + the hstack of TrainGenerator.negative_sampling
  * (recbox/matching/pytorch/dataloaders/h5_generator.py:72-95, 144-181): uniform draws with

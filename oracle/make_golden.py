@@ -355,6 +355,25 @@ def golden_collate_unique():
     npz("collate_unique", **out)
 
 
+def golden_interaction_machine(L):
+    """f4: the reference's InteractionMachine (orders 1..5, with and without batch norm) forward + backward."""
+    g = torch.Generator().manual_seed(55)
+    out = {}
+    for order in (1, 2, 3, 4, 5):
+        for bn in (False, True):
+            torch.manual_seed(700 + order)
+            m = L.InteractionMachine(8, order=order, batch_norm=bn)
+            X = (torch.randn(23, 6, 8, generator=g) * 0.7).requires_grad_(True)
+            w = torch.randn(23, 1, generator=g)
+            y = m(X)
+            (y * w).sum().backward()
+            tag = "o%d_bn%d." % (order, int(bn))
+            out[tag + "X"], out[tag + "w"], out[tag + "y"], out[tag + "dX"] = X.detach(), w, y.detach(), X.grad
+            out.update({tag + "sd." + k: v.clone() for k, v in m.state_dict().items()})
+            out.update({tag + "grad." + k: p.grad.clone() for k, p in m.named_parameters()})
+    npz("interaction_machine", **out)
+
+
 class _NumpyFlatIP(object):
     """Stand-in for faiss.IndexFlatIP (faiss is absent from this image): exact float32 inner products, descending,
     (-3.4028235e38, -1) padding -- enough for the reference's FaissIndex / evaluate_block to run unmodified."""
@@ -428,6 +447,8 @@ def main(only=None):
         return golden_collate_unique()
     if only == "retrieval":
         return golden_retrieval()
+    if only == "interaction_machine":
+        return golden_interaction_machine(L)
     with tempfile.TemporaryDirectory() as tmp:
         golden_interaction(L)
         golden_pooling(L)
@@ -442,6 +463,7 @@ def main(only=None):
         golden_config1(L, tmp)
     golden_collate_unique()
     golden_retrieval()
+    golden_interaction_machine(L)
 
 
 if __name__ == "__main__":

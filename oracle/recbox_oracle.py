@@ -294,6 +294,36 @@ def collate_unique_reference(item_indexes):
 
 
 # --------------------------------------------------------------------------------------------
+# (f4)  InteractionMachine
+# --------------------------------------------------------------------------------------------
+def power_sums(E, order):
+    """p_k = (X ** k).sum(dim=1) as interaction_machine.py:47-65 forms them (Q = Q * X, then Q.sum(dim=1)) -> [B, order, D]."""
+    out, Q = [], E
+    for k in range(order):
+        if k:
+            Q = Q * E
+        out.append(Q.sum(dim=1))
+    return torch.stack(out, dim=1)
+
+
+def interaction_machine(E, order, fc_weight, fc_bias):
+    """InteractionMachine.forward without batch norm (ranking/pytorch/layers/interactions/interaction_machine.py:29-70)."""
+    P = power_sums(E, order)
+    p = [P[:, k] for k in range(order)]
+    out = [p[0]]
+    if order >= 2:
+        out.append((p[0].pow(2) - p[1]) / 2)
+    if order >= 3:
+        out.append((p[0].pow(3) - 3 * p[0] * p[1] + 2 * p[2]) / 6)
+    if order >= 4:
+        out.append((p[0].pow(4) - 6 * p[0].pow(2) * p[1] + 3 * p[1].pow(2) + 8 * p[0] * p[2] - 6 * p[3]) / 24)
+    if order == 5:
+        out.append((p[0].pow(5) - 10 * p[0].pow(3) * p[1] + 20 * p[0].pow(2) * p[2] - 30 * p[0] * p[3]
+                    - 20 * p[1] * p[2] + 15 * p[0] * p[1].pow(2) + 24 * p[4]) / 120)
+    return torch.nn.functional.linear(torch.cat(out, dim=-1), fc_weight, fc_bias)
+
+
+# --------------------------------------------------------------------------------------------
 # (f2)  negative sampling
 # --------------------------------------------------------------------------------------------
 def sampling_block(num_items, block_query_indexes, num_negs, user2items_dict, ignore_pos_items=False, seed=None):

@@ -25,7 +25,7 @@ from ._lib import RbxError, build, load  # noqa: F401
 _RANKING = {"FeatureEmbedding": "FeatureEmbedding", "FeatureEmbeddingDict": "FeatureEmbeddingDict",
             "InnerProductInteraction": "InnerProductInteraction", "LogisticRegression": "LogisticRegression",
             "FactorizationMachine": "FactorizationMachine", "MaskedAveragePooling": "MaskedAveragePooling",
-            "MaskedSumPooling": "MaskedSumPooling"}
+            "MaskedSumPooling": "MaskedSumPooling", "InteractionMachine": "InteractionMachine"}
 _CORE = {"EmbeddingLayer": "EmbeddingLayer", "EmbeddingDictLayer": "EmbeddingDictLayer",
          "MaskedAveragePooling": "CoreMaskedAveragePooling", "MaskedSumPooling": "CoreMaskedSumPooling"}
 _TARGETS = (("recbox.ranking.pytorch.layers", _RANKING), ("fuxictr.pytorch.layers", _RANKING),

@@ -118,6 +118,8 @@ SIGNATURES = {
     "rbx_unique_ws_bytes": [_I64],
     "rbx_unique_ids_i64": [_P, _I64, _I64, _P, _c.c_size_t, _P, _P, _P, _P, _P],
     "rbx_unique_ids_i32": [_P, _I64, _I64, _P, _c.c_size_t, _P, _P, _P, _P, _P],
+    "rbx_power_sums_fwd": [_P, _P, _I64, _I, _I, _I, _P],
+    "rbx_power_sums_bwd": [_P, _P, _P, _I64, _I, _I, _I, _P],
     "rbx_sample_negatives": [_I64, _I, _I64, _c.c_uint64, _P, _P, _P, _P, _P, _P, _P],
     "rbx_topk_ws_bytes": [_I64, _I, _I64],
     "rbx_topk_ip": [_P, _P, _I64, _I64, _I, _I, _I64, _P, _P, _P, _c.c_size_t, _P],

@@ -446,6 +446,111 @@ inline int warp_grid(K kernel, int wpc, size_t smem, int64_t B) {
     return capped_grid((B + wpc - 1) / wpc, per_sm);
 }
 
+// ------------------------------------------------------------------ f4: power sums over the fields (InteractionMachine)
+// P[b,k-1,:] = sum_f e_f^k for k = 1..order (order <= 5), the only pass over [B,F,D] that InteractionMachine.forward
+// (ranking/pytorch/layers/interactions/interaction_machine.py:44-70) needs: the reference walks E `order` times and
+// materialises Q = Q * X each time.  Backward: dE[b,f,:] = sum_k k * e_f^(k-1) * dP[b,k-1,:]  (one read of E, one write).
+constexpr int kMaxOrder = 5;
+
+template <int LPR>
+__global__ void __launch_bounds__(kThreads) k_power_sums_fwd_vec(const float* __restrict__ E, float* __restrict__ P, int64_t B,
+                                                                int F, int order) {
+    constexpr int D = 4 * LPR, SPW = 32 / LPR;
+    const int lane = threadIdx.x & 31, lig = lane & (LPR - 1), gi = lane / LPR;
+    const int64_t warp0 = (int64_t)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
+    const int64_t nwarps = (int64_t)gridDim.x * (kThreads / 32);
+    for (int64_t base = warp0 * SPW; base < B; base += nwarps * SPW) {
+        const int64_t b = base + gi;
+        if (b >= B) continue;
+        float4 acc[kMaxOrder];
+#pragma unroll
+        for (int k = 0; k < kMaxOrder; ++k) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+        const float* e = E + (size_t)b * F * D + 4 * lig;
+#pragma unroll 4
+        for (int f = 0; f < F; ++f) {
+            const float4 v = ld_stream_f4(e + (size_t)f * D);
+            float4 q = v;
+#pragma unroll
+            for (int k = 0; k < kMaxOrder; ++k) {
+                if (k < order) {
+                    acc[k] = f4_add(acc[k], q);
+                    q = f4_mul(q, v);
+                }
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < kMaxOrder; ++k)
+            if (k < order) *reinterpret_cast<float4*>(P + ((size_t)b * order + k) * D + 4 * lig) = acc[k];
+    }
+}
+
+template <int LPR>
+__global__ void __launch_bounds__(kThreads) k_power_sums_bwd_vec(const float* __restrict__ E, const float* __restrict__ dP,
+                                                                float* __restrict__ dE, int64_t B, int F, int order) {
+    constexpr int D = 4 * LPR, SPW = 32 / LPR;
+    const int lane = threadIdx.x & 31, lig = lane & (LPR - 1), gi = lane / LPR;
+    const int64_t warp0 = (int64_t)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
+    const int64_t nwarps = (int64_t)gridDim.x * (kThreads / 32);
+    for (int64_t base = warp0 * SPW; base < B; base += nwarps * SPW) {
+        const int64_t b = base + gi;
+        if (b >= B) continue;
+        float4 g[kMaxOrder];                              // k * dP_k
+#pragma unroll
+        for (int k = 0; k < kMaxOrder; ++k) {
+            g[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (k < order) g[k] = f4_scale(ld_row_f4(dP + ((size_t)b * order + k) * D + 4 * lig), (float)(k + 1));
+        }
+        const float* e = E + (size_t)b * F * D + 4 * lig;
+        float* de = dE + (size_t)b * F * D + 4 * lig;
+#pragma unroll 4
+        for (int f = 0; f < F; ++f) {
+            const float4 v = ld_stream_f4(e + (size_t)f * D);
+            float4 r = g[0], q = v;
+#pragma unroll
+            for (int k = 1; k < kMaxOrder; ++k) {
+                if (k < order) {
+                    r = f4_fma4(g[k], q, r);
+                    q = f4_mul(q, v);
+                }
+            }
+            st_stream_f4(de + (size_t)f * D, r);
+        }
+    }
+}
+
+// any D: warp per sample, lane owns columns d, d + 32, ...
+__global__ void __launch_bounds__(kThreads) k_power_sums_any(const float* __restrict__ E, const float* __restrict__ dP,
+                                                            float* __restrict__ out, int64_t B, int F, int D, int order, int bwd) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp0 = (int64_t)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
+    const int64_t nwarps = (int64_t)gridDim.x * (kThreads / 32);
+    for (int64_t b = warp0; b < B; b += nwarps) {
+        for (int d = lane; d < D; d += 32) {
+            float acc[kMaxOrder];
+#pragma unroll
+            for (int k = 0; k < kMaxOrder; ++k) acc[k] = (bwd && k < order) ? (k + 1) * __ldg(dP + ((size_t)b * order + k) * D + d) : 0.f;
+            for (int f = 0; f < F; ++f) {
+                const size_t o = ((size_t)b * F + f) * D + d;
+                const float v = __ldg(E + o);
+                float q = v, r = acc[0];
+#pragma unroll
+                for (int k = 0; k < kMaxOrder; ++k) {
+                    if (k < order) {
+                        if (!bwd) acc[k] += q;
+                        else if (k >= 1) r = fmaf(acc[k], q, r);
+                        if (!bwd || k >= 1) q *= v;
+                    }
+                }
+                if (bwd) out[o] = r;
+            }
+            if (!bwd)
+#pragma unroll
+                for (int k = 0; k < kMaxOrder; ++k)
+                    if (k < order) out[((size_t)b * order + k) * D + d] = acc[k];
+        }
+    }
+}
+
 inline bool vec_ok(int D, const void* a, const void* b, const void* c) {
     return D % 4 == 0 && D <= 128 && (D & (D - 1)) == 0 && (uintptr_t)a % 16 == 0 && (uintptr_t)b % 16 == 0 &&
            (uintptr_t)c % 16 == 0;
@@ -562,6 +667,38 @@ int rbx_interact_bwd(const float* E, const float* dout, float* dE, int64_t B, in
         RBX_REQUIRE(smem <= 200 * 1024, "%s: F=%d D=%d needs %zu B shared memory", who, F, D, smem);
         if (smem > 48 * 1024) cudaFuncSetAttribute(k_pairs_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         k_pairs_bwd<<<capped_grid(B, 6), kThreads, smem, st>>>(E, dout, dE, B, F, D, mode);
+    }
+    RBX_LAUNCH_CHECK(who);
+    return RBX_OK;
+}
+
+int rbx_power_sums_fwd(const float* E, float* P, int64_t B, int F, int D, int order, rbx_stream_t stream) {
+    const char* who = "rbx_power_sums_fwd";
+    RBX_REQUIRE(B >= 0 && F >= 1 && D >= 1 && D <= RBX_MAX_DIM, "%s: bad size", who);
+    RBX_REQUIRE(order >= 1 && order <= kMaxOrder, "%s: order=%d is not supported", who, order);
+    if (B == 0) return RBX_OK;
+    RBX_REQUIRE(E && P, "%s: null pointer", who);
+    cudaStream_t st = rbx_cast_stream(stream);
+    if (vec_ok(D, E, P, nullptr)) {
+        RBX_DISPATCH_LPR(D, (k_power_sums_fwd_vec<LPR><<<capped_grid((B + 32 / LPR * 8 - 1) / (32 / LPR * 8), 8), kThreads, 0, st>>>(E, P, B, F, order)));
+    } else {
+        k_power_sums_any<<<capped_grid((B + 7) / 8, 8), kThreads, 0, st>>>(E, nullptr, P, B, F, D, order, 0);
+    }
+    RBX_LAUNCH_CHECK(who);
+    return RBX_OK;
+}
+
+int rbx_power_sums_bwd(const float* E, const float* dP, float* dE, int64_t B, int F, int D, int order, rbx_stream_t stream) {
+    const char* who = "rbx_power_sums_bwd";
+    RBX_REQUIRE(B >= 0 && F >= 1 && D >= 1 && D <= RBX_MAX_DIM, "%s: bad size", who);
+    RBX_REQUIRE(order >= 1 && order <= kMaxOrder, "%s: order=%d is not supported", who, order);
+    if (B == 0) return RBX_OK;
+    RBX_REQUIRE(E && dP && dE, "%s: null pointer", who);
+    cudaStream_t st = rbx_cast_stream(stream);
+    if (vec_ok(D, E, dP, dE)) {
+        RBX_DISPATCH_LPR(D, (k_power_sums_bwd_vec<LPR><<<capped_grid((B + 32 / LPR * 8 - 1) / (32 / LPR * 8), 8), kThreads, 0, st>>>(E, dP, dE, B, F, order)));
+    } else {
+        k_power_sums_any<<<capped_grid((B + 7) / 8, 8), kThreads, 0, st>>>(E, dP, dE, B, F, D, order, 1);
     }
     RBX_LAUNCH_CHECK(who);
     return RBX_OK;

@@ -339,6 +339,19 @@ class _InteractFn(torch.autograd.Function):
         return ops.interact_bwd(E, g.contiguous(), ctx.mode), None
 
 
+class _PowerSumFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, E, order):
+        E = E.contiguous()
+        ctx.save_for_backward(E)
+        return ops.power_sums_fwd(E, order)
+
+    @staticmethod
+    def backward(ctx, g):
+        (E,) = ctx.saved_tensors
+        return ops.power_sums_bwd(E, g.contiguous()), None
+
+
 class _RowDotFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, u, v):
@@ -866,6 +879,55 @@ class InnerProductInteraction(nn.Module):
         if not feature_emb.is_cuda:
             raise RbxError("recbox_b200 layers have no CPU path")
         return _InteractFn.apply(feature_emb, ops.MODES[self._output_type])
+
+
+class InteractionMachine(nn.Module):
+    """ranking/pytorch/layers/interactions/interaction_machine.py:20-70 (same ctor, `bn` / `fc` parameter names).  The
+    power sums p_k = sum_f e_f^k come from ONE pass over [B,F,D] (rbx_power_sums_fwd) instead of `order` passes with
+    `order` [B,F,D] temporaries; the Newton-identity polynomials of :29-42 act on the [B,D] sums."""
+
+    def __init__(self, embedding_dim, order=2, batch_norm=False):
+        super(InteractionMachine, self).__init__()
+        assert order < 6, "order={} is not supported.".format(order)
+        self.order = order
+        self.bn = nn.BatchNorm1d(embedding_dim * order) if batch_norm else None
+        self.fc = nn.Linear(order * embedding_dim, 1)
+
+    def second_order(self, p1, p2):
+        return (p1.pow(2) - p2) / 2
+
+    def third_order(self, p1, p2, p3):
+        return (p1.pow(3) - 3 * p1 * p2 + 2 * p3) / 6
+
+    def fourth_order(self, p1, p2, p3, p4):
+        return (p1.pow(4) - 6 * p1.pow(2) * p2 + 3 * p2.pow(2)
+                + 8 * p1 * p3 - 6 * p4) / 24
+
+    def fifth_order(self, p1, p2, p3, p4, p5):
+        return (p1.pow(5) - 10 * p1.pow(3) * p2 + 20 * p1.pow(2) * p3 - 30 * p1 * p4
+                - 20 * p2 * p3 + 15 * p1 * p2.pow(2) + 24 * p5) / 120
+
+    def forward(self, X):
+        if not X.is_cuda:
+            raise RbxError("recbox_b200 layers have no CPU path")
+        if self.order < 1:
+            out = X.new_zeros((X.shape[0], 0))
+        else:
+            P = _PowerSumFn.apply(X, self.order)
+            p = [P[:, k, :] for k in range(self.order)]
+            out = [p[0]]
+            if self.order >= 2:
+                out.append(self.second_order(p[0], p[1]))
+            if self.order >= 3:
+                out.append(self.third_order(p[0], p[1], p[2]))
+            if self.order >= 4:
+                out.append(self.fourth_order(p[0], p[1], p[2], p[3]))
+            if self.order == 5:
+                out.append(self.fifth_order(p[0], p[1], p[2], p[3], p[4]))
+            out = torch.cat(out, dim=-1)
+        if self.bn is not None:
+            out = self.bn(out)
+        return self.fc(out)
 
 
 class LogisticRegression(nn.Module):

@@ -433,6 +433,22 @@ def unique_ids(ids, vocab, want_first=True, want_inverse=True, sync=True):
     return uniq[:U], (first[:U] if want_first else None), inverse
 
 
+# ------------------------------------------------------------------------------------------- f4
+def power_sums_fwd(E, order):
+    """E [B,F,D] -> P [B,order,D], P[:,k-1] = (E ** k).sum(1)  (InteractionMachine's p_1..p_order in one pass)."""
+    B, F, D = E.shape
+    P = torch.empty((B, order, D), dtype=F32, device=E.device)
+    _call("rbx_power_sums_fwd", _p(E, F32, "E"), _p(P), B, F, D, int(order), _stream())
+    return P
+
+
+def power_sums_bwd(E, dP):
+    B, F, D = E.shape
+    dE = torch.empty_like(E)
+    _call("rbx_power_sums_bwd", _p(E, F32, "E"), _p(dP, F32, "dP"), _p(dE), B, F, D, dP.shape[1], _stream())
+    return dE
+
+
 # ------------------------------------------------------------------------------------------- f2
 def sample_negatives(n_queries, num_negs, num_items, seed, pos=None, user_of_query=None, pos_ptr=None, pos_items=None,
                      device=None):

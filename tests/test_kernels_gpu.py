@@ -273,6 +273,26 @@ def test_interact_pairs_many_samples_per_warp(mode):
     assert_close(dE, E.grad, atol_scale=2e-5, what=name + " bwd")
 
 
+@pytest.mark.parametrize("order", [1, 2, 5])
+@pytest.mark.parametrize("F,D", [(39, 16), (6, 8), (3, 10), (5, 128), (2, 4), (7, 1)])
+def test_power_sums(F, D, order):
+    """f4: rbx_power_sums_fwd/bwd against the oracle's Q = Q * X; Q.sum(1) chain and its autograd."""
+    ops = _ops()
+    g = torch.Generator().manual_seed(F * D + order)
+    B = 203
+    E = (torch.randn(B, F, D, generator=g) * 0.8).requires_grad_(True)
+    ref = oracle.power_sums(E, order)
+    P = ops.power_sums_fwd(E.detach().to(DEV), order)
+    assert_close(P, ref, what="power sums")
+    dP = torch.randn(B, order, D, generator=g)
+    (ref * dP).sum().backward()
+    dE = ops.power_sums_bwd(E.detach().to(DEV), dP.to(DEV))
+    assert_close(dE, E.grad, atol_scale=2e-5, what="power sums bwd")
+    from recbox_b200 import RbxError
+    with pytest.raises(RbxError):
+        ops.power_sums_fwd(E.detach().to(DEV), 6)
+
+
 # ------------------------------------------------------------------------------------ (e) shard
 @pytest.mark.parametrize("world", [1, 2, 3, 8])
 @pytest.mark.parametrize("N", [1, 255, 2048, 2049, 100003])

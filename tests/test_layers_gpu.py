@@ -287,3 +287,21 @@ def test_module_to_and_deepcopy_keep_the_fused_storage():
         emb2.embedding_layer.embedding_layers["C1"].weight.mul_(2.0)
     assert torch.equal(emb(X).cpu(), g["E"])                      # the copy owns its own table
     assert not torch.equal(emb2(X).cpu(), g["E"])
+
+
+@pytest.mark.parametrize("bn", [False, True])
+@pytest.mark.parametrize("order", [1, 2, 3, 4, 5])
+def test_interaction_machine_matches_reference(order, bn):
+    """f4: layers.InteractionMachine (one-pass power sums) against the reference module's forward / backward."""
+    g = load("interaction_machine")
+    tag = "o%d_bn%d." % (order, int(bn))
+    m = layers.InteractionMachine(8, order=order, batch_norm=bn)
+    m.load_state_dict(_sub(g, tag + "sd."))
+    m.to(DEV).train()
+    X = g[tag + "X"].to(DEV).requires_grad_(True)
+    y = m(X)
+    assert_close(y, g[tag + "y"], atol_scale=2e-5, what="y")
+    (y * g[tag + "w"].to(DEV)).sum().backward()
+    assert_close(X.grad, g[tag + "dX"], atol_scale=5e-5, what="dX")
+    for k, p_ in m.named_parameters():
+        assert_close(p_.grad, g[tag + "grad." + k], atol_scale=5e-5, what=k)

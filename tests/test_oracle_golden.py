@@ -305,3 +305,19 @@ def test_touched_rows_adam_is_lazy_not_dense():
     q = oracle.touched_rows_step("adam_rows", w, grad, state, 2)
     assert torch.equal(q[0], w[0]) and not torch.equal(q[1], w[1])
     assert float(state["m"][0, 0]) == pytest.approx(0.1)     # dense Adam would have decayed it to 0.09
+
+
+# ------------------------------------------------------------------------------- f4 InteractionMachine
+@pytest.mark.parametrize("order", [1, 2, 3, 4, 5])
+def test_interaction_machine_golden(order):
+    """oracle.interaction_machine / power_sums against the reference's InteractionMachine (no batch norm)."""
+    g = load("interaction_machine")
+    tag = "o%d_bn0." % order
+    X = g[tag + "X"].clone().requires_grad_(True)
+    y = oracle.interaction_machine(X, order, g[tag + "sd.fc.weight"], g[tag + "sd.fc.bias"])
+    same_sum(y, g[tag + "y"], "y")
+    (y * g[tag + "w"]).sum().backward()
+    same_sum(X.grad, g[tag + "dX"], "dX")
+    P = oracle.power_sums(g[tag + "X"], order)
+    assert P.shape == (23, order, 8)
+    same_sum(P[:, 0], g[tag + "X"].sum(1), "p1")

@@ -102,6 +102,10 @@ for D in (16, 32, 64, 128):
             do = torch.randn(ops.interact_out_shape(B, Ft, D, mode), generator=g).to(dev)
             case("a6", "rbx_interact_fwd[%s]" % nm, "B=65536 F=39 D=16", B * (4 * Ft * D + out_b), lambda: ops.interact_fwd(E, mode))
             case("a6", "rbx_interact_bwd[%s]" % nm, "B=65536 F=39 D=16", B * (8 * Ft * D + out_b), lambda: ops.interact_bwd(E, do, mode))
+        for order in (2, 5):
+            dP = torch.randn(B, order, D, generator=g).to(dev)
+            case("f4", "rbx_power_sums_fwd[order %d]" % order, "B=65536 F=39 D=16", B * (4 * Ft * D + 4 * order * D), lambda: ops.power_sums_fwd(E, order))
+            case("f4", "rbx_power_sums_bwd[order %d]" % order, "B=65536 F=39 D=16", B * (8 * Ft * D + 4 * order * D), lambda: ops.power_sums_bwd(E, dP))
         Bs = 8192
         Es = E[:Bs].contiguous()
         do = torch.randn(Bs, P, D, generator=g).to(dev)
