@@ -73,6 +73,85 @@ __global__ void __launch_bounds__(kThreads) k_sumsq_bwd_vec(const float* __restr
     }
 }
 
+// ------------------------------------------------------------------ modes 0/1, register-resident form
+// A sample is spread over LPR (column chunks) x FG (field groups) lanes; lane (c, fg) holds the 16-byte chunk c of the
+// fields fg, fg + FG, ... in registers (R of them), so E is read from HBM exactly ONCE also in the backward (the plain
+// kernels above re-read it for the second pass: 0.46 of the roofline) and all of a lane's loads are independent.
+template <int LPR>
+struct SumsqMap {
+    static constexpr int FG = (32 / LPR) < 4 ? (32 / LPR) : 4;     // field groups per sample
+    static constexpr int SPW = 32 / (LPR * FG);                    // samples per warp
+};
+
+template <int LPR, int R>
+__global__ void __launch_bounds__(kThreads) k_sumsq_reg(const float* __restrict__ E, const float* __restrict__ dout,
+                                                       float* __restrict__ out, int64_t B, int F, int mode, int bwd) {
+    constexpr int D = 4 * LPR, FG = SumsqMap<LPR>::FG, SPW = SumsqMap<LPR>::SPW;
+    const int lane = threadIdx.x & 31, lig = lane & (LPR - 1), fg = (lane / LPR) & (FG - 1), sg = lane / (LPR * FG);
+    const int64_t warp0 = (int64_t)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
+    const int64_t nwarps = (int64_t)gridDim.x * (kThreads / 32);
+    for (int64_t base = warp0 * SPW; base < B; base += nwarps * SPW) {
+        const int64_t b = base + sg;
+        const bool valid = b < B;
+        const float* e = E + (size_t)(valid ? b : 0) * F * D + 4 * lig;
+        float4 v[R];
+#pragma unroll
+        for (int i = 0; i < R; ++i) {
+            const int f = i * FG + fg;
+            v[i] = (valid && f < F) ? ld_stream_f4(e + (size_t)f * D) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        float4 S = make_float4(0.f, 0.f, 0.f, 0.f), Q = S;
+#pragma unroll
+        for (int i = 0; i < R; ++i) {
+            S = f4_add(S, v[i]);
+            Q = f4_sqacc(v[i], Q);
+        }
+#pragma unroll
+        for (int o = LPR; o < LPR * FG; o <<= 1) {                // sum over the field groups (same column chunk)
+            S.x += __shfl_xor_sync(0xffffffffu, S.x, o); S.y += __shfl_xor_sync(0xffffffffu, S.y, o);
+            S.z += __shfl_xor_sync(0xffffffffu, S.z, o); S.w += __shfl_xor_sync(0xffffffffu, S.w, o);
+            Q.x += __shfl_xor_sync(0xffffffffu, Q.x, o); Q.y += __shfl_xor_sync(0xffffffffu, Q.y, o);
+            Q.z += __shfl_xor_sync(0xffffffffu, Q.z, o); Q.w += __shfl_xor_sync(0xffffffffu, Q.w, o);
+        }
+        if (!bwd) {
+            const float4 bi = make_float4((S.x * S.x - Q.x) * 0.5f, (S.y * S.y - Q.y) * 0.5f, (S.z * S.z - Q.z) * 0.5f,
+                                          (S.w * S.w - Q.w) * 0.5f);
+            if (mode == 1) {
+                if (valid && fg == 0) *reinterpret_cast<float4*>(out + (size_t)b * D + 4 * lig) = bi;
+            } else {
+                const float s = group_sum<LPR>((bi.x + bi.y) + (bi.z + bi.w));
+                if (valid && fg == 0 && lig == 0) out[b] = s;
+            }
+        } else if (valid) {
+            float4 g;
+            if (mode == 1) g = ld_stream_f4(dout + (size_t)b * D + 4 * lig);
+            else { const float s = __ldg(dout + b); g = make_float4(s, s, s, s); }
+            float* de = out + (size_t)b * F * D + 4 * lig;
+#pragma unroll
+            for (int i = 0; i < R; ++i) {
+                const int f = i * FG + fg;
+                if (f < F)
+                    st_stream_f4(de + (size_t)f * D, make_float4(g.x * (S.x - v[i].x), g.y * (S.y - v[i].y), g.z * (S.z - v[i].z),
+                                                                 g.w * (S.w - v[i].w)));
+            }
+        }
+    }
+}
+
+// launch the register-resident kernel when the sample fits (F <= FG * 16); returns false otherwise
+template <int LPR>
+bool launch_sumsq_reg(const float* E, const float* dout, float* out, int64_t B, int F, int mode, int bwd, cudaStream_t st) {
+    constexpr int FG = SumsqMap<LPR>::FG, SPW = SumsqMap<LPR>::SPW;
+    const int need = (F + FG - 1) / FG;
+    const int grid = capped_grid((B + SPW * 8 - 1) / (SPW * 8), 8);
+    if (need <= 4) k_sumsq_reg<LPR, 4><<<grid, kThreads, 0, st>>>(E, dout, out, B, F, mode, bwd);
+    else if (need <= 8) k_sumsq_reg<LPR, 8><<<grid, kThreads, 0, st>>>(E, dout, out, B, F, mode, bwd);
+    else if (need <= 12) k_sumsq_reg<LPR, 12><<<grid, kThreads, 0, st>>>(E, dout, out, B, F, mode, bwd);
+    else if (need <= 16) k_sumsq_reg<LPR, 16><<<grid, kThreads, 0, st>>>(E, dout, out, B, F, mode, bwd);
+    else return false;
+    return true;
+}
+
 // ------------------------------------------------------------------ modes 0/1, any D: warp per sample
 __global__ void __launch_bounds__(kThreads) k_sumsq_fwd_any(const float* __restrict__ E, float* __restrict__ out, int64_t B,
                                                            int F, int D, int mode) {
@@ -579,7 +658,10 @@ int rbx_interact_fwd(const float* E, float* out, int64_t B, int F, int D, int mo
     cudaStream_t st = rbx_cast_stream(stream);
     if (mode <= 1) {
         if (vec_ok(D, E, mode == 1 ? out : nullptr, nullptr)) {
-            RBX_DISPATCH_LPR(D, (k_sumsq_fwd_vec<LPR><<<capped_grid((B + 32 / LPR * 8 - 1) / (32 / LPR * 8), 8), kThreads, 0, st>>>(E, out, B, F, mode)));
+            bool done = false;
+            RBX_DISPATCH_LPR(D, (done = launch_sumsq_reg<LPR>(E, nullptr, out, B, F, mode, 0, st)));
+            if (!done)
+                RBX_DISPATCH_LPR(D, (k_sumsq_fwd_vec<LPR><<<capped_grid((B + 32 / LPR * 8 - 1) / (32 / LPR * 8), 8), kThreads, 0, st>>>(E, out, B, F, mode)));
         } else {
             k_sumsq_fwd_any<<<capped_grid((B + 7) / 8, 8), kThreads, 0, st>>>(E, out, B, F, D, mode);
         }
@@ -621,7 +703,10 @@ int rbx_interact_bwd(const float* E, const float* dout, float* dE, int64_t B, in
     cudaStream_t st = rbx_cast_stream(stream);
     if (mode <= 1) {
         if (vec_ok(D, E, dE, mode == 1 ? dout : nullptr)) {
-            RBX_DISPATCH_LPR(D, (k_sumsq_bwd_vec<LPR><<<capped_grid((B + 32 / LPR * 8 - 1) / (32 / LPR * 8), 8), kThreads, 0, st>>>(E, dout, dE, B, F, mode)));
+            bool done = false;
+            RBX_DISPATCH_LPR(D, (done = launch_sumsq_reg<LPR>(E, dout, dE, B, F, mode, 1, st)));
+            if (!done)
+                RBX_DISPATCH_LPR(D, (k_sumsq_bwd_vec<LPR><<<capped_grid((B + 32 / LPR * 8 - 1) / (32 / LPR * 8), 8), kThreads, 0, st>>>(E, dout, dE, B, F, mode)));
         } else {
             k_sumsq_bwd_any<<<capped_grid((B + 7) / 8, 8), kThreads, 0, st>>>(E, dout, dE, B, F, D, mode);
         }

@@ -239,7 +239,7 @@ def test_interact_elementwise_known_answer():
 
 
 @pytest.mark.parametrize("mode", [0, 1, 2, 3])
-@pytest.mark.parametrize("F,D", [(39, 16), (5, 10), (2, 64), (13, 128), (7, 1), (8, 4), (40, 8), (33, 32), (4, 16)])
+@pytest.mark.parametrize("F,D", [(39, 16), (5, 10), (2, 64), (13, 128), (7, 1), (8, 4), (40, 8), (33, 32), (4, 16), (70, 16)])
 def test_interact_random(mode, F, D):
     ops = _ops()
     name = [k for k, v in ops.MODES.items() if v == mode][0]
