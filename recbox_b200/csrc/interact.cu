@@ -309,7 +309,9 @@ __global__ void __launch_bounds__(kThreads) k_ip_fwd_warp(const float* __restric
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpc = blockDim.x >> 5;
     const int FB = (F + 3) >> 2, NT = FB * (FB + 1) / 2, P = F * (F - 1) / 2;
     int* sTile = reinterpret_cast<int*>(smem);                       // [NT] (ti << 8) | tj, ti <= tj
-    float* sE = smem + ((NT + 3) & ~3) + (size_t)warp * slice_floats(F, D);
+    const int per_warp = slice_floats(F, D) + ((P + 3) & ~3);
+    float* sE = smem + ((NT + 3) & ~3) + (size_t)warp * per_warp;
+    float* sOut = sE + slice_floats(F, D);                           // [P] the sample's output row, written back coalesced
     for (int ti = threadIdx.x; ti < FB; ti += blockDim.x)
         for (int tj = ti; tj < FB; ++tj) sTile[ti * FB - ti * (ti - 1) / 2 + (tj - ti)] = (ti << 8) | tj;
     zero_pad_rows<LPR>(sE, F, lane);
@@ -350,10 +352,13 @@ __global__ void __launch_bounds__(kThreads) k_ip_fwd_warp(const float* __restric
 #pragma unroll
                 for (int y = 0; y < 4; ++y) {
                     const int j = 4 * tj + y;
-                    if (j > i && j < F) ob[base + j] = acc[x][y];
+                    if (j > i && j < F) sOut[base + j] = acc[x][y];
                 }
             }
         }
+        // 741 scattered 4-byte stores per sample would each cost an L2 sector write; one coalesced pass instead
+        __syncwarp();
+        for (int i = lane; i < P; i += 32) ob[i] = sOut[i];
     }
 }
 
@@ -597,6 +602,88 @@ __global__ void __launch_bounds__(kThreads) k_power_sums_bwd_vec(const float* __
     }
 }
 
+// Lane mapping of k_sumsq_reg: a sample is spread over LPR column chunks x FG field groups, every lane's loads are
+// independent (the first version walked the 39 fields serially per lane: 0.45 / 0.60 of the roofline).
+template <int LPR, int R>
+__global__ void __launch_bounds__(kThreads) k_power_sums_reg(const float* __restrict__ E, const float* __restrict__ dP,
+                                                            float* __restrict__ out, int64_t B, int F, int order, int bwd) {
+    constexpr int D = 4 * LPR, FG = SumsqMap<LPR>::FG, SPW = SumsqMap<LPR>::SPW;
+    const int lane = threadIdx.x & 31, lig = lane & (LPR - 1), fg = (lane / LPR) & (FG - 1), sg = lane / (LPR * FG);
+    const int64_t warp0 = (int64_t)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
+    const int64_t nwarps = (int64_t)gridDim.x * (kThreads / 32);
+    for (int64_t base = warp0 * SPW; base < B; base += nwarps * SPW) {
+        const int64_t b = base + sg;
+        const bool valid = b < B;
+        const float* e = E + (size_t)(valid ? b : 0) * F * D + 4 * lig;
+        float4 v[R];
+#pragma unroll
+        for (int i = 0; i < R; ++i) {
+            const int f = i * FG + fg;
+            v[i] = (valid && f < F) ? ld_stream_f4(e + (size_t)f * D) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        if (!bwd) {
+            float4 acc[kMaxOrder];
+#pragma unroll
+            for (int k = 0; k < kMaxOrder; ++k) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int i = 0; i < R; ++i) {
+                float4 q = v[i];
+#pragma unroll
+                for (int k = 0; k < kMaxOrder; ++k)
+                    if (k < order) {
+                        acc[k] = f4_add(acc[k], q);
+                        q = f4_mul(q, v[i]);
+                    }
+            }
+#pragma unroll
+            for (int k = 0; k < kMaxOrder; ++k) {
+                if (k < order) {
+#pragma unroll
+                    for (int o = LPR; o < LPR * FG; o <<= 1) {
+                        acc[k].x += __shfl_xor_sync(0xffffffffu, acc[k].x, o); acc[k].y += __shfl_xor_sync(0xffffffffu, acc[k].y, o);
+                        acc[k].z += __shfl_xor_sync(0xffffffffu, acc[k].z, o); acc[k].w += __shfl_xor_sync(0xffffffffu, acc[k].w, o);
+                    }
+                    if (valid && fg == 0) *reinterpret_cast<float4*>(out + ((size_t)b * order + k) * D + 4 * lig) = acc[k];
+                }
+            }
+        } else if (valid) {
+            float4 g[kMaxOrder];                              // k * dP_k
+#pragma unroll
+            for (int k = 0; k < kMaxOrder; ++k) {
+                g[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (k < order) g[k] = f4_scale(ld_row_f4(dP + ((size_t)b * order + k) * D + 4 * lig), (float)(k + 1));
+            }
+            float* de = out + (size_t)b * F * D + 4 * lig;
+#pragma unroll
+            for (int i = 0; i < R; ++i) {
+                const int f = i * FG + fg;
+                if (f < F) {
+                    float4 r = g[0], q = v[i];
+#pragma unroll
+                    for (int k = 1; k < kMaxOrder; ++k)
+                        if (k < order) {
+                            r = f4_fma4(g[k], q, r);
+                            q = f4_mul(q, v[i]);
+                        }
+                    st_stream_f4(de + (size_t)f * D, r);
+                }
+            }
+        }
+    }
+}
+
+template <int LPR>
+bool launch_power_sums_reg(const float* E, const float* dP, float* out, int64_t B, int F, int order, int bwd, cudaStream_t st) {
+    constexpr int FG = SumsqMap<LPR>::FG, SPW = SumsqMap<LPR>::SPW;
+    const int need = (F + FG - 1) / FG;
+    const int grid = capped_grid((B + SPW * 8 - 1) / (SPW * 8), 8);
+    if (need <= 4) k_power_sums_reg<LPR, 4><<<grid, kThreads, 0, st>>>(E, dP, out, B, F, order, bwd);
+    else if (need <= 8) k_power_sums_reg<LPR, 8><<<grid, kThreads, 0, st>>>(E, dP, out, B, F, order, bwd);
+    else if (need <= 12) k_power_sums_reg<LPR, 12><<<grid, kThreads, 0, st>>>(E, dP, out, B, F, order, bwd);
+    else return false;
+    return true;
+}
+
 // any D: warp per sample, lane owns columns d, d + 32, ...
 __global__ void __launch_bounds__(kThreads) k_power_sums_any(const float* __restrict__ E, const float* __restrict__ dP,
                                                             float* __restrict__ out, int64_t B, int F, int D, int order, int bwd) {
@@ -673,7 +760,7 @@ int rbx_interact_fwd(const float* E, float* out, int64_t B, int F, int D, int mo
             const int FB = (F + 3) / 4;
             size_t wsmem = 0;
             const size_t fixed = mode == 2 ? (size_t)((FB * (FB + 1) / 2 + 3) & ~3) : ((P + 3) & ~(size_t)3);
-            const int wpc = warps_for(fixed, slice_floats(F, D), &wsmem);
+            const int wpc = warps_for(fixed, slice_floats(F, D) + (mode == 2 ? ((P + 3) & ~(size_t)3) : 0), &wsmem);
             if (wpc > 0) {
                 if (mode == 2) {
                     RBX_DISPATCH_LPR(D, (k_ip_fwd_warp<LPR><<<warp_grid(k_ip_fwd_warp<LPR>, wpc, wsmem, B), wpc * 32, wsmem, st>>>(E, out, B, F)));
@@ -764,7 +851,10 @@ int rbx_power_sums_fwd(const float* E, float* P, int64_t B, int F, int D, int or
     if (B == 0) return RBX_OK;
     RBX_REQUIRE(E && P, "%s: null pointer", who);
     cudaStream_t st = rbx_cast_stream(stream);
-    if (vec_ok(D, E, P, nullptr)) {
+    bool done = false;
+    if (vec_ok(D, E, P, nullptr)) RBX_DISPATCH_LPR(D, (done = launch_power_sums_reg<LPR>(E, nullptr, P, B, F, order, 0, st)));
+    if (done) {
+    } else if (vec_ok(D, E, P, nullptr)) {
         RBX_DISPATCH_LPR(D, (k_power_sums_fwd_vec<LPR><<<capped_grid((B + 32 / LPR * 8 - 1) / (32 / LPR * 8), 8), kThreads, 0, st>>>(E, P, B, F, order)));
     } else {
         k_power_sums_any<<<capped_grid((B + 7) / 8, 8), kThreads, 0, st>>>(E, nullptr, P, B, F, D, order, 0);
@@ -780,7 +870,10 @@ int rbx_power_sums_bwd(const float* E, const float* dP, float* dE, int64_t B, in
     if (B == 0) return RBX_OK;
     RBX_REQUIRE(E && dP && dE, "%s: null pointer", who);
     cudaStream_t st = rbx_cast_stream(stream);
-    if (vec_ok(D, E, dP, dE)) {
+    bool done = false;
+    if (vec_ok(D, E, dP, dE)) RBX_DISPATCH_LPR(D, (done = launch_power_sums_reg<LPR>(E, dP, dE, B, F, order, 1, st)));
+    if (done) {
+    } else if (vec_ok(D, E, dP, dE)) {
         RBX_DISPATCH_LPR(D, (k_power_sums_bwd_vec<LPR><<<capped_grid((B + 32 / LPR * 8 - 1) / (32 / LPR * 8), 8), kThreads, 0, st>>>(E, dP, dE, B, F, order)));
     } else {
         k_power_sums_any<<<capped_grid((B + 7) / 8, 8), kThreads, 0, st>>>(E, dP, dE, B, F, D, order, 1);
