@@ -439,6 +439,8 @@ def main_sharded(args, rank, world, local_rank):
         dist.init_process_group("nccl", device_id=dev)
     B, F, Fn, D, V = CFG["B"], CFG["F"], CFG["Fn"], args.dim, args.rows_per_field
     Ft, R = F + Fn, F * V
+    if args.shard_layout == "auto":     # ROW+LR wins on multi-GB tables at every N (profiles/r1_sharded_runs.jsonl, r2e / r1w)
+        args.shard_layout = "rowlr" if (args.shard_mode == "peer" and not args.no_lr and D in (4, 8, 16)) else "split"
     sh = sharded.ShardedEmbeddingFM(R, D, mode=args.shard_mode, device=dev, max_ids=B * F, alloc=args.peer_alloc, with_lr=not args.no_lr,
                                     layout=args.shard_layout)
     gen = torch.Generator(device=dev).manual_seed(20240 + 4 + rank)
@@ -552,7 +554,7 @@ def main():
                          "sharded: configs[3], 100M-row table row-sharded over the ranks")
     ap.add_argument("--shard-mode", default="peer", choices=["push", "peer", "a2a"])
     ap.add_argument("--peer-alloc", default="symm", choices=["ipc", "symm"])
-    ap.add_argument("--shard-layout", default="split", choices=["split", "rowlr"],
+    ap.add_argument("--shard-layout", default="auto", choices=["auto", "split", "rowlr"],
                     help="rowlr: embedding row + first-order weight in one physical row (one NVLink request per slot)")
     ap.add_argument("--no-lr", action="store_true", help="sharded workload without the first-order (LR) table")
     ap.add_argument("--dim", type=int, default=16)

@@ -8,8 +8,8 @@
 // BITMAP of vocab bits (1.25 MB for 10 M items -- it lives in L2), the rank of an id is a
 // popcount prefix over that bitmap, and the whole job is five streaming passes:
 //   1 clear bitmap            2 mark: atomicOr(bitmap[id>>5], 1 << (id&31))
-//   3 per-CTA popcount sums   4 scan of the CTA sums (one CTA) + word prefixes, emit sorted uniques
-//   5 inverse[i] = prefix[id>>5] + popc(bitmap[id>>5] & lower bits); first[rank] = min(i)
+//   3 per-CTA popcount sums   4 scan of the CTA sums (one CTA), then the exclusive prefix of every word
+//   5 rank(id) = prefix[id>>5] + popc(bitmap[id>>5] & lower bits): uniq[rank] = id, inverse[i] = rank, first[rank] = min(i)
 // Integer work: results are bit-identical to numpy/torch unique (tests compare with the oracle).
 #include "rbx_common.cuh"
 
@@ -106,36 +106,37 @@ __global__ void __launch_bounds__(kT) k_scan_chunks(uint32_t* blocksum, int64_t 
     if (threadIdx.x == 0) n_out[0] = (int64_t)carry;
 }
 
-template <typename IdT>
-__global__ void __launch_bounds__(kT) k_emit(const uint32_t* __restrict__ bitmap, int64_t W, const uint32_t* __restrict__ blocksum,
-                                             uint32_t* wprefix, IdT* uniq, int64_t* first, int64_t n) {
+// exclusive popcount prefix of every bitmap word (rank of the first id of the word)
+__global__ void __launch_bounds__(kT) k_prefix(const uint32_t* __restrict__ bitmap, int64_t W, const uint32_t* __restrict__ blocksum,
+                                               uint32_t* wprefix) {
     const int64_t w0 = (int64_t)blockIdx.x * kChunk + (int64_t)threadIdx.x * kWPT;
-    uint32_t words[kWPT], c = 0;
+    uint32_t cnt[kWPT], c = 0;
 #pragma unroll
     for (int k = 0; k < kWPT; ++k) {
-        words[k] = (w0 + k < W) ? bitmap[w0 + k] : 0u;
-        c += __popc(words[k]);
+        cnt[k] = (w0 + k < W) ? __popc(bitmap[w0 + k]) : 0u;
+        c += cnt[k];
     }
     uint32_t total;
     uint32_t rank = blocksum[blockIdx.x] + block_exclusive_scan(c, &total);
 #pragma unroll
     for (int k = 0; k < kWPT; ++k) {
         if (w0 + k < W) wprefix[w0 + k] = rank;
-        uint32_t m = words[k];
-        while (m) {
-            const int b = __ffs(m) - 1;
-            m &= m - 1;
-            if (uniq) uniq[rank] = (IdT)((w0 + k) * 32 + b);
-            if (first) first[rank] = n;           // sentinel; k_inverse takes the minimum position
-            ++rank;
-        }
+        rank += cnt[k];
     }
 }
 
+__global__ void __launch_bounds__(kT) k_fill_i64(int64_t* p, int64_t n, int64_t v) {
+    for (int64_t i = (int64_t)blockIdx.x * kT + threadIdx.x; i < n; i += (int64_t)gridDim.x * kT) p[i] = v;
+}
+
+// rank of every id = word prefix + popcount of the lower bits.  The sorted unique list is written from HERE
+// (uniq[rank] = id: all duplicates store the same value), so no pass has to walk the bitmap bit by bit -- the first
+// version emitted the uniques with a serial per-bit loop over 8 words per thread in a 15-CTA launch, which was most
+// of its 134 us on a 1 M-row vocabulary.
 template <typename IdT>
 __global__ void __launch_bounds__(kT) k_inverse(const IdT* __restrict__ ids, int64_t n, int64_t vocab,
                                                 const uint32_t* __restrict__ bitmap, const uint32_t* __restrict__ wprefix,
-                                                IdT* inverse, int64_t* first) {
+                                                IdT* uniq, IdT* inverse, int64_t* first) {
     for (int64_t i = (int64_t)blockIdx.x * kT + threadIdx.x; i < n; i += (int64_t)gridDim.x * kT) {
         const int64_t id = (int64_t)ids[i];
         if (id < 0 || id >= vocab) {
@@ -144,6 +145,7 @@ __global__ void __launch_bounds__(kT) k_inverse(const IdT* __restrict__ ids, int
         }
         const uint32_t word = __ldg(bitmap + (id >> 5));
         const uint32_t rank = __ldg(wprefix + (id >> 5)) + __popc(word & ((1u << (id & 31)) - 1u));
+        if (uniq) uniq[rank] = (IdT)id;
         if (inverse) inverse[i] = (IdT)rank;
         if (first) atomicMin(reinterpret_cast<unsigned long long*>(first + rank), (unsigned long long)i);
     }
@@ -173,8 +175,13 @@ int unique_impl(const char* who, const IdT* ids, int64_t n, int64_t vocab, void*
     if (n > 0) k_mark<IdT><<<(int)g, kT, 0, st>>>(ids, n, vocab, u.bitmap, n_out);
     k_count<<<(int)NB, kT, 0, st>>>(u.bitmap, W, u.blocksum);
     k_scan_chunks<<<1, kT, 0, st>>>(u.blocksum, NB, n_out);
-    k_emit<IdT><<<(int)NB, kT, 0, st>>>(u.bitmap, W, u.blocksum, u.wprefix, uniq, first, n);
-    if (n > 0 && (inverse || first)) k_inverse<IdT><<<(int)g, kT, 0, st>>>(ids, n, vocab, u.bitmap, u.wprefix, inverse, first);
+    k_prefix<<<(int)NB, kT, 0, st>>>(u.bitmap, W, u.blocksum, u.wprefix);
+    if (n > 0 && first) {
+        const int64_t cap_u = n < vocab ? n : vocab;          // capacity of `first` (rbx_unique_ids_* contract)
+        k_fill_i64<<<(int)((cap_u + kT - 1) / kT < cap ? (cap_u + kT - 1) / kT : cap), kT, 0, st>>>(first, cap_u, n);
+    }
+    if (n > 0 && (uniq || inverse || first))
+        k_inverse<IdT><<<(int)g, kT, 0, st>>>(ids, n, vocab, u.bitmap, u.wprefix, uniq, inverse, first);
     RBX_LAUNCH_CHECK(who);
     return RBX_OK;
 }
