@@ -64,3 +64,17 @@ def test_sampling_block_restatement():
         assert not set(row.tolist()) & set(u2i[q])
     b = oracle.sampling_block(50, [0, 1], 1000, u2i, seed=4)
     assert b.shape == (2, 1000) and len(np.unique(b)) == 50
+
+
+def test_retrieval_host_helpers():
+    """build_csr keeps duplicates and sorts each row; the index refuses a CPU device (no CPU path)."""
+    import torch
+    from recbox_b200 import RbxError, retrieval
+    u2i = {7: [5, 2, 2, 9], 3: [], 11: [4]}
+    ptr, items = retrieval.build_csr(u2i, [11, 7, 3, 99], "cpu")
+    assert ptr.tolist() == [0, 1, 5, 5, 5] and items.tolist() == [4, 2, 2, 5, 9]
+    assert ptr.dtype == torch.int64 and items.dtype == torch.int64
+    with pytest.raises(RbxError):
+        retrieval.FlatIPIndex(np.zeros((4, 8), np.float32), dim=8, device="cpu")
+    with pytest.raises(NotImplementedError):
+        retrieval.FlatIPIndex(np.zeros((4, 8), np.float32), dim=8, index_name="IndexIVFFlat")
