@@ -449,8 +449,9 @@ int rbx_topk_ip(const float* q, const float* items, int64_t U, int64_t N, int D,
     t.count = reinterpret_cast<int*>(w);               w += align256(U * 4);
     t.R = reinterpret_cast<unsigned long long*>(w);    w += align256((size_t)U * Kp * 8);
     t.queue = reinterpret_cast<unsigned long long*>(w);
-    cudaMemsetAsync(t.count, 0, (size_t)U * 4, st);
-    cudaMemsetAsync(t.R, 0, (size_t)U * Kp * 8, st);
+    cudaError_t me = cudaMemsetAsync(t.count, 0, (size_t)U * 4, st);
+    if (me == cudaSuccess) me = cudaMemsetAsync(t.R, 0, (size_t)U * Kp * 8, st);
+    if (me != cudaSuccess) return rbx_fail(RBX_ERR_CUDA, "%s: memset: %s", who, cudaGetErrorString(me));
     k_topk_init<<<(int)((U + 255) / 256 < 1024 ? (U + 255) / 256 : 1024), 256, 0, st>>>(t.tau, U);
     RBX_LAUNCH_CHECK(who);
 
