@@ -130,6 +130,7 @@ def test_install_rebinds_reference_symbols():
         done = recbox_b200.install()
         assert ("recbox.ranking.pytorch.layers", "FeatureEmbedding") in done
         assert L.FeatureEmbedding is layers.FeatureEmbedding and L.FactorizationMachine is layers.FactorizationMachine
+        assert L.InteractionMachine is layers.InteractionMachine
         import fuxictr.pytorch.layers as FL
         assert FL.LogisticRegression is layers.LogisticRegression
         import recbox.core.pytorch.layers as CL
@@ -165,3 +166,18 @@ def test_install_rebinds_reference_symbols():
     finally:
         recbox_b200.uninstall()
     assert L.FeatureEmbedding is ref_cls
+
+
+def test_interaction_machine_parameter_names_match_reference():
+    """state_dict keys of layers.InteractionMachine equal the reference module's (golden minted from it), and the CPU
+    call is refused (no CPU path)."""
+    g = load("interaction_machine")
+    for order, bn in ((2, 0), (5, 1)):
+        tag = "o%d_bn%d.sd." % (order, bn)
+        want = sorted(k[len(tag):] for k in g if k.startswith(tag))
+        m = layers.InteractionMachine(8, order=order, batch_norm=bool(bn))
+        assert sorted(m.state_dict()) == want
+        with pytest.raises(RbxError):
+            m(torch.zeros(2, 3, 8))
+    with pytest.raises(AssertionError):
+        layers.InteractionMachine(8, order=6)
