@@ -386,12 +386,12 @@ int rbx_optim_rows(float* w, float* g, float* m /*| NULL*/, float* v /*| NULL*/,
  * a14  sorted unique + inverse + first occurrence of a bag of ids bounded by a vocabulary
  * (collate_fn_unique, recbox/matching/pytorch/dataloaders/h5_generator.py:45-53:
  *  torch.unique(item_indexes.flatten(), return_inverse=True, sorted=True) + the flip/scatter_
- *  "return_index").  No sort: a vocab-bit bitmap + popcount prefix (csrc/dedup.cu).
+ *  "return_index").  No sort: a vocab-bit bitmap (byte map for dense batches) + popcount prefix (csrc/dedup.cu).
  *   uniq[0..U)   ascending distinct ids            (capacity min(n, vocab))
  *   first[u]     smallest flat position i with ids[i] == uniq[u]   (int64; NULL to skip)
  *   inverse[i]   u with uniq[u] == ids[i]; -1 for an id outside [0, vocab)   (NULL to skip)
  *   n_out[0] = U, n_out[1] = number of out-of-range ids          (DEVICE int64[2])
- * ws = rbx_unique_ws_bytes(vocab) bytes of 8-byte aligned DEVICE scratch.  Also used to list the
+ * ws = rbx_unique_ws_bytes(vocab) bytes of 16-byte aligned DEVICE scratch.  Also used to list the
  * table rows a batch touched (vocab = R) for the f1 optimizer.
  * ------------------------------------------------------------------------------------------ */
 size_t rbx_unique_ws_bytes(int64_t vocab);

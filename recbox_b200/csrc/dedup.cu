@@ -19,43 +19,71 @@ constexpr int kT = 256;             // threads per CTA
 constexpr int kWPT = 8;             // bitmap words per thread in the count / emit passes
 constexpr int kChunk = kT * kWPT;   // words per CTA (= 65 536 ids of vocabulary)
 
+// workspace: counters (64 B) | wp[W] = (bitmap word, exclusive popcount prefix) pairs | blocksum[NB] | byte map [32 W]
 struct UniqueWs {
-    uint32_t* bitmap;    // [W]
-    uint32_t* wprefix;   // [W]   exclusive popcount prefix of every word
+    uint2* wp;           // [W]   .x bitmap word, .y rank of the word's first id
     uint32_t* blocksum;  // [NB]  popcount of every chunk, then its exclusive prefix
-    int64_t* counters;   // [2]   n_unique, n_out_of_range (mirrors of n_out, for the kernels)
+    uint8_t* bytemap;    // [32 W] dense mode: one byte per id, written with plain stores (no atomics)
+    int64_t* counters;   // [2]   reserved
 };
 
 __host__ __device__ inline int64_t words_of(int64_t vocab) { return (vocab + 31) / 32; }
 
 size_t ws_bytes(int64_t vocab) {
     const int64_t W = words_of(vocab), NB = (W + kChunk - 1) / kChunk;
-    return (size_t)(2 * W + NB) * 4 + 64;
+    return 64 + (((size_t)W * 8 + 15) & ~(size_t)15) + (((size_t)NB * 4 + 15) & ~(size_t)15) + (size_t)W * 32;
 }
 
 UniqueWs carve(void* ws, int64_t vocab) {
     const int64_t W = words_of(vocab), NB = (W + kChunk - 1) / kChunk;
     UniqueWs u;
-    u.counters = reinterpret_cast<int64_t*>(ws);                              // 64 bytes reserved
-    u.bitmap = reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(ws) + 64);
-    u.wprefix = u.bitmap + W;
-    u.blocksum = u.wprefix + W;
-    (void)NB;
+    char* p = reinterpret_cast<char*>(ws);
+    u.counters = reinterpret_cast<int64_t*>(p);                               // 64 bytes reserved
+    u.wp = reinterpret_cast<uint2*>(p + 64);
+    const size_t wp_bytes = ((size_t)W * 8 + 15) & ~(size_t)15;
+    u.blocksum = reinterpret_cast<uint32_t*>(p + 64 + wp_bytes);
+    u.bytemap = reinterpret_cast<uint8_t*>(p + 64 + wp_bytes + (((size_t)NB * 4 + 15) & ~(size_t)15));   // 16-byte aligned
     return u;
 }
 
+// Sparse batches (n << vocab): set bits with atomicOr -- few ids share a word, the bitmap is all that is cleared.
 template <typename IdT>
-__global__ void __launch_bounds__(kT) k_mark(const IdT* __restrict__ ids, int64_t n, int64_t vocab, uint32_t* bitmap,
-                                             int64_t* n_out) {
+__global__ void __launch_bounds__(kT) k_mark(const IdT* __restrict__ ids, int64_t n, int64_t vocab, uint2* wp, int64_t* n_out) {
     int64_t bad = 0;
     for (int64_t i = (int64_t)blockIdx.x * kT + threadIdx.x; i < n; i += (int64_t)gridDim.x * kT) {
         const int64_t id = (int64_t)ids[i];
         if (id < 0 || id >= vocab) { ++bad; continue; }
         const uint32_t bit = 1u << (id & 31);
+        uint32_t* word = &wp[id >> 5].x;
         // most ids of a batch are distinct: test first so repeated (hot) ids do not serialise on the atomic
-        if (!(__ldcg(bitmap + (id >> 5)) & bit)) atomicOr(bitmap + (id >> 5), bit);
+        if (!(__ldcg(word) & bit)) atomicOr(word, bit);
     }
     if (bad) atomicAdd(reinterpret_cast<unsigned long long*>(n_out + 1), (unsigned long long)bad);
+}
+
+// Dense batches (n comparable to vocab, e.g. the rows a 65 536 x 26 batch touches in a 1 M-row table): dozens of ids
+// fall into every bitmap word and their atomics serialise in L2 (31 us of the 90 us total, ncu launch list r1z).  Plain
+// byte stores of the same value race harmlessly instead; k_count folds the bytes into bitmap words.
+template <typename IdT>
+__global__ void __launch_bounds__(kT) k_mark_bytes(const IdT* __restrict__ ids, int64_t n, int64_t vocab, uint8_t* bytemap,
+                                                   int64_t* n_out) {
+    int64_t bad = 0;
+    for (int64_t i = (int64_t)blockIdx.x * kT + threadIdx.x; i < n; i += (int64_t)gridDim.x * kT) {
+        const int64_t id = (int64_t)ids[i];
+        if (id < 0 || id >= vocab) { ++bad; continue; }
+        bytemap[id] = 1;
+    }
+    if (bad) atomicAdd(reinterpret_cast<unsigned long long*>(n_out + 1), (unsigned long long)bad);
+}
+
+// 32 flag bytes (0 / 1) -> one bitmap word; (x * 0x01020408) >> 24 gathers the four flags of a 32-bit group
+__device__ __forceinline__ uint32_t fold_flags(const uint8_t* p) {
+    const uint4 a = *reinterpret_cast<const uint4*>(p), b = *reinterpret_cast<const uint4*>(p + 16);
+    const uint32_t g[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    uint32_t word = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) word |= ((((g[k] & 0x01010101u) * 0x01020408u) >> 24) & 0xfu) << (4 * k);
+    return word;
 }
 
 __device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t* total) {
@@ -81,12 +109,22 @@ __device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t* t
     return base + inc - v;
 }
 
-__global__ void __launch_bounds__(kT) k_count(const uint32_t* __restrict__ bitmap, int64_t W, uint32_t* blocksum) {
+__global__ void __launch_bounds__(kT) k_count(uint2* wp, const uint8_t* __restrict__ bytemap, int64_t W, uint32_t* blocksum) {
     const int64_t w0 = (int64_t)blockIdx.x * kChunk + (int64_t)threadIdx.x * kWPT;
     uint32_t c = 0;
 #pragma unroll
-    for (int k = 0; k < kWPT; ++k)
-        if (w0 + k < W) c += __popc(bitmap[w0 + k]);
+    for (int k = 0; k < kWPT; ++k) {
+        if (w0 + k < W) {
+            uint32_t word;
+            if (bytemap) {
+                word = fold_flags(bytemap + (w0 + k) * 32);
+                wp[w0 + k].x = word;
+            } else {
+                word = wp[w0 + k].x;
+            }
+            c += __popc(word);
+        }
+    }
     uint32_t total;
     (void)block_exclusive_scan(c, &total);
     if (threadIdx.x == 0) blocksum[blockIdx.x] = total;
@@ -106,21 +144,20 @@ __global__ void __launch_bounds__(kT) k_scan_chunks(uint32_t* blocksum, int64_t 
     if (threadIdx.x == 0) n_out[0] = (int64_t)carry;
 }
 
-// exclusive popcount prefix of every bitmap word (rank of the first id of the word)
-__global__ void __launch_bounds__(kT) k_prefix(const uint32_t* __restrict__ bitmap, int64_t W, const uint32_t* __restrict__ blocksum,
-                                               uint32_t* wprefix) {
+// exclusive popcount prefix of every bitmap word (rank of the first id of the word), stored next to the word
+__global__ void __launch_bounds__(kT) k_prefix(uint2* wp, int64_t W, const uint32_t* __restrict__ blocksum) {
     const int64_t w0 = (int64_t)blockIdx.x * kChunk + (int64_t)threadIdx.x * kWPT;
     uint32_t cnt[kWPT], c = 0;
 #pragma unroll
     for (int k = 0; k < kWPT; ++k) {
-        cnt[k] = (w0 + k < W) ? __popc(bitmap[w0 + k]) : 0u;
+        cnt[k] = (w0 + k < W) ? __popc(wp[w0 + k].x) : 0u;
         c += cnt[k];
     }
     uint32_t total;
     uint32_t rank = blocksum[blockIdx.x] + block_exclusive_scan(c, &total);
 #pragma unroll
     for (int k = 0; k < kWPT; ++k) {
-        if (w0 + k < W) wprefix[w0 + k] = rank;
+        if (w0 + k < W) wp[w0 + k].y = rank;
         rank += cnt[k];
     }
 }
@@ -134,8 +171,7 @@ __global__ void __launch_bounds__(kT) k_fill_i64(int64_t* p, int64_t n, int64_t 
 // version emitted the uniques with a serial per-bit loop over 8 words per thread in a 15-CTA launch, which was most
 // of its 134 us on a 1 M-row vocabulary.
 template <typename IdT>
-__global__ void __launch_bounds__(kT) k_inverse(const IdT* __restrict__ ids, int64_t n, int64_t vocab,
-                                                const uint32_t* __restrict__ bitmap, const uint32_t* __restrict__ wprefix,
+__global__ void __launch_bounds__(kT) k_inverse(const IdT* __restrict__ ids, int64_t n, int64_t vocab, const uint2* __restrict__ wp,
                                                 IdT* uniq, IdT* inverse, int64_t* first) {
     for (int64_t i = (int64_t)blockIdx.x * kT + threadIdx.x; i < n; i += (int64_t)gridDim.x * kT) {
         const int64_t id = (int64_t)ids[i];
@@ -143,8 +179,8 @@ __global__ void __launch_bounds__(kT) k_inverse(const IdT* __restrict__ ids, int
             if (inverse) inverse[i] = (IdT)-1;
             continue;
         }
-        const uint32_t word = __ldg(bitmap + (id >> 5));
-        const uint32_t rank = __ldg(wprefix + (id >> 5)) + __popc(word & ((1u << (id & 31)) - 1u));
+        const uint2 e = __ldg(wp + (id >> 5));               // one 8-byte read: the word and its prefix
+        const uint32_t rank = e.y + __popc(e.x & ((1u << (id & 31)) - 1u));
         if (uniq) uniq[rank] = (IdT)id;
         if (inverse) inverse[i] = (IdT)rank;
         if (first) atomicMin(reinterpret_cast<unsigned long long*>(first + rank), (unsigned long long)i);
@@ -161,27 +197,32 @@ int unique_impl(const char* who, const IdT* ids, int64_t n, int64_t vocab, void*
     RBX_REQUIRE(n_out, "%s: n_out (device int64[2]) is required", who);
     RBX_REQUIRE(ws && ws_have >= ws_bytes(vocab), "%s: workspace of %zu bytes needed (rbx_unique_ws_bytes), got %zu", who,
                 ws_bytes(vocab), ws_have);
-    RBX_REQUIRE((uintptr_t)ws % 8 == 0, "%s: workspace must be 8-byte aligned", who);
+    RBX_REQUIRE((uintptr_t)ws % 16 == 0, "%s: workspace must be 16-byte aligned", who);
     cudaStream_t st = rbx_cast_stream(stream);
     const int64_t W = words_of(vocab), NB = (W + kChunk - 1) / kChunk;
     const UniqueWs u = carve(ws, vocab);
-    cudaError_t e = cudaMemsetAsync(ws, 0, 64 + (size_t)W * 4, st);           // counters + bitmap
+    const bool dense = n * 4 >= vocab;                     // >= 1 id per 4 vocabulary entries: byte map, no atomics
+    cudaError_t e = dense ? cudaMemsetAsync(u.bytemap, 0, (size_t)W * 32, st)
+                          : cudaMemsetAsync(ws, 0, 64 + (size_t)W * 8, st);   // counters + (word, prefix) pairs
     if (e == cudaSuccess) e = cudaMemsetAsync(n_out, 0, 16, st);
     if (e != cudaSuccess) return rbx_fail(RBX_ERR_CUDA, "%s: memset: %s", who, cudaGetErrorString(e));
     const int64_t cap = (int64_t)rbx_sm_count() * 8;
     int64_t g = (n + kT - 1) / kT;
     if (g > cap) g = cap;
     if (g < 1) g = 1;
-    if (n > 0) k_mark<IdT><<<(int)g, kT, 0, st>>>(ids, n, vocab, u.bitmap, n_out);
-    k_count<<<(int)NB, kT, 0, st>>>(u.bitmap, W, u.blocksum);
+    if (n > 0) {
+        if (dense) k_mark_bytes<IdT><<<(int)g, kT, 0, st>>>(ids, n, vocab, u.bytemap, n_out);
+        else k_mark<IdT><<<(int)g, kT, 0, st>>>(ids, n, vocab, u.wp, n_out);
+    }
+    k_count<<<(int)NB, kT, 0, st>>>(u.wp, dense ? u.bytemap : nullptr, W, u.blocksum);
     k_scan_chunks<<<1, kT, 0, st>>>(u.blocksum, NB, n_out);
-    k_prefix<<<(int)NB, kT, 0, st>>>(u.bitmap, W, u.blocksum, u.wprefix);
+    k_prefix<<<(int)NB, kT, 0, st>>>(u.wp, W, u.blocksum);
     if (n > 0 && first) {
         const int64_t cap_u = n < vocab ? n : vocab;          // capacity of `first` (rbx_unique_ids_* contract)
         k_fill_i64<<<(int)((cap_u + kT - 1) / kT < cap ? (cap_u + kT - 1) / kT : cap), kT, 0, st>>>(first, cap_u, n);
     }
     if (n > 0 && (uniq || inverse || first))
-        k_inverse<IdT><<<(int)g, kT, 0, st>>>(ids, n, vocab, u.bitmap, u.wprefix, uniq, inverse, first);
+        k_inverse<IdT><<<(int)g, kT, 0, st>>>(ids, n, vocab, u.wp, uniq, inverse, first);
     RBX_LAUNCH_CHECK(who);
     return RBX_OK;
 }

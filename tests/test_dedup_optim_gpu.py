@@ -21,7 +21,8 @@ def _ops():
 # --------------------------------------------------------------------------------------- a14
 @pytest.mark.parametrize("dtype", [torch.int64, torch.int32])
 @pytest.mark.parametrize("n,vocab", [(1, 1), (7, 5), (90112, 10_000_001), (4096, 31), (65537, 65536), (300_000, 2_000_003),
-                                     (1000, 1 << 22)])
+                                     (1000, 1 << 22), (1_703_936, 1_000_012), (250_003, 1_000_012), (250_002, 1_000_012),
+                                     (33, 33), (100_000, 4097)])
 def test_unique_ids_matches_oracle(dtype, n, vocab):
     ops = _ops()
     rng = np.random.default_rng(n + vocab)
