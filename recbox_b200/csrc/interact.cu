@@ -309,9 +309,7 @@ __global__ void __launch_bounds__(kThreads) k_ip_fwd_warp(const float* __restric
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpc = blockDim.x >> 5;
     const int FB = (F + 3) >> 2, NT = FB * (FB + 1) / 2, P = F * (F - 1) / 2;
     int* sTile = reinterpret_cast<int*>(smem);                       // [NT] (ti << 8) | tj, ti <= tj
-    const int per_warp = slice_floats(F, D) + ((P + 3) & ~3);
-    float* sE = smem + ((NT + 3) & ~3) + (size_t)warp * per_warp;
-    float* sOut = sE + slice_floats(F, D);                           // [P] the sample's output row, written back coalesced
+    float* sE = smem + ((NT + 3) & ~3) + (size_t)warp * slice_floats(F, D);
     for (int ti = threadIdx.x; ti < FB; ti += blockDim.x)
         for (int tj = ti; tj < FB; ++tj) sTile[ti * FB - ti * (ti - 1) / 2 + (tj - ti)] = (ti << 8) | tj;
     zero_pad_rows<LPR>(sE, F, lane);
@@ -344,21 +342,30 @@ __global__ void __launch_bounds__(kThreads) k_ip_fwd_warp(const float* __restric
 #pragma unroll
                     for (int y = 0; y < 4; ++y) acc[x][y] = dot4(a[x], bb[y], acc[x][y]);
             }
+            // pair_index(i, j) = base(i) + j with base(i) = i (2F - i - 1) / 2 - i - 1
+            if (tj > ti && 4 * tj + 3 < F) {
+                // interior tile: all 16 pairs exist, no tests (the epilogue was half of the kernel's instructions, ncu r1z)
 #pragma unroll
-            for (int x = 0; x < 4; ++x) {
-                const int i = 4 * ti + x;
-                if (i >= F - 1) continue;
-                const int base = i * (2 * F - i - 1) / 2 - i - 1;          // pair_index(i, j) = base + j
+                for (int x = 0; x < 4; ++x) {
+                    const int i = 4 * ti + x;
+                    float* o = ob + (i * (2 * F - i - 1) / 2 - i - 1) + 4 * tj;
 #pragma unroll
-                for (int y = 0; y < 4; ++y) {
-                    const int j = 4 * tj + y;
-                    if (j > i && j < F) sOut[base + j] = acc[x][y];
+                    for (int y = 0; y < 4; ++y) o[y] = acc[x][y];
+                }
+            } else {
+#pragma unroll
+                for (int x = 0; x < 4; ++x) {
+                    const int i = 4 * ti + x;
+                    if (i >= F - 1) continue;
+                    const int base = i * (2 * F - i - 1) / 2 - i - 1;
+#pragma unroll
+                    for (int y = 0; y < 4; ++y) {
+                        const int j = 4 * tj + y;
+                        if (j > i && j < F) ob[base + j] = acc[x][y];
+                    }
                 }
             }
         }
-        // 741 scattered 4-byte stores per sample would each cost an L2 sector write; one coalesced pass instead
-        __syncwarp();
-        for (int i = lane; i < P; i += 32) ob[i] = sOut[i];
     }
 }
 
@@ -368,6 +375,19 @@ __global__ void __launch_bounds__(kThreads) k_ip_fwd_warp(const float* __restric
 // 8 row blocks of 5 x 4 chunks); per j it reads RPT scalars of G (lanes of a row block share the address) and one
 // 16-byte chunk of e_j for 4*RPT FMAs.  (The first version used 4-row tasks: 40 tasks = two rounds, the second with
 // 8 lanes, and two LDS.128 per 16 FMAs -- 0.28 of the HBM roofline.)
+__device__ __forceinline__ void cp_async_16(void* smem_dst, const void* gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_4(void* smem_dst, const void* gsrc) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit_group() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+// Per-warp slice: sE[2] (double-buffered sample rows) | sW (the sample's P upstream gradients, linear) | sG (F x GS).
+// While sample b is in the FMA loop, the rows and gradients of the warp's NEXT sample stream in with cp.async (the first
+// version loaded, then computed, with nothing in flight: `long_scoreboard` was its top stall and it ran at 0.41 of the
+// roofline, profiles/r1_ncu_summary.md).
 template <int LPR, int RPT>
 __global__ void __launch_bounds__(kThreads) k_ip_bwd_warp(const float* __restrict__ E, const float* __restrict__ dout,
                                                          float* __restrict__ dE, int64_t B, int F) {
@@ -377,26 +397,42 @@ __global__ void __launch_bounds__(kThreads) k_ip_bwd_warp(const float* __restric
     const int P = F * (F - 1) / 2;
     const int NB = (F + RPT - 1) / RPT;               // row blocks
     const int GS = NB * RPT + 1;                      // odd-ish stride: the transposed scatter below spreads over banks
+    const int SL = slice_floats(F, D), P4 = (P + 3) & ~3, G4 = (F * GS + 3) & ~3;
     int* sPair = reinterpret_cast<int*>(smem);                        // [P] (i << 16) | j
-    const int per_warp = slice_floats(F, D) + ((F * GS + 3) & ~3);
-    float* sE = smem + ((P + 3) & ~3) + (size_t)warp * per_warp;
-    float* sG = sE + slice_floats(F, D);
+    float* sE0 = smem + P4 + (size_t)warp * (2 * SL + P4 + G4);
+    float* sE1 = sE0 + SL;
+    float* sW = sE1 + SL;
+    float* sG = sW + P4;
     for (int i = threadIdx.x; i < F; i += blockDim.x)
         for (int j = i + 1; j < F; ++j) sPair[pair_index(i, j, F)] = (i << 16) | j;
+    zero_pad_rows<LPR>(sE0, F, lane);
+    zero_pad_rows<LPR>(sE1, F, lane);
     for (int t = lane; t < F * GS; t += 32) sG[t] = 0.f;               // diagonal and padding stay zero
     __syncthreads();
     const int64_t gw = (int64_t)blockIdx.x * wpc + warp, nw = (int64_t)gridDim.x * wpc;
     const int NTask = NB * LPR;
-    for (int64_t b = gw; b < B; b += nw) {
-        __syncwarp();
-        stage_sample<LPR>(sE, E + (size_t)b * F * D, F, lane);
+    auto prefetch = [&](int64_t bn, float* sEn) {
+        const float* Eb = E + (size_t)bn * F * D;
+        for (int t = lane; t < F * LPR; t += 32) cp_async_16(sEn + row_off(t / LPR, D) + 4 * (t & (LPR - 1)), Eb + 4 * (size_t)t);
+        const float* wb = dout + (size_t)bn * P;
+        for (int p = lane; p < P; p += 32) cp_async_4(sW + p, wb + p);
+    };
+    if (gw < B) prefetch(gw, sE0);
+    cp_async_commit_group();
+    int cur = 0;
+    for (int64_t b = gw; b < B; b += nw, cur ^= 1) {
+        cp_async_wait_all();
+        __syncwarp();                                  // sample b has landed; everyone is done with sample b - nw
+        const float* sE = cur ? sE1 : sE0;
         for (int p = lane; p < P; p += 32) {
             const int ij = sPair[p], i = ij >> 16, j = ij & 0xffff;
-            const float w = ld_stream_f1(dout + (size_t)b * P + p);
+            const float w = sW[p];
             sG[j * GS + i] = w;
             sG[i * GS + j] = w;
         }
-        __syncwarp();
+        __syncwarp();                                  // sW is free again, sG is complete
+        if (b + nw < B) prefetch(b + nw, cur ? sE0 : sE1);
+        cp_async_commit_group();
         float* db = dE + (size_t)b * F * D;
         for (int t = lane; t < NTask; t += 32) {
             const int ib = t / LPR, c = t & (LPR - 1);
@@ -416,6 +452,7 @@ __global__ void __launch_bounds__(kThreads) k_ip_bwd_warp(const float* __restric
                 if (ib * RPT + x < F) st_stream_f4(db + (size_t)(ib * RPT + x) * D + 4 * c, acc[x]);
         }
     }
+    cp_async_wait_all();
 }
 
 // mode 3 forward: out[b, p, :] = e_i * e_j.  LPR lanes per pair, 32/LPR pairs per step, 512-byte coalesced stores.
@@ -760,7 +797,7 @@ int rbx_interact_fwd(const float* E, float* out, int64_t B, int F, int D, int mo
             const int FB = (F + 3) / 4;
             size_t wsmem = 0;
             const size_t fixed = mode == 2 ? (size_t)((FB * (FB + 1) / 2 + 3) & ~3) : ((P + 3) & ~(size_t)3);
-            const int wpc = warps_for(fixed, slice_floats(F, D) + (mode == 2 ? ((P + 3) & ~(size_t)3) : 0), &wsmem);
+            const int wpc = warps_for(fixed, slice_floats(F, D), &wsmem);
             if (wpc > 0) {
                 if (mode == 2) {
                     RBX_DISPATCH_LPR(D, (k_ip_fwd_warp<LPR><<<warp_grid(k_ip_fwd_warp<LPR>, wpc, wsmem, B), wpc * 32, wsmem, st>>>(E, out, B, F)));
@@ -812,8 +849,19 @@ int rbx_interact_bwd(const float* E, const float* dout, float* dE, int64_t B, in
             rpt = rpt < 1 ? 1 : (rpt > 8 ? 8 : rpt);
             const int NBk = (F + rpt - 1) / rpt, GS = NBk * rpt + 1;
             const size_t fixed = mode == 2 ? ((P + 3) & ~(size_t)3) : 0;
-            const size_t per_warp = mode == 2 ? (size_t)slice_floats(F, D) + (((size_t)F * GS + 3) & ~(size_t)3) : 2 * (size_t)slice_floats(F, D);
-            const int wpc = warps_for(fixed, per_warp, &wsmem);
+            const size_t per_warp = mode == 2 ? 2 * (size_t)slice_floats(F, D) + ((P + 3) & ~(size_t)3) + (((size_t)F * GS + 3) & ~(size_t)3)
+                                              : 2 * (size_t)slice_floats(F, D);
+            int wpc = warps_for(fixed, per_warp, &wsmem);
+            if (mode == 2 && wpc > 0) {       // most resident warps per SM (227 KB, ~1 KB reserved per CTA), not per CTA
+                int best = wpc, best_warps = 0;
+                for (int w = wpc; w >= 1; --w) {
+                    const size_t cta = (fixed + (size_t)w * per_warp) * 4 + 1024;
+                    const int warps = (int)((227 * 1024) / cta) * w;
+                    if (warps > best_warps) { best_warps = warps; best = w; }
+                }
+                wpc = best;
+                wsmem = (fixed + (size_t)wpc * per_warp) * 4;
+            }
             if (wpc > 0) {
                 if (mode == 2) {
 #define RBX_IPB(R) RBX_DISPATCH_LPR(D, (k_ip_bwd_warp<LPR, R><<<warp_grid(k_ip_bwd_warp<LPR, R>, wpc, wsmem, B), wpc * 32, wsmem, st>>>(E, dout, dE, B, F)))
