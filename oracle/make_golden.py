@@ -374,6 +374,45 @@ def golden_interaction_machine(L):
     npz("interaction_machine", **out)
 
 
+def golden_sasrec_gather():
+    """a11: rechub SASRec (third_party/rechub/models/matching/sasrec.py:98-107) -- the three shared-table lookups
+    `item_emb(x, features)` [B,3,L,D], the token dots against the model's own sequence output, and the item-table gradient
+    that BCE on those logits sends back through the lookups."""
+    ref_shim.install_rechub()
+    from recbox.third_party.rechub.basic.features import SequenceFeature
+    from recbox.third_party.rechub.models.matching.sasrec import SASRec
+    torch.manual_seed(61)
+    V, D, L, B = 50, 8, 12, 9
+    feats = [SequenceFeature("seq", vocab_size=V, embed_dim=D, pooling="concat", padding_idx=0),
+             SequenceFeature("pos", vocab_size=V, embed_dim=D, pooling="concat", shared_with="seq"),
+             SequenceFeature("neg", vocab_size=V, embed_dim=D, pooling="concat", shared_with="seq")]
+    model = SASRec(feats, max_len=L, dropout_rate=0.0, num_blocks=1, num_heads=1)
+    model.eval()
+    table = [p for n, p in model.item_emb.named_parameters()][0]
+    with torch.no_grad():
+        table.copy_(torch.randn(V, D) * 0.3)
+    rng = np.random.default_rng(62)
+    x = {}
+    lens = rng.integers(2, L + 1, size=B)
+    for k in ("seq", "pos", "neg"):
+        a = rng.integers(1, V, size=(B, L))
+        for b in range(B):
+            a[b, :L - lens[b]] = 0                     # left padding with the pad id
+        x[k] = a
+    emb = model.item_emb({k: torch.from_numpy(v) for k, v in x.items()}, model.features)        # [B,3,L,D]
+    xt = {k: torch.from_numpy(v) for k, v in x.items()}
+    pos_logits, neg_logits = model(xt)
+    loss = torch.nn.functional.binary_cross_entropy_with_logits(pos_logits, torch.ones_like(pos_logits)) + \
+        torch.nn.functional.binary_cross_entropy_with_logits(neg_logits, torch.zeros_like(neg_logits))
+    loss.backward()
+    # the sequence output the logits were formed with (recomputed; seq_forward mutates its input in place)
+    with torch.no_grad():
+        e2 = model.item_emb({k: torch.from_numpy(v) for k, v in x.items()}, model.features)
+        seq_out = model.seq_forward(xt, e2[:, 0].clone())
+    npz("sasrec_gather", table=table.detach(), seq=x["seq"], pos=x["pos"], neg=x["neg"], emb=emb.detach(), seq_out=seq_out,
+        pos_logits=pos_logits.detach(), neg_logits=neg_logits.detach(), table_grad=table.grad)
+
+
 class _NumpyFlatIP(object):
     """Stand-in for faiss.IndexFlatIP (faiss is absent from this image): exact float32 inner products, descending,
     (-3.4028235e38, -1) padding -- enough for the reference's FaissIndex / evaluate_block to run unmodified."""
@@ -449,6 +488,8 @@ def main(only=None):
         return golden_retrieval()
     if only == "interaction_machine":
         return golden_interaction_machine(L)
+    if only == "sasrec_gather":
+        return golden_sasrec_gather()
     with tempfile.TemporaryDirectory() as tmp:
         golden_interaction(L)
         golden_pooling(L)
@@ -464,6 +505,7 @@ def main(only=None):
     golden_collate_unique()
     golden_retrieval()
     golden_interaction_machine(L)
+    golden_sasrec_gather()
 
 
 if __name__ == "__main__":

@@ -321,3 +321,39 @@ def test_interaction_machine_golden(order):
     P = oracle.power_sums(g[tag + "X"], order)
     assert P.shape == (23, order, 8)
     same_sum(P[:, 0], g[tag + "X"].sum(1), "p1")
+
+
+# ------------------------------------------------------------------------------- a11 SASRec gathers + token dots
+def test_sasrec_gather_and_token_dot_golden():
+    """oracle.sasrec_gather / token_dot against rechub's SASRec (third_party/rechub/models/matching/sasrec.py:98-107):
+    the [B,3,L,D] shared-table lookup is bit-exact, the logits are the token dots with the model's own sequence
+    output, and the lookups route the gradient back into one table (pad row 0 of `seq` gets none)."""
+    g = load("sasrec_gather")
+    table = g["table"].clone().requires_grad_(True)
+    emb = oracle.sasrec_gather(table, g["seq"], g["pos"], g["neg"], padding_idx=0)
+    assert emb.shape == g["emb"].shape and torch.equal(emb, g["emb"])
+    same_sum(oracle.token_dot(g["seq_out"], emb[:, 1]), g["pos_logits"], "pos_logits")
+    same_sum(oracle.token_dot(g["seq_out"], emb[:, 2]), g["neg_logits"], "neg_logits")
+    # rows never looked up (and the pad row) carry no gradient in the reference either
+    used = torch.zeros(table.shape[0], dtype=torch.bool)
+    for k in ("seq", "pos", "neg"):
+        used[g[k].reshape(-1).long()] = True
+    used[0] = False
+    assert torch.equal(g["table_grad"][~used], torch.zeros_like(g["table_grad"][~used]))
+    assert float(g["table_grad"][used].abs().sum()) > 0
+
+
+def test_inbatch_scores_and_mlp_restatements():
+    """a10 in-batch score matrix (youtube_sbc.py:67: cosine similarity of every user with every item, positives on the
+    diagonal) and the a13 dense tail used by DeepFMOracle."""
+    g = torch.Generator().manual_seed(3)
+    u, v = torch.randn(5, 4, generator=g), torch.randn(5, 4, generator=g)
+    s = oracle.inbatch_scores(u, v)
+    assert s.shape == (5, 5)
+    for i in range(5):
+        for j in range(5):
+            assert abs(float(s[i, j]) - float((u[i] * v[j]).sum() / (u[i].norm() * v[j].norm()))) < 1e-6
+    x = torch.randn(3, 4, generator=g)
+    W1, b1, W2, b2 = torch.randn(6, 4, generator=g), torch.randn(6, generator=g), torch.randn(1, 6, generator=g), torch.randn(1, generator=g)
+    want = torch.relu(x @ W1.t() + b1) @ W2.t() + b2
+    assert torch.allclose(oracle.mlp(x, [(W1, b1), (W2, b2)]), want, atol=1e-6)
