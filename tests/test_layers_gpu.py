@@ -305,3 +305,19 @@ def test_interaction_machine_matches_reference(order, bn):
     assert_close(X.grad, g[tag + "dX"], atol_scale=5e-5, what="dX")
     for k, p_ in m.named_parameters():
         assert_close(p_.grad, g[tag + "grad." + k], atol_scale=5e-5, what=k)
+
+
+def test_sasrec_lookups_and_token_dots_match_rechub():
+    """a11 against the golden minted from rechub's SASRec (sasrec.py:98-107): the three shared-table lookups are one
+    rbx_gather_rows call (bit-exact), the per-token logits one rbx_rowdot call each."""
+    from recbox_b200 import ops
+    g = load("sasrec_gather")
+    table = g["table"].to(DEV)
+    ids = torch.stack([g["seq"], g["pos"], g["neg"]], 1).to(torch.int32).to(DEV)          # [B,3,L]
+    emb = ops.gather_rows(table, ids)
+    assert torch.equal(emb.cpu(), g["emb"])
+    B, _, L, D = emb.shape
+    so = g["seq_out"].to(DEV).reshape(B * L, D).contiguous()
+    for k, name in ((1, "pos_logits"), (2, "neg_logits")):
+        y = ops.rowdot_fwd(so, emb[:, k].reshape(B * L, 1, D).contiguous())
+        assert_close(y.view(B, L), g[name], atol_scale=2e-5, what=name)
