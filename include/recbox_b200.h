@@ -61,26 +61,34 @@ long long   rbx_l2_set_persisting_bytes(long long bytes);
  *   rows[b, s]   = (int32)trunc(batch[b,c]) + field_off[s]      (kind 1)
  *   dense_x[b,s] = (float)batch[b,c]                            (kind 2)
  *   label[b]     = (float)batch[b,c]                            (kind 3)
+ * field_rows[s] (nullable) is the vocabulary size of slot s: an id outside [0, field_rows[s]) -- where
+ * nn.Embedding raises IndexError -- becomes row -1 (reads as a zero row, receives no gradient) instead of
+ * aliasing a neighbouring feature's rows in the fused table, and is counted in n_bad[0] (DEVICE int32,
+ * nullable, accumulated; the caller zeroes it).
  * ------------------------------------------------------------------------------------------ */
 int rbx_split_batch_f64(const double* batch /*DEVICE [B, ld]*/, int64_t B, int n_cols, int64_t ld,
                         const int8_t* col_kind /*HOST [n_cols]*/,
                         const int16_t* col_slot /*HOST [n_cols]*/,
-                        const int64_t* field_off /*HOST [F]*/, int F, int Fn,
+                        const int64_t* field_off /*HOST [F]*/,
+                        const int64_t* field_rows /*HOST [F] | NULL*/, int F, int Fn,
                         int32_t* rows /*DEVICE [B,F] | NULL*/,
                         float* dense_x /*DEVICE [B,Fn] | NULL*/,
                         float* label /*DEVICE [B] | NULL*/,
+                        int32_t* n_bad /*DEVICE [1] | NULL*/,
                         rbx_stream_t stream);
 
 /* Same conversion for the dict-of-columns form of X (feature_embedding.py:188-214 receives
  * {feature: Tensor[B]}): up to RBX_MAX_SLOTS separate column pointers with element strides.
  * dtype codes: 0 = float64, 1 = float32, 2 = int64, 3 = int32.  Writes out[b, s] for every
- * column s as int32 (+ add[s]) when as_rows != 0, else as float32. */
+ * column s as int32 (+ add[s]) when as_rows != 0, else as float32.  vocab[s] / n_bad: as field_rows / n_bad above. */
 int rbx_pack_columns(const void* const* cols /*HOST [n] of DEVICE ptrs*/,
                      const int64_t* strides /*HOST [n], in elements*/,
                      const int8_t* dtypes /*HOST [n]*/,
                      const int64_t* add /*HOST [n] | NULL*/,
+                     const int64_t* vocab /*HOST [n] | NULL*/,
                      int n, int64_t B, int as_rows,
                      void* out /*DEVICE [B, n] int32 or float32*/,
+                     int32_t* n_bad /*DEVICE [1] | NULL*/,
                      rbx_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------

@@ -77,8 +77,8 @@ SIGNATURES = {
     "rbx_last_error": [],
     "rbx_device_sm_count": [],
     "rbx_l2_set_persisting_bytes": [_c.c_longlong],
-    "rbx_split_batch_f64": [_P, _I64, _I, _I64, _P, _P, _P, _I, _I, _P, _P, _P, _P],
-    "rbx_pack_columns": [_P, _P, _P, _P, _I, _I64, _I, _P, _P],
+    "rbx_split_batch_f64": [_P, _I64, _I, _I64, _P, _P, _P, _P, _I, _I, _P, _P, _P, _P, _P],
+    "rbx_pack_columns": [_P, _P, _P, _P, _P, _I, _I64, _I, _P, _P, _P],
     "rbx_embed_fm_fwd": [_P] * 15 + [_I64, _I64, _I, _I, _I, _I, _P],
     "rbx_embed_fm_bwd": [_P] * 19 + [_I64, _I64, _I, _I, _I, _I, _P],
     "rbx_gather_rows": [_P, _P, _P, _I64, _I, _P],

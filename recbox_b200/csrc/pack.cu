@@ -14,7 +14,9 @@ struct SplitParams {
     float* label;
     int64_t B, ld;
     int n_cols, F, Fn;
+    int32_t* n_bad;              // [1] device counter of ids outside their slot's vocabulary | NULL
     int32_t col_add[kMaxCols];   // field offset of the column's slot (kind 1)
+    int32_t col_rows[kMaxCols];  // vocabulary size of the column's slot (kind 1), 0 = unchecked
     int16_t col_slot[kMaxCols];
     int8_t col_kind[kMaxCols];
 };
@@ -28,10 +30,12 @@ struct SplitParams {
 constexpr int kSplitRows = 32;
 __global__ void __launch_bounds__(256) k_split_batch(const __grid_constant__ SplitParams p) {
     __shared__ int32_t s_add[kMaxCols];
+    __shared__ int32_t s_rows[kMaxCols];
     __shared__ int16_t s_slot[kMaxCols];
     __shared__ int8_t s_kind[kMaxCols];
     for (int c = threadIdx.x; c < p.n_cols; c += blockDim.x) {
         s_add[c] = p.col_add[c];
+        s_rows[c] = p.col_rows[c];
         s_slot[c] = p.col_slot[c];
         s_kind[c] = p.col_kind[c];
     }
@@ -49,7 +53,13 @@ __global__ void __launch_bounds__(256) k_split_batch(const __grid_constant__ Spl
             const double v = __ldcs(p.batch + b * p.ld + c);
             const int s = s_slot[c];
             if (kind == 1) {
-                p.rows[b * p.F + s] = (int32_t)(int64_t)v + s_add[c];   // .long(): truncation toward zero
+                const int64_t id = (int64_t)v;                          // .long(): truncation toward zero
+                int32_t row = (int32_t)id + s_add[c];
+                if (s_rows[c] > 0 && (id < 0 || id >= s_rows[c])) {     // nn.Embedding would raise: never alias a neighbour's rows
+                    row = -1;
+                    if (p.n_bad) atomicAdd(p.n_bad, 1);
+                }
+                p.rows[b * p.F + s] = row;
             } else if (kind == 2) {
                 p.dense_x[b * p.Fn + s] = (float)v;                     // .float(): round to nearest
             } else {
@@ -64,8 +74,10 @@ struct PackParams {
     const void* col[kPackCols];
     int64_t stride[kPackCols];
     int64_t add[kPackCols];
+    int64_t rows[kPackCols];     // vocabulary size per column (as_rows), 0 = unchecked
     int8_t dtype[kPackCols];
     void* out;
+    int32_t* n_bad;
     int64_t B;
     int n_total, c0, n_here, as_rows;
 };
@@ -96,6 +108,10 @@ __global__ void __launch_bounds__(256) k_pack_columns(const __grid_constant__ Pa
                     else if (dt == 3) id = reinterpret_cast<const int32_t*>(p.col[c])[b * p.stride[c]];
                     else id = (int64_t)load_any(p.col[c], b * p.stride[c], dt);
                     bits = (int32_t)(id + p.add[c]);
+                    if (p.rows[c] > 0 && (id < 0 || id >= p.rows[c])) {
+                        bits = -1;
+                        if (p.n_bad) atomicAdd(p.n_bad, 1);
+                    }
                 } else {
                     bits = __float_as_int((float)load_any(p.col[c], b * p.stride[c], dt));
                 }
@@ -118,8 +134,8 @@ __global__ void __launch_bounds__(256) k_pack_columns(const __grid_constant__ Pa
 extern "C" {
 
 int rbx_split_batch_f64(const double* batch, int64_t B, int n_cols, int64_t ld, const int8_t* col_kind,
-                        const int16_t* col_slot, const int64_t* field_off, int F, int Fn, int32_t* rows,
-                        float* dense_x, float* label, rbx_stream_t stream) {
+                        const int16_t* col_slot, const int64_t* field_off, const int64_t* field_rows, int F, int Fn,
+                        int32_t* rows, float* dense_x, float* label, int32_t* n_bad, rbx_stream_t stream) {
     const char* who = "rbx_split_batch_f64";
     RBX_REQUIRE(B >= 0 && n_cols >= 0 && ld >= n_cols, "%s: bad shape", who);
     RBX_REQUIRE(n_cols <= kMaxCols, "%s: n_cols=%d > %d", who, n_cols, kMaxCols);
@@ -127,7 +143,7 @@ int rbx_split_batch_f64(const double* batch, int64_t B, int n_cols, int64_t ld, 
     RBX_REQUIRE(batch && col_kind && col_slot, "%s: null pointer", who);
     SplitParams p;
     p.batch = batch; p.rows = rows; p.dense_x = dense_x; p.label = label; p.B = B; p.ld = ld;
-    p.n_cols = n_cols; p.F = F; p.Fn = Fn;
+    p.n_cols = n_cols; p.F = F; p.Fn = Fn; p.n_bad = n_bad;
     for (int c = 0; c < n_cols; ++c) {
         const int k = col_kind[c], s = col_slot[c];
         RBX_REQUIRE(k >= 0 && k <= 3, "%s: col_kind[%d]=%d", who, c, k);
@@ -136,8 +152,12 @@ int rbx_split_batch_f64(const double* batch, int64_t B, int n_cols, int64_t ld, 
             const int64_t off = field_off ? field_off[s] : 0;
             RBX_REQUIRE(off >= 0 && off <= INT32_MAX, "%s: field_off[%d] outside int32", who, s);
             p.col_add[c] = (int32_t)off;
+            const int64_t nr = field_rows ? field_rows[s] : 0;
+            RBX_REQUIRE(nr >= 0 && nr <= INT32_MAX, "%s: field_rows[%d] outside int32", who, s);
+            p.col_rows[c] = (int32_t)nr;
         } else {
             p.col_add[c] = 0;
+            p.col_rows[c] = 0;
         }
         if (k == 2) RBX_REQUIRE(dense_x && s >= 0 && s < Fn, "%s: column %d -> numeric slot %d of %d", who, c, s, Fn);
         if (k == 3) RBX_REQUIRE(label != nullptr, "%s: label column without label output", who);
@@ -153,14 +173,14 @@ int rbx_split_batch_f64(const double* batch, int64_t B, int n_cols, int64_t ld, 
 }
 
 int rbx_pack_columns(const void* const* cols, const int64_t* strides, const int8_t* dtypes, const int64_t* add,
-                     int n, int64_t B, int as_rows, void* out, rbx_stream_t stream) {
+                     const int64_t* vocab, int n, int64_t B, int as_rows, void* out, int32_t* n_bad, rbx_stream_t stream) {
     const char* who = "rbx_pack_columns";
     RBX_REQUIRE(n >= 0 && B >= 0, "%s: negative size", who);
     if (n == 0 || B == 0) return RBX_OK;
     RBX_REQUIRE(cols && strides && dtypes && out, "%s: null pointer", who);
     for (int c0 = 0; c0 < n; c0 += kPackCols) {
         PackParams p;
-        p.out = out; p.B = B; p.n_total = n; p.c0 = c0; p.as_rows = as_rows;
+        p.out = out; p.B = B; p.n_total = n; p.c0 = c0; p.as_rows = as_rows; p.n_bad = n_bad;
         p.n_here = (n - c0 < kPackCols) ? n - c0 : kPackCols;
         for (int c = 0; c < p.n_here; ++c) {
             RBX_REQUIRE(cols[c0 + c] != nullptr, "%s: column %d is null", who, c0 + c);
@@ -169,6 +189,7 @@ int rbx_pack_columns(const void* const* cols, const int64_t* strides, const int8
             p.stride[c] = strides[c0 + c];
             p.dtype[c] = dtypes[c0 + c];
             p.add[c] = add ? add[c0 + c] : 0;
+            p.rows[c] = (vocab && as_rows) ? vocab[c0 + c] : 0;
         }
         int64_t ctas = (B + 31) / 32;
         const int64_t cap = (int64_t)rbx_sm_count() * 8;

@@ -106,6 +106,9 @@ def _pool_mode(module):
 # =================================================================================================
 # fused parameter storage
 # =================================================================================================
+_FUSE_GEN = [0]          # bumped by every _FusedStore.fuse(); launch-plan caches are valid for one generation
+
+
 class _Group(object):
     """All unique embedding modules of one embedding dim, stored back to back."""
 
@@ -142,6 +145,7 @@ class _FusedStore(object):
         self.fuse()
 
     def fuse(self):
+        _FUSE_GEN[0] += 1              # every cached launch plan holds Parameter objects / offsets of the old fusion
         for g in self.groups.values():
             ref = (g.emb[0] if g.emb else g.lin[0]).weight
             dev, dt = ref.device, ref.dtype
@@ -424,13 +428,77 @@ def get_labels(model, inputs):
 
 
 class _EmbDict(OrderedDict):
-    """OrderedDict of per-feature embeddings that remembers the stacked tensor they are views of."""
-    stacked = None
+    """OrderedDict of per-feature embeddings that remembers the stacked tensor they are views of.
+
+    The reference's dict2tensor always stacks the CURRENT dict values (feature_embedding.py:169-186), and model code is
+    free to replace an entry first (DIN-style `feature_emb_dict[seq_field] = pooled`).  So any mutation after the producer
+    has sealed the dict drops the cached stack, and so does an in-place write into it (checked through `_version`)."""
+    _stacked = None
+    _stacked_version = -1
+    _sealed = False
     names = ()
+
+    @property
+    def stacked(self):
+        E = self._stacked
+        if E is not None and E._version != self._stacked_version:
+            self._stacked = E = None          # somebody wrote into E (or into one of its views) in place
+        return E
+
+    @stacked.setter
+    def stacked(self, E):
+        self._stacked = E
+        self._stacked_version = E._version if E is not None else -1
+        self._sealed = E is not None
+
+    def _touch(self):
+        if self._sealed:
+            self._stacked = None
+
+    def __setitem__(self, key, value):
+        self._touch()
+        OrderedDict.__setitem__(self, key, value)
+
+    def __delitem__(self, key):
+        self._touch()
+        OrderedDict.__delitem__(self, key)
+
+    def pop(self, *a, **k):
+        self._touch()
+        return OrderedDict.pop(self, *a, **k)
+
+    def popitem(self, *a, **k):
+        self._touch()
+        return OrderedDict.popitem(self, *a, **k)
+
+    def update(self, *a, **k):
+        self._touch()
+        return OrderedDict.update(self, *a, **k)
+
+    def setdefault(self, key, default=None):
+        if key not in self:
+            self._touch()
+        return OrderedDict.setdefault(self, key, default)
+
+    def clear(self):
+        self._touch()
+        OrderedDict.clear(self)
+
+    def move_to_end(self, *a, **k):
+        self._touch()
+        return OrderedDict.move_to_end(self, *a, **k)
+
+
+def _stash_of(feature_emb):
+    """The fused launch's by-products riding on its E tensor -- ignored once E has been modified in place."""
+    st = getattr(feature_emb, "_rbx_stash", None)
+    if st is not None and st.version != feature_emb._version:
+        return None
+    return st
 
 
 class _Stash(object):
-    __slots__ = ("X", "fm", "lr", "lr_owner", "producer", "full")
+    __slots__ = ("X", "fm", "lr", "lr_owner", "producer", "full", "version")
 
 
 # =================================================================================================
@@ -449,13 +517,35 @@ class _FusedDictBase(nn.Module):
     def _build_store(self):
         self._store = _FusedStore(list(self.embedding_layers.values()))
         self._calls = {}
+        self._calls_gen = _FUSE_GEN[0]
         self._lr_partner = None
+
+    def _sync_store(self):
+        """Re-fuse if a parameter was re-pointed (`emb.weight = nn.Parameter(...)`, pretrained weights loaded after
+        construction), and drop every cached launch plan made before the last fusion of ANY store: plans hold the
+        Parameter objects autograd routes gradients to, and the partner LR module's as well."""
+        self._store.ensure()
+        if self._calls_gen != _FUSE_GEN[0]:
+            self._calls = {}
+            self._calls_gen = _FUSE_GEN[0]
+
+    def __getstate__(self):
+        # the store keys its offsets by id(module) and aliases one allocation: rebuilt on unpickle
+        state = dict(self.__dict__)
+        for k in ("_store", "_calls", "_calls_gen", "_lr_partner"):
+            state.pop(k, None)
+        return state
+
+    def __setstate__(self, state):
+        super(_FusedDictBase, self).__setstate__(state)
+        self._build_store()
 
     def _apply(self, fn, *args, **kwargs):
         out = super(_FusedDictBase, self)._apply(fn, *args, **kwargs)
         if getattr(self, "_store", None) is not None:
             self._store.fuse()          # Module.to()/cuda()/float() re-pointed every parameter
             self._calls = {}
+            self._calls_gen = _FUSE_GEN[0]
         return out
 
     def __deepcopy__(self, memo):
@@ -464,7 +554,7 @@ class _FusedDictBase(nn.Module):
         new = cls.__new__(cls)
         memo[id(self)] = new
         for k, v in self.__dict__.items():
-            if k in ("_store", "_calls", "_lr_partner"):
+            if k in ("_store", "_calls", "_calls_gen", "_lr_partner"):
                 continue
             setattr(new, k, copy.deepcopy(v, memo))
         new._build_store()
@@ -544,7 +634,7 @@ class _FusedDictBase(nn.Module):
         for n in seq_pool:
             m = self.embedding_layers[n]
             o = g.emb_off[id(m)]
-            c.seq.append({"name": n, "pos": pos[n], "off": o, "mode": _pool_mode(enc[n]),
+            c.seq.append({"name": n, "pos": pos[n], "off": o, "mode": _pool_mode(enc[n]), "vocab": m.num_embeddings,
                           "pad_row": -1 if m.padding_idx is None else o + m.padding_idx})
         params, kinds = [], []
         for i, m in enumerate(g.emb):
@@ -571,11 +661,25 @@ class _FusedDictBase(nn.Module):
                 kinds.append(("bias", 0))
             c.lr_emb_sizes = [m.num_embeddings for m in lg.emb]
         c.params, c.kinds = params, kinds
-        c_names = {"cats": cats, "nums": nums, "offs": offs}
+        c_names = {"cats": cats, "nums": nums, "offs": offs,
+                   "vocab": [self.embedding_layers[n].num_embeddings for n in cats]}
         return c, c_names
 
     # -- packing ---------------------------------------------------------------------------------
-    def _pack(self, inputs, cats, nums, offs):
+    def _bad_counter(self, dev):
+        """int32 device counter of ids that fell outside their feature's vocabulary (where nn.Embedding raises
+        IndexError); such ids read a zero row and get no gradient.  `out_of_range_ids()` reads it (synchronises)."""
+        c = self.__dict__.get("_n_bad")
+        if c is None or c.device != dev:
+            c = torch.zeros(1, dtype=I32, device=dev)
+            self.__dict__["_n_bad"] = c
+        return c
+
+    def out_of_range_ids(self):
+        c = self.__dict__.get("_n_bad")
+        return int(c.item()) if c is not None else 0
+
+    def _pack(self, inputs, cats, nums, offs, vocab=None):
         fm = self._feature_map
         if isinstance(inputs, PackedInputs) and inputs.feature_map is fm and inputs.batch.is_cuda \
                 and inputs.batch.dtype == torch.float64 and inputs.batch.stride(1) == 1:
@@ -587,7 +691,8 @@ class _FusedDictBase(nn.Module):
             for i, n in enumerate(nums):
                 ci = fm.get_column_index(n)
                 kind[ci], slot[ci] = 2, i
-            rows, dense_x, _ = ops.split_batch(inputs.batch, kind, slot, offs, len(cats), len(nums), want_label=False)
+            rows, dense_x, _ = ops.split_batch(inputs.batch, kind, slot, offs, len(cats), len(nums), want_label=False,
+                                               field_rows=vocab, n_bad=self._bad_counter(inputs.batch.device) if vocab else None)
             return rows, dense_x
         rows = dense_x = None
         if isinstance(inputs, PackedColumns):
@@ -601,7 +706,9 @@ class _FusedDictBase(nn.Module):
             if nums and pb.dense is not None and pb.dense.is_cuda and list(nums) == list(pb.num_names):
                 dense_x = pb.dense
         if cats and rows is None:
-            rows = ops.pack_columns([self._col(inputs[n]) for n in cats], add=offs, as_rows=True)
+            cols = [self._col(inputs[n]) for n in cats]
+            rows = ops.pack_columns(cols, add=offs, as_rows=True, vocab=vocab,
+                                    n_bad=self._bad_counter(cols[0].device) if vocab else None)
         if nums and dense_x is None:
             dense_x = ops.pack_columns([self._col(inputs[n]) for n in nums], as_rows=False)
         return rows, dense_x
@@ -615,7 +722,10 @@ class _FusedDictBase(nn.Module):
     # -- the forward all variants share ------------------------------------------------------------
     def _embed(self, inputs, key, names):
         """-> _EmbDict of per-feature embeddings for `names` (in order)."""
-        self._store.ensure()
+        lr_partner = self._lr_partner() if self._lr_partner is not None else None
+        if lr_partner is not None:      # its parameters ride in this launch: a re-fusion there invalidates our plans too
+            lr_partner.embedding_layer.embedding_layer._sync_store()
+        self._sync_store()
         for g in self._store.groups.values():
             ref = g.table if g.table is not None else g.dense_w
             if not ref.is_cuda:
@@ -634,17 +744,19 @@ class _FusedDictBase(nn.Module):
                     pc = self._make_call(names, plan["fused"], plan["D"], partner) + (partner,)
                     plan["lr_call"] = pc
                 call, cn, use_lr = pc[0], pc[1], partner
-            rows, dense_x = self._pack(inputs, cn["cats"], cn["nums"], cn["offs"])
-            seq_ids = tuple(self._seq_rows(inputs[sq["name"]], sq["off"]) for sq in call.seq)
+            rows, dense_x = self._pack(inputs, cn["cats"], cn["nums"], cn["offs"], cn.get("vocab"))
+            seq_ids = tuple(self._seq_rows(inputs[sq["name"]], sq["off"], sq["vocab"],
+                                          self._bad_counter(inputs[sq["name"]].device)) for sq in call.seq)
             E, fm, lr = _FusedEmbedFn.apply(call, rows, dense_x, seq_ids, *call.params)
             if not plan["seq_pool"]:
                 st = _Stash()
                 st.X, st.fm, st.lr, st.lr_owner, st.producer = inputs, fm, lr, use_lr, weakref.ref(self)
                 st.full = key == self._full_key()
+                st.version = E._version
                 E._rbx_stash = st
-            out.stacked = E
             for i, name in enumerate(names):
                 out[name] = E[:, i, :]
+            out.stacked = E                  # seals the dict: a later mutation drops the cached stack
             return out
         # generic path: per-feature kernels, torch.stack later (mixed dims, custom encoders, ...)
         for name in names:
@@ -672,7 +784,7 @@ class _FusedDictBase(nn.Module):
         return out
 
     @staticmethod
-    def _seq_rows(ids, off):
+    def _seq_rows(ids, off, vocab=0, n_bad=None):
         """[B, L] ids (float64 / int64 / int32 as the loader delivers them) -> int32 global rows."""
         if not ids.is_cuda:
             raise RbxError("recbox_b200 layers need CUDA inputs (no CPU path)")
@@ -681,8 +793,12 @@ class _FusedDictBase(nn.Module):
         L = ids.shape[1]
         if L == 0 or L > 192:
             out = ids.to(I32)
+            if vocab:
+                out = torch.where((out >= 0) & (out < vocab), out + off, torch.full_like(out, -1))
+                return out.contiguous()
             return (out + off if off else out).contiguous()
-        return ops.pack_columns([ids[:, l] for l in range(L)], add=[off] * L, as_rows=True)
+        return ops.pack_columns([ids[:, l] for l in range(L)], add=[off] * L, as_rows=True,
+                                vocab=[vocab] * L if vocab else None, n_bad=n_bad)
 
     def _full_key(self):
         return ((), ())
@@ -873,7 +989,7 @@ class InnerProductInteraction(nn.Module):
 
     def forward(self, feature_emb):
         if self._output_type == "product_sum":
-            st = getattr(feature_emb, "_rbx_stash", None)
+            st = _stash_of(feature_emb)
             if st is not None and st.fm is not None:
                 return st.fm                 # computed by the launch that produced feature_emb
         if not feature_emb.is_cuda:
@@ -941,6 +1057,7 @@ class LogisticRegression(nn.Module):
 
     def forward(self, X):
         d = self.embedding_layer.embedding_layer
+        d._sync_store()
         key, names = d._select([], [])
         plan = d._plan(key, names)
         if plan["call"] is None or plan["seq_pool"]:
@@ -967,7 +1084,7 @@ class LogisticRegression(nn.Module):
             c = (lo, cn)
             plan["lr_only"] = c
         call, cn = c
-        rows, dense_x = d._pack(X, cn["cats"], cn["nums"], cn["offs"])
+        rows, dense_x = d._pack(X, cn["cats"], cn["nums"], cn["offs"], cn.get("vocab"))
         _, _, lr = _FusedEmbedFn.apply(call, rows, dense_x, (), *call.params)
         return lr
 
@@ -981,7 +1098,7 @@ class FactorizationMachine(nn.Module):
         self.lr_layer = LogisticRegression(feature_map, use_bias=True)
 
     def forward(self, X, feature_emb):
-        st = getattr(feature_emb, "_rbx_stash", None)
+        st = _stash_of(feature_emb)
         if st is not None and st.X is X and st.lr is not None and st.lr_owner is self.lr_layer:
             return st.fm + st.lr             # both came out of the launch that produced feature_emb
         lr_out = self.lr_layer(X)

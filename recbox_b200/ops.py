@@ -5,6 +5,7 @@ into librecbox_b200.so with raw pointers.  There is no fallback of any kind: a n
 missing library raises.
 """
 import ctypes
+import threading
 
 import torch
 
@@ -15,20 +16,42 @@ MODES = {"product_sum": 0, "bi_interaction": 1, "inner_product": 2, "elementwise
 _DTYPE_CODE = {torch.float64: 0, torch.float32: 1, torch.int64: 2, torch.int32: 3}
 
 
+# Device of the call being assembled.  Arguments are evaluated left to right, so every `_p()` of a call
+# runs before its trailing `_stream()`, which in turn runs before `_call()`: the first tensor pins the
+# device, a tensor on another device is an error, the stream is that device's current stream, and the C
+# call runs inside that device's context (the reference's `get_device(gpu)` hands out `cuda:<gpu>`
+# without ever calling `set_device`, torch_utils.py:37-42, so tensors off the current device are normal).
+_ctx = threading.local()
+
+
+def _note_device(dev, name="tensor"):
+    cur = getattr(_ctx, "dev", None)
+    if cur is None:
+        _ctx.dev = dev
+    elif cur != dev:
+        _ctx.dev = None
+        raise RbxError("%s is on %s but an earlier argument of the same call is on %s" % (name, dev, cur))
+
+
 def _p(t, dtype=None, name="tensor"):
     if t is None:
         return None
     if not t.is_cuda:
+        _ctx.dev = None
         raise RbxError("%s must be a CUDA tensor (recbox_b200 has no CPU path)" % name)
     if not t.is_contiguous():
+        _ctx.dev = None
         raise RbxError("%s must be contiguous" % name)
     if dtype is not None and t.dtype != dtype:
+        _ctx.dev = None
         raise RbxError("%s must be %s, got %s" % (name, dtype, t.dtype))
+    _note_device(t.device, name)
     return ctypes.c_void_p(t.data_ptr())
 
 
 def _stream():
-    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    dev = getattr(_ctx, "dev", None)
+    return ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
 
 
 def _i32(xs):
@@ -38,7 +61,12 @@ def _i32(xs):
 
 def _call(name, *args):
     lib = _lib.load()
-    rc = getattr(lib, name)(*args)
+    dev, _ctx.dev = getattr(_ctx, "dev", None), None
+    if dev is not None and dev.index is not None and dev.index != torch.cuda.current_device():
+        with torch.cuda.device(dev):
+            rc = getattr(lib, name)(*args)
+    else:
+        rc = getattr(lib, name)(*args)
     if rc != 0:
         raise RbxError("%s failed (%d): %s" % (name, rc, lib.rbx_last_error().decode()))
 
@@ -55,8 +83,10 @@ def l2_set_persisting_bytes(nbytes):
 
 
 # ------------------------------------------------------------------------------------------- a1
-def split_batch(batch, col_kind, col_slot, field_off, F, Fn, want_label=True):
-    """[B, n_cols] float64 device matrix -> (rows int32 [B,F], dense_x fp32 [B,Fn], label fp32 [B])."""
+def split_batch(batch, col_kind, col_slot, field_off, F, Fn, want_label=True, field_rows=None, n_bad=None):
+    """[B, n_cols] float64 device matrix -> (rows int32 [B,F], dense_x fp32 [B,Fn], label fp32 [B]).
+    field_rows: vocabulary size per categorical slot -- ids outside it become row -1 (zero row, no gradient) and are
+    counted in the int32 device counter `n_bad` instead of aliasing another feature's rows."""
     if batch.dim() != 2 or batch.dtype != torch.float64 or not batch.is_cuda or batch.stride(1) != 1:
         raise RbxError("split_batch: batch must be a CUDA float64 matrix with unit column stride")
     B, n_cols = batch.shape
@@ -67,13 +97,16 @@ def split_batch(batch, col_kind, col_slot, field_off, F, Fn, want_label=True):
     kinds = (ctypes.c_int8 * max(n_cols, 1))(*col_kind)
     slots = (ctypes.c_int16 * max(n_cols, 1))(*col_slot)
     offs = (ctypes.c_int64 * max(F, 1))(*field_off)
-    _call("rbx_split_batch_f64", ctypes.c_void_p(batch.data_ptr()), B, n_cols, batch.stride(0), kinds, slots, offs,
-          F, Fn, _p(rows), _p(dense), _p(label), _stream())
+    nrows = (ctypes.c_int64 * max(F, 1))(*field_rows) if field_rows is not None else None
+    _note_device(dev, "batch")
+    _call("rbx_split_batch_f64", ctypes.c_void_p(batch.data_ptr()), B, n_cols, batch.stride(0), kinds, slots, offs, nrows,
+          F, Fn, _p(rows), _p(dense), _p(label), _p(n_bad, I32, "n_bad"), _stream())
     return rows, dense, label
 
 
-def pack_columns(cols, add=None, as_rows=True):
-    """list of [B] device tensors (any of f64/f32/i64/i32, any stride) -> [B, n] int32 (+add) or fp32."""
+def pack_columns(cols, add=None, as_rows=True, vocab=None, n_bad=None):
+    """list of [B] device tensors (any of f64/f32/i64/i32, any stride) -> [B, n] int32 (+add) or fp32.
+    vocab / n_bad: per-column vocabulary guard, see split_batch."""
     n = len(cols)
     B = cols[0].shape[0]
     dev = cols[0].device
@@ -85,7 +118,9 @@ def pack_columns(cols, add=None, as_rows=True):
     strides = (ctypes.c_int64 * n)(*[c.stride(0) if B > 1 else 1 for c in cols])
     dts = (ctypes.c_int8 * n)(*[_DTYPE_CODE[c.dtype] for c in cols])
     adds = (ctypes.c_int64 * n)(*(add if add is not None else [0] * n))
-    _call("rbx_pack_columns", ptrs, strides, dts, adds, n, B, 1 if as_rows else 0, _p(out), _stream())
+    voc = (ctypes.c_int64 * n)(*vocab) if (vocab is not None and as_rows) else None
+    _call("rbx_pack_columns", ptrs, strides, dts, adds, voc, n, B, 1 if as_rows else 0, _p(out), _p(n_bad, I32, "n_bad"),
+          _stream())
     return out
 
 

@@ -75,7 +75,13 @@ class TouchedRowsOptimizer(object):
     def touched(self, rows):
         """rows: int32 CUDA tensor of global row ids (any shape) -> (sorted unique rows buffer, device count)."""
         uniq, _, _, n_out = ops.unique_ids(rows, self.R, want_first=False, want_inverse=False, sync=False)
+        self.last_counts = n_out              # [n unique, n ids outside [0, R)] on the device; see out_of_range()
         return uniq, n_out[:1]
+
+    def out_of_range(self):
+        """Ids of the last step that fell outside [0, R) and were therefore not updated (synchronises)."""
+        c = getattr(self, "last_counts", None)
+        return int(c[1].item()) if c is not None and c.numel() > 1 else 0
 
     def step(self, rows, max_norm=None, extra_sqnorm=None, zero_grad=True):
         self.t += 1

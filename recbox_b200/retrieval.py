@@ -45,7 +45,9 @@ def build_csr(user2items, query_indices, device, sort=True):
                         for q in query_indices), dtype=np.int64, count=len(query_indices))
     ptr = np.zeros(len(query_indices) + 1, dtype=np.int64)
     np.cumsum(lens, out=ptr[1:])
-    items = np.empty(int(ptr[-1]), dtype=np.int64)
+    # at least one element: a chunk whose users have no items at all (cold start, empty train_user2items) must still hand
+    # rbx_rank_metrics a non-null items pointer (ptr[U] == 0 tells it there is nothing to read)
+    items = np.zeros(max(int(ptr[-1]), 1), dtype=np.int64)
     for i, q in enumerate(query_indices):
         row = user2items.get(q, ()) if hasattr(user2items, "get") else user2items[q]
         if len(row):

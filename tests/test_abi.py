@@ -44,7 +44,7 @@ def test_argument_errors_come_before_any_cuda_call():
     assert lib.rbx_topk_ip(None, None, 3, 10, 6, 2, 128, None, None, None, 0, None) == -1      # D % 4 != 0
     assert b"D=6" in lib.rbx_last_error()
     assert lib.rbx_shard_set_rank(99) == -1 and lib.rbx_shard_set_rank(-1) == 0
-    assert lib.rbx_split_batch_f64(None, 4, 3, 2, None, None, None, 0, 0, None, None, None, None) == -1   # ld < n_cols
+    assert lib.rbx_split_batch_f64(None, 4, 3, 2, None, None, None, None, 0, 0, None, None, None, None, None) == -1   # ld < n_cols
     # pure host helpers
     assert lib.rbx_topk_ws_bytes(1000, 100, 4096) >= 1000 * 4096 * 8
     assert lib.rbx_topk_ws_bytes(1000, 5000, 4096) == 0                          # k above the supported maximum
