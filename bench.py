@@ -439,8 +439,10 @@ def main_sharded(args, rank, world, local_rank):
         dist.init_process_group("nccl", device_id=dev)
     B, F, Fn, D, V = CFG["B"], CFG["F"], CFG["Fn"], args.dim, args.rows_per_field
     Ft, R = F + Fn, F * V
+    if args.shard_mode == "auto":       # one GPU: the local fused kernels; several: the streamed exchange
+        args.shard_mode = "peer" if world == 1 else "stream"
     if args.shard_layout == "auto":     # ROW+LR wins on multi-GB tables at every N (profiles/r1_sharded_runs.jsonl, r2e / r1w)
-        args.shard_layout = "rowlr" if (args.shard_mode == "peer" and not args.no_lr and D in (4, 8, 16)) else "split"
+        args.shard_layout = "rowlr" if (args.shard_mode in ("peer", "stream") and not args.no_lr and D in (4, 8, 16)) else "split"
     sh = sharded.ShardedEmbeddingFM(R, D, mode=args.shard_mode, device=dev, max_ids=B * F, alloc=args.peer_alloc, with_lr=not args.no_lr,
                                     layout=args.shard_layout)
     gen = torch.Generator(device=dev).manual_seed(20240 + 4 + rank)
@@ -471,7 +473,8 @@ def main_sharded(args, rank, world, local_rank):
         if evs: evs[1].record()
         sh.backward(rows, cat_pos, pad_row, dx, dense_w, num_pos, E, S, dE, d_fm, d_lr, gw, gw1, gb)
         if evs: evs[2].record()
-        sh.device_barrier()            # remote reductions of this step have landed in every owner's shard
+        if args.shard_mode != "stream":
+            sh.device_barrier()        # remote reductions of this step have landed in every owner's shard
         if evs: evs[3].record()
         return fm
 
@@ -517,12 +520,15 @@ def main_sharded(args, rank, world, local_rank):
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": "BASELINE configs[3]: DeepFM hot path, %d-row fused table (26 x %d) row-sharded over %d GPU(s), "
                                    "D=%d, B=65536 per GPU; mode=%s%s" % (R, V, world, D, args.shard_mode,
-                                                                            ", layout=rowlr" if args.shard_layout == "rowlr" else ""),
+                                                                            ", layout=%s" % args.shard_layout if args.shard_layout != "split" else ""),
                        "global_batch": B * world, "ids": args.ids, "batches_rotated": NB,
                        "l2": "table shard (%.1f GB) and E/dE streams exceed the 126 MB L2" % (sh.cap * D * 4 / 1e9),
                        "parallelism": "dp%d batch shards + row-sharded table (r %% %d), exchange inside the fused kernels over NVLink" % (world, world)
-                       if args.shard_mode == "peer" else "dp%d + row-sharded table, NCCL all_to_all" % world},
-            "gpu_launches": (3 if args.shard_mode == "peer" else 12) * K,
+                       if args.shard_mode == "peer" else
+                       ("dp%d batch shards + row-sharded table (r %% %d); streamed exchange: ids / rows / row gradients cross NVLink as contiguous runs "
+                        "written by the kernels, flag barriers over peer memory" % (world, world) if args.shard_mode == "stream"
+                        else "dp%d + row-sharded table, NCCL all_to_all" % world)},
+            "gpu_launches": {"peer": 3, "stream": 9}.get(args.shard_mode, 12) * K,
             "roofline": {"bound": "hbm" if world == 1 else "nvlink", "kernel": "embed_fm_bwd_sharded" if t_b >= t_f else "embed_fm_fwd_sharded",
                          "achieved": max(bf / t_f, bb / t_b) / 1e6 if world == 1 else (nv_b / t_b if t_b >= t_f else nv_f / t_f) / 1e6,
                          "peak": peak if world == 1 else 770.0, "unit": "GB/s",
@@ -552,9 +558,9 @@ def main():
     ap.add_argument("--workload", default="cfg2", choices=["cfg2", "sharded"],
                     help="cfg2: BASELINE configs[1], replicated 1M-row table (default, the metric's config); "
                          "sharded: configs[3], 100M-row table row-sharded over the ranks")
-    ap.add_argument("--shard-mode", default="peer", choices=["push", "peer", "a2a"])
+    ap.add_argument("--shard-mode", default="auto", choices=["auto", "stream", "push", "peer", "a2a"])
     ap.add_argument("--peer-alloc", default="symm", choices=["ipc", "symm"])
-    ap.add_argument("--shard-layout", default="auto", choices=["auto", "split", "rowlr"],
+    ap.add_argument("--shard-layout", default="auto", choices=["auto", "split", "rowlr", "rowpad"],
                     help="rowlr: embedding row + first-order weight in one physical row (one NVLink request per slot)")
     ap.add_argument("--no-lr", action="store_true", help="sharded workload without the first-order (LR) table")
     ap.add_argument("--dim", type=int, default=16)

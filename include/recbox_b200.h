@@ -339,6 +339,57 @@ int rbx_shard_apply_grads(const float* ginbox /*DEVICE [world,cap,D]*/, const fl
                           int world, int64_t cap, int D,
                           const int32_t* pad_local /*DEVICE [n_pad] | NULL*/, int n_pad, rbx_stream_t stream);
 
+/* Streamed exchange (csrc/shard_stream.cu; the default data path of the row-sharded table): the all-to-all of
+ * SURVEY.md section 8e done by the kernels themselves so that every random access is local to the row's owner and
+ * only contiguous runs cross NVLink.  The reference has no counterpart (no sharded embedding anywhere); the contract
+ * is equality with rbx_embed_fm_fwd / rbx_embed_fm_bwd on the concatenated table.  world must be a power of two
+ * <= RBX_MAX_WORLD; all `void* const*` arguments are HOST arrays of `world` DEVICE pointers valid on the calling
+ * device (own block first-class, peers' through rbx_peer_open / CUDA VMM); `cap` = slots per (owner, requester)
+ * pair.  A step is: route, barrier(counts), serve, barrier, consume | grad_push, barrier, apply.  Inbox buffers
+ * (ids, counts) are double-buffered by the caller (step parity), so apply needs no trailing barrier.
+ *   rbx_xs_tile_samples  samples per tile T for (F, D) (0 = unsupported shape); tiles index tile_base / tile_cnt
+ *                        ([n_tiles, RBX_MAX_WORLD] int32) and pair_sorted ([n_tiles, T*F] uint16)
+ *   rbx_xs_route         requester: buckets rows[B,F] by owner (row % world) tile by tile; the ids (local rows,
+ *                        row / world) of one tile for one owner form one contiguous run of that owner's
+ *                        inbox_ids[w][rank*cap + slot]; cursor[w] (DEVICE int32 [RBX_MAX_WORLD], zero before the
+ *                        first call) counts the slots used; overflow[0] is set if a lane would exceed cap
+ *   rbx_xs_barrier       all ranks: publishes cursor[w] into meta[w][rank] (then clears it) when cursor != NULL,
+ *                        writes `epoch` into every rank's flags[w][rank] (st.release.sys) and waits until its own
+ *                        flags[rank][*] reached `epoch` -- a stream-ordered barrier with no host involvement
+ *   rbx_xs_serve         owner: rowbuf[q][rank*cap + j] = table[inbox_ids[q*cap + j]] (row stride `row_stride`
+ *                        floats), rowbuf_lr[q][rank*cap + j] = lr[id * lr_stride]
+ *   rbx_xs_consume       requester: E / S / fm_out / lr_out of rbx_embed_fm_fwd from its row buffer
+ *   rbx_xs_grad_push     requester: ginbox[w][rank*cap + slot] = dE + d_fm (S - e) (zero for padding rows),
+ *                        ginbox_lr likewise = d_lr; numeric-slot gradients stay with rbx_embed_fm_bwd (F = 0)
+ *   rbx_xs_apply         owner: g_table[inbox_ids[q*cap + j]] += ginbox[q*cap + j] (red.global.add) */
+int rbx_xs_tile_samples(int F, int D);
+int rbx_xs_route(const int32_t* rows /*DEVICE [B,F]*/, int64_t B, int F, int64_t R, int D,
+                 int rank, int world, int64_t cap,
+                 int32_t* cursor, int32_t* tile_base, int32_t* tile_cnt, uint16_t* pair_sorted, int32_t* overflow,
+                 void* const* inbox_ids, rbx_stream_t stream);
+int rbx_xs_barrier(void* const* flags /*each DEVICE uint32 [RBX_MAX_WORLD]*/, void* const* meta /*each DEVICE int32 [RBX_MAX_WORLD] | NULL*/,
+                   int32_t* cursor /*| NULL*/, int rank, int world, uint32_t epoch, rbx_stream_t stream);
+int rbx_xs_serve(const float* table, int64_t row_stride, const float* lr /*| NULL*/, int64_t lr_stride, int D,
+                 const int32_t* inbox_ids /*DEVICE [world,cap]*/, const int32_t* meta /*DEVICE [RBX_MAX_WORLD]*/,
+                 int64_t cap, int rank, int world, void* const* rowbuf, void* const* rowbuf_lr /*| NULL*/,
+                 rbx_stream_t stream);
+int rbx_xs_consume(const float* rowbuf /*DEVICE [world,cap,D]*/, const float* rowbuf_lr /*DEVICE [world,cap] | NULL*/,
+                   const int32_t* tile_base, const int32_t* tile_cnt, const uint16_t* pair_sorted,
+                   const int32_t* cat_pos /*HOST [F]*/, const float* dense_x, const float* dense_w,
+                   const float* dense_w_lr, const int32_t* num_pos /*HOST [Fn]*/, const int32_t* num_widx /*HOST | NULL*/,
+                   const float* lr_bias, float* E, float* S, float* fm_out, float* lr_out,
+                   int64_t B, int64_t cap, int F, int Fn, int D, int n_slots, int world, rbx_stream_t stream);
+int rbx_xs_grad_push(const float* E /*| NULL: e re-read from rowbuf*/, const float* rowbuf, const float* S,
+                     const float* dE, const float* d_fm, const float* d_lr,
+                     const int32_t* rows /*DEVICE [B,F]*/, const int32_t* pad_row /*HOST [F] | NULL*/,
+                     const int32_t* tile_base, const int32_t* tile_cnt, const uint16_t* pair_sorted,
+                     const int32_t* cat_pos /*HOST [F]*/, int64_t B, int64_t cap, int F, int D, int n_slots,
+                     int rank, int world, void* const* ginbox, void* const* ginbox_lr /*| NULL*/, rbx_stream_t stream);
+int rbx_xs_apply(const float* ginbox /*DEVICE [world,cap,D]*/, const float* ginbox_lr /*| NULL*/,
+                 const int32_t* inbox_ids, const int32_t* meta, int64_t cap, int world,
+                 float* g_table, int64_t row_stride, float* g_lr /*| NULL*/, int64_t lr_stride, int D,
+                 rbx_stream_t stream);
+
 /* Peer-visible device memory (CUDA IPC; one process per GPU, all on one box).
  * rbx_peer_alloc  : cudaMalloc'd block (IPC-exportable, unlike a caching-allocator sub-block)
  * rbx_peer_export : 64-byte handle the owner sends to its peers (any byte transport)

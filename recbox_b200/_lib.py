@@ -104,6 +104,13 @@ SIGNATURES = {
     "rbx_shard_serve_rows": [_P, _P, _I, _P, _P, _P, _P, _I, _I64, _P],
     "rbx_shard_push_grads": [_P, _P, _P, _P, _P, _I, _I, _I64, _I, _I64, _P],
     "rbx_shard_apply_grads": [_P, _P, _P, _P, _P, _P, _I, _I64, _I, _P, _I, _P],
+    "rbx_xs_tile_samples": [_I, _I],
+    "rbx_xs_route": [_P, _I64, _I, _I64, _I, _I, _I, _I64, _P, _P, _P, _P, _P, _P, _P],
+    "rbx_xs_barrier": [_P, _P, _P, _I, _I, _c.c_uint32, _P],
+    "rbx_xs_serve": [_P, _I64, _P, _I64, _I, _P, _P, _I64, _I, _I, _P, _P, _P],
+    "rbx_xs_consume": [_P] * 16 + [_I64, _I64, _I, _I, _I, _I, _I, _P],
+    "rbx_xs_grad_push": [_P] * 12 + [_I64, _I64, _I, _I, _I, _I, _I, _P, _P, _P],
+    "rbx_xs_apply": [_P, _P, _P, _P, _I64, _I, _P, _I64, _P, _I64, _I, _P],
     "rbx_peer_alloc": [_c.c_size_t, _P],
     "rbx_peer_free": [_P],
     "rbx_peer_export": [_P, _P],

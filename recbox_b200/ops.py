@@ -395,6 +395,72 @@ def shard_apply_grads(ginbox, ginbox_lr, inbox_ids, inbox_meta, g_table, g_table
           _p(pad_local, I32, "pad_local"), 0 if pad_local is None else pad_local.numel(), _stream())
 
 
+# ---- streamed exchange (csrc/shard_stream.cu): only contiguous runs cross NVLink ---------------------------------
+def xs_tile_samples(F, D):
+    return int(_lib.load().rbx_xs_tile_samples(int(F), int(D)))
+
+
+def _lr_of(phys, D, lr_vec, lr_in_row):
+    """(pointer, element stride) of the first-order weight of local row r: a separate vector, or column D of the row."""
+    if lr_vec is not None:
+        return _p(lr_vec, F32, "lr"), 1
+    if lr_in_row:
+        return ctypes.c_void_p(phys.data_ptr() + 4 * D), phys.shape[1]
+    return None, 0
+
+
+def xs_route(rows, R, D, rank, world, cap, cursor, tile_base, tile_cnt, pair_sorted, overflow, inbox_ids_ptrs):
+    B, F = rows.shape
+    _call("rbx_xs_route", _p(rows, I32, "rows"), B, F, int(R), int(D), rank, world, int(cap), _p(cursor, I32, "cursor"),
+          _p(tile_base, I32, "tile_base"), _p(tile_cnt, I32, "tile_cnt"), _p(pair_sorted, torch.int16, "pair_sorted"),
+          _p(overflow, I32, "overflow"), inbox_ids_ptrs, _stream())
+
+
+def xs_barrier(flags_ptrs, meta_ptrs, cursor, rank, world, epoch, device):
+    _note_device(torch.device(device), "device")
+    _call("rbx_xs_barrier", flags_ptrs, meta_ptrs, _p(cursor, I32, "cursor"), rank, world, int(epoch) & 0xFFFFFFFF, _stream())
+
+
+def xs_serve(phys, D, lr_vec, lr_in_row, inbox_ids, meta, cap, rank, world, rowbuf_ptrs, rowbuf_lr_ptrs):
+    lr_ptr, lr_stride = _lr_of(phys, D, lr_vec, lr_in_row)
+    _call("rbx_xs_serve", _p(phys, F32, "table"), phys.shape[1], lr_ptr, lr_stride, int(D), _p(inbox_ids, I32, "inbox_ids"),
+          _p(meta, I32, "meta"), int(cap), rank, world, rowbuf_ptrs, rowbuf_lr_ptrs if lr_ptr is not None else None, _stream())
+
+
+def xs_consume(rowbuf, rowbuf_lr, tile_base, tile_cnt, pair_sorted, cat_pos, dense_x, dense_w, dense_w_lr, num_pos, lr_bias,
+               B, cap, D, world, want_E=True, want_lr=True, num_widx=None, n_slots=None):
+    F, Fn = len(cat_pos), len(num_pos)
+    Ft = n_slots or (F + Fn)
+    dev = rowbuf.device
+    E = torch.empty((B, Ft, D), dtype=F32, device=dev) if want_E else None
+    S = torch.empty((B, D), dtype=F32, device=dev)
+    fm = torch.empty((B,), dtype=F32, device=dev)
+    lr = torch.empty((B,), dtype=F32, device=dev) if want_lr else None
+    _call("rbx_xs_consume", _p(rowbuf, F32, "rowbuf"), _p(rowbuf_lr, F32, "rowbuf_lr") if want_lr else None,
+          _p(tile_base, I32, "tile_base"), _p(tile_cnt, I32, "tile_cnt"), _p(pair_sorted, torch.int16, "pair_sorted"),
+          _i32(cat_pos), _p(dense_x, F32, "dense_x"), _p(dense_w, F32, "dense_w"), _p(dense_w_lr, F32, "dense_w_lr"),
+          _i32(num_pos), _i32(num_widx) if num_widx is not None else None, _p(lr_bias, F32, "lr_bias"),
+          _p(E), _p(S), _p(fm), _p(lr), B, int(cap), F, Fn, int(D), Ft, world, _stream())
+    return E, S, fm, lr
+
+
+def xs_grad_push(E, rowbuf, S, dE, d_fm, d_lr, rows, pad_row, tile_base, tile_cnt, pair_sorted, cat_pos, cap, D, n_slots,
+                 rank, world, ginbox_ptrs, ginbox_lr_ptrs):
+    B, F = rows.shape
+    _call("rbx_xs_grad_push", _p(E, F32, "E"), _p(rowbuf, F32, "rowbuf"), _p(S, F32, "S"), _p(dE, F32, "dE"),
+          _p(d_fm, F32, "d_fm"), _p(d_lr, F32, "d_lr"), _p(rows, I32, "rows"),
+          _i32(pad_row if pad_row is not None else [-1] * F), _p(tile_base, I32, "tile_base"),
+          _p(tile_cnt, I32, "tile_cnt"), _p(pair_sorted, torch.int16, "pair_sorted"), _i32(cat_pos), B, int(cap), F, int(D),
+          int(n_slots), rank, world, ginbox_ptrs, ginbox_lr_ptrs if d_lr is not None else None, _stream())
+
+
+def xs_apply(ginbox, ginbox_lr, inbox_ids, meta, cap, world, g_phys, D, g_lr_vec, lr_in_row):
+    lr_ptr, lr_stride = _lr_of(g_phys, D, g_lr_vec, lr_in_row)
+    _call("rbx_xs_apply", _p(ginbox, F32, "ginbox"), _p(ginbox_lr, F32, "ginbox_lr") if lr_ptr is not None else None,
+          _p(inbox_ids, I32, "inbox_ids"), _p(meta, I32, "meta"), int(cap), world, _p(g_phys, F32, "g_table"),
+          g_phys.shape[1], lr_ptr, lr_stride, int(D), _stream())
+
+
 # ------------------------------------------------------------------------------------------ a12
 def sqnorm_(g, acc):
     """acc (float64 [1], device) += sum(g^2)."""

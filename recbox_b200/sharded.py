@@ -6,7 +6,14 @@ backward produce exactly what the single-table fused kernels (ops.embed_fm_fwd /
 reference-parity path) produce on the concatenated table.
 
 Partition: global row r (= id + field offset in the fused table) lives on rank r % world at local
-row r // world.  One process per GPU, torch.distributed for the plumbing.  Two data paths:
+row r // world.  One process per GPU, torch.distributed for the plumbing.  Data paths:
+
+  mode="stream" (product path at world > 1; csrc/shard_stream.cu) the all-to-all done by the kernels themselves with
+               every random access local to the row's owner and only CONTIGUOUS runs crossing NVLink: ids are
+               bucketed by owner tile by tile (one run per tile and owner), owners gather and store rows back in
+               slot order, the requester scatters the runs through a shared-memory E tile into the FM sums; the
+               backward writes row gradients in slot order into the owners' inboxes, owners reduce locally.
+               Cross-rank barriers are one tiny kernel over peer-mapped flags (no NCCL, no host sync).
 
   mode="peer"  (product path)  every rank maps every other rank's table / gradient shard through
                CUDA IPC (rbx_peer_*), and ONE fused kernel per direction does compute + exchange:
@@ -98,6 +105,34 @@ class SymmBlock(object):
         self.hdl = None
 
 
+class FileBlock(object):
+    """Host stand-in used by the world_size-2 gloo tests (no GPU): the same peer-visible block as a file-backed
+    shared mapping that every rank opens, so the stream-mode orchestration (parity buffers, slot bookkeeping,
+    barrier epochs) runs unchanged with a CPU kernel provider.  Never used on a CUDA device."""
+    _count = 0
+
+    def __init__(self, numel, group=None):
+        import os
+        import tempfile
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+        box = [tempfile.mkdtemp(prefix="rbx_fileblock_") if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0, group=group)
+        FileBlock._count += 1
+        self.numel = int(numel)
+        n = max(self.numel, 4)
+        paths = [os.path.join(box[0], "blk%d_r%d" % (FileBlock._count, w)) for w in range(world)]
+        self.tensor = torch.from_file(paths[rank], shared=True, size=n, dtype=F32)
+        self.tensor.zero_()
+        dist.barrier(group=group)
+        self.peer_tensors = [self.tensor if w == rank else torch.from_file(paths[w], shared=True, size=n, dtype=F32)
+                             for w in range(world)]
+        self.ptr = None
+
+    def free(self):
+        self.tensor = None
+        self.peer_tensors = None
+
+
 def open_peer(handle, device):
     lib = _lib.load()
     out = ctypes.c_void_p()
@@ -141,13 +176,15 @@ class ShardedEmbeddingFM(object):
 
     def __init__(self, R, D, mode="peer", group=None, device=None, with_lr=True, kern=None, max_ids=None, slack=1.5,
                  alloc="symm", layout="split"):
-        if mode not in ("peer", "push", "a2a"):
-            raise RbxError("ShardedEmbeddingFM: mode must be 'peer', 'push' or 'a2a'")
-        if layout not in ("split", "rowlr"):
-            raise RbxError("ShardedEmbeddingFM: layout must be 'split' or 'rowlr'")
-        if layout == "rowlr" and (mode != "peer" or not with_lr or D not in (4, 8, 16)):
+        if mode not in ("peer", "push", "a2a", "stream"):
+            raise RbxError("ShardedEmbeddingFM: mode must be 'stream', 'peer', 'push' or 'a2a'")
+        if layout not in ("split", "rowlr", "rowpad"):
+            raise RbxError("ShardedEmbeddingFM: layout must be 'split', 'rowlr' or 'rowpad'")
+        if layout == "rowlr" and mode != "stream" and (mode != "peer" or not with_lr or D not in (4, 8, 16)):
             raise RbxError("layout='rowlr' (row + first-order weight in one 2D-float physical row) needs mode='peer', "
                            "with_lr=True and D in {4, 8, 16}")
+        if layout == "rowpad" and mode != "stream":
+            raise RbxError("layout='rowpad' (physical rows of D + 4 floats) exists in mode='stream' only")
         self.layout = layout
         self.R, self.D, self.mode, self.group, self.with_lr = int(R), int(D), mode, group, with_lr
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
@@ -165,6 +202,14 @@ class ShardedEmbeddingFM(object):
         n_l4 = (n_l + 3) // 4 * 4
         self._block = None
         self._peers = []
+        self._ws = self._saved = self._ptr_arrays = None
+        if mode == "stream":
+            if self.world & (self.world - 1) or self.world > 8:
+                raise RbxError("stream mode needs a power-of-two world <= 8 (got %d)" % self.world)
+            if max_ids is None:
+                raise RbxError("stream mode needs max_ids (= max batch * categorical slots per rank)")
+            self._init_stream(int(max_ids), float(slack))
+            return
         if mode == "peer" and layout == "rowlr":
             if self.world & (self.world - 1) or self.world > 8:
                 raise RbxError("peer mode needs a power-of-two world <= 8 (got %d)" % self.world)
@@ -209,6 +254,146 @@ class ShardedEmbeddingFM(object):
                 raise RbxError("push mode needs max_ids (= max batch * categorical slots per rank)")
             self._init_push(int(max_ids), float(slack))
 
+    # -- stream mode ------------------------------------------------------------------------------------
+    def _init_stream(self, max_ids, slack):
+        """Table and gradient shards are LOCAL allocations (only their owner ever touches them); the exchange
+        workspace -- flags, count / id inboxes (double-buffered by step parity), row buffer, gradient inbox -- is one
+        peer-visible block."""
+        W, D, cap_rows, dev = self.world, self.D, self.cap, self.device
+        if self.layout == "split" or not self.with_lr:
+            self.layout = "split"
+            n_t, n_l4 = cap_rows * D, (cap_rows + 3) // 4 * 4
+            flat = torch.zeros(2 * n_t + 2 * n_l4, dtype=F32, device=dev)
+            self._tphys, self._gphys = flat[:n_t].view(cap_rows, D), flat[n_t + n_l4:2 * n_t + n_l4].view(cap_rows, D)
+            self.table, self.g_table = self._tphys, self._gphys
+            self.table_lr = flat[n_t:n_t + cap_rows]
+            self.g_table_lr = flat[2 * n_t + n_l4:2 * n_t + n_l4 + cap_rows]
+            self._gflat = flat[n_t + n_l4:]
+        else:
+            RS = 2 * D if self.layout == "rowlr" else D + 4
+            flat = torch.zeros(2 * cap_rows * RS, dtype=F32, device=dev)
+            self._tphys, self._gphys = flat[:cap_rows * RS].view(cap_rows, RS), flat[cap_rows * RS:].view(cap_rows, RS)
+            self.table, self.table_lr = self._tphys[:, :D], self._tphys[:, D]
+            self.g_table, self.g_table_lr = self._gphys[:, :D], self._gphys[:, D]
+            self._gflat = flat[cap_rows * RS:]
+        self._flat = flat
+        self.max_ids = max_ids
+        self.slot_cap = min(max_ids, int(max_ids / W * slack) + 1024) if W > 1 else max_ids
+        cap = self.slot_cap
+        al = lambda n: (n + 3) // 4 * 4
+        sizes = [("flags", 8), ("meta", 16), ("inbox_ids", al(2 * W * cap)), ("rowbuf", al(W * cap * D)),
+                 ("rowbuf_lr", al(W * cap)), ("ginbox", al(W * cap * D)), ("ginbox_lr", al(W * cap))]
+        offs, tot = {}, 0
+        for name, n in sizes:
+            offs[name] = (tot, n)
+            tot += n
+        self._ws = self._shared_block(tot)
+        wsf = self._ws.tensor
+        v = {name: wsf[o:o + n] for name, (o, n) in offs.items()}
+        self._xs_flags = v["flags"].view(I32)
+        self._xs_meta = v["meta"].view(I32).view(2, 8)
+        self._xs_inbox_ids = v["inbox_ids"].view(I32)[:2 * W * cap].view(2, W * cap)
+        self.rowbuf = v["rowbuf"][:W * cap * D]
+        self.rowbuf_lr = v["rowbuf_lr"][:W * cap]
+        self.ginbox = v["ginbox"][:W * cap * D]
+        self.ginbox_lr = v["ginbox_lr"][:W * cap]
+        self._xs_peers = {}
+        for name, (o, n) in offs.items():
+            self._xs_peers[name] = self._peer_views(self._ws, o, n)
+        for par in (0, 1):
+            self._xs_peers[("meta", par)] = self._peer_views(self._ws, offs["meta"][0] + 8 * par, 8)
+            self._xs_peers[("inbox_ids", par)] = self._peer_views(self._ws, offs["inbox_ids"][0] + par * W * cap, W * cap)
+        self._xs_cursor = torch.zeros(8, dtype=I32, device=dev)
+        self._xs_overflow = torch.zeros(1, dtype=I32, device=dev)
+        self._xs_tiles = None
+        self._step = 0
+        self._epoch = 0
+        self.barrier()
+
+    def _peer_views(self, block, off, n):
+        """What the kernel provider gets for "every rank's copy of words [off, off + n) of `block`": a ctypes array of
+        device pointers on CUDA; the list of the ranks' (shared-memory) tensors under the CPU stand-in of the tests."""
+        if hasattr(block, "peer_tensors"):
+            return [t[off:off + n] for t in block.peer_tensors]
+        return (ctypes.c_void_p * self.world)(*[b + off * 4 for b in self._peer_bases_cached(block)])
+
+    def _peer_bases_cached(self, block):
+        c = getattr(self, "_bases_cache", None)
+        if c is None or c[0] is not block:
+            self._bases_cache = c = (block, self._peer_bases(block))
+        return c[1]
+
+    def _xs_tile_state(self, B, F):
+        T = self.kern.xs_tile_samples(F, self.D)
+        if T <= 0:
+            raise RbxError("sharded stream mode: F=%d, D=%d is outside what the tile kernels cover" % (F, self.D))
+        n_tiles = (B + T - 1) // T
+        st = self._xs_tiles
+        if st is None or st[0] != (T, F) or st[1].shape[0] < n_tiles:
+            dev = self.device
+            st = ((T, F), torch.zeros((n_tiles, 8), dtype=I32, device=dev), torch.zeros((n_tiles, 8), dtype=I32, device=dev),
+                  torch.zeros((n_tiles * T * F,), dtype=torch.int16, device=dev))
+            self._xs_tiles = st
+        return st
+
+    def _xs_barrier(self, par=None, with_counts=False):
+        self._epoch += 1
+        self.kern.xs_barrier(self._xs_peers["flags"], self._xs_peers[("meta", par)] if with_counts else None,
+                             self._xs_cursor if with_counts else None, self.rank, self.world, self._epoch, self.device)
+
+    def _fwd_stream(self, rows, cat_pos, dense_x, dense_w, dense_w_lr, num_pos, lr_bias, want_E, n_slots):
+        k = self.kern
+        B, F = rows.shape
+        if B * F > self.max_ids:
+            raise RbxError("sharded stream: %d ids exceed max_ids=%d" % (B * F, self.max_ids))
+        _, tile_base, tile_cnt, pair_sorted = self._xs_tile_state(B, F)
+        par = self._step & 1
+        self._step += 1
+        cap, W = self.slot_cap, self.world
+        k.xs_route(rows, self.R, self.D, self.rank, W, cap, self._xs_cursor, tile_base, tile_cnt, pair_sorted,
+                   self._xs_overflow, self._xs_peers[("inbox_ids", par)])
+        self._xs_barrier(par, with_counts=True)          # every requester's ids and counts are in my inboxes
+        in_row = self.layout != "split"
+        k.xs_serve(self._tphys, self.D, self.table_lr if (self.with_lr and not in_row) else None, self.with_lr and in_row,
+                   self._xs_inbox_ids[par], self._xs_meta[par], cap, self.rank, W, self._xs_peers["rowbuf"],
+                   self._xs_peers["rowbuf_lr"] if self.with_lr else None)
+        self._xs_barrier()                               # every owner's rows are in my row buffer
+        E, S, fm, lr = k.xs_consume(self.rowbuf, self.rowbuf_lr if self.with_lr else None, tile_base, tile_cnt, pair_sorted,
+                                    cat_pos, dense_x, dense_w, dense_w_lr, num_pos, lr_bias, B, cap, self.D, W,
+                                    want_E=want_E, want_lr=self.with_lr, n_slots=n_slots)
+        self._saved = (par, B, F)
+        self._bwd_pending = False
+        return E, S, fm, lr
+
+    def _bwd_stream(self, rows, cat_pos, pad_rows, dense_x, dense_w, num_pos, E, S, dE, d_fm, d_lr,
+                    g_dense_w, g_dense_w_lr, g_lr_bias, n_slots):
+        if self._saved is None:
+            raise RbxError("ShardedEmbeddingFM.backward (stream) needs the forward of the same batch first")
+        k = self.kern
+        par, B, F = self._saved
+        if tuple(rows.shape) != (B, F):
+            raise RbxError("ShardedEmbeddingFM.backward (stream): rows differ in shape from the forward's")
+        _, tile_base, tile_cnt, pair_sorted = self._xs_tiles
+        cap, W = self.slot_cap, self.world
+        use_lr = self.with_lr and d_lr is not None
+        Ft = n_slots or (F + len(num_pos))
+        if getattr(self, "_bwd_pending", False):
+            self._xs_barrier()       # a second backward on the same forward: the owners may still be reading the last one's inbox
+        self._bwd_pending = True
+        k.xs_grad_push(E, self.rowbuf, S, dE, d_fm, d_lr if use_lr else None, rows, pad_rows, tile_base, tile_cnt,
+                       pair_sorted, cat_pos, cap, self.D, Ft, self.rank, W, self._xs_peers["ginbox"],
+                       self._xs_peers["ginbox_lr"] if use_lr else None)
+        if not len(num_pos) and g_lr_bias is not None and d_lr is not None:
+            g_lr_bias.add_(d_lr.sum())                   # no numeric slot: the bias gradient is all that is left
+        elif len(num_pos):
+            # numeric slots / bias: batch reductions with no exchange (the F = 0 form of the fused backward)
+            k.embed_fm_bwd(None, None, [], None, dense_x, dense_w, num_pos, None, S, dE, d_fm, d_lr, None, None,
+                           g_dense_w, g_dense_w_lr, g_lr_bias, self.D, self.R, B=B, n_slots=Ft)
+        self._xs_barrier()                               # every requester's gradients are in my inbox
+        in_row = self.layout != "split"
+        k.xs_apply(self.ginbox, self.ginbox_lr if use_lr else None, self._xs_inbox_ids[par], self._xs_meta[par], cap, W,
+                   self._gphys, self.D, self.g_table_lr if (use_lr and not in_row) else None, use_lr and in_row)
+
     # -- push-mode workspace: inboxes every peer can write ---------------------------------------------
     def _init_push(self, max_ids, slack):
         W, D = self.world, self.D
@@ -243,9 +428,13 @@ class ShardedEmbeddingFM(object):
         """Host check (synchronises): did any (owner, requester) bucket exceed its slot capacity?"""
         if self.mode == "push" and int(self.inbox_meta.view(self.world, 4)[:, 2].max()) != 0:
             raise RbxError("sharded push: an id bucket exceeded the slot capacity %d; raise `slack`" % self.slot_cap)
+        if self.mode == "stream" and int(self._xs_overflow.item()) != 0:
+            raise RbxError("sharded stream: an id lane exceeded the slot capacity %d; raise `slack`" % self.slot_cap)
 
     # -- peer mapping ------------------------------------------------------------------------------
     def _shared_block(self, numel):
+        if self.device.type != "cuda":
+            return FileBlock(numel, self.group)
         if self.alloc == "symm":
             return SymmBlock(numel, self.device, self.group)
         return PeerBlock(numel, self.device)
@@ -281,6 +470,7 @@ class ShardedEmbeddingFM(object):
         if self._ws is not None:
             self.barrier()
             self.inbox_ids = self.inbox_meta = self.rowbuf = self.rowbuf_lr = self.ginbox = self.ginbox_lr = None
+            self._xs_flags = self._xs_meta = self._xs_inbox_ids = self._xs_peers = self._bases_cache = None
             self._ws.free()
             self._ws = None
         if self._block is not None:
@@ -334,7 +524,9 @@ class ShardedEmbeddingFM(object):
     def forward(self, rows, cat_pos, dense_x=None, dense_w=None, dense_w_lr=None, num_pos=(), lr_bias=None,
                 want_E=True, n_slots=None):
         """rows: int32 [B, F] GLOBAL row ids of this rank's batch shard.  Returns (E, S, fm, lr)."""
-        if self.mode == "peer":
+        if self.mode == "stream":
+            out = self._fwd_stream(rows, cat_pos, dense_x, dense_w, dense_w_lr, list(num_pos), lr_bias, want_E, n_slots)
+        elif self.mode == "peer":
             out = self._fwd_peer(rows, cat_pos, dense_x, dense_w, dense_w_lr, list(num_pos), lr_bias, want_E, n_slots)
         elif self.mode == "push":
             out = self._fwd_push(rows, cat_pos, dense_x, dense_w, dense_w_lr, list(num_pos), lr_bias, want_E, n_slots)
@@ -346,7 +538,10 @@ class ShardedEmbeddingFM(object):
                  g_dense_w=None, g_dense_w_lr=None, g_lr_bias=None, n_slots=None):
         """Accumulates into this rank's AND (peer mode) the owners' gradient shards; the dense
         (replicated) gradients g_dense_* are local partial sums the caller all-reduces."""
-        if self.mode == "peer":
+        if self.mode == "stream":
+            self._bwd_stream(rows, cat_pos, pad_rows, dense_x, dense_w, list(num_pos), E, S, dE, d_fm, d_lr,
+                             g_dense_w, g_dense_w_lr, g_lr_bias, n_slots)
+        elif self.mode == "peer":
             self._bwd_peer(rows, cat_pos, pad_rows, dense_x, dense_w, list(num_pos), E, S, dE, d_fm, d_lr,
                            g_dense_w, g_dense_w_lr, g_lr_bias, n_slots)
         elif self.mode == "push":

@@ -172,15 +172,16 @@ class CpuKern:
     @staticmethod
     def embed_fm_bwd(table, rows, cat_pos, pad_row, dense_x, dense_w, num_pos, E, S, dE, d_fm, d_lr,
                      g_table, g_table_lr, g_dense_w, g_dense_w_lr, g_lr_bias, D, R, n_slots=None, **_):
-        B, F = rows.shape
-        e_cat = table[rows.long()]                                          # [B,F,D]
-        g_e = dE[:, list(cat_pos)] + d_fm.view(-1, 1, 1) * (S[:, None, :] - e_cat)
-        keep = torch.ones(B, F, dtype=torch.bool)
-        if pad_row is not None:
-            keep = rows != torch.tensor(pad_row, dtype=rows.dtype)[None]
-        g_table.index_add_(0, rows[keep].long(), g_e[keep])
-        if g_table_lr is not None and d_lr is not None:
-            g_table_lr.index_add_(0, rows[keep].long(), d_lr.view(-1, 1).expand(B, F)[keep])
+        if rows is not None and len(cat_pos):
+            B, F = rows.shape
+            e_cat = table[rows.long()]                                          # [B,F,D]
+            g_e = dE[:, list(cat_pos)] + d_fm.view(-1, 1, 1) * (S[:, None, :] - e_cat)
+            keep = torch.ones(B, F, dtype=torch.bool)
+            if pad_row is not None:
+                keep = rows != torch.tensor(pad_row, dtype=rows.dtype)[None]
+            g_table.index_add_(0, rows[keep].long(), g_e[keep])
+            if g_table_lr is not None and d_lr is not None:
+                g_table_lr.index_add_(0, rows[keep].long(), d_lr.view(-1, 1).expand(B, F)[keep])
         if len(num_pos) and g_dense_w is not None:
             e_num = dense_x[:, :, None] * dense_w[None]
             g_n = dE[:, list(num_pos)] + d_fm.view(-1, 1, 1) * (S[:, None, :] - e_num)
@@ -189,3 +190,130 @@ class CpuKern:
                 g_dense_w_lr += (dense_x * d_lr.view(-1, 1)).sum(0)
         if g_lr_bias is not None and d_lr is not None:
             g_lr_bias += d_lr.sum()
+
+
+    # ---- streamed exchange (csrc/shard_stream.cu), same buffer layouts and slot bookkeeping as the kernels; "peer
+    # pointers" are the ranks' shared-memory tensors (recbox_b200.sharded.FileBlock) ------------------------------
+    XS_T = 4                    # small tiles: several tiles and a partial last tile in every test batch
+
+    @staticmethod
+    def xs_tile_samples(F, D):
+        return CpuKern.XS_T
+
+    @staticmethod
+    def xs_route(rows, R, D, rank, world, cap, cursor, tile_base, tile_cnt, pair_sorted, overflow, inbox_peers):
+        B, F = rows.shape
+        T = CpuKern.XS_T
+        r = rows.numpy()
+        inb = [t.view(torch.int32) for t in inbox_peers]
+        for tile in range((B + T - 1) // T):
+            blk = r[tile * T:(tile + 1) * T].reshape(-1)
+            n = 0
+            for o in range(world):
+                sel = [k for k, v in enumerate(blk) if 0 <= v < R and v % world == o]
+                base = int(cursor[o])
+                cursor[o] += len(sel)
+                tile_base[tile, o], tile_cnt[tile, o] = base, len(sel)
+                if base + len(sel) > cap:
+                    overflow[0] = 1
+                for j, k in enumerate(sel):
+                    if base + j < cap:
+                        inb[o][rank * cap + base + j] = int(blk[k]) // world
+                    pair_sorted[tile * T * F + n] = k
+                    n += 1
+
+    @staticmethod
+    def xs_barrier(flags_peers, meta_peers, cursor, rank, world, epoch, device):
+        import time
+        if cursor is not None:
+            for o in range(world):
+                meta_peers[o].view(torch.int32)[rank] = int(cursor[o])
+                cursor[o] = 0
+        for o in range(world):
+            flags_peers[o].view(torch.int32)[rank] = epoch
+        mine = flags_peers[rank].view(torch.int32)
+        t0 = time.time()
+        while any(int(mine[q]) < epoch for q in range(world)):
+            time.sleep(0.0005)
+            assert time.time() - t0 < 60, "stand-in barrier timed out"
+
+    @staticmethod
+    def _lr_view(phys, D, lr_vec, lr_in_row):
+        return lr_vec if lr_vec is not None else (phys[:, D] if lr_in_row else None)
+
+    @staticmethod
+    def xs_serve(phys, D, lr_vec, lr_in_row, inbox_ids, meta, cap, rank, world, rowbuf_peers, rowbuf_lr_peers):
+        lr = CpuKern._lr_view(phys, D, lr_vec, lr_in_row)
+        for q in range(world):
+            n = min(int(meta[q]), cap)
+            ids = inbox_ids[q * cap:q * cap + n].long()
+            rowbuf_peers[q][rank * cap * D:(rank * cap + n) * D] = phys[ids, :D].reshape(-1)
+            if lr is not None and rowbuf_lr_peers is not None:
+                rowbuf_lr_peers[q][rank * cap:rank * cap + n] = lr[ids]
+
+    @staticmethod
+    def _pairs(tile_base, tile_cnt, pair_sorted, B, F, world):
+        """-> list of (b, f, owner, slot) in the kernels' tile / run order."""
+        T = CpuKern.XS_T
+        out = []
+        for tile in range((B + T - 1) // T):
+            n = 0
+            for o in range(world):
+                for j in range(int(tile_cnt[tile, o])):
+                    k = int(pair_sorted[tile * T * F + n])
+                    out.append((tile * T + k // F, k % F, o, int(tile_base[tile, o]) + j))
+                    n += 1
+        return out
+
+    @staticmethod
+    def xs_consume(rowbuf, rowbuf_lr, tile_base, tile_cnt, pair_sorted, cat_pos, dense_x, dense_w, dense_w_lr, num_pos,
+                   lr_bias, B, cap, D, world, want_E=True, want_lr=True, num_widx=None, n_slots=None):
+        F, Fn = len(cat_pos), len(num_pos)
+        E = torch.zeros(B, n_slots or (F + Fn), D)
+        lr = torch.zeros(B)
+        rb = rowbuf.view(-1, D)
+        for b, f, o, slot in CpuKern._pairs(tile_base, tile_cnt, pair_sorted, B, F, world):
+            if slot < cap:
+                E[b, cat_pos[f]] = rb[o * cap + slot]
+                if want_lr:
+                    lr[b] += rowbuf_lr[o * cap + slot]
+        if Fn:
+            E[:, list(num_pos)] = dense_x[:, :, None] * dense_w[None]
+            if want_lr:
+                lr = lr + (dense_x * dense_w_lr[None]).sum(1)
+        if want_lr and lr_bias is not None:
+            lr = lr + lr_bias
+        S = E.sum(1)
+        fm = oracle.inner_product_interaction(E, "product_sum").reshape(-1)
+        return (E if want_E else None), S, fm, (lr if want_lr else None)
+
+    @staticmethod
+    def xs_grad_push(E, rowbuf, S, dE, d_fm, d_lr, rows, pad_row, tile_base, tile_cnt, pair_sorted, cat_pos, cap, D,
+                     n_slots, rank, world, ginbox_peers, ginbox_lr_peers):
+        B, F = rows.shape
+        rb = rowbuf.view(-1, D)
+        for b, f, o, slot in CpuKern._pairs(tile_base, tile_cnt, pair_sorted, B, F, world):
+            if slot >= cap:
+                continue
+            g = torch.zeros(D)
+            is_pad = pad_row is not None and int(rows[b, f]) == pad_row[f]
+            if not is_pad:
+                if dE is not None:
+                    g = dE[b, cat_pos[f]].clone()
+                if d_fm is not None:
+                    e = E[b, cat_pos[f]] if E is not None else rb[o * cap + slot]
+                    g = g + d_fm[b] * (S[b] - e)
+            ginbox_peers[o][(rank * cap + slot) * D:(rank * cap + slot + 1) * D] = g
+            if d_lr is not None and ginbox_lr_peers is not None:
+                ginbox_lr_peers[o][rank * cap + slot] = 0.0 if is_pad else float(d_lr[b])
+
+    @staticmethod
+    def xs_apply(ginbox, ginbox_lr, inbox_ids, meta, cap, world, g_phys, D, g_lr_vec, lr_in_row):
+        g_lr = CpuKern._lr_view(g_phys, D, g_lr_vec, lr_in_row)
+        gi = ginbox.view(-1, D)
+        for q in range(world):
+            n = min(int(meta[q]), cap)
+            ids = inbox_ids[q * cap:q * cap + n].long()
+            g_phys[:, :D].index_add_(0, ids, gi[q * cap:q * cap + n])
+            if g_lr is not None and ginbox_lr is not None:
+                g_lr.index_add_(0, ids, ginbox_lr[q * cap:q * cap + n])

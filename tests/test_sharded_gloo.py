@@ -34,11 +34,11 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, out_dir):
+def _worker(rank, world, port, out_dir, mode="a2a", layout="split"):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
-        B, D = 48, 8
+        B, D = 46 if mode == "stream" else 48, 8       # 46: the stream stand-in's last tile is partial
         pb = Problem(B * world, "nccncc", D, vocab=[11, 7, 13, 5], seed=3)
         f = pb.fused("cpu")
         g = torch.Generator().manual_seed(4)
@@ -46,15 +46,22 @@ def _worker(rank, world, port, out_dir):
         d_fm = torch.randn(B * world, generator=g)
         d_lr = torch.randn(B * world, generator=g)
         sl = slice(rank * B, (rank + 1) * B)
-        sh = sharded.ShardedEmbeddingFM(pb.R, D, mode="a2a", device="cpu", kern=CpuKern)
+        sh = sharded.ShardedEmbeddingFM(pb.R, D, mode=mode, device="cpu", kern=CpuKern, max_ids=B * pb.F, slack=3.0,
+                                        layout=layout)
         assert sh.world == world and sh.rank == rank
         sh.load_global(f["table"], f["table_lr"])
-        E, S, fm, lr = sh.forward(f["rows"][sl], pb.cat_pos, f["dense_x"][sl], f["dense_w"], f["dense_w_lr"], pb.num_pos,
-                                  f["bias"])
         gw, gw1, gb = torch.zeros_like(f["dense_w"]), torch.zeros_like(f["dense_w_lr"]), torch.zeros(1)
         sh.zero_grad()
-        sh.backward(f["rows"][sl], pb.cat_pos, pb.pad_row, f["dense_x"][sl], f["dense_w"], pb.num_pos, E, S, dE[sl],
-                    d_fm[sl], d_lr[sl], gw, gw1, gb)
+        # three steps on the same batch (stream mode alternates its parity buffers; gradients accumulate), the last
+        # one without the saved E (e re-read from the row buffer)
+        steps = 3 if mode == "stream" else 1
+        for it in range(steps):
+            E, S, fm, lr = sh.forward(f["rows"][sl], pb.cat_pos, f["dense_x"][sl], f["dense_w"], f["dense_w_lr"],
+                                      pb.num_pos, f["bias"])
+            sh.backward(f["rows"][sl], pb.cat_pos, pb.pad_row, f["dense_x"][sl], f["dense_w"], pb.num_pos,
+                        E if it < 2 else None, S, dE[sl], d_fm[sl], d_lr[sl], gw, gw1, gb)
+        sh.barrier()
+        sh.check_overflow()
         for t in (gw, gw1, gb):
             dist.all_reduce(t)
         gt = sh.gather_global("g_table")
@@ -66,7 +73,10 @@ def _worker(rank, world, port, out_dir):
         assert_close(lr, lrr.reshape(-1)[sl], what="lr")
         want = pb.oracle_grads(dE, d_fm, d_lr)
         for got, ref, name in zip((gt, gt1, gw, gw1, gb), want, ("g_table", "g_table_lr", "g_dense_w", "g_dense_w_lr", "g_bias")):
-            assert_close(got, ref, atol_scale=2e-5, what=name)
+            assert_close(got, ref * steps, atol_scale=2e-5, what=name)
+        for p in pb.pad_row:
+            assert float(gt[p].abs().sum()) == 0.0 and float(gt1[p]) == 0.0, "padding rows keep a zero gradient"
+        sh.close()
         open(os.path.join(out_dir, "ok%d" % rank), "w").write("ok")
     finally:
         dist.destroy_process_group()
@@ -76,4 +86,13 @@ def _worker(rank, world, port, out_dir):
 def test_a2a_orchestration_world2_gloo(world, tmp_path):
     port = _free_port()
     mp.spawn(_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    assert all(os.path.exists(os.path.join(str(tmp_path), "ok%d" % r)) for r in range(world))
+
+
+@pytest.mark.parametrize("layout", ["split", "rowlr", "rowpad"])
+def test_stream_orchestration_world2_gloo(layout, tmp_path):
+    """mode="stream": slot bookkeeping, parity-double-buffered inboxes, barrier epochs and the three shard layouts, with the
+    CPU stand-ins writing into the peers' (file-backed) blocks exactly where the kernels write over NVLink."""
+    world = 2
+    mp.spawn(_worker, args=(world, _free_port(), str(tmp_path), "stream", layout), nprocs=world, join=True)
     assert all(os.path.exists(os.path.join(str(tmp_path), "ok%d" % r)) for r in range(world))

@@ -42,11 +42,14 @@ def _worker(rank, world, port, mode, D, out_dir):
         sl = slice(rank * B, (rank + 1) * B)
         rows, dx = f["rows"][sl].contiguous(), f["dense_x"][sl].contiguous()
 
-        layout = "rowlr" if mode == "peer_rowlr" else "split"
-        mode = "peer" if mode == "peer_rowlr" else mode
+        layout = mode.split("_")[1] if "_" in mode else "split"
+        mode = mode.split("_")[0]
         sh = sharded.ShardedEmbeddingFM(pb.R, D, mode=mode, device=dev, max_ids=B * pb.F, slack=3.0, layout=layout)
         sh.load_global(f["table"], f["table_lr"])
         E, S, fm, lr = sh.forward(rows, pb.cat_pos, dx, f["dense_w"], f["dense_w_lr"], pb.num_pos, f["bias"])
+        if mode == "stream":       # a second forward lands in the other parity buffers and must agree bit for bit
+            E2, S2, fm2, lr2 = sh.forward(rows, pb.cat_pos, dx, f["dense_w"], f["dense_w_lr"], pb.num_pos, f["bias"])
+            assert torch.equal(E, E2) and torch.equal(S, S2) and torch.equal(fm, fm2) and torch.equal(lr, lr2)
         gw, gw1, gb = torch.zeros_like(f["dense_w"]), torch.zeros_like(f["dense_w_lr"]), torch.zeros(1, device=dev)
         sh.zero_grad()
         sh.barrier()
@@ -63,8 +66,15 @@ def _worker(rank, world, port, mode, D, out_dir):
         Er, Sr, fmr, lrr = ops.embed_fm_fwd(f["table"], f["table_lr"], f["rows"], pb.cat_pos, f["dense_x"], f["dense_w"],
                                             f["dense_w_lr"], pb.num_pos, f["bias"])
         assert torch.equal(E, Er[sl]), "gathered rows must be bit-exact"
-        assert torch.equal(S, Sr[sl]) and torch.equal(fm, fmr[sl]), "same kernel, same order"
-        if layout == "rowlr":   # the first-order weights ride in the row: one lane sums them, in slot order
+        if mode == "stream":    # the tile kernel sums the slots in a different order than the single-table kernel
+            assert_close(S, Sr[sl], what="S[stream]")
+            assert_close(fm, fmr[sl], atol_scale=2e-5, what="fm[stream]")
+            assert_close(lr, lrr[sl], what="lr[stream]")
+        else:
+            assert torch.equal(S, Sr[sl]) and torch.equal(fm, fmr[sl]), "same kernel, same order"
+        if mode == "stream":
+            pass
+        elif layout == "rowlr":   # the first-order weights ride in the row: one lane sums them, in slot order
             assert_close(lr, lrr[sl], what="lr[rowlr]")
         else:
             assert torch.equal(lr, lrr[sl]), "same kernel, same order"
@@ -100,10 +110,19 @@ def _world():
 
 
 @pytest.mark.parametrize("D", [16, 64])
-@pytest.mark.parametrize("mode", ["peer", "push", "a2a"])
+@pytest.mark.parametrize("mode", ["stream", "peer", "push", "a2a"])
 def test_sharded_matches_single_table(mode, D, tmp_path):
     world = _world()
     mp.spawn(_worker, args=(world, _free_port(), mode, D, str(tmp_path)), nprocs=world, join=True)
+    assert all(os.path.exists(os.path.join(str(tmp_path), "ok%d" % r)) for r in range(world))
+
+
+@pytest.mark.parametrize("D", [4, 16, 32, 128])
+@pytest.mark.parametrize("layout", ["rowlr", "rowpad"])
+def test_sharded_stream_layouts_match_single_table(layout, D, tmp_path):
+    """Streamed exchange with the row + first-order weight in one physical row (2 D or D + 4 floats)."""
+    world = _world()
+    mp.spawn(_worker, args=(world, _free_port(), "stream_" + layout, D, str(tmp_path)), nprocs=world, join=True)
     assert all(os.path.exists(os.path.join(str(tmp_path), "ok%d" % r)) for r in range(world))
 
 
