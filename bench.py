@@ -444,7 +444,7 @@ def main_sharded(args, rank, world, local_rank):
     if args.shard_layout == "auto":     # ROW+LR wins on multi-GB tables at every N (profiles/r1_sharded_runs.jsonl, r2e / r1w)
         args.shard_layout = "rowlr" if (args.shard_mode in ("peer", "stream") and not args.no_lr and D in (4, 8, 16)) else "split"
     sh = sharded.ShardedEmbeddingFM(R, D, mode=args.shard_mode, device=dev, max_ids=B * F, alloc=args.peer_alloc, with_lr=not args.no_lr,
-                                    layout=args.shard_layout)
+                                    layout=args.shard_layout, chunks=args.shard_chunks, slack=1.25)
     gen = torch.Generator(device=dev).manual_seed(20240 + 4 + rank)
     sh.table.normal_(0, 0.01, generator=gen)
     sh.table_lr.normal_(0, 0.01, generator=gen)
@@ -503,6 +503,15 @@ def main_sharded(args, rank, world, local_rank):
     t_f = sum(e[0].elapsed_time(e[1]) for e in evs) / K
     t_b = sum(e[1].elapsed_time(e[2]) for e in evs) / K
     t_s = sum(e[2].elapsed_time(e[3]) for e in evs) / K
+    phases = None
+    if args.shard_mode == "stream":       # a second, separately timed pass with an event after every phase (rank 0's view)
+        sh.profile = []
+        for i in range(K):
+            step(i)
+        torch.cuda.synchronize()
+        phases = {k: v / K for k, v in sh.phase_times(sh.profile).items()}
+        sh.profile = None
+        barrier()
     times = torch.tensor([ms_total, t_f, t_b, t_s], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
@@ -520,7 +529,8 @@ def main_sharded(args, rank, world, local_rank):
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": "BASELINE configs[3]: DeepFM hot path, %d-row fused table (26 x %d) row-sharded over %d GPU(s), "
                                    "D=%d, B=65536 per GPU; mode=%s%s" % (R, V, world, D, args.shard_mode,
-                                                                            ", layout=%s" % args.shard_layout if args.shard_layout != "split" else ""),
+                                                                            (", layout=%s" % args.shard_layout if args.shard_layout != "split" else "") +
+                                                                            (", %d pipelined sample ranges" % args.shard_chunks if args.shard_chunks > 1 else "")),
                        "global_batch": B * world, "ids": args.ids, "batches_rotated": NB,
                        "l2": "table shard (%.1f GB) and E/dE streams exceed the 126 MB L2" % (sh.cap * D * 4 / 1e9),
                        "parallelism": "dp%d batch shards + row-sharded table (r %% %d), exchange inside the fused kernels over NVLink" % (world, world)
@@ -540,6 +550,8 @@ def main_sharded(args, rank, world, local_rank):
                         "step_barrier": {"ms": t_s}},
             "clocks": sampler.summary(),
         }
+        if phases is not None:
+            line["phases_ms_rank0"] = phases
         print(json.dumps(line))
     sh.close()
     if world > 1:
@@ -562,6 +574,7 @@ def main():
     ap.add_argument("--peer-alloc", default="symm", choices=["ipc", "symm"])
     ap.add_argument("--shard-layout", default="auto", choices=["auto", "split", "rowlr", "rowpad"],
                     help="rowlr: embedding row + first-order weight in one physical row (one NVLink request per slot)")
+    ap.add_argument("--shard-chunks", type=int, default=1, help="stream mode: sample ranges pipelined on their own streams")
     ap.add_argument("--no-lr", action="store_true", help="sharded workload without the first-order (LR) table")
     ap.add_argument("--dim", type=int, default=16)
     ap.add_argument("--rows-per-field", type=int, default=3846154)

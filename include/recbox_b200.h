@@ -91,6 +91,16 @@ int rbx_pack_columns(const void* const* cols /*HOST [n] of DEVICE ptrs*/,
                      int32_t* n_bad /*DEVICE [1] | NULL*/,
                      rbx_stream_t stream);
 
+/* Compact form of the id block (recbox_b200.loader.PackedDataset, every vocabulary < 65 536 -- the
+ * Criteo config of BASELINE configs[1]): uint16 local ids [B,F] cross PCIe (2 B instead of the 8 B the
+ * reference's float64 batch matrix spends, h5_dataloader.py:46); rows[b,f] = ids[b,f] + field_off[f]. */
+int rbx_unpack_ids_u16(const uint16_t* ids /*DEVICE [B,F]*/, int64_t B, int F, const int64_t* field_off /*HOST [F] | NULL*/,
+                       int32_t* rows /*DEVICE [B,F]*/, rbx_stream_t stream);
+
+/* optimizer.zero_grad() of the fused gradient buffer (ranking_model.py:192): one streaming fill, so the
+ * zero-fill can run on a side stream under the forward instead of on the backward's critical path. */
+int rbx_zero_f32(float* ptr /*DEVICE [n]*/, int64_t n, rbx_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------
  * a2+a3+a6+a7+a8  fused multi-slot gather + FM + LR, forward      (kernel K1/K2)
  * One launch does what the reference spreads over
@@ -360,7 +370,8 @@ int rbx_shard_apply_grads(const float* ginbox /*DEVICE [world,cap,D]*/, const fl
  *                        floats), rowbuf_lr[q][rank*cap + j] = lr[id * lr_stride]
  *   rbx_xs_consume       requester: E / S / fm_out / lr_out of rbx_embed_fm_fwd from its row buffer
  *   rbx_xs_grad_push     requester: ginbox[w][rank*cap + slot] = dE + d_fm (S - e) (zero for padding rows),
- *                        ginbox_lr likewise = d_lr; numeric-slot gradients stay with rbx_embed_fm_bwd (F = 0)
+ *                        ginbox_lr likewise = d_lr; the numeric-slot / bias batch reductions of rbx_embed_fm_bwd
+ *                        (g_dense_w, g_dense_w_lr, g_lr_bias) ride in the same launch (Fn * D / 4 <= 256)
  *   rbx_xs_apply         owner: g_table[inbox_ids[q*cap + j]] += ginbox[q*cap + j] (red.global.add) */
 int rbx_xs_tile_samples(int F, int D);
 int rbx_xs_route(const int32_t* rows /*DEVICE [B,F]*/, int64_t B, int F, int64_t R, int D,
@@ -383,7 +394,11 @@ int rbx_xs_grad_push(const float* E /*| NULL: e re-read from rowbuf*/, const flo
                      const float* dE, const float* d_fm, const float* d_lr,
                      const int32_t* rows /*DEVICE [B,F]*/, const int32_t* pad_row /*HOST [F] | NULL*/,
                      const int32_t* tile_base, const int32_t* tile_cnt, const uint16_t* pair_sorted,
-                     const int32_t* cat_pos /*HOST [F]*/, int64_t B, int64_t cap, int F, int D, int n_slots,
+                     const int32_t* cat_pos /*HOST [F]*/,
+                     const float* dense_x, const float* dense_w, const int32_t* num_pos /*HOST [Fn]*/,
+                     const int32_t* num_widx /*HOST | NULL*/, int Fn,
+                     float* g_dense_w /*[Fn_total,D] | NULL*/, float* g_dense_w_lr /*| NULL*/, float* g_lr_bias /*| NULL*/,
+                     int64_t B, int64_t cap, int F, int D, int n_slots,
                      int rank, int world, void* const* ginbox, void* const* ginbox_lr /*| NULL*/, rbx_stream_t stream);
 int rbx_xs_apply(const float* ginbox /*DEVICE [world,cap,D]*/, const float* ginbox_lr /*| NULL*/,
                  const int32_t* inbox_ids, const int32_t* meta, int64_t cap, int world,

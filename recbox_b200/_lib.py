@@ -17,7 +17,7 @@ HEADER = os.path.join(os.path.dirname(_HERE), "include", "recbox_b200.h")
 NVCC_FLAGS = [
     "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
     "-Xptxas=-v",
-    "-Xcompiler", "-fPIC", "-shared",
+    "-Xcompiler", "-fPIC", "-shared", "-ldl",
 ]
 
 
@@ -79,6 +79,8 @@ SIGNATURES = {
     "rbx_l2_set_persisting_bytes": [_c.c_longlong],
     "rbx_split_batch_f64": [_P, _I64, _I, _I64, _P, _P, _P, _P, _I, _I, _P, _P, _P, _P, _P],
     "rbx_pack_columns": [_P, _P, _P, _P, _P, _I, _I64, _I, _P, _P, _P],
+    "rbx_unpack_ids_u16": [_P, _I64, _I, _P, _P, _P],
+    "rbx_zero_f32": [_P, _I64, _P],
     "rbx_embed_fm_fwd": [_P] * 15 + [_I64, _I64, _I, _I, _I, _I, _P],
     "rbx_embed_fm_bwd": [_P] * 19 + [_I64, _I64, _I, _I, _I, _I, _P],
     "rbx_gather_rows": [_P, _P, _P, _I64, _I, _P],
@@ -109,7 +111,7 @@ SIGNATURES = {
     "rbx_xs_barrier": [_P, _P, _P, _I, _I, _c.c_uint32, _P],
     "rbx_xs_serve": [_P, _I64, _P, _I64, _I, _P, _P, _I64, _I, _I, _P, _P, _P],
     "rbx_xs_consume": [_P] * 16 + [_I64, _I64, _I, _I, _I, _I, _I, _P],
-    "rbx_xs_grad_push": [_P] * 12 + [_I64, _I64, _I, _I, _I, _I, _I, _P, _P, _P],
+    "rbx_xs_grad_push": [_P] * 16 + [_I, _P, _P, _P, _I64, _I64, _I, _I, _I, _I, _I, _P, _P, _P],
     "rbx_xs_apply": [_P, _P, _P, _P, _I64, _I, _P, _I64, _P, _I64, _I, _P],
     "rbx_peer_alloc": [_c.c_size_t, _P],
     "rbx_peer_free": [_P],

@@ -190,6 +190,7 @@ __global__ void __launch_bounds__(kT) k_inverse(const IdT* __restrict__ ids, int
 template <typename IdT>
 int unique_impl(const char* who, const IdT* ids, int64_t n, int64_t vocab, void* ws, size_t ws_have, IdT* uniq, int64_t* first,
                 IdT* inverse, int64_t* n_out, rbx_stream_t stream) {
+    RBX_RANGE(who);
     RBX_REQUIRE(n >= 0 && vocab >= 1, "%s: n=%lld vocab=%lld", who, (long long)n, (long long)vocab);
     RBX_REQUIRE(vocab <= (int64_t)INT32_MAX * 32, "%s: vocab=%lld too large for the bitmap", who, (long long)vocab);
     RBX_REQUIRE(sizeof(IdT) == 8 || vocab <= (int64_t)INT32_MAX, "%s: int32 ids need vocab < 2^31", who);

@@ -1011,6 +1011,7 @@ int embed_fm_fwd_impl(const char* who, const float* table, const float* table_lr
                       const float* dense_w_lr, const int32_t* num_pos, const int32_t* num_widx, const float* lr_bias,
                       float* E, float* S, float* fm_out, float* lr_out, int64_t B, int64_t R, int F, int Fn, int D,
                       int n_slots, rbx_stream_t stream) {
+    RBX_RANGE(who);
     const bool sharded = sh.world > 0;
     RBX_REQUIRE(B >= 0 && F >= 0 && Fn >= 0 && D >= 1, "%s: negative size", who);
     RBX_REQUIRE(F <= RBX_MAX_SLOTS && Fn <= RBX_MAX_SLOTS, "%s: more than %d slots", who, RBX_MAX_SLOTS);
@@ -1080,6 +1081,7 @@ int embed_fm_bwd_impl(const char* who, const float* table, const ShardArgs& sh, 
                       const float* d_fm, const float* d_lr, float* g_table, float* g_table_lr, float* g_dense_w,
                       float* g_dense_w_lr, float* g_lr_bias, int64_t B, int64_t R, int F, int Fn, int D, int n_slots,
                       rbx_stream_t stream) {
+    RBX_RANGE(who);
     const bool sharded = sh.world > 0;
     RBX_REQUIRE(B >= 0 && F >= 0 && Fn >= 0 && D >= 1, "%s: negative size", who);
     RBX_REQUIRE(F <= RBX_MAX_SLOTS && Fn <= RBX_MAX_SLOTS, "%s: more than %d slots", who, RBX_MAX_SLOTS);

@@ -381,6 +381,7 @@ extern "C" {
 
 int rbx_gather_rows(const float* table, const int32_t* ids, float* out, int64_t N, int D, rbx_stream_t stream) {
     const char* who = "rbx_gather_rows";
+    RBX_RANGE(who);
     RBX_REQUIRE(N >= 0 && D >= 1 && D <= RBX_MAX_DIM, "%s: bad size", who);
     if (N == 0) return RBX_OK;
     RBX_REQUIRE(table && ids && out, "%s: null pointer", who);
@@ -398,6 +399,7 @@ int rbx_gather_rows(const float* table, const int32_t* ids, float* out, int64_t 
 int rbx_scatter_add_rows(const float* g, const int32_t* ids, int32_t pad_row, float* g_table, int64_t N, int D,
                          rbx_stream_t stream) {
     const char* who = "rbx_scatter_add_rows";
+    RBX_RANGE(who);
     RBX_REQUIRE(N >= 0 && D >= 1 && D <= RBX_MAX_DIM, "%s: bad size", who);
     if (N == 0) return RBX_OK;
     RBX_REQUIRE(g && ids && g_table, "%s: null pointer", who);
@@ -415,6 +417,7 @@ int rbx_scatter_add_rows(const float* g, const int32_t* ids, int32_t pad_row, fl
 int rbx_pooled_gather_fwd(const float* table, const int32_t* ids, int64_t ids_ld, float* out, int64_t out_ld,
                           float* cnt, int64_t B, int L, int D, int mode, rbx_stream_t stream) {
     const char* who = "rbx_pooled_gather_fwd";
+    RBX_RANGE(who);
     RBX_REQUIRE(B >= 0 && L >= 0 && D >= 1 && D <= RBX_MAX_DIM, "%s: bad size", who);
     RBX_REQUIRE(mode == 0 || mode == 1, "%s: mode %d", who, mode);
     RBX_REQUIRE(ids_ld >= L && out_ld >= D, "%s: leading dimension too small", who);
@@ -434,6 +437,7 @@ int rbx_pooled_gather_fwd(const float* table, const int32_t* ids, int64_t ids_ld
 int rbx_pooled_gather_bwd(const float* g, int64_t g_ld, const int32_t* ids, int64_t ids_ld, const float* cnt,
                           int32_t pad_row, float* g_table, int64_t B, int L, int D, int mode, rbx_stream_t stream) {
     const char* who = "rbx_pooled_gather_bwd";
+    RBX_RANGE(who);
     RBX_REQUIRE(B >= 0 && L >= 0 && D >= 1 && D <= RBX_MAX_DIM, "%s: bad size", who);
     RBX_REQUIRE(mode == 0 || mode == 1, "%s: mode %d", who, mode);
     RBX_REQUIRE(mode == 0 || cnt, "%s: cnt (saved by the forward) required for masked average", who);
@@ -454,6 +458,7 @@ int rbx_pooled_gather_bwd(const float* g, int64_t g_ld, const int32_t* ids, int6
 int rbx_pool_fwd(const float* emb, const uint8_t* mask, float* out, float* cnt, int64_t B, int L, int D, int mode,
                  rbx_stream_t stream) {
     const char* who = "rbx_pool_fwd";
+    RBX_RANGE(who);
     RBX_REQUIRE(B >= 0 && L >= 0 && D >= 1 && D <= RBX_MAX_DIM, "%s: bad size", who);
     RBX_REQUIRE(mode == 0 || mode == 1, "%s: mode %d", who, mode);
     if (B == 0) return RBX_OK;
@@ -469,6 +474,7 @@ int rbx_pool_fwd(const float* emb, const uint8_t* mask, float* out, float* cnt, 
 
 int rbx_pool_bwd(const float* g, const float* cnt, float* d_emb, int64_t B, int L, int D, int mode, rbx_stream_t stream) {
     const char* who = "rbx_pool_bwd";
+    RBX_RANGE(who);
     RBX_REQUIRE(B >= 0 && L >= 0 && D >= 1 && D <= RBX_MAX_DIM, "%s: bad size", who);
     RBX_REQUIRE(mode == 0 || (mode == 1 && cnt), "%s: mode %d / cnt", who, mode);
     if (B == 0 || L == 0) return RBX_OK;

@@ -775,6 +775,7 @@ extern "C" {
 
 int rbx_interact_fwd(const float* E, float* out, int64_t B, int F, int D, int mode, rbx_stream_t stream) {
     const char* who = "rbx_interact_fwd";
+    RBX_RANGE(who);
     RBX_REQUIRE(B >= 0 && F >= 1 && D >= 1 && D <= RBX_MAX_DIM, "%s: bad size", who);
     RBX_REQUIRE(mode >= 0 && mode <= 3, "%s: InnerProductInteraction mode %d is not supported", who, mode);
     if (B == 0) return RBX_OK;
@@ -820,6 +821,7 @@ int rbx_interact_fwd(const float* E, float* out, int64_t B, int F, int D, int mo
 int rbx_interact_bwd(const float* E, const float* dout, float* dE, int64_t B, int F, int D, int mode,
                      rbx_stream_t stream) {
     const char* who = "rbx_interact_bwd";
+    RBX_RANGE(who);
     RBX_REQUIRE(B >= 0 && F >= 1 && D >= 1 && D <= RBX_MAX_DIM, "%s: bad size", who);
     RBX_REQUIRE(mode >= 0 && mode <= 3, "%s: InnerProductInteraction mode %d is not supported", who, mode);
     if (B == 0) return RBX_OK;
@@ -894,6 +896,7 @@ int rbx_interact_bwd(const float* E, const float* dout, float* dE, int64_t B, in
 
 int rbx_power_sums_fwd(const float* E, float* P, int64_t B, int F, int D, int order, rbx_stream_t stream) {
     const char* who = "rbx_power_sums_fwd";
+    RBX_RANGE(who);
     RBX_REQUIRE(B >= 0 && F >= 1 && D >= 1 && D <= RBX_MAX_DIM, "%s: bad size", who);
     RBX_REQUIRE(order >= 1 && order <= kMaxOrder, "%s: order=%d is not supported", who, order);
     if (B == 0) return RBX_OK;
@@ -913,6 +916,7 @@ int rbx_power_sums_fwd(const float* E, float* P, int64_t B, int F, int D, int or
 
 int rbx_power_sums_bwd(const float* E, const float* dP, float* dE, int64_t B, int F, int D, int order, rbx_stream_t stream) {
     const char* who = "rbx_power_sums_bwd";
+    RBX_RANGE(who);
     RBX_REQUIRE(B >= 0 && F >= 1 && D >= 1 && D <= RBX_MAX_DIM, "%s: bad size", who);
     RBX_REQUIRE(order >= 1 && order <= kMaxOrder, "%s: order=%d is not supported", who, order);
     if (B == 0) return RBX_OK;

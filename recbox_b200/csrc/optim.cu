@@ -192,6 +192,7 @@ extern "C" {
 
 int rbx_sqnorm(const float* g, int64_t n, double* out, rbx_stream_t stream) {
     const char* who = "rbx_sqnorm";
+    RBX_RANGE(who);
     RBX_REQUIRE(n >= 0 && out, "%s: bad argument", who);
     if (n == 0) return RBX_OK;
     RBX_REQUIRE(g != nullptr, "%s: null pointer", who);
@@ -206,6 +207,7 @@ int rbx_sqnorm(const float* g, int64_t n, double* out, rbx_stream_t stream) {
 
 int rbx_clip_coef(const double* sqnorm, float max_norm, float* coef, float* norm_out, rbx_stream_t stream) {
     const char* who = "rbx_clip_coef";
+    RBX_RANGE(who);
     RBX_REQUIRE(sqnorm && coef, "%s: null pointer", who);
     k_clip_coef<<<1, 1, 0, rbx_cast_stream(stream)>>>(sqnorm, max_norm, coef, norm_out);
     RBX_LAUNCH_CHECK(who);
@@ -215,6 +217,7 @@ int rbx_clip_coef(const double* sqnorm, float max_norm, float* coef, float* norm
 int rbx_adam_dense(float* w, const float* g, float* m, float* v, int64_t n, const float* clip, float lr, float beta1,
                    float beta2, float eps, int step, rbx_stream_t stream) {
     const char* who = "rbx_adam_dense";
+    RBX_RANGE(who);
     RBX_REQUIRE(n >= 0 && step >= 1, "%s: bad argument (step counts from 1)", who);
     if (n == 0) return RBX_OK;
     RBX_REQUIRE(w && g && m && v, "%s: null pointer", who);
@@ -241,6 +244,7 @@ int rbx_adam_dense(float* w, const float* g, float* m, float* v, int64_t n, cons
 int rbx_sqnorm_rows(const float* g, const int32_t* rows, const int64_t* n_rows_dev, int64_t max_rows, int D, double* out,
                     rbx_stream_t stream) {
     const char* who = "rbx_sqnorm_rows";
+    RBX_RANGE(who);
     RBX_REQUIRE(max_rows >= 0 && D >= 1 && out, "%s: bad argument", who);
     if (max_rows == 0) return RBX_OK;
     RBX_REQUIRE(g && rows, "%s: null pointer", who);
@@ -255,6 +259,7 @@ int rbx_optim_rows(float* w, float* g, float* m, float* v, const int32_t* rows, 
                    int D, const float* clip, int kind, float lr, float beta1, float beta2, float eps, int step, int zero_grad,
                    rbx_stream_t stream) {
     const char* who = "rbx_optim_rows";
+    RBX_RANGE(who);
     RBX_REQUIRE(max_rows >= 0 && D >= 1 && step >= 1, "%s: bad argument (step counts from 1)", who);
     RBX_REQUIRE(kind >= 0 && kind <= 3, "%s: kind=%d (0 sgd, 1 adagrad, 2 adam rows, 3 sparse adam)", who, kind);
     if (max_rows == 0) return RBX_OK;

@@ -129,14 +129,86 @@ __global__ void __launch_bounds__(256) k_pack_columns(const __grid_constant__ Pa
     }
 }
 
+// compact ids: uint16 local ids (every vocabulary < 65 536) -> int32 fused-table rows
+__global__ void __launch_bounds__(256) k_unpack_ids_u16(const uint16_t* __restrict__ ids, int32_t* __restrict__ rows, int64_t n,
+                                                        int F, const __grid_constant__ SplitParams p) {
+    __shared__ int32_t s_add[kMaxCols];
+    for (int c = threadIdx.x; c < F; c += blockDim.x) s_add[c] = p.col_add[c];
+    __syncthreads();
+    // 8 ids (16 bytes) per thread; F is arbitrary, so the slot of element e is e % F
+    const int64_t n8 = ((uintptr_t)ids % 16 == 0 && (uintptr_t)rows % 16 == 0) ? n / 8 : 0;
+    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n8; i += (int64_t)gridDim.x * 256) {
+        const uint4 v = __ldcs(reinterpret_cast<const uint4*>(ids) + i);
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+        int f = (int)((i * 8) % F);
+        int32_t out[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            out[j] = (int32_t)((w[j >> 1] >> (16 * (j & 1))) & 0xffffu) + s_add[f];
+            f = f + 1 == F ? 0 : f + 1;
+        }
+        reinterpret_cast<int4*>(rows)[2 * i] = make_int4(out[0], out[1], out[2], out[3]);
+        reinterpret_cast<int4*>(rows)[2 * i + 1] = make_int4(out[4], out[5], out[6], out[7]);
+    }
+    for (int64_t e = 8 * n8 + (int64_t)blockIdx.x * 256 + threadIdx.x; e < n; e += (int64_t)gridDim.x * 256)
+        rows[e] = (int32_t)ids[e] + s_add[e % F];
+}
+
+__global__ void __launch_bounds__(256) k_zero_f32(float* __restrict__ p, int64_t n) {
+    const int64_t head = ((16 - (uintptr_t)p % 16) % 16) / 4;          // floats up to the first 16-byte boundary
+    const int64_t h = head < n ? head : n;
+    const int64_t n4 = (n - h) / 4;
+    float4* p4 = reinterpret_cast<float4*>(p + h);
+    const int64_t tid = (int64_t)blockIdx.x * 256 + threadIdx.x, nth = (int64_t)gridDim.x * 256;
+    for (int64_t i = tid; i < n4; i += nth) p4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int64_t i = tid; i < h; i += nth) p[i] = 0.f;
+    for (int64_t i = h + 4 * n4 + tid; i < n; i += nth) p[i] = 0.f;
+}
+
 }  // namespace
 
 extern "C" {
+
+int rbx_unpack_ids_u16(const uint16_t* ids, int64_t B, int F, const int64_t* field_off, int32_t* rows, rbx_stream_t stream) {
+    const char* who = "rbx_unpack_ids_u16";
+    RBX_RANGE(who);
+    RBX_REQUIRE(B >= 0 && F >= 0 && F <= kMaxCols, "%s: bad shape", who);
+    if (B == 0 || F == 0) return RBX_OK;
+    RBX_REQUIRE(ids && rows, "%s: null pointer", who);
+    SplitParams p;
+    for (int f = 0; f < F; ++f) {
+        const int64_t off = field_off ? field_off[f] : 0;
+        RBX_REQUIRE(off >= 0 && off <= INT32_MAX - 65535, "%s: field_off[%d] outside int32", who, f);
+        p.col_add[f] = (int32_t)off;
+    }
+    const int64_t n = B * F;
+    int64_t ctas = (n / 8 + 255) / 256 + 1;
+    const int64_t cap = (int64_t)rbx_sm_count() * 8;
+    if (ctas > cap) ctas = cap;
+    k_unpack_ids_u16<<<(int)ctas, 256, 0, rbx_cast_stream(stream)>>>(ids, rows, n, F, p);
+    RBX_LAUNCH_CHECK(who);
+    return RBX_OK;
+}
+
+int rbx_zero_f32(float* ptr, int64_t n, rbx_stream_t stream) {
+    const char* who = "rbx_zero_f32";
+    RBX_RANGE(who);
+    RBX_REQUIRE(n >= 0, "%s: negative size", who);
+    if (n == 0) return RBX_OK;
+    RBX_REQUIRE(ptr != nullptr, "%s: null pointer", who);
+    int64_t ctas = (n / 4 + 255) / 256 + 1;
+    const int64_t cap = (int64_t)rbx_sm_count() * 8;
+    if (ctas > cap) ctas = cap;
+    k_zero_f32<<<(int)ctas, 256, 0, rbx_cast_stream(stream)>>>(ptr, n);
+    RBX_LAUNCH_CHECK(who);
+    return RBX_OK;
+}
 
 int rbx_split_batch_f64(const double* batch, int64_t B, int n_cols, int64_t ld, const int8_t* col_kind,
                         const int16_t* col_slot, const int64_t* field_off, const int64_t* field_rows, int F, int Fn,
                         int32_t* rows, float* dense_x, float* label, int32_t* n_bad, rbx_stream_t stream) {
     const char* who = "rbx_split_batch_f64";
+    RBX_RANGE(who);
     RBX_REQUIRE(B >= 0 && n_cols >= 0 && ld >= n_cols, "%s: bad shape", who);
     RBX_REQUIRE(n_cols <= kMaxCols, "%s: n_cols=%d > %d", who, n_cols, kMaxCols);
     if (B == 0 || n_cols == 0) return RBX_OK;
@@ -175,6 +247,7 @@ int rbx_split_batch_f64(const double* batch, int64_t B, int n_cols, int64_t ld, 
 int rbx_pack_columns(const void* const* cols, const int64_t* strides, const int8_t* dtypes, const int64_t* add,
                      const int64_t* vocab, int n, int64_t B, int as_rows, void* out, int32_t* n_bad, rbx_stream_t stream) {
     const char* who = "rbx_pack_columns";
+    RBX_RANGE(who);
     RBX_REQUIRE(n >= 0 && B >= 0, "%s: negative size", who);
     if (n == 0 || B == 0) return RBX_OK;
     RBX_REQUIRE(cols && strides && dtypes && out, "%s: null pointer", who);

@@ -19,6 +19,7 @@ extern "C" {
 
 int rbx_peer_alloc(size_t bytes, void** ptr) {
     const char* who = "rbx_peer_alloc";
+    RBX_RANGE(who);
     RBX_REQUIRE(ptr != nullptr, "%s: null out pointer", who);
     *ptr = nullptr;
     if (bytes == 0) bytes = 16;
@@ -33,6 +34,7 @@ int rbx_peer_free(void* ptr) {
 
 int rbx_peer_export(const void* ptr, unsigned char handle[RBX_PEER_HANDLE_BYTES]) {
     const char* who = "rbx_peer_export";
+    RBX_RANGE(who);
     RBX_REQUIRE(ptr && handle, "%s: null pointer", who);
     cudaIpcMemHandle_t h;
     RBX_CUDA(cudaIpcGetMemHandle(&h, const_cast<void*>(ptr)), who);
@@ -42,6 +44,7 @@ int rbx_peer_export(const void* ptr, unsigned char handle[RBX_PEER_HANDLE_BYTES]
 
 int rbx_peer_open(const unsigned char handle[RBX_PEER_HANDLE_BYTES], void** ptr) {
     const char* who = "rbx_peer_open";
+    RBX_RANGE(who);
     RBX_REQUIRE(ptr && handle, "%s: null pointer", who);
     cudaIpcMemHandle_t h;
     memcpy(&h, handle, sizeof(h));

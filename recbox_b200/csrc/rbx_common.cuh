@@ -23,6 +23,15 @@ int rbx_fail(int code, const char* fmt, ...);
             return rbx_fail(RBX_ERR_CUDA, "%s: launch failed: %s", name, cudaGetErrorString(e__)); \
     } while (0)
 
+// NVTX range around an entry point (tracing): visible in nsys / ncu --nvtx timelines, a few
+// nanoseconds when no tool is attached.
+#include <nvtx3/nvToolsExt.h>
+struct RbxRange {
+    explicit RbxRange(const char* name) { nvtxRangePushA(name); }
+    ~RbxRange() { nvtxRangePop(); }
+};
+#define RBX_RANGE(name) RbxRange rbx_range__(name)
+
 // SM count of the current device, cached per device.
 int rbx_sm_count();
 

@@ -118,6 +118,7 @@ extern "C" {
 
 int rbx_rowdot_fwd(const float* u, const float* v, float* y, int64_t B, int K, int D, rbx_stream_t stream) {
     const char* who = "rbx_rowdot_fwd";
+    RBX_RANGE(who);
     RBX_REQUIRE(B >= 0 && K >= 0 && D >= 1 && D <= RBX_MAX_DIM, "%s: bad size", who);
     if (B == 0 || K == 0) return RBX_OK;
     RBX_REQUIRE(u && v && y, "%s: null pointer", who);
@@ -134,6 +135,7 @@ int rbx_rowdot_fwd(const float* u, const float* v, float* y, int64_t B, int K, i
 int rbx_rowdot_bwd(const float* u, const float* v, const float* dy, float* du, float* dv, int64_t B, int K, int D,
                    rbx_stream_t stream) {
     const char* who = "rbx_rowdot_bwd";
+    RBX_RANGE(who);
     RBX_REQUIRE(B >= 0 && K >= 0 && D >= 1 && D <= RBX_MAX_DIM, "%s: bad size", who);
     if (B == 0 || (!du && !dv)) return RBX_OK;
     RBX_REQUIRE(u && v && (dy || K == 0), "%s: null pointer", who);

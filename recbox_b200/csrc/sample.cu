@@ -70,6 +70,7 @@ int rbx_sample_negatives(int64_t n_queries, int num_negs, int64_t num_items, uin
                          const int64_t* user_of_query, const int64_t* pos_ptr, const int64_t* pos_items, int64_t* out,
                          int* gave_up, rbx_stream_t stream) {
     const char* who = "rbx_sample_negatives";
+    RBX_RANGE(who);
     RBX_REQUIRE(n_queries >= 0 && num_negs >= 0 && num_items >= 1, "%s: bad size", who);
     if (n_queries == 0 || (num_negs == 0 && !pos)) return RBX_OK;
     RBX_REQUIRE(out != nullptr, "%s: null output", who);

@@ -147,6 +147,7 @@ size_t rbx_shard_ws_bytes(int64_t N, int world) {
 int rbx_shard_route(const int32_t* rows, int64_t N, int world, void* ws, size_t ws_bytes, int32_t* send, int32_t* pos,
                     int32_t* counts, rbx_stream_t stream) {
     const char* who = "rbx_shard_route";
+    RBX_RANGE(who);
     RBX_REQUIRE(N >= 0 && N <= INT32_MAX, "%s: N outside int32", who);
     RBX_REQUIRE(world >= 1 && world <= kMaxWorld, "%s: world=%d outside [1,%d]", who, world, kMaxWorld);
     RBX_REQUIRE(counts != nullptr, "%s: counts required", who);
@@ -172,6 +173,7 @@ int rbx_shard_route(const int32_t* rows, int64_t N, int world, void* ws, size_t 
 
 static int permute(const char* who, bool inverse, const float* in, const int32_t* pos, float* out, int64_t N, int D,
                    rbx_stream_t stream) {
+    RBX_RANGE(who);
     RBX_REQUIRE(N >= 0 && D >= 1, "%s: bad size", who);
     if (N == 0) return RBX_OK;
     RBX_REQUIRE(in && pos && out, "%s: null pointer", who);

@@ -195,6 +195,7 @@ extern "C" {
 int rbx_shard_push_ids(const int32_t* send, const int32_t* counts, int32_t* const* inbox_ids, int32_t* const* inbox_meta,
                        int rank, int world, int64_t cap, int64_t N, rbx_stream_t stream) {
     const char* who = "rbx_shard_push_ids";
+    RBX_RANGE(who);
     RBX_REQUIRE(world >= 1 && world <= RBX_MAX_WORLD && rank >= 0 && rank < world, "%s: rank/world", who);
     RBX_REQUIRE(cap >= 1 && N >= 0 && counts, "%s: bad size", who);
     RBX_REQUIRE(N == 0 || send, "%s: null send", who);
@@ -213,6 +214,7 @@ int rbx_shard_serve_rows(const float* table, const float* table_lr, int D, const
                          const int32_t* inbox_meta, float* const* out_rows, float* const* out_lr, int world, int64_t cap,
                          rbx_stream_t stream) {
     const char* who = "rbx_shard_serve_rows";
+    RBX_RANGE(who);
     RBX_REQUIRE(world >= 1 && world <= RBX_MAX_WORLD && cap >= 1, "%s: bad size", who);
     RBX_REQUIRE(table && inbox_ids && inbox_meta, "%s: null pointer", who);
     RBX_REQUIRE(!out_lr || table_lr, "%s: table_lr required with out_lr", who);
@@ -230,6 +232,7 @@ int rbx_shard_serve_rows(const float* table, const float* table_lr, int D, const
 int rbx_shard_push_grads(const float* gsend, const float* gsend_lr, const int32_t* counts, float* const* ginbox,
                          float* const* ginbox_lr, int rank, int world, int64_t cap, int D, int64_t N, rbx_stream_t stream) {
     const char* who = "rbx_shard_push_grads";
+    RBX_RANGE(who);
     RBX_REQUIRE(world >= 1 && world <= RBX_MAX_WORLD && rank >= 0 && rank < world, "%s: rank/world", who);
     RBX_REQUIRE(cap >= 1 && N >= 0 && counts && D % 4 == 0, "%s: bad size (D %% 4 == 0 required)", who);
     RBX_REQUIRE(N == 0 || gsend, "%s: null gsend", who);
@@ -246,6 +249,7 @@ int rbx_shard_apply_grads(const float* ginbox, const float* ginbox_lr, const int
                           float* g_table, float* g_table_lr, int world, int64_t cap, int D, const int32_t* pad_local,
                           int n_pad, rbx_stream_t stream) {
     const char* who = "rbx_shard_apply_grads";
+    RBX_RANGE(who);
     RBX_REQUIRE(world >= 1 && world <= RBX_MAX_WORLD && cap >= 1, "%s: bad size", who);
     RBX_REQUIRE(ginbox && inbox_ids && inbox_meta && g_table, "%s: null pointer", who);
     if (!pow2_dim(D)) return rbx_fail(RBX_ERR_UNSUPPORTED, "%s: D=%d (covers 4..128, powers of two)", who, D);

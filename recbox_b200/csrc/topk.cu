@@ -432,6 +432,7 @@ size_t rbx_topk_ws_bytes(int64_t U, int k, int64_t chunk) {
 int rbx_topk_ip(const float* q, const float* items, int64_t U, int64_t N, int D, int k, int64_t chunk, float* out_scores,
                 int64_t* out_idx, void* ws, size_t ws_bytes, rbx_stream_t stream) {
     const char* who = "rbx_topk_ip";
+    RBX_RANGE(who);
     RBX_REQUIRE(U >= 0 && N >= 0 && N < 0xffffffffll, "%s: bad size", who);
     RBX_REQUIRE(k >= 1 && k <= kMaxK, "%s: k=%d outside [1, %d]", who, k, kMaxK);
     RBX_REQUIRE(D >= 4 && D <= 128 && D % 4 == 0, "%s: D=%d (needs a multiple of 4 in [4, 128])", who, D);
@@ -495,6 +496,7 @@ int rbx_rank_metrics(const int64_t* cand, int T, int64_t U, const int64_t* train
                      const int64_t* valid_ptr, const int64_t* valid_items, int kmax, const int* kinds, const int* ks, int M,
                      int64_t* ranked, uint8_t* hit, double* out, rbx_stream_t stream) {
     const char* who = "rbx_rank_metrics";
+    RBX_RANGE(who);
     RBX_REQUIRE(U >= 0 && T >= 1 && kmax >= 1 && M >= 0, "%s: bad size", who);
     if (U == 0) return RBX_OK;
     RBX_REQUIRE(cand && valid_ptr && valid_items && ranked && hit, "%s: null pointer", who);

@@ -196,6 +196,44 @@ class _Call(object):
                  "lr_group", "lr_bias", "params", "kinds", "emb_sizes", "lr_emb_sizes", "with_main", "with_lr", "seq")
 
 
+ASYNC_ZERO = True        # zero-fill of the dense gradient buffer on a side stream, under the forward
+_side_streams = {}
+
+
+def _grad_layout(call, with_main, with_lr):
+    """Sizes and offsets (floats, 16-byte aligned) of [table | numeric weights | lr table | lr numeric | lr bias] in the one
+    gradient allocation of a fused launch."""
+    g, lg, D = call.group, call.lr_group, call.D
+    sizes = (g.R * D if (with_main and g is not None and g.emb) else 0,
+             len(g.lin) * D if (with_main and g is not None and g.lin) else 0,
+             lg.R if (with_lr and lg is not None and lg.emb) else 0,
+             len(lg.lin) if (with_lr and lg is not None and lg.lin) else 0,
+             1 if (with_lr and call.lr_bias is not None) else 0)
+    offs, tot = [], 0
+    for n in sizes:
+        offs.append(tot)
+        tot += (n + 3) // 4 * 4
+    return sizes, offs, tot
+
+
+def _prezero(layout, dev):
+    """-> (buffer, event): buffer allocated on the current stream, zero-filled (rbx_zero_f32) on the device's side stream."""
+    tot = max(layout[2], 1)
+    main = torch.cuda.current_stream(dev)
+    side = _side_streams.get(dev)
+    if side is None:
+        side = _side_streams[dev] = torch.cuda.Stream(device=dev)
+    buf = torch.empty(tot, dtype=F32, device=dev)
+    here = torch.cuda.Event()
+    here.record(main)                  # the block is free in `main`'s order from here on
+    side.wait_event(here)
+    with torch.cuda.stream(side):
+        ops.zero_(buf)
+    done = torch.cuda.Event()
+    done.record(side)
+    return buf, done
+
+
 class _FusedEmbedFn(torch.autograd.Function):
     """E, fm, lr = fused(rows, dense_x; per-feature parameters).  The parameters are passed so that
     autograd tracks them; the kernels read the fused buffers they alias."""
@@ -225,6 +263,12 @@ class _FusedEmbedFn(torch.autograd.Function):
         ctx.call = call
         ctx.n_seq = len(seq)
         ctx.has_cnt = [c is not None for c in cnts]
+        # optimizer.zero_grad() of the dense gradient buffer, off the backward's critical path: the buffer the backward
+        # will scatter into is allocated NOW and zero-filled on a side stream while the forward kernels (and the rest
+        # of the model's forward) run; the backward only waits for the fill's event
+        ctx.gbuf = None
+        if ASYNC_ZERO and E is not None and E.is_cuda and any(ctx.needs_input_grad[4:]):
+            ctx.gbuf = _prezero(_grad_layout(call, call.with_main, call.with_lr), E.device)
         ctx.save_for_backward(rows, dense_x, E if want_fm else None, S, *seq_ids, *[c for c in cnts if c is not None])
         return (E, fm.view(-1, 1) if fm is not None else None, lr.view(-1, 1) if lr is not None else None)
 
@@ -243,16 +287,18 @@ class _FusedEmbedFn(torch.autograd.Function):
         have_main = call.with_main and (dE is not None or d_fm is not None)
         have_lr = call.with_lr and d_lr is not None
         # one allocation, one zero-fill, for every dense gradient this launch produces
-        n_t = g.R * D if (have_main and g.emb) else 0
-        n_w = len(g.lin) * D if (have_main and g.lin) else 0
-        n_t1 = lg.R if (have_lr and lg.emb) else 0
-        n_w1 = len(lg.lin) if (have_lr and lg.lin) else 0
-        n_b = 1 if (have_lr and call.lr_bias is not None) else 0
-        offs, tot = [], 0
-        for n in (n_t, n_w, n_t1, n_w1, n_b):
-            offs.append(tot)
-            tot += (n + 3) // 4 * 4
-        buf = torch.zeros(max(tot, 1), dtype=F32, device=dev)
+        pre, ctx.gbuf = ctx.gbuf, None                 # (a second backward through a retained graph gets a fresh buffer)
+        if pre is not None:
+            (n_t, n_w, n_t1, n_w1, n_b), offs, tot = _grad_layout(call, call.with_main, call.with_lr)
+            buf, ev = pre
+            torch.cuda.current_stream(dev).wait_event(ev)
+            if not have_main:
+                n_t = n_w = 0
+            if not have_lr:
+                n_t1 = n_w1 = n_b = 0
+        else:
+            (n_t, n_w, n_t1, n_w1, n_b), offs, tot = _grad_layout(call, have_main, have_lr)
+            buf = torch.zeros(max(tot, 1), dtype=F32, device=dev)
         g_table = buf[offs[0]:offs[0] + n_t].view(-1, D) if n_t else None
         g_dw = buf[offs[1]:offs[1] + n_w].view(-1, D) if n_w else None
         g_t1 = buf[offs[2]:offs[2] + n_t1] if n_t1 else None
@@ -703,6 +749,8 @@ class _FusedDictBase(nn.Module):
             if cats and pb.ids is not None and pb.ids.is_cuda and list(cats) == list(pb.cat_names) \
                     and pb.offsets is not None and not any(offs):
                 rows = pb.ids                           # the block IS the kernels' `rows` argument
+            elif cats and pb.ids16 is not None and pb.ids16.is_cuda and list(cats) == list(pb.cat_names):
+                rows = ops.unpack_ids_u16(pb.ids16, offs)   # compact block: uint16 local ids + row offsets, one launch
             if nums and pb.dense is not None and pb.dense.is_cuda and list(nums) == list(pb.num_names):
                 dense_x = pb.dense
         if cats and rows is None:

@@ -7,7 +7,7 @@ where every embedding lookup casts its column back with `.long()` (`feature_embe
 floats travel as 8-byte doubles: 320 B per Criteo sample over PCIe.
 
 `PackedDataset` does the conversion ONCE when the data is loaded: categorical ids -> one pinned int32
-`[N, F]` block, numeric values -> one pinned fp32 `[N, Fn]` block, label -> pinned fp32 `[N]` -- 160 B per
+`[N, F]` block (uint16 when every vocabulary is below 65 536: 108 B per Criteo sample), numeric values -> one pinned fp32 `[N, Fn]` block, label -> pinned fp32 `[N]` -- 160 B per
 Criteo sample.  `PackedDataLoader` mirrors the reference `DataLoader`'s surface (`num_samples`,
 `num_batches`, `len()`, iteration, `shuffle`) and yields `PackedBatch`es: three contiguous pinned slices
 (shuffle: one host index-gather per block into a pinned ring), each one async H2D copy; the fused embedding
@@ -27,29 +27,34 @@ I32, F32 = torch.int32, torch.float32
 
 
 class PackedBatch(object):
-    """One batch: ids int32 [B,F] (+ row offsets when `offsets` is set), dense fp32 [B,Fn], labels fp32 [B]."""
-    __slots__ = ("ids", "dense", "labels", "cat_names", "num_names", "offsets", "feature_map")
+    """One batch: ids int32 [B,F] (+ row offsets when `offsets` is set) -- or, in the compact form, ids16: int16 [B,F]
+    holding uint16 LOCAL ids (every vocabulary < 65 536; the layer adds the row offsets on the device) --, dense fp32
+    [B,Fn], labels fp32 [B]."""
+    __slots__ = ("ids", "ids16", "dense", "labels", "cat_names", "num_names", "offsets", "feature_map")
 
-    def __init__(self, ids, dense, labels, cat_names, num_names, offsets, feature_map):
-        self.ids, self.dense, self.labels = ids, dense, labels
+    def __init__(self, ids, dense, labels, cat_names, num_names, offsets, feature_map, ids16=None):
+        self.ids, self.ids16, self.dense, self.labels = ids, ids16, dense, labels
         self.cat_names, self.num_names, self.offsets, self.feature_map = cat_names, num_names, offsets, feature_map
 
     def __len__(self):
-        return (self.ids if self.ids is not None else self.dense).shape[0]
+        for t in (self.ids, self.ids16, self.dense, self.labels):
+            if t is not None:
+                return t.shape[0]
+        return 0
 
     @property
     def nbytes(self):
-        return sum(t.numel() * t.element_size() for t in (self.ids, self.dense, self.labels) if t is not None)
+        return sum(t.numel() * t.element_size() for t in (self.ids, self.ids16, self.dense, self.labels) if t is not None)
 
     def to(self, device, non_blocking=True):
         """Three async copies (pinned -> device) on the current stream."""
         mv = lambda t: None if t is None else t.to(device, non_blocking=non_blocking)
         return PackedBatch(mv(self.ids), mv(self.dense), mv(self.labels), self.cat_names, self.num_names, self.offsets,
-                           self.feature_map)
+                           self.feature_map, ids16=mv(self.ids16))
 
     def copy_into(self, dst, non_blocking=True):
         """Copy into a preallocated device PackedBatch of the same shape (double-buffered prefetch)."""
-        for a, b in ((dst.ids, self.ids), (dst.dense, self.dense), (dst.labels, self.labels)):
+        for a, b in ((dst.ids, self.ids), (dst.ids16, self.ids16), (dst.dense, self.dense), (dst.labels, self.labels)):
             if a is not None:
                 a.copy_(b, non_blocking=non_blocking)
         return dst
@@ -67,9 +72,30 @@ class PackedColumns(dict):
         super(PackedColumns, self).__init__()
         self.packed = batch
         for i, n in enumerate(batch.cat_names):
-            self[n] = batch.ids[:, i]
+            if batch.ids is not None:
+                self[n] = batch.ids[:, i]
+            else:                       # compact form: widened lazily, only if somebody indexes the column
+                self[n] = _LazyU16Column(batch.ids16, i)
         for i, n in enumerate(batch.num_names):
             self[n] = batch.dense[:, i]
+
+    def __getitem__(self, key):
+        v = dict.__getitem__(self, key)
+        if isinstance(v, _LazyU16Column):
+            v = v.widen()
+            dict.__setitem__(self, key, v)
+        return v
+
+
+class _LazyU16Column(object):
+    """Column i of a compact id block, materialised as int32 on first access (generic, non-fused consumers)."""
+    __slots__ = ("block", "i")
+
+    def __init__(self, block, i):
+        self.block, self.i = block, i
+
+    def widen(self):
+        return self.block[:, self.i].to(torch.int32) & 0xFFFF
 
 
 def _pin(t):
@@ -85,7 +111,9 @@ class PackedDataset(object):
     data: the reference's `[N, n_cols]` float64 array / tensor (columns = features in feature_map order, then the
     labels, as `load_data_array` builds it) or a dict {column: array} as `load_h5` returns it."""
 
-    def __init__(self, feature_map, data, pin=True):
+    def __init__(self, feature_map, data, pin=True, compact="auto"):
+        """compact: store the ids as uint16 (2 B instead of 4 B per id over PCIe) -- "auto": when every categorical
+        vocabulary is below 65 536 (the Criteo config: 26 x 2 B + 13 x 4 B + 4 B = 108 B per sample)."""
         self.feature_map = feature_map
         feats = [(n, s) for n, s in feature_map.features.items() if s["type"] != "meta"]
         for n, s in feats:
@@ -120,33 +148,50 @@ class PackedDataset(object):
         for i, n in enumerate(self.num_names):
             dense[:, i] = col(n)                # == .float()
         lab = np.asarray(col(labels[0]), dtype=np.float32)
-        self.ids = torch.from_numpy(ids)
+        vocabs = [feature_map.features[n].get("vocab_size") for n in self.cat_names]
+        fits = bool(self.cat_names) and all(v is not None and v <= 65536 for v in vocabs)
+        if compact is True and not fits:
+            raise RbxError("PackedDataset(compact=True): a vocabulary is missing or above 65 536")
+        self.compact = fits if compact == "auto" else bool(compact)
+        self.ids = self.ids16 = None
+        if self.compact:
+            self.ids16 = torch.from_numpy(ids.astype(np.uint16).view(np.int16))     # uint16 bit patterns
+        else:
+            self.ids = torch.from_numpy(ids)
         self.dense = torch.from_numpy(dense)
         self.labels = torch.from_numpy(np.ascontiguousarray(lab))
         self.offsets = None
         if pin:
-            self.ids, self.dense, self.labels = _pin(self.ids), _pin(self.dense), _pin(self.labels)
+            self.dense, self.labels = _pin(self.dense), _pin(self.labels)
+            if self.ids is not None:
+                self.ids = _pin(self.ids)
+            if self.ids16 is not None:
+                self.ids16 = _pin(self.ids16)
 
     def __len__(self):
         return self.labels.shape[0]
 
     @property
     def bytes_per_sample(self):
-        return 4 * (len(self.cat_names) + len(self.num_names) + 1)
+        return (2 if self.compact else 4) * len(self.cat_names) + 4 * (len(self.num_names) + 1)
 
     def add_row_offsets(self, offsets):
-        """Turn local ids into fused-table rows once (offsets[f] = first row of feature f's table)."""
+        """Turn local ids into fused-table rows once (offsets[f] = first row of feature f's table).  The compact form
+        keeps local ids (a fused-table row does not fit 16 bits): the layer adds its offsets on the device."""
         if self.offsets is not None:
             raise RbxError("row offsets were already added")
         offsets = [int(o) for o in offsets]
         if len(offsets) != len(self.cat_names):
             raise RbxError("need one offset per categorical feature")
+        if self.compact:
+            return
         self.ids += torch.tensor(offsets, dtype=I32)[None, :]
         self.offsets = offsets
 
     def batch(self, lo, hi):
-        return PackedBatch(self.ids[lo:hi], self.dense[lo:hi], self.labels[lo:hi], self.cat_names, self.num_names,
-                           self.offsets, self.feature_map)
+        return PackedBatch(self.ids[lo:hi] if self.ids is not None else None, self.dense[lo:hi], self.labels[lo:hi],
+                           self.cat_names, self.num_names, self.offsets, self.feature_map,
+                           ids16=self.ids16[lo:hi] if self.ids16 is not None else None)
 
 
 class PackedDataLoader(object):
@@ -186,15 +231,18 @@ class PackedDataLoader(object):
         perm = torch.randperm(N, generator=self._gen)
         if self._ring is None:
             mk = lambda t: _pin(torch.empty((bs,) + tuple(t.shape[1:]), dtype=t.dtype))
-            self._ring = [(mk(ds.ids), mk(ds.dense), mk(ds.labels)) for _ in range(self._ring_n)]
+            ids_src = ds.ids16 if ds.compact else ds.ids
+            self._ring = [(mk(ids_src), mk(ds.dense), mk(ds.labels)) for _ in range(self._ring_n)]
+        ids_src = ds.ids16 if ds.compact else ds.ids
         for k, lo in enumerate(range(0, N, bs)):
             idx = perm[lo:lo + bs]
             n = idx.numel()
             bi, bd, bl = self._ring[k % self._ring_n]
-            torch.index_select(ds.ids, 0, idx, out=bi[:n])
+            torch.index_select(ids_src, 0, idx, out=bi[:n])
             torch.index_select(ds.dense, 0, idx, out=bd[:n])
             torch.index_select(ds.labels, 0, idx, out=bl[:n])
-            yield PackedBatch(bi[:n], bd[:n], bl[:n], ds.cat_names, ds.num_names, ds.offsets, self.feature_map)
+            yield PackedBatch(None if ds.compact else bi[:n], bd[:n], bl[:n], ds.cat_names, ds.num_names, ds.offsets,
+                              self.feature_map, ids16=bi[:n] if ds.compact else None)
 
     def __iter__(self):
         if self.device is None:
@@ -229,7 +277,7 @@ class PackedDataLoader(object):
     def _hand_over(pending, main):
         pb, pev = pending
         main.wait_event(pev)
-        for t in (pb.ids, pb.dense, pb.labels):
+        for t in (pb.ids, pb.ids16, pb.dense, pb.labels):
             if t is not None:
                 t.record_stream(main)
         return pb

@@ -124,6 +124,23 @@ def pack_columns(cols, add=None, as_rows=True, vocab=None, n_bad=None):
     return out
 
 
+def unpack_ids_u16(ids16, field_off):
+    """[B, F] int16 tensor holding uint16 local ids (loader.PackedDataset compact form) -> int32 fused-table rows."""
+    if ids16.dtype != torch.int16 or ids16.dim() != 2:
+        raise RbxError("unpack_ids_u16: ids must be a [B, F] int16 tensor (uint16 bit patterns)")
+    B, F = ids16.shape
+    rows = torch.empty((B, F), dtype=I32, device=ids16.device)
+    offs = (ctypes.c_int64 * max(F, 1))(*field_off) if field_off is not None else None
+    _call("rbx_unpack_ids_u16", _p(ids16, torch.int16, "ids"), B, F, offs, _p(rows), _stream())
+    return rows
+
+
+def zero_(t):
+    """Streaming zero-fill of a contiguous fp32 tensor on the current stream (the fused gradient buffer)."""
+    _call("rbx_zero_f32", _p(t, F32, "t"), t.numel(), _stream())
+    return t
+
+
 # ---------------------------------------------------------------------------------- K1 / K2 / K3
 def embed_fm_fwd(table, table_lr, rows, cat_pos, dense_x, dense_w, dense_w_lr, num_pos, lr_bias,
                  want_E=True, want_S=True, want_fm=True, want_lr=True, B=None, lr_delta=None, num_widx=None, D=None,
@@ -428,30 +445,39 @@ def xs_serve(phys, D, lr_vec, lr_in_row, inbox_ids, meta, cap, rank, world, rowb
 
 
 def xs_consume(rowbuf, rowbuf_lr, tile_base, tile_cnt, pair_sorted, cat_pos, dense_x, dense_w, dense_w_lr, num_pos, lr_bias,
-               B, cap, D, world, want_E=True, want_lr=True, num_widx=None, n_slots=None):
+               B, cap, D, world, want_E=True, want_lr=True, num_widx=None, n_slots=None, out=None):
+    """out: (E | None, S, fm, lr | None) preallocated (contiguous slices of the full batch's outputs), else allocated."""
     F, Fn = len(cat_pos), len(num_pos)
     Ft = n_slots or (F + Fn)
     dev = rowbuf.device
-    E = torch.empty((B, Ft, D), dtype=F32, device=dev) if want_E else None
-    S = torch.empty((B, D), dtype=F32, device=dev)
-    fm = torch.empty((B,), dtype=F32, device=dev)
-    lr = torch.empty((B,), dtype=F32, device=dev) if want_lr else None
+    if out is not None:
+        E, S, fm, lr = out
+    else:
+        E = torch.empty((B, Ft, D), dtype=F32, device=dev) if want_E else None
+        S = torch.empty((B, D), dtype=F32, device=dev)
+        fm = torch.empty((B,), dtype=F32, device=dev)
+        lr = torch.empty((B,), dtype=F32, device=dev) if want_lr else None
     _call("rbx_xs_consume", _p(rowbuf, F32, "rowbuf"), _p(rowbuf_lr, F32, "rowbuf_lr") if want_lr else None,
           _p(tile_base, I32, "tile_base"), _p(tile_cnt, I32, "tile_cnt"), _p(pair_sorted, torch.int16, "pair_sorted"),
           _i32(cat_pos), _p(dense_x, F32, "dense_x"), _p(dense_w, F32, "dense_w"), _p(dense_w_lr, F32, "dense_w_lr"),
           _i32(num_pos), _i32(num_widx) if num_widx is not None else None, _p(lr_bias, F32, "lr_bias"),
-          _p(E), _p(S), _p(fm), _p(lr), B, int(cap), F, Fn, int(D), Ft, world, _stream())
+          _p(E, F32, "E"), _p(S, F32, "S"), _p(fm, F32, "fm"), _p(lr, F32, "lr"), B, int(cap), F, Fn, int(D), Ft, world, _stream())
     return E, S, fm, lr
 
 
 def xs_grad_push(E, rowbuf, S, dE, d_fm, d_lr, rows, pad_row, tile_base, tile_cnt, pair_sorted, cat_pos, cap, D, n_slots,
-                 rank, world, ginbox_ptrs, ginbox_lr_ptrs):
+                 rank, world, ginbox_ptrs, ginbox_lr_ptrs, dense_x=None, dense_w=None, num_pos=(), num_widx=None,
+                 g_dense_w=None, g_dense_w_lr=None, g_lr_bias=None):
     B, F = rows.shape
+    Fn = len(num_pos)
     _call("rbx_xs_grad_push", _p(E, F32, "E"), _p(rowbuf, F32, "rowbuf"), _p(S, F32, "S"), _p(dE, F32, "dE"),
           _p(d_fm, F32, "d_fm"), _p(d_lr, F32, "d_lr"), _p(rows, I32, "rows"),
           _i32(pad_row if pad_row is not None else [-1] * F), _p(tile_base, I32, "tile_base"),
-          _p(tile_cnt, I32, "tile_cnt"), _p(pair_sorted, torch.int16, "pair_sorted"), _i32(cat_pos), B, int(cap), F, int(D),
-          int(n_slots), rank, world, ginbox_ptrs, ginbox_lr_ptrs if d_lr is not None else None, _stream())
+          _p(tile_cnt, I32, "tile_cnt"), _p(pair_sorted, torch.int16, "pair_sorted"), _i32(cat_pos),
+          _p(dense_x, F32, "dense_x"), _p(dense_w, F32, "dense_w"), _i32(num_pos),
+          _i32(num_widx) if num_widx is not None else None, Fn, _p(g_dense_w, F32, "g_dense_w"),
+          _p(g_dense_w_lr, F32, "g_dense_w_lr"), _p(g_lr_bias, F32, "g_lr_bias"), B, int(cap), F, int(D),
+          int(n_slots), rank, world, ginbox_ptrs, ginbox_lr_ptrs, _stream())
 
 
 def xs_apply(ginbox, ginbox_lr, inbox_ids, meta, cap, world, g_phys, D, g_lr_vec, lr_in_row):

@@ -175,7 +175,7 @@ class ShardedEmbeddingFM(object):
     into multi-GB tables, kept for small tables / debugging)."""
 
     def __init__(self, R, D, mode="peer", group=None, device=None, with_lr=True, kern=None, max_ids=None, slack=1.5,
-                 alloc="symm", layout="split"):
+                 alloc="symm", layout="split", chunks=1):
         if mode not in ("peer", "push", "a2a", "stream"):
             raise RbxError("ShardedEmbeddingFM: mode must be 'stream', 'peer', 'push' or 'a2a'")
         if layout not in ("split", "rowlr", "rowpad"):
@@ -186,6 +186,7 @@ class ShardedEmbeddingFM(object):
         if layout == "rowpad" and mode != "stream":
             raise RbxError("layout='rowpad' (physical rows of D + 4 floats) exists in mode='stream' only")
         self.layout = layout
+        self.chunks = max(1, int(chunks)) if mode == "stream" else 1
         self.R, self.D, self.mode, self.group, self.with_lr = int(R), int(D), mode, group, with_lr
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
@@ -278,36 +279,15 @@ class ShardedEmbeddingFM(object):
             self._gflat = flat[cap_rows * RS:]
         self._flat = flat
         self.max_ids = max_ids
-        self.slot_cap = min(max_ids, int(max_ids / W * slack) + 1024) if W > 1 else max_ids
-        cap = self.slot_cap
-        al = lambda n: (n + 3) // 4 * 4
-        sizes = [("flags", 8), ("meta", 16), ("inbox_ids", al(2 * W * cap)), ("rowbuf", al(W * cap * D)),
-                 ("rowbuf_lr", al(W * cap)), ("ginbox", al(W * cap * D)), ("ginbox_lr", al(W * cap))]
-        offs, tot = {}, 0
-        for name, n in sizes:
-            offs[name] = (tot, n)
-            tot += n
-        self._ws = self._shared_block(tot)
-        wsf = self._ws.tensor
-        v = {name: wsf[o:o + n] for name, (o, n) in offs.items()}
-        self._xs_flags = v["flags"].view(I32)
-        self._xs_meta = v["meta"].view(I32).view(2, 8)
-        self._xs_inbox_ids = v["inbox_ids"].view(I32)[:2 * W * cap].view(2, W * cap)
-        self.rowbuf = v["rowbuf"][:W * cap * D]
-        self.rowbuf_lr = v["rowbuf_lr"][:W * cap]
-        self.ginbox = v["ginbox"][:W * cap * D]
-        self.ginbox_lr = v["ginbox_lr"][:W * cap]
-        self._xs_peers = {}
-        for name, (o, n) in offs.items():
-            self._xs_peers[name] = self._peer_views(self._ws, o, n)
-        for par in (0, 1):
-            self._xs_peers[("meta", par)] = self._peer_views(self._ws, offs["meta"][0] + 8 * par, 8)
-            self._xs_peers[("inbox_ids", par)] = self._peer_views(self._ws, offs["inbox_ids"][0] + par * W * cap, W * cap)
-        self._xs_cursor = torch.zeros(8, dtype=I32, device=dev)
-        self._xs_overflow = torch.zeros(1, dtype=I32, device=dev)
-        self._xs_tiles = None
-        self._step = 0
-        self._epoch = 0
+        # `chunks` lanes: the batch is cut into that many sample ranges, each with its own workspace, barrier flags and
+        # CUDA stream, so one range's NVLink-bound phases (serve, grad_push) overlap the other ranges' HBM-bound ones
+        # (route, consume, apply) and the waits at the cross-rank barriers
+        per_lane = (max_ids + self.chunks - 1) // self.chunks + 64 * 32
+        self._lanes = [_StreamLane(self, per_lane, slack) for _ in range(self.chunks)]
+        self.slot_cap = self._lanes[0].cap
+        self.rowbuf = self._lanes[0].rowbuf
+        self._ws = _LaneBlocks(self._lanes)
+        self._lane_streams = None
         self.barrier()
 
     def _peer_views(self, block, off, n):
@@ -315,53 +295,66 @@ class ShardedEmbeddingFM(object):
         device pointers on CUDA; the list of the ranks' (shared-memory) tensors under the CPU stand-in of the tests."""
         if hasattr(block, "peer_tensors"):
             return [t[off:off + n] for t in block.peer_tensors]
-        return (ctypes.c_void_p * self.world)(*[b + off * 4 for b in self._peer_bases_cached(block)])
+        return (ctypes.c_void_p * self.world)(*[b + off * 4 for b in self._peer_bases(block)])
 
-    def _peer_bases_cached(self, block):
-        c = getattr(self, "_bases_cache", None)
-        if c is None or c[0] is not block:
-            self._bases_cache = c = (block, self._peer_bases(block))
-        return c[1]
+    def _mark(self, name):
+        """Phase timing for bench.py / tools (off unless `self.profile` is a list): CUDA events between the phases."""
+        prof = getattr(self, "profile", None)
+        if prof is not None:
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record()
+            prof.append((name, ev))
 
-    def _xs_tile_state(self, B, F):
-        T = self.kern.xs_tile_samples(F, self.D)
-        if T <= 0:
-            raise RbxError("sharded stream mode: F=%d, D=%d is outside what the tile kernels cover" % (F, self.D))
-        n_tiles = (B + T - 1) // T
-        st = self._xs_tiles
-        if st is None or st[0] != (T, F) or st[1].shape[0] < n_tiles:
-            dev = self.device
-            st = ((T, F), torch.zeros((n_tiles, 8), dtype=I32, device=dev), torch.zeros((n_tiles, 8), dtype=I32, device=dev),
-                  torch.zeros((n_tiles * T * F,), dtype=torch.int16, device=dev))
-            self._xs_tiles = st
-        return st
+    @staticmethod
+    def phase_times(prof):
+        """[(name, event)] -> {phase: total ms}; a phase is the span that ENDS at its mark."""
+        out = {}
+        for (_, e0), (n1, e1) in zip(prof[:-1], prof[1:]):
+            if n1 != "begin":
+                out[n1] = out.get(n1, 0.0) + e0.elapsed_time(e1)
+        return out
 
-    def _xs_barrier(self, par=None, with_counts=False):
-        self._epoch += 1
-        self.kern.xs_barrier(self._xs_peers["flags"], self._xs_peers[("meta", par)] if with_counts else None,
-                             self._xs_cursor if with_counts else None, self.rank, self.world, self._epoch, self.device)
+    def _chunk_bounds(self, B):
+        C = min(self.chunks, max(1, B))
+        per = (B + C - 1) // C
+        per = (per + 31) // 32 * 32                      # tile-aligned cuts keep every chunk's tiles whole
+        return [(lo, min(lo + per, B)) for lo in range(0, B, per)]
+
+    def _run_lanes(self, bounds, fn):
+        """fn(lane, lo, hi) for every chunk; on CUDA each lane runs on its own stream, fenced against the caller's."""
+        if len(bounds) == 1 or self.device.type != "cuda" or getattr(self, "profile", None) is not None:
+            for lane, (lo, hi) in zip(self._lanes, bounds):
+                fn(lane, lo, hi)
+            return
+        if self._lane_streams is None:
+            self._lane_streams = [torch.cuda.Stream(device=self.device) for _ in self._lanes]
+        main = torch.cuda.current_stream(self.device)
+        start = torch.cuda.Event()
+        start.record(main)
+        for lane, st, (lo, hi) in zip(self._lanes, self._lane_streams, bounds):
+            st.wait_event(start)
+            with torch.cuda.stream(st):
+                fn(lane, lo, hi)
+        for st in self._lane_streams[:len(bounds)]:
+            main.wait_stream(st)
 
     def _fwd_stream(self, rows, cat_pos, dense_x, dense_w, dense_w_lr, num_pos, lr_bias, want_E, n_slots):
-        k = self.kern
         B, F = rows.shape
         if B * F > self.max_ids:
             raise RbxError("sharded stream: %d ids exceed max_ids=%d" % (B * F, self.max_ids))
-        _, tile_base, tile_cnt, pair_sorted = self._xs_tile_state(B, F)
-        par = self._step & 1
-        self._step += 1
-        cap, W = self.slot_cap, self.world
-        k.xs_route(rows, self.R, self.D, self.rank, W, cap, self._xs_cursor, tile_base, tile_cnt, pair_sorted,
-                   self._xs_overflow, self._xs_peers[("inbox_ids", par)])
-        self._xs_barrier(par, with_counts=True)          # every requester's ids and counts are in my inboxes
-        in_row = self.layout != "split"
-        k.xs_serve(self._tphys, self.D, self.table_lr if (self.with_lr and not in_row) else None, self.with_lr and in_row,
-                   self._xs_inbox_ids[par], self._xs_meta[par], cap, self.rank, W, self._xs_peers["rowbuf"],
-                   self._xs_peers["rowbuf_lr"] if self.with_lr else None)
-        self._xs_barrier()                               # every owner's rows are in my row buffer
-        E, S, fm, lr = k.xs_consume(self.rowbuf, self.rowbuf_lr if self.with_lr else None, tile_base, tile_cnt, pair_sorted,
-                                    cat_pos, dense_x, dense_w, dense_w_lr, num_pos, lr_bias, B, cap, self.D, W,
-                                    want_E=want_E, want_lr=self.with_lr, n_slots=n_slots)
-        self._saved = (par, B, F)
+        Ft = n_slots or (F + len(num_pos))
+        dev, D = rows.device, self.D
+        E = torch.empty((B, Ft, D), dtype=F32, device=dev) if want_E else None
+        S = torch.empty((B, D), dtype=F32, device=dev)
+        fm = torch.empty((B,), dtype=F32, device=dev)
+        lr = torch.empty((B,), dtype=F32, device=dev) if self.with_lr else None
+        bounds = self._chunk_bounds(B)
+
+        def one(lane, lo, hi):
+            lane.forward(rows[lo:hi], cat_pos, dense_x[lo:hi] if dense_x is not None else None, dense_w, dense_w_lr, num_pos,
+                         lr_bias, Ft, (E[lo:hi] if E is not None else None, S[lo:hi], fm[lo:hi], lr[lo:hi] if lr is not None else None))
+        self._run_lanes(bounds, one)
+        self._saved = (bounds, B, F)
         self._bwd_pending = False
         return E, S, fm, lr
 
@@ -369,30 +362,18 @@ class ShardedEmbeddingFM(object):
                     g_dense_w, g_dense_w_lr, g_lr_bias, n_slots):
         if self._saved is None:
             raise RbxError("ShardedEmbeddingFM.backward (stream) needs the forward of the same batch first")
-        k = self.kern
-        par, B, F = self._saved
+        bounds, B, F = self._saved
         if tuple(rows.shape) != (B, F):
             raise RbxError("ShardedEmbeddingFM.backward (stream): rows differ in shape from the forward's")
-        _, tile_base, tile_cnt, pair_sorted = self._xs_tiles
-        cap, W = self.slot_cap, self.world
-        use_lr = self.with_lr and d_lr is not None
         Ft = n_slots or (F + len(num_pos))
-        if getattr(self, "_bwd_pending", False):
-            self._xs_barrier()       # a second backward on the same forward: the owners may still be reading the last one's inbox
-        self._bwd_pending = True
-        k.xs_grad_push(E, self.rowbuf, S, dE, d_fm, d_lr if use_lr else None, rows, pad_rows, tile_base, tile_cnt,
-                       pair_sorted, cat_pos, cap, self.D, Ft, self.rank, W, self._xs_peers["ginbox"],
-                       self._xs_peers["ginbox_lr"] if use_lr else None)
-        if not len(num_pos) and g_lr_bias is not None and d_lr is not None:
-            g_lr_bias.add_(d_lr.sum())                   # no numeric slot: the bias gradient is all that is left
-        elif len(num_pos):
-            # numeric slots / bias: batch reductions with no exchange (the F = 0 form of the fused backward)
-            k.embed_fm_bwd(None, None, [], None, dense_x, dense_w, num_pos, None, S, dE, d_fm, d_lr, None, None,
-                           g_dense_w, g_dense_w_lr, g_lr_bias, self.D, self.R, B=B, n_slots=Ft)
-        self._xs_barrier()                               # every requester's gradients are in my inbox
-        in_row = self.layout != "split"
-        k.xs_apply(self.ginbox, self.ginbox_lr if use_lr else None, self._xs_inbox_ids[par], self._xs_meta[par], cap, W,
-                   self._gphys, self.D, self.g_table_lr if (use_lr and not in_row) else None, use_lr and in_row)
+        again, self._bwd_pending = self._bwd_pending, True
+        cut = lambda t, lo, hi: None if t is None else t[lo:hi]
+
+        def one(lane, lo, hi):
+            lane.backward(rows[lo:hi], cat_pos, pad_rows, cut(dense_x, lo, hi), dense_w, num_pos, cut(E, lo, hi), S[lo:hi],
+                          cut(dE, lo, hi), cut(d_fm, lo, hi), cut(d_lr, lo, hi), g_dense_w, g_dense_w_lr, g_lr_bias, Ft, again)
+        self._run_lanes(bounds, one)
+
 
     # -- push-mode workspace: inboxes every peer can write ---------------------------------------------
     def _init_push(self, max_ids, slack):
@@ -428,7 +409,7 @@ class ShardedEmbeddingFM(object):
         """Host check (synchronises): did any (owner, requester) bucket exceed its slot capacity?"""
         if self.mode == "push" and int(self.inbox_meta.view(self.world, 4)[:, 2].max()) != 0:
             raise RbxError("sharded push: an id bucket exceeded the slot capacity %d; raise `slack`" % self.slot_cap)
-        if self.mode == "stream" and int(self._xs_overflow.item()) != 0:
+        if self.mode == "stream" and any(int(lane.overflow.item()) != 0 for lane in self._lanes):
             raise RbxError("sharded stream: an id lane exceeded the slot capacity %d; raise `slack`" % self.slot_cap)
 
     # -- peer mapping ------------------------------------------------------------------------------
@@ -470,7 +451,7 @@ class ShardedEmbeddingFM(object):
         if self._ws is not None:
             self.barrier()
             self.inbox_ids = self.inbox_meta = self.rowbuf = self.rowbuf_lr = self.ginbox = self.ginbox_lr = None
-            self._xs_flags = self._xs_meta = self._xs_inbox_ids = self._xs_peers = self._bases_cache = None
+            self._lanes = None
             self._ws.free()
             self._ws = None
         if self._block is not None:
@@ -683,3 +664,134 @@ class ShardedEmbeddingFM(object):
             idx = torch.tensor(mine, dtype=torch.long, device=dev)
             self.g_table.index_fill_(0, idx, 0.0)
             self.g_table_lr.index_fill_(0, idx, 0.0)
+
+
+class _LaneBlocks(object):
+    """The lanes' peer-visible workspaces behind the one `free()` ShardedEmbeddingFM.close() calls."""
+
+    def __init__(self, lanes):
+        self.lanes = lanes
+
+    def free(self):
+        for lane in self.lanes:
+            lane.free()
+
+
+class _StreamLane(object):
+    """One sample range of the streamed exchange: workspace (flags, count / id inboxes double-buffered by step parity,
+    row buffer, gradient inbox -- one peer-visible block), slot bookkeeping and the phase sequence."""
+
+    def __init__(self, owner, max_ids, slack):
+        self.o = owner
+        W, D, dev = owner.world, owner.D, owner.device
+        self.max_ids = max_ids
+        self.cap = cap = min(max_ids, int(max_ids / W * slack) + 1024) if W > 1 else max_ids
+        al = lambda n: (n + 3) // 4 * 4
+        sizes = [("flags", 8), ("meta", 16), ("inbox_ids", al(2 * W * cap)), ("rowbuf", al(W * cap * D)),
+                 ("rowbuf_lr", al(W * cap)), ("ginbox", al(W * cap * D)), ("ginbox_lr", al(W * cap))]
+        offs, tot = {}, 0
+        for name, n in sizes:
+            offs[name] = (tot, n)
+            tot += n
+        self.block = owner._shared_block(tot)
+        wsf = self.block.tensor
+        v = {name: wsf[o:o + n] for name, (o, n) in offs.items()}
+        self.meta = v["meta"].view(I32).view(2, 8)
+        self.inbox_ids = v["inbox_ids"].view(I32)[:2 * W * cap].view(2, W * cap)
+        self.rowbuf = v["rowbuf"][:W * cap * D]
+        self.rowbuf_lr = v["rowbuf_lr"][:W * cap]
+        self.ginbox = v["ginbox"][:W * cap * D]
+        self.ginbox_lr = v["ginbox_lr"][:W * cap]
+        self.peers = {name: owner._peer_views(self.block, o, n) for name, (o, n) in offs.items()}
+        for par in (0, 1):
+            self.peers[("meta", par)] = owner._peer_views(self.block, offs["meta"][0] + 8 * par, 8)
+            self.peers[("inbox_ids", par)] = owner._peer_views(self.block, offs["inbox_ids"][0] + par * W * cap, W * cap)
+        self.cursor = torch.zeros(8, dtype=I32, device=dev)
+        self.overflow = torch.zeros(1, dtype=I32, device=dev)
+        self.tiles = None
+        self.step = self.epoch = 0
+        self.saved = None
+
+    def free(self):
+        self.meta = self.inbox_ids = self.rowbuf = self.rowbuf_lr = self.ginbox = self.ginbox_lr = self.peers = None
+        self.block.free()
+
+    def tile_state(self, B, F):
+        o = self.o
+        T = o.kern.xs_tile_samples(F, o.D)
+        if T <= 0:
+            raise RbxError("sharded stream mode: F=%d, D=%d is outside what the tile kernels cover" % (F, o.D))
+        n_tiles = (B + T - 1) // T
+        st = self.tiles
+        if st is None or st[0] != (T, F) or st[1].shape[0] < n_tiles:
+            dev = o.device
+            st = ((T, F), torch.zeros((n_tiles, 8), dtype=I32, device=dev), torch.zeros((n_tiles, 8), dtype=I32, device=dev),
+                  torch.zeros((n_tiles * T * F,), dtype=torch.int16, device=dev))
+            self.tiles = st
+        return st
+
+    def barrier(self, par=None, with_counts=False):
+        o = self.o
+        self.epoch += 1
+        o.kern.xs_barrier(self.peers["flags"], self.peers[("meta", par)] if with_counts else None,
+                          self.cursor if with_counts else None, o.rank, o.world, self.epoch, o.device)
+
+    def forward(self, rows, cat_pos, dense_x, dense_w, dense_w_lr, num_pos, lr_bias, Ft, out):
+        o, k = self.o, self.o.kern
+        B, F = rows.shape
+        if B * F > self.max_ids:
+            raise RbxError("sharded stream: a chunk of %d ids exceeds its lane's %d" % (B * F, self.max_ids))
+        _, tile_base, tile_cnt, pair_sorted = self.tile_state(B, F)
+        par = self.step & 1
+        self.step += 1
+        cap, W = self.cap, o.world
+        o._mark("begin")
+        k.xs_route(rows, o.R, o.D, o.rank, W, cap, self.cursor, tile_base, tile_cnt, pair_sorted, self.overflow,
+                   self.peers[("inbox_ids", par)])
+        o._mark("route")
+        self.barrier(par, with_counts=True)              # every requester's ids and counts are in my inboxes
+        o._mark("barrier_ids")
+        in_row = o.layout != "split"
+        k.xs_serve(o._tphys, o.D, o.table_lr if (o.with_lr and not in_row) else None, o.with_lr and in_row,
+                   self.inbox_ids[par], self.meta[par], cap, o.rank, W, self.peers["rowbuf"],
+                   self.peers["rowbuf_lr"] if o.with_lr else None)
+        o._mark("serve")
+        self.barrier()                                   # every owner's rows are in my row buffer
+        o._mark("barrier_rows")
+        k.xs_consume(self.rowbuf, self.rowbuf_lr if o.with_lr else None, tile_base, tile_cnt, pair_sorted,
+                     cat_pos, dense_x, dense_w, dense_w_lr, num_pos, lr_bias, B, cap, o.D, W,
+                     want_E=out[0] is not None, want_lr=o.with_lr, n_slots=Ft, out=out)
+        o._mark("consume")
+        self.saved = (par, B, F)
+
+    def backward(self, rows, cat_pos, pad_rows, dense_x, dense_w, num_pos, E, S, dE, d_fm, d_lr,
+                 g_dense_w, g_dense_w_lr, g_lr_bias, Ft, again):
+        o, k = self.o, self.o.kern
+        par, B, F = self.saved
+        if tuple(rows.shape) != (B, F):
+            raise RbxError("ShardedEmbeddingFM.backward (stream): chunk shapes differ from the forward's")
+        _, tile_base, tile_cnt, pair_sorted = self.tiles
+        cap, W = self.cap, o.world
+        use_lr = o.with_lr and d_lr is not None
+        if again:
+            self.barrier()       # a second backward on the same forward: the owners may still be reading the last one's inbox
+        o._mark("begin")
+        # numeric slots / bias are batch reductions with no exchange: they ride in the same launch when they fit
+        fuse_num = len(num_pos) * (o.D // 4) <= 256 and len(num_pos) <= 64
+        k.xs_grad_push(E, self.rowbuf, S, dE, d_fm, d_lr, rows, pad_rows, tile_base, tile_cnt,
+                       pair_sorted, cat_pos, cap, o.D, Ft, o.rank, W, self.peers["ginbox"],
+                       self.peers["ginbox_lr"] if use_lr else None,
+                       dense_x=dense_x if fuse_num else None, dense_w=dense_w if fuse_num else None,
+                       num_pos=num_pos if fuse_num else (), g_dense_w=g_dense_w if fuse_num else None,
+                       g_dense_w_lr=g_dense_w_lr if fuse_num else None, g_lr_bias=g_lr_bias if fuse_num else None)
+        o._mark("grad_push")
+        if not fuse_num:         # (the F = 0 form of the fused backward)
+            k.embed_fm_bwd(None, None, [], None, dense_x, dense_w, num_pos, None, S, dE, d_fm, d_lr, None, None,
+                           g_dense_w, g_dense_w_lr, g_lr_bias, o.D, o.R, B=B, n_slots=Ft)
+        o._mark("numeric_slots")
+        self.barrier()                                   # every requester's gradients are in my inbox
+        o._mark("barrier_grads")
+        in_row = o.layout != "split"
+        k.xs_apply(self.ginbox, self.ginbox_lr if use_lr else None, self.inbox_ids[par], self.meta[par], cap, W,
+                   o._gphys, o.D, o.g_table_lr if (use_lr and not in_row) else None, use_lr and in_row)
+        o._mark("apply")

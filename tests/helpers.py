@@ -267,7 +267,7 @@ class CpuKern:
 
     @staticmethod
     def xs_consume(rowbuf, rowbuf_lr, tile_base, tile_cnt, pair_sorted, cat_pos, dense_x, dense_w, dense_w_lr, num_pos,
-                   lr_bias, B, cap, D, world, want_E=True, want_lr=True, num_widx=None, n_slots=None):
+                   lr_bias, B, cap, D, world, want_E=True, want_lr=True, num_widx=None, n_slots=None, out=None):
         F, Fn = len(cat_pos), len(num_pos)
         E = torch.zeros(B, n_slots or (F + Fn), D)
         lr = torch.zeros(B)
@@ -285,12 +285,20 @@ class CpuKern:
             lr = lr + lr_bias
         S = E.sum(1)
         fm = oracle.inner_product_interaction(E, "product_sum").reshape(-1)
+        if out is not None:
+            for dst, src in zip(out, (E, S, fm, lr)):
+                if dst is not None:
+                    dst.copy_(src)
+            return out
         return (E if want_E else None), S, fm, (lr if want_lr else None)
 
     @staticmethod
     def xs_grad_push(E, rowbuf, S, dE, d_fm, d_lr, rows, pad_row, tile_base, tile_cnt, pair_sorted, cat_pos, cap, D,
-                     n_slots, rank, world, ginbox_peers, ginbox_lr_peers):
+                     n_slots, rank, world, ginbox_peers, ginbox_lr_peers, dense_x=None, dense_w=None, num_pos=(),
+                     num_widx=None, g_dense_w=None, g_dense_w_lr=None, g_lr_bias=None):
         B, F = rows.shape
+        CpuKern.embed_fm_bwd(None, None, [], None, dense_x, dense_w, num_pos, None, S, dE, d_fm, d_lr, None, None,
+                             g_dense_w, g_dense_w_lr, g_lr_bias, D, 0)
         rb = rowbuf.view(-1, D)
         for b, f, o, slot in CpuKern._pairs(tile_base, tile_cnt, pair_sorted, B, F, world):
             if slot >= cap:

@@ -6,6 +6,7 @@ import pytest
 import torch
 
 from helpers import Problem, assert_close, oracle
+from recbox_b200 import RbxError
 
 pytestmark = pytest.mark.gpu
 
@@ -392,3 +393,74 @@ def test_errors_are_loud():
         ops.gather_rows(torch.zeros(4, 4), torch.zeros(2, dtype=torch.int32))       # CPU tensors
     with pytest.raises(RbxError):
         ops.interact_fwd(torch.zeros(2, 3, 4, device=DEV), 7)                        # unknown mode
+
+
+# ------------------------------------------------------------------------------ a1: range guard, compact ids, zero fill
+def test_out_of_vocabulary_ids_never_alias_a_neighbour_table():
+    """nn.Embedding raises IndexError for an id outside [0, vocab); in the fused table id + field offset would silently read
+    (and scatter into) ANOTHER feature's rows.  With the vocabulary sizes given, such ids become row -1 (zero row, no
+    gradient) and are counted."""
+    ops = _ops()
+    B = 257
+    rng = np.random.default_rng(3)
+    vocab, off = [10, 20, 5], [0, 10, 30]
+    M = np.stack([rng.integers(0, v, B) for v in vocab] + [rng.standard_normal(B)], 1).astype(np.float64)
+    M[5, 0], M[6, 1], M[7, 2], M[8, 1] = 10, -1, 5, 1e6
+    n_bad = torch.zeros(1, dtype=torch.int32, device=DEV)
+    rows, dense, _ = ops.split_batch(torch.from_numpy(M).to(DEV), [1, 1, 1, 2], [0, 1, 2, 0], off, 3, 1, want_label=False,
+                                     field_rows=vocab, n_bad=n_bad)
+    want = M[:, :3].astype(np.int64) + np.asarray(off)[None]
+    want[5, 0] = want[6, 1] = want[7, 2] = want[8, 1] = -1
+    assert np.array_equal(rows.cpu().numpy(), want) and int(n_bad) == 4
+    unchecked, _, _ = ops.split_batch(torch.from_numpy(M).to(DEV), [1, 1, 1, 2], [0, 1, 2, 0], off, 3, 1, want_label=False)
+    assert int(unchecked[5, 0]) == 10                               # (the documented unchecked behaviour)
+    n_bad.zero_()
+    Md = torch.from_numpy(M).to(DEV)
+    packed = ops.pack_columns([Md[:, 0], Md[:, 1].long().contiguous(), Md[:, 2].int().contiguous()], add=off, as_rows=True,
+                              vocab=vocab, n_bad=n_bad)
+    assert np.array_equal(packed.cpu().numpy(), want) and int(n_bad) == 4
+
+
+@pytest.mark.parametrize("B,F", [(1, 1), (7, 3), (1000, 26), (65536, 26), (333, 5)])
+def test_unpack_ids_u16(B, F):
+    ops = _ops()
+    rng = np.random.default_rng(B + F)
+    ids = rng.integers(0, 65536, (B, F)).astype(np.uint16)
+    off = (np.arange(F) * 65536).tolist()
+    t = torch.from_numpy(ids.view(np.int16)).to(DEV)
+    rows = ops.unpack_ids_u16(t, off)
+    assert np.array_equal(rows.cpu().numpy(), ids.astype(np.int64) + np.asarray(off)[None])
+    if B > 2:                                                        # a view that is not 16-byte aligned
+        rows2 = ops.unpack_ids_u16(t[1:].contiguous()[:], off)
+        assert np.array_equal(rows2.cpu().numpy(), (ids.astype(np.int64) + np.asarray(off)[None])[1:])
+
+
+@pytest.mark.parametrize("n,skew", [(1, 0), (5, 1), (1025, 3), (17000003, 2)])
+def test_zero_fill(n, skew):
+    ops = _ops()
+    buf = torch.full((n + skew + 8,), 7.0, device=DEV)
+    ops.zero_(buf[skew:skew + n])
+    assert float(buf[skew:skew + n].abs().sum()) == 0.0
+    assert float(buf[:skew].sum()) == 7.0 * skew and float(buf[skew + n:].sum()) == 7.0 * 8
+
+
+def test_ops_run_on_the_tensors_device_not_the_current_one():
+    """The reference's get_device(gpu) hands out cuda:<gpu> without set_device (torch_utils.py:37-42): tensors off the
+    current device are normal.  Needs two GPUs; on one it checks the mixed-device error only."""
+    ops = _ops()
+    pb = Problem(300, "ccn", 16, vocab=50, seed=2)
+    with pytest.raises(RbxError):
+        ops.zero_(torch.zeros(4))                                    # CPU tensor: no CPU path
+    if torch.cuda.device_count() < 2:
+        return
+    f1 = pb.fused("cuda:1")
+    assert torch.cuda.current_device() == 0
+    E1, S1, fm1, lr1 = ops.embed_fm_fwd(f1["table"], f1["table_lr"], f1["rows"], pb.cat_pos, f1["dense_x"], f1["dense_w"],
+                                        f1["dense_w_lr"], pb.num_pos, f1["bias"])
+    f0 = pb.fused("cuda:0")
+    E0, S0, fm0, lr0 = ops.embed_fm_fwd(f0["table"], f0["table_lr"], f0["rows"], pb.cat_pos, f0["dense_x"], f0["dense_w"],
+                                        f0["dense_w_lr"], pb.num_pos, f0["bias"])
+    assert E1.device.index == 1 and torch.equal(E1.cpu(), E0.cpu()) and torch.equal(fm1.cpu(), fm0.cpu())
+    with pytest.raises(RbxError):
+        ops.embed_fm_fwd(f1["table"], f1["table_lr"], f0["rows"], pb.cat_pos, f1["dense_x"], f1["dense_w"],
+                         f1["dense_w_lr"], pb.num_pos, f1["bias"])

@@ -181,3 +181,61 @@ def test_interaction_machine_parameter_names_match_reference():
             m(torch.zeros(2, 3, 8))
     with pytest.raises(AssertionError):
         layers.InteractionMachine(8, order=6)
+
+
+def test_embdict_drops_its_cached_stack_when_mutated():
+    """dict2tensor stacks the CURRENT dict values (feature_embedding.py:169-186): a model that replaces an entry after the
+    fused forward (DIN-style `feature_emb_dict[seq_field] = pooled`) must not get the stale cached [B,F,D] back."""
+    E = torch.arange(24, dtype=torch.float32).view(2, 3, 4)
+    d = layers._EmbDict()
+    d.names = ("a", "b", "c")
+    for i, n in enumerate(d.names):
+        d[n] = E[:, i, :]
+    d.stacked = E                                   # what the fused forward does last
+    assert d.stacked is E
+    d["b"] = torch.zeros(2, 4)                      # replace an entry -> cache dropped
+    assert d.stacked is None
+    d2 = layers._EmbDict()
+    d2.names = ("a", "b")
+    d2["a"], d2["b"] = E[:, 0, :], E[:, 1, :]
+    d2.stacked = E
+    d2.pop("a")
+    assert d2.stacked is None
+    d3 = layers._EmbDict()
+    d3["a"] = E[:, 0, :]
+    d3.stacked = E
+    E[:, 0, :] += 1                                 # in-place write through a view bumps the version -> cache dropped
+    assert d3.stacked is None
+    st = layers._Stash()
+    E2 = torch.zeros(2, 3, 4)
+    st.version = E2._version
+    E2._rbx_stash = st
+    assert layers._stash_of(E2) is st
+    E2.mul_(2)
+    assert layers._stash_of(E2) is None             # the launch's by-products no longer describe E
+
+
+def test_refused_store_invalidates_cached_plans_and_survives_pickle():
+    import copy
+    import pickle
+    fm = feature_map("ranking_layers_d8", 8)
+    emb = layers.FeatureEmbedding(fm, 8)
+    d = emb.embedding_layer
+    key, names = d._select([], [])
+    plan = d._plan(key, names)
+    assert d._calls and plan["call"] is not None
+    old_param = d.embedding_layers[names[-1]].weight
+    d.embedding_layers[names[-1]].weight = nn.Parameter(torch.ones_like(old_param))      # pretrained weights loaded late
+    d._sync_store()
+    assert not d._calls, "plans made before the re-fusion hold the orphaned Parameter"
+    call, _ = d._plan(key, names)["call"]
+    assert all(p is not old_param for p in call.params)
+    assert any(p is d.embedding_layers[names[-1]].weight for p in call.params)
+    # pickling rebuilds the store (its offsets are keyed by id(module))
+    emb2 = pickle.loads(pickle.dumps(emb))
+    d2 = emb2.embedding_layer
+    for n in names:
+        assert torch.equal(d2.embedding_layers[n].weight, d.embedding_layers[n].weight)
+    g = next(iter(d2._store.groups.values()))
+    assert all(id(m) in g.emb_off for m in g.emb)
+    assert copy.deepcopy(emb).state_dict().keys() == emb.state_dict().keys()

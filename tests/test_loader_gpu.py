@@ -34,9 +34,10 @@ def _run(emb, fml, X, wE, wy):
     return E.detach().clone(), y.detach().clone(), grads
 
 
+@pytest.mark.parametrize("compact", [False, "auto"])
 @pytest.mark.parametrize("bind", [False, True])
 @pytest.mark.parametrize("tag,D", [("ranking_layers_d8", 8), ("ranking_layers_d10", 10)])
-def test_packed_batch_equals_float64_batch(tag, D, bind):
+def test_packed_batch_equals_float64_batch(tag, D, bind, compact):
     g = load(tag)
     fm = feature_map(tag, D)
     emb = layers.FeatureEmbedding(fm, D)
@@ -49,7 +50,8 @@ def test_packed_batch_equals_float64_batch(tag, D, bind):
     wE, wy = g["wE"].to(DEV), g["wy"].to(DEV)
     ref = _run(emb, fml, layers.get_inputs(model, g["batch"]), wE, wy)
     assert torch.equal(ref[0].cpu(), g["E"])
-    dl = PackedDataLoader(fm, g["batch"], batch_size=len(g["batch"]))
+    dl = PackedDataLoader(fm, PackedDataset(fm, g["batch"], compact=compact), batch_size=len(g["batch"]))
+    assert dl.dataset.compact == (compact == "auto")         # every vocabulary of the golden config is below 65 536
     if bind:
         dl.bind(emb)
     (pb,) = list(dl)
@@ -64,22 +66,25 @@ def test_packed_batch_equals_float64_batch(tag, D, bind):
     assert torch.equal(layers.get_labels(model, g["batch"]).cpu(), g["batch"][:, -1].float().view(-1, 1))
 
 
-def test_device_prefetch_epoch_shuffled():
+@pytest.mark.parametrize("compact", [False, "auto"])
+def test_device_prefetch_epoch_shuffled(compact):
     fm = feature_map("ranking_layers_d8", 8)
     arr = _data(5000, fm, 5)
     arr[:, -1] = np.arange(5000)
-    dl = PackedDataLoader(fm, arr, batch_size=512, shuffle=True, seed=1, device=DEV)
+    dl = PackedDataLoader(fm, PackedDataset(fm, arr, compact=compact), batch_size=512, shuffle=True, seed=1, device=DEV)
     ds = dl.dataset
     labs = []
     for b in dl:
-        assert b.ids.is_cuda and b.dense.is_cuda and b.labels.is_cuda
+        got, want = (b.ids16, ds.ids16) if ds.compact else (b.ids, ds.ids)
+        assert got.is_cuda and b.dense.is_cuda and b.labels.is_cuda
         lab = b.labels.long().cpu()
-        assert torch.equal(b.ids.cpu(), ds.ids[lab]) and torch.equal(b.dense.cpu(), ds.dense[lab])
+        assert torch.equal(got.cpu(), want[lab]) and torch.equal(b.dense.cpu(), ds.dense[lab])
         labs.append(lab)
     assert sorted(torch.cat(labs).tolist()) == list(range(5000))
 
 
-def test_feature_source_subset_with_bound_offsets():
+@pytest.mark.parametrize("compact", [False, "auto"])
+def test_feature_source_subset_with_bound_offsets(compact):
     """A bound loader's ids carry the main layer's row offsets; a layer that selects a subset of the features (or
     the D=1 LR table with other offsets) must still read the right rows."""
     g = load("ranking_layers_d8")
@@ -91,7 +96,7 @@ def test_feature_source_subset_with_bound_offsets():
     emb.to(DEV)
     fml.to(DEV)
     model = _M(fm)
-    (pb,) = list(PackedDataLoader(fm, g["batch"], batch_size=len(g["batch"])).bind(emb))
+    (pb,) = list(PackedDataLoader(fm, PackedDataset(fm, g["batch"], compact=compact), batch_size=len(g["batch"])).bind(emb))
     X = layers.get_inputs(model, pb)
     assert_close(fml.lr_layer(X), g["lr_out"], what="lr_out (own offsets)")
     sub = emb(X, feature_type="categorical")

@@ -34,7 +34,7 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, out_dir, mode="a2a", layout="split"):
+def _worker(rank, world, port, out_dir, mode="a2a", layout="split", chunks=1):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
@@ -47,7 +47,7 @@ def _worker(rank, world, port, out_dir, mode="a2a", layout="split"):
         d_lr = torch.randn(B * world, generator=g)
         sl = slice(rank * B, (rank + 1) * B)
         sh = sharded.ShardedEmbeddingFM(pb.R, D, mode=mode, device="cpu", kern=CpuKern, max_ids=B * pb.F, slack=3.0,
-                                        layout=layout)
+                                        layout=layout, chunks=chunks)
         assert sh.world == world and sh.rank == rank
         sh.load_global(f["table"], f["table_lr"])
         gw, gw1, gb = torch.zeros_like(f["dense_w"]), torch.zeros_like(f["dense_w_lr"]), torch.zeros(1)
@@ -89,10 +89,10 @@ def test_a2a_orchestration_world2_gloo(world, tmp_path):
     assert all(os.path.exists(os.path.join(str(tmp_path), "ok%d" % r)) for r in range(world))
 
 
-@pytest.mark.parametrize("layout", ["split", "rowlr", "rowpad"])
-def test_stream_orchestration_world2_gloo(layout, tmp_path):
+@pytest.mark.parametrize("layout,chunks", [("split", 1), ("rowlr", 1), ("rowpad", 1), ("split", 2)])
+def test_stream_orchestration_world2_gloo(layout, chunks, tmp_path):
     """mode="stream": slot bookkeeping, parity-double-buffered inboxes, barrier epochs and the three shard layouts, with the
     CPU stand-ins writing into the peers' (file-backed) blocks exactly where the kernels write over NVLink."""
     world = 2
-    mp.spawn(_worker, args=(world, _free_port(), str(tmp_path), "stream", layout), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, _free_port(), str(tmp_path), "stream", layout, chunks), nprocs=world, join=True)
     assert all(os.path.exists(os.path.join(str(tmp_path), "ok%d" % r)) for r in range(world))

@@ -42,9 +42,10 @@ def _worker(rank, world, port, mode, D, out_dir):
         sl = slice(rank * B, (rank + 1) * B)
         rows, dx = f["rows"][sl].contiguous(), f["dense_x"][sl].contiguous()
 
-        layout = mode.split("_")[1] if "_" in mode else "split"
-        mode = mode.split("_")[0]
-        sh = sharded.ShardedEmbeddingFM(pb.R, D, mode=mode, device=dev, max_ids=B * pb.F, slack=3.0, layout=layout)
+        parts = mode.split("_")                     # mode[_layout[_chunks]]
+        mode, layout, chunks = parts[0], (parts[1] if len(parts) > 1 else "split"), (int(parts[2]) if len(parts) > 2 else 1)
+        sh = sharded.ShardedEmbeddingFM(pb.R, D, mode=mode, device=dev, max_ids=B * pb.F, slack=3.0, layout=layout,
+                                        chunks=chunks)
         sh.load_global(f["table"], f["table_lr"])
         E, S, fm, lr = sh.forward(rows, pb.cat_pos, dx, f["dense_w"], f["dense_w_lr"], pb.num_pos, f["bias"])
         if mode == "stream":       # a second forward lands in the other parity buffers and must agree bit for bit
@@ -123,6 +124,15 @@ def test_sharded_stream_layouts_match_single_table(layout, D, tmp_path):
     """Streamed exchange with the row + first-order weight in one physical row (2 D or D + 4 floats)."""
     world = _world()
     mp.spawn(_worker, args=(world, _free_port(), "stream_" + layout, D, str(tmp_path)), nprocs=world, join=True)
+    assert all(os.path.exists(os.path.join(str(tmp_path), "ok%d" % r)) for r in range(world))
+
+
+@pytest.mark.parametrize("chunks", [2, 3])
+def test_sharded_stream_chunk_lanes_match_single_table(chunks, tmp_path):
+    """The batch cut into sample ranges that run the exchange on their own streams / workspaces (overlap of the
+    NVLink-bound and the HBM-bound phases) gives the same result as one range."""
+    world = _world()
+    mp.spawn(_worker, args=(world, _free_port(), "stream_rowlr_%d" % chunks, 16, str(tmp_path)), nprocs=world, join=True)
     assert all(os.path.exists(os.path.join(str(tmp_path), "ok%d" % r)) for r in range(world))
 
 

@@ -20,5 +20,7 @@ case "$1" in
     shift; MODE=$1; LAYOUT=$2; shift 2
     if [ "$N" -gt 1 ]; then $TR bench.py --gpus $N --workload sharded --shard-mode $MODE --shard-layout $LAYOUT --steps 30 --warmup 5 "$@"
     else python bench.py --workload sharded --shard-mode $MODE --shard-layout $LAYOUT --steps 30 --warmup 5 "$@"; fi 2>&1 | tail -2 | tee -a $OUT/${TAG}_sharded.jsonl ;;
+  nvlink)       # all-to-all write bandwidth microbenchmark
+    shift; $TR tools/nvlink_microbench.py "$@" 2>&1 | tail -2 | tee -a $OUT/${TAG}_nvlink.jsonl ;;
   *) echo "unknown target $1"; exit 2 ;;
 esac
