@@ -131,8 +131,64 @@ class ClockSampler(threading.Thread):
 
 
 # ------------------------------------------------------------------------------------------------
-# reference arm / cpu_baseline: the oracle's restatement of the same step, on the host cores
+# reference arm / cpu_baseline: the reference's OWN modules (baseline/_ref, copied unmodified by baseline/fetch_ref.py)
+# on the host cores; the oracle's restatement (kind "port") only when that copy is absent
 # ------------------------------------------------------------------------------------------------
+REF_DIR = os.path.join(ROOT, "baseline", "_ref")
+
+
+def criteo_feature_map(cls, name="bench_criteo"):
+    """FeatureMap of BASELINE configs[1]: I1..I13 numeric, C1..C26 categorical (38 462 rows each, padding_idx 0), built the
+    way SURVEY.md Appendix A drives the reference's FeatureMap by hand; `cls` is the reference's class or ours."""
+    fm = cls(name, ROOT)
+    for n in range(CFG["Fn"]):
+        fm.features["I%d" % (n + 1)] = {"source": "", "type": "numeric"}
+    for f in range(CFG["F"]):
+        fm.features["C%d" % (f + 1)] = {"source": "", "type": "categorical", "vocab_size": CFG["V"], "padding_idx": 0}
+    fm.labels = ["label"]
+    fm.num_fields = fm.get_num_fields()
+    fm.set_column_index()
+    fm.default_emb_dim = CFG["D"]
+    return fm
+
+
+def host_batch_matrix(B, ids_kind, seed, g):
+    """The reference loader's batch: one float64 [B, 40] matrix, features in FeatureMap order then the label
+    (h5_dataloader.py:36-47)."""
+    ids = make_ids(B, CFG["F"], CFG["V"], ids_kind, seed)
+    dx = torch.rand(B, CFG["Fn"], generator=g, dtype=torch.float64)
+    lab = (torch.rand(B, 1, generator=g) < 0.5).double()
+    return torch.cat([dx, torch.from_numpy(ids).double(), lab], 1).contiguous()
+
+
+def ref_step_factory(B, ids_kind, seed):
+    """One pass of the hot path through the reference's FeatureEmbedding + FactorizationMachine (unmodified source under
+    baseline/_ref): forward E and the FM logit, backward with the same upstream gradients the B200 arm uses."""
+    os.environ["RECBOX_REFERENCE"] = REF_DIR
+    from oracle import ref_shim                      # import aliases only (fuxictr.* -> recbox.ranking.*, stub h5py / faiss)
+    L = ref_shim.install()
+    from recbox.ranking.features import FeatureMap as RefFeatureMap
+    fm = criteo_feature_map(RefFeatureMap)
+    torch.manual_seed(seed)
+    emb, fml = L.FeatureEmbedding(fm, CFG["D"]), L.FactorizationMachine(fm)
+    g = torch.Generator().manual_seed(seed)
+    M = host_batch_matrix(B, ids_kind, seed, g)
+    dE = torch.randn(B, CFG["F"] + CFG["Fn"], CFG["D"], generator=g) * 1e-3
+    d_out = torch.randn(B, 1, generator=g) * 1e-3
+    params = list(emb.parameters()) + list(fml.parameters())
+    cols = {n: fm.get_column_index(n) for n in fm.features}
+
+    def step():
+        for p in params:
+            p.grad = None                                          # optimizer.zero_grad()
+        X = {n: M[:, c] for n, c in cols.items()}                  # RankingModel.get_inputs (ranking_model.py:106-116)
+        E = emb(X)
+        y = fml(X, E)
+        torch.autograd.backward([E, y], [dE, d_out])               # dense embedding grads
+        return y
+    return step
+
+
 def cpu_step_factory(B, ids_kind, seed):
     from collections import OrderedDict
     from oracle import recbox_oracle as oracle     # checker / baseline only (never the product path)
@@ -168,15 +224,25 @@ def cpu_step_factory(B, ids_kind, seed):
 
 
 def run_cpu(steps, warmup, B, ids_kind):
+    """-> (samples/s, s per step, kind, description): the reference's own modules when baseline/_ref is present."""
     torch.set_num_threads(os.cpu_count() or 1)
-    step = cpu_step_factory(B, ids_kind, 20242)
+    kind, what = "port", "oracle/recbox_oracle.py (CPU restatement; baseline/_ref absent)"
+    step = None
+    if os.path.isdir(os.path.join(REF_DIR, "recbox", "ranking")):
+        try:
+            step = ref_step_factory(B, ids_kind, 20242)
+            kind, what = "reference", "the reference's own FeatureEmbedding + FactorizationMachine (baseline/_ref, unmodified)"
+        except Exception as e:             # say so instead of silently timing something else
+            what = "oracle/recbox_oracle.py (CPU restatement; baseline/_ref failed to import: %s)" % str(e)[:120]
+    if step is None:
+        step = cpu_step_factory(B, ids_kind, 20242)
     for _ in range(warmup):
         step()
     t0 = time.perf_counter()
     for _ in range(steps):
         step()
     dt = (time.perf_counter() - t0) / max(steps, 1)
-    return B / dt, dt
+    return B / dt, dt, kind, what
 
 
 def main_reference(args, rank, world):
@@ -184,15 +250,17 @@ def main_reference(args, rank, world):
         return
     B = CFG["B"]
     steps, warmup = max(1, min(args.steps, 20)), max(1, min(args.warmup, 3))
-    sps, dt = run_cpu(steps, warmup, B, args.ids)
+    sps, dt, kind, what = run_cpu(steps, warmup, B, args.ids)
     cores = torch.get_num_threads()
+    cfg = workload_config(args.ids, 1)
+    cfg["parallelism"] = "one host process, %d threads (the reference's CPU path has no multi-device mode)" % cores
     line = {
         "impl": "reference", "metric": "samples/sec on Criteo-shaped synthetic (embedding + FM hot path, fwd+bwd)",
         "value": sps, "unit": "samples/s", "n_gpus": args.gpus, "steps": steps, "warmup": warmup,
         "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32", "data": "synthetic", "config": workload_config(args.ids, 1),
-        "cpu_baseline": {"value": sps, "unit": "samples/s", "cores": cores, "kind": "port",
-                         "sample": "%d step(s) of the full B=%d batch through oracle/recbox_oracle.py (torch %s CPU ops)" % (steps, B, torch.__version__)},
+        "dtype": "f32", "data": "synthetic", "config": cfg,
+        "cpu_baseline": {"value": sps, "unit": "samples/s", "cores": cores, "kind": kind,
+                         "sample": "%d step(s) of the full B=%d batch through %s (torch %s CPU ops)" % (steps, B, what, torch.__version__)},
         "e2e": {"value": sps, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -200,11 +268,15 @@ def main_reference(args, rank, world):
 
 
 def workload_config(ids_kind, world):
+    par = ("1 GPU" if world == 1 else
+           "dp%d replicas of the 1M-row table, each on its own batch shard; the fused dense gradient buffer (68 MB) is "
+           "all-reduced over NCCL/NVLink INSIDE the timed step (SURVEY 8e 'replicas only')" % world)
     return {"workload": "BASELINE configs[1] DeepFM hot path: 26 cat + 13 dense, 26x38462 = 1000012-row fused table, "
-                        "D=16, B=65536 per GPU; fused gather+FM+LR fwd, dense-grad zero + scatter-add bwd; MLP tail outside the path",
+                        "D=16, B=65536 per GPU; fused gather+FM+LR fwd, dense-grad zero (side stream, under the fwd) + scatter-add bwd; "
+                        "MLP tail outside the path",
             "global_batch": CFG["B"] * world, "ids": ids_kind, "batches_rotated": 4,
             "l2": "working set per step (E 163 MB + dE 163 MB + table/grad 136 MB) exceeds the 126 MB L2; 4 id batches rotate",
-            "parallelism": "dp%d replicas, no data-path collective" % world}
+            "parallelism": par}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -215,7 +287,8 @@ def main_b200(args, rank, world, local_rank):
         raise SystemExit("bench.py: no CUDA device (the B200 arm has no CPU path; use --impl reference for the CPU baseline)")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
-    from recbox_b200 import ops
+    from recbox_b200 import layers, loader, ops
+    from recbox_b200.features import FeatureMap
     import torch.distributed as dist
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
@@ -238,10 +311,7 @@ def main_b200(args, rank, world, local_rank):
     col_kind = [2] * Fn + [1] * F + [3]
     col_slot = list(range(Fn)) + list(range(F)) + [0]
     for i in range(NB):
-        ids = make_ids(B, F, V, args.ids, 1000 * rank + i)
-        dx = torch.rand(B, Fn, generator=g, dtype=torch.float64)
-        lab = (torch.rand(B, 1, generator=g) < 0.5).double()
-        M = torch.cat([dx, torch.from_numpy(ids).double(), lab], 1).contiguous().pin_memory()
+        M = host_batch_matrix(B, args.ids, 1000 * rank + i, g).pin_memory()
         host_batches.append(M)
         r, d, _ = ops.split_batch(M.to(dev), col_kind, col_slot, field_off, F, Fn)
         rows_l.append(r)
@@ -249,23 +319,32 @@ def main_b200(args, rank, world, local_rank):
     dE = (torch.randn(B, Ft, D, generator=g) * 1e-3).to(dev)
     d_fm = (torch.randn(B, generator=g) * 1e-3).to(dev)
     d_lr = d_fm.clone()
-    # dense gradients of every fused parameter live in ONE allocation -> one zero-fill launch
+    # dense gradients of every fused parameter live in ONE allocation -> one zero-fill launch, one all-reduce
     sizes = [R * D, R, Fn * D, Fn, 1]
     offs = [0]
     for n in sizes:
         offs.append((offs[-1] + n + 3) // 4 * 4)
-    gbuf = torch.empty(offs[-1], device=dev)
+    gbuf = torch.zeros(offs[-1], device=dev)
     g_table = gbuf[offs[0]:offs[0] + R * D].view(R, D)
     g_table_lr = gbuf[offs[1]:offs[1] + R]
     g_dense_w = gbuf[offs[2]:offs[2] + Fn * D].view(Fn, D)
     g_dense_w_lr = gbuf[offs[3]:offs[3] + Fn]
     g_bias = gbuf[offs[4]:offs[4] + 1]
+    main = torch.cuda.current_stream()
+    side = torch.cuda.Stream()
+    ev_consumed, ev_zero = torch.cuda.Event(), torch.cuda.Event()
+    ev_consumed.record(main)
 
     def fwd(rows, dx):
         return ops.embed_fm_fwd(table, table_lr, rows, cat_pos, dx, dense_w, dense_w_lr, num_pos, bias)
 
-    def zero():
-        gbuf.zero_()
+    def zero_async():
+        """optimizer.zero_grad() of the fused gradient buffer on the side stream: runs under the forward, after the last
+        reader of the previous step's gradients (the all-reduce / the backward) is done."""
+        side.wait_event(ev_consumed)
+        with torch.cuda.stream(side):
+            ops.zero_(gbuf)
+            ev_zero.record(side)
 
     def bwd(rows, dx, E, S):
         ops.embed_fm_bwd(table, rows, cat_pos, pad_row, dx, dense_w, num_pos, E, S, dE, d_fm, d_lr,
@@ -273,13 +352,18 @@ def main_b200(args, rank, world, local_rank):
 
     def step(i, evs=None):
         rows, dx = rows_l[i % NB], dense_l[i % NB]
+        zero_async()
         if evs: evs[0].record()
         E, S, fm, lr = fwd(rows, dx)
         if evs: evs[1].record()
-        zero()
+        main.wait_event(ev_zero)
         if evs: evs[2].record()
         bwd(rows, dx, E, S)
         if evs: evs[3].record()
+        if world > 1:
+            dist.all_reduce(gbuf)              # replicas train ONE model: dense gradient exchange inside the step
+        if evs: evs[4].record()
+        ev_consumed.record(main)
         return fm, lr
 
     def barrier():
@@ -293,7 +377,7 @@ def main_b200(args, rank, world, local_rank):
     # ---- value: device-resident, CUDA events, max over ranks ----
     sampler = ClockSampler(local_rank)
     sampler.start()
-    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(K)]
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(5)] for _ in range(K)]
     t_beg, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     t_beg.record()
@@ -303,29 +387,55 @@ def main_b200(args, rank, world, local_rank):
     barrier()
     ms_total = t_beg.elapsed_time(t_end)
     t_f = sum(e[0].elapsed_time(e[1]) for e in evs) / K
-    t_z = sum(e[1].elapsed_time(e[2]) for e in evs) / K
+    t_w = sum(e[1].elapsed_time(e[2]) for e in evs) / K          # backward waiting for the zero-fill (0 when it hid)
     t_b = sum(e[2].elapsed_time(e[3]) for e in evs) / K
+    t_ar = sum(e[3].elapsed_time(e[4]) for e in evs) / K
+    # the zero-fill kernel alone (own events on its stream, separate pass so that it does not perturb the timed region)
+    z0, z1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    with torch.cuda.stream(side):
+        z0.record(side)
+        for _ in range(10):
+            ops.zero_(gbuf)
+        z1.record(side)
+    torch.cuda.synchronize()
+    t_z = z0.elapsed_time(z1) / 10
 
-    # ---- e2e: pinned HOST batch -> H2D -> (split) -> step -> logits back to host --------------------
-    # Every step's input crosses PCIe inside the timed region.  The loader-side prefetch is the usual
-    # one: batch i+1 is copied on a copy stream while batch i computes (two device buffers, events
-    # both ways); the logits go back on a third stream.
-    #   mode "f64":    the reference loader's float64 [B,40] batch matrix (h5_dataloader.py:46) + rbx_split_batch_f64
-    #   mode "packed": recbox_b200.loader.PackedDataLoader's blocks (int32 rows [B,F] + fp32 dense [B,Fn], converted
-    #                  once at load time) -- the kernels read the copied blocks directly
-    main = torch.cuda.current_stream()
+    # ---- e2e: pinned HOST batch -> H2D -> step -> logits back to host, every step, inside the timed region ----------
+    # Through the public layer API a RecBox model calls (FeatureEmbedding + FactorizationMachine modules, autograd
+    # backward with the MLP tail's stand-in gradient), fed by
+    #   "packed":  recbox_b200.loader.PackedDataLoader's blocks -- uint16 ids [B,26] (every vocabulary < 65 536) + fp32
+    #              dense [B,13] + fp32 label, converted once at load time: 108 B / sample   <- `e2e`
+    #   "f64":     the reference loader's float64 [B,40] batch matrix (h5_dataloader.py:46): 320 B / sample  <- `e2e_f64`
+    # and once below the layer API, straight on the ops (int32 packed blocks), to show what the Python layer costs.
+    # The loader-side prefetch is the usual one: batch i+1 is copied on a copy stream while batch i computes (two device
+    # buffers, events both ways); the logits go back on a third stream.
+    fmap = criteo_feature_map(FeatureMap)
+    torch.manual_seed(20240 + 2)
+    emb = layers.FeatureEmbedding(fmap, D).to(dev)
+    fml = layers.FactorizationMachine(fmap).to(dev)
+    params = list(emb.parameters()) + list(fml.parameters())
+    d_out = d_fm.view(-1, 1)
+
+    class _Model(object):                                        # what layers.get_inputs needs of a RankingModel
+        feature_map, device = fmap, dev
+    ds = loader.PackedDataset(fmap, torch.cat(host_batches, 0))  # compact: uint16 ids
+    host_packed = [ds.batch(i * B, (i + 1) * B) for i in range(NB)]
     h2d, d2h = torch.cuda.Stream(), torch.cuda.Stream()
-    out_host = [torch.empty(B, dtype=torch.float32).pin_memory() for _ in range(2)]
-    logit_dev = [torch.empty(B, dtype=torch.float32, device=dev) for _ in range(2)]
-    packed_host = [(r.cpu().pin_memory(), d.cpu().pin_memory()) for r, d in zip(rows_l, dense_l)]
+    out_host = [torch.empty(B, 1, dtype=torch.float32).pin_memory() for _ in range(2)]
+    logit_dev = [torch.empty(B, 1, dtype=torch.float32, device=dev) for _ in range(2)]
+    packed32_host = [(r.cpu().pin_memory(), d.cpu().pin_memory()) for r, d in zip(rows_l, dense_l)]
 
     def e2e_measure(mode):
         if mode == "f64":
-            dev_in = [(torch.empty_like(host_batches[0], device=dev),) for _ in range(2)]
-            src = [(m,) for m in host_batches]
+            dev_in = [torch.empty_like(host_batches[0], device=dev) for _ in range(2)]
+            nbytes = host_batches[0].numel() * 8
+        elif mode == "packed":
+            dev_in = [host_packed[0].to(dev) for _ in range(2)]
+            nbytes = host_packed[0].nbytes
         else:
             dev_in = [(torch.empty_like(rows_l[0]), torch.empty_like(dense_l[0])) for _ in range(2)]
-            src = packed_host
+            nbytes = sum(t.numel() * t.element_size() for t in packed32_host[0])
         ev_in = [torch.cuda.Event() for _ in range(2)]      # batch landed in dev_in[j]
         ev_free = [torch.cuda.Event() for _ in range(2)]    # dev_in[j] consumed
         ev_out = [torch.cuda.Event() for _ in range(2)]     # logits of slot j computed
@@ -335,30 +445,49 @@ def main_b200(args, rank, world, local_rank):
             j = i % 2
             with torch.cuda.stream(h2d):
                 h2d.wait_event(ev_free[j])
-                for d_, s_ in zip(dev_in[j], src[i % NB]):
-                    d_.copy_(s_, non_blocking=True)
+                if mode == "f64":
+                    dev_in[j].copy_(host_batches[i % NB], non_blocking=True)
+                elif mode == "packed":
+                    host_packed[i % NB].copy_into(dev_in[j])
+                else:
+                    for d_, s_ in zip(dev_in[j], packed32_host[i % NB]):
+                        d_.copy_(s_, non_blocking=True)
                 ev_in[j].record(h2d)
 
         def compute(i):
             j = i % 2
             main.wait_event(ev_in[j])
-            if mode == "f64":
-                rows, dx, lab = ops.split_batch(dev_in[j][0], col_kind, col_slot, field_off, F, Fn)
-                ev_free[j].record(main)
-            else:
+            if mode == "ops":
                 rows, dx = dev_in[j]
-            E, S, fm, lr = fwd(rows, dx)
-            main.wait_event(ev_read[j])                      # the previous logits of this slot left the device
-            torch.add(fm, lr, out=logit_dev[j])
+                zero_async()
+                E, S, fm, lr = fwd(rows, dx)
+                main.wait_event(ev_read[j])                  # the previous logits of this slot left the device
+                torch.add(fm.view(-1, 1), lr.view(-1, 1), out=logit_dev[j])
+            else:
+                for p in params:
+                    p.grad = None                            # optimizer.zero_grad() (ranking_model.py:192)
+                X = layers.get_inputs(_Model, dev_in[j])     # PackedColumns / PackedInputs views, no copies
+                E = emb(X)
+                y = fml(X, E)
+                main.wait_event(ev_read[j])
+                logit_dev[j].copy_(y.detach())
             ev_out[j].record(main)
             with torch.cuda.stream(d2h):
                 d2h.wait_event(ev_out[j])
                 out_host[j].copy_(logit_dev[j], non_blocking=True)
                 ev_read[j].record(d2h)
-            zero()
-            bwd(rows, dx, E, S)
-            if mode != "f64":
-                ev_free[j].record(main)                      # the backward still reads the copied blocks
+            if mode == "ops":
+                main.wait_event(ev_zero)
+                bwd(rows, dx, E, S)
+                ev_consumed.record(main)
+            else:
+                torch.autograd.backward([E, y], [dE, d_out])
+            if world > 1:                                    # the replicas' gradient exchange belongs to the step
+                if mode == "ops":
+                    dist.all_reduce(gbuf)
+                else:
+                    layers.sync_replica_gradients(params)
+            ev_free[j].record(main)                          # the backward still reads the copied blocks
 
         def run(n):
             copy_in(0)
@@ -376,50 +505,74 @@ def main_b200(args, rank, world, local_rank):
         run(K)
         e_end.record()
         barrier()
-        return e_beg.elapsed_time(e_end), sum(t.numel() * t.element_size() for t in src[0])
+        return e_beg.elapsed_time(e_end), nbytes
 
-    ms_e2e, e2e_bytes, ms_e2e_packed, e2e_packed_bytes = 0.0, 0, 0.0, 0
+    e2e_ms = {}
     if not args.no_e2e:
-        ms_e2e, e2e_bytes = e2e_measure("f64")
-        ms_e2e_packed, e2e_packed_bytes = e2e_measure("packed")
+        for mode in ("packed", "f64", "ops"):
+            e2e_ms[mode] = e2e_measure(mode)
     sampler.stop_flag = True
     sampler.join(timeout=2)
 
-    times = torch.tensor([ms_total, ms_e2e, t_f, t_z, t_b, ms_e2e_packed], dtype=torch.float64, device=dev)
+    names = ["packed", "f64", "ops"]
+    times = torch.tensor([ms_total, t_f, t_w, t_b, t_ar, t_z] + [e2e_ms[m][0] if m in e2e_ms else 0.0 for m in names],
+                         dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
-    ms_total, ms_e2e, t_f, t_z, t_b, ms_e2e_packed = times.tolist()
+    ms_total, t_f, t_w, t_b, t_ar, t_z = times.tolist()[:6]
+    e2e_t = dict(zip(names, times.tolist()[6:]))
+
+    sharded_line = None
+    if not args.no_sharded:     # configs[3] at the same N, in the same invocation (driver-witnessed exchange + parity)
+        try:
+            sharded_line = run_sharded(args, rank, world, dev, min(K, 30), 3)
+            if sharded_line is not None:
+                for k in ("metric", "unit", "higher_is_better", "scaling", "vs_baseline", "dtype", "data", "n_gpus"):
+                    sharded_line.pop(k, None)
+        except Exception as e:    # the headline line must survive a failure of the secondary workload; the failure is reported
+            sharded_line = {"error": repr(e)[:300]}
 
     if rank == 0:
         peak, peak_src = peaks()
         bf, bb = bytes_fwd(F, Fn, D) * B, bytes_bwd(F, Fn, D) * B
         kern = {"embed_fm_fwd": {"ms": t_f, "alg_bytes": bf, "gbs": bf / t_f / 1e6},
-                "grad_zero_fill(memset)": {"ms": t_z, "alg_bytes": (R * D + R) * 4, "gbs": (R * D + R) * 4 / t_z / 1e6},
+                "grad_zero_fill (rbx_zero_f32, side stream under the forward)": {"ms": t_z, "alg_bytes": offs[-1] * 4, "gbs": offs[-1] * 4 / t_z / 1e6,
+                                                                                  "exposed_ms": t_w},
                 "embed_fm_bwd(+dense_w_bwd)": {"ms": t_b, "alg_bytes": bb, "gbs": bb / t_b / 1e6}}
+        if world > 1:
+            kern["nccl_all_reduce(grad buffer)"] = {"ms": t_ar, "bytes": offs[-1] * 4,
+                                                    "busbw_gbs": 2 * (world - 1) / world * offs[-1] * 4 / t_ar / 1e6}
         dom = "embed_fm_bwd(+dense_w_bwd)" if t_b >= t_f else "embed_fm_fwd"
         ach = kern[dom]["gbs"]
+
+        def e2e_obj(mode, what):
+            ms, nbytes = e2e_t[mode], e2e_ms[mode][1]
+            return {"value": B * world * K / (ms * 1e-3), "unit": "samples/s", "h2d_bytes_per_step": nbytes,
+                    "d2h_bytes_per_step": B * 4, "ms_per_step": ms / K, "input": what}
         line = {
             "metric": "samples/sec on Criteo-shaped synthetic (embedding + FM hot path, fwd+bwd)",
             "value": B * world * K / (ms_total * 1e-3), "unit": "samples/s", "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic", "config": workload_config(args.ids, world),
-            "e2e": None if args.no_e2e else {"value": B * world * K / (ms_e2e * 1e-3), "unit": "samples/s",
-                    "h2d_bytes_per_step": e2e_bytes, "d2h_bytes_per_step": B * 4, "ms_per_step": ms_e2e / K,
-                    "input": "reference loader's float64 [B,40] batch matrix (h5_dataloader.py:46), pinned"},
-            "e2e_packed": None if args.no_e2e else {"value": B * world * K / (ms_e2e_packed * 1e-3), "unit": "samples/s",
-                    "h2d_bytes_per_step": e2e_packed_bytes, "d2h_bytes_per_step": B * 4, "ms_per_step": ms_e2e_packed / K,
-                    "input": "recbox_b200.loader.PackedDataLoader blocks (int32 rows + fp32 dense, converted once at load), pinned"},
-            "gpu_launches": 2 * K, "library_launches": K,   # ours: k_embed_fm_fwd + k_embed_fm_bwd; torch fill zeroes the grads
+            "e2e": None if args.no_e2e else e2e_obj("packed", "layer API (FeatureEmbedding + FactorizationMachine modules, autograd) fed by "
+                    "recbox_b200.loader.PackedDataset blocks: uint16 ids + fp32 dense + fp32 label (108 B/sample), pinned"),
+            "e2e_f64": None if args.no_e2e else e2e_obj("f64", "layer API fed by the reference loader's float64 [B,40] batch matrix "
+                    "(h5_dataloader.py:46; 320 B/sample), pinned -- the compatibility number"),
+            "e2e_ops": None if args.no_e2e else e2e_obj("ops", "below the layer API: recbox_b200.ops on int32 packed blocks (160 B/sample), pinned"),
+            # ours per step: k_embed_fm_fwd + k_zero_f32 + k_embed_fm_bwd; library: the NCCL all-reduce at N > 1
+            "gpu_launches": 3 * K, "library_launches": K if world > 1 else 0,
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                          "traffic": ncu_traffic(dom) if args.ids == "uniform" else None, "peak_source": peak_src,
                          "pair_achieved": (bf + bb) / (t_f + t_b) / 1e6, "pair_frac": (bf + bb) / (t_f + t_b) / 1e6 / peak},
             "kernels": kern, "l2_persisting_bytes": l2_persist,
             "clocks": sampler.summary(),
         }
+        if sharded_line is not None:
+            line["sharded"] = sharded_line
         if world == 1 and not args.no_cpu_baseline:
-            sps, dt = run_cpu(3, 1, B, args.ids)
-            line["cpu_baseline"] = {"value": sps, "unit": "samples/s", "cores": torch.get_num_threads(), "kind": "port",
-                                    "sample": "3 steps of the full B=%d batch through oracle/recbox_oracle.py (%.0f ms/step)" % (B, dt * 1e3)}
+            sps, dt, kind, what = run_cpu(3, 1, B, args.ids)
+            line["cpu_baseline"] = {"value": sps, "unit": "samples/s", "cores": torch.get_num_threads(), "kind": kind,
+                                    "sample": "3 steps of the full B=%d batch through %s (%.0f ms/step)" % (B, what, dt * 1e3)}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -428,21 +581,79 @@ def main_b200(args, rank, world, local_rank):
 # ------------------------------------------------------------------------------------------------
 # B200 arm, BASELINE configs[3]: 100M-row table row-sharded over the ranks (weak scaling: B per GPU fixed)
 # ------------------------------------------------------------------------------------------------
-def main_sharded(args, rank, world, local_rank):
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device")
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
+def sharded_parity(args, rank, world, dev):
+    """In-run parity of the exchange at THIS world size: a small row-sharded table (same mode / layout as the timed run)
+    against the single-table fused kernels (the oracle-pinned path, tests/test_kernels_gpu.py) on the same seeded inputs --
+    gathered rows bit-exact, sums and gradients within 1e-5 (transitive parity: sharded == single-table == oracle).
+    -> True / False over all ranks."""
     import torch.distributed as dist
     from recbox_b200 import ops, sharded
+    F, Fn, D, V, B = 8, 3, args.dim, 997, 2048
+    Ft, R = F + Fn, F * V
+    g = torch.Generator().manual_seed(4242)                       # every rank builds the same global problem
+    table = (torch.randn(R, D, generator=g) * 0.1).to(dev)
+    table_lr = (torch.randn(R, generator=g) * 0.1).to(dev)
+    dense_w = (torch.randn(Fn, D, generator=g) * 0.1).to(dev)
+    dense_w_lr = (torch.randn(Fn, generator=g) * 0.1).to(dev)
+    bias = torch.full((1,), 0.25, device=dev)
+    field_off = [f * V for f in range(F)]
+    ids = torch.randint(0, V, (B * world, F), generator=g)
+    rows_all = (ids + torch.tensor(field_off)[None]).to(torch.int32).to(dev)
+    dx_all = torch.rand(B * world, Fn, generator=g).to(dev)
+    dE = torch.randn(B * world, Ft, D, generator=g).to(dev)
+    d_fm = torch.randn(B * world, generator=g).to(dev)
+    d_lr = torch.randn(B * world, generator=g).to(dev)
+    cat_pos, num_pos, pad_row = list(range(Fn, Ft)), list(range(Fn)), field_off
+    sl = slice(rank * B, (rank + 1) * B)
+    ok = True
+    sh = sharded.ShardedEmbeddingFM(R, D, mode=args.shard_mode, device=dev, max_ids=B * F, alloc=args.peer_alloc, layout=args.shard_layout,
+                                    chunks=args.shard_chunks, slack=3.0)
+    try:
+        sh.load_global(table, table_lr)
+        rows, dx = rows_all[sl].contiguous(), dx_all[sl].contiguous()
+        E, S, fm, lr = sh.forward(rows, cat_pos, dx, dense_w, dense_w_lr, num_pos, bias)
+        gw, gw1, gb = torch.zeros(Fn, D, device=dev), torch.zeros(Fn, device=dev), torch.zeros(1, device=dev)
+        sh.zero_grad()
+        sh.barrier()
+        sh.backward(rows, cat_pos, pad_row, dx, dense_w, num_pos, E, S, dE[sl].contiguous(), d_fm[sl].contiguous(), d_lr[sl].contiguous(),
+                    gw, gw1, gb)
+        sh.barrier()
+        sh.check_overflow()
+        if world > 1:
+            for t in (gw, gw1, gb):
+                dist.all_reduce(t)
+        gt, gt1 = sh.gather_global("g_table"), sh.gather_global("g_table_lr")
+        Er, Sr, fmr, lrr = ops.embed_fm_fwd(table, table_lr, rows_all, cat_pos, dx_all, dense_w, dense_w_lr, num_pos, bias)
+        rt, rt1 = torch.zeros_like(table), torch.zeros_like(table_lr)
+        rw, rw1, rb = torch.zeros_like(gw), torch.zeros_like(gw1), torch.zeros_like(gb)
+        ops.embed_fm_bwd(table, rows_all, cat_pos, pad_row, dx_all, dense_w, num_pos, Er, Sr, dE, d_fm, d_lr, rt, rt1, rw, rw1, rb, D, R)
+
+        def close(a, b):
+            return bool(((a - b).abs() <= 1e-5 * b.abs() + 2e-5 * b.abs().max()).all())
+        ok = torch.equal(E, Er[sl]) and close(S, Sr[sl]) and close(fm, fmr[sl]) and close(lr, lrr[sl])
+        ok = ok and all(close(a, b) for a, b in ((gt, rt), (gt1, rt1), (gw, rw), (gw1, rw1), (gb, rb)))
+    except Exception as e:                       # a failed check must not take the bench line with it; it is reported
+        sys.stderr.write("sharded_parity[rank %d]: %r\n" % (rank, e))
+        ok = False
+    finally:
+        sh.close()
+    flag = torch.tensor([1 if ok else 0], device=dev)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    return bool(flag.item())
+
+
+def run_sharded(args, rank, world, dev, K, W):
+    """configs[3] on the ranks of an initialised process group -> the JSON object (rank 0; None elsewhere)."""
+    import torch.distributed as dist
+    from recbox_b200 import sharded
     B, F, Fn, D, V = CFG["B"], CFG["F"], CFG["Fn"], args.dim, args.rows_per_field
     Ft, R = F + Fn, F * V
-    if args.shard_mode == "auto":       # one GPU: the local fused kernels; several: the streamed exchange
-        args.shard_mode = "peer" if world == 1 else "stream"
+    if args.shard_mode == "auto":       # the fused kernels with the exchange inside them: best measured at N = 1, 2 and 8
+        args.shard_mode = "peer"        # (profiles/r2_sharded_runs.jsonl: 673 us at N = 8 vs 800 us streamed)
     if args.shard_layout == "auto":     # ROW+LR wins on multi-GB tables at every N (profiles/r1_sharded_runs.jsonl, r2e / r1w)
         args.shard_layout = "rowlr" if (args.shard_mode in ("peer", "stream") and not args.no_lr and D in (4, 8, 16)) else "split"
+    parity_ok = sharded_parity(args, rank, world, dev) if not args.no_lr else None
     sh = sharded.ShardedEmbeddingFM(R, D, mode=args.shard_mode, device=dev, max_ids=B * F, alloc=args.peer_alloc, with_lr=not args.no_lr,
                                     layout=args.shard_layout, chunks=args.shard_chunks, slack=1.25)
     gen = torch.Generator(device=dev).manual_seed(20240 + 4 + rank)
@@ -483,11 +694,10 @@ def main_sharded(args, rank, world, local_rank):
             dist.barrier()
         torch.cuda.synchronize()
 
-    K, W = args.steps, max(args.warmup, 3)
     for i in range(W):
         step(i)
     sh.check_overflow()
-    sampler = ClockSampler(local_rank)
+    sampler = ClockSampler(dev.index)
     sampler.start()
     evs = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(K)]
     t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -512,10 +722,18 @@ def main_sharded(args, rank, world, local_rank):
         phases = {k: v / K for k, v in sh.phase_times(sh.profile).items()}
         sh.profile = None
         barrier()
+        if world > 1:                          # slowest and fastest rank per phase
+            names = sorted(phases)
+            mine = torch.tensor([phases[n] for n in names], dtype=torch.float64, device=dev)
+            hi, lo = mine.clone(), mine.clone()
+            dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+            dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+            phases = {n: {"rank0": phases[n], "min": float(lo[i]), "max": float(hi[i])} for i, n in enumerate(names)}
     times = torch.tensor([ms_total, t_f, t_b, t_s], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
     ms_total, t_f, t_b, t_s = times.tolist()
+    line = None
     if rank == 0:
         peak, peak_src = peaks()
         bf, bb = bytes_fwd(F, Fn, D) * B, bytes_bwd(F, Fn, D) * B
@@ -527,6 +745,11 @@ def main_sharded(args, rank, world, local_rank):
             "value": B * world * K / (ms_total * 1e-3), "unit": "samples/s", "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
+            "mode": args.shard_mode, "layout": args.shard_layout, "parity_ok": parity_ok,
+            "fwd_us": t_f * 1e3, "bwd_us": t_b * 1e3,
+            "nvlink_gbs": {"fwd": nv_f / t_f / 1e6, "bwd": nv_b / t_b / 1e6, "peak": 770.0,
+                           "what": "payload bytes (remote rows + first-order weights) per direction per GPU / phase time; peak = measured "
+                                   "peer copy per direction (B200_PROFILING.md)"},
             "config": {"workload": "BASELINE configs[3]: DeepFM hot path, %d-row fused table (26 x %d) row-sharded over %d GPU(s), "
                                    "D=%d, B=65536 per GPU; mode=%s%s" % (R, V, world, D, args.shard_mode,
                                                                             (", layout=%s" % args.shard_layout if args.shard_layout != "split" else "") +
@@ -552,8 +775,23 @@ def main_sharded(args, rank, world, local_rank):
         }
         if phases is not None:
             line["phases_ms_rank0"] = phases
-        print(json.dumps(line))
     sh.close()
+    del sh
+    torch.cuda.empty_cache()
+    return line
+
+
+def main_sharded(args, rank, world, local_rank):
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    import torch.distributed as dist
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    line = run_sharded(args, rank, world, dev, args.steps, max(args.warmup, 3))
+    if rank == 0:
+        print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
 
@@ -567,6 +805,7 @@ def main():
     ap.add_argument("--ids", default="uniform", choices=["uniform", "zipf"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end leg (profiling runs under ncu)")
+    ap.add_argument("--no-sharded", action="store_true", help="cfg2 run without the attached configs[3] (100M-row sharded table) object")
     ap.add_argument("--workload", default="cfg2", choices=["cfg2", "sharded"],
                     help="cfg2: BASELINE configs[1], replicated 1M-row table (default, the metric's config); "
                          "sharded: configs[3], 100M-row table row-sharded over the ranks")

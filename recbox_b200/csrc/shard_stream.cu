@@ -203,14 +203,18 @@ struct ServeParams {
 template <int LPR>
 __global__ void __launch_bounds__(kThreads) k_xs_serve(const __grid_constant__ ServeParams p) {
     constexpr int D = 4 * LPR, RPW = 32 / LPR, U = 8;
-    const int q = blockIdx.y;
+    // destination = blockIdx.x % world, so the CTAs resident at any moment feed every peer's ingress evenly (with the
+    // destination on grid.y the last destinations only start when the first ones are done, and their ingress then takes
+    // all eight sources at once: measured 316 us instead of ~190 for the same bytes at 8 GPUs)
+    const int q = (blockIdx.x + p.rank) % p.world;
+    const int bx = blockIdx.x / p.world, gx = gridDim.x / p.world;
     int64_t n = __ldg(p.meta + q);
     if (n > p.cap) n = p.cap;
     float* out = reinterpret_cast<float*>(p.rowbuf.p[q]) + (size_t)p.rank * p.cap * D;
     float* out_lr = (p.lr && p.rowbuf_lr.p[q]) ? reinterpret_cast<float*>(p.rowbuf_lr.p[q]) + (size_t)p.rank * p.cap : nullptr;
     const int32_t* ids = p.inbox_ids + (size_t)q * p.cap;
     const int lane = threadIdx.x & 31, lig = lane & (LPR - 1), gi = lane / LPR;
-    const int64_t warp0 = (int64_t)blockIdx.x * kWarps + (threadIdx.x >> 5), nwarps = (int64_t)gridDim.x * kWarps;
+    const int64_t warp0 = (int64_t)bx * kWarps + (threadIdx.x >> 5), nwarps = (int64_t)gx * kWarps;
     const uint64_t pol_keep = l2_policy_evict_last();
     for (int64_t base = warp0 * (RPW * U); base < n; base += nwarps * (RPW * U)) {
         int32_t r[U];
@@ -736,9 +740,9 @@ int rbx_xs_serve(const float* table, int64_t row_stride, const float* lr, int64_
     p.cap = cap; p.rank = rank; p.world = world;
     if (int rc = fill_peers(p.rowbuf, rowbuf, world, true, who, "rowbuf")) return rc;
     if (int rc = fill_peers(p.rowbuf_lr, rowbuf_lr, world, lr != nullptr, who, "rowbuf_lr")) return rc;
-    int64_t per = (int64_t)rbx_sm_count() * 6 / world;
+    int64_t per = (int64_t)rbx_sm_count() * 4 / world;      // 4 resident CTAs per SM (64 registers): one wave, every destination in it
     if (per < 1) per = 1;
-    XS_DISPATCH_LPR(D, (k_xs_serve<LPR><<<dim3((unsigned)per, world), kThreads, 0, rbx_cast_stream(stream)>>>(p)));
+    XS_DISPATCH_LPR(D, (k_xs_serve<LPR><<<(unsigned)(per * world), kThreads, 0, rbx_cast_stream(stream)>>>(p)));
     RBX_LAUNCH_CHECK(who);
     return RBX_OK;
 }

@@ -338,6 +338,38 @@ class _FusedEmbedFn(torch.autograd.Function):
         return (None, None, None, None) + tuple(grads)
 
 
+def fused_grad_buffers(params):
+    """The distinct gradient allocations behind `params`: the per-feature .grad tensors a fused backward hands to autograd
+    are views of ONE buffer per launch (see _FusedEmbedFn.backward), so a replica's gradient exchange is one collective over
+    that buffer instead of one per feature.  Gradients that are not views come back as they are."""
+    seen, out = set(), []
+    for p in params:
+        g = p.grad
+        if g is None:
+            continue
+        b = g._base if g._base is not None else g
+        key = (b.data_ptr(), b.numel())
+        if key not in seen:
+            seen.add(key)
+            out.append(b)
+    return out
+
+
+def sync_replica_gradients(params, group=None, average=False):
+    """Data-parallel replicas of a table that fits every GPU (SURVEY 8e "replicas only"): dense all-reduce of the fused
+    gradient buffers over NCCL / NVLink, in place -- what DistributedDataParallel does for the reference's RecBole / rechub
+    trainers (third_party/recbole/trainer/trainer.py:60-64), with one bucket per fused launch."""
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return 0
+    bufs = fused_grad_buffers(params)
+    for b in bufs:
+        dist.all_reduce(b, group=group)
+        if average:
+            b.div_(dist.get_world_size(group))
+    return len(bufs)
+
+
 class _GatherFn(torch.autograd.Function):
     """Plain lookup [.., ] ids -> [.., D] (un-pooled sequence features, generic encoders)."""
 

@@ -96,3 +96,34 @@ def test_stream_orchestration_world2_gloo(layout, chunks, tmp_path):
     world = 2
     mp.spawn(_worker, args=(world, _free_port(), str(tmp_path), "stream", layout, chunks), nprocs=world, join=True)
     assert all(os.path.exists(os.path.join(str(tmp_path), "ok%d" % r)) for r in range(world))
+
+
+def _replica_worker(rank, world, port, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from recbox_b200 import layers
+        # the shape a fused backward leaves behind: per-feature .grad tensors that are views of ONE buffer, plus a
+        # gradient with its own storage
+        buf = torch.arange(24, dtype=torch.float32) * (rank + 1)
+        ps = [torch.nn.Parameter(torch.zeros(4, 4)), torch.nn.Parameter(torch.zeros(2, 4)), torch.nn.Parameter(torch.zeros(3))]
+        ps[0].grad, ps[1].grad = buf[:16].view(4, 4), buf[16:24].view(2, 4)
+        ps[2].grad = torch.full((3,), float(rank + 1))
+        bufs = layers.fused_grad_buffers(ps)
+        assert len(bufs) == 2 and bufs[0].data_ptr() == buf.data_ptr() and bufs[0].numel() == 24
+        assert layers.sync_replica_gradients(ps) == 2             # two collectives, not three
+        tot = sum(r + 1 for r in range(world))
+        assert torch.equal(ps[0].grad, (torch.arange(16, dtype=torch.float32) * tot).view(4, 4))
+        assert torch.equal(ps[1].grad, (torch.arange(16, 24, dtype=torch.float32) * tot).view(2, 4))
+        assert torch.equal(ps[2].grad, torch.full((3,), float(tot)))
+        open(os.path.join(out_dir, "ok%d" % rank), "w").write("ok")
+    finally:
+        dist.destroy_process_group()
+
+
+def test_replica_gradient_sync_world2_gloo(tmp_path):
+    """Replica mode (SURVEY 8e "replicas only"): one all-reduce per fused gradient buffer, results land in every
+    parameter's .grad view."""
+    world = 2
+    mp.spawn(_replica_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    assert all(os.path.exists(os.path.join(str(tmp_path), "ok%d" % r)) for r in range(world))
