@@ -512,6 +512,32 @@ int rbx_sample_negatives(int64_t n_queries, int num_negs, int64_t num_items, uin
                          rbx_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
+ * a13  dense MLP tail (csrc/gemm.cu): fp32 GEMM on the tcgen05 tensor cores, fused epilogue
+ * Replaces nn.Linear + activation of MLP_Block (recbox/ranking/pytorch/layers/blocks/mlp_block.py:43-61;
+ * core/pytorch/layers/mlp.py) and their autograd backward inside loss.backward()
+ * (recbox/ranking/pytorch/models/ranking_model.py:191-197):
+ *     C[M,N] (+)= relu?( A[M,K] * B[N,K]^T + bias[N] ) * (mask[M,N] > 0)?
+ * A is logically [M,K], B logically [N,K]; a_mn / b_mn say how they lie in memory:
+ *     a_mn = 0: A stored row-major [M,K] (K contiguous, pitch lda)    a_mn = 1: stored [K,M] (M contiguous)
+ *     b_mn = 0: B stored row-major [N,K] (nn.Linear.weight)           b_mn = 1: stored [K,N] (N contiguous)
+ *   forward  H' = relu(H W^T + b):  A = H, B = W,            a_mn = 0, b_mn = 0, bias, act = 1
+ *   backward dH = (dZ W) * (H > 0): A = dZ, B = W as [K=N_lin, N=K_lin],  b_mn = 1, mask = H
+ *            dW = dZ^T H:           A = dZ as [K=batch, M=N_lin], B = H as [K=batch, N=K_lin], a_mn = b_mn = 1
+ * precision 3: every operand split into two TF32 words in shared memory, three MMAs per k-step, fp32 accumulation in
+ * TMEM -> fp32-level results (the 1e-5 contract); precision 1: plain TF32 (~1e-3 rel).  act: 0 none, 1 ReLU.
+ * accumulate != 0 adds into C.  Outputs with few tiles and a long K are split over K (red.add into C; not with act / mask).
+ * lda, ldb multiples of 4 floats and A, B 16-byte aligned on the tensor-core path; N <= 8, K <= 8 and M <= 8 shapes
+ * (the Linear(hidden, 1) head) run memory-bound SIMT kernels.
+ * rbx_colsum_f32: out[n] (+)= sum_m X[m,n]  (bias gradient).
+ * ------------------------------------------------------------------------------------------ */
+int rbx_gemm_f32(const float* A /*DEVICE*/, int64_t lda, int a_mn, const float* B /*DEVICE*/, int64_t ldb, int b_mn,
+                 float* C /*DEVICE [M,N] pitch ldc*/, int64_t ldc, int64_t M, int64_t N, int64_t K,
+                 const float* bias /*DEVICE [N] | NULL*/, int act, const float* mask /*DEVICE [M,N] pitch ldmask | NULL*/,
+                 int64_t ldmask, int precision, int accumulate, rbx_stream_t stream);
+int rbx_colsum_f32(const float* X /*DEVICE [M,N] pitch ldx*/, int64_t ldx, float* out /*DEVICE [N]*/, int64_t M, int64_t N,
+                   int accumulate, rbx_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
  * f3  retrieval evaluation (csrc/topk.cu)
  * rbx_topk_ip replaces FaissIndex.search = faiss.IndexFlatIP(dim).search(query, topk)
  * (recbox/utils/ann/faiss.py:3-14; called from evaluate_block, recbox/core/metrics.py:52-54):

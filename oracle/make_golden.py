@@ -477,6 +477,37 @@ def golden_retrieval():
         average=np.array([avg[m] for m in metrics]), per_user=np.array(per_user, dtype=np.float64))
 
 
+def golden_mlp_block(L):
+    """a13: the reference's MLP_Block (ranking) and MLP_Layer (core) themselves -- seeded init, forward, backward.
+    plain: the DeepFM / DNN shape (ReLU hidden layers, Linear(., 1) head); mixed: batch-norm before the activation, a tanh
+    layer, no bias, sigmoid output (everything around the GEMMs stays torch; the Linear layers are ours)."""
+    from recbox.core.pytorch.layers import MLP_Layer
+    out = {}
+    g = torch.Generator().manual_seed(77)
+    x = torch.randn(64, 104, generator=g)
+    wy = torch.randn(64, 1, generator=g)
+    cases = {
+        "plain": lambda: L.MLP_Block(input_dim=104, hidden_units=[96, 48], hidden_activations="ReLU", output_dim=1),
+        "mixed": lambda: L.MLP_Block(input_dim=104, hidden_units=[64, 32], hidden_activations=["relu", "tanh"], output_dim=1,
+                                     output_activation="sigmoid", batch_norm=True, use_bias=False),
+        "nohead": lambda: L.MLP_Block(input_dim=104, hidden_units=[48], hidden_activations="ReLU"),      # chain ENDS in a ReLU
+        "core": lambda: MLP_Layer(input_dim=104, output_dim=1, hidden_units=[32, 16], hidden_activations="ReLU", final_activation=None,
+                                  dropout_rates=[0.0, 0.0]),
+    }
+    for tag, mk in cases.items():
+        torch.manual_seed(5)
+        m = mk()
+        m.train()
+        out.update({k: v.clone() for k, v in sd_arrays(m, tag + ".init.").items()})    # before the forward (batch-norm stats move)
+        xin = x.clone().requires_grad_(True)
+        y = m(xin)
+        w = wy if y.shape[1] == 1 else torch.randn(y.shape, generator=torch.Generator().manual_seed(6))
+        (y * w).sum().backward()
+        out[tag + ".y"], out[tag + ".dx"], out[tag + ".w"] = y, xin.grad, w
+        out.update(grads_of(m, tag + ".grad."))
+    npz("mlp_block", x=x, **out)
+
+
 def main(only=None):
     if not ref_shim.available():
         raise SystemExit("reference tree not found at %s" % ref_shim.REFERENCE_ROOT)
@@ -490,6 +521,8 @@ def main(only=None):
         return golden_interaction_machine(L)
     if only == "sasrec_gather":
         return golden_sasrec_gather()
+    if only == "mlp_block":
+        return golden_mlp_block(L)
     with tempfile.TemporaryDirectory() as tmp:
         golden_interaction(L)
         golden_pooling(L)
@@ -506,6 +539,7 @@ def main(only=None):
     golden_retrieval()
     golden_interaction_machine(L)
     golden_sasrec_gather()
+    golden_mlp_block(L)
 
 
 if __name__ == "__main__":

@@ -25,9 +25,9 @@ from ._lib import RbxError, build, load  # noqa: F401
 _RANKING = {"FeatureEmbedding": "FeatureEmbedding", "FeatureEmbeddingDict": "FeatureEmbeddingDict",
             "InnerProductInteraction": "InnerProductInteraction", "LogisticRegression": "LogisticRegression",
             "FactorizationMachine": "FactorizationMachine", "MaskedAveragePooling": "MaskedAveragePooling",
-            "MaskedSumPooling": "MaskedSumPooling", "InteractionMachine": "InteractionMachine"}
+            "MaskedSumPooling": "MaskedSumPooling", "InteractionMachine": "InteractionMachine", "MLP_Block": "MLP_Block"}
 _CORE = {"EmbeddingLayer": "EmbeddingLayer", "EmbeddingDictLayer": "EmbeddingDictLayer",
-         "MaskedAveragePooling": "CoreMaskedAveragePooling", "MaskedSumPooling": "CoreMaskedSumPooling"}
+         "MaskedAveragePooling": "CoreMaskedAveragePooling", "MaskedSumPooling": "CoreMaskedSumPooling", "MLP_Layer": "MLP_Layer"}
 _TARGETS = (("recbox.ranking.pytorch.layers", _RANKING), ("fuxictr.pytorch.layers", _RANKING),
             ("recbox.core.pytorch.layers", _CORE), ("recbox.matching.pytorch.layers", _CORE))
 _saved = []

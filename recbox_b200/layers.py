@@ -370,6 +370,166 @@ def sync_replica_gradients(params, group=None, average=False):
     return len(bufs)
 
 
+# =================================================================================================
+# a13: dense MLP tail on the tcgen05 GEMM (csrc/gemm.cu)
+# =================================================================================================
+class _MLPChainFn(torch.autograd.Function):
+    """A run of Linear (+ ReLU) layers as ONE autograd node: forward = one fused GEMM per layer (bias + ReLU in the
+    epilogue); backward = per layer dW = dZ^T H (split-K GEMM reading both operands as stored), db = column sums, and
+    dH = (dZ W) * (H_prev > 0) with the ReLU mask of the previous layer fused into the epilogue, so no elementwise pass
+    runs between the layers.  x: [M, K0]; args: relu flags, has-bias flags, then weight / bias tensors."""
+
+    @staticmethod
+    def forward(ctx, x, relus, *wb):
+        x2 = x.reshape(-1, x.shape[-1])
+        if not x2.is_contiguous():
+            x2 = x2.contiguous()
+        hs, ws, bs = [x2], [], []
+        it = iter(wb)
+        for relu in relus:
+            w, b = next(it), next(it)
+            ws.append(w)
+            bs.append(b)
+            hs.append(ops.gemm(hs[-1], w.detach(), bias=b.detach() if b is not None else None, relu=relu))
+        ctx.relus, ctx.n_out = tuple(relus), len(hs)
+        ctx.shape = x.shape
+        ctx.save_for_backward(*hs, *ws)
+        ctx.has_bias = [b is not None for b in bs]
+        return hs[-1].view(*x.shape[:-1], hs[-1].shape[-1])
+
+    @staticmethod
+    def backward(ctx, dy):
+        L = len(ctx.relus)
+        saved = ctx.saved_tensors
+        hs, ws = saved[:L + 1], saved[L + 1:]
+        dz = dy.reshape(-1, dy.shape[-1])
+        if not dz.is_contiguous():
+            dz = dz.contiguous()
+        if ctx.relus[-1]:
+            dz = dz * (hs[-1] > 0)                     # only when the chain ENDS in a ReLU (not the DeepFM / DNN shape)
+        grads = [None] * (2 * L)
+        dx = None
+        for l in range(L - 1, -1, -1):
+            need_w = ctx.needs_input_grad[2 + 2 * l]
+            need_b = ctx.has_bias[l] and ctx.needs_input_grad[3 + 2 * l]
+            if need_w:
+                grads[2 * l] = ops.gemm(dz, hs[l], a_mn=True, b_mn=True)           # dW [N, K] = dZ^T H
+            if need_b:
+                grads[2 * l + 1] = ops.colsum(dz)
+            if l > 0 or ctx.needs_input_grad[0]:
+                prev_relu = l > 0 and ctx.relus[l - 1]
+                dz = ops.gemm(dz, ws[l].detach(), b_mn=True, mask=hs[l] if prev_relu else None)   # dH = (dZ W) * (H > 0)
+                if l == 0:
+                    dx = dz.view(ctx.shape)
+        return (dx, None) + tuple(grads)
+
+
+def _mlp_forward(seq, x):
+    """nn.Sequential of MLP_Block / MLP_Layer: maximal runs of Linear (+ nn.ReLU) go through _MLPChainFn, every other
+    module (BatchNorm1d, Dropout, other activations) is called as it is."""
+    mods = list(seq)
+    i, n = 0, len(mods)
+    while i < n:
+        if type(mods[i]) is nn.Linear and x.is_cuda and x.dtype == F32:
+            relus, wb = [], []
+            while i < n and type(mods[i]) is nn.Linear:
+                lin = mods[i]
+                relu = i + 1 < n and type(mods[i + 1]) is nn.ReLU
+                relus.append(relu)
+                wb += [lin.weight, lin.bias]
+                i += 2 if relu else 1
+            x = _MLPChainFn.apply(x, tuple(relus), *wb)
+        elif type(mods[i]) is nn.Linear:
+            raise RbxError("MLP_Block: input must be an fp32 CUDA tensor (recbox_b200 has no CPU path)")
+        else:
+            x = mods[i](x)
+            i += 1
+    return x
+
+
+def _activation(act, units=None):
+    """fuxictr.pytorch.torch_utils.get_activation (ranking/pytorch/torch_utils.py:85-110) for the names the configs use."""
+    if isinstance(act, str):
+        low = act.lower()
+        if low == "relu":
+            return nn.ReLU()
+        if low == "sigmoid":
+            return nn.Sigmoid()
+        if low == "tanh":
+            return nn.Tanh()
+        if low == "softmax":
+            return nn.Softmax(dim=-1)
+        if low == "prelu":
+            return nn.PReLU(units, init=0.1)
+        return getattr(nn, act)()
+    return act
+
+
+class MLP_Block(nn.Module):
+    """Drop-in for ranking/pytorch/layers/blocks/mlp_block.py:23-61: same constructor, same `mlp` nn.Sequential (state_dict
+    keys mlp.<i>.weight / bias, default nn.Linear init order), forward through the fused GEMM chain."""
+
+    def __init__(self, input_dim, hidden_units=[], hidden_activations="ReLU", output_dim=None, output_activation=None,
+                 dropout_rates=0.0, batch_norm=False, norm_before_activation=True, use_bias=True):
+        super(MLP_Block, self).__init__()
+        dense_layers = []
+        if not isinstance(dropout_rates, list):
+            dropout_rates = [dropout_rates] * len(hidden_units)
+        if not isinstance(hidden_activations, list):
+            hidden_activations = [hidden_activations] * len(hidden_units)
+        hidden_activations = [_activation(a, u) for a, u in zip(hidden_activations, hidden_units)]
+        hidden_units = [input_dim] + list(hidden_units)
+        for idx in range(len(hidden_units) - 1):
+            dense_layers.append(nn.Linear(hidden_units[idx], hidden_units[idx + 1], bias=use_bias))
+            if norm_before_activation and batch_norm:
+                dense_layers.append(nn.BatchNorm1d(hidden_units[idx + 1]))
+            if hidden_activations[idx]:
+                dense_layers.append(hidden_activations[idx])
+            if not norm_before_activation and batch_norm:
+                dense_layers.append(nn.BatchNorm1d(hidden_units[idx + 1]))
+            if dropout_rates[idx] > 0:
+                dense_layers.append(nn.Dropout(p=dropout_rates[idx]))
+        if output_dim is not None:
+            dense_layers.append(nn.Linear(hidden_units[-1], output_dim, bias=use_bias))
+        if output_activation is not None:
+            dense_layers.append(_activation(output_activation))
+        self.mlp = nn.Sequential(*dense_layers)
+
+    def forward(self, inputs):
+        return _mlp_forward(self.mlp, inputs)
+
+
+class MLP_Layer(nn.Module):
+    """Drop-in for core/pytorch/layers/mlp.py:9-41 (the matching-side name and argument order of the same block)."""
+
+    def __init__(self, input_dim, output_dim=None, hidden_units=[], hidden_activations="ReLU", final_activation=None,
+                 dropout_rates=[], batch_norm=False, use_bias=True):
+        super(MLP_Layer, self).__init__()
+        dense_layers = []
+        if not isinstance(dropout_rates, list):
+            dropout_rates = [dropout_rates] * len(hidden_units)
+        if not isinstance(hidden_activations, list):
+            hidden_activations = [hidden_activations] * len(hidden_units)
+        hidden_activations = [_activation(a) for a in hidden_activations]
+        hidden_units = [input_dim] + list(hidden_units)
+        for idx in range(len(hidden_units) - 1):
+            dense_layers.append(nn.Linear(hidden_units[idx], hidden_units[idx + 1], bias=use_bias))
+            if batch_norm:
+                dense_layers.append(nn.BatchNorm1d(hidden_units[idx + 1]))
+            if hidden_activations[idx]:
+                dense_layers.append(hidden_activations[idx])
+            if dropout_rates[idx] > 0:
+                dense_layers.append(nn.Dropout(p=dropout_rates[idx]))
+        if output_dim is not None:
+            dense_layers.append(nn.Linear(hidden_units[-1], output_dim, bias=use_bias))
+        if final_activation is not None:
+            dense_layers.append(_activation(final_activation))
+        self.mlp = nn.Sequential(*dense_layers)
+
+    def forward(self, inputs):
+        return _mlp_forward(self.mlp, inputs)
+
+
 class _GatherFn(torch.autograd.Function):
     """Plain lookup [.., ] ids -> [.., D] (un-pooled sequence features, generic encoders)."""
 

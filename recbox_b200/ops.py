@@ -643,3 +643,49 @@ def rank_metrics(cand, train_ptr, train_items, valid_ptr, valid_items, kinds, ks
           _p(valid_ptr, I64, "valid_ptr"), _p(valid_items, I64, "valid_items"), kmax, _p(kd), _p(kk), M, _p(ranked), _p(hit),
           _p(out), _stream())
     return ranked, hit, out
+
+
+# ------------------------------------------------------------------------------------------- a13
+GEMM_PRECISION = 3       # 3 = 3xTF32 (fp32-level, the 1e-5 contract); 1 = plain TF32 (stated option, ~1e-3 rel)
+
+
+def _mat(t, name):
+    """2-D fp32 CUDA tensor whose rows are contiguous -> (pointer, pitch in floats)."""
+    if t.dim() != 2 or t.dtype != F32 or not t.is_cuda or (t.shape[1] > 1 and t.stride(1) != 1):
+        raise RbxError("%s must be a 2-D fp32 CUDA tensor with contiguous rows" % name)
+    _note_device(t.device, name)
+    return ctypes.c_void_p(t.data_ptr()), (t.stride(0) if t.shape[0] > 1 else max(t.shape[1], 1))
+
+
+def gemm(a, b, a_mn=False, b_mn=False, bias=None, relu=False, mask=None, out=None, accumulate=False, precision=None):
+    """out[M,N] (+)= relu?(A B^T + bias) * (mask > 0)?   (rbx_gemm_f32, tcgen05 tensor cores).
+    a: [M,K] (a_mn: stored [K,M]); b: [N,K] as nn.Linear.weight (b_mn: stored [K,N])."""
+    (M, K) = (a.shape[1], a.shape[0]) if a_mn else a.shape
+    (N, Kb) = (b.shape[1], b.shape[0]) if b_mn else b.shape
+    if K != Kb:
+        raise RbxError("gemm: inner dimensions differ (%d vs %d)" % (K, Kb))
+    if out is None:
+        out = torch.empty((M, N), dtype=F32, device=a.device)
+        accumulate = False
+    elif tuple(out.shape) != (M, N):
+        raise RbxError("gemm: out must be [%d, %d]" % (M, N))
+    if mask is not None and tuple(mask.shape) != (M, N):
+        raise RbxError("gemm: mask must be [%d, %d]" % (M, N))
+    pa, lda = _mat(a, "a")
+    pb, ldb = _mat(b, "b")
+    pc, ldc = _mat(out, "out")
+    pm, ldm = _mat(mask, "mask") if mask is not None else (None, 0)
+    _call("rbx_gemm_f32", pa, lda, 1 if a_mn else 0, pb, ldb, 1 if b_mn else 0, pc, ldc, M, N, K, _p(bias, F32, "bias"), 1 if relu else 0,
+          pm, ldm, int(precision or GEMM_PRECISION), 1 if accumulate else 0, _stream())
+    return out
+
+
+def colsum(x, out=None, accumulate=False):
+    """out[n] (+)= sum_m x[m, n]  (bias gradient)."""
+    M, N = x.shape
+    if out is None:
+        out = torch.empty((N,), dtype=F32, device=x.device)
+        accumulate = False
+    px, ldx = _mat(x, "x")
+    _call("rbx_colsum_f32", px, ldx, _p(out, F32, "out"), M, N, 1 if accumulate else 0, _stream())
+    return out

@@ -175,21 +175,10 @@ def test_pooling_modules_on_materialised_tensor():
     assert_close(emb.grad, ref.grad, what="pool grad")
 
 
-class _MLP(nn.Module):
-    """MLP_Block(hidden_units, ReLU, output_dim=1) of blocks/mlp_block.py:23-61 with the reference's
-    parameter names (mlp.0, mlp.2, ...): the dense tail is a true GEMM and stays on cuBLAS."""
-
-    def __init__(self, input_dim, hidden):
-        super().__init__()
-        mods, d = [], input_dim
-        for h in hidden:
-            mods += [nn.Linear(d, h), nn.ReLU()]
-            d = h
-        mods.append(nn.Linear(d, 1))
-        self.mlp = nn.Sequential(*mods)
-
-    def forward(self, x):
-        return self.mlp(x)
+def _MLP(input_dim, hidden):
+    """MLP_Block(hidden_units, ReLU, output_dim=1) of blocks/mlp_block.py:23-61 (parameter names mlp.0, mlp.2, ...): the fused
+    tcgen05 GEMM chain of csrc/gemm.cu behind the reference's constructor."""
+    return layers.MLP_Block(input_dim=input_dim, hidden_units=list(hidden), hidden_activations="ReLU", output_dim=1)
 
 
 class _DeepFM(nn.Module):
@@ -321,3 +310,30 @@ def test_sasrec_lookups_and_token_dots_match_rechub():
     for k, name in ((1, "pos_logits"), (2, "neg_logits")):
         y = ops.rowdot_fwd(so, emb[:, k].reshape(B * L, 1, D).contiguous())
         assert_close(y.view(B, L), g[name], atol_scale=2e-5, what=name)
+
+
+@pytest.mark.parametrize("tag", ["plain", "mixed", "nohead", "core"])
+def test_mlp_block_matches_reference(tag):
+    """a13: our MLP_Block / MLP_Layer (Linear layers on the tcgen05 GEMM chain, bias + ReLU + ReLU-mask fused) against the
+    outputs and gradients of the reference's own modules on the same seeded init and input (tests/golden/mlp_block.npz)."""
+    g = load("mlp_block")
+    mk = {"plain": lambda: layers.MLP_Block(input_dim=104, hidden_units=[96, 48], hidden_activations="ReLU", output_dim=1),
+          "mixed": lambda: layers.MLP_Block(input_dim=104, hidden_units=[64, 32], hidden_activations=["relu", "tanh"], output_dim=1,
+                                            output_activation="sigmoid", batch_norm=True, use_bias=False),
+          "nohead": lambda: layers.MLP_Block(input_dim=104, hidden_units=[48], hidden_activations="ReLU"),
+          "core": lambda: layers.MLP_Layer(input_dim=104, output_dim=1, hidden_units=[32, 16], hidden_activations="ReLU",
+                                           final_activation=None, dropout_rates=[0.0, 0.0])}[tag]
+    torch.manual_seed(5)
+    m = mk()
+    init = _sub(g, tag + ".init.")
+    assert sorted(m.state_dict()) == sorted(init)
+    for k, v in m.state_dict().items():          # same constructor, same seed -> the reference's own initial weights
+        assert torch.equal(v, init[k]), k
+    m.to(DEV).train()
+    x = g["x"].to(DEV).requires_grad_(True)
+    y = m(x)
+    assert_close(y, g[tag + ".y"], rtol=1e-5, atol_scale=1e-5, what="y")
+    (y * g[tag + ".w"].to(DEV)).sum().backward()
+    assert_close(x.grad, g[tag + ".dx"], rtol=1e-5, atol_scale=1e-5, what="dx")
+    for k, p in m.named_parameters():
+        assert_close(p.grad, g["%s.grad.%s" % (tag, k)], rtol=1e-5, atol_scale=1e-5, what=k)

@@ -239,3 +239,24 @@ def test_refused_store_invalidates_cached_plans_and_survives_pickle():
     g = next(iter(d2._store.groups.values()))
     assert all(id(m) in g.emb_off for m in g.emb)
     assert copy.deepcopy(emb).state_dict().keys() == emb.state_dict().keys()
+
+
+def test_mlp_block_constructor_matches_reference_init():
+    """a13 host side: same constructor arguments, same `mlp` Sequential (state_dict keys), same RNG call order as the
+    reference's MLP_Block / MLP_Layer (golden minted from the reference under torch.manual_seed(5))."""
+    from test_oracle_golden import load
+    g = load("mlp_block")
+    cases = {"plain": lambda: layers.MLP_Block(input_dim=104, hidden_units=[96, 48], hidden_activations="ReLU", output_dim=1),
+             "mixed": lambda: layers.MLP_Block(input_dim=104, hidden_units=[64, 32], hidden_activations=["relu", "tanh"], output_dim=1,
+                                               output_activation="sigmoid", batch_norm=True, use_bias=False),
+             "core": lambda: layers.MLP_Layer(input_dim=104, output_dim=1, hidden_units=[32, 16], hidden_activations="ReLU",
+                                              final_activation=None, dropout_rates=[0.0, 0.0])}
+    for tag, mk in cases.items():
+        torch.manual_seed(5)
+        m = mk()
+        want = {k[len(tag) + 6:]: v for k, v in g.items() if k.startswith(tag + ".init.")}
+        assert sorted(m.state_dict()) == sorted(want)
+        for k, v in m.state_dict().items():
+            assert torch.equal(v, want[k]), (tag, k)
+    with pytest.raises(layers.RbxError):              # no CPU path for the Linear layers either
+        cases["plain"]()(torch.zeros(2, 104))

@@ -357,3 +357,19 @@ def test_inbatch_scores_and_mlp_restatements():
     W1, b1, W2, b2 = torch.randn(6, 4, generator=g), torch.randn(6, generator=g), torch.randn(1, 6, generator=g), torch.randn(1, generator=g)
     want = torch.relu(x @ W1.t() + b1) @ W2.t() + b2
     assert torch.allclose(oracle.mlp(x, [(W1, b1), (W2, b2)]), want, atol=1e-6)
+
+
+def test_mlp_restatement_matches_reference_mlp_block():
+    """a13: oracle.mlp (ReLU hidden layers, linear head) against the reference's own MLP_Block / MLP_Layer outputs."""
+    g = load("mlp_block")
+    for tag, idx in (("plain", (0, 2, 4)), ("core", (0, 2, 4))):
+        layers_ = [(g["%s.init.mlp.%d.weight" % (tag, i)], g["%s.init.mlp.%d.bias" % (tag, i)]) for i in idx]
+        x = g["x"].clone().requires_grad_(True)
+        ws = [(W.clone().requires_grad_(True), b.clone().requires_grad_(True)) for W, b in layers_]
+        y = oracle.mlp(x, ws)
+        assert torch.allclose(y, g[tag + ".y"], rtol=1e-6, atol=1e-6)
+        (y * g[tag + ".w"]).sum().backward()
+        assert torch.allclose(x.grad, g[tag + ".dx"], rtol=1e-5, atol=1e-6)
+        for (W, b), i in zip(ws, idx):
+            assert torch.allclose(W.grad, g["%s.grad.mlp.%d.weight" % (tag, i)], rtol=1e-5, atol=1e-6)
+            assert torch.allclose(b.grad, g["%s.grad.mlp.%d.bias" % (tag, i)], rtol=1e-5, atol=1e-6)
