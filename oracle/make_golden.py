@@ -508,6 +508,49 @@ def golden_mlp_block(L):
     npz("mlp_block", x=x, **out)
 
 
+def golden_blocks(L):
+    """f4: the GEMM-shaped consumers of [B, F, D] -- the reference's own CrossNet / CrossNetV2 / CompressedInteractionNet /
+    DIN_Attention / MultiHeadTargetAttention: seeded init, forward, gradients of every parameter and input."""
+    out = {}
+    g = torch.Generator().manual_seed(91)
+    B, F_, D = 48, 6, 8
+    E = torch.randn(B, F_, D, generator=g)
+    flat = E.flatten(1)                                  # [B, 48]
+    target = torch.randn(B, D, generator=g)
+    hist = torch.randn(B, 7, D, generator=g)
+    mask = (torch.rand(B, 7, generator=g) > 0.3).float()
+    mask[:, 0] = 1.0
+    out.update(E=E, target=target, hist=hist, mask=mask)
+    cases = {
+        "crossnet": (lambda: L.CrossNet(F_ * D, 2), lambda m, a: m(a[0]), [flat]),
+        "crossnetv2": (lambda: L.CrossNetV2(F_ * D, 3), lambda m, a: m(a[0]), [flat]),
+        "cin": (lambda: L.CompressedInteractionNet(F_, [8, 4], output_dim=1), lambda m, a: m(a[0]), [E]),
+        "din": (lambda: L.DIN_Attention(embedding_dim=D, attention_units=[16], hidden_activations="ReLU"),
+                lambda m, a: m(a[0], a[1], mask), [target, hist]),
+        "din_softmax": (lambda: L.DIN_Attention(embedding_dim=D, attention_units=[16, 8], hidden_activations="ReLU", use_softmax=True),
+                        lambda m, a: m(a[0], a[1], mask), [target, hist]),
+        "mhta": (lambda: L.MultiHeadTargetAttention(input_dim=D, attention_dim=16, num_heads=2),
+                 lambda m, a: m(a[0], a[1], mask), [target, hist]),
+    }
+    for tag, (mk, call, args) in cases.items():
+        torch.manual_seed(11)
+        m = mk()
+        for p in m.parameters():                         # biases start at zero in some of these: make every term count
+            if p.dim() == 1:
+                with torch.no_grad():
+                    p.add_(torch.randn(p.shape, generator=g) * 0.1)
+        out.update({k: v.clone() for k, v in sd_arrays(m, tag + ".init.").items()})
+        ins = [a.clone().requires_grad_(True) for a in args]
+        y = call(m, ins)
+        w = torch.randn(y.shape, generator=torch.Generator().manual_seed(12))
+        (y * w).sum().backward()
+        out[tag + ".y"], out[tag + ".w"] = y, w
+        for i, a in enumerate(ins):
+            out["%s.din%d" % (tag, i)] = a.grad
+        out.update(grads_of(m, tag + ".grad."))
+    npz("blocks", **out)
+
+
 def main(only=None):
     if not ref_shim.available():
         raise SystemExit("reference tree not found at %s" % ref_shim.REFERENCE_ROOT)
@@ -523,6 +566,8 @@ def main(only=None):
         return golden_sasrec_gather()
     if only == "mlp_block":
         return golden_mlp_block(L)
+    if only == "blocks":
+        return golden_blocks(L)
     with tempfile.TemporaryDirectory() as tmp:
         golden_interaction(L)
         golden_pooling(L)
@@ -540,6 +585,7 @@ def main(only=None):
     golden_interaction_machine(L)
     golden_sasrec_gather()
     golden_mlp_block(L)
+    golden_blocks(L)
 
 
 if __name__ == "__main__":

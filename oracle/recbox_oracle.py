@@ -249,6 +249,66 @@ def mlp(x, layers):
 
 
 # --------------------------------------------------------------------------------------------
+# f4  GEMM-shaped consumers of [B, F, D]
+# --------------------------------------------------------------------------------------------
+def cross_net_v2(x0, layers):
+    """recbox/ranking/pytorch/layers/interactions/cross_net.py:48-59: X_{i+1} = X_i + X_0 * (W_i X_i + b_i)."""
+    xi = x0
+    for W, b in layers:
+        xi = xi + x0 * F.linear(xi, W, b)
+    return xi
+
+
+def cross_net(x0, layers):
+    """cross_net.py:23-45: X_{i+1} = X_i + (w_i . X_i) X_0 + b_i; layers = [(w [1, d], b [d]), ...]."""
+    xi = x0
+    for w, b in layers:
+        xi = xi + (F.linear(xi, w) * x0 + b)
+    return xi
+
+
+def cin(E, convs, fc):
+    """compressed_interaction_net.py:35-48: outer product over the field axes, 1x1 convolution over the H*M channels,
+    sum-pool over the embedding dim, Linear over the concatenated pools.  convs = [(W [out, H*M], b [out])], fc = (W, b)."""
+    B, _, D = E.shape
+    x0, xi, pools = E, E, []
+    for W, b in convs:
+        had = torch.einsum("bhd,bmd->bhmd", x0, xi).reshape(B, -1, D)
+        xi = torch.einsum("oc,bcd->bod", W, had) + b.view(1, -1, 1)
+        pools.append(xi.sum(dim=-1))
+    return F.linear(torch.cat(pools, dim=-1), fc[0], fc[1])
+
+
+def din_attention(target, hist, mask, mlp_layers, use_softmax=False):
+    """ranking/pytorch/layers/attentions/target_attention.py:47-66 with a ReLU scoring MLP (layers as in `mlp`)."""
+    L = hist.shape[1]
+    t = target.unsqueeze(1).expand(-1, L, -1)
+    a = torch.cat([t, hist, t - hist, t * hist], dim=-1)
+    w = mlp(a.reshape(-1, a.shape[-1]), mlp_layers).view(-1, L)
+    if mask is not None:
+        w = w * mask.float()
+    if use_softmax:
+        if mask is not None:
+            w = w + -1.e9 * (1 - mask.float())
+        w = w.softmax(dim=-1)
+    return (w.unsqueeze(-1) * hist).sum(dim=1)
+
+
+def multi_head_target_attention(target, hist, mask, Wq, Wk, Wv, Wo, num_heads):
+    """target_attention.py:92-121 (use_qkvo, use_scale): one query per sample against its history."""
+    B, L, _ = hist.shape
+    hd = Wq.shape[0] // num_heads
+    q = F.linear(target, Wq).view(B, 1, num_heads, hd).transpose(1, 2)
+    k = F.linear(hist, Wk).view(B, L, num_heads, hd).transpose(1, 2)
+    v = F.linear(hist, Wv).view(B, L, num_heads, hd).transpose(1, 2)
+    scores = torch.matmul(q, k.transpose(-1, -2)) / hd ** 0.5
+    if mask is not None:
+        scores = scores.masked_fill(mask.view(B, 1, 1, L).expand(-1, num_heads, -1, -1).float() == 0, -1.e9)
+    out = torch.matmul(scores.softmax(dim=-1), v).transpose(1, 2).reshape(B, num_heads * hd)
+    return F.linear(out, Wo)
+
+
+# --------------------------------------------------------------------------------------------
 # a12  clip + optimizer
 # --------------------------------------------------------------------------------------------
 def clip_grad_norm(grads, max_norm):

@@ -25,7 +25,10 @@ from ._lib import RbxError, build, load  # noqa: F401
 _RANKING = {"FeatureEmbedding": "FeatureEmbedding", "FeatureEmbeddingDict": "FeatureEmbeddingDict",
             "InnerProductInteraction": "InnerProductInteraction", "LogisticRegression": "LogisticRegression",
             "FactorizationMachine": "FactorizationMachine", "MaskedAveragePooling": "MaskedAveragePooling",
-            "MaskedSumPooling": "MaskedSumPooling", "InteractionMachine": "InteractionMachine", "MLP_Block": "MLP_Block"}
+            "MaskedSumPooling": "MaskedSumPooling", "InteractionMachine": "InteractionMachine", "MLP_Block": "MLP_Block",
+            "CrossInteraction": "CrossInteraction", "CrossNet": "CrossNet", "CrossNetV2": "CrossNetV2",
+            "CompressedInteractionNet": "CompressedInteractionNet", "ScaledDotProductAttention": "ScaledDotProductAttention",
+            "DIN_Attention": "DIN_Attention", "MultiHeadTargetAttention": "MultiHeadTargetAttention"}
 _CORE = {"EmbeddingLayer": "EmbeddingLayer", "EmbeddingDictLayer": "EmbeddingDictLayer",
          "MaskedAveragePooling": "CoreMaskedAveragePooling", "MaskedSumPooling": "CoreMaskedSumPooling", "MLP_Layer": "MLP_Layer"}
 _TARGETS = (("recbox.ranking.pytorch.layers", _RANKING), ("fuxictr.pytorch.layers", _RANKING),
@@ -38,7 +41,10 @@ def install(import_reference=True):
     with import_reference, importable) reference module.  Returns the list of (module, attribute)
     pairs that were rebound.  Idempotent; `uninstall()` restores the originals."""
     import importlib
-    from . import layers as ours
+    from . import blocks, layers as ours
+    for name in blocks.__all__:                       # the GEMM-shaped consumers live in blocks.py
+        if not hasattr(ours, name):
+            setattr(ours, name, getattr(blocks, name))
     done = []
     for prefix, table in _TARGETS:
         if import_reference and prefix not in sys.modules:

@@ -373,3 +373,26 @@ def test_mlp_restatement_matches_reference_mlp_block():
         for (W, b), i in zip(ws, idx):
             assert torch.allclose(W.grad, g["%s.grad.mlp.%d.weight" % (tag, i)], rtol=1e-5, atol=1e-6)
             assert torch.allclose(b.grad, g["%s.grad.mlp.%d.bias" % (tag, i)], rtol=1e-5, atol=1e-6)
+
+
+def test_f4_block_restatements_match_reference():
+    """f4: CrossNet / CrossNetV2 / CIN / DIN attention / multi-head target attention restated in the oracle against the
+    outputs of the reference's own modules (tests/golden/blocks.npz)."""
+    g = load("blocks")
+    E, target, hist, mask = g["E"], g["target"], g["hist"], g["mask"]
+    flat = E.flatten(1)
+    p = lambda tag, k: g["%s.init.%s" % (tag, k)]
+    y = oracle.cross_net_v2(flat, [(p("crossnetv2", "cross_layers.%d.weight" % i), p("crossnetv2", "cross_layers.%d.bias" % i)) for i in range(3)])
+    assert torch.allclose(y, g["crossnetv2.y"], rtol=1e-5, atol=1e-6)
+    y = oracle.cross_net(flat, [(p("crossnet", "cross_net.%d.weight.weight" % i), p("crossnet", "cross_net.%d.bias" % i)) for i in range(2)])
+    assert torch.allclose(y, g["crossnet.y"], rtol=1e-5, atol=1e-6)
+    convs = [(p("cin", "cin_layer.layer_%d.weight" % i).squeeze(-1), p("cin", "cin_layer.layer_%d.bias" % i)) for i in (1, 2)]
+    y = oracle.cin(E, convs, (p("cin", "fc.weight"), p("cin", "fc.bias")))
+    assert torch.allclose(y, g["cin.y"], rtol=1e-5, atol=1e-5)
+    for tag, idx, sm in (("din", (0, 2), False), ("din_softmax", (0, 2, 4), True)):
+        ls = [(p(tag, "attention_layer.mlp.%d.weight" % i), p(tag, "attention_layer.mlp.%d.bias" % i)) for i in idx]
+        y = oracle.din_attention(target, hist, mask, ls, use_softmax=sm)
+        assert torch.allclose(y, g[tag + ".y"], rtol=1e-5, atol=1e-6), tag
+    y = oracle.multi_head_target_attention(target, hist, mask, p("mhta", "W_q.weight"), p("mhta", "W_k.weight"), p("mhta", "W_v.weight"),
+                                           p("mhta", "W_o.weight"), 2)
+    assert torch.allclose(y, g["mhta.y"], rtol=1e-5, atol=1e-6)
