@@ -49,7 +49,20 @@ struct GemmArgs {
     uint32_t a_boxes, b_boxes;        // TMA boxes per tile (1 for K-major, tile/32 for MN-major)
     uint32_t a_box_bytes, b_box_bytes;
     int write_hi;                     // debug: also overwrite the raw tile with the masked hi words
+    // top-k filter epilogue (f3): scores above the row's running k-th best go to the row's candidate queue, nothing else is stored
+    int filter;
+    const float* tau;                 // [M]
+    int* count;                       // [M]
+    unsigned long long* queue;        // [M, qcap]
+    int64_t qcap, col_off;
 };
+
+// sortable 64-bit key of (score, item): larger = better, ties to the smaller index (same encoding as csrc/topk.cu)
+__device__ __forceinline__ unsigned long long topk_key(float score, uint32_t idx) {
+    const uint32_t b = __float_as_uint(score);
+    const uint32_t f = (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+    return ((unsigned long long)f << 32) | (unsigned long long)(0xffffffffu - idx);
+}
 
 // ---- raw PTX wrappers ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -236,10 +249,23 @@ __global__ void __launch_bounds__(kThreads, 1) k_gemm_tc(const __grid_constant__
         const bool vec_ok = ((p.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0) &&
                             (!p.mask || (((p.ldmask & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.mask) & 15) == 0)));
         const bool first_split = blockIdx.z == 0;
+        const float tau = (p.filter && row_ok) ? __ldcg(p.tau + row) : __int_as_float(0x7f800000);
         for (int c = 0; c < p.BN; c += 16) {
             uint32_t r[16];
             tc_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, r);
             if (!row_ok) continue;
+            if (p.filter) {
+#pragma unroll
+                for (int e = 0; e < 16; ++e) {
+                    const float sc = __uint_as_float(r[e]);
+                    const int col = n0 + c + e;
+                    if (sc > tau && col < p.N) {
+                        const int pos = atomicAdd(p.count + row, 1);
+                        if (pos < p.qcap) p.queue[(size_t)row * p.qcap + pos] = topk_key(sc, (uint32_t)(p.col_off + col));
+                    }
+                }
+                continue;
+            }
 #pragma unroll
             for (int g = 0; g < 4; ++g) {
                 const int col = n0 + c + 4 * g;
@@ -417,7 +443,109 @@ int env_int(const char* name, int dflt) {
     return s && *s ? atoi(s) : dflt;
 }
 
+// Fills tile shape, descriptors and tensor maps of `g` (epilogue fields already set) and launches k_gemm_tc.
+// bn_force / kb_force / max_stages = 0: chosen here.  allow_split: split-K (red.add epilogue) when the output has too few tiles.
+int launch_tc(const char* who, GemmArgs& g, const float* A, int64_t lda, const float* B, int64_t ldb, int64_t M, int64_t N, int64_t K,
+              int bn_force, int kb_force, int max_stages, bool allow_split, int accumulate, cudaStream_t st) {
+    const int sms = rbx_sm_count();
+    const int precision = g.prec;
+    g.M = (int)M; g.N = (int)N; g.K = (int)K;
+    g.write_hi = env_int("RBX_GEMM_WRITE_HI", 0);
+    // tile width: the fewest tiles that cover N, then the narrowest such tile (N = 400 -> 2 x 208; 624 -> 3 x 208)
+    const int gran = g.b_mn ? 32 : 16;
+    int tiles_n = (int)((N + 255) / 256);
+    int BN = (int)(((N + tiles_n - 1) / tiles_n + gran - 1) / gran * gran);
+    if (BN < 16) BN = 16;
+    if (bn_force) BN = bn_force;
+    if (int f = env_int("RBX_GEMM_BN", 0)) BN = f;
+    RBX_REQUIRE(BN >= 16 && BN <= 256 && BN % gran == 0, "%s: tile width %d not supported", who, BN);
+    tiles_n = (int)((N + BN - 1) / BN);
+    const int tiles_m = (int)((M + kBM - 1) / kBM);
+    RBX_REQUIRE(tiles_m <= 65535, "%s: M too large for one launch", who);
+    g.BN = BN;
+    int KB = kb_force ? kb_force : env_int("RBX_GEMM_KB", 0);
+    if (KB != 16 && KB != 32) KB = (precision == 3 && BN > 128) ? 16 : 32;
+    g.KB = KB;
+    g.kb_total = (int)((K + KB - 1) / KB);
+    int splits = 1;
+    if (allow_split && tiles_m * tiles_n * 2 <= sms) {
+        splits = sms / (tiles_m * tiles_n);
+        if (splits > g.kb_total / 4) splits = g.kb_total / 4;
+        if (splits < 1) splits = 1;
+    }
+    if (int f = env_int("RBX_GEMM_SPLITS", 0)) splits = allow_split ? f : 1;
+    g.kb_per_split = (g.kb_total + splits - 1) / splits;
+    splits = (g.kb_total + g.kb_per_split - 1) / g.kb_per_split;
+    g.atomic = (splits > 1 || accumulate) ? 1 : 0;
+    if (splits > 1 && !accumulate) {
+        cudaError_t e = cudaMemset2DAsync(g.C, (size_t)g.ldc * 4, 0, (size_t)N * 4, (size_t)M, st);
+        if (e != cudaSuccess) return rbx_fail(RBX_ERR_CUDA, "%s: memset: %s", who, cudaGetErrorString(e));
+    }
+    g.a_bytes = (uint32_t)(kBM * KB * 4);
+    g.b_bytes = (uint32_t)(BN * KB * 4);
+    const uint32_t stage_bytes = (precision == 3 ? 2u : 1u) * (g.a_bytes + g.b_bytes);
+    const uint32_t bar_bytes = 8u * (3 * kMaxStages + 2);
+    int stages = (int)((227u * 1024u - 1024u - bar_bytes) / stage_bytes);
+    if (stages > kMaxStages) stages = kMaxStages;
+    if (max_stages && stages > max_stages) stages = max_stages;
+    if (int f = env_int("RBX_GEMM_STAGES", 0)) stages = f < stages ? f : stages;
+    if (stages > g.kb_per_split) stages = g.kb_per_split < 2 ? 2 : g.kb_per_split;      // no deeper than the k loop
+    RBX_REQUIRE(stages >= 2, "%s: tile does not fit shared memory", who);
+    g.stages = stages;
+    const size_t smem = (size_t)stages * stage_bytes + bar_bytes + 1024;
+    uint32_t cols = 32;
+    while (cols < (uint32_t)BN) cols <<= 1;
+    g.tmem_cols = cols;
+    g.idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)g.a_mn << 15) | ((uint32_t)g.b_mn << 16) | ((uint32_t)(BN >> 3) << 17) |
+              ((uint32_t)(kBM >> 4) << 24);
+    // shared-memory matrix descriptors (version 1 in bits [46,48), swizzle mode in bits [61,64))
+    const CUtensorMapSwizzle k_sw = KB == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+    const uint32_t k_layout = KB == 32 ? 2u : 4u;
+    auto desc_hi = [](uint32_t sbo_bytes, uint32_t layout) { return ((sbo_bytes >> 4) & 0x3fffu) | (1u << 14) | (layout << 29); };
+    if (g.a_mn) {       // [KB k-rows][32 m] boxes, 128 B rows, SWIZZLE_128B: LBO = box pitch, SBO = 8 k-rows = 1024 B
+        g.a_boxes = kBM / 32; g.a_box_bytes = (uint32_t)(KB * 128);
+        g.a_desc_hi = desc_hi(1024, 2); g.a_lbo_sbo = ((g.a_box_bytes >> 4) & 0x3fffu) << 16; g.a_kstep = 1024 >> 4;
+        if (int rc = make_map(&g.ta, A, M, K, lda, 32, KB, CU_TENSOR_MAP_SWIZZLE_128B, who)) return rc;
+    } else {            // [128 rows][KB k] one box, rows of KB*4 B: SBO = 8 rows
+        g.a_boxes = 1; g.a_box_bytes = g.a_bytes;
+        g.a_desc_hi = desc_hi((uint32_t)(8 * KB * 4), k_layout); g.a_lbo_sbo = 1u << 16; g.a_kstep = 32 >> 4;
+        if (int rc = make_map(&g.ta, A, K, M, lda, KB, kBM, k_sw, who)) return rc;
+    }
+    if (g.b_mn) {
+        g.b_boxes = (uint32_t)(BN / 32); g.b_box_bytes = (uint32_t)(KB * 128);
+        g.b_desc_hi = desc_hi(1024, 2); g.b_lbo_sbo = ((g.b_box_bytes >> 4) & 0x3fffu) << 16; g.b_kstep = 1024 >> 4;
+        if (int rc = make_map(&g.tb, B, N, K, ldb, 32, KB, CU_TENSOR_MAP_SWIZZLE_128B, who)) return rc;
+    } else {
+        g.b_boxes = 1; g.b_box_bytes = g.b_bytes;
+        g.b_desc_hi = desc_hi((uint32_t)(8 * KB * 4), k_layout); g.b_lbo_sbo = 1u << 16; g.b_kstep = 32 >> 4;
+        if (int rc = make_map(&g.tb, B, K, N, ldb, KB, BN, k_sw, who)) return rc;
+    }
+    static bool attr_set[64];
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev >= 0 && dev < 64 && !attr_set[dev]) {
+        cudaError_t e = cudaFuncSetAttribute(k_gemm_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e != cudaSuccess) return rbx_fail(RBX_ERR_CUDA, "%s: cudaFuncSetAttribute: %s", who, cudaGetErrorString(e));
+        attr_set[dev] = true;
+    }
+    k_gemm_tc<<<dim3(tiles_n, tiles_m, splits), kThreads, smem, st>>>(g);
+    RBX_LAUNCH_CHECK(who);
+    return RBX_OK;
+}
+
 }  // namespace
+
+// f3 pass A on the tensor cores (called from csrc/topk.cu): scores of users [0, U) against items [n0, n1) as a 3xTF32 GEMM
+// whose epilogue keeps only what beats the user's running k-th best.  Two 48 KB stages per CTA, so two CTAs share an SM and
+// one tile's loads / filter epilogue run under the other's MMAs.
+int rbx_topk_filter_tc(const float* q, const float* items, int64_t U, int64_t n0, int64_t n1, int D, const float* tau, int* count,
+                       unsigned long long* queue, int64_t qcap, cudaStream_t st) {
+    GemmArgs g;
+    memset(&g, 0, sizeof(g));
+    g.prec = 3;
+    g.filter = 1; g.tau = tau; g.count = count; g.queue = queue; g.qcap = qcap; g.col_off = n0;
+    return launch_tc("rbx_topk_ip", g, q, D, items + (size_t)n0 * D, D, U, n1 - n0, D, 256, 16, 2, false, 0, st);
+}
 
 extern "C" {
 
@@ -479,87 +607,8 @@ int rbx_gemm_f32(const float* A, int64_t lda, int a_mn, const float* B, int64_t 
     GemmArgs g;
     memset(&g, 0, sizeof(g));
     g.C = C; g.bias = bias; g.mask = mask; g.ldc = ldc; g.ldmask = ldmask;
-    g.M = (int)M; g.N = (int)N; g.K = (int)K;
     g.a_mn = a_mn ? 1 : 0; g.b_mn = b_mn ? 1 : 0; g.prec = precision; g.act = act;
-    g.write_hi = env_int("RBX_GEMM_WRITE_HI", 0);
-    // tile width: the fewest tiles that cover N, then the narrowest such tile (N = 400 -> 2 x 208; 624 -> 3 x 208)
-    const int gran = g.b_mn ? 32 : 16;
-    int tiles_n = (int)((N + 255) / 256);
-    int BN = (int)(((N + tiles_n - 1) / tiles_n + gran - 1) / gran * gran);
-    if (BN < 16) BN = 16;
-    if (int f = env_int("RBX_GEMM_BN", 0)) BN = f;
-    RBX_REQUIRE(BN >= 16 && BN <= 256 && BN % gran == 0, "%s: tile width %d not supported", who, BN);
-    tiles_n = (int)((N + BN - 1) / BN);
-    const int tiles_m = (int)((M + kBM - 1) / kBM);
-    g.BN = BN;
-    int KB = env_int("RBX_GEMM_KB", 0);
-    if (KB != 16 && KB != 32) KB = (precision == 3 && BN > 128) ? 16 : 32;
-    g.KB = KB;
-    g.kb_total = (int)((K + KB - 1) / KB);
-    // split-K when the output has too few tiles to fill the machine (dW: reduction over the batch)
-    int splits = 1;
-    const bool can_split = act == 0 && !mask;
-    if (can_split && tiles_m * tiles_n * 2 <= sms) {
-        splits = sms / (tiles_m * tiles_n);
-        if (splits > g.kb_total / 4) splits = g.kb_total / 4;
-        if (splits < 1) splits = 1;
-    }
-    if (int f = env_int("RBX_GEMM_SPLITS", 0)) splits = can_split ? f : 1;
-    g.kb_per_split = (g.kb_total + splits - 1) / splits;
-    splits = (g.kb_total + g.kb_per_split - 1) / g.kb_per_split;
-    g.atomic = (splits > 1 || accumulate) ? 1 : 0;
-    if (splits > 1 && !accumulate) {
-        cudaError_t e = cudaMemset2DAsync(C, (size_t)ldc * 4, 0, (size_t)N * 4, (size_t)M, st);
-        if (e != cudaSuccess) return rbx_fail(RBX_ERR_CUDA, "%s: memset: %s", who, cudaGetErrorString(e));
-    }
-    g.a_bytes = (uint32_t)(kBM * KB * 4);
-    g.b_bytes = (uint32_t)(BN * KB * 4);
-    const uint32_t stage_bytes = (precision == 3 ? 2u : 1u) * (g.a_bytes + g.b_bytes);
-    const uint32_t bar_bytes = 8u * (3 * kMaxStages + 2);
-    int stages = (int)((227u * 1024u - 1024u - bar_bytes) / stage_bytes);
-    if (stages > kMaxStages) stages = kMaxStages;
-    if (int f = env_int("RBX_GEMM_STAGES", 0)) stages = f < stages ? f : stages;
-    RBX_REQUIRE(stages >= 2, "%s: tile does not fit shared memory", who);
-    g.stages = stages;
-    const size_t smem = (size_t)stages * stage_bytes + bar_bytes + 1024;
-    uint32_t cols = 32;
-    while (cols < (uint32_t)BN) cols <<= 1;
-    g.tmem_cols = cols;
-    g.idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)g.a_mn << 15) | ((uint32_t)g.b_mn << 16) | ((uint32_t)(BN >> 3) << 17) |
-              ((uint32_t)(kBM >> 4) << 24);
-    // shared-memory matrix descriptors (version 1 in bits [46,48), swizzle mode in bits [61,64))
-    const CUtensorMapSwizzle k_sw = KB == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
-    const uint32_t k_layout = KB == 32 ? 2u : 4u;
-    auto desc_hi = [](uint32_t sbo_bytes, uint32_t layout) { return ((sbo_bytes >> 4) & 0x3fffu) | (1u << 14) | (layout << 29); };
-    if (g.a_mn) {       // [KB k-rows][32 m] boxes, 128 B rows, SWIZZLE_128B: LBO = box pitch, SBO = 8 k-rows = 1024 B
-        g.a_boxes = kBM / 32; g.a_box_bytes = (uint32_t)(KB * 128);
-        g.a_desc_hi = desc_hi(1024, 2); g.a_lbo_sbo = ((g.a_box_bytes >> 4) & 0x3fffu) << 16; g.a_kstep = 1024 >> 4;
-        if (int rc = make_map(&g.ta, A, M, K, lda, 32, KB, CU_TENSOR_MAP_SWIZZLE_128B, who)) return rc;
-    } else {            // [128 rows][KB k] one box, rows of KB*4 B: SBO = 8 rows
-        g.a_boxes = 1; g.a_box_bytes = g.a_bytes;
-        g.a_desc_hi = desc_hi((uint32_t)(8 * KB * 4), k_layout); g.a_lbo_sbo = 1u << 16; g.a_kstep = 32 >> 4;
-        if (int rc = make_map(&g.ta, A, K, M, lda, KB, kBM, k_sw, who)) return rc;
-    }
-    if (g.b_mn) {
-        g.b_boxes = (uint32_t)(BN / 32); g.b_box_bytes = (uint32_t)(KB * 128);
-        g.b_desc_hi = desc_hi(1024, 2); g.b_lbo_sbo = ((g.b_box_bytes >> 4) & 0x3fffu) << 16; g.b_kstep = 1024 >> 4;
-        if (int rc = make_map(&g.tb, B, N, K, ldb, 32, KB, CU_TENSOR_MAP_SWIZZLE_128B, who)) return rc;
-    } else {
-        g.b_boxes = 1; g.b_box_bytes = g.b_bytes;
-        g.b_desc_hi = desc_hi((uint32_t)(8 * KB * 4), k_layout); g.b_lbo_sbo = 1u << 16; g.b_kstep = 32 >> 4;
-        if (int rc = make_map(&g.tb, B, K, N, ldb, KB, BN, k_sw, who)) return rc;
-    }
-    static bool attr_set[64];
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (dev >= 0 && dev < 64 && !attr_set[dev]) {
-        cudaError_t e = cudaFuncSetAttribute(k_gemm_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        if (e != cudaSuccess) return rbx_fail(RBX_ERR_CUDA, "%s: cudaFuncSetAttribute: %s", who, cudaGetErrorString(e));
-        attr_set[dev] = true;
-    }
-    k_gemm_tc<<<dim3(tiles_n, tiles_m, splits), kThreads, smem, st>>>(g);
-    RBX_LAUNCH_CHECK(who);
-    return RBX_OK;
+    return launch_tc(who, g, A, lda, B, ldb, M, N, K, 0, 0, 0, act == 0 && !mask, accumulate, st);
 }
 
 int rbx_colsum_f32(const float* X, int64_t ldx, float* out, int64_t M, int64_t N, int accumulate, rbx_stream_t stream) {

@@ -35,6 +35,10 @@ struct RbxRange {
 // SM count of the current device, cached per device.
 int rbx_sm_count();
 
+// tensor-core pass A of the top-k search (csrc/gemm.cu), used by csrc/topk.cu
+int rbx_topk_filter_tc(const float* q, const float* items, int64_t U, int64_t n0, int64_t n1, int D, const float* tau, int* count,
+                       unsigned long long* queue, int64_t qcap, cudaStream_t st);
+
 static inline cudaStream_t rbx_cast_stream(rbx_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
 
 // ---------------------------------------------------------------------------------------------

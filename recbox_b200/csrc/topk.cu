@@ -18,6 +18,7 @@
 // while tau is still loose.  Everything is stream-ordered; the host never reads a count.
 // Accuracy: fp32 level -- the default pass A forms every product as a 3xTF32 split on the tensor cores with fp32 accumulators
 // (k_ip_filter_mma); RBX_TOPK_MMA=0 builds the plain fp32 FMA-chain kernel.  Ties go to the smaller item index.
+#include <stdlib.h>
 #include "rbx_common.cuh"
 
 namespace {
@@ -457,20 +458,17 @@ int rbx_topk_ip(const float* q, const float* items, int64_t U, int64_t N, int D,
     RBX_LAUNCH_CHECK(who);
 
     const size_t smem = ((size_t)3 * TM * (D + 4) + TM) * 4;
-#if RBX_TOPK_MMA
-    const auto kernel_a = k_ip_filter_mma;
-    (void)&k_ip_filter;
-#else
-    const auto kernel_a = k_ip_filter;
-    (void)&k_ip_filter_mma;
-#endif
-    cudaError_t e = cudaFuncSetAttribute(kernel_a, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(k_ip_filter_mma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_ip_filter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return rbx_fail(RBX_ERR_CUDA, "%s: %s", who, cudaGetErrorString(e));
     const int64_t UT = (U + TM - 1) / TM;
     RBX_REQUIRE(UT <= 65535, "%s: U too large for one call", who);
     const int resident = rbx_sm_count() * 2;
     IpParams p;
     p.q = q; p.items = items; p.U = U; p.N = N; p.D = D; p.tau = t.tau; p.count = t.count; p.queue = t.queue; p.qcap = chunk;
+    // pass A engine: 2 (default) = tcgen05 GEMM with the filter epilogue (csrc/gemm.cu); 1 = warp-level mma.sync; 0 = fp32 FMA
+    const char* eng_s = getenv("RBX_TOPK_ENGINE");
+    const int engine = (eng_s && *eng_s) ? atoi(eng_s) : 2;
     int64_t c = chunk < 4096 ? chunk : 4096;
     for (int64_t n0 = 0; n0 < N;) {
         const int64_t n1 = n0 + c < N ? n0 + c : N;
@@ -479,7 +477,13 @@ int rbx_topk_ip(const float* q, const float* items, int64_t U, int64_t N, int D,
         int64_t gx = resident / UT;
         if (gx < 1) gx = 1;
         if (gx > tiles) gx = tiles;
-        kernel_a<<<dim3((unsigned)gx, (unsigned)UT), kT, smem, st>>>(p);
+        if (engine == 2) {
+            if (int rc = rbx_topk_filter_tc(q, items, U, n0, n1, D, t.tau, t.count, t.queue, chunk, st)) return rc;
+        } else if (engine == 1) {
+            k_ip_filter_mma<<<dim3((unsigned)gx, (unsigned)UT), kT, smem, st>>>(p);
+        } else {
+            k_ip_filter<<<dim3((unsigned)gx, (unsigned)UT), kT, smem, st>>>(p);
+        }
         RBX_LAUNCH_CHECK(who);
         k_select<<<(unsigned)U, kT, 0, st>>>(t.R, t.queue, t.count, t.tau, chunk, Kp, k);
         RBX_LAUNCH_CHECK(who);
