@@ -332,16 +332,16 @@ def main_b200(args, rank, world, local_rank):
     g_bias = gbuf[offs[4]:offs[4] + 1]
     main = torch.cuda.current_stream()
     side = torch.cuda.Stream()
-    ev_consumed, ev_zero = torch.cuda.Event(), torch.cuda.Event()
-    ev_consumed.record(main)
+    ev_fork, ev_zero = torch.cuda.Event(), torch.cuda.Event()
 
     def fwd(rows, dx):
         return ops.embed_fm_fwd(table, table_lr, rows, cat_pos, dx, dense_w, dense_w_lr, num_pos, bias)
 
     def zero_async():
-        """optimizer.zero_grad() of the fused gradient buffer on the side stream: runs under the forward, after the last
-        reader of the previous step's gradients (the all-reduce / the backward) is done."""
-        side.wait_event(ev_consumed)
+        """optimizer.zero_grad() of the fused gradient buffer on the side stream: forked from the step's stream (so it
+        follows the last reader of the previous step's gradients -- the backward / the all-reduce) and run under the forward."""
+        ev_fork.record(torch.cuda.current_stream())
+        side.wait_event(ev_fork)
         with torch.cuda.stream(side):
             ops.zero_(gbuf)
             ev_zero.record(side)
@@ -350,21 +350,40 @@ def main_b200(args, rank, world, local_rank):
         ops.embed_fm_bwd(table, rows, cat_pos, pad_row, dx, dense_w, num_pos, E, S, dE, d_fm, d_lr,
                          g_table, g_table_lr, g_dense_w, g_dense_w_lr, g_bias, D, R)
 
-    def step(i, evs=None):
+    def kernels_step(i, evs=None):
+        """forward + zero-fill + backward on batch i (three launches of ours)."""
         rows, dx = rows_l[i % NB], dense_l[i % NB]
         zero_async()
         if evs: evs[0].record()
         E, S, fm, lr = fwd(rows, dx)
         if evs: evs[1].record()
-        main.wait_event(ev_zero)
+        torch.cuda.current_stream().wait_event(ev_zero)
         if evs: evs[2].record()
         bwd(rows, dx, E, S)
         if evs: evs[3].record()
+        return fm, lr
+
+    # the three launches of each of the NB rotating batches as a CUDA graph: the step is ~0.19 ms, so the gaps between
+    # eagerly issued launches (ctypes + event calls) are a measurable part of it
+    graphed = None
+    if not args.eager:
+        from recbox_b200 import graphs
+        try:
+            graphed = [graphs.GraphedStep(lambda i=i: kernels_step(i), warmup=2) for i in range(NB)]
+        except Exception as e:
+            sys.stderr.write("bench: GraphedStep failed (%r); the device-resident loop issues its launches eagerly\n" % (e,))
+            graphed = None
+            torch.cuda.synchronize()
+
+    def step(i, evs=None):
+        if evs is None and graphed is not None:
+            out = graphed[i % NB]()
+        else:
+            out = kernels_step(i, evs)
         if world > 1:
             dist.all_reduce(gbuf)              # replicas train ONE model: dense gradient exchange inside the step
         if evs: evs[4].record()
-        ev_consumed.record(main)
-        return fm, lr
+        return out
 
     def barrier():
         if world > 1:
@@ -374,18 +393,28 @@ def main_b200(args, rank, world, local_rank):
     K, W = args.steps, max(args.warmup, 3)
     for i in range(W):
         step(i)
-    # ---- value: device-resident, CUDA events, max over ranks ----
+    # ---- value: device-resident, CUDA events around EXACTLY K steps, max over ranks ----
     sampler = ClockSampler(local_rank)
     sampler.start()
-    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(5)] for _ in range(K)]
     t_beg, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     t_beg.record()
     for i in range(K):
-        step(i, evs[i])
+        step(i)
     t_end.record()
     barrier()
     ms_total = t_beg.elapsed_time(t_end)
+    # ---- per-kernel times: a second pass over the same K steps, issued eagerly with an event after every launch ----
+    # (the GPU first spins for ~0.3 ms per step, so the host is ahead of it for the whole pass and the gaps between the
+    # events are device time, not the time the host needs to issue a launch)
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(5)] for _ in range(K)]
+    for i in range(3):
+        step(i, evs[i])
+    torch.cuda.synchronize()
+    torch.cuda._sleep(int(0.3e-3 * K * 1.9e9))
+    for i in range(K):
+        step(i, evs[i])
+    barrier()
     t_f = sum(e[0].elapsed_time(e[1]) for e in evs) / K
     t_w = sum(e[1].elapsed_time(e[2]) for e in evs) / K          # backward waiting for the zero-fill (0 when it hid)
     t_b = sum(e[2].elapsed_time(e[3]) for e in evs) / K
@@ -426,6 +455,8 @@ def main_b200(args, rank, world, local_rank):
     logit_dev = [torch.empty(B, 1, dtype=torch.float32, device=dev) for _ in range(2)]
     packed32_host = [(r.cpu().pin_memory(), d.cpu().pin_memory()) for r, d in zip(rows_l, dense_l)]
 
+    issue = {"packed": "eager", "f64": "eager", "ops": "eager"}
+
     def e2e_measure(mode):
         if mode == "f64":
             dev_in = [torch.empty_like(host_batches[0], device=dev) for _ in range(2)]
@@ -454,34 +485,51 @@ def main_b200(args, rank, world, local_rank):
                         d_.copy_(s_, non_blocking=True)
                 ev_in[j].record(h2d)
 
+        # the layer-API step of slot j as a CUDA graph (recbox_b200.graphs.GraphedStep): ~80 per-feature Parameters cross
+        # autograd per step (1.2 ms of host work measured eagerly, profiles/r2_layer_overhead.txt) although two kernels do
+        # the work; the replay re-issues the captured launches with no Python in between.  "eager" keeps the plain calls.
+        graphed = [None, None]
+
+        def layer_step(j):
+            for p in params:
+                p.grad = None                                # optimizer.zero_grad() (ranking_model.py:192)
+            X = layers.get_inputs(_Model, dev_in[j])         # PackedColumns / PackedInputs views, no copies
+            E = emb(X)
+            y = fml(X, E)
+            logit_dev[j].copy_(y.detach())
+            torch.autograd.backward([E, y], [dE, d_out])
+
+        if mode in ("packed", "f64") and not args.eager:
+            from recbox_b200 import graphs
+            try:
+                for j in range(2):
+                    graphed[j] = graphs.GraphedStep(lambda j=j: layer_step(j), warmup=2)
+                issue[mode] = "cuda-graph replay"
+            except Exception as e:
+                sys.stderr.write("bench: GraphedStep failed (%r); the layer-API e2e leg runs eagerly\n" % (e,))
+                graphed = [None, None]
+                torch.cuda.synchronize()
+
         def compute(i):
             j = i % 2
             main.wait_event(ev_in[j])
+            main.wait_event(ev_read[j])                      # the previous logits of this slot left the device
             if mode == "ops":
                 rows, dx = dev_in[j]
                 zero_async()
                 E, S, fm, lr = fwd(rows, dx)
-                main.wait_event(ev_read[j])                  # the previous logits of this slot left the device
                 torch.add(fm.view(-1, 1), lr.view(-1, 1), out=logit_dev[j])
+                main.wait_event(ev_zero)
+                bwd(rows, dx, E, S)
+            elif graphed[j] is not None:
+                graphed[j]()
             else:
-                for p in params:
-                    p.grad = None                            # optimizer.zero_grad() (ranking_model.py:192)
-                X = layers.get_inputs(_Model, dev_in[j])     # PackedColumns / PackedInputs views, no copies
-                E = emb(X)
-                y = fml(X, E)
-                main.wait_event(ev_read[j])
-                logit_dev[j].copy_(y.detach())
+                layer_step(j)
             ev_out[j].record(main)
             with torch.cuda.stream(d2h):
                 d2h.wait_event(ev_out[j])
                 out_host[j].copy_(logit_dev[j], non_blocking=True)
                 ev_read[j].record(d2h)
-            if mode == "ops":
-                main.wait_event(ev_zero)
-                bwd(rows, dx, E, S)
-                ev_consumed.record(main)
-            else:
-                torch.autograd.backward([E, y], [dE, d_out])
             if world > 1:                                    # the replicas' gradient exchange belongs to the step
                 if mode == "ops":
                     dist.all_reduce(gbuf)
@@ -548,7 +596,7 @@ def main_b200(args, rank, world, local_rank):
         def e2e_obj(mode, what):
             ms, nbytes = e2e_t[mode], e2e_ms[mode][1]
             return {"value": B * world * K / (ms * 1e-3), "unit": "samples/s", "h2d_bytes_per_step": nbytes,
-                    "d2h_bytes_per_step": B * 4, "ms_per_step": ms / K, "input": what}
+                    "d2h_bytes_per_step": B * 4, "ms_per_step": ms / K, "input": what, "issue": issue[mode]}
         line = {
             "metric": "samples/sec on Criteo-shaped synthetic (embedding + FM hot path, fwd+bwd)",
             "value": B * world * K / (ms_total * 1e-3), "unit": "samples/s", "n_gpus": world, "steps": K, "warmup": W,
@@ -561,6 +609,7 @@ def main_b200(args, rank, world, local_rank):
             "e2e_ops": None if args.no_e2e else e2e_obj("ops", "below the layer API: recbox_b200.ops on int32 packed blocks (160 B/sample), pinned"),
             # ours per step: k_embed_fm_fwd + k_zero_f32 + k_embed_fm_bwd; library: the NCCL all-reduce at N > 1
             "gpu_launches": 3 * K, "library_launches": K if world > 1 else 0,
+            "issue": "cuda-graph replay (one graph per rotating batch)" if graphed is not None else "eager",
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                          "traffic": ncu_traffic(dom) if args.ids == "uniform" else None, "peak_source": peak_src,
                          "pair_achieved": (bf + bb) / (t_f + t_b) / 1e6, "pair_frac": (bf + bb) / (t_f + t_b) / 1e6 / peak},
@@ -796,6 +845,24 @@ def main_sharded(args, rank, world, local_rank):
         dist.destroy_process_group()
 
 
+def main_matching(args, rank, world, local_rank):
+    """BASELINE configs[2] / configs[4] (tools/matching_workloads.py)."""
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    import torch.distributed as dist
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import matching_workloads as mw
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    line = (mw.run_dssm if args.workload == "dssm" else mw.run_sasrec)(args, rank, world, dev, sys.modules[__name__])
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -805,10 +872,11 @@ def main():
     ap.add_argument("--ids", default="uniform", choices=["uniform", "zipf"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end leg (profiling runs under ncu)")
+    ap.add_argument("--eager", action="store_true", help="layer-API e2e legs without CUDA-graph replay (host-bound: ~80 Parameters cross autograd)")
     ap.add_argument("--no-sharded", action="store_true", help="cfg2 run without the attached configs[3] (100M-row sharded table) object")
-    ap.add_argument("--workload", default="cfg2", choices=["cfg2", "sharded"],
+    ap.add_argument("--workload", default="cfg2", choices=["cfg2", "sharded", "dssm", "sasrec"],
                     help="cfg2: BASELINE configs[1], replicated 1M-row table (default, the metric's config); "
-                         "sharded: configs[3], 100M-row table row-sharded over the ranks")
+                         "sharded: configs[3], 100M-row table row-sharded over the ranks; dssm: configs[2]; sasrec: configs[4]")
     ap.add_argument("--shard-mode", default="auto", choices=["auto", "stream", "push", "peer", "a2a"])
     ap.add_argument("--peer-alloc", default="symm", choices=["ipc", "symm"])
     ap.add_argument("--shard-layout", default="auto", choices=["auto", "split", "rowlr", "rowpad"],
@@ -825,6 +893,8 @@ def main():
         main_reference(args, rank, world)
     elif args.workload == "sharded":
         main_sharded(args, rank, world, local_rank)
+    elif args.workload in ("dssm", "sasrec"):
+        main_matching(args, rank, world, local_rank)
     else:
         main_b200(args, rank, world, local_rank)
 

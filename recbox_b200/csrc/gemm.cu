@@ -221,17 +221,29 @@ __global__ void __launch_bounds__(kThreads, 1) k_gemm_tc(const __grid_constant__
                 const uint32_t ph = (uint32_t)(i / p.stages) & 1u;
                 mbar_wait(full_bar(s), ph);
                 const uint32_t raw = smem_base + (uint32_t)s * stage_bytes;
-                for (uint32_t j = t; j < n16; j += 128) {
-                    float4 v;
-                    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(raw + 16u * j));
-                    const float4 lo = make_float4(tf32_lo(v.x), tf32_lo(v.y), tf32_lo(v.z), tf32_lo(v.w));
-                    asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(raw + plane_bytes + 16u * j), "f"(lo.x), "f"(lo.y), "f"(lo.z),
-                                 "f"(lo.w)
-                                 : "memory");
-                    if (p.write_hi) {
-                        asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(raw + 16u * j), "f"(tf32_hi(v.x)), "f"(tf32_hi(v.y)),
-                                     "f"(tf32_hi(v.z)), "f"(tf32_hi(v.w))
-                                     : "memory");
+                // four independent 16-byte loads in flight per thread before the first store (the asm stores order memory)
+                for (uint32_t j0 = t; j0 < n16; j0 += 4 * 128) {
+                    float4 v[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const uint32_t j = j0 + 128u * u;
+                        if (j < n16)
+                            asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];"
+                                         : "=f"(v[u].x), "=f"(v[u].y), "=f"(v[u].z), "=f"(v[u].w)
+                                         : "r"(raw + 16u * j));
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const uint32_t j = j0 + 128u * u;
+                        if (j < n16) {
+                            asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(raw + plane_bytes + 16u * j), "f"(tf32_lo(v[u].x)),
+                                         "f"(tf32_lo(v[u].y)), "f"(tf32_lo(v[u].z)), "f"(tf32_lo(v[u].w))
+                                         : "memory");
+                            if (p.write_hi)
+                                asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(raw + 16u * j), "f"(tf32_hi(v[u].x)),
+                                             "f"(tf32_hi(v[u].y)), "f"(tf32_hi(v[u].z)), "f"(tf32_hi(v[u].w))
+                                             : "memory");
+                        }
                     }
                 }
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the tensor core
@@ -275,9 +287,14 @@ __global__ void __launch_bounds__(kThreads, 1) k_gemm_tc(const __grid_constant__
                 for (int e = 0; e < 4; ++e) v[e] = __uint_as_float(r[4 * g + e]);
                 const bool full4 = vec_ok && col + 4 <= p.N;
                 if (p.bias && first_split) {
+                    if (col + 4 <= p.N && ((reinterpret_cast<uintptr_t>(p.bias) & 15) == 0)) {
+                        const float4 bv = __ldg(reinterpret_cast<const float4*>(p.bias + col));
+                        v[0] += bv.x; v[1] += bv.y; v[2] += bv.z; v[3] += bv.w;
+                    } else {
 #pragma unroll
-                    for (int e = 0; e < 4; ++e)
-                        if (col + e < p.N) v[e] += __ldg(p.bias + col + e);
+                        for (int e = 0; e < 4; ++e)
+                            if (col + e < p.N) v[e] += __ldg(p.bias + col + e);
+                    }
                 }
                 if (p.act == 1) {
 #pragma unroll
@@ -467,9 +484,19 @@ int launch_tc(const char* who, GemmArgs& g, const float* A, int64_t lda, const f
     if (KB != 16 && KB != 32) KB = (precision == 3 && BN > 128) ? 16 : 32;
     g.KB = KB;
     g.kb_total = (int)((K + KB - 1) / KB);
+    // split-K: when the output has too few tiles to fill the machine (dW: reduction over the batch), and always so that one
+    // TMEM accumulation chain stays at or below 1024 products (the tensor core's fp32 adds are not round-to-nearest: at K = 65 536
+    // one chain of 5461 products per output drifts to 4.6e-5 of max|C|, 2048 to 1.4e-5; chains of <= 1024 combined by fp32
+    // red.add stay within 1e-5)
     int splits = 1;
-    if (allow_split && tiles_m * tiles_n * 2 <= sms) {
-        splits = sms / (tiles_m * tiles_n);
+    if (allow_split) {
+        const int tiles = tiles_m * tiles_n, slots = 2 * sms;            // two CTAs per SM (see the stage count below)
+        int want = (int)((K + 1023) / 1024);                             // chains of <= 1024 products
+        if (tiles * 2 <= sms && want < slots / tiles) want = slots / tiles;
+        if (want > 1) {                                                  // whole waves: 12 tiles x 74 splits = 3 x 296 CTAs
+            const int waves = (want * tiles + slots - 1) / slots;
+            splits = waves * slots / tiles;
+        }
         if (splits > g.kb_total / 4) splits = g.kb_total / 4;
         if (splits < 1) splits = 1;
     }
@@ -485,7 +512,10 @@ int launch_tc(const char* who, GemmArgs& g, const float* A, int64_t lda, const f
     g.b_bytes = (uint32_t)(BN * KB * 4);
     const uint32_t stage_bytes = (precision == 3 ? 2u : 1u) * (g.a_bytes + g.b_bytes);
     const uint32_t bar_bytes = 8u * (3 * kMaxStages + 2);
-    int stages = (int)((227u * 1024u - 1024u - bar_bytes) / stage_bytes);
+    // two CTAs per SM when two stages of each fit (one CTA's prologue / epilogue then runs under the other's MMAs: measured
+    // 225 us against 280 us with one 5-stage CTA on the 65 536 x 400 x 624 layer); otherwise one CTA with every stage that fits
+    int stages = (int)((113u * 1024u - 1024u - bar_bytes) / stage_bytes);
+    if (stages < 2) stages = (int)((227u * 1024u - 1024u - bar_bytes) / stage_bytes);
     if (stages > kMaxStages) stages = kMaxStages;
     if (max_stages && stages > max_stages) stages = max_stages;
     if (int f = env_int("RBX_GEMM_STAGES", 0)) stages = f < stages ? f : stages;
@@ -502,10 +532,12 @@ int launch_tc(const char* who, GemmArgs& g, const float* A, int64_t lda, const f
     const CUtensorMapSwizzle k_sw = KB == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
     const uint32_t k_layout = KB == 32 ? 2u : 4u;
     auto desc_hi = [](uint32_t sbo_bytes, uint32_t layout) { return ((sbo_bytes >> 4) & 0x3fffu) | (1u << 14) | (layout << 29); };
-    if (g.a_mn) {       // [KB k-rows][32 m] boxes, 128 B rows, SWIZZLE_128B: LBO = box pitch, SBO = 8 k-rows = 1024 B
+    // MN-major tf32 operands have ONE legal shared-memory layout: 128-byte rows swizzled in 32-byte chunks (descriptor
+    // layout type 1 = SWIZZLE_128B_BASE32B, TMA CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B); its atom is 32 elements (MN) x 4 k-rows.
+    if (g.a_mn) {       // [KB k-rows][32 m] boxes, 128 B rows: LBO = box pitch (next 32 m), SBO = 4 k-rows = 512 B
         g.a_boxes = kBM / 32; g.a_box_bytes = (uint32_t)(KB * 128);
-        g.a_desc_hi = desc_hi(1024, 2); g.a_lbo_sbo = ((g.a_box_bytes >> 4) & 0x3fffu) << 16; g.a_kstep = 1024 >> 4;
-        if (int rc = make_map(&g.ta, A, M, K, lda, 32, KB, CU_TENSOR_MAP_SWIZZLE_128B, who)) return rc;
+        g.a_desc_hi = desc_hi(512, 1); g.a_lbo_sbo = ((g.a_box_bytes >> 4) & 0x3fffu) << 16; g.a_kstep = 1024 >> 4;
+        if (int rc = make_map(&g.ta, A, M, K, lda, 32, KB, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, who)) return rc;
     } else {            // [128 rows][KB k] one box, rows of KB*4 B: SBO = 8 rows
         g.a_boxes = 1; g.a_box_bytes = g.a_bytes;
         g.a_desc_hi = desc_hi((uint32_t)(8 * KB * 4), k_layout); g.a_lbo_sbo = 1u << 16; g.a_kstep = 32 >> 4;
@@ -513,8 +545,8 @@ int launch_tc(const char* who, GemmArgs& g, const float* A, int64_t lda, const f
     }
     if (g.b_mn) {
         g.b_boxes = (uint32_t)(BN / 32); g.b_box_bytes = (uint32_t)(KB * 128);
-        g.b_desc_hi = desc_hi(1024, 2); g.b_lbo_sbo = ((g.b_box_bytes >> 4) & 0x3fffu) << 16; g.b_kstep = 1024 >> 4;
-        if (int rc = make_map(&g.tb, B, N, K, ldb, 32, KB, CU_TENSOR_MAP_SWIZZLE_128B, who)) return rc;
+        g.b_desc_hi = desc_hi(512, 1); g.b_lbo_sbo = ((g.b_box_bytes >> 4) & 0x3fffu) << 16; g.b_kstep = 1024 >> 4;
+        if (int rc = make_map(&g.tb, B, N, K, ldb, 32, KB, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, who)) return rc;
     } else {
         g.b_boxes = 1; g.b_box_bytes = g.b_bytes;
         g.b_desc_hi = desc_hi((uint32_t)(8 * KB * 4), k_layout); g.b_lbo_sbo = 1u << 16; g.b_kstep = 32 >> 4;

@@ -636,7 +636,8 @@ def get_inputs(model, inputs, feature_source=None):
     """Drop-in for RankingModel.get_inputs (ranking_model.py:106-116): ONE host->device copy of the
     batch matrix, then per-feature views of it."""
     if isinstance(inputs, PackedBatch):          # loader.PackedDataLoader: 160 B / Criteo sample, no casts
-        pb = inputs if inputs.ids is None or inputs.ids.is_cuda else inputs.to(model.device, non_blocking=True)
+        probe = next((t for t in (inputs.ids, inputs.ids16, inputs.dense, inputs.labels) if t is not None), None)
+        pb = inputs if probe is None or probe.is_cuda else inputs.to(model.device, non_blocking=True)
         X = PackedColumns(pb)
         if feature_source:
             if type(feature_source) == str:

@@ -55,8 +55,13 @@ def run(M, N, K, a_mn, b_mn, prec, env, time_it=False):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--time", action="store_true")
+    ap.add_argument("--one", default="", help="M,N,K,a_mn,b_mn,prec: one configuration, three launches (for ncu)")
     args = ap.parse_args()
     torch.cuda.set_device(0)
+    if args.one:
+        M, N, K, a_mn, b_mn, prec = (int(x) for x in args.one.split(","))
+        run(M, N, K, a_mn, b_mn, prec, {}, False)
+        return
     if not args.time:
         for prec in (1, 3):
             for KB in (32, 16):
@@ -70,7 +75,8 @@ def main():
         return
     B = 65536
     for prec in (3, 1):
-        for env in ({}, {"RBX_GEMM_KB": 32}, {"RBX_GEMM_KB": 16}, {"RBX_GEMM_BN": 128}, {"RBX_GEMM_BN": 256}):
+        for env in ({}, {"RBX_GEMM_KB": 32}, {"RBX_GEMM_STAGES": 2}, {"RBX_GEMM_STAGES": 3}, {"RBX_GEMM_KB": 32, "RBX_GEMM_BN": 128, "RBX_GEMM_STAGES": 2},
+                    {"RBX_GEMM_BN": 256}):
             run(B, 400, 624, 0, 0, prec, env, True)
         run(B, 400, 400, 0, 0, prec, {}, True)
         run(B, 624, 400, 0, 1, prec, {}, True)

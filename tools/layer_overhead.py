@@ -70,11 +70,11 @@ def main():
         pstats.Stats(pr, stream=s).sort_stats("cumulative").print_stats(35)
         print(s.getvalue()[:6000])
     from recbox_b200 import graphs
-    gs = graphs.GraphedStep(step, warmup=3)
-    y_ref = step().clone()
+    y_ref = step().detach().clone()               # (a live autograd graph would pin AccumulateGrad nodes to this stream)
     gref = [p.grad.clone() for p in params]
+    gs = graphs.GraphedStep(step, warmup=3)          # after the capture the parameters' .grad are the graph's static tensors
     for p in params:
-        p.grad = None
+        p.grad.zero_()
     y = gs()
     torch.cuda.synchronize()
     print("graph replay == eager:", torch.equal(y, y_ref), all(torch.allclose(p.grad, r, rtol=1e-5, atol=1e-7) for p, r in zip(params, gref)))

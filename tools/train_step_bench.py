@@ -6,8 +6,9 @@ layer API of recbox_b200.layers exactly the way a RecBox model is (INTEGRATION.m
     zero_grad -> get_inputs -> FeatureEmbedding -> FactorizationMachine + MLP -> sigmoid -> BCE(mean) -> backward
     -> clip_grad_norm_(all params, 10) -> Adam.step        (RankingModel.train_step, ranking_model.py:191-197)
 
-The embedding / FM part runs on the fused kernels, the MLP on cuBLAS (nn.Linear), the optimizer is either
-torch.optim.Adam over every parameter (the reference's dense semantics) or the touched-rows optimizer for the tables.
+The embedding / FM part runs on the fused kernels; the MLP either on cuBLAS (nn.Linear, the round-1 state) or on the tcgen05
+GEMM chain of csrc/gemm.cu behind layers.MLP_Block (a13); the optimizer is torch.optim.Adam over every parameter (the
+reference's dense semantics); the `graph` variants replay the whole step from a CUDA graph.
 The CPU arm is oracle.DeepFMOracle (the reference train step restated) on the host cores, a few steps.
 
   python tools/train_step_bench.py [tag]  -> gpurun_out/<tag>_train_step.json
@@ -46,11 +47,15 @@ def feature_map():
 
 
 class DeepFM(nn.Module):
-    def __init__(self, fm):
+    def __init__(self, fm, ours=False):
         super().__init__()
         self.feature_map, self.device = fm, dev
         self.embedding_layer = layers.FeatureEmbedding(fm, D)
         self.fm_layer = layers.FactorizationMachine(fm)
+        if ours:          # a13 on the tcgen05 GEMM chain (csrc/gemm.cu) behind the reference's MLP_Block constructor
+            self.mlp = layers.MLP_Block(input_dim=fm.sum_emb_out_dim(), hidden_units=[400, 400, 400], hidden_activations="ReLU",
+                                        output_dim=1)
+            return
         mods, d = [], fm.sum_emb_out_dim()
         for h in (400, 400, 400):
             mods += [nn.Linear(d, h), nn.ReLU()]
@@ -74,21 +79,24 @@ def make_batches(n, seed):
     return out
 
 
-def run_gpu(tf32, packed, steps=30, warmup=5):
+def run_gpu(tf32, packed, steps=30, warmup=5, ours=False, precision=3, graph=False):
+    """ours: MLP_Block on the tcgen05 GEMM (precision 3 = 3xTF32 fp32-level, 1 = plain TF32) instead of nn.Linear on cuBLAS;
+    graph: the whole train step (device batch -> loss -> backward -> clip -> Adam) replayed from a CUDA graph."""
+    from recbox_b200 import graphs, ops
     torch.backends.cuda.matmul.allow_tf32 = tf32
     torch.backends.cudnn.allow_tf32 = tf32
+    ops.GEMM_PRECISION = precision
     torch.manual_seed(0)
     fm = feature_map()
-    model = DeepFM(fm).to(dev)
-    opt = torch.optim.Adam(model.parameters(), lr=1e-3)
+    model = DeepFM(fm, ours=ours).to(dev)
+    opt = torch.optim.Adam(model.parameters(), lr=1e-3, capturable=graph)
     host = make_batches(4, 1)
     if packed:
         feed = [list(PackedDataLoader(fm, h, batch_size=B).bind(model.embedding_layer))[0] for h in host]
     else:
         feed = [torch.from_numpy(h).pin_memory() for h in host]
 
-    def step(i):
-        batch = feed[i % len(feed)]
+    def train(batch):
         y_true = layers.get_labels(model, batch)
         opt.zero_grad()
         loss = torch.nn.functional.binary_cross_entropy(model(batch), y_true, reduction="mean")
@@ -96,6 +104,17 @@ def run_gpu(tf32, packed, steps=30, warmup=5):
         torch.nn.utils.clip_grad_norm_(model.parameters(), 10.0)
         opt.step()
         return loss
+
+    if graph:
+        static = feed[0].to(dev)                                 # the graph reads its batch from these device blocks
+        gs = graphs.GraphedStep(lambda: train(static), warmup=3)
+
+        def step(i):
+            feed[i % len(feed)].copy_into(static)                # H2D of the step's packed batch, then the replay
+            return gs()
+    else:
+        def step(i):
+            return train(feed[i % len(feed)])
 
     for i in range(warmup):
         step(i)
@@ -107,8 +126,11 @@ def run_gpu(tf32, packed, steps=30, warmup=5):
     b.record()
     torch.cuda.synchronize()
     ms = a.elapsed_time(b) / steps
-    return {"ms_per_step": ms, "samples_per_s": B / ms * 1e3, "tf32_mlp": tf32, "input": "packed" if packed else "float64",
-            "loss": float(loss), "steps": steps}
+    ops.GEMM_PRECISION = 3
+    return {"ms_per_step": ms, "samples_per_s": B / ms * 1e3, "input": "packed" if packed else "float64",
+            "mlp": ("tcgen05 GEMM chain, %s" % ("3xTF32 (fp32-level)" if precision == 3 else "plain TF32")) if ours else
+                   ("nn.Linear / cuBLAS, %s" % ("TF32" if tf32 else "fp32")),
+            "issue": "cuda-graph replay" if graph else "eager", "loss": float(loss), "steps": steps}
 
 
 def run_cpu(steps=2):
@@ -134,9 +156,18 @@ def run_cpu(steps=2):
 if __name__ == "__main__":
     out = OrderedDict()
     out["config"] = "BASELINE configs[1] DeepFM: 26 cat + 13 dense, 26x38462 rows, D=16, MLP 400-400-400-1, B=65536, dense Adam + clip 10"
-    out["gpu_fp32_mlp_float64_batches"] = run_gpu(False, False)
-    out["gpu_fp32_mlp_packed_batches"] = run_gpu(False, True)
-    out["gpu_tf32_mlp_packed_batches"] = run_gpu(True, True)
+    variants = [("cublas_fp32_mlp_float64_batches", dict(tf32=False, packed=False)),
+                ("cublas_fp32_mlp_packed_batches", dict(tf32=False, packed=True)),
+                ("cublas_tf32_mlp_packed_batches", dict(tf32=True, packed=True)),
+                ("ours_3xtf32_mlp_packed_batches", dict(tf32=False, packed=True, ours=True, precision=3)),
+                ("ours_3xtf32_mlp_packed_batches_graph", dict(tf32=False, packed=True, ours=True, precision=3, graph=True)),
+                ("ours_tf32_mlp_packed_batches_graph", dict(tf32=False, packed=True, ours=True, precision=1, graph=True))]
+    for name, kw in variants:
+        try:
+            out[name] = run_gpu(**kw)
+        except Exception as e:
+            out[name] = {"error": repr(e)[:300]}
+            torch.cuda.synchronize()
     out["cpu_reference_port"] = run_cpu()
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     with open(os.path.join(ROOT, "gpurun_out", tag + "_train_step.json"), "w") as f:
