@@ -530,9 +530,9 @@ def main_b200(args, rank, world, local_rank):
                 d2h.wait_event(ev_out[j])
                 out_host[j].copy_(logit_dev[j], non_blocking=True)
                 ev_read[j].record(d2h)
-            if world > 1:                                    # the replicas' gradient exchange belongs to the step
-                if mode == "ops":
-                    dist.all_reduce(gbuf)
+            if world > 1:                                    # the replicas' gradient exchange belongs to the step; issued eagerly
+                if mode == "ops":                            # after the replay (a graph that holds NCCL kernels hung the
+                    dist.all_reduce(gbuf)                    # process-group teardown in run r2t)
                 else:
                     layers.sync_replica_gradients(params)
             ev_free[j].record(main)                          # the backward still reads the copied blocks

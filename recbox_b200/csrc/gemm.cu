@@ -339,23 +339,36 @@ __global__ void __launch_bounds__(kThreads, 1) k_gemm_tc(const __grid_constant__
 }
 
 // ---- skinny shapes (the Linear(hidden, 1) head of the MLP): memory-bound, no tensor cores ------------------------------
-// C[M,N] = act(A[M,K] B[N,K]^T + bias), N <= 8: one warp per row
+// C[M,N] = act(A[M,K] B[N,K]^T + bias), N <= 8: one warp per row, 16-byte streaming loads of the row
 template <int NMAX>
 __global__ void __launch_bounds__(256) k_skinny_nt(const float* __restrict__ A, int64_t lda, const float* __restrict__ B, int64_t ldb,
                                                    float* __restrict__ C, int64_t ldc, int M, int N, int K, const float* __restrict__ bias,
                                                    int act, int accumulate) {
     const int lane = threadIdx.x & 31;
     const int64_t warp0 = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), nw = (int64_t)gridDim.x * (blockDim.x >> 5);
+    const bool vec = ((lda | ldb) & 3) == 0 && (K & 3) == 0 && ((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(B)) & 15) == 0;
     for (int64_t m = warp0; m < M; m += nw) {
         float acc[NMAX];
 #pragma unroll
         for (int n = 0; n < NMAX; ++n) acc[n] = 0.0f;
         const float* a = A + m * lda;
-        for (int k = lane; k < K; k += 32) {
-            const float x = ld_stream_f1(a + k);
+        if (vec) {
+            for (int k = 4 * lane; k < K; k += 128) {
+                const float4 x = ld_stream_f4(a + k);
 #pragma unroll
-            for (int n = 0; n < NMAX; ++n)
-                if (n < N) acc[n] = fmaf(x, __ldg(B + n * ldb + k), acc[n]);
+                for (int n = 0; n < NMAX; ++n)
+                    if (n < N) {
+                        const float4 w = __ldg(reinterpret_cast<const float4*>(B + n * ldb + k));
+                        acc[n] = fmaf(x.x, w.x, fmaf(x.y, w.y, fmaf(x.z, w.z, fmaf(x.w, w.w, acc[n]))));
+                    }
+            }
+        } else {
+            for (int k = lane; k < K; k += 32) {
+                const float x = ld_stream_f1(a + k);
+#pragma unroll
+                for (int n = 0; n < NMAX; ++n)
+                    if (n < N) acc[n] = fmaf(x, __ldg(B + n * ldb + k), acc[n]);
+            }
         }
 #pragma unroll
         for (int n = 0; n < NMAX; ++n) acc[n] = group_sum<32>(acc[n]);
@@ -370,23 +383,56 @@ __global__ void __launch_bounds__(256) k_skinny_nt(const float* __restrict__ A, 
     }
 }
 
-// C[M,N] = (A[M,K] Bt[K,N]) * (mask > 0), K <= 8 (rank-K update: dH = dy w for the head)
+// C[M,N] = (A[M,K] Bt[K,N]) * (mask > 0), K <= 8 (rank-K update: dH = dy w for the head): a thread owns 4 columns of a row
 __global__ void __launch_bounds__(256) k_skinny_k(const float* __restrict__ A, int64_t lda, const float* __restrict__ Bt, int64_t ldb,
                                                   float* __restrict__ C, int64_t ldc, int64_t M, int N, int K, const float* __restrict__ mask,
                                                   int64_t ldmask, int accumulate) {
-    const int64_t total = M * N;
+    const int n4 = (N + 3) >> 2;
+    const bool vec = (N & 3) == 0 && ((ldb | ldc) & 3) == 0 && (!mask || (ldmask & 3) == 0) &&
+                     ((reinterpret_cast<uintptr_t>(Bt) | reinterpret_cast<uintptr_t>(C) | reinterpret_cast<uintptr_t>(mask)) & 15) == 0;
+    const int64_t total = M * n4;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t m = i / N;
-        const int n = (int)(i - m * N);
-        float v = 0.0f;
-        for (int k = 0; k < K; ++k) v = fmaf(__ldg(A + m * lda + k), __ldg(Bt + k * ldb + n), v);
-        if (mask) v = mask[m * ldmask + n] > 0.0f ? v : 0.0f;
-        if (accumulate) v += C[m * ldc + n];
-        C[m * ldc + n] = v;
+        const int64_t m = i / n4;
+        const int n = 4 * (int)(i - m * n4);
+        float v[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+        for (int k = 0; k < K; ++k) {
+            const float a = __ldg(A + m * lda + k);
+            if (vec) {
+                const float4 w = __ldg(reinterpret_cast<const float4*>(Bt + k * ldb + n));
+                v[0] = fmaf(a, w.x, v[0]); v[1] = fmaf(a, w.y, v[1]); v[2] = fmaf(a, w.z, v[2]); v[3] = fmaf(a, w.w, v[3]);
+            } else {
+#pragma unroll
+                for (int e = 0; e < 4; ++e)
+                    if (n + e < N) v[e] = fmaf(a, __ldg(Bt + k * ldb + n + e), v[e]);
+            }
+        }
+        if (vec) {
+            if (mask) {
+                const float4 mk = ld_stream_f4(mask + m * ldmask + n);
+                v[0] = mk.x > 0.0f ? v[0] : 0.0f; v[1] = mk.y > 0.0f ? v[1] : 0.0f;
+                v[2] = mk.z > 0.0f ? v[2] : 0.0f; v[3] = mk.w > 0.0f ? v[3] : 0.0f;
+            }
+            float4* c = reinterpret_cast<float4*>(C + m * ldc + n);
+            if (accumulate) {
+                const float4 o = *c;
+                v[0] += o.x; v[1] += o.y; v[2] += o.z; v[3] += o.w;
+            }
+            *c = make_float4(v[0], v[1], v[2], v[3]);
+        } else {
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+                if (n + e < N) {
+                    float x = v[e];
+                    if (mask) x = mask[m * ldmask + n + e] > 0.0f ? x : 0.0f;
+                    if (accumulate) x += C[m * ldc + n + e];
+                    C[m * ldc + n + e] = x;
+                }
+        }
     }
 }
 
-// C[M,N] += At[Kr,M]^T Bt[Kr,N], M <= 8 (dw = dy^T H for the head): rows of the reduction are split over the CTAs
+// C[M,N] += At[Kr,M]^T Bt[Kr,N], M <= 8 (dw = dy^T H for the head): rows of the reduction are split over the CTAs, four rows
+// in flight per thread
 template <int MMAX>
 __global__ void __launch_bounds__(256) k_skinny_m(const float* __restrict__ At, int64_t lda, const float* __restrict__ Bt, int64_t ldb,
                                                   float* __restrict__ C, int64_t ldc, int M, int N, int64_t Kr, int64_t rows_per_cta) {
@@ -397,7 +443,18 @@ __global__ void __launch_bounds__(256) k_skinny_m(const float* __restrict__ At, 
         float acc[MMAX];
 #pragma unroll
         for (int m = 0; m < MMAX; ++m) acc[m] = 0.0f;
-        for (int64_t r = r0; r < r1; ++r) {
+        int64_t r = r0;
+        for (; r + 4 <= r1; r += 4) {
+            float x[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) x[u] = ld_stream_f1(Bt + (r + u) * ldb + n);
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+#pragma unroll
+                for (int m = 0; m < MMAX; ++m)
+                    if (m < M) acc[m] = fmaf(__ldg(At + (r + u) * lda + m), x[u], acc[m]);
+        }
+        for (; r < r1; ++r) {
             const float x = ld_stream_f1(Bt + r * ldb + n);
 #pragma unroll
             for (int m = 0; m < MMAX; ++m)
@@ -604,7 +661,7 @@ int rbx_gemm_f32(const float* A, int64_t lda, int a_mn, const float* B, int64_t 
         return RBX_OK;
     }
     if (K <= 8 && !a_mn && b_mn && !bias && act == 0) {
-        int64_t grid = (M * N + 255) / 256;
+        int64_t grid = (M * ((N + 3) / 4) + 255) / 256;
         if (grid > (int64_t)sms * 16) grid = (int64_t)sms * 16;
         k_skinny_k<<<(unsigned)grid, 256, 0, st>>>(A, lda, B, ldb, C, ldc, M, (int)N, (int)K, mask, ldmask, accumulate);
         RBX_LAUNCH_CHECK(who);
@@ -615,12 +672,13 @@ int rbx_gemm_f32(const float* A, int64_t lda, int a_mn, const float* B, int64_t 
             cudaError_t e = cudaMemset2DAsync(C, (size_t)ldc * 4, 0, (size_t)N * 4, (size_t)M, st);
             if (e != cudaSuccess) return rbx_fail(RBX_ERR_CUDA, "%s: memset: %s", who, cudaGetErrorString(e));
         }
-        const int gx = (int)((N + 255) / 256);
-        int gy = sms * 4 / gx;
+        const int bt = N >= 256 ? 256 : (N >= 128 ? 128 : 64);         // N = 400: 4 x 128 threads cover the columns, 112 idle
+        const int gx = (int)((N + bt - 1) / bt);
+        int gy = sms * 8 / gx;
         if (gy < 1) gy = 1;
         if (gy > K) gy = (int)(K > 0 ? K : 1);
         const int64_t per = (K + gy - 1) / gy;
-        if (K > 0) k_skinny_m<8><<<dim3(gx, gy), 256, 0, st>>>(A, lda, B, ldb, C, ldc, (int)M, (int)N, K, per);
+        if (K > 0) k_skinny_m<8><<<dim3(gx, gy), bt, 0, st>>>(A, lda, B, ldb, C, ldc, (int)M, (int)N, K, per);
         RBX_LAUNCH_CHECK(who);
         return RBX_OK;
     }

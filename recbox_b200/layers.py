@@ -339,35 +339,67 @@ class _FusedEmbedFn(torch.autograd.Function):
 
 
 def fused_grad_buffers(params):
-    """The distinct gradient allocations behind `params`: the per-feature .grad tensors a fused backward hands to autograd
-    are views of ONE buffer per launch (see _FusedEmbedFn.backward), so a replica's gradient exchange is one collective over
-    that buffer instead of one per feature.  Gradients that are not views come back as they are."""
-    seen, out = set(), []
+    """-> (shared, single): `shared` = one flat fp32 view per gradient STORAGE that several parameters' .grad alias (the
+    per-feature .grad tensors a fused backward hands to autograd are views of one buffer per launch, see
+    _FusedEmbedFn.backward) -- a replica's gradient exchange is then one collective over that buffer instead of one per
+    feature; `single` = the gradients that own their storage."""
+    groups = OrderedDict()
     for p in params:
         g = p.grad
         if g is None:
             continue
-        b = g._base if g._base is not None else g
-        key = (b.data_ptr(), b.numel())
-        if key not in seen:
-            seen.add(key)
-            out.append(b)
-    return out
+        groups.setdefault(g.untyped_storage().data_ptr(), []).append(g)
+    shared, single = [], []
+    for gs in groups.values():
+        g0 = gs[0]
+        if len(gs) == 1 and g0.is_contiguous() and g0.untyped_storage().nbytes() == g0.numel() * g0.element_size():
+            single.append(g0)
+        elif all(g.dtype == g0.dtype for g in gs):
+            st = g0.untyped_storage()
+            shared.append(torch.empty(0, dtype=g0.dtype, device=g0.device).set_(st, 0, (st.nbytes() // g0.element_size(),)))
+        else:
+            single.extend(gs)
+    return shared, single
 
 
 def sync_replica_gradients(params, group=None, average=False):
-    """Data-parallel replicas of a table that fits every GPU (SURVEY 8e "replicas only"): dense all-reduce of the fused
-    gradient buffers over NCCL / NVLink, in place -- what DistributedDataParallel does for the reference's RecBole / rechub
-    trainers (third_party/recbole/trainer/trainer.py:60-64), with one bucket per fused launch."""
+    """Data-parallel replicas of a table that fits every GPU (SURVEY 8e "replicas only"): dense all-reduce of the gradients
+    over NCCL / NVLink, in place -- what DistributedDataParallel does for the reference's RecBole / rechub trainers
+    (third_party/recbole/trainer/trainer.py:60-64) -- in as few collectives as the storage allows: one per fused gradient
+    buffer, and ONE flattened bucket for all gradients that own their storage (copied in and out, like a DDP bucket).
+    Returns the number of collectives issued."""
     import torch.distributed as dist
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
         return 0
-    bufs = fused_grad_buffers(params)
-    for b in bufs:
+    shared, single = fused_grad_buffers(params)
+    n = 0
+    for b in shared:
         dist.all_reduce(b, group=group)
         if average:
             b.div_(dist.get_world_size(group))
-    return len(bufs)
+        n += 1
+    by_kind = OrderedDict()
+    for g in single:
+        by_kind.setdefault((g.dtype, g.device), []).append(g)
+    for gs in by_kind.values():
+        if len(gs) == 1:
+            flat = gs[0]
+            dist.all_reduce(flat, group=group)
+            if average:
+                flat.div_(dist.get_world_size(group))
+        else:
+            flat = torch.cat([g.reshape(-1) for g in gs])
+            dist.all_reduce(flat, group=group)
+            if average:
+                flat.div_(dist.get_world_size(group))
+            parts = flat.split([g.numel() for g in gs])
+            if all(g.is_contiguous() for g in gs):
+                torch._foreach_copy_(gs, [c.view_as(g) for c, g in zip(parts, gs)])      # one multi-tensor launch
+            else:
+                for g, c in zip(gs, parts):
+                    g.copy_(c.reshape(g.shape))
+        n += 1
+    return n
 
 
 # =================================================================================================

@@ -103,19 +103,22 @@ def _replica_worker(rank, world, port, out_dir):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         from recbox_b200 import layers
-        # the shape a fused backward leaves behind: per-feature .grad tensors that are views of ONE buffer, plus a
-        # gradient with its own storage
+        # the shape a fused backward leaves behind: per-feature .grad tensors that alias ONE buffer (detached, so not
+        # "views" in autograd's sense), plus two gradients that own their storage
         buf = torch.arange(24, dtype=torch.float32) * (rank + 1)
-        ps = [torch.nn.Parameter(torch.zeros(4, 4)), torch.nn.Parameter(torch.zeros(2, 4)), torch.nn.Parameter(torch.zeros(3))]
-        ps[0].grad, ps[1].grad = buf[:16].view(4, 4), buf[16:24].view(2, 4)
+        ps = [torch.nn.Parameter(torch.zeros(4, 4)), torch.nn.Parameter(torch.zeros(2, 4)), torch.nn.Parameter(torch.zeros(3)),
+              torch.nn.Parameter(torch.zeros(2, 2))]
+        ps[0].grad, ps[1].grad = buf[:16].view(4, 4).detach(), buf[16:24].view(2, 4).detach()
         ps[2].grad = torch.full((3,), float(rank + 1))
-        bufs = layers.fused_grad_buffers(ps)
-        assert len(bufs) == 2 and bufs[0].data_ptr() == buf.data_ptr() and bufs[0].numel() == 24
-        assert layers.sync_replica_gradients(ps) == 2             # two collectives, not three
+        ps[3].grad = torch.full((2, 2), 10.0 * (rank + 1))
+        shared, single = layers.fused_grad_buffers(ps)
+        assert len(shared) == 1 and shared[0].data_ptr() == buf.data_ptr() and shared[0].numel() == 24 and len(single) == 2
+        assert layers.sync_replica_gradients(ps) == 2             # the fused buffer + one bucket for the rest, not four
         tot = sum(r + 1 for r in range(world))
         assert torch.equal(ps[0].grad, (torch.arange(16, dtype=torch.float32) * tot).view(4, 4))
         assert torch.equal(ps[1].grad, (torch.arange(16, 24, dtype=torch.float32) * tot).view(2, 4))
         assert torch.equal(ps[2].grad, torch.full((3,), float(tot)))
+        assert torch.equal(ps[3].grad, torch.full((2, 2), 10.0 * tot))
         open(os.path.join(out_dir, "ok%d" % rank), "w").write("ok")
     finally:
         dist.destroy_process_group()

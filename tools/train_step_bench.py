@@ -79,7 +79,7 @@ def make_batches(n, seed):
     return out
 
 
-def run_gpu(tf32, packed, steps=30, warmup=5, ours=False, precision=3, graph=False):
+def run_gpu(tf32, packed, steps=30, warmup=5, ours=False, precision=3, graph=False, fused_adam=False):
     """ours: MLP_Block on the tcgen05 GEMM (precision 3 = 3xTF32 fp32-level, 1 = plain TF32) instead of nn.Linear on cuBLAS;
     graph: the whole train step (device batch -> loss -> backward -> clip -> Adam) replayed from a CUDA graph."""
     from recbox_b200 import graphs, ops
@@ -89,7 +89,7 @@ def run_gpu(tf32, packed, steps=30, warmup=5, ours=False, precision=3, graph=Fal
     torch.manual_seed(0)
     fm = feature_map()
     model = DeepFM(fm, ours=ours).to(dev)
-    opt = torch.optim.Adam(model.parameters(), lr=1e-3, capturable=graph)
+    opt = torch.optim.Adam(model.parameters(), lr=1e-3, capturable=graph, fused=True if fused_adam else None)
     host = make_batches(4, 1)
     if packed:
         feed = [list(PackedDataLoader(fm, h, batch_size=B).bind(model.embedding_layer))[0] for h in host]
@@ -130,6 +130,7 @@ def run_gpu(tf32, packed, steps=30, warmup=5, ours=False, precision=3, graph=Fal
     return {"ms_per_step": ms, "samples_per_s": B / ms * 1e3, "input": "packed" if packed else "float64",
             "mlp": ("tcgen05 GEMM chain, %s" % ("3xTF32 (fp32-level)" if precision == 3 else "plain TF32")) if ours else
                    ("nn.Linear / cuBLAS, %s" % ("TF32" if tf32 else "fp32")),
+            "optimizer": "torch.optim.Adam(fused=True)" if fused_adam else "torch.optim.Adam (foreach, the reference's default)",
             "issue": "cuda-graph replay" if graph else "eager", "loss": float(loss), "steps": steps}
 
 
@@ -161,14 +162,19 @@ if __name__ == "__main__":
                 ("cublas_tf32_mlp_packed_batches", dict(tf32=True, packed=True)),
                 ("ours_3xtf32_mlp_packed_batches", dict(tf32=False, packed=True, ours=True, precision=3)),
                 ("ours_3xtf32_mlp_packed_batches_graph", dict(tf32=False, packed=True, ours=True, precision=3, graph=True)),
-                ("ours_tf32_mlp_packed_batches_graph", dict(tf32=False, packed=True, ours=True, precision=1, graph=True))]
+                ("ours_3xtf32_mlp_fused_adam_graph", dict(tf32=False, packed=True, ours=True, precision=3, graph=True, fused_adam=True)),
+                ("ours_tf32_mlp_fused_adam_graph", dict(tf32=False, packed=True, ours=True, precision=1, graph=True, fused_adam=True))]
+    only = os.environ.get("TS_ONLY")            # one variant, few steps (launch lists under ncu)
+    if only:
+        variants = [(n, dict(kw, steps=int(os.environ.get("TS_STEPS", "3")), warmup=2)) for n, kw in variants if n == only]
     for name, kw in variants:
         try:
             out[name] = run_gpu(**kw)
         except Exception as e:
             out[name] = {"error": repr(e)[:300]}
             torch.cuda.synchronize()
-    out["cpu_reference_port"] = run_cpu()
+    if not only:
+        out["cpu_reference_port"] = run_cpu()
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     with open(os.path.join(ROOT, "gpurun_out", tag + "_train_step.json"), "w") as f:
         json.dump(out, f, indent=1)
