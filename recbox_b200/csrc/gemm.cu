@@ -254,19 +254,22 @@ __global__ void __launch_bounds__(kThreads, 1) k_gemm_tc(const __grid_constant__
         mbar_wait(accum_bar, 0u);
         tc_fence_after();
         const int q = warp & 3;                        // TMEM lane quarter this warp may read
-        const int row = m0 + q * 32 + lane;
-        const bool row_ok = row < p.M;
-        float* crow = p.C + (int64_t)row * p.ldc;
-        const float* mrow = p.mask ? p.mask + (int64_t)row * p.ldmask : nullptr;
         const bool vec_ok = ((p.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0) &&
                             (!p.mask || (((p.ldmask & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.mask) & 15) == 0)));
         const bool first_split = blockIdx.z == 0;
-        const float tau = (p.filter && row_ok) ? __ldcg(p.tau + row) : __int_as_float(0x7f800000);
-        for (int c = 0; c < p.BN; c += 16) {
-            uint32_t r[16];
-            tc_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, r);
-            if (!row_ok) continue;
-            if (p.filter) {
+        if (p.filter) {
+            // ---- f3: keep what beats the row's running k-th best; nothing is stored ----
+            const int row = m0 + q * 32 + lane;
+            const bool row_ok = row < p.M;
+            const float tau = row_ok ? __ldcg(p.tau + row) : __int_as_float(0x7f800000);
+            for (int c = 0; c < p.BN; c += 16) {
+                uint32_t r[16];
+                tc_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, r);
+                if (!row_ok) continue;
+                float mx = __uint_as_float(r[0]);
+#pragma unroll
+                for (int e = 1; e < 16; ++e) mx = fmaxf(mx, __uint_as_float(r[e]));
+                if (!(mx > tau)) continue;
 #pragma unroll
                 for (int e = 0; e < 16; ++e) {
                     const float sc = __uint_as_float(r[e]);
@@ -276,57 +279,83 @@ __global__ void __launch_bounds__(kThreads, 1) k_gemm_tc(const __grid_constant__
                         if (pos < p.qcap) p.queue[(size_t)row * p.qcap + pos] = topk_key(sc, (uint32_t)(p.col_off + col));
                     }
                 }
-                continue;
             }
+        } else {
+            // ---- a13: tcgen05.ld hands a thread 16 columns of ONE row (a warp store would touch 32 different lines); the
+            // chunk is transposed through a per-warp shared-memory slab (the stage ring is idle by now) so that four lanes
+            // cover one row's 64 bytes and a warp instruction writes 8 rows of whole sectors -- and reads the ReLU mask and the
+            // bias the same way ----
+            const uint32_t slab = smem_base + (uint32_t)(warp - 2) * (32u * 80u);       // 32 rows x 20 floats
+            const int rsub = lane >> 2, cg = lane & 3;
+            for (int c = 0; c < p.BN; c += 16) {
+                uint32_t r[16];
+                tc_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, r);
 #pragma unroll
-            for (int g = 0; g < 4; ++g) {
-                const int col = n0 + c + 4 * g;
-                if (col >= p.N) break;
-                float v[4];
-#pragma unroll
-                for (int e = 0; e < 4; ++e) v[e] = __uint_as_float(r[4 * g + e]);
+                for (int g = 0; g < 4; ++g)
+                    asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(slab + (uint32_t)lane * 80u + 16u * g), "r"(r[4 * g]),
+                                 "r"(r[4 * g + 1]), "r"(r[4 * g + 2]), "r"(r[4 * g + 3])
+                                 : "memory");
+                __syncwarp();
+                const int col = n0 + c + 4 * cg;
+                const bool col_ok = col < p.N;
                 const bool full4 = vec_ok && col + 4 <= p.N;
-                if (p.bias && first_split) {
+                float bv[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+                if (p.bias && first_split && col_ok) {
                     if (col + 4 <= p.N && ((reinterpret_cast<uintptr_t>(p.bias) & 15) == 0)) {
-                        const float4 bv = __ldg(reinterpret_cast<const float4*>(p.bias + col));
-                        v[0] += bv.x; v[1] += bv.y; v[2] += bv.z; v[3] += bv.w;
+                        const float4 t4 = __ldg(reinterpret_cast<const float4*>(p.bias + col));
+                        bv[0] = t4.x; bv[1] = t4.y; bv[2] = t4.z; bv[3] = t4.w;
                     } else {
 #pragma unroll
                         for (int e = 0; e < 4; ++e)
-                            if (col + e < p.N) v[e] += __ldg(p.bias + col + e);
+                            if (col + e < p.N) bv[e] = __ldg(p.bias + col + e);
                     }
                 }
-                if (p.act == 1) {
 #pragma unroll
-                    for (int e = 0; e < 4; ++e) v[e] = fmaxf(v[e], 0.0f);
-                }
-                if (mrow) {
-                    if (full4) {
-                        const float4 mk = ld_stream_f4(mrow + col);
-                        v[0] = mk.x > 0.0f ? v[0] : 0.0f;
-                        v[1] = mk.y > 0.0f ? v[1] : 0.0f;
-                        v[2] = mk.z > 0.0f ? v[2] : 0.0f;
-                        v[3] = mk.w > 0.0f ? v[3] : 0.0f;
+                for (int i = 0; i < 4; ++i) {
+                    const int rr = 8 * i + rsub;
+                    const int row = m0 + q * 32 + rr;
+                    float v[4];
+                    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];"
+                                 : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3])
+                                 : "r"(slab + (uint32_t)rr * 80u + 16u * cg));
+                    if (row >= p.M || !col_ok) continue;
+                    float* crow = p.C + (int64_t)row * p.ldc;
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) v[e] += bv[e];
+                    if (p.act == 1) {
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) v[e] = fmaxf(v[e], 0.0f);
+                    }
+                    if (p.mask) {
+                        const float* mrow = p.mask + (int64_t)row * p.ldmask;
+                        if (full4) {
+                            const float4 mk = ld_stream_f4(mrow + col);
+                            v[0] = mk.x > 0.0f ? v[0] : 0.0f;
+                            v[1] = mk.y > 0.0f ? v[1] : 0.0f;
+                            v[2] = mk.z > 0.0f ? v[2] : 0.0f;
+                            v[3] = mk.w > 0.0f ? v[3] : 0.0f;
+                        } else {
+#pragma unroll
+                            for (int e = 0; e < 4; ++e)
+                                if (col + e < p.N) v[e] = mrow[col + e] > 0.0f ? v[e] : 0.0f;
+                        }
+                    }
+                    if (p.atomic) {
+                        if (full4) red_add_f4(crow + col, make_float4(v[0], v[1], v[2], v[3]));
+                        else {
+#pragma unroll
+                            for (int e = 0; e < 4; ++e)
+                                if (col + e < p.N) red_add_f1(crow + col + e, v[e]);
+                        }
+                    } else if (full4) {
+                        *reinterpret_cast<float4*>(crow + col) = make_float4(v[0], v[1], v[2], v[3]);
                     } else {
 #pragma unroll
                         for (int e = 0; e < 4; ++e)
-                            if (col + e < p.N) v[e] = mrow[col + e] > 0.0f ? v[e] : 0.0f;
+                            if (col + e < p.N) crow[col + e] = v[e];
                     }
                 }
-                if (p.atomic) {
-                    if (full4) red_add_f4(crow + col, make_float4(v[0], v[1], v[2], v[3]));
-                    else {
-#pragma unroll
-                        for (int e = 0; e < 4; ++e)
-                            if (col + e < p.N) red_add_f1(crow + col + e, v[e]);
-                    }
-                } else if (full4) {
-                    *reinterpret_cast<float4*>(crow + col) = make_float4(v[0], v[1], v[2], v[3]);
-                } else {
-#pragma unroll
-                    for (int e = 0; e < 4; ++e)
-                        if (col + e < p.N) crow[col + e] = v[e];
-                }
+                __syncwarp();                              // the slab is rewritten by the next chunk
             }
         }
     }
@@ -622,18 +651,256 @@ int launch_tc(const char* who, GemmArgs& g, const float* A, int64_t lda, const f
     return RBX_OK;
 }
 
+// =====================================================================================================================
+// f3 pass A, persistent form: one CTA per SM keeps its 128-user tile (raw + lo planes, every k-block) resident in shared
+// memory and streams 256-item tiles through a stage ring; two 256-column TMEM accumulators alternate, so the filter epilogue of
+// tile i runs under the MMAs of tile i + 1, and the per-tile fixed costs of the one-tile-per-CTA kernel (barrier init, TMEM
+// allocation, first TMA round trip, re-loading and re-splitting the user tile: ~4 us against 1.6 us of MMAs at D = 64) are
+// paid once per CTA.  10 warps: 0 TMA producer, 1 MMA issuer, 2..5 transform (lo planes), 6..9 filter epilogue.
+// =====================================================================================================================
+constexpr int kTkThreads = 320;
+constexpr int kTkBN = 256, kTkKB = 16;
+constexpr uint32_t kTkABlk = kBM * kTkKB * 4;       // 8 KB: one k-block of the user tile
+constexpr uint32_t kTkBBlk = kTkBN * kTkKB * 4;     // 16 KB: one k-block of an item tile
+
+struct TopkArgs {
+    CUtensorMap ta, tb;
+    int M, N, nkb, stages, tiles_n;
+    uint32_t idesc, desc_hi;
+    const float* tau;
+    int* count;
+    unsigned long long* queue;
+    int64_t qcap, col_off;
+};
+
+__global__ void __launch_bounds__(kTkThreads, 1) k_topk_tc(const __grid_constant__ TopkArgs p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t a_raw = smem_base, a_lo = a_raw + (uint32_t)p.nkb * kTkABlk;
+    const uint32_t b_ring = a_lo + (uint32_t)p.nkb * kTkABlk;
+    const uint32_t stage_bytes = 2 * kTkBBlk;                                    // raw | lo
+    const uint32_t bars = b_ring + (uint32_t)p.stages * stage_bytes;
+    auto full_bar = [&](int s) { return bars + 8u * s; };
+    auto xform_bar = [&](int s) { return bars + 8u * (kMaxStages + s); };
+    auto empty_bar = [&](int s) { return bars + 8u * (2 * kMaxStages + s); };
+    const uint32_t a_full = bars + 8u * (3 * kMaxStages), a_ready = a_full + 8u;
+    auto acc_full = [&](int b) { return a_ready + 8u + 8u * b; };
+    auto acc_empty = [&](int b) { return a_ready + 24u + 8u * b; };
+    const uint32_t tmem_slot = a_ready + 40u;
+    const int m0 = blockIdx.y * kBM;
+    int my_tiles = 0;
+    if ((int)blockIdx.x < p.tiles_n) my_tiles = (p.tiles_n - 1 - (int)blockIdx.x) / (int)gridDim.x + 1;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < p.stages; ++s) {
+            mbar_init(full_bar(s), 1);
+            mbar_init(xform_bar(s), 4);
+            mbar_init(empty_bar(s), 1);
+        }
+        mbar_init(a_full, 1);
+        mbar_init(a_ready, 4);
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(acc_full(b), 1);
+            mbar_init(acc_empty(b), 4);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    uint32_t tmem_base;
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+    if (warp == 0) {
+        // ===== TMA producer: the user tile once, then the item tiles =====
+        if (lane == 0 && my_tiles > 0) {
+            mbar_arrive_expect_tx(a_full, (uint32_t)p.nkb * kTkABlk);
+            for (int kb = 0; kb < p.nkb; ++kb) tma_load_2d(a_raw + (uint32_t)kb * kTkABlk, &p.ta, a_full, kb * kTkKB, m0);
+            int it = 0;
+            for (int j = 0; j < my_tiles; ++j) {
+                const int n0 = ((int)blockIdx.x + j * (int)gridDim.x) * kTkBN;
+                for (int kb = 0; kb < p.nkb; ++kb, ++it) {
+                    const int s = it % p.stages;
+                    const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
+                    mbar_wait(empty_bar(s), ph ^ 1u);
+                    mbar_arrive_expect_tx(full_bar(s), kTkBBlk);
+                    tma_load_2d(b_ring + (uint32_t)s * stage_bytes, &p.tb, full_bar(s), kb * kTkKB, n0);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer =====
+        if (lane == 0 && my_tiles > 0) {
+            mbar_wait(a_ready, 0u);
+            tc_fence_after();
+            int it = 0;
+            for (int j = 0; j < my_tiles; ++j) {
+                const int buf = j & 1;
+                mbar_wait(acc_empty(buf), ((uint32_t)(j >> 1) & 1u) ^ 1u);       // the epilogue drained this accumulator
+                tc_fence_after();
+                const uint32_t acc_addr = tmem_base + (uint32_t)buf * kTkBN;
+                uint32_t acc = 0;
+                for (int kb = 0; kb < p.nkb; ++kb, ++it) {
+                    const int s = it % p.stages;
+                    const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
+                    mbar_wait(xform_bar(s), ph);
+                    tc_fence_after();
+                    const uint32_t b_hi = b_ring + (uint32_t)s * stage_bytes, b_lo = b_hi + kTkBBlk;
+                    const uint32_t ah = a_raw + (uint32_t)kb * kTkABlk, al = a_lo + (uint32_t)kb * kTkABlk;
+#pragma unroll
+                    for (int k = 0; k < kTkKB / 8; ++k) {
+                        const uint64_t hi64 = (uint64_t)p.desc_hi << 32;
+                        const uint64_t da_hi = hi64 | ((1u << 16) | (((ah >> 4) + 2u * k) & 0x3fffu));
+                        const uint64_t da_lo = hi64 | ((1u << 16) | (((al >> 4) + 2u * k) & 0x3fffu));
+                        const uint64_t db_hi = hi64 | ((1u << 16) | (((b_hi >> 4) + 2u * k) & 0x3fffu));
+                        const uint64_t db_lo = hi64 | ((1u << 16) | (((b_lo >> 4) + 2u * k) & 0x3fffu));
+                        tc_mma_tf32(acc_addr, da_lo, db_hi, p.idesc, acc);
+                        tc_mma_tf32(acc_addr, da_hi, db_lo, p.idesc, 1u);
+                        tc_mma_tf32(acc_addr, da_hi, db_hi, p.idesc, 1u);
+                        acc = 1u;
+                    }
+                    tc_commit(empty_bar(s));
+                }
+                tc_commit(acc_full(buf));
+            }
+        }
+    } else if (warp < 6) {
+        // ===== transform warps: lo plane of the user tile once, then of every item stage =====
+        const int t = threadIdx.x - 64;          // 0..127
+        if (my_tiles > 0) {
+            auto split_plane = [&](uint32_t raw, uint32_t lo, uint32_t n16) {
+                for (uint32_t j0 = t; j0 < n16; j0 += 4 * 128) {
+                    float4 v[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const uint32_t j = j0 + 128u * u;
+                        if (j < n16)
+                            asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];"
+                                         : "=f"(v[u].x), "=f"(v[u].y), "=f"(v[u].z), "=f"(v[u].w)
+                                         : "r"(raw + 16u * j));
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const uint32_t j = j0 + 128u * u;
+                        if (j < n16)
+                            asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(lo + 16u * j), "f"(tf32_lo(v[u].x)), "f"(tf32_lo(v[u].y)),
+                                         "f"(tf32_lo(v[u].z)), "f"(tf32_lo(v[u].w))
+                                         : "memory");
+                    }
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                __syncwarp();
+            };
+            mbar_wait(a_full, 0u);
+            split_plane(a_raw, a_lo, ((uint32_t)p.nkb * kTkABlk) >> 4);
+            if (lane == 0) mbar_arrive(a_ready);
+            const int total = my_tiles * p.nkb;
+            for (int it = 0; it < total; ++it) {
+                const int s = it % p.stages;
+                const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
+                mbar_wait(full_bar(s), ph);
+                const uint32_t raw = b_ring + (uint32_t)s * stage_bytes;
+                split_plane(raw, raw + kTkBBlk, kTkBBlk >> 4);
+                if (lane == 0) mbar_arrive(xform_bar(s));
+            }
+        }
+    } else {
+        // ===== filter epilogue: a thread owns one user row of the tile =====
+        const int q = warp & 3;
+        const int row = m0 + q * 32 + lane;
+        const bool row_ok = row < p.M;
+        const float tau = row_ok ? __ldcg(p.tau + row) : __int_as_float(0x7f800000);
+        for (int j = 0; j < my_tiles; ++j) {
+            const int buf = j & 1;
+            const int n0 = ((int)blockIdx.x + j * (int)gridDim.x) * kTkBN;
+            mbar_wait(acc_full(buf), (uint32_t)(j >> 1) & 1u);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)buf * kTkBN;
+            for (int c = 0; c < kTkBN; c += 16) {
+                uint32_t r[16];
+                tc_ld16(taddr + (uint32_t)c, r);
+                if (!row_ok) continue;
+                // survivors are rare once tau has tightened (~k * chunk / seen per user and pass): one max over the 16 scores
+                // decides whether the slow path runs at all
+                float mx = __uint_as_float(r[0]);
+#pragma unroll
+                for (int e = 1; e < 16; ++e) mx = fmaxf(mx, __uint_as_float(r[e]));
+                if (!(mx > tau)) continue;
+#pragma unroll
+                for (int e = 0; e < 16; ++e) {
+                    const float sc = __uint_as_float(r[e]);
+                    const int col = n0 + c + e;
+                    if (sc > tau && col < p.N) {
+                        const int pos = atomicAdd(p.count + row, 1);
+                        if (pos < p.qcap) p.queue[(size_t)row * p.qcap + pos] = topk_key(sc, (uint32_t)(p.col_off + col));
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(acc_empty(buf));
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    }
+}
+
 }  // namespace
 
 // f3 pass A on the tensor cores (called from csrc/topk.cu): scores of users [0, U) against items [n0, n1) as a 3xTF32 GEMM
-// whose epilogue keeps only what beats the user's running k-th best.  Two 48 KB stages per CTA, so two CTAs share an SM and
-// one tile's loads / filter epilogue run under the other's MMAs.
+// whose epilogue keeps only what beats the user's running k-th best.  Default: the persistent kernel above; RBX_TOPK_PERSIST=0
+// (or a chunk of fewer item tiles than CTAs) runs the one-tile-per-CTA GEMM with the filter epilogue.
 int rbx_topk_filter_tc(const float* q, const float* items, int64_t U, int64_t n0, int64_t n1, int D, const float* tau, int* count,
                        unsigned long long* queue, int64_t qcap, cudaStream_t st) {
+    const char* who = "rbx_topk_ip";
+    const int64_t N = n1 - n0;
+    const int tiles_n = (int)((N + kTkBN - 1) / kTkBN), tiles_m = (int)((U + kBM - 1) / kBM);
+    const int sms = rbx_sm_count();
+    if (env_int("RBX_TOPK_PERSIST", 1) && tiles_m <= 65535 && (int64_t)tiles_n * tiles_m >= 2 * sms) {
+        TopkArgs a;
+        memset(&a, 0, sizeof(a));
+        a.M = (int)U; a.N = (int)N; a.nkb = (D + kTkKB - 1) / kTkKB; a.tiles_n = tiles_n;
+        a.tau = tau; a.count = count; a.queue = queue; a.qcap = qcap; a.col_off = n0;
+        const uint32_t bar_bytes = 8u * (3 * kMaxStages + 8);
+        const uint32_t fixed = 2u * (uint32_t)a.nkb * kTkABlk + bar_bytes + 1024u;
+        int stages = (int)((227u * 1024u - fixed) / (2 * kTkBBlk));
+        if (stages > kMaxStages) stages = kMaxStages;
+        RBX_REQUIRE(stages >= 2, "%s: D=%d does not fit the persistent top-k kernel", who, D);
+        a.stages = stages;
+        a.idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kTkBN >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24);
+        a.desc_hi = ((uint32_t)(8 * kTkKB * 4) >> 4) | (1u << 14) | (4u << 29);              // K-major, 64-byte swizzle, SBO = 8 rows
+        if (int rc = make_map(&a.ta, q, D, U, D, kTkKB, kBM, CU_TENSOR_MAP_SWIZZLE_64B, who)) return rc;
+        if (int rc = make_map(&a.tb, items + (size_t)n0 * D, D, N, D, kTkKB, kTkBN, CU_TENSOR_MAP_SWIZZLE_64B, who)) return rc;
+        static bool attr_set[64];
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (dev >= 0 && dev < 64 && !attr_set[dev]) {
+            cudaError_t e = cudaFuncSetAttribute(k_topk_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+            if (e != cudaSuccess) return rbx_fail(RBX_ERR_CUDA, "%s: cudaFuncSetAttribute: %s", who, cudaGetErrorString(e));
+            attr_set[dev] = true;
+        }
+        int gx = sms / tiles_m;                     // one CTA per SM; user tiles of the same item range run side by side (L2)
+        if (gx < 1) gx = 1;
+        if (gx > tiles_n) gx = tiles_n;
+        const size_t smem = fixed + (size_t)stages * 2 * kTkBBlk;
+        k_topk_tc<<<dim3(gx, tiles_m), kTkThreads, smem, st>>>(a);
+        RBX_LAUNCH_CHECK(who);
+        return RBX_OK;
+    }
     GemmArgs g;
     memset(&g, 0, sizeof(g));
     g.prec = 3;
     g.filter = 1; g.tau = tau; g.count = count; g.queue = queue; g.qcap = qcap; g.col_off = n0;
-    return launch_tc("rbx_topk_ip", g, q, D, items + (size_t)n0 * D, D, U, n1 - n0, D, 256, 16, 2, false, 0, st);
+    return launch_tc(who, g, q, D, items + (size_t)n0 * D, D, U, n1 - n0, D, 256, 16, 2, false, 0, st);
 }
 
 extern "C" {

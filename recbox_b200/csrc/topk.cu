@@ -285,9 +285,13 @@ __global__ void __launch_bounds__(kT) k_select(unsigned long long* __restrict__ 
     for (int i = threadIdx.x; i < Kp; i += kT) s[i] = R[(size_t)u * Kp + i];
     for (int off = 0; off < cnt; off += T) {
         const int here = min(T, cnt - off);
-        for (int i = threadIdx.x; i < T; i += kT) s[Kp + i] = i < here ? queue[(size_t)u * qcap + off + i] : 0ull;
+        // sort only as many keys as there are: late in a search a user keeps a handful of candidates per pass, and a
+        // 256-key network is ~15x cheaper than the 2048-key one
+        int n_sort = 2 * Kp;
+        while (n_sort < Kp + here) n_sort <<= 1;
+        for (int i = threadIdx.x; i < n_sort - Kp; i += kT) s[Kp + i] = i < here ? queue[(size_t)u * qcap + off + i] : 0ull;
         __syncthreads();
-        bitonic_desc(s, kSortN);                         // ends with a barrier; the best Kp keys are s[0..Kp)
+        bitonic_desc(s, n_sort);                         // ends with a barrier; the best Kp keys are s[0..Kp)
     }
     for (int i = threadIdx.x; i < Kp; i += kT) R[(size_t)u * Kp + i] = s[i];
     if (threadIdx.x == 0) {
