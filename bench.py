@@ -284,7 +284,7 @@ def main_reference(args, rank, world):
 def workload_config(ids_kind, world):
     par = ("1 GPU" if world == 1 else
            "dp%d replicas of the 1M-row table, each on its own batch shard; the fused dense gradient buffer (68 MB) is "
-           "all-reduced over NCCL/NVLink INSIDE the timed step (SURVEY 8e 'replicas only')" % world)
+           "all-reduced over NVLink / NVSwitch INSIDE the timed step (SURVEY 8e 'replicas only'; kernels.all_reduce.path says how)" % world)
     return {"workload": "BASELINE configs[1] DeepFM hot path: 26 cat + 13 dense, 26x38462 = 1000012-row fused table, "
                         "D=16, B=65536 per GPU; fused gather+FM+LR fwd, dense-grad zero (side stream, under the fwd) + scatter-add bwd; "
                         "MLP tail outside the path",
@@ -338,7 +338,15 @@ def main_b200(args, rank, world, local_rank):
     offs = [0]
     for n in sizes:
         offs.append((offs[-1] + n + 3) // 4 * 4)
-    gbuf = torch.zeros(offs[-1], device=dev)
+    # replicas (N > 1): the buffer lives in symmetric multicast memory and is summed by the in-switch all-reduce kernel
+    # (recbox_b200.replica.ReplicaReducer -> rbx_nvls_allreduce_f32); --allreduce nccl keeps torch.distributed's collective
+    reducer = None
+    if world > 1 and (args.allreduce == "nvls" or (args.allreduce == "auto" and world >= 8)):
+        from recbox_b200 import replica
+        reducer = replica.ReplicaReducer(offs[-1], dev)
+        gbuf = reducer.buffer
+    else:
+        gbuf = torch.zeros(offs[-1], device=dev)
     g_table = gbuf[offs[0]:offs[0] + R * D].view(R, D)
     g_table_lr = gbuf[offs[1]:offs[1] + R]
     g_dense_w = gbuf[offs[2]:offs[2] + Fn * D].view(Fn, D)
@@ -399,8 +407,8 @@ def main_b200(args, rank, world, local_rank):
             out = graphed[i % NB]()
         else:
             out = kernels_step(i, evs)
-        if world > 1:
-            dist.all_reduce(gbuf)              # replicas train ONE model: dense gradient exchange inside the step
+        if world > 1:                          # replicas train ONE model: dense gradient exchange inside the step
+            reducer.all_reduce() if reducer is not None else dist.all_reduce(gbuf)
         if evs: evs[4].record()
         return out
 
@@ -578,9 +586,9 @@ def main_b200(args, rank, world, local_rank):
                 ev_read[j].record(d2h)
             if world > 1:                                    # the replicas' gradient exchange belongs to the step; issued eagerly
                 if mode == "ops":                            # after the replay (a graph that holds NCCL kernels hung the
-                    dist.all_reduce(gbuf)                    # process-group teardown in run r2t)
+                    reducer.all_reduce() if reducer is not None else dist.all_reduce(gbuf)   # process-group teardown in run r2t)
                 else:
-                    layers.sync_replica_gradients(params)
+                    layers.sync_replica_gradients(params, reducer=reducer)
             ev_free[j].record(main)                          # the backward still reads the copied blocks
 
         def run(n):
@@ -634,8 +642,8 @@ def main_b200(args, rank, world, local_rank):
                                                                                   "exposed_ms": t_w},
                 "embed_fm_bwd(+dense_w_bwd)": {"ms": t_b, "alg_bytes": bb, "gbs": bb / t_b / 1e6}}
         if world > 1:
-            kern["nccl_all_reduce(grad buffer)"] = {"ms": t_ar, "bytes": offs[-1] * 4,
-                                                    "busbw_gbs": 2 * (world - 1) / world * offs[-1] * 4 / t_ar / 1e6}
+            kern["all_reduce(grad buffer)"] = {"ms": t_ar, "bytes": offs[-1] * 4, "path": reducer.path if reducer is not None else "NCCL all_reduce",
+                                               "busbw_gbs": 2 * (world - 1) / world * offs[-1] * 4 / t_ar / 1e6}
         if t_f_graph is not None:
             kern["graph_regime"] = {
                 "what": "the regime `value` is measured in (CUDA-graph replay, launches back to back, no events between them): "
@@ -670,7 +678,8 @@ def main_b200(args, rank, world, local_rank):
                     "(h5_dataloader.py:46; 320 B/sample), pinned -- the compatibility number"),
             "e2e_ops": None if args.no_e2e else e2e_obj("ops", "below the layer API: recbox_b200.ops on int32 packed blocks (160 B/sample), pinned"),
             # ours per step: k_embed_fm_fwd + k_zero_f32 + k_embed_fm_bwd; library: the NCCL all-reduce at N > 1
-            "gpu_launches": 3 * K, "library_launches": K if world > 1 else 0,
+            "gpu_launches": (3 + (1 if (reducer is not None and reducer.mc) else 0)) * K,
+            "library_launches": (K if reducer is None else 2 * K) if world > 1 else 0,      # NCCL all-reduce, or the two barrier launches around ours
             "issue": "cuda-graph replay (one graph per rotating batch)" if graphed is not None else "eager",
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                          "traffic": ncu_traffic(dom) if args.ids == "uniform" else None, "peak_source": peak_src, "how": how,
@@ -938,6 +947,9 @@ def main():
     ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end leg (profiling runs under ncu)")
     ap.add_argument("--zero", default="side", choices=["side", "inline"],
                     help="gradient zero-fill on a side stream under the forward (default) or on the step's stream before it")
+    ap.add_argument("--allreduce", default="auto", choices=["auto", "nvls", "nccl"],
+                    help="replica gradient exchange at N > 1: in-switch all-reduce kernel over multicast memory or NCCL; auto = the "
+                         "faster one measured at that N (r2ad / r2ae: NCCL 157 / 201 us at N = 2 / 4, the kernel 205 us at N = 8 vs NCCL 284)")
     ap.add_argument("--eager", action="store_true", help="layer-API e2e legs without CUDA-graph replay (host-bound: ~80 Parameters cross autograd)")
     ap.add_argument("--no-sharded", action="store_true", help="cfg2 run without the attached configs[3] (100M-row sharded table) object")
     ap.add_argument("--workload", default="cfg2", choices=["cfg2", "sharded", "dssm", "sasrec"],

@@ -538,6 +538,16 @@ int rbx_colsum_f32(const float* X /*DEVICE [M,N] pitch ldx*/, int64_t ldx, float
                    int accumulate, rbx_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
+ * e  replicas: in-switch all-reduce of the fused gradient buffer (csrc/allreduce.cu)
+ * The reference's multi-device mode is DistributedDataParallel over replicas (third_party/recbole/trainer/trainer.py:48-64,
+ * third_party/rechub/trainers/ctr_trainer.py:43): the dense gradients are all-reduced once per step.  mc is the MULTICAST
+ * address of a symmetric buffer of n floats (n % 4 == 0) that every rank of the NVSwitch domain has mapped; rank r sums
+ * floats [r n / world, (r+1) n / world) across all copies with multimem.ld_reduce and writes the sums back to all copies
+ * with multimem.st.  The caller brackets the call with cross-rank barriers.
+ * ------------------------------------------------------------------------------------------ */
+int rbx_nvls_allreduce_f32(float* mc /*DEVICE multicast address*/, int64_t n, int rank, int world, rbx_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
  * f3  retrieval evaluation (csrc/topk.cu)
  * rbx_topk_ip replaces FaissIndex.search = faiss.IndexFlatIP(dim).search(query, topk)
  * (recbox/utils/ann/faiss.py:3-14; called from evaluate_block, recbox/core/metrics.py:52-54):

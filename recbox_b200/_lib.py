@@ -132,6 +132,7 @@ SIGNATURES = {
     "rbx_sample_negatives": [_I64, _I, _I64, _c.c_uint64, _P, _P, _P, _P, _P, _P, _P],
     "rbx_gemm_f32": [_P, _I64, _I, _P, _I64, _I, _P, _I64, _I64, _I64, _I64, _P, _I, _P, _I64, _I, _I, _P],
     "rbx_colsum_f32": [_P, _I64, _P, _I64, _I64, _I, _P],
+    "rbx_nvls_allreduce_f32": [_P, _I64, _I, _I, _P],
     "rbx_topk_ws_bytes": [_I64, _I, _I64],
     "rbx_topk_ip": [_P, _P, _I64, _I64, _I, _I, _I64, _P, _P, _P, _c.c_size_t, _P],
     "rbx_rank_metrics": [_P, _I, _I64, _P, _P, _P, _P, _I, _P, _P, _I, _P, _P, _P, _P],

@@ -362,7 +362,7 @@ def fused_grad_buffers(params):
     return shared, single
 
 
-def sync_replica_gradients(params, group=None, average=False):
+def sync_replica_gradients(params, group=None, average=False, reducer=None):
     """Data-parallel replicas of a table that fits every GPU (SURVEY 8e "replicas only"): dense all-reduce of the gradients
     over NCCL / NVLink, in place -- what DistributedDataParallel does for the reference's RecBole / rechub trainers
     (third_party/recbole/trainer/trainer.py:60-64) -- in as few collectives as the storage allows: one per fused gradient
@@ -374,9 +374,12 @@ def sync_replica_gradients(params, group=None, average=False):
     shared, single = fused_grad_buffers(params)
     n = 0
     for b in shared:
-        dist.all_reduce(b, group=group)
-        if average:
-            b.div_(dist.get_world_size(group))
+        if reducer is not None and b.numel() <= reducer.numel:      # recbox_b200.replica.ReplicaReducer: in-switch all-reduce
+            reducer.reduce_tensor(b, average)
+        else:
+            dist.all_reduce(b, group=group)
+            if average:
+                b.div_(dist.get_world_size(group))
         n += 1
     by_kind = OrderedDict()
     for g in single:

@@ -1,0 +1,71 @@
+"""Gradient exchange of data-parallel REPLICAS (SURVEY.md section 8e "replicas only": the table fits every GPU, each rank runs
+the path on its own batch shard and the dense gradients are summed once per step -- the reference's multi-device mode,
+DistributedDataParallel in third_party/recbole/trainer/trainer.py:48-64).
+
+`ReplicaReducer` owns a symmetric (CUDA VMM, multicast-mapped) fp32 buffer and sums it across the ranks with the in-switch
+all-reduce kernel of csrc/allreduce.cu (rbx_nvls_allreduce_f32: multimem.ld_reduce + multimem.st over NVLink / NVSwitch);
+where multicast memory is not available (no NVSwitch, a gloo group in the CPU tests) it falls back to the collective of
+torch.distributed and says so in `.path`."""
+import ctypes
+
+import torch
+import torch.distributed as dist
+
+from . import _lib
+from ._lib import RbxError
+
+
+class ReplicaReducer(object):
+    def __init__(self, numel, device, group=None):
+        self.group = group if group is not None else dist.group.WORLD
+        self.world, self.rank = dist.get_world_size(self.group), dist.get_rank(self.group)
+        self.numel = (int(numel) + 3) // 4 * 4
+        self.device = torch.device(device)
+        self.hdl, self.mc = None, 0
+        self.path = "torch.distributed all_reduce"
+        if self.device.type == "cuda" and self.world > 1:
+            try:
+                import torch.distributed._symmetric_memory as symm_mem
+                self.buffer = symm_mem.empty(self.numel, dtype=torch.float32, device=self.device)
+                self.hdl = symm_mem.rendezvous(self.buffer, self.group)
+                self.mc = int(self.hdl.multicast_ptr or 0)
+                if self.mc:
+                    self.path = "rbx_nvls_allreduce_f32 (multimem.ld_reduce / multimem.st over NVSwitch multicast memory)"
+            except Exception as e:                      # no symmetric memory on this system: plain allocation + NCCL
+                self.hdl, self.mc = None, 0
+                self.path = "torch.distributed all_reduce (symmetric memory unavailable: %s)" % str(e)[:80]
+        if self.hdl is None:
+            self.buffer = torch.empty(self.numel, dtype=torch.float32, device=self.device)
+        self.buffer.zero_()
+
+    def all_reduce(self, average=False):
+        """Sum `self.buffer` over the ranks, in place, on the current stream."""
+        if self.world == 1:
+            return self.buffer
+        if self.mc:
+            lib = _lib.load()
+            with torch.cuda.device(self.device):
+                self.hdl.barrier(channel=0)            # every rank's contribution is written
+                rc = lib.rbx_nvls_allreduce_f32(ctypes.c_void_p(self.mc), self.numel, self.rank, self.world,
+                                                ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream))
+                if rc != 0:
+                    raise RbxError("rbx_nvls_allreduce_f32 failed (%d): %s" % (rc, lib.rbx_last_error().decode()))
+                self.hdl.barrier(channel=1)            # every slice is reduced and broadcast
+        else:
+            dist.all_reduce(self.buffer, group=self.group)
+        if average:
+            self.buffer.div_(self.world)
+        return self.buffer
+
+    def reduce_tensor(self, t, average=False):
+        """All-reduce an arbitrary contiguous fp32 tensor through the symmetric buffer (copy in, reduce, copy out)."""
+        n = t.numel()
+        if n > self.numel:
+            raise RbxError("ReplicaReducer: tensor of %d floats exceeds the %d-float buffer" % (n, self.numel))
+        flat = t.reshape(-1)
+        self.buffer[:n].copy_(flat)
+        if n < self.numel:
+            self.buffer[n:].zero_()
+        self.all_reduce(average)
+        flat.copy_(self.buffer[:n])
+        return t

@@ -130,3 +130,31 @@ def test_replica_gradient_sync_world2_gloo(tmp_path):
     world = 2
     mp.spawn(_replica_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
     assert all(os.path.exists(os.path.join(str(tmp_path), "ok%d" % r)) for r in range(world))
+
+
+def _reducer_worker(rank, world, port, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from recbox_b200 import layers, replica
+        red = replica.ReplicaReducer(10, "cpu")              # no multicast memory on the host: the collective fallback
+        assert red.numel == 12 and red.mc == 0 and "all_reduce" in red.path
+        red.buffer.copy_(torch.arange(12, dtype=torch.float32) * (rank + 1))
+        tot = sum(r + 1 for r in range(world))
+        assert torch.equal(red.all_reduce(), torch.arange(12, dtype=torch.float32) * tot)
+        t = torch.full((7,), float(rank + 1))
+        assert torch.equal(red.reduce_tensor(t, average=True), torch.full((7,), tot / world))
+        buf = torch.arange(8, dtype=torch.float32) * (rank + 1)
+        ps = [torch.nn.Parameter(torch.zeros(4)), torch.nn.Parameter(torch.zeros(4))]
+        ps[0].grad, ps[1].grad = buf[:4].detach(), buf[4:].detach()
+        assert layers.sync_replica_gradients(ps, reducer=red) == 1
+        assert torch.equal(ps[1].grad, torch.arange(4, 8, dtype=torch.float32) * tot)
+        open(os.path.join(out_dir, "ok%d" % rank), "w").write("ok")
+    finally:
+        dist.destroy_process_group()
+
+
+def test_replica_reducer_fallback_world2_gloo(tmp_path):
+    world = 2
+    mp.spawn(_reducer_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    assert all(os.path.exists(os.path.join(str(tmp_path), "ok%d" % r)) for r in range(world))

@@ -142,3 +142,37 @@ def test_sharded_rowlr_layout_matches_single_table(D, tmp_path):
     world, mode = _world(), "peer_rowlr"
     mp.spawn(_worker, args=(world, _free_port(), mode, D, str(tmp_path)), nprocs=world, join=True)
     assert all(os.path.exists(os.path.join(str(tmp_path), "ok%d" % r)) for r in range(world))
+
+
+def _reducer_worker(rank, world, port, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    try:
+        from recbox_b200 import layers, replica
+        n = 1_000_003                                   # not a multiple of 4 * world: ragged slices
+        red = replica.ReplicaReducer(n, dev)
+        g = torch.Generator().manual_seed(7)
+        parts = [torch.randn(red.numel, generator=g) for _ in range(world)]
+        want = torch.stack(parts).double().sum(0)
+        for it in range(3):                             # repeated use: the barriers re-arm
+            red.buffer.copy_(parts[rank].to(dev))
+            got = red.all_reduce()
+            assert_close(got, want, rtol=1e-6, atol_scale=1e-6, what="all_reduce[%s] pass %d" % (red.path[:24], it))
+        t = parts[rank][:777].to(dev).clone()
+        red.reduce_tensor(t, average=True)
+        assert_close(t, want[:777] / world, rtol=1e-6, atol_scale=1e-6, what="reduce_tensor")
+        open(os.path.join(out_dir, "ok%d" % rank), "w").write(red.path)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_replica_reducer_in_switch_all_reduce(tmp_path):
+    """Replica gradient exchange (SURVEY 8e "replicas only"): rbx_nvls_allreduce_f32 over multicast memory (or the collective
+    fallback where the box has no NVSwitch multicast) sums the symmetric buffer of every rank."""
+    world = _world()
+    if world < 2:
+        pytest.skip("needs at least two GPUs")
+    mp.spawn(_reducer_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    assert all(os.path.exists(os.path.join(str(tmp_path), "ok%d" % r)) for r in range(world))
