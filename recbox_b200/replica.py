@@ -60,6 +60,8 @@ class ReplicaReducer(object):
     def reduce_tensor(self, t, average=False):
         """All-reduce an arbitrary contiguous fp32 tensor through the symmetric buffer (copy in, reduce, copy out)."""
         n = t.numel()
+        if not t.is_contiguous() or t.dtype != torch.float32:
+            raise RbxError("ReplicaReducer.reduce_tensor: needs a contiguous fp32 tensor")
         if n > self.numel:
             raise RbxError("ReplicaReducer: tensor of %d floats exceeds the %d-float buffer" % (n, self.numel))
         flat = t.reshape(-1)

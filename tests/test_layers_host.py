@@ -260,3 +260,20 @@ def test_mlp_block_constructor_matches_reference_init():
             assert torch.equal(v, want[k]), (tag, k)
     with pytest.raises(layers.RbxError):              # no CPU path for the Linear layers either
         cases["plain"]()(torch.zeros(2, 104))
+
+
+def test_dense_tail_ops_have_no_cpu_path():
+    """a13 / f4 host side: the GEMM wrappers and the blocks built on them refuse CPU tensors loudly."""
+    from recbox_b200 import blocks, ops
+    with pytest.raises(layers.RbxError):
+        ops.gemm(torch.zeros(4, 8), torch.zeros(2, 8))
+    with pytest.raises(layers.RbxError):
+        ops.colsum(torch.zeros(4, 8))
+    with pytest.raises(layers.RbxError):
+        blocks.linear(torch.zeros(4, 8), torch.zeros(2, 8))
+    with pytest.raises(layers.RbxError):
+        blocks.CrossNetV2(8, 2)(torch.zeros(4, 8))
+    m = blocks.CompressedInteractionNet(3, [4, 2])          # constructor parity: the reference's parameter names
+    assert sorted(m.state_dict()) == ["cin_layer.layer_1.bias", "cin_layer.layer_1.weight", "cin_layer.layer_2.bias",
+                                      "cin_layer.layer_2.weight", "fc.bias", "fc.weight"]
+    assert tuple(m.cin_layer["layer_1"].weight.shape) == (4, 9, 1) and tuple(m.cin_layer["layer_2"].weight.shape) == (2, 12, 1)
