@@ -71,3 +71,48 @@ class ReplicaReducer(object):
         self.all_reduce(average)
         flat.copy_(self.buffer[:n])
         return t
+
+
+class SparseRowExchange(object):
+    """Gradient exchange of replicas whose batch touches only a sliver of the table ("switching to a
+    sparse all_gather of (row-id, row-grad) pairs when B_loc * F << rows" -- the 10 M-row item table of configs[2], the 1 M-row
+    table of configs[4]): every rank lists the rows its batch touched (rbx_unique_ids), gathers their gradient rows
+    (rbx_gather_rows), all ranks all_gather the fixed-capacity (ids, rows) blocks, and each adds the OTHER ranks' rows into
+    its dense gradient table (rbx_scatter_add_rows; ids of -1 pad the blocks and are skipped).  No host synchronisation: the
+    capacity is the batch's id count, the unique count stays on the device.  Afterwards every replica holds the summed
+    gradient on the union of the touched rows, which `exchange` returns for the touched-rows optimizer.
+
+    kern: provider of unique_ids / gather_rows / scatter_add_rows (recbox_b200.ops; a CPU stand-in in the gloo tests)."""
+
+    def __init__(self, R, D, max_ids, device, group=None, kern=None):
+        if kern is None:
+            from . import ops as kern
+        self.kern = kern
+        self.group = group if group is not None else dist.group.WORLD
+        self.world, self.rank = dist.get_world_size(self.group), dist.get_rank(self.group)
+        self.R, self.D, self.cap = int(R), int(D), int(max_ids)
+        dev = torch.device(device)
+        self.ids_all = torch.empty((self.world, self.cap), dtype=torch.int32, device=dev)
+        self.rows_all = torch.empty((self.world, self.cap, self.D), dtype=torch.float32, device=dev)
+        self._slot = torch.arange(self.cap, device=dev)
+
+    def exchange(self, g_table, rows):
+        """g_table [R, D]: this rank's dense gradient table (its own contributions already scattered in); rows: the int32 row
+        ids this rank's batch touched (any shape, duplicates welcome, at most max_ids of them).
+        -> int32 [world * cap] ids touched by ANY rank (-1 = padding), for TouchedRowsOptimizer.step."""
+        flat = rows.reshape(-1)
+        if flat.numel() > self.cap:
+            raise RbxError("SparseRowExchange: %d ids exceed the capacity %d" % (flat.numel(), self.cap))
+        uniq, _, _, n_out = self.kern.unique_ids(flat, self.R, want_first=False, want_inverse=False, sync=False)
+        mine = self.ids_all[self.rank]
+        mine.fill_(-1)
+        k = uniq.numel()
+        mine[:k] = torch.where(self._slot[:k] < n_out[0], uniq.to(torch.int32), torch.full_like(uniq, -1, dtype=torch.int32))
+        self.rows_all[self.rank] = self.kern.gather_rows(g_table, mine)
+        if self.world > 1:
+            dist.all_gather_into_tensor(self.ids_all.view(-1), mine.clone(), group=self.group)
+            dist.all_gather_into_tensor(self.rows_all.view(-1), self.rows_all[self.rank].reshape(-1).clone(), group=self.group)
+            for w in range(self.world):
+                if w != self.rank:
+                    self.kern.scatter_add_rows(self.rows_all[w], self.ids_all[w], -1, g_table)
+        return self.ids_all.view(-1)

@@ -158,3 +158,58 @@ def test_replica_reducer_fallback_world2_gloo(tmp_path):
     world = 2
     mp.spawn(_reducer_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
     assert all(os.path.exists(os.path.join(str(tmp_path), "ok%d" % r)) for r in range(world))
+
+
+class _SparseKern(CpuKern):
+    """CPU stand-ins for the three kernels SparseRowExchange calls."""
+
+    @staticmethod
+    def unique_ids(ids, vocab, want_first=True, want_inverse=True, sync=True):
+        u = torch.unique(ids.reshape(-1))
+        cap = max(min(ids.numel(), vocab), 1)
+        buf = torch.full((cap,), 12345, dtype=ids.dtype)          # capacity buffer, garbage past the count (as on the GPU)
+        buf[:u.numel()] = u
+        return buf, None, None, torch.tensor([u.numel(), 0])
+
+    @staticmethod
+    def gather_rows(table, ids):
+        out = torch.zeros(tuple(ids.shape) + (table.shape[1],))
+        ok = ids >= 0
+        out[ok] = table[ids[ok].long()]
+        return out
+
+    @staticmethod
+    def scatter_add_rows(g, ids, pad_row, g_table):
+        keep = (ids >= 0) & (ids != pad_row)
+        g_table.index_add_(0, ids[keep].long(), g[keep])
+
+
+def _sparse_worker(rank, world, port, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from recbox_b200 import replica
+        R, D, n = 50, 4, 12
+        gen = torch.Generator().manual_seed(3)
+        rows = [torch.randint(0, R, (n,), generator=gen, dtype=torch.int32) for _ in range(world)]
+        grads = [torch.randn(n, D, generator=gen) for _ in range(world)]
+        want = torch.zeros(R, D)
+        for r_, g_ in zip(rows, grads):
+            want.index_add_(0, r_.long(), g_)
+        g_table = torch.zeros(R, D)
+        g_table.index_add_(0, rows[rank].long(), grads[rank])           # the local backward
+        ex = replica.SparseRowExchange(R, D, n, "cpu", kern=_SparseKern)
+        touched = ex.exchange(g_table, rows[rank])
+        assert torch.allclose(g_table, want, atol=1e-6)
+        assert set(touched[touched >= 0].tolist()) == set(torch.cat(rows).tolist())
+        open(os.path.join(out_dir, "ok%d" % rank), "w").write("ok")
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sparse_row_exchange_world2_gloo(tmp_path):
+    """Replicas of a table the batch barely touches: all_gather of (row id, gradient row) blocks, every replica ends with the
+    summed gradient on the union of the touched rows."""
+    world = 2
+    mp.spawn(_sparse_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    assert all(os.path.exists(os.path.join(str(tmp_path), "ok%d" % r)) for r in range(world))

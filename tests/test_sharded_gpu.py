@@ -176,3 +176,45 @@ def test_replica_reducer_in_switch_all_reduce(tmp_path):
         pytest.skip("needs at least two GPUs")
     mp.spawn(_reducer_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
     assert all(os.path.exists(os.path.join(str(tmp_path), "ok%d" % r)) for r in range(world))
+
+
+def _sparse_worker(rank, world, port, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    try:
+        from recbox_b200 import ops, optim, replica
+        R, D, n = 100_003, 64, 5000
+        gen = torch.Generator().manual_seed(3)
+        rows = [torch.randint(0, R, (n,), generator=gen, dtype=torch.int32) for _ in range(world)]
+        grads = [torch.randn(n, D, generator=gen) for _ in range(world)]
+        want = torch.zeros(R, D)
+        for r_, g_ in zip(rows, grads):
+            want.index_add_(0, r_.long(), g_)
+        g_table = torch.zeros(R, D, device=dev)
+        ops.scatter_add_rows(grads[rank].to(dev), rows[rank].to(dev), -1, g_table)      # the local backward
+        ex = replica.SparseRowExchange(R, D, n, dev)
+        touched = ex.exchange(g_table, rows[rank].to(dev))
+        assert_close(g_table, want, rtol=1e-6, atol_scale=1e-6, what="summed sparse gradient")
+        got = set(touched[touched >= 0].cpu().tolist())
+        assert got == set(torch.cat(rows).tolist())
+        # and the touched-rows optimizer consumes the padded id list (ids of -1 are counted as out of range, not updated)
+        w = torch.ones(R, D, device=dev)
+        opt = optim.TouchedRowsOptimizer([(w, g_table)], kind="sgd", lr=0.5)
+        opt.step(touched)
+        assert_close(w, 1.0 - 0.5 * want, rtol=1e-6, atol_scale=1e-6, what="sgd on the union of the touched rows")
+        assert float(g_table.abs().sum()) == 0.0                                        # consumed rows are cleared
+        open(os.path.join(out_dir, "ok%d" % rank), "w").write("ok")
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sparse_row_exchange_of_replicas(tmp_path):
+    """Replicas of a table the batch barely touches: all_gather of (row id, gradient row) blocks; every replica ends
+    with the summed gradient on the union of the touched rows, and the touched-rows optimizer applies it."""
+    world = _world()
+    if world < 2:
+        pytest.skip("needs at least two GPUs")
+    mp.spawn(_sparse_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    assert all(os.path.exists(os.path.join(str(tmp_path), "ok%d" % r)) for r in range(world))

@@ -7,8 +7,9 @@ path's kernels: rbx_gather_rows, rbx_pooled_gather_fwd/bwd, rbx_rowdot, rbx_scat
 tables, and the touched-rows update that consumes and clears them (f1; no O(table) memset or dense optimizer pass).  The
 launch-bound step (B = 8 192 / 1 024 sequences) is replayed from a CUDA graph (recbox_b200.graphs.GraphedStep).
 
-Multi-GPU: replicas only (the 2.6 GB / 256 MB tables fit every GPU): each rank runs its own batch shard; the
-sparse gradient exchange of the touched rows is not built, so N > 1 lines are weak-scaling replicas and say so.
+Multi-GPU: replicas only (the 2.6 GB / 256 MB tables fit every GPU): each rank runs its own batch shard and the
+replicas stay ONE model: the touched rows' gradients are exchanged as (row id, gradient row) blocks (replica.SparseRowExchange:
+rbx_unique_ids -> rbx_gather_rows -> all_gather -> rbx_scatter_add_rows), the dense tower / block gradients by NCCL.
 
 Reference shapes: rechub DSSM third_party/rechub/models/matching/dssm.py:39-65, YoutubeSBC youtube_sbc.py:58-84 (in-batch
 negatives), SASRec sasrec.py:65-107; towers are rechub MLP (basic/layers.py:233-266) without batch-norm / dropout."""
@@ -124,6 +125,11 @@ def run_dssm(args, rank, world, dev, bench):
     tower_opt = torch.optim.SGD(tower_params, lr=1e-3)
     opt_item = optim.TouchedRowsOptimizer([(item_table, g_item)], kind="sgd", lr=1e-3)
     opt_user = optim.TouchedRowsOptimizer([(user_table, g_user)], kind="sgd", lr=1e-3)
+    ex_item = ex_user = None
+    if world > 1:                     # replicas: sparse (row id, gradient row) exchange of the touched rows, dense tower grads by NCCL
+        from recbox_b200 import replica
+        ex_item = replica.SparseRowExchange(n_items + 1, D, B * (L + 1 + negs), dev)
+        ex_user = replica.SparseRowExchange(n_users, D, B, dev)
     NB = 4
     batches = []
     for i in range(NB):
@@ -159,16 +165,20 @@ def run_dssm(args, rank, world, dev, bench):
             for p in tower_params:
                 p.grad = None
             loss.backward()
+            users = b["user"]
+            if world > 1:
+                layers.sync_replica_gradients(tower_params, average=True)
+                touched, users = ex_item.exchange(g_item, touched), ex_user.exchange(g_user, users)
             tower_opt.step()
             opt_item.step(touched)
-            opt_user.step(b["user"])
+            opt_user.step(users)
             return loss
         return step
 
     out = {}
     K, W = min(args.steps, 50), args.warmup
     for variant in ("inbatch", "sampled"):
-        ms, mode = _timed_steps(make_step(variant), K, W, world)
+        ms, mode = _timed_steps(make_step(variant), K, W, world, graph=world == 1)     # (collectives stay outside CUDA graphs)
         out[variant] = {"ms_per_step": ms, "value": B * world / (ms * 1e-3), "issue": mode}
     # the hot-path kernels alone (one launch each, inputs of the first batch), against the HBM roofline
     peak, peak_src = bench.peaks()
@@ -205,7 +215,8 @@ def run_dssm(args, rank, world, dev, bench):
                                    "([B,B] score GEMM, softmax CE); `sampled` = 10 sampled negatives ([B,11] row dots)",
                        "global_batch": B * world, "ids": args.ids, "batches_rotated": 1,
                        "l2": "item table 2.56 GB exceeds the 126 MB L2",
-                       "parallelism": "1 GPU" if world == 1 else "dp%d replicas (no gradient exchange of the touched rows yet)" % world},
+                       "parallelism": "1 GPU" if world == 1 else "dp%d replicas of the tables; sparse all_gather of the touched (row id, gradient row) blocks + "
+                                                                   "NCCL all-reduce of the tower gradients inside the step" % world},
             "variants": out, "gpu_launches_issue": out["inbatch"]["issue"],
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": kern[dom]["gbs"], "peak": peak, "unit": "GB/s", "frac": kern[dom]["frac"],
                          "traffic": None, "peak_source": peak_src},
@@ -271,6 +282,10 @@ def run_sasrec(args, rank, world, dev, bench):
     dense_params = [p for m in mods for p in m.parameters()]
     dense_opt = torch.optim.SGD(dense_params, lr=1e-3)
     opt_tab = optim.TouchedRowsOptimizer([(table, g_table)], kind="sgd", lr=1e-3)
+    ex_tab = None
+    if world > 1:
+        from recbox_b200 import layers, replica
+        ex_tab = replica.SparseRowExchange(n_items + 1, D, 3 * B * L, dev)
     rng = np.random.default_rng(100 + rank)
     lens = torch.from_numpy(rng.integers(20, L + 1, size=(B, 1)))
     keep = torch.arange(L)[None, :] >= (L - lens)               # left-padded
@@ -303,12 +318,16 @@ def run_sasrec(args, rank, world, dev, bench):
         for p in dense_params:
             p.grad = None
         loss.backward()
+        touched = ids3
+        if world > 1:
+            layers.sync_replica_gradients(dense_params, average=True)
+            touched = ex_tab.exchange(g_table, ids3)
         dense_opt.step()
-        opt_tab.step(ids3)
+        opt_tab.step(touched)
         return loss
 
     K, W = min(args.steps, 30), args.warmup
-    ms, mode = _timed_steps(step, K, W, world)
+    ms, mode = _timed_steps(step, K, W, world, graph=world == 1)
     peak, peak_src = bench.peaks()
     g3 = torch.randn(3, B, L, D, device=dev)
     kern = {}
@@ -331,7 +350,8 @@ def run_sasrec(args, rank, world, dev, bench):
                                    "L=200 (lengths U[20,200], left-padded), D=64, 2 blocks, 1 head, B=1024 sequences per GPU; projections / FFN on "
                                    "the tcgen05 GEMM, attention core = torch SDPA (library)",
                        "global_batch": B * world, "ids": args.ids, "issue": mode,
-                       "parallelism": "1 GPU" if world == 1 else "dp%d replicas (pure data parallel sweep; no gradient exchange of the touched rows yet)" % world},
+                       "parallelism": "1 GPU" if world == 1 else "dp%d replicas (pure data parallel sweep); sparse all_gather of the touched (row id, gradient row) "
+                                                                   "blocks + NCCL all-reduce of the dense gradients inside the step" % world},
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": kern[dom]["gbs"], "peak": peak, "unit": "GB/s", "frac": kern[dom]["frac"],
                          "traffic": None, "peak_source": peak_src},
             "kernels": kern,
