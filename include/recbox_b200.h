@@ -189,6 +189,12 @@ int rbx_gather_rows(const float* table /*DEVICE [R,D]*/, const int32_t* ids /*DE
 int rbx_scatter_add_rows(const float* g /*DEVICE [N,D]*/, const int32_t* ids /*DEVICE [N]*/,
                          int32_t pad_row, float* g_table /*DEVICE [R,D]*/,
                          int64_t N, int D, rbx_stream_t stream);
+/* Deterministic form: the caller sorts the ids STABLY (sorted_ids ascending, order[i] = original
+ * position of sorted entry i); every run of equal ids is summed in position order by one warp and added to its row with a
+ * plain read-modify-write -- no atomics, bit-identical results from run to run. */
+int rbx_segment_sum_rows(const float* g /*DEVICE [N,D]*/, const int64_t* order /*DEVICE [N]*/,
+                         const int32_t* sorted_ids /*DEVICE [N]*/, int32_t pad_row, float* g_table /*DEVICE [R,D]*/,
+                         int64_t N, int D, rbx_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * a9  pooled sequence gather  (nn.Embedding on [B,L] ids followed by MaskedSumPooling /

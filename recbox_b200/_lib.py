@@ -85,6 +85,7 @@ SIGNATURES = {
     "rbx_embed_fm_bwd": [_P] * 19 + [_I64, _I64, _I, _I, _I, _I, _P],
     "rbx_gather_rows": [_P, _P, _P, _I64, _I, _P],
     "rbx_scatter_add_rows": [_P, _P, _c.c_int32, _P, _I64, _I, _P],
+    "rbx_segment_sum_rows": [_P, _P, _P, _c.c_int32, _P, _I64, _I, _P],
     "rbx_pooled_gather_fwd": [_P, _P, _I64, _P, _I64, _P, _I64, _I, _I, _I, _P],
     "rbx_pooled_gather_bwd": [_P, _I64, _P, _I64, _P, _c.c_int32, _P, _I64, _I, _I, _I, _P],
     "rbx_pool_fwd": [_P, _P, _P, _P, _I64, _I, _I, _I, _P],

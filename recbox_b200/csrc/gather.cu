@@ -100,6 +100,31 @@ __global__ void __launch_bounds__(kThreads) k_scatter_any(const float* __restric
 // ---------------------------------------------------------------------------------- pooled gather
 // group (LPR lanes) per sample; L ids walked U at a time.  mode 1 divides by the number of
 // positions whose gathered row has a non-zero element sum (sequence.py:10 / pooling.py:29).
+// ------------------------------------------------------------------------- deterministic scatter-add
+// a reproducible form of aten::embedding_dense_backward.  The ids arrive stably SORTED (sorted_ids, with
+// `order` = the original positions, ascending within equal ids); a warp takes position i and works only if i starts a run of
+// equal ids: it walks the run in position order, sums the gradient rows in registers and adds the total to the row with a
+// plain read-modify-write -- exactly one warp owns a row, no atomics, the same bits on every run.
+__global__ void __launch_bounds__(kThreads) k_segment_sum(const float* __restrict__ g, const int64_t* __restrict__ order,
+                                                          const int32_t* __restrict__ sorted_ids, int32_t pad_row,
+                                                          float* __restrict__ g_table, int64_t N, int D) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp0 = (int64_t)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
+    const int64_t nwarps = (int64_t)gridDim.x * (kThreads / 32);
+    for (int64_t i = warp0; i < N; i += nwarps) {
+        const int32_t r = __ldg(sorted_ids + i);
+        if (r < 0 || r == pad_row) continue;
+        if (i > 0 && __ldg(sorted_ids + i - 1) == r) continue;          // not the first position of its run
+        for (int d0 = 0; d0 < D; d0 += 32) {
+            const int d = d0 + lane;
+            float acc = 0.0f;
+            for (int64_t j = i; j < N && __ldg(sorted_ids + j) == r; ++j)
+                if (d < D) acc += __ldg(g + (size_t)__ldg(order + j) * D + d);
+            if (d < D) g_table[(size_t)r * D + d] += acc;
+        }
+    }
+}
+
 template <int LPR, int U>
 __global__ void __launch_bounds__(kThreads) k_pooled_fwd_vec(const float* __restrict__ table, const int32_t* __restrict__ ids,
                                                             int64_t ids_ld, float* __restrict__ out, int64_t out_ld,
@@ -410,6 +435,19 @@ int rbx_scatter_add_rows(const float* g, const int32_t* ids, int32_t pad_row, fl
     } else {
         k_scatter_any<<<capped_grid(N, 8), kThreads, 0, st>>>(g, ids, pad_row, g_table, N, D);
     }
+    RBX_LAUNCH_CHECK(who);
+    return RBX_OK;
+}
+
+int rbx_segment_sum_rows(const float* g, const int64_t* order, const int32_t* sorted_ids, int32_t pad_row, float* g_table,
+                         int64_t N, int D, rbx_stream_t stream) {
+    const char* who = "rbx_segment_sum_rows";
+    RBX_RANGE(who);
+    RBX_REQUIRE(N >= 0 && D >= 1 && D <= RBX_MAX_DIM, "%s: bad size", who);
+    if (N == 0) return RBX_OK;
+    RBX_REQUIRE(g && order && sorted_ids && g_table, "%s: null pointer", who);
+    k_segment_sum<<<capped_grid((N + kThreads / 32 - 1) / (kThreads / 32), 8), kThreads, 0, rbx_cast_stream(stream)>>>(g, order, sorted_ids,
+                                                                                                              pad_row, g_table, N, D);
     RBX_LAUNCH_CHECK(who);
     return RBX_OK;
 }

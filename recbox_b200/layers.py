@@ -565,6 +565,10 @@ class MLP_Layer(nn.Module):
         return _mlp_forward(self.mlp, inputs)
 
 
+DETERMINISTIC = False    # True: the plain lookups' backward uses the sorted, atomics-free scatter (rbx_segment_sum_rows); the fused FM
+                         # backward has the same mode at the ops level (ops.embed_fm_bwd_deterministic)
+
+
 class _GatherFn(torch.autograd.Function):
     """Plain lookup [.., ] ids -> [.., D] (un-pooled sequence features, generic encoders)."""
 
@@ -579,7 +583,10 @@ class _GatherFn(torch.autograd.Function):
         (ids,) = ctx.saved_tensors
         shape, pad = ctx.meta
         gt = torch.zeros(shape, dtype=F32, device=g.device)
-        ops.scatter_add_rows(g.contiguous(), ids, pad, gt)
+        if DETERMINISTIC:          # reproducible summation order: sort + segmented sum, no atomics
+            ops.scatter_add_rows_deterministic(g.contiguous(), ids, pad, gt)
+        else:
+            ops.scatter_add_rows(g.contiguous(), ids, pad, gt)
         return gt, None, None
 
 

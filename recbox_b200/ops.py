@@ -264,6 +264,38 @@ def scatter_add_rows(g, ids, pad_row, g_table):
           _p(g_table, F32, "g_table"), N, D, _stream())
 
 
+def scatter_add_rows_deterministic(g, ids, pad_row, g_table):
+    """g_table[ids[i]] += g[i] with a reproducible summation order: stable sort of the ids (torch.sort: plumbing),
+    then one warp per distinct row sums its run in position order and adds it with a plain read-modify-write
+    (rbx_segment_sum_rows).  Bit-identical from run to run; slower than the atomic kernel, opt-in."""
+    flat = ids.reshape(-1)
+    sorted_ids, order = torch.sort(flat, stable=True)
+    N, D = flat.numel(), g_table.shape[1]
+    _call("rbx_segment_sum_rows", _p(g.reshape(N, D) if g.is_contiguous() else g.contiguous().view(N, D), F32, "g"), _p(order, torch.int64, "order"),
+          _p(sorted_ids, I32, "sorted_ids"), -1 if pad_row is None else int(pad_row), _p(g_table, F32, "g_table"), N, D, _stream())
+
+
+def embed_fm_bwd_deterministic(table, rows, cat_pos, pad_row, E, S, dE, d_fm, d_lr, g_table, g_table_lr):
+    """Reproducible table gradients of the fused FM backward (the atomic kernel's sums depend on the order the red.adds land):
+    the per-slot gradient rows g = dE + d_fm * (S - e) are materialised (element-wise torch ops: plumbing) and reduced per
+    table row by the deterministic scatter above; first-order rows likewise.  Numeric-slot / bias gradients are plain batch
+    sums (torch.sum is deterministic).  Opt-in, ~3x the traffic of rbx_embed_fm_bwd."""
+    B, F = rows.shape
+    D = table.shape[1]
+    pos = torch.as_tensor(list(cat_pos), device=rows.device)
+    e = E.index_select(1, pos) if E is not None else gather_rows(table, rows.clamp_min(0))
+    G = dE.index_select(1, pos) if dE is not None else torch.zeros_like(e)
+    if d_fm is not None and S is not None:
+        G = G + d_fm.view(-1, 1, 1) * (S.view(B, 1, D) - e)
+    flat_rows = rows.reshape(-1)
+    pads = torch.as_tensor([p if p is not None else -1 for p in pad_row], device=rows.device, dtype=rows.dtype).repeat(B)
+    keep_rows = torch.where(flat_rows == pads, torch.full_like(flat_rows, -1), flat_rows)       # padding rows get no gradient
+    scatter_add_rows_deterministic(G.reshape(B * F, D).contiguous(), keep_rows, -1, g_table)
+    if d_lr is not None and g_table_lr is not None:
+        g1 = d_lr.view(B, 1).expand(B, F).reshape(B * F, 1).contiguous()
+        scatter_add_rows_deterministic(g1, keep_rows, -1, g_table_lr.view(-1, 1))
+
+
 def pooled_gather_fwd(table, ids, mode, out=None, want_cnt=None):
     """ids int32 [B, L] (row stride may exceed L) -> (out [B,D], cnt [B] | None)."""
     if ids.dim() != 2 or ids.dtype != I32 or not ids.is_cuda or ids.stride(1) != 1:

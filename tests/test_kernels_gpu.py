@@ -464,3 +464,56 @@ def test_ops_run_on_the_tensors_device_not_the_current_one():
     with pytest.raises(RbxError):
         ops.embed_fm_fwd(f1["table"], f1["table_lr"], f0["rows"], pb.cat_pos, f1["dense_x"], f1["dense_w"],
                          f1["dense_w_lr"], pb.num_pos, f1["bias"])
+
+
+# ----------------------------------------------------------------------------- deterministic scatter
+@pytest.mark.parametrize("D", [1, 10, 16, 64, 200])
+def test_scatter_add_rows_deterministic_is_bit_exact_and_reproducible(D):
+    """rbx_segment_sum_rows: every row's gradient rows are summed in position order, so the result equals numpy's sequential
+    np.add.at BIT FOR BIT and does not change from run to run (the atomic kernel agrees within 1e-5 only)."""
+    ops = _ops()
+    rng = np.random.default_rng(D)
+    N, R = 20000, 300                                   # ~67 contributions per row: the order of the adds matters
+    ids = rng.integers(0, R, N).astype(np.int32)
+    ids[::97] = 7                                       # a hot row
+    g = rng.standard_normal((N, D)).astype(np.float32)
+    want = np.zeros((R, D), np.float32)
+    keep = ids != 5
+    np.add.at(want, ids[keep], g[keep])                 # sequential, in position order, fp32
+    outs = []
+    for _ in range(2):
+        gt = torch.zeros(R, D, device=DEV)
+        ops.scatter_add_rows_deterministic(torch.from_numpy(g).to(DEV), torch.from_numpy(ids).to(DEV), 5, gt)
+        outs.append(gt.cpu())
+    assert torch.equal(outs[0], outs[1]), "not reproducible"
+    assert torch.equal(outs[0], torch.from_numpy(want)), "not the position-order sum"
+    assert float(outs[0][5].abs().sum()) == 0.0
+    gt = torch.zeros(R, D, device=DEV)
+    ops.scatter_add_rows(torch.from_numpy(g).to(DEV), torch.from_numpy(ids).to(DEV), 5, gt)
+    assert_close(gt, outs[0], atol_scale=1e-5, what="atomic vs deterministic")
+
+
+def test_embed_fm_bwd_deterministic_matches_the_atomic_kernel():
+    ops = _ops()
+    B, D = 500, 16
+    pb = Problem(B, "nncccccn", D, vocab=23, seed=77, zipf=1.3)
+    f = pb.fused(DEV)
+    g = torch.Generator().manual_seed(9)
+    dE = torch.randn(B, pb.F + pb.Fn, D, generator=g).to(DEV)
+    d_fm, d_lr = torch.randn(B, generator=g).to(DEV), torch.randn(B, generator=g).to(DEV)
+    E, S, fm, lr = ops.embed_fm_fwd(f["table"], f["table_lr"], f["rows"], pb.cat_pos, f["dense_x"], f["dense_w"], f["dense_w_lr"],
+                                    pb.num_pos, f["bias"])
+    rt, rt1 = torch.zeros_like(f["table"]), torch.zeros_like(f["table_lr"])
+    rw, rw1, rb = torch.zeros_like(f["dense_w"]), torch.zeros_like(f["dense_w_lr"]), torch.zeros(1, device=DEV)
+    ops.embed_fm_bwd(f["table"], f["rows"], pb.cat_pos, pb.pad_row, f["dense_x"], f["dense_w"], pb.num_pos, E, S, dE, d_fm, d_lr,
+                     rt, rt1, rw, rw1, rb, D, pb.R)
+    outs = []
+    for _ in range(2):
+        gt, gt1 = torch.zeros_like(f["table"]), torch.zeros_like(f["table_lr"])
+        ops.embed_fm_bwd_deterministic(f["table"], f["rows"], pb.cat_pos, pb.pad_row, E, S, dE, d_fm, d_lr, gt, gt1)
+        outs.append((gt.cpu(), gt1.cpu()))
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1]), "not reproducible"
+    assert_close(outs[0][0], rt, atol_scale=2e-5, what="g_table")
+    assert_close(outs[0][1], rt1, atol_scale=2e-5, what="g_table_lr")
+    for p in pb.pad_row:
+        assert float(outs[0][0][p].abs().sum()) == 0.0
