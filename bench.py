@@ -2,20 +2,24 @@
 """bench.py -- samples/sec of the RecBox embedding + FM hot path on B200 (BASELINE.json metric).
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--ids uniform|zipf]
+                  [--workload cfg2|sharded|dssm|sasrec]
 
 A "step" is one pass of the hot path over one Criteo-shaped synthetic batch (configs[1]: DeepFM,
 26 categorical + 13 numeric fields, 26 x 38 462 rows = 1 000 012-row fused table, D = 16,
 B = 65 536 per GPU):
     forward  : fused multi-slot gather + numeric Linear(1,D) + FM product_sum + LR  -> E, S, fm, lr
-    backward : zero the dense grad tables, then scatter-add dE + d_fm*(S-e) (and d_lr) into them,
-               plus the numeric-slot / bias batch reductions
-The dense MLP tail (a true GEMM) is outside the path: its input gradient dE
-is a device-resident stand-in.  `value` times the step with inputs resident in HBM; `e2e` times
-the same step fed from a pinned HOST float64 batch matrix (what the reference's DataLoader hands
-to train_step) through H2D + rbx_split_batch_f64, with the logits read back to the host.
-`--impl reference` times the CPU restatement of the reference (oracle/, torch CPU ops on all host
-cores) on the same step.  Under torchrun each rank runs an independent replica of the path on its
-own batch shard (weak scaling, no data-path collective; DESIGN.md "Multi-GPU").
+    backward : zero the fused dense gradient buffer (our kernel, side stream), then scatter-add dE + d_fm*(S-e) (and d_lr)
+               into it, plus the numeric-slot / bias batch reductions
+The dense MLP tail (a13) has its own numbers (tools/train_step_bench.py); here its input gradient dE is a
+device-resident stand-in.
+  value   the step with inputs resident in HBM, replayed from CUDA graphs, EXACTLY K steps between two CUDA events
+  e2e     the same step through the LAYER API (FeatureEmbedding + FactorizationMachine modules, autograd), fed every step from
+          pinned host memory (packed uint16 ids + fp32 dense), logits read back to the host -- copies inside the timed region
+  sharded BASELINE configs[3] (100 M-row table row-sharded over the ranks) at the same N, with an in-run parity check
+`--impl reference` times the reference's OWN FeatureEmbedding + FactorizationMachine (baseline/_ref, copied unmodified by
+baseline/fetch_ref.py; the oracle port only when that copy is absent) on all host cores.  Under torchrun (N > 1) the ranks are
+replicas that train ONE model: each runs the path on its own batch shard and the fused gradient buffer is all-reduced inside the
+timed step (our in-switch kernel or NCCL).
 """
 import argparse
 import json
