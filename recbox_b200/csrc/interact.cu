@@ -3,6 +3,7 @@
 //   0 product_sum / 1 bi_interaction : streaming, group-of-lanes per sample, sums in registers
 //   2 inner_product / 3 elementwise_product : one CTA per sample, E[b] staged in shared memory
 //     (row stride D+1 floats -> conflict-free when lanes read different fields)
+#include <stdlib.h>
 #include "rbx_common.cuh"
 
 namespace {
@@ -278,6 +279,18 @@ __host__ __device__ inline int slice_floats(int F, int D) { const int FB = (F + 
 __device__ __forceinline__ float dot4(float4 a, float4 b, float acc) {
     acc = fmaf(a.x, b.x, acc); acc = fmaf(a.y, b.y, acc); acc = fmaf(a.z, b.z, acc); return fmaf(a.w, b.w, acc);
 }
+// Blackwell's packed fp32 FMA (FFMA2, fma.rn.f32x2): the two halves of a 16-byte chunk go through ONE issue slot.
+// dot4x2 keeps an (even-k, odd-k) pair of partial sums; the pair is folded once per output at the end.
+__device__ __forceinline__ float2 dot4x2(float4 a, float4 b, float2 acc) {
+    acc = __ffma2_rn(make_float2(a.x, a.y), make_float2(b.x, b.y), acc);
+    return __ffma2_rn(make_float2(a.z, a.w), make_float2(b.z, b.w), acc);
+}
+__device__ __forceinline__ float4 f4_fma_x2(float4 a, float s, float4 c) {  // a*s + c, two FFMA2
+    const float2 ss = make_float2(s, s);
+    const float2 lo = __ffma2_rn(make_float2(a.x, a.y), ss, make_float2(c.x, c.y));
+    const float2 hi = __ffma2_rn(make_float2(a.z, a.w), ss, make_float2(c.z, c.w));
+    return make_float4(lo.x, lo.y, hi.x, hi.y);
+}
 __device__ __forceinline__ float4 f4_mul(float4 a, float4 b) { return make_float4(a.x * b.x, a.y * b.y, a.z * b.z, a.w * b.w); }
 __device__ __forceinline__ float4 f4_fma4(float4 a, float4 b, float4 c) {
     return make_float4(fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y), fmaf(a.z, b.z, c.z), fmaf(a.w, b.w, c.w));
@@ -322,11 +335,11 @@ __global__ void __launch_bounds__(kThreads) k_ip_fwd_warp(const float* __restric
         float* ob = out + (size_t)b * P;
         for (int t = lane; t < NT; t += 32) {
             const int ti = sTile[t] >> 8, tj = sTile[t] & 0xff;
-            float acc[4][4];
+            float2 acc2[4][4];
 #pragma unroll
             for (int x = 0; x < 4; ++x)
 #pragma unroll
-                for (int y = 0; y < 4; ++y) acc[x][y] = 0.f;
+                for (int y = 0; y < 4; ++y) acc2[x][y] = make_float2(0.f, 0.f);
             const float* pa = sE + row_off(4 * ti, D);
             const float* pb = sE + row_off(4 * tj, D);
 #pragma unroll 4
@@ -340,8 +353,13 @@ __global__ void __launch_bounds__(kThreads) k_ip_fwd_warp(const float* __restric
 #pragma unroll
                 for (int x = 0; x < 4; ++x)
 #pragma unroll
-                    for (int y = 0; y < 4; ++y) acc[x][y] = dot4(a[x], bb[y], acc[x][y]);
+                    for (int y = 0; y < 4; ++y) acc2[x][y] = dot4x2(a[x], bb[y], acc2[x][y]);
             }
+            float acc[4][4];
+#pragma unroll
+            for (int x = 0; x < 4; ++x)
+#pragma unroll
+                for (int y = 0; y < 4; ++y) acc[x][y] = acc2[x][y].x + acc2[x][y].y;
             // pair_index(i, j) = base(i) + j with base(i) = i (2F - i - 1) / 2 - i - 1
             if (tj > ti && 4 * tj + 3 < F) {
                 // interior tile: all 16 pairs exist, no tests (the epilogue was half of the kernel's instructions, ncu r1z)
@@ -368,6 +386,12 @@ __global__ void __launch_bounds__(kThreads) k_ip_fwd_warp(const float* __restric
         }
     }
 }
+
+// (Round 2, measured and dropped: packing the FMAs of this kernel and of the backward into FFMA2 changed nothing -- 122.9 /
+// 192.5 us before and after, r2am --, and a variant with two samples per warp and 8x8 register tiles, i.e. half the LDS.128
+// wavefronts per sample and all lanes busy in one round, was SLOWER: 190 us at 128 registers, r2an.  The kernel is bound by the
+// latency of its dependent LDS -> FMA -> STG chains at the occupancy its shared-memory slices allow, not by FMA issue or
+// shared-memory bandwidth.)
 
 // mode 2 backward: dE[b,i,:] = sum_j G[i,j] e_j with G the symmetric, zero-diagonal matrix of dout[b, p(i,j)].
 // G is scattered into the warp's slice as sG[j][i] (row stride GS).  A lane owns RPT consecutive rows i x one 16-byte
@@ -445,7 +469,7 @@ __global__ void __launch_bounds__(kThreads) k_ip_bwd_warp(const float* __restric
             for (int j = 0; j < F; ++j) {
                 const float4 e = *reinterpret_cast<const float4*>(ecol + row_off(j, D));
 #pragma unroll
-                for (int x = 0; x < RPT; ++x) acc[x] = f4_fma(e, gcol[j * GS + x], acc[x]);
+                for (int x = 0; x < RPT; ++x) acc[x] = f4_fma_x2(e, gcol[j * GS + x], acc[x]);
             }
 #pragma unroll
             for (int x = 0; x < RPT; ++x)
