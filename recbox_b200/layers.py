@@ -188,6 +188,203 @@ class _FusedStore(object):
 
 
 # =================================================================================================
+# row-sharded storage behind the same modules (BASELINE configs[3])
+# =================================================================================================
+_SHARD_CFG = [None]
+_SHARD_DIMS = (4, 8, 16, 32, 64, 128)         # physical row widths the sharded kernels cover (csrc/embed_fm.cu)
+
+
+class sharded_tables(object):
+    """Switch (context manager) under which FeatureEmbeddingDict / EmbeddingDictLayer keep their embedding tables
+    ROW-SHARDED across the ranks of `group` (recbox_b200.sharded.ShardedEmbeddingFM: global fused row r lives on rank
+    r % world) instead of replicated:
+
+        with recbox_b200.layers.sharded_tables():          # or RECBOX_B200_SHARD=peer in the environment
+            model = DeepFM(feature_map, ...)                # unmodified model code, reference ctor arguments
+        model.load_state_dict(reference_checkpoint)         # full tables, reference key names -- still on the host
+        model.to(device)                                    # <- the tables are cut here (collective over `group`)
+
+    After the cut `embedding_layers.<feature>.weight` is this rank's [rows owned, D] shard (same parameter names;
+    optimizers and state_dict see the shard; gather_state_dict() rebuilds the global one).  Every rank feeds its own batch
+    shard; a training forward is: zero of the local gradient shard -> cross-rank fence -> fused gather over NVLink; the
+    backward reduces straight into the owners' gradient shards, fences, and hands autograd views of the local shard.
+    Replicated parameters (numeric-slot weights, LR bias, the dense tail) are the caller's to all-reduce
+    (sync_replica_gradients skips the sharded ones).  Supported: one training forward / backward per embedding
+    dictionary and step, plain categorical + numeric slots of one embedding dim (no pooled sequence slots)."""
+
+    def __init__(self, mode="peer", group=None, alloc="symm", max_ids=None, slack=1.5, kern=None):
+        self.mode, self.group, self.alloc, self.max_ids, self.slack, self.kern = mode, group, alloc, max_ids, slack, kern
+        self._prev = None
+
+    def __enter__(self):
+        self._prev, _SHARD_CFG[0] = _SHARD_CFG[0], self
+        return self
+
+    def __exit__(self, *exc):
+        _SHARD_CFG[0] = self._prev
+        return False
+
+
+def _shard_config():
+    cfg = _SHARD_CFG[0]
+    if cfg is None:
+        import os
+        mode = os.environ.get("RECBOX_B200_SHARD", "")
+        if mode and mode != "0":
+            cfg = sharded_tables(mode="peer" if mode == "1" else mode)
+    return cfg
+
+
+class _ShardedStore(_FusedStore):
+    """_FusedStore whose embedding groups turn into row shards once the parameters reach a CUDA device (or on
+    shard_now()).  Until then it IS a _FusedStore: construction, seeded init and load_state_dict of a full reference
+    checkpoint run on the host exactly as in the replicated case, so the cut table equals the reference's row for row."""
+
+    def __init__(self, modules, cfg):
+        self.cfg = cfg
+        self.sharded = False
+        self.serial = 0                    # bumped by every training forward (= every zero-fill of the gradient shards)
+        _FusedStore.__init__(self, modules)
+
+    def fuse(self):
+        if self.sharded:
+            self.ensure()
+            return
+        ref = next((m.weight for g in self.groups.values() for m in (g.emb + g.lin)), None)
+        if ref is not None and ref.device.type == "cuda":
+            self.shard()
+        else:
+            _FusedStore.fuse(self)
+
+    def ensure(self):
+        if not self.sharded:
+            return _FusedStore.ensure(self)
+        for g in self.groups.values():
+            if [m.weight.data_ptr() for m in g.emb] + [m.weight.data_ptr() for m in g.lin] != g.ptrs:
+                raise RbxError("a row-sharded table stays where it was cut: parameters cannot be re-pointed or moved "
+                               "afterwards (gather_state_dict() rebuilds the global tables)")
+
+    def shard(self):
+        """Cut every embedding group: allocate this rank's table / gradient shards (peer-visible), keep the rows
+        r % world == rank of the fused table, re-point the per-feature Parameters at their slice.  Collective."""
+        from . import sharded
+        _FUSE_GEN[0] += 1
+        cfg = self.cfg
+        for g in self.groups.values():
+            ref = (g.emb[0] if g.emb else g.lin[0]).weight
+            dev = ref.device
+            if ref.dtype != F32:
+                raise RbxError("sharded tables are fp32")
+            D = g.D
+            Dp = D if D in _SHARD_DIMS else (4 if D < 4 else None)
+            if Dp is None:
+                raise RbxError("sharded tables cover embedding dims 1..4 and %s (got %d)" % (_SHARD_DIMS[1:], D))
+            g.Dp, g.sem, g.local, g.store = Dp, None, [], self
+            if g.emb:
+                sem = sharded.ShardedEmbeddingFM(g.R, Dp, mode=cfg.mode, group=cfg.group, device=dev, with_lr=False,
+                                                 kern=cfg.kern, max_ids=cfg.max_ids, slack=cfg.slack, alloc=cfg.alloc)
+                W, rank = sem.world, sem.rank
+                for m in g.emb:
+                    o, V = g.emb_off[id(m)], m.num_embeddings
+                    lo, hi = sharded.local_rows(o, W, rank), sharded.local_rows(o + V, W, rank)
+                    view = sem.table[lo:hi, :D]
+                    view.copy_(m.weight.data[(rank - o) % W::W])
+                    m.weight.data = view
+                    m.weight._rbx_shard = (self, g, m)
+                    g.local.append((lo, hi))
+                g.sem, g.table = sem, None
+                sem.barrier()
+            if g.lin:
+                dw = torch.zeros((len(g.lin), Dp), dtype=F32, device=dev)
+                for m in g.lin:
+                    i = g.lin_idx[id(m)]
+                    dw[i, :D].copy_(m.weight.data.reshape(-1))
+                    m.weight.data = dw[i, :D].view(D, 1)
+                g.dense_w = dw
+            g.ptrs = [m.weight.data_ptr() for m in g.emb] + [m.weight.data_ptr() for m in g.lin]
+        self.sharded = True
+
+    def gather_param(self, g, m, grad=False):
+        """-> the full [V, D] table of one feature (or its gradient), rebuilt from every rank's rows (collective)."""
+        import torch.distributed as dist
+        sem = g.sem
+        W, local = sem.world, m.weight.data
+        if grad:
+            local = m.weight.grad if m.weight.grad is not None else torch.zeros_like(local)
+        if W == 1:
+            return local.clone()
+        o, V, D = g.emb_off[id(m)], m.num_embeddings, g.D
+        n_max = (V + W - 1) // W + 1
+        mine = torch.zeros((n_max, D), dtype=F32, device=local.device)
+        mine[:local.shape[0]] = local
+        parts = [torch.empty_like(mine) for _ in range(W)]
+        dist.all_gather(parts, mine, group=sem.group)
+        full = torch.empty((V, D), dtype=F32, device=local.device)
+        for w in range(W):
+            first = (w - o) % W
+            full[first::W] = parts[w][:len(range(first, V, W))]
+        return full
+
+
+def shard_now(module):
+    """Cut the tables of every not-yet-sharded dictionary under `module` on the device they are on (Module.to(cuda)
+    does this by itself; this is the explicit form).  Collective over the configured group."""
+    for sub in module.modules():
+        st = getattr(sub, "_store", None)
+        if isinstance(st, _ShardedStore) and not st.sharded:
+            st.shard()
+            sub._calls, sub._calls_gen = {}, _FUSE_GEN[0]
+    return module
+
+
+def is_sharded(p):
+    return getattr(p, "_rbx_shard", None) is not None
+
+
+def gather_state_dict(module, grads=False):
+    """state_dict() with every row-sharded parameter rebuilt to its global [V, D] shape under the reference's key names
+    (checkpoints stay interchangeable with the replicated / reference model).  grads=True: the parameters' gradients
+    instead (sharded ones rebuilt, the others as they are).  Collective."""
+    named = OrderedDict(module.named_parameters(remove_duplicate=False))
+    out = OrderedDict()
+    for k, v in (named.items() if grads else module.state_dict().items()):
+        p = named.get(k)
+        if p is not None and is_sharded(p):
+            store, g, m = p._rbx_shard
+            out[k] = store.gather_param(g, m, grad=grads)
+        elif grads:
+            out[k] = None if v.grad is None else v.grad.detach().clone()
+        else:
+            out[k] = v.detach().clone()
+    return out
+
+
+def clip_grad_norm_(parameters, max_norm, group=None):
+    """torch.nn.utils.clip_grad_norm_ (2-norm) for a model whose tables are row-sharded: the squared norms of the sharded
+    gradients are summed over the ranks, those of the replicated ones (already all-reduced) counted once
+    (RankingModel.train_step, ranking_model.py:191-197).  Returns the global norm."""
+    import torch.distributed as dist
+    ps = [p for p in parameters if p.grad is not None]
+    if not ps:
+        return torch.zeros(())
+    dev = ps[0].grad.device
+    sq_sh, sq_rep = torch.zeros((), dtype=F32, device=dev), torch.zeros((), dtype=F32, device=dev)
+    for p in ps:
+        s = p.grad.detach().float().pow(2).sum()
+        if is_sharded(p):
+            sq_sh = sq_sh + s
+        else:
+            sq_rep = sq_rep + s
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(sq_sh, group=group)
+    total = (sq_sh + sq_rep).sqrt()
+    coef = torch.clamp(max_norm / (total + 1e-6), max=1.0)
+    for p in ps:
+        p.grad.detach().mul_(coef)
+    return total
+
+
+# =================================================================================================
 # the autograd node around the two fused kernels
 # =================================================================================================
 class _Call(object):
@@ -338,6 +535,71 @@ class _FusedEmbedFn(torch.autograd.Function):
         return (None, None, None, None) + tuple(grads)
 
 
+class _ShardedEmbedFn(torch.autograd.Function):
+    """E, fm = fused(rows, dense_x; this rank's parameter shards) over the row-sharded table of a _ShardedStore group.
+    forward : [zero of the local gradient shard -> cross-rank fence] -> ShardedEmbeddingFM.forward (remote rows over NVLink)
+    backward: ShardedEmbeddingFM.backward (reductions land in the owners' gradient shards) -> fence -> views of the local
+              gradient shard for the per-feature parameters; numeric-slot weights get this rank's partial sums."""
+
+    @staticmethod
+    def forward(ctx, call, rows, dense_x, *params):
+        g = call.group
+        sem, store = g.sem, g.store
+        train = any(ctx.needs_input_grad[3:])
+        dw = None
+        if call.Fn:
+            dw = g.dense_w if list(call.num_widx) == list(range(g.dense_w.shape[0])) else g.dense_w[list(call.num_widx)]
+        if call.F:
+            if train:
+                # the zero-fill precedes the fence: no peer starts this step's backward (which reduces into this shard)
+                # before every rank has passed the fence, i.e. before every shard is clean; and every rank's optimizer
+                # step on its table shard has landed before any peer gathers from it
+                sem.zero_grad()
+                store.serial += 1
+                sem.device_barrier()
+            E, S, fm, _ = sem.forward(rows, call.cat_pos, dense_x, dw, None, call.num_pos, None, want_E=True, n_slots=call.Ft)
+        else:
+            E, S, fm, _ = ops.embed_fm_fwd(None, None, None, [], dense_x, dw, None, call.num_pos, None, want_lr=False,
+                                           n_slots=call.Ft)
+        ctx.call, ctx.dw, ctx.serial, ctx.done = call, dw, store.serial, False
+        ctx.save_for_backward(rows, dense_x, E, S)
+        return E, fm.view(-1, 1)
+
+    @staticmethod
+    def backward(ctx, dE, d_fm):
+        call = ctx.call
+        g = call.group
+        sem, store, D, dw = g.sem, g.store, call.D, ctx.dw
+        rows, dense_x, E, S = ctx.saved_tensors
+        if ctx.done or (call.F and ctx.serial != store.serial):
+            raise RbxError("sharded tables take ONE training forward / backward per embedding dictionary and step: the "
+                           "gradient shard this backward reduces into was re-zeroed by a later forward (or used twice)")
+        ctx.done = True
+        dE = torch.zeros_like(E) if dE is None else dE.contiguous()
+        d_fm = torch.zeros(E.shape[0], dtype=F32, device=E.device) if d_fm is None else d_fm.contiguous().view(-1)
+        gw = torch.zeros_like(dw) if dw is not None else None
+        if call.F:
+            sem.backward(rows, call.cat_pos, call.pad_row, dense_x, dw, call.num_pos, E, S, dE, d_fm, None, gw, None, None,
+                         n_slots=call.Ft)
+            sem.device_barrier()               # every peer's reductions into this rank's shard have landed
+        else:
+            ops.embed_fm_bwd(None, None, [], None, dense_x, dw, call.num_pos, None, S, dE, d_fm, None, None, None, gw, None,
+                             None, E.shape[-1], 0, B=E.shape[0], n_slots=call.Ft)
+        widx = list(call.num_widx)
+        grads = []
+        for (kind, idx), p, need in zip(call.kinds, call.params, ctx.needs_input_grad[3:]):
+            v = None
+            if need and kind == "emb" and call.F:
+                lo, hi = g.local[idx]
+                v = sem.g_table[lo:hi, :D]
+                if p.grad is not None and p.grad.data_ptr() == v.data_ptr() and p.grad.stride() == v.stride():
+                    v = None                   # .grad still aliases the shard (zero_grad(set_to_none=False)): already in place
+            elif need and kind == "lin" and gw is not None and idx in widx:
+                v = gw[widx.index(idx), :D].reshape(D, 1)
+            grads.append(v)
+        return (None, None, None) + tuple(grads)
+
+
 def fused_grad_buffers(params):
     """-> (shared, single): `shared` = one flat fp32 view per gradient STORAGE that several parameters' .grad alias (the
     per-feature .grad tensors a fused backward hands to autograd are views of one buffer per launch, see
@@ -371,7 +633,7 @@ def sync_replica_gradients(params, group=None, average=False, reducer=None):
     import torch.distributed as dist
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
         return 0
-    shared, single = fused_grad_buffers(params)
+    shared, single = fused_grad_buffers([p for p in params if not is_sharded(p)])   # sharded rows have one owner: nothing to reduce
     n = 0
     for b in shared:
         if reducer is not None and b.numel() <= reducer.numel:      # recbox_b200.replica.ReplicaReducer: in-switch all-reduce
@@ -796,7 +1058,9 @@ class _FusedDictBase(nn.Module):
 
     # -- storage ---------------------------------------------------------------------------------
     def _build_store(self):
-        self._store = _FusedStore(list(self.embedding_layers.values()))
+        cfg = _shard_config()
+        mods = list(self.embedding_layers.values())
+        self._store = _FusedStore(mods) if cfg is None else _ShardedStore(mods, cfg)
         self._calls = {}
         self._calls_gen = _FUSE_GEN[0]
         self._lr_partner = None
@@ -812,6 +1076,8 @@ class _FusedDictBase(nn.Module):
 
     def __getstate__(self):
         # the store keys its offsets by id(module) and aliases one allocation: rebuilt on unpickle
+        if getattr(self._store, "sharded", False):
+            raise RbxError("a module with row-sharded tables is not picklable: save gather_state_dict(module)")
         state = dict(self.__dict__)
         for k in ("_store", "_calls", "_calls_gen", "_lr_partner"):
             state.pop(k, None)
@@ -831,6 +1097,8 @@ class _FusedDictBase(nn.Module):
 
     def __deepcopy__(self, memo):
         import copy
+        if getattr(self._store, "sharded", False):
+            raise RbxError("a module with row-sharded tables cannot be deep-copied: rebuild it from gather_state_dict(module)")
         cls = self.__class__
         new = cls.__new__(cls)
         memo[id(self)] = new
@@ -1009,6 +1277,8 @@ class _FusedDictBase(nn.Module):
         if lr_partner is not None:      # its parameters ride in this launch: a re-fusion there invalidates our plans too
             lr_partner.embedding_layer.embedding_layer._sync_store()
         self._sync_store()
+        if getattr(self._store, "sharded", False):
+            return self._embed_sharded(inputs, key, names)
         for g in self._store.groups.values():
             ref = g.table if g.table is not None else g.dense_w
             if not ref.is_cuda:
@@ -1064,6 +1334,31 @@ class _FusedDictBase(nn.Module):
             if name in enc:
                 e = enc[name](e)
             out[name] = e
+        return out
+
+    def _embed_sharded(self, inputs, key, names):
+        """_embed over row-sharded tables (_ShardedStore): the same [B, F, D] tensor and FM by-product, produced by the
+        sharded fused kernels; the first-order term is NOT paired into the launch (LogisticRegression is its own
+        dictionary, sharded the same way, and runs its own lookup)."""
+        plan = self._plan(key, names)
+        if plan["call"] is None or plan["seq_pool"]:
+            raise RbxError("sharded tables cover plain categorical / numeric slots of ONE embedding dim (no pooled sequence "
+                           "slots, custom encoders or mixed dims): selection %r is outside that" % (list(names),))
+        call, cn = plan["call"]
+        rows, dense_x = self._pack(inputs, cn["cats"], cn["nums"], cn["offs"], cn.get("vocab"))
+        E, fm = _ShardedEmbedFn.apply(call, rows, dense_x, *call.params)
+        if E.shape[-1] != call.D:                  # D < 4 tables (the D = 1 LogisticRegression trick) live in 4-float rows
+            E, fm = E[..., :call.D], None
+        out = _EmbDict()
+        out.names = tuple(names)
+        st = _Stash()
+        st.X, st.fm, st.lr, st.lr_owner, st.producer = inputs, fm, None, None, weakref.ref(self)
+        st.full = key == self._full_key()
+        st.version = E._version
+        E._rbx_stash = st
+        for i, name in enumerate(names):
+            out[name] = E[:, i, :]
+        out.stacked = E
         return out
 
     @staticmethod
@@ -1343,8 +1638,8 @@ class LogisticRegression(nn.Module):
         d._sync_store()
         key, names = d._select([], [])
         plan = d._plan(key, names)
-        if plan["call"] is None or plan["seq_pool"]:
-            embed_weights = self.embedding_layer(X)        # generic route (sequence slots): sum over fields
+        if plan["call"] is None or plan["seq_pool"] or getattr(d._store, "sharded", False):
+            embed_weights = self.embedding_layer(X)        # generic route (sequence slots, sharded tables): sum over fields
             output = embed_weights.sum(dim=1)
             if self.bias is not None:
                 output = output + self.bias
@@ -1395,10 +1690,10 @@ def _try_pair(producer, lr_module):
     """Let `producer` (the FeatureEmbeddingDict that made feature_emb) compute this FM block's
     first-order term in its own launch from now on.  Only when both see the same features as
     plain categorical / numeric slots."""
-    if producer is None or not FUSE_FM:
+    if producer is None or not FUSE_FM or getattr(producer._store, "sharded", False):
         return
     ld = lr_module.embedding_layer.embedding_layer
-    if ld._feature_map is not producer._feature_map:
+    if ld._feature_map is not producer._feature_map or getattr(ld._store, "sharded", False):
         return
     kp, np_ = producer._select([], [])
     kl, nl = ld._select([], [])
