@@ -105,3 +105,67 @@ def test_full_size_backward_properties(setup):
     ref = torch.zeros(s["R"], D, dtype=torch.float64, device=DEV)
     ref.index_add_(0, s["rows"].long().reshape(-1), (ge * keep[:, :, None]).reshape(-1, D))
     assert_close(gt, ref, atol_scale=2e-5, what="scatter-add vs index_add_")
+
+
+@pytest.mark.parametrize("Dl", [16, 128])
+def test_hundred_million_row_table(Dl):
+    """configs[3]'s table on ONE GPU: 100 M rows x D (6.4 GB at D = 16, 51 GB at D = 128; row offsets beyond 2^31 elements),
+    the shapes whose addressing nothing else in the suite reaches.  Same properties as above, with the references
+    computed on the rows the batch touches (the table itself is too large for a float64 twin)."""
+    from recbox_b200 import ops
+    R, Bl, Fl = 100_000_000, 16384, 26
+    need = 2 * R * Dl * 4 + (24 << 30)
+    torch.cuda.empty_cache()
+    free = torch.cuda.mem_get_info()[0]
+    if free < need:
+        pytest.skip("needs %.0f GB of free HBM, %.0f GB available" % (need / 2 ** 30, free / 2 ** 30))
+    table = torch.empty((R, Dl), dtype=torch.float32, device=DEV)
+    torch.manual_seed(11)
+    step = 10_000_000
+    for lo in range(0, R, step):                              # filled in slabs: no 51 GB temporary
+        table[lo:lo + step].normal_(0.0, 0.05)
+    Vf = R // Fl
+    rng = np.random.default_rng(11)
+    ids = rng.integers(0, Vf, size=(Bl, Fl))
+    ids[rng.random((Bl, Fl)) < 0.05] = 0                      # padding ids
+    hot = rng.random((Bl, Fl)) < 0.2
+    ids[hot] = rng.integers(1, 64, size=int(hot.sum()))       # a hot head: colliding reductions
+    ids[:, -1] = np.where(rng.random(Bl) < 0.5, Vf - 1, ids[:, -1])      # the table's last rows
+    off = np.arange(Fl, dtype=np.int64) * Vf
+    rows = torch.from_numpy((ids + off).astype(np.int32)).to(DEV)
+    assert int(rows.max()) * Dl > 2 ** 31 or Dl == 16
+    pad_row = [int(o) for o in off]
+    table[torch.tensor(pad_row, device=DEV)] = 0
+    cat_pos = list(range(Fl))
+    E, S, fm, _ = ops.embed_fm_fwd(table, None, rows, cat_pos, None, None, None, [], None, want_lr=False)
+    assert torch.equal(E, table[rows.long()]), "gather must be bit-exact over the whole 100 M-row range"
+    E64 = E.double()
+    assert_close(S, E64.sum(1), what="S")
+    assert_close(fm, 0.5 * (E64.sum(1).pow(2).sum(-1) - E64.pow(2).sum((1, 2))), atol_scale=2e-5, what="fm identity")
+    g = torch.Generator().manual_seed(12)
+    dE = torch.randn(Bl, Fl, Dl, generator=g).to(DEV)
+    d_fm = torch.randn(Bl, generator=g).to(DEV)
+    gt = torch.zeros_like(table)
+    ops.embed_fm_bwd(table, rows, cat_pos, pad_row, None, None, [], E, S, dE, d_fm, None, gt, None, None, None, None, Dl, R)
+    # reference on the touched rows only: index_add_ over the compacted (unique) row set, float64
+    pads = torch.tensor(pad_row, device=DEV)
+    keep = (rows != pads[None].int())
+    ge = (dE.double() + d_fm.double()[:, None, None] * (S.double()[:, None, :] - E64)) * keep[:, :, None]
+    uniq, inv = torch.unique(rows.reshape(-1).long(), return_inverse=True)
+    ref = torch.zeros((uniq.numel(), Dl), dtype=torch.float64, device=DEV)
+    ref.index_add_(0, inv, ge.reshape(-1, Dl))
+    assert_close(gt[uniq], ref, atol_scale=2e-5, what="scatter-add on the touched rows")
+    assert float(gt[pads].abs().sum()) == 0.0, "padding rows keep a zero gradient"
+    # nothing landed outside the touched rows: the whole-table column sums equal the touched rows' sums
+    tot = torch.zeros(Dl, dtype=torch.float64, device=DEV)
+    mass = 0.0
+    for lo in range(0, R, step):
+        slab = gt[lo:lo + step].double()
+        tot += slab.sum(0)
+        mass += float(slab.abs_().sum())
+        del slab
+    assert_close(tot, ref.sum(0), atol_scale=1e-5, rtol=1e-5, what="whole-table gradient checksum")
+    touched = float(gt[uniq].double().abs().sum())
+    assert abs(mass - touched) <= 1e-9 * max(touched, 1.0), "gradient mass outside the touched rows"
+    del table, gt
+    torch.cuda.empty_cache()
