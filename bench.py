@@ -378,6 +378,8 @@ def main_b200(args, rank, world, local_rank):
             ev_zero.record(side)
 
     def bwd(rows, dx, E, S):
+        if not args.bwd_saved_e:           # e re-read from the (mostly L2-resident) table instead of the forward's E stream:
+            E = None                       # same algorithmic bytes (F * 4D either way), fewer DRAM bytes (r2ba: 355 vs 351 M samples/s)
         ops.embed_fm_bwd(table, rows, cat_pos, pad_row, dx, dense_w, num_pos, E, S, dE, d_fm, d_lr,
                          g_table, g_table_lr, g_dense_w, g_dense_w_lr, g_bias, D, R)
 
@@ -954,6 +956,8 @@ def main():
     ap.add_argument("--allreduce", default="auto", choices=["auto", "nvls", "nccl"],
                     help="replica gradient exchange at N > 1: in-switch all-reduce kernel over multicast memory or NCCL; auto = the "
                          "faster one measured at that N (r2ad / r2ae: NCCL 157 / 201 us at N = 2 / 4, the kernel 205 us at N = 8 vs NCCL 284)")
+    ap.add_argument("--bwd-saved-e", action="store_true",
+                    help="cfg2: the backward reads the forward's saved E instead of re-gathering e from the table (the round-1 form)")
     ap.add_argument("--eager", action="store_true", help="layer-API e2e legs without CUDA-graph replay (host-bound: ~80 Parameters cross autograd)")
     ap.add_argument("--no-sharded", action="store_true", help="cfg2 run without the attached configs[3] (100M-row sharded table) object")
     ap.add_argument("--workload", default="cfg2", choices=["cfg2", "sharded", "dssm", "sasrec"],

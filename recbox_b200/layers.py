@@ -466,7 +466,11 @@ class _FusedEmbedFn(torch.autograd.Function):
         ctx.gbuf = None
         if ASYNC_ZERO and E is not None and E.is_cuda and any(ctx.needs_input_grad[4:]):
             ctx.gbuf = _prezero(_grad_layout(call, call.with_main, call.with_lr), E.device)
-        ctx.save_for_backward(rows, dense_x, E if want_fm else None, S, *seq_ids, *[c for c in cnts if c is not None])
+        # the backward needs e only for the FM term d_fm * (S - e); it re-reads e from the table (rows mostly L2-resident)
+        # rather than from the [B, F, D] stream the forward wrote (measured: 355 vs 351 M samples/s on the bench step), so
+        # E is saved only when there is no table to re-read from (numeric-only selections)
+        keep_E = want_fm and not (g is not None and g.emb and call.F)
+        ctx.save_for_backward(rows, dense_x, E if keep_E else None, S, *seq_ids, *[c for c in cnts if c is not None])
         return (E, fm.view(-1, 1) if fm is not None else None, lr.view(-1, 1) if lr is not None else None)
 
     @staticmethod
