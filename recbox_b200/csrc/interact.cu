@@ -479,6 +479,231 @@ __global__ void __launch_bounds__(kThreads) k_ip_bwd_warp(const float* __restric
     cp_async_wait_all();
 }
 
+// ------------------------------------------------------------------ mode 2 on the tensor cores (D = 16, 25 <= F <= 40)
+// The per-sample work of mode 2 is a tiny matrix product -- forward: the upper triangle of the Gram matrix E E^T
+// ([F,16] x [16,F]); backward: dE = G E with G the symmetric zero-diagonal [F,F] matrix of the upstream gradients -- and
+// the SIMT kernels above spend their time moving operands from shared memory to the FMA pipe (389 / 530 shared-memory
+// wavefronts and 1 153 / 1 832 warp instructions per sample at F = 39, profiles/r1_ncu_summary.md).  Here a warp still
+// owns a sample, but the products run as warp-level mma.sync.m16n8k8 in 3xTF32 (x = hi + lo, hi = tf32(x),
+// lo = tf32(x - hi); a_lo b_hi + a_hi b_lo + a_hi b_hi in fp32 accumulators: fp32-level accuracy, the 1e-5 contract) with
+// every operand element read from shared memory ONCE per lane, as a conflict-free LDS.32 into its fragment register:
+//   fragments (g = lane >> 2, t = lane & 3):  A 16x8: a0 (g, t) a1 (g+8, t) a2 (g, t+4) a3 (g+8, t+4)
+//                                             B 8x8 : b0 (k = t, n = g) b1 (k = t+4, n = g)
+//                                             C 16x8: c0 (g, 2t) c1 (g, 2t+1) c2 (g+8, 2t) c3 (g+8, 2t+1)
+// These are per-sample 40 x 40 x 16 products, far below a tcgen05 tile (M = 128 per instruction, operands through
+// descriptors): the warp-level form is the one that fits, the kernels stay HBM-bound by design.
+// forward : rows padded to 40 (5 row blocks of 8).  x[rb][ks][h] = E[8 rb + g][8 ks + 4 h + t] serves as the A fragment
+//           of m-tile i (row blocks 2i, 2i+1) AND as the B fragment of n-tile rb, because B = E^T.  Only the 9 (m, n) tile
+//           pairs that touch the upper triangle are computed: 9 x 2 k-steps x 3 = 54 mma per sample.  C goes to a dense
+//           [40][40] tile in shared memory (STS.64, conflict-free at stride 40), from where the lanes write the P outputs
+//           in order with coalesced 4-byte stores; the (i, j) -> offset table of a lane's 25 outputs sits in registers.
+// backward: dE^T [16 x F] = E^T [16 x 40] G [40 x F]: one m-tile, 5 n-tiles, 5 k-steps: 75 mma per sample (the
+//           untransposed form needs 3 m-tiles of which the last is half empty: 90).  G is expanded from the staged
+//           gradients into a dense symmetric [40][44] tile (diagonal and padding stay zero), B fragments are plain LDS.32.
+// The next sample's rows (and gradients) stream in with cp.async as soon as the current sample's fragments are in
+// registers, into the same buffers.
+constexpr int kIpmRows = 40;          // padded fields
+constexpr int kIpmES = 20;            // forward: row stride of the staged sample (bank = 20 g + t: conflict-free)
+constexpr int kIpmCS = 40;            // forward: row stride of the C tile (STS.64 of (g, 2t): conflict-free)
+constexpr int kIpmBS = 24;            // backward: row stride of the staged sample (bank = 24 t + g: conflict-free)
+constexpr int kIpmGS = 44;            // backward: row stride of the G tile (bank = 12 g + t: conflict-free)
+constexpr int kIpmMaxK = 25;          // ceil(40 * 39 / 2 / 32) outputs per lane
+constexpr int kIpmTab = 400;          // forward: floats reserved for the CTA's pair table (780 x uint16)
+constexpr int kIpmTabB = 800;         // backward: 780 x uint32
+constexpr int kIpmFwdWarps = 4, kIpmBwdWarps = 3;
+constexpr int kIpmFwdSlice = kIpmRows * kIpmES + kIpmRows * kIpmCS;           // 2 400 floats per warp
+constexpr int kIpmW = 784;                                                    // staged gradients: P + 3 (alignment slack), /4
+constexpr int kIpmBwdSlice = kIpmRows * kIpmBS + kIpmW + kIpmRows * kIpmGS;   // 3 504 floats per warp
+
+// x = hi + lo for 3xTF32.  tf32 = the upper 19 bits of an fp32; the mma reads exactly those and ignores the low 13, so
+// rounding (to nearest, ties away -- what cvt.rna.tf32.f32 does) is "+ 0x1000" on the bit pattern.  hi is also masked
+// because x - hi must be exact; lo only carries the rounding increment (its low bits are ignored by the mma).  Four
+// integer / FP instructions per element; ptxas expands the two cvt.rna of the textbook form into nine.
+__device__ __forceinline__ void ipm_split(float x, uint32_t& hi, uint32_t& lo) {
+    hi = (__float_as_uint(x) + 0x1000u) & 0xffffe000u;
+    lo = __float_as_uint(x - __uint_as_float(hi)) + 0x1000u;
+}
+__device__ __forceinline__ void ipm_mma(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+
+__global__ void __launch_bounds__(kIpmFwdWarps * 32, 5) k_ip_fwd_mma(const float* __restrict__ E, float* __restrict__ out, int64_t B, int F) {
+    extern __shared__ __align__(16) float smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
+    const int P = F * (F - 1) / 2;
+    unsigned short* sPair = reinterpret_cast<unsigned short*>(smem);                  // [P] -> i * CS + j
+    float* sE = smem + kIpmTab + (size_t)warp * kIpmFwdSlice;
+    float* sC = sE + kIpmRows * kIpmES;
+    for (int i = threadIdx.x; i < F; i += blockDim.x)
+        for (int j = i + 1; j < F; ++j) sPair[pair_index(i, j, F)] = (unsigned short)(i * kIpmCS + j);
+    for (int q = F * kIpmES + lane; q < kIpmRows * kIpmES; q += 32) sE[q] = 0.f;      // rows F .. 39: zero, never refilled
+    __syncthreads();
+    uint32_t tab[(kIpmMaxK + 1) / 2];
+#pragma unroll
+    for (int k = 0; k < (kIpmMaxK + 1) / 2; ++k) {
+        const int p0 = lane + 64 * k, p1 = p0 + 32;
+        const uint32_t lo = p0 < P ? sPair[p0] : 0u, hi = p1 < P ? sPair[p1] : 0u;
+        tab[k] = lo | (hi << 16);
+    }
+    const int64_t gw = (int64_t)blockIdx.x * kIpmFwdWarps + warp, nw = (int64_t)gridDim.x * kIpmFwdWarps;
+    // chunk q = lane + 32 k of the sample's F * 4 sixteen-byte chunks -> row q >> 2, column 4 (q & 3): lane-constant
+    // addresses plus k * 512 B (global) / k * 8 rows (shared)
+    float* const pfDst = sE + (lane >> 2) * kIpmES + 4 * (lane & 3);
+    const int nChunk = F * 4;
+    auto prefetch = [&](int64_t bn) {
+        const float* src = E + (size_t)bn * F * 16 + 4 * lane;
+#pragma unroll
+        for (int k = 0; k < 5; ++k)
+            if (lane + 32 * k < nChunk) cp_async_16(pfDst + 8 * k * kIpmES, src + 128 * k);
+    };
+    if (gw < B) prefetch(gw);
+    cp_async_commit_group();
+    const float* xE = sE + g * kIpmES + t;
+    float* cW = sC + g * kIpmCS + 2 * t;
+    for (int64_t b = gw; b < B; b += nw) {
+        cp_async_wait_all();
+        __syncwarp();                                  // sample b has landed; every lane is done with the previous C tile
+        uint32_t xh[5][2][2], xl[5][2][2];
+#pragma unroll
+        for (int rb = 0; rb < 5; ++rb)
+#pragma unroll
+            for (int ks = 0; ks < 2; ++ks)
+#pragma unroll
+                for (int h = 0; h < 2; ++h) ipm_split(xE[8 * rb * kIpmES + 8 * ks + 4 * h], xh[rb][ks][h], xl[rb][ks][h]);
+        __syncwarp();                                  // the staged rows are in registers everywhere: refill the buffer
+        if (b + nw < B) prefetch(b + nw);
+        cp_async_commit_group();
+        // tile (i, j): rows 16 i .. 16 i + 15 (row blocks 2i, 2i+1; block 5 does not exist: zeros), columns 8 j .. 8 j + 7
+#define RBX_IPM_TILE(i, j)                                                                                              \
+        {                                                                                                               \
+            float c[4] = {0.f, 0.f, 0.f, 0.f};                                                                          \
+            _Pragma("unroll") for (int ks = 0; ks < 2; ++ks) {                                                          \
+                const uint32_t ah0 = xh[2 * (i)][ks][0], ah2 = xh[2 * (i)][ks][1], al0 = xl[2 * (i)][ks][0], al2 = xl[2 * (i)][ks][1]; \
+                const uint32_t ah1 = (i) < 2 ? xh[(i) < 2 ? 2 * (i) + 1 : 0][ks][0] : 0u, ah3 = (i) < 2 ? xh[(i) < 2 ? 2 * (i) + 1 : 0][ks][1] : 0u; \
+                const uint32_t al1 = (i) < 2 ? xl[(i) < 2 ? 2 * (i) + 1 : 0][ks][0] : 0u, al3 = (i) < 2 ? xl[(i) < 2 ? 2 * (i) + 1 : 0][ks][1] : 0u; \
+                ipm_mma(c, al0, al1, al2, al3, xh[j][ks][0], xh[j][ks][1]);                                             \
+                ipm_mma(c, ah0, ah1, ah2, ah3, xl[j][ks][0], xl[j][ks][1]);                                             \
+                ipm_mma(c, ah0, ah1, ah2, ah3, xh[j][ks][0], xh[j][ks][1]);                                             \
+            }                                                                                                           \
+            *reinterpret_cast<float2*>(cW + 16 * (i) * kIpmCS + 8 * (j)) = make_float2(c[0], c[1]);                     \
+            if ((i) < 2) *reinterpret_cast<float2*>(cW + (16 * (i) + 8) * kIpmCS + 8 * (j)) = make_float2(c[2], c[3]);  \
+        }
+        RBX_IPM_TILE(0, 0) RBX_IPM_TILE(0, 1) RBX_IPM_TILE(0, 2) RBX_IPM_TILE(0, 3) RBX_IPM_TILE(0, 4)
+        RBX_IPM_TILE(1, 2) RBX_IPM_TILE(1, 3) RBX_IPM_TILE(1, 4) RBX_IPM_TILE(2, 4)
+#undef RBX_IPM_TILE
+        __syncwarp();                                  // the C tile is complete
+        float* ob = out + (size_t)b * P;
+#pragma unroll
+        for (int k = 0; k < kIpmMaxK; ++k) {
+            const int p = lane + 32 * k;
+            const uint32_t off = (k & 1) ? (tab[k >> 1] >> 16) : (tab[k >> 1] & 0xffffu);
+            if (p < P) __stcs(ob + p, sC[off]);
+        }
+    }
+    cp_async_wait_all();
+}
+
+__global__ void __launch_bounds__(kIpmBwdWarps * 32, 5) k_ip_bwd_mma(const float* __restrict__ E, const float* __restrict__ dout,
+                                                                    float* __restrict__ dE, int64_t B, int F) {
+    extern __shared__ __align__(16) float smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
+    const int P = F * (F - 1) / 2;
+    const int64_t total = B * (int64_t)P;
+    uint32_t* sPair = reinterpret_cast<uint32_t*>(smem);          // [P] -> float offsets (i * GS + j) | (j * GS + i) << 16
+    float* sE = smem + kIpmTabB + (size_t)warp * kIpmBwdSlice;
+    float* sW = sE + kIpmRows * kIpmBS;
+    float* sG = sW + kIpmW;
+    for (int i = threadIdx.x; i < F; i += blockDim.x)
+        for (int j = i + 1; j < F; ++j) sPair[pair_index(i, j, F)] = (uint32_t)(i * kIpmGS + j) | ((uint32_t)(j * kIpmGS + i) << 16);
+    for (int q = F * kIpmBS + lane; q < kIpmRows * kIpmBS; q += 32) sE[q] = 0.f;      // rows F .. 39 (multiplied by G's zero columns)
+    for (int q = lane; q < kIpmRows * kIpmGS; q += 32) sG[q] = 0.f;                   // diagonal and padding stay zero
+    __syncthreads();
+    const int64_t gw = (int64_t)blockIdx.x * kIpmBwdWarps + warp, nw = (int64_t)gridDim.x * kIpmBwdWarps;
+    float* const pfDst = sE + (lane >> 2) * kIpmBS + 4 * (lane & 3);
+    const int nChunk = F * 4;
+    auto prefetch = [&](int64_t bn) {
+        const float* src = E + (size_t)bn * F * 16 + 4 * lane;
+#pragma unroll
+        for (int k = 0; k < 5; ++k)
+            if (lane + 32 * k < nChunk) cp_async_16(pfDst + 8 * k * kIpmBS, src + 128 * k);
+        // the sample's P gradients start at float bn * P, 16-byte aligned only when (bn * P) % 4 == 0: copy the aligned
+        // 16-byte chunks that cover them (element p lands at sW[mis + p]); a chunk reaching past the end of dout goes float by float
+        const int64_t first = bn * (int64_t)P;
+        const int mis = (int)(first & 3);
+        const int64_t base = first - mis + 4 * lane;
+        const int nq = (mis + P + 3) >> 2;
+        const float* wsrc = dout + base;
+        float* wdst = sW + 4 * lane;
+#pragma unroll
+        for (int k = 0; k < 7; ++k) {
+            if (lane + 32 * k < nq) {
+                if (base + 128 * k + 4 <= total) {
+                    cp_async_16(wdst + 128 * k, wsrc + 128 * k);
+                } else {
+                    for (int e = 0; e < 4; ++e)
+                        if (base + 128 * k + e < total) cp_async_4(wdst + 128 * k + e, wsrc + 128 * k + e);
+                }
+            }
+        }
+    };
+    if (gw < B) prefetch(gw);
+    cp_async_commit_group();
+    for (int64_t b = gw; b < B; b += nw) {
+        cp_async_wait_all();
+        __syncwarp();                                  // sample b has landed; every lane is done with the previous G tile
+        // A = E^T: a0 = E[8 ks + t][g], a1 = E[8 ks + t][g + 8], a2 = E[8 ks + t + 4][g], a3 = E[8 ks + t + 4][g + 8]
+        uint32_t ah[5][4], al[5][4];
+#pragma unroll
+        for (int ks = 0; ks < 5; ++ks) {
+            const float* r0 = sE + (8 * ks + t) * kIpmBS + g;
+            ipm_split(r0[0], ah[ks][0], al[ks][0]);
+            ipm_split(r0[8], ah[ks][1], al[ks][1]);
+            ipm_split(r0[4 * kIpmBS], ah[ks][2], al[ks][2]);
+            ipm_split(r0[4 * kIpmBS + 8], ah[ks][3], al[ks][3]);
+        }
+        const float* wv = sW + (int)((b * (int64_t)P) & 3);
+#pragma unroll 5
+        for (int p = lane; p < P; p += 32) {
+            const uint32_t oo = sPair[p];
+            const float w = wv[p];
+            sG[oo & 0xffffu] = w;
+            sG[oo >> 16] = w;
+        }
+        __syncwarp();                                  // G is complete; the staging buffers are free: refill them
+        if (b + nw < B) prefetch(b + nw);
+        cp_async_commit_group();
+        float* db = dE + (size_t)b * F * 16;
+#pragma unroll
+        for (int nt = 0; nt < 5; ++nt) {
+            // B = G (symmetric): b0 = G[8 nt + g][8 ks + t], b1 = G[8 nt + g][8 ks + t + 4]
+            const float* gr = sG + (8 * nt + g) * kIpmGS + t;
+            float c[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int ks = 0; ks < 5; ++ks) {
+                uint32_t bh0, bl0, bh1, bl1;
+                ipm_split(gr[8 * ks], bh0, bl0);
+                ipm_split(gr[8 * ks + 4], bh1, bl1);
+                ipm_mma(c, al[ks][0], al[ks][1], al[ks][2], al[ks][3], bh0, bh1);
+                ipm_mma(c, ah[ks][0], ah[ks][1], ah[ks][2], ah[ks][3], bl0, bl1);
+                ipm_mma(c, ah[ks][0], ah[ks][1], ah[ks][2], ah[ks][3], bh0, bh1);
+            }
+            // C = dE^T: c0 = dE[8 nt + 2t][g], c1 = dE[8 nt + 2t + 1][g], c2 / c3 the same rows at column g + 8
+            const int r0 = 8 * nt + 2 * t;
+            if (r0 < F) {
+                __stcs(db + (size_t)r0 * 16 + g, c[0]);
+                __stcs(db + (size_t)r0 * 16 + g + 8, c[2]);
+            }
+            if (r0 + 1 < F) {
+                __stcs(db + (size_t)(r0 + 1) * 16 + g, c[1]);
+                __stcs(db + (size_t)(r0 + 1) * 16 + g + 8, c[3]);
+            }
+        }
+    }
+    cp_async_wait_all();
+}
+
 // mode 3 forward: out[b, p, :] = e_i * e_j.  LPR lanes per pair, 32/LPR pairs per step, 512-byte coalesced stores.
 template <int LPR>
 __global__ void __launch_bounds__(kThreads) k_ew_fwd_warp(const float* __restrict__ E, float* __restrict__ out, int64_t B, int F) {
@@ -778,6 +1003,14 @@ __global__ void __launch_bounds__(kThreads) k_power_sums_any(const float* __rest
     }
 }
 
+// mode 2 on the warp-level tensor-core path: D = 16 and 25 <= F <= 40 (the Criteo-shaped configs; smaller F leave most of
+// the padded 40 x 40 product empty and stay on the SIMT tiles).  RBX_IP_ENGINE=0 selects the SIMT kernels everywhere.
+inline bool ipm_covers(int F, int D) {
+    if (D != 16 || F < 25 || F > kIpmRows) return false;
+    const char* e = getenv("RBX_IP_ENGINE");
+    return !(e && *e == '0');
+}
+
 inline bool vec_ok(int D, const void* a, const void* b, const void* c) {
     return D % 4 == 0 && D <= 128 && (D & (D - 1)) == 0 && (uintptr_t)a % 16 == 0 && (uintptr_t)b % 16 == 0 &&
            (uintptr_t)c % 16 == 0;
@@ -818,6 +1051,12 @@ int rbx_interact_fwd(const float* E, float* out, int64_t B, int F, int D, int mo
         if (F < 2) return RBX_OK;
         RBX_REQUIRE(F < 32768, "%s: F too large", who);
         const size_t P = (size_t)F * (F - 1) / 2;
+        if (mode == 2 && ipm_covers(F, D) && (uintptr_t)E % 16 == 0) {       // warp-level 3xTF32 mma (RBX_IP_ENGINE=0: SIMT tiles)
+            const size_t msmem = ((size_t)kIpmTab + (size_t)kIpmFwdWarps * kIpmFwdSlice) * 4;
+            k_ip_fwd_mma<<<warp_grid(k_ip_fwd_mma, kIpmFwdWarps, msmem, B), kIpmFwdWarps * 32, msmem, st>>>(E, out, B, F);
+            RBX_LAUNCH_CHECK(who);
+            return RBX_OK;
+        }
         if (vec_ok(D, E, mode == 3 ? out : nullptr, nullptr) && F <= 255) {
             const int FB = (F + 3) / 4;
             size_t wsmem = 0;
@@ -866,6 +1105,12 @@ int rbx_interact_bwd(const float* E, const float* dout, float* dE, int64_t B, in
             return RBX_OK;
         }
         const size_t P = (size_t)F * (F - 1) / 2;
+        if (mode == 2 && ipm_covers(F, D) && (uintptr_t)E % 16 == 0 && (uintptr_t)dout % 16 == 0) {
+            const size_t msmem = ((size_t)kIpmTabB + (size_t)kIpmBwdWarps * kIpmBwdSlice) * 4;
+            k_ip_bwd_mma<<<warp_grid(k_ip_bwd_mma, kIpmBwdWarps, msmem, B), kIpmBwdWarps * 32, msmem, st>>>(E, dout, dE, B, F);
+            RBX_LAUNCH_CHECK(who);
+            return RBX_OK;
+        }
         if (vec_ok(D, E, dE, mode == 3 ? dout : nullptr) && F <= 255) {
             const int FB = (F + 3) / 4;
             size_t wsmem = 0;

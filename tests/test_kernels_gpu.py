@@ -257,6 +257,36 @@ def test_interact_random(mode, F, D):
     assert_close(dE, E.grad, atol_scale=2e-5, what=name + " bwd")
 
 
+@pytest.mark.parametrize("B", [1, 3, 67, 4099])
+@pytest.mark.parametrize("F", [25, 32, 33, 39, 40])
+def test_interact_inner_product_tensor_core_path(F, B, monkeypatch):
+    """mode 2 at D = 16, 25 <= F <= 40 runs as warp-level mma.sync in 3xTF32 (csrc/interact.cu, k_ip_fwd_mma / k_ip_bwd_mma):
+    fp32-level accuracy against the oracle (1e-5 contract) and against a float64 product (well inside it), every padded
+    row / column shape (F = 25 ... 40), batches that end inside a 16-byte chunk of the gradient stream (B * P % 4 != 0), and
+    agreement with the SIMT engine (RBX_IP_ENGINE=0)."""
+    ops = _ops()
+    g = torch.Generator().manual_seed(100 * F + B)
+    E = torch.randn(B, F, 16, generator=g, requires_grad=True)
+    ref = oracle.inner_product_interaction(E, "inner_product")
+    dout = torch.randn(ref.shape, generator=g)
+    (ref * dout).sum().backward()
+    Ed, dd = E.detach().to(DEV), dout.to(DEV).contiguous()
+    monkeypatch.setenv("RBX_IP_ENGINE", "1")
+    out = ops.interact_fwd(Ed, 2)
+    dE = ops.interact_bwd(Ed, dd, 2)
+    assert_close(out.reshape(ref.shape), ref, what="inner_product (mma)")
+    assert_close(dE, E.grad, atol_scale=2e-5, what="inner_product bwd (mma)")
+    iu = torch.triu_indices(F, F, 1)
+    E64 = E.detach().double()
+    want = torch.bmm(E64, E64.transpose(1, 2))[:, iu[0], iu[1]]
+    assert float((out.double().cpu() - want).abs().max()) <= 3e-6 * float(want.abs().max()), "3xTF32 keeps fp32-level accuracy"
+    monkeypatch.setenv("RBX_IP_ENGINE", "0")
+    out0 = ops.interact_fwd(Ed, 2)
+    dE0 = ops.interact_bwd(Ed, dd, 2)
+    assert_close(out, out0, what="mma vs SIMT engine")
+    assert_close(dE, dE0, atol_scale=2e-5, what="mma vs SIMT engine (bwd)")
+
+
 @pytest.mark.parametrize("mode", [2, 3])
 def test_interact_pairs_many_samples_per_warp(mode):
     """B far above the resident warp count: every warp of the warp-per-sample kernels reuses its shared-memory slice."""
