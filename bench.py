@@ -285,13 +285,14 @@ def main_reference(args, rank, world):
     print(json.dumps(line))
 
 
-def workload_config(ids_kind, world):
+def workload_config(ids_kind, world, saved_e=False):
     par = ("1 GPU" if world == 1 else
            "dp%d replicas of the 1M-row table, each on its own batch shard; the fused dense gradient buffer (68 MB) is "
            "all-reduced over NVLink / NVSwitch INSIDE the timed step (SURVEY 8e 'replicas only'; kernels.all_reduce.path says how)" % world)
+    e_src = "read from the forward's saved E" if saved_e else "re-read from the table, not from the forward's E stream"
     return {"workload": "BASELINE configs[1] DeepFM hot path: 26 cat + 13 dense, 26x38462 = 1000012-row fused table, "
-                        "D=16, B=65536 per GPU; fused gather+FM+LR fwd, dense-grad zero (side stream, under the fwd) + scatter-add bwd; "
-                        "MLP tail outside the path",
+                        "D=16, B=65536 per GPU; fused gather+FM+LR fwd, dense-grad zero (side stream, under the fwd) + scatter-add bwd "
+                        "(the FM term's e " + e_src + "); MLP tail outside the path",
             "global_batch": CFG["B"] * world, "ids": ids_kind, "batches_rotated": 4,
             "l2": "working set per step (E 163 MB + dE 163 MB + table/grad 136 MB) exceeds the 126 MB L2; 4 id batches rotate",
             "parallelism": par}
@@ -677,7 +678,7 @@ def main_b200(args, rank, world, local_rank):
             "metric": "samples/sec on Criteo-shaped synthetic (embedding + FM hot path, fwd+bwd)",
             "value": B * world * K / (ms_total * 1e-3), "unit": "samples/s", "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic", "config": workload_config(args.ids, world),
+            "dtype": "f32", "data": "synthetic", "config": workload_config(args.ids, world, args.bwd_saved_e),
             "e2e": None if args.no_e2e else e2e_obj("packed", "layer API (FeatureEmbedding + FactorizationMachine modules, autograd) fed by "
                     "recbox_b200.loader.PackedDataset blocks: uint16 ids + fp32 dense + fp32 label (108 B/sample), pinned"),
             "e2e_f64": None if args.no_e2e else e2e_obj("f64", "layer API fed by the reference loader's float64 [B,40] batch matrix "
