@@ -5,7 +5,7 @@ Layout:
   _lib.py      in-tree build + ctypes loader (no fallback: missing library = exception)
   ops.py       one-call-per-op tensor wrappers over the C ABI
   layers.py    the reference's nn.Module operator API on top (same names / ctor args / state_dict keys)
-  features.py  FeatureMap schema objects (same surface / feature_map.json as the reference's)
+  features.py  small FeatureMap schema holders for tests / bench (the layers accept the reference's own FeatureMap unchanged)
   sharded.py   row-sharded table across the GPUs of one box (NCCL all-to-all or NVLink peer access)
   optim.py     exact-dense clip + Adam on the fused tables, and the touched-rows variant
   loader.py    packed input pipeline (ids / dense converted once to pinned int32 / fp32 blocks), epoch negative sampler

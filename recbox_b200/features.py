@@ -3,12 +3,10 @@
 The layers accept the reference's own `recbox.ranking.features.FeatureMap`
 (ranking/features.py:25-125) and the matching side's feature-spec holder
 (matching/features.py:12-58) unchanged -- they only touch `.features` / `.feature_specs`,
-`.num_fields`, `.labels`, `.data_dir`, `.get_column_index()`.  These two small classes provide the
-same surface (and read / write the same feature_map.json) for use without the reference package:
-tests, bench.py and stand-alone deployments.
+`.num_fields`, `.labels`, `.data_dir`, `.get_column_index()`.  These two small holders provide that
+surface for use without the reference package (tests, bench.py, tools): builders for a schema plus the
+column layout of the batch matrix.  feature_map.json I/O is the reference's (out of scope).
 """
-import json
-import os
 from collections import OrderedDict
 
 
@@ -57,44 +55,8 @@ class FeatureMap(object):
         self.set_column_index()
         return self
 
-    # -- the reference's surface
-    def load(self, json_file, params=None):
-        params = params or {}
-        with open(json_file, "r", encoding="utf-8") as fd:
-            fm = json.load(fd)
-        if fm["dataset_id"] != self.dataset_id:
-            raise RuntimeError("dataset_id={} does not match feature_map!".format(self.dataset_id))
-        self.num_fields = fm["num_fields"]
-        self.labels = fm.get("labels", [])
-        self.total_features = fm.get("total_features", 0)
-        self.input_length = fm.get("input_length", 0)
-        self.group_id = fm.get("group_id", None)
-        self.default_emb_dim = params.get("embedding_dim", None)
-        self.features = OrderedDict((k, v) for x in fm["features"] for k, v in x.items())
-        if params.get("use_features", None):
-            self.features = OrderedDict((x, self.features[x]) for x in params["use_features"])
-        for col in params.get("feature_specs", None) or []:
-            names = col["name"] if isinstance(col["name"], list) else [col["name"]]
-            for name in names:
-                for k, v in col.items():
-                    if k != "name":
-                        self.features[name][k] = v
-        self.set_column_index()
-
-    def save(self, json_file):
-        os.makedirs(os.path.dirname(json_file) or ".", exist_ok=True)
-        fm = OrderedDict()
-        fm["dataset_id"] = self.dataset_id
-        fm["num_fields"] = self.num_fields
-        fm["total_features"] = self.total_features
-        fm["input_length"] = self.input_length
-        fm["labels"] = self.labels
-        if self.group_id is not None:
-            fm["group_id"] = self.group_id
-        fm["features"] = [{k: v} for k, v in self.features.items()]
-        with open(json_file, "w") as fd:
-            json.dump(fm, fd, indent=4)
-
+    # -- what the layers and the batch packers read (ranking/features.py:92-125); reading / writing feature_map.json stays
+    #    with the reference's own FeatureMap, which the layers accept unchanged
     def get_num_fields(self, feature_source=[]):
         if type(feature_source) != list:
             feature_source = [feature_source]
