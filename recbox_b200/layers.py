@@ -275,6 +275,8 @@ class _ShardedStore(_FusedStore):
             dev = ref.device
             if ref.dtype != F32:
                 raise RbxError("sharded tables are fp32")
+            if dev.type != "cuda" and cfg.kern is None:
+                raise RbxError("recbox_b200 layers have no CPU path: move the model to a CUDA device (that is where the tables are cut)")
             D = g.D
             Dp = D if D in _SHARD_DIMS else (4 if D < 4 else None)
             if Dp is None:

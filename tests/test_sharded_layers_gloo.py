@@ -162,6 +162,12 @@ def test_sharded_dictionary_rejects_what_it_does_not_cover(monkeypatch):
     with pytest.raises(RbxError):
         layers.shard_now(emb)
     pb = Problem(8, "cc", 8, vocab=[5, 4], seed=1)
+    with layers.sharded_tables():                                # the product configuration has no CPU path
+        emb = layers.FeatureEmbedding(_fmap(pb), 8)
+    with pytest.raises(RbxError):
+        layers.shard_now(emb)
+    with pytest.raises(RbxError):
+        emb({"C0": torch.zeros(2), "C1": torch.zeros(2)})
     with layers.sharded_tables(mode="a2a", kern=CpuKern):
         emb = layers.FeatureEmbedding(_fmap(pb), 8)
     layers.shard_now(emb)
