@@ -119,7 +119,11 @@ def test_hundred_million_row_table(Dl):
     free = torch.cuda.mem_get_info()[0]
     if free < need:
         pytest.skip("needs %.0f GB of free HBM, %.0f GB available" % (need / 2 ** 30, free / 2 ** 30))
-    table = torch.empty((R, Dl), dtype=torch.float32, device=DEV)
+    try:
+        table = torch.empty((R, Dl), dtype=torch.float32, device=DEV)
+        gt = torch.zeros_like(table)
+    except torch.cuda.OutOfMemoryError:                       # a shared or fragmented device: an environment limit, not a parity result
+        pytest.skip("could not allocate the %.0f GB table and gradient table" % (2 * R * Dl * 4 / 2 ** 30))
     torch.manual_seed(11)
     step = 10_000_000
     for lo in range(0, R, step):                              # filled in slabs: no 51 GB temporary
@@ -145,7 +149,6 @@ def test_hundred_million_row_table(Dl):
     g = torch.Generator().manual_seed(12)
     dE = torch.randn(Bl, Fl, Dl, generator=g).to(DEV)
     d_fm = torch.randn(Bl, generator=g).to(DEV)
-    gt = torch.zeros_like(table)
     ops.embed_fm_bwd(table, rows, cat_pos, pad_row, None, None, [], E, S, dE, d_fm, None, gt, None, None, None, None, Dl, R)
     # reference on the touched rows only: index_add_ over the compacted (unique) row set, float64
     pads = torch.tensor(pad_row, device=DEV)
