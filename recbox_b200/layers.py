@@ -386,6 +386,36 @@ def clip_grad_norm_(parameters, max_norm, group=None):
     return total
 
 
+def train_step(model, batch_data, group=None):
+    """RankingModel.train_step (ranking_model.py:191-197: zero_grad, total loss, backward, clip_grad_norm_, optimizer step) for
+    ONE model trained by several ranks -- row-sharded tables (sharded_tables) and / or replicas: every rank passes its equal-sized
+    slice of the global batch; the slice's mean loss is scaled by 1 / world so that the table gradients (reduced into their
+    owners' shards by the backward) and the all-reduced replicated gradients are those of the GLOBAL batch mean, the clip uses
+    the global norm, and every rank takes the same optimizer step.  Returns the global mean loss.  Bind it over the reference's
+    method (`model.train_step = functools.partial(layers.train_step, model)`) to keep `fit()` / `train_epoch()` unchanged.
+    With one rank it is the reference's step.  Regularisers are not covered (their sharded / replicated parts scale differently)."""
+    import torch.distributed as dist
+    world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
+    if world > 1 and (getattr(model, "_embedding_regularizer", None) or getattr(model, "_net_regularizer", None)):
+        raise NotImplementedError("layers.train_step: embedding / net regularizers are not covered at world > 1")
+    model.optimizer.zero_grad()
+    loss = model.get_total_loss(batch_data)
+    (loss / world if world > 1 else loss).backward()
+    params = list(model.parameters())
+    if world > 1:
+        sync_replica_gradients(params, group=group)
+    if any(is_sharded(p) for p in params):
+        clip_grad_norm_(params, model._max_gradient_norm, group=group)
+    else:
+        nn.utils.clip_grad_norm_(params, model._max_gradient_norm)
+    model.optimizer.step()
+    if world > 1:
+        loss = loss.detach().clone()
+        dist.all_reduce(loss, group=group)
+        loss = loss / world
+    return loss
+
+
 # =================================================================================================
 # the autograd node around the two fused kernels
 # =================================================================================================

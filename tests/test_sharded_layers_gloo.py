@@ -203,3 +203,99 @@ def test_sharded_layers_world2_gloo(tmp_path):
     world = 2
     mp.spawn(_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
     assert all(os.path.exists(os.path.join(str(tmp_path), "ok%d" % r)) for r in range(world))
+
+
+def _ref_trainer_worker(rank, world, port, out_dir):
+    """layers.train_step on a RankingModel subclass (the reference's base class) whose tables are sharded over `world` ranks
+    against the ALL-reference model trained by its own train_step on the whole batch."""
+    import tempfile
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    if world > 1:
+        dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import recbox_b200
+        from oracle import ref_shim
+        from test_oracle_golden import ranking_features
+        L = ref_shim.install()
+        from recbox.ranking.features import FeatureMap as RefFeatureMap
+        from recbox.ranking.pytorch.models.ranking_model import RankingModel
+        layers._FusedDictBase._pack = _cpu_pack
+        tmp = tempfile.mkdtemp()
+        fm = RefFeatureMap("golden", tmp)
+        for k, v in ranking_features("ranking_layers_d8").items():
+            fm.features[k] = dict(v)
+        fm.labels = ["label"]
+        fm.num_fields = fm.get_num_fields()
+        fm.set_column_index()
+        fm.default_emb_dim = 8
+
+        def make(LL):
+            class FM(RankingModel):                       # FuxiCTR-style FM body against whatever layer set LL is
+                def __init__(self, feature_map, **kw):
+                    super(FM, self).__init__(feature_map, **kw)
+                    self.embedding_layer = LL.FeatureEmbedding(feature_map, 8)
+                    self.fm_layer = LL.FactorizationMachine(feature_map)
+                    self.compile("adam", "binary_cross_entropy", 1e-3)
+                    self.reset_parameters()
+                    self.model_to_device()
+
+                def forward(self, inputs):
+                    X = self.get_inputs(inputs)
+                    y = self.fm_layer(X, self.embedding_layer(X))
+                    return {"y_pred": self.output_activation(y)}
+            m = FM(fm, model_id="m", gpu=-1, verbose=0, model_root=tmp, metrics=["AUC"])
+            m._max_gradient_norm = 10.
+            return m
+
+        torch.manual_seed(5)
+        ref = make(L)                                     # the reference's own layers
+        g = torch.Generator().manual_seed(6)
+        with torch.no_grad():                             # O(0.1) weights so gradients and Adam moments are not ~1e-8
+            for k, p in ref.named_parameters():
+                p.copy_(torch.randn(p.shape, generator=g) * 0.1)
+            for mod in ref.modules():
+                if isinstance(mod, torch.nn.Embedding) and mod.padding_idx is not None:
+                    mod.weight[mod.padding_idx] = 0
+        init = {k: v.clone() for k, v in ref.state_dict().items()}
+        try:
+            recbox_b200.install()
+            with layers.sharded_tables(mode="a2a", kern=CpuKern):
+                ours = make(L)                            # same class body, rebound layer set, tables to be sharded
+        finally:
+            recbox_b200.uninstall()
+        ours.load_state_dict(init)
+        layers.shard_now(ours)
+        B = 64
+        gb = torch.Generator().manual_seed(7)
+        for step in range(3):
+            cols = [torch.rand(B, generator=gb, dtype=torch.float64) if s["type"] == "numeric"
+                    else torch.randint(0, s["vocab_size"], (B,), generator=gb).double() for s in fm.features.values()]
+            batch = torch.stack(cols + [(torch.rand(B, generator=gb) < 0.5).double()], 1)
+            ref.train()
+            want = float(ref.train_step(batch))
+            ours.train()
+            sl = slice(rank * (B // world), (rank + 1) * (B // world))
+            got = float(layers.train_step(ours, batch[sl]))
+            assert abs(got - want) <= 2e-6 * abs(want), (step, got, want)
+        final = layers.gather_state_dict(ours)
+        for k, v in ref.state_dict().items():
+            assert_close(final[k], v, rtol=1e-4, atol_scale=2e-5, what="final." + k)
+        open(os.path.join(out_dir, "ok%d" % rank), "w").write("ok")
+    finally:
+        if world > 1:
+            dist.destroy_process_group()
+
+
+@pytest.mark.reference
+@pytest.mark.parametrize("world", [1, 2])
+def test_reference_trainer_step_on_sharded_tables(world, tmp_path):
+    if world == 1:
+        import multiprocessing
+        ctx = multiprocessing.get_context("spawn")           # own process: the worker patches layers and installs the shim
+        p = ctx.Process(target=_ref_trainer_worker, args=(0, 1, 0, str(tmp_path)))
+        p.start()
+        p.join()
+        assert p.exitcode == 0
+    else:
+        mp.spawn(_ref_trainer_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    assert all(os.path.exists(os.path.join(str(tmp_path), "ok%d" % r)) for r in range(world))
