@@ -33,11 +33,11 @@ def _fmap(pb):
     return fm
 
 
-def _build(pb):
+def _build(pb, mode="a2a"):
     """FeatureEmbedding + FactorizationMachine of the reference's DeepFM front, built under the switch, loaded with the
     problem's FULL per-feature weights under the reference's names (as load_state_dict of a reference checkpoint does)."""
     fm = _fmap(pb)
-    with layers.sharded_tables(mode="a2a", kern=CpuKern):
+    with layers.sharded_tables(mode=mode, kern=CpuKern, max_ids=pb.B * pb.F, slack=3.0):
         emb = layers.FeatureEmbedding(fm, pb.D)
         fml = layers.FactorizationMachine(fm)
     sd = OrderedDict(("embedding_layer.embedding_layers.%s.weight" % n, pb.W[n].clone()) for n in pb.features)
@@ -49,14 +49,14 @@ def _build(pb):
     return fm, emb, fml, sd, sd1
 
 
-def _run(pb, rank, world, monkey_target):
+def _run(pb, rank, world, mode="a2a"):
     B = pb.B // world
     sl = slice(rank * B, (rank + 1) * B)
     g = torch.Generator().manual_seed(4)
     Ft = pb.F + pb.Fn
     dE = torch.randn(pb.B, Ft, pb.D, generator=g)
     d_y = torch.randn(pb.B, generator=g)
-    fm, emb, fml, sd, sd1 = _build(pb)
+    fm, emb, fml, sd, sd1 = _build(pb, mode)
     assert not emb.embedding_layer._store.sharded                   # still the full tables on the host
     layers.shard_now(emb)
     layers.shard_now(fml)
@@ -139,7 +139,7 @@ def _run(pb, rank, world, monkey_target):
 def test_sharded_layers_world1_host(monkeypatch):
     monkeypatch.setattr(layers._FusedDictBase, "_pack", _cpu_pack)
     pb = Problem(40, "nccncc", 8, vocab=[11, 7, 13, 5], seed=3)
-    _run(pb, 0, 1, None)
+    _run(pb, 0, 1)
 
 
 def test_switch_is_scoped_and_env_driven(monkeypatch):
@@ -187,21 +187,24 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, out_dir):
+def _worker(rank, world, port, out_dir, mode):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         layers._FusedDictBase._pack = _cpu_pack
         pb = Problem(24 * world, "nccncc", 8, vocab=[11, 7, 13, 5], seed=3)
-        _run(pb, rank, world, None)
+        _run(pb, rank, world, mode)
         open(os.path.join(out_dir, "ok%d" % rank), "w").write("ok")
     finally:
         dist.destroy_process_group()
 
 
-def test_sharded_layers_world2_gloo(tmp_path):
+@pytest.mark.parametrize("mode", ["a2a", "stream"])
+def test_sharded_layers_world2_gloo(mode, tmp_path):
+    """The layer protocol over the NCCL-style exchange ("a2a") and over the streamed exchange ("stream": peer-visible
+    workspaces, flag barriers, parity-double-buffered inboxes -- file-backed stand-ins here)."""
     world = 2
-    mp.spawn(_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, _free_port(), str(tmp_path), mode), nprocs=world, join=True)
     assert all(os.path.exists(os.path.join(str(tmp_path), "ok%d" % r)) for r in range(world))
 
 
